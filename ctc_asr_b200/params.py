@@ -1,0 +1,133 @@
+"""Hyper-parameters of the hot path, with the reference's flag names and defaults.
+
+Mirrors the subset of `tf.flags` definitions the hot path reads (asr/params.py:31-50, 66-100,
+106, 128, 138-148); `asr/model.py` reads them as `FLAGS.<name>` inside `inference_fn`
+(asr/model.py:149,167-172,200-207,220,224-225,232).  Here they are one frozen dataclass that is
+handed to `CTCModel`; `FLAGS` below is the module-level default instance so reference-style code
+(`from ctc_asr_b200.params import FLAGS`) keeps reading the same attribute names.
+"""
+import dataclasses
+from dataclasses import dataclass
+
+from . import labels as _labels
+
+NP_FLOAT = "float32"        # asr/params.py:137-139  (TF_FLOAT = tf.float32)
+NUM_FEATURES = 80           # asr/params.py:148
+WIN_LENGTH = 0.025          # asr/params.py:146
+WIN_STEP = 0.010            # asr/params.py:147
+MIN_EXAMPLE_LENGTH = 0.7    # asr/params.py:142
+MAX_EXAMPLE_LENGTH = 17.0   # asr/params.py:143
+
+RNN_CELLS = ("rnn_relu", "rnn_tanh", "lstm", "gru")     # asr/model.py:194-199
+NUM_GATES = {"rnn_relu": 1, "rnn_tanh": 1, "lstm": 4, "gru": 3}
+CELL_ID = {"rnn_tanh": 0, "rnn_relu": 1, "lstm": 2, "gru": 3}   # ctcasr.h CTCASR_CELL_*
+
+
+@dataclass(frozen=True)
+class ModelConfig:
+    # --- names and defaults of asr/params.py -------------------------------------------------
+    used_model: str = "ds1"             # reference default 'ds2' (conv front-end) is a "next" row
+    num_units_dense: int = 2048         # :35
+    relu_cutoff: float = 20.0           # :37
+    num_layers_rnn: int = 4             # :43
+    num_units_rnn: int = 2048           # :45
+    rnn_cell: str = "rnn_relu"          # :48
+    batch_size: int = 16                # :53
+    learning_rate: float = 1e-5         # :66
+    adam_beta1: float = 0.9             # :77
+    adam_beta2: float = 0.999           # :79
+    adam_epsilon: float = 1e-8          # :81
+    beam_width: int = 1024              # :85
+    rnn_dropout_rate: float = 0.0       # :91
+    dense_dropout_rate: float = 0.1     # :93
+    num_buckets: int = 96               # :97
+    num_classes: int = _labels.num_classes()    # :100  (29, blank = 28)
+    cudnn: bool = True                  # :106  True: RNN ignores seq_length (cuDNN path semantics)
+    random_seed: int = 0                # :128
+    # --- knobs the reference hard-codes ------------------------------------------------------
+    num_layers_dense: int = 3           # asr/util/tf_contrib.py:35 (num_layers=3)
+    num_features: int = NUM_FEATURES
+    lstm_forget_bias: float = 1.0       # tf.nn.rnn_cell.LSTMCell default
+    # --- B200 execution choices (not in the reference) ---------------------------------------
+    # 'fp32': SIMT FFMA kernels everywhere (exact-order fp32, parity mode)
+    # 'tf32': tcgen05 kind::tf32 on fp32-stored operands (fp32 accumulate)
+    compute: str = "tf32"
+
+    def __post_init__(self):
+        if self.used_model != "ds1":
+            raise ValueError('Unsupported model "{}" in flags.'.format(self.used_model))  # asr/model.py:163
+        if self.rnn_cell not in RNN_CELLS:
+            raise ValueError("rnn_cell must be one of {}".format(RNN_CELLS))
+        if self.compute not in ("fp32", "tf32"):
+            raise ValueError("compute must be 'fp32' or 'tf32'")
+
+    def replace(self, **kw):
+        return dataclasses.replace(self, **kw)
+
+    @property
+    def num_gates(self):
+        return NUM_GATES[self.rnn_cell]
+
+    @property
+    def blank(self):
+        return self.num_classes - 1     # asr/labels.py:6 — TF ctc_loss: blank = num_classes - 1
+
+
+FLAGS = ModelConfig()
+
+
+def param_specs(cfg: ModelConfig):
+    """Ordered (name, shape, init) of every trainable tensor in the flat parameter buffer.
+
+    Names follow the reference's variable scopes ('dense', 'rnn', 'dense4', 'logits';
+    asr/util/tf_contrib.py:50, asr/model.py:166,219,231).  RNN layer l holds
+      rnn/l{l}/wx   [in_l, 2*G*H]   input kernels of the fw | bw cell side by side
+      rnn/l{l}/wh   [2, H, G*H]     recurrent kernels fw, bw
+      rnn/l{l}/bias [2*G*H]
+    i.e. TF's fused cell kernel [in+H, G*H] of direction d is vstack(wx[:, d*GH:(d+1)*GH], wh[d]).
+    init: 'truncnorm' = truncated_normal(stddev=0.046875) (asr/model.py:146), 'glorot' = Glorot
+    uniform over the fused [in+H, G*H] matrix (rnn_cell default / asr/model.py:209), 'zeros'.
+    """
+    specs = []
+    D, H, G, V = cfg.num_units_dense, cfg.num_units_rnn, cfg.num_gates, cfg.num_classes
+    nin = cfg.num_features
+    for i in range(cfg.num_layers_dense):
+        scope = "dense/dense" if i == 0 else "dense/dense_%d" % i
+        specs.append((scope + "/kernel", (nin, D), "truncnorm"))
+        specs.append((scope + "/bias", (D,), "zeros"))
+        nin = D
+    for l in range(cfg.num_layers_rnn):
+        specs.append(("rnn/l%d/wx" % l, (nin, 2 * G * H), ("glorot", nin + H, G * H)))
+        specs.append(("rnn/l%d/wh" % l, (2, H, G * H), ("glorot", nin + H, G * H)))
+        specs.append(("rnn/l%d/bias" % l, (2 * G * H,), "zeros"))
+        nin = 2 * H
+    specs.append(("dense4/dense/kernel", (nin, D), "truncnorm"))
+    specs.append(("dense4/dense/bias", (D,), "zeros"))
+    specs.append(("logits/dense/kernel", (D, V), "truncnorm"))
+    specs.append(("logits/dense/bias", (V,), "zeros"))
+    return specs
+
+
+def param_offsets(cfg: ModelConfig, align=64):
+    """name -> (offset, shape) in elements inside the flat buffer; every tensor starts on an
+    `align`-element (256 B) boundary so TMA descriptors and float4 accesses are always legal."""
+    out, off = {}, 0
+    for name, shape, _ in param_specs(cfg):
+        n = 1
+        for s in shape:
+            n *= s
+        out[name] = (off, shape)
+        off += (n + align - 1) // align * align
+    return out, off
+
+
+def flops_per_frame_fwd(cfg: ModelConfig):
+    """GEMM FLOPs per input frame, forward (2 FLOP/MAC) — the figure of BASELINE.md §4."""
+    F, D, H, G, V = cfg.num_features, cfg.num_units_dense, cfg.num_units_rnn, cfg.num_gates, cfg.num_classes
+    f = 2 * F * D + (cfg.num_layers_dense - 1) * 2 * D * D
+    nin = D
+    for _ in range(cfg.num_layers_rnn):
+        f += 2 * 2 * (nin + H) * G * H
+        nin = 2 * H
+    f += 2 * nin * D + 2 * D * V
+    return f

@@ -1,0 +1,90 @@
+"""Whole-path oracle: the reference's inference_fn + loss_fn + backward, composed from oracle/ref.py.
+
+TEST INFRASTRUCTURE ONLY ("parity unpinned", see oracle/oracle_impl.h).  Follows
+asr/model.py:123-269: dense stack (asr/util/tf_contrib.py:50-61) -> stacked bidirectional RNN
+(asr/model.py:169-216) -> dense4 (asr/model.py:219-226) -> logits, transposed to time-major
+(asr/model.py:231-235) -> tf.nn.ctc_loss + reduce_mean (asr/model.py:259-267).
+
+`cfg` is any object with the attribute names of ctc_asr_b200.params.ModelConfig; `params` is a
+dict name -> numpy array with the names/shapes of ctc_asr_b200.params.param_specs.
+"""
+import numpy as np
+
+from . import ref
+
+_CELL = {"rnn_tanh": 0, "rnn_relu": 1, "lstm": 2, "gru": 3}
+
+
+def _dense_names(cfg):
+    return ["dense/dense" if i == 0 else "dense/dense_%d" % i for i in range(cfg.num_layers_dense)]
+
+
+def forward(cfg, params, sequences, seq_length, training=False, seed=0, dtype=np.float64):
+    """sequences [B,T,F] batch-major (asr/model.py:129) -> logits [T,B,V] time-major + cache."""
+    x = np.ascontiguousarray(np.transpose(np.asarray(sequences, dtype), (1, 0, 2)))   # [T,B,F]
+    T, B, _ = x.shape
+    seq_length = np.asarray(seq_length, np.int32)
+    rate = cfg.dense_dropout_rate if training else 0.0
+    cache = {"acts": [], "rnn": []}
+    h = x.reshape(T * B, -1)
+    for li, name in enumerate(_dense_names(cfg)):
+        w, b = params[name + "/kernel"].astype(dtype), params[name + "/bias"].astype(dtype)
+        y = ref.dense_fwd(h, w, b, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + li)
+        cache["acts"].append((h, y))
+        h = y
+    cell = _CELL[cfg.rnn_cell]
+    use_len = not cfg.cudnn
+    for l in range(cfg.num_layers_rnn):
+        wx, wh, bias = (params["rnn/l%d/%s" % (l, k)].astype(dtype) for k in ("wx", "wh", "bias"))
+        xin = h.reshape(T, B, -1)
+        y, gates, cst = ref.birnn_fwd(xin, seq_length, wx, wh, bias, cell, use_len=use_len,
+                                      forget_bias=cfg.lstm_forget_bias)
+        cache["rnn"].append((xin, y, gates, cst))
+        h = y.reshape(T * B, -1)
+    w, b = params["dense4/dense/kernel"].astype(dtype), params["dense4/dense/bias"].astype(dtype)
+    y4 = ref.dense_fwd(h, w, b, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + 100)
+    cache["d4"] = (h, y4)
+    w, b = params["logits/dense/kernel"].astype(dtype), params["logits/dense/bias"].astype(dtype)
+    logits = ref.dense_fwd(y4, w, b, act=0)
+    cache["lg"] = (y4,)
+    cache["meta"] = (T, B, rate, seed)
+    return logits.reshape(T, B, -1), cache
+
+
+def loss_and_grads(cfg, params, sequences, seq_length, labels, label_len, training=False, seed=0,
+                   dtype=np.float64):
+    """Mean CTC loss (asr/model.py:267) and d loss / d params (what AdamOptimizer.minimize
+    differentiates, asr/model.py:83).  Returns (loss, grads dict, logits, dlogits)."""
+    logits, cache = forward(cfg, params, sequences, seq_length, training, seed, dtype)
+    T, B, rate, seed = cache["meta"]
+    seq_length = np.asarray(seq_length, np.int32)
+    loss_b, g, status = ref.ctc_loss(logits, labels, label_len, seq_length, blank=cfg.num_classes - 1)
+    assert (status == 0).all(), status
+    loss = loss_b.mean()
+    dlogits = g / B
+    grads = {}
+    dy = dlogits.reshape(T * B, -1)
+    (y4,) = cache["lg"]
+    w = params["logits/dense/kernel"].astype(dtype)
+    dy, grads["logits/dense/kernel"], grads["logits/dense/bias"] = ref.dense_bwd(
+        y4, w, y4[:, :1], dy, act=0)
+    h, y4 = cache["d4"]
+    w = params["dense4/dense/kernel"].astype(dtype)
+    dy, grads["dense4/dense/kernel"], grads["dense4/dense/bias"] = ref.dense_bwd(
+        h, w, y4, dy, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + 100)
+    cell = _CELL[cfg.rnn_cell]
+    use_len = not cfg.cudnn
+    for l in reversed(range(cfg.num_layers_rnn)):
+        xin, y, gates, cst = cache["rnn"][l]
+        wx, wh = (params["rnn/l%d/%s" % (l, k)].astype(dtype) for k in ("wx", "wh"))
+        dx, dwx, dwh, db = ref.birnn_bwd(xin, seq_length, wx, wh, y, gates, cst,
+                                         dy.reshape(T, B, -1), cell, use_len=use_len)
+        grads["rnn/l%d/wx" % l], grads["rnn/l%d/wh" % l], grads["rnn/l%d/bias" % l] = dwx, dwh, db
+        dy = dx.reshape(T * B, -1)
+    names = _dense_names(cfg)
+    for li in reversed(range(len(names))):
+        h, y = cache["acts"][li]
+        w = params[names[li] + "/kernel"].astype(dtype)
+        dy, grads[names[li] + "/kernel"], grads[names[li] + "/bias"] = ref.dense_bwd(
+            h, w, y, dy, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + li, want_dx=li > 0)
+    return loss, grads, logits, dlogits

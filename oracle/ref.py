@@ -1,0 +1,161 @@
+"""ctypes/numpy front-end of the CPU oracle (oracle/oracle.c) — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package (ctc_asr_b200) never does.  "parity unpinned": see
+oracle/oracle_impl.h.
+
+Every wrapper takes/returns numpy arrays; dtype float32 -> *_f32 symbols, float64 -> *_f64.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    """Compile oracle.c with the committed Makefile (gcc only, seconds)."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+            for f in ("oracle.c", "oracle_impl.h", "Makefile")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _suf(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "_f32", ctypes.c_float
+    if dtype == np.float64:
+        return "_f64", ctypes.c_double
+    raise TypeError(dtype)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+NUM_GATES = {0: 1, 1: 1, 2: 4, 3: 3}
+CELL_IDS = {"rnn_tanh": 0, "rnn_relu": 1, "lstm": 2, "gru": 3}
+
+
+def ctc_loss(logits, labels, label_len, seq_len, blank=None, want_grad=True):
+    """logits [T,B,V]; labels [B,Lmax] int32 -> (loss[B], grad[T,B,V] or None, status[B])."""
+    dtype = logits.dtype
+    suf, _ = _suf(dtype)
+    logits = _c(logits, dtype)
+    T, B, V = logits.shape
+    blank = V - 1 if blank is None else blank
+    labels = _c(labels, np.int32).reshape(B, -1)
+    label_len = _c(label_len, np.int32)
+    seq_len = _c(seq_len, np.int32)
+    loss = np.zeros(B, dtype)
+    grad = np.zeros((T, B, V), dtype) if want_grad else None
+    status = np.zeros(B, np.int32)
+    getattr(lib(), "oracle_ctc_loss" + suf)(
+        _p(logits), T, B, V, blank, _p(labels), labels.shape[1], _p(label_len), _p(seq_len),
+        _p(loss), _p(grad), _p(status))
+    return loss, grad, status
+
+
+def greedy_decode(logits, seq_len, blank=None):
+    dtype = logits.dtype
+    suf, _ = _suf(dtype)
+    logits = _c(logits, dtype)
+    T, B, V = logits.shape
+    blank = V - 1 if blank is None else blank
+    ids = np.zeros((B, T), np.int32)
+    n = np.zeros(B, np.int32)
+    getattr(lib(), "oracle_greedy_decode" + suf)(_p(logits), T, B, V, blank,
+                                                 _p(_c(seq_len, np.int32)), _p(ids), _p(n))
+    return ids, n
+
+
+def dense_fwd(x, w, b, act=1, cutoff=20.0, drop_rate=0.0, seed=0):
+    dtype = x.dtype
+    suf, cr = _suf(dtype)
+    x, w = _c(x, dtype), _c(w, dtype)
+    b = _c(b, dtype) if b is not None else None
+    M, K = x.shape
+    N = w.shape[1]
+    y = np.zeros((M, N), dtype)
+    getattr(lib(), "oracle_dense_fwd" + suf)(_p(x), _p(w), _p(b), _p(y), M, K, N, act, cr(cutoff),
+                                             ctypes.c_float(drop_rate), ctypes.c_uint32(seed))
+    return y
+
+
+def dense_bwd(x, w, y, dy, act=1, cutoff=20.0, drop_rate=0.0, seed=0, want_dx=True):
+    dtype = x.dtype
+    suf, cr = _suf(dtype)
+    x, w, y, dy = (_c(a, dtype) for a in (x, w, y, dy))
+    M, K = x.shape
+    N = w.shape[1]
+    dx = np.zeros((M, K), dtype) if want_dx else None
+    dw = np.zeros((K, N), dtype)
+    db = np.zeros(N, dtype)
+    getattr(lib(), "oracle_dense_bwd" + suf)(_p(x), _p(w), _p(y), _p(dy), _p(dx), _p(dw), _p(db),
+                                             M, K, N, act, cr(cutoff), ctypes.c_float(drop_rate),
+                                             ctypes.c_uint32(seed))
+    return dx, dw, db
+
+
+def birnn_fwd(x, seq_len, wx, wh, bias, cell, use_len=True, forget_bias=1.0):
+    """x [T,B,in]; wx [in,2GH]; wh [2,H,GH]; bias [2GH] -> y [T,B,2H], gates [2,T,B,GH], c [2,T,B,H]."""
+    dtype = x.dtype
+    suf, cr = _suf(dtype)
+    x, wx, wh, bias = (_c(a, dtype) for a in (x, wx, wh, bias))
+    T, B, nin = x.shape
+    H = wh.shape[1]
+    G = NUM_GATES[cell]
+    assert wx.shape == (nin, 2 * G * H) and wh.shape == (2, H, G * H) and bias.shape == (2 * G * H,)
+    y = np.zeros((T, B, 2 * H), dtype)
+    gates = np.zeros((2, T, B, G * H), dtype)
+    cst = np.zeros((2, T, B, H), dtype)
+    rc = getattr(lib(), "oracle_birnn_fwd" + suf)(
+        _p(x), _p(_c(seq_len, np.int32)), _p(wx), _p(wh), _p(bias), _p(y), _p(gates), _p(cst),
+        T, B, nin, H, cell, int(use_len), cr(forget_bias))
+    assert rc == 0
+    return y, gates, cst
+
+
+def birnn_bwd(x, seq_len, wx, wh, y, gates, cst, dy, cell, use_len=True, want_dx=True):
+    dtype = x.dtype
+    suf, _ = _suf(dtype)
+    x, wx, wh, y, gates, cst, dy = (_c(a, dtype) for a in (x, wx, wh, y, gates, cst, dy))
+    T, B, nin = x.shape
+    H = wh.shape[1]
+    G = NUM_GATES[cell]
+    dx = np.zeros((T, B, nin), dtype) if want_dx else None
+    dwx = np.zeros((nin, 2 * G * H), dtype)
+    dwh = np.zeros((2, H, G * H), dtype)
+    db = np.zeros(2 * G * H, dtype)
+    rc = getattr(lib(), "oracle_birnn_bwd" + suf)(
+        _p(x), _p(_c(seq_len, np.int32)), _p(wx), _p(wh), _p(y), _p(gates), _p(cst), _p(dy),
+        _p(dx), _p(dwx), _p(dwh), _p(db), T, B, nin, H, cell, int(use_len))
+    assert rc == 0
+    return dx, dwx, dwh, db
+
+
+def adam(p, m, v, g, step, lr=1e-5, b1=0.9, b2=0.999, eps=1e-8):
+    """In-place TF1 Adam on flat arrays."""
+    dtype = p.dtype
+    suf, cr = _suf(dtype)
+    assert all(a.flags.c_contiguous and a.dtype == dtype for a in (p, m, v, g))
+    getattr(lib(), "oracle_adam" + suf)(_p(p), _p(m), _p(v), _p(g), ctypes.c_size_t(p.size), step,
+                                        cr(lr), cr(b1), cr(b2), cr(eps))

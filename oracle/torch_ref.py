@@ -1,0 +1,100 @@
+"""torch-CPU restatement of the reference's TF graph for this path — TEST INFRASTRUCTURE ONLY.
+
+Two uses: (1) an independent cross-check of the C oracle (different code, different maths
+library, autograd instead of hand-written backward); (2) the "reference path timed beside it"
+CPU baseline of bench.py (`--impl reference`, `cpu_baseline`), since TensorFlow 1.12 itself is
+not installable offline.  "parity unpinned": see oracle/oracle_impl.h.
+
+Mirrors, op for op, what the TF graph executes:
+  tf.layers.dense -> relu -> tf.minimum(., relu_cutoff)           asr/util/tf_contrib.py:52-58
+  stack_bidirectional_dynamic_rnn: per-timestep concat([x, h]) @ K + b -> gate math, `where`
+  masking by sequence_length, reverse_sequence for the backward cell, concat(fw, bw) per layer
+                                                                  asr/model.py:176-183
+  dense4, logits, transpose to time-major                         asr/model.py:219-235
+  tf.nn.ctc_loss(...) + tf.reduce_mean                            asr/model.py:259-267
+"""
+import torch
+import torch.nn.functional as F
+
+
+def params_to_torch(params, dtype=torch.float32, requires_grad=True):
+    return {k: torch.tensor(v, dtype=dtype).requires_grad_(requires_grad) for k, v in params.items()}
+
+
+def _dense_names(cfg):
+    return ["dense/dense" if i == 0 else "dense/dense_%d" % i for i in range(cfg.num_layers_dense)]
+
+
+def _reverse_sequence(x, lengths):
+    """tf.reverse_sequence on [T,B,C] along time: only the first len_b frames of row b flip."""
+    T, B = x.shape[0], x.shape[1]
+    t = torch.arange(T).unsqueeze(1)                      # [T,1]
+    ln = lengths.unsqueeze(0).to(torch.long)              # [1,B]
+    idx = torch.where(t < ln, ln - 1 - t, t)              # [T,B]
+    return torch.gather(x, 0, idx.unsqueeze(2).expand(-1, -1, x.shape[2]))
+
+
+def _dynamic_rnn(cfg, x, lengths, kernel, bias):
+    """tf.nn.dynamic_rnn(cell, x, sequence_length) on time-major x [T,B,in]; kernel [in+H, G*H]."""
+    T, B, _ = x.shape
+    H = cfg.num_units_rnn
+    h = x.new_zeros(B, H)
+    c = x.new_zeros(B, H)
+    outs = []
+    for t in range(T):
+        z = torch.cat([x[t], h], 1) @ kernel + bias
+        if cfg.rnn_cell == "lstm":
+            i, j, f, o = z.split(H, 1)                    # TF LSTMCell gate order
+            c_new = torch.sigmoid(f + cfg.lstm_forget_bias) * c + torch.sigmoid(i) * torch.tanh(j)
+            h_new = torch.sigmoid(o) * torch.tanh(c_new)
+        else:
+            h_new = torch.tanh(z) if cfg.rnn_cell == "rnn_tanh" else torch.relu(z)
+            c_new = c
+        if lengths is not None:
+            live = (t < lengths).unsqueeze(1)
+            outs.append(torch.where(live, h_new, torch.zeros_like(h_new)))
+            h = torch.where(live, h_new, h)
+            c = torch.where(live, c_new, c)
+        else:
+            outs.append(h_new)
+            h, c = h_new, c_new
+    return torch.stack(outs, 0)
+
+
+def inference(cfg, p, sequences, seq_length):
+    """sequences [B,T,F] -> logits [T,B,V] (dropout off; parity / eval mode)."""
+    x = sequences.transpose(0, 1)                         # time-major inside, like our layout
+    for name in _dense_names(cfg):
+        x = torch.clamp(torch.relu(x @ p[name + "/kernel"] + p[name + "/bias"]), max=cfg.relu_cutoff)
+    lengths = None if cfg.cudnn else seq_length
+    H, G = cfg.num_units_rnn, {"lstm": 4, "gru": 3}.get(cfg.rnn_cell, 1)
+    T = x.shape[0]
+    full = torch.full_like(seq_length, T)
+    for l in range(cfg.num_layers_rnn):
+        wx, wh, b = p["rnn/l%d/wx" % l], p["rnn/l%d/wh" % l], p["rnn/l%d/bias" % l]
+        GH = G * H
+        k_fw = torch.cat([wx[:, :GH], wh[0]], 0)
+        k_bw = torch.cat([wx[:, GH:], wh[1]], 0)
+        fw = _dynamic_rnn(cfg, x, lengths, k_fw, b[:GH])
+        rl = seq_length if lengths is not None else full
+        bw = _reverse_sequence(_dynamic_rnn(cfg, _reverse_sequence(x, rl), lengths, k_bw, b[GH:]), rl)
+        x = torch.cat([fw, bw], 2)
+    x = torch.clamp(torch.relu(x @ p["dense4/dense/kernel"] + p["dense4/dense/bias"]), max=cfg.relu_cutoff)
+    return x @ p["logits/dense/kernel"] + p["logits/dense/bias"]
+
+
+def loss(cfg, logits, seq_length, labels, label_len):
+    """Mean over the batch of the per-utterance CTC negative log-likelihood."""
+    per_utt = F.ctc_loss(F.log_softmax(logits, 2), labels.to(torch.long), seq_length.to(torch.long),
+                         label_len.to(torch.long), blank=cfg.num_classes - 1, reduction="none",
+                         zero_infinity=False)
+    return per_utt.mean(), per_utt
+
+
+def train_step_grads(cfg, p, sequences, seq_length, labels, label_len):
+    logits = inference(cfg, p, sequences, seq_length)
+    mean_loss, _ = loss(cfg, logits, seq_length, labels, label_len)
+    for v in p.values():
+        v.grad = None
+    mean_loss.backward()
+    return mean_loss.detach(), {k: v.grad for k, v in p.items()}, logits.detach()

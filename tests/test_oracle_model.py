@@ -1,0 +1,146 @@
+"""CPU tests pinning the RNN / dense / whole-path oracle (oracle/oracle.c + oracle/model_ref.py).
+
+Independent implementations used as pins (the reference has no tests):
+  * oracle/torch_ref.py — per-timestep torch restatement of the TF graph + autograd
+  * torch.nn.LSTM / torch.nn.RNN with pack_padded_sequence — library RNN with the TF fused
+    kernel mapped to torch's (W_ih, W_hh) layout
+"""
+import numpy as np
+import pytest
+import torch
+
+from ctc_asr_b200.params import ModelConfig
+from ctc_asr_b200 import synthetic
+from oracle import model_ref, ref, torch_ref
+
+
+def _small_cfg(cell, cudnn, layers=2):
+    return ModelConfig(num_units_dense=24, num_units_rnn=16, num_layers_rnn=layers, rnn_cell=cell,
+                       num_layers_dense=2, num_features=10, cudnn=cudnn, dense_dropout_rate=0.0)
+
+
+def _batch(cfg, B=3, T=12, seed=0, ragged=True):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, T, cfg.num_features))
+    sl = np.array([T, T - 3, T - 7][:B], np.int32) if ragged else np.full(B, T, np.int32)
+    for b in range(B):
+        x[b, sl[b]:] = 0
+    lab, ll = synthetic.make_labels(rng, B, np.array([4, 3, 2][:B]), sl)
+    return x, sl, lab, ll
+
+
+@pytest.mark.parametrize("cell", ["rnn_tanh", "rnn_relu", "lstm"])
+@pytest.mark.parametrize("cudnn", [False, True])
+def test_whole_path_vs_torch_autograd(cell, cudnn):
+    cfg = _small_cfg(cell, cudnn)
+    params = synthetic.init_params(cfg, seed=1, dtype=np.float64)
+    for k in params:                                    # non-zero biases exercise every term
+        if k.endswith("bias"):
+            params[k] = np.random.default_rng(5).standard_normal(params[k].shape) * 0.1
+    x, sl, lab, ll = _batch(cfg)
+    loss, grads, logits, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll)
+    p = torch_ref.params_to_torch(params, torch.float64)
+    tloss, tgrads, tlogits = torch_ref.train_step_grads(
+        cfg, p, torch.tensor(x), torch.tensor(sl), torch.tensor(lab), torch.tensor(ll))
+    np.testing.assert_allclose(logits, tlogits.numpy(), atol=1e-10)
+    np.testing.assert_allclose(loss, float(tloss), rtol=1e-10)
+    for k in params:
+        np.testing.assert_allclose(grads[k], tgrads[k].numpy(), atol=1e-9, err_msg=k)
+
+
+def _tf_to_torch_lstm(wx, wh, bias, H, forget_bias):
+    """TF gate order (i, j, f, o) -> torch (i, f, g, o); forget_bias folded into b_ih."""
+    def perm(m):                                        # m [..., 4H] in TF order
+        i, j, f, o = np.split(m, 4, axis=-1)
+        return np.concatenate([i, f, j, o], -1)
+    b = perm(bias.copy())
+    b[H:2 * H] += forget_bias
+    return perm(wx).T.copy(), perm(wh).T.copy(), b
+
+
+@pytest.mark.parametrize("use_len", [True, False])
+def test_lstm_layer_vs_torch_nn_lstm(use_len):
+    rng = np.random.default_rng(2)
+    T, B, nin, H = 9, 4, 6, 5
+    x = rng.standard_normal((T, B, nin))
+    sl = np.array([9, 7, 4, 1], np.int32)
+    wx = rng.standard_normal((nin, 8 * H)) * 0.4
+    wh = rng.standard_normal((2, H, 4 * H)) * 0.4
+    bias = rng.standard_normal(8 * H) * 0.2
+    y, _, _ = ref.birnn_fwd(x, sl, wx, wh, bias, cell=2, use_len=use_len, forget_bias=1.0)
+    lstm = torch.nn.LSTM(nin, H, bidirectional=True).double()
+    with torch.no_grad():
+        for d, suf in enumerate(["", "_reverse"]):
+            w_ih, w_hh, b = _tf_to_torch_lstm(wx[:, d * 4 * H:(d + 1) * 4 * H], wh[d],
+                                              bias[d * 4 * H:(d + 1) * 4 * H], H, 1.0)
+            getattr(lstm, "weight_ih_l0" + suf).copy_(torch.tensor(w_ih))
+            getattr(lstm, "weight_hh_l0" + suf).copy_(torch.tensor(w_hh))
+            getattr(lstm, "bias_ih_l0" + suf).copy_(torch.tensor(b))
+            getattr(lstm, "bias_hh_l0" + suf).zero_()
+    xt = torch.tensor(x)
+    if use_len:
+        packed = torch.nn.utils.rnn.pack_padded_sequence(xt, torch.tensor(sl, dtype=torch.long))
+        out, _ = torch.nn.utils.rnn.pad_packed_sequence(lstm(packed)[0], total_length=T)
+    else:
+        out, _ = lstm(xt)
+    np.testing.assert_allclose(y, out.detach().numpy(), atol=1e-12)
+
+
+def test_tanh_layer_vs_torch_nn_rnn():
+    rng = np.random.default_rng(4)
+    T, B, nin, H = 8, 3, 5, 7
+    x = rng.standard_normal((T, B, nin))
+    sl = np.array([8, 5, 2], np.int32)
+    wx = rng.standard_normal((nin, 2 * H)) * 0.5
+    wh = rng.standard_normal((2, H, H)) * 0.5
+    bias = rng.standard_normal(2 * H) * 0.2
+    y, _, _ = ref.birnn_fwd(x, sl, wx, wh, bias, cell=0, use_len=True)
+    rnn = torch.nn.RNN(nin, H, bidirectional=True).double()
+    with torch.no_grad():
+        for d, suf in enumerate(["", "_reverse"]):
+            getattr(rnn, "weight_ih_l0" + suf).copy_(torch.tensor(wx[:, d * H:(d + 1) * H].T.copy()))
+            getattr(rnn, "weight_hh_l0" + suf).copy_(torch.tensor(wh[d].T.copy()))
+            getattr(rnn, "bias_ih_l0" + suf).copy_(torch.tensor(bias[d * H:(d + 1) * H]))
+            getattr(rnn, "bias_hh_l0" + suf).zero_()
+    packed = torch.nn.utils.rnn.pack_padded_sequence(torch.tensor(x), torch.tensor(sl, dtype=torch.long))
+    out, _ = torch.nn.utils.rnn.pad_packed_sequence(rnn(packed)[0], total_length=T)
+    np.testing.assert_allclose(y, out.detach().numpy(), atol=1e-12)
+    assert not y[5:, 1].any() and not y[2:, 2].any()       # dynamic_rnn: zeros past the length
+
+
+def test_dense_dropout_mask_consistency():
+    """Forward keep-mask and backward mask come from the same counter hash."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((40, 7))
+    w = rng.standard_normal((7, 11))
+    b = rng.standard_normal(11) * 0.1
+    y = ref.dense_fwd(x, w, b, act=1, cutoff=1.5, drop_rate=0.3, seed=42)
+    y0 = ref.dense_fwd(x, w, b, act=1, cutoff=1.5, drop_rate=0.0)
+    kept = y != 0
+    assert 0.5 < kept[y0 > 0].mean() < 0.9
+    np.testing.assert_allclose(y[kept], y0[kept] / 0.7, rtol=1e-6)
+    dy = rng.standard_normal(y.shape)
+    dx, dw, db = ref.dense_bwd(x, w, y, dy, act=1, cutoff=1.5, drop_rate=0.3, seed=42)
+    dz = np.where(kept & (y0 > 0) & (y0 < 1.5), dy / 0.7, 0.0)
+    np.testing.assert_allclose(dw, x.T @ dz, atol=1e-12)
+    np.testing.assert_allclose(db, dz.sum(0), atol=1e-12)
+    np.testing.assert_allclose(dx, dz @ w.T, atol=1e-12)
+
+
+def test_adam_tf1_formula():
+    rng = np.random.default_rng(1)
+    p, g = rng.standard_normal(100), rng.standard_normal(100)
+    m, v = np.zeros(100), np.zeros(100)
+    p0 = p.copy()
+    ref.adam(p, m, v, g, step=1, lr=1e-3)
+    # first step of Adam moves every weight by ~lr against the sign of its gradient
+    np.testing.assert_allclose(p0 - p, 1e-3 * np.sign(g), rtol=1e-2)
+    tp = torch.tensor(p0.copy(), requires_grad=True)
+    opt = torch.optim.Adam([tp], lr=1e-3, eps=1e-8)
+    p2, m2, v2 = p0.copy(), np.zeros(100), np.zeros(100)
+    for step in range(1, 4):
+        tp.grad = torch.tensor(g * step)
+        opt.step()
+        ref.adam(p2, m2, v2, g * step, step=step, lr=1e-3)
+    # TF1's epsilon placement differs from torch's by O(eps): agreement to ~1e-6 relative
+    np.testing.assert_allclose(p2, tp.detach().numpy(), rtol=1e-5, atol=1e-8)
