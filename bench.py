@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — audio-frames/s of one full training step of the hot path (BASELINE.json metric).
+
+A "step" = inference_fn (dense stack + stacked BiLSTM) + CTC loss forward-backward + backward pass
++ (N>1: NCCL all-reduce of the flat gradient) + Adam, on one synthetic batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (sm_100a kernels)
+  python bench.py --impl reference ...                         the reference path on host cores
+  python bench.py --workload ctc ...                           cfg5: CTC forward-backward alone
+
+At N=1 the workload is BASELINE.json configs[1] ("DS2": 3 dense + 2 BiLSTM-2048 + 2 dense, batch
+32 x 10 s, 80-bin features, fp32 storage).  N>1: one process per GPU (torchrun), the same per-GPU
+batch on every rank (weak scaling), one all-reduce of the gradient per step.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = dict(num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_units_rnn=2048, rnn_cell="lstm",
+            cudnn=False, dense_dropout_rate=0.1)
+CFG2_B, CFG2_T, CFG2_L = 32, 1000, 160
+CFG5 = dict(B=512, T=1700, L=84, V=29)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "ctc"])
+    ap.add_argument("--compute", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=CFG2_B)
+    ap.add_argument("--frames", type=int, default=CFG2_T)
+    ap.add_argument("--units", type=int, default=2048, help="debug: shrink D and H")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames per utterance in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0, period=0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------- reference (CPU) arm
+def cpu_reference_frames_per_s(cfg, B, sample_T, L, steps=2, warmup=1):
+    """The reference's path restated on torch-CPU (oracle/torch_ref.py), timed on the host cores on
+    a bounded sample: the same batch size and model, `sample_T` frames per utterance instead of the
+    full length (every op on the path is linear in T)."""
+    import torch
+    from ctc_asr_b200 import synthetic
+    from oracle import torch_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = synthetic.init_params(cfg, seed=1)
+    p = torch_ref.params_to_torch(params, torch.float32)
+    x, sl, lab, ll = synthetic.fixed_batch(B, sample_T, L, seed=0)
+    xs, sls, labs, lls = (torch.from_numpy(a) for a in (x, sl, lab, ll))
+    opt = torch.optim.Adam(list(p.values()), lr=cfg.learning_rate, betas=(cfg.adam_beta1, cfg.adam_beta2),
+                           eps=cfg.adam_epsilon)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _, _ = torch_ref.train_step_grads(cfg, p, xs, sls, labs, lls)
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times[warmup:]))
+    return B * sample_T / dt, dt, cores
+
+
+def run_reference(args):
+    from ctc_asr_b200.params import ModelConfig
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = ModelConfig(**dict(CFG2, num_units_dense=args.units, num_units_rnn=args.units, dense_dropout_rate=0.0))
+    sample_T = args.cpu_sample_frames or 8
+    L = max(1, min(CFG2_L, sample_T // 4))
+    t0 = time.perf_counter()
+    fps, dt, cores = cpu_reference_frames_per_s(cfg, args.batch, sample_T, L, steps=args.steps, warmup=args.warmup)
+    sample = "B=%d utterances x %d frames per step (of %d), %d warm-up + %d timed steps, torch-CPU restatement of the TF graph" % (
+        args.batch, sample_T, args.frames, args.warmup, args.steps)
+    line = {
+        "impl": "reference", "metric": "audio-frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "cfg2: 3 dense + 2 BiLSTM-%d + 2 dense, B=%d x T=%d frames x 80 features, L=%d, full train step "
+                               "(TF 1.12 not installable offline: TF-equivalent restatement on torch-CPU)" % (
+                                   args.units, args.batch, args.frames, CFG2_L)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ctc_asr_b200 import _lib, ops, synthetic
+    from ctc_asr_b200.model import CTCModel
+    from ctc_asr_b200.params import ModelConfig, flops_per_frame_fwd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    peaks = load_peaks()
+    K, W = args.steps, max(args.warmup, 3)
+
+    if args.workload == "ctc":
+        return run_ctc(args, torch, lib, ops, synthetic, peaks, rank, world)
+
+    cfg = ModelConfig(**dict(CFG2, num_units_dense=args.units, num_units_rnn=args.units, compute=args.compute))
+    B, T, L = args.batch, args.frames, min(CFG2_L, max(1, args.frames // 4))
+    model = CTCModel(cfg, seed=1)
+    x, sl, lab, ll = synthetic.fixed_batch(B, T, L, seed=rank)
+    hx, hsl = torch.from_numpy(x).pin_memory(), torch.from_numpy(sl).pin_memory()
+    hlab, hll = torch.from_numpy(lab).pin_memory(), torch.from_numpy(ll).pin_memory()
+    dx, dsl, dlab, dll = hx.cuda(), hsl.cuda(), hlab.cuda(), hll.cuda()
+    gb = B * world
+    allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(loop_body, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loop_body()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        model.train_step(dx, dsl, (dlab, dll), global_batch=gb, allreduce=allreduce)
+
+    def step_e2e():
+        a = hx.cuda(non_blocking=True); b = hsl.cuda(non_blocking=True)
+        c = hlab.cuda(non_blocking=True); d = hll.cuda(non_blocking=True)
+        loss = model.train_step(a, b, (c, d), global_batch=gb, allreduce=allreduce)
+        return float(loss)          # D2H read of the step's result
+
+    for _ in range(W):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = lib.ctcasr_launch_count()
+    ms = timed(step_resident, K)
+    launches = lib.ctcasr_launch_count() - l0
+    clocks = sampler.finish()
+    ms_e2e = timed(step_e2e, K)
+
+    frames = B * T * world
+    value = frames * K / (ms * 1e-3)
+    e2e = frames * K / (ms_e2e * 1e-3)
+    flops_step = 3.0 * flops_per_frame_fwd(cfg) * B * T            # per GPU
+    tflops = flops_step * K / (ms * 1e-3) / 1e12
+    # tensor roofline of the step: tf32 runs at half the measured bf16 rate (no tf32 peak measured)
+    peak = peaks["bf16_tflops_sustained"] / 2.0 if args.compute == "tf32" else 2 * 148 * 128 * 1.9e-3
+    line = {
+        "metric": "audio-frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.compute, "data": "synthetic",
+        "config": {"workload": "cfg2: 3 dense + 2 BiLSTM-%d + 2 dense (3d2r2d), per-GPU B=%d x T=%d frames x 80 features, "
+                               "L=%d labels, fwd + CTC + bwd + %sAdam, dense dropout 0.1" % (
+                                   args.units, B, T, L, "NCCL all-reduce + " if world > 1 else ""),
+                   "global_batch": gb, "params": model.num_params,
+                   "l2_policy": "inputs larger than L2 (>=7 GB of activations per step), no explicit flush"},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(x.nbytes + sl.nbytes + lab.nbytes + ll.nbytes),
+                "d2h_bytes_per_step": 4 + 4 * B},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
+                     "traffic": None,
+                     "note": "whole-step GEMM FLOPs (3 x fwd) / step time; peak = %s bf16 sustained / 2 for tf32" % peaks["source"]},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ccfg = cfg.replace(dense_dropout_rate=0.0)
+        sT = args.cpu_sample_frames or 8
+        fps, dt, cores = cpu_reference_frames_per_s(ccfg, B, sT, max(1, min(L, sT // 4)), steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "B=%d x %d frames per step (of %d), 1 warm-up + 2 timed steps, torch-CPU "
+                                          "restatement of the TF graph (oracle/torch_ref.py)" % (B, sT, T)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_ctc(args, torch, lib, ops, synthetic, peaks, rank, world):
+    """cfg5: CTC forward-backward in isolation, judged on HBM GB/s."""
+    B, T, L, V = CFG5["B"], CFG5["T"], CFG5["L"], CFG5["V"]
+    rng = np.random.default_rng(rank)
+    logits = torch.from_numpy((rng.standard_normal((T, B, V)) * 3).astype(np.float32))
+    lab, ll = synthetic.make_labels(rng, B, L, T)
+    hl = logits.pin_memory()
+    dl, dlab, dll = hl.cuda(), torch.from_numpy(lab).cuda(), torch.from_numpy(ll).cuda()
+    dsl = torch.full((B,), T, dtype=torch.int32, device="cuda")
+    grad = torch.empty_like(dl)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    K, W = args.steps, max(args.warmup, 3)
+    for _ in range(W):
+        ops.ctc_loss(dl, dlab, dll, dsl, out_grad=grad)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    l0 = lib.ctcasr_launch_count()
+    tot = 0.0
+    for _ in range(K):
+        flush.zero_()                                       # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.ctc_loss(dl, dlab, dll, dsl, out_grad=grad)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    launches = lib.ctcasr_launch_count() - l0
+    clocks = sampler.finish()
+    ms = tot / K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        d = hl.cuda(non_blocking=True)
+        loss, g, st = ops.ctc_loss(d, dlab, dll, dsl, out_grad=grad)
+        g.cpu()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / K
+    alg_bytes = B * (2 * T * V * 4 + L * 4 + 12)
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    line = {
+        "metric": "audio-frames/s (CTC forward-backward only)", "value": B * T / (ms * 1e-3), "unit": "frames/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "cfg5: CTC alpha/beta, B=%d, T=%d, L=%d, V=%d" % (B, T, L, V), "l2_policy": "256 MiB flush between iterations"},
+        "e2e": {"value": B * T / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(logits.numel() * 4),
+                "d2h_bytes_per_step": int(logits.numel() * 4)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": gbs / peaks["hbm_gbs"], "traffic": None, "note": "peak of %s" % peaks["source"]},
+    }
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+// api.cu — C-ABI entry points that are thin compositions of the kernels: dense layer forward /
+// backward (asr/util/tf_contrib.py:52-58, asr/model.py:220-226,232), the generic GEMM, and the
+// library-level bookkeeping (version, last error, launch counter).
+#include "gemm.cuh"
+
+namespace ctcasr {
+thread_local char g_last_error[512] = "";
+std::atomic<uint64_t> g_launch_count{0};
+
+int gemm(const GemmArgs &g, int compute, cudaStream_t stream)
+{
+    if (compute == CTCASR_COMPUTE_TF32 && gemm_tc_eligible(g)) return gemm_tc(g, stream);
+    return gemm_simt(g, stream);
+}
+}  // namespace ctcasr
+
+using namespace ctcasr;
+
+extern "C" int ctcasr_abi_version(void) { return CTCASR_ABI_VERSION; }
+extern "C" const char *ctcasr_last_error(void) { return g_last_error; }
+extern "C" uint64_t ctcasr_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" int ctcasr_gemm(const float *A, const float *B, float *C, int M, int N, int K,
+                           int ta, int tb, int lda, int ldb, int ldc, int accumulate, int compute, void *stream)
+{
+    CTCASR_REQUIRE(A && B && C && M >= 0 && N >= 0 && K >= 0, "gemm: bad args");
+    GemmArgs g;
+    g.A[0] = A; g.B[0] = B; g.C[0] = C; g.M = M; g.N = N; g.K = K; g.ta = ta; g.tb = tb;
+    g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.epi.accumulate = accumulate;
+    return gemm(g, compute, (cudaStream_t)stream);
+}
+
+extern "C" int ctcasr_dense_fwd(const float *x, const float *w, const float *bias, float *y,
+                                int M, int K, int N, int act, float cutoff, float drop_rate, uint32_t seed,
+                                int compute, void *stream)
+{
+    CTCASR_REQUIRE(x && w && y && M >= 0 && K >= 1 && N >= 1, "dense_fwd: bad args");
+    CTCASR_REQUIRE(drop_rate >= 0.f && drop_rate < 1.f, "dense_fwd: drop_rate %f", drop_rate);
+    GemmArgs g;
+    g.A[0] = x; g.B[0] = w; g.C[0] = y; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = N; g.ldc = N;
+    g.epi.mode = EPI_BIAS_ACT; g.epi.bias = bias; g.epi.act = act; g.epi.cutoff = cutoff;
+    g.epi.drop_rate = drop_rate; g.epi.seed = seed;
+    return gemm(g, compute, (cudaStream_t)stream);
+}
+
+extern "C" int ctcasr_dense_bwd(const float *x, const float *w, const float *y, float *dy,
+                                float *dx, float *dw, float *db, int M, int K, int N,
+                                int act, float cutoff, float drop_rate, uint32_t seed,
+                                int compute, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTCASR_REQUIRE(x && w && dy && dw && db && M >= 0 && K >= 1 && N >= 1, "dense_bwd: bad args");
+    CTCASR_REQUIRE(act == 0 || y, "dense_bwd: activation mask needs the forward output y");
+    int rc = mask_inplace(dy, y, (size_t)M, N, act, cutoff, drop_rate, seed, stream);   // dy -> dz
+    if (rc != CTCASR_OK) return rc;
+    rc = colsum(dy, M, N, N, db, stream);
+    if (rc != CTCASR_OK) return rc;
+    {   // dW[K,N] = X^T dz
+        GemmArgs g;
+        g.A[0] = x; g.B[0] = dy; g.C[0] = dw; g.ta = 1; g.M = K; g.N = N; g.K = M; g.lda = K; g.ldb = N; g.ldc = N;
+        rc = gemm(g, compute, stream);
+        if (rc != CTCASR_OK) return rc;
+    }
+    if (dx) {   // dX[M,K] = dz W^T
+        GemmArgs g;
+        g.A[0] = dy; g.B[0] = w; g.C[0] = dx; g.tb = 1; g.M = M; g.N = K; g.K = N; g.lda = N; g.ldb = N; g.ldc = K;
+        rc = gemm(g, compute, stream);
+        if (rc != CTCASR_OK) return rc;
+    }
+    return CTCASR_OK;
+}

@@ -1,0 +1,550 @@
+// ctc.cu — CTC loss forward-backward and greedy decode for sm_100a.
+//
+// Replaces tf.nn.ctc_loss (asr/model.py:259-264; a CPU-only op in TF 1.x that costs a D2H copy of
+// the logits and an H2D copy of the gradient every step) and the greedy stand-in
+// for decode_fn (asr/model.py:271-309).  Semantics: SURVEY.md Appendix A.7 / oracle_impl.h.
+//
+// Kernel design (one CTA per utterance, the 2L+1 blank-expanded lattice lives in shared memory):
+//   phase 1  alpha sweep over t = 0..T_b-1 in chunks of CH frames.  Only one re-normalised alpha
+//            row per chunk (a "checkpoint", S floats) goes to global memory, never the [T,S] table.
+//   phase 2  for chunks from the last to the first, the alpha warps re-compute the chunk's alpha
+//            rows from its checkpoint into shared memory while the beta warps sweep the
+//            previously re-computed chunk backwards, turning alpha rows into posteriors in place;
+//            then all warps reduce posteriors per class (deterministic CSR gather, no atomics)
+//            and write the gradient rows.
+//   HBM traffic is therefore the algorithmic one: logits in (re-read from L2 in phase 2),
+//   gradient out, plus T/CH checkpoint rows.
+//   alpha/beta are log-domain fp32 but re-based per chunk (offsets accumulated in fp64) so that
+//   values stay O(chunk) instead of O(T): un-normalised fp32 rows of magnitude ~3e3 carry ~1e-2
+//   of gradient noise at T=1700 (tests/test_oracle_ctc.py), which would eat the 1e-3 budget.
+//   Each recursion step is one shared-memory row read + a 3-way log-sum-exp (MUFU ex2/lg2) + one
+//   named barrier per warp group; alpha and beta groups run on separate barriers.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace ctcasr {
+namespace ctc {
+
+constexpr int kMaxSPT = 4;      // lattice states per thread
+constexpr int kMaxVPT = 4;      // classes per lane in the softmax (V <= 128)
+constexpr int kMaxGT = 480;     // threads per group (alpha / beta)
+
+struct Params {
+    const float *logits; int T, B, V, blank;
+    const int *labels; int lstride; const int *label_len; const int *seq_len;
+    float *loss; float *grad; float grad_scale; int *status;
+    float *ckpt; double *ckoff;     // [B][NCH][RS], [B][NCH]
+    int CH, RS, GT, NCH, Lmax, VP;
+};
+
+struct SmemLayout {
+    size_t lab, csr_start, csr_pos, rowA, rowB, A, LY, red, total;
+    __host__ __device__ SmemLayout(int Lmax, int V, int RS, int CH, int VP)
+    {
+        size_t o = 0;
+        lab = o;       o += (size_t)((Lmax + 3) / 4 * 4 + 4) * 4;
+        csr_start = o; o += (size_t)((V + 1 + 3) / 4 * 4) * 4;
+        csr_pos = o;   o += (size_t)((Lmax + 3) / 4 * 4 + 4) * 4;
+        rowA = o;      o += (size_t)2 * RS * 4;
+        rowB = o;      o += (size_t)2 * RS * 4;
+        A = o;         o += (size_t)2 * CH * RS * 4;
+        LY = o;        o += (size_t)2 * CH * VP * 4;
+        red = o;       o += 64 * 4 + 64;
+        total = o;
+    }
+};
+
+__device__ __forceinline__ float lse3(float a, float b, float c)
+{
+    const float m = fmaxf(a, fmaxf(b, c));
+    if (m == -INFINITY) return -INFINITY;
+    return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
+__device__ __forceinline__ void group_bar(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// max over a thread group (GT threads, group-local thread id gt, barrier id bar)
+__device__ float group_max(float v, float *red, int gt, int GT, int bar)
+{
+    v = warp_max(v);
+    const int w = gt >> 5, nw = GT >> 5;
+    if ((gt & 31) == 0) red[w] = v;
+    group_bar(bar, GT);
+    float m = -INFINITY;
+    for (int i = 0; i < nw; ++i) m = fmaxf(m, red[i]);
+    group_bar(bar, GT);        // red[] may be reused immediately afterwards
+    return m;
+}
+
+// log-softmax of the frames of chunk c into LY[buf]; one warp per frame, all warps of the CTA.
+__device__ void compute_logy(const Params &p, int b, int Tb, int c, float *LY)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int lo = c * p.CH, hi = min(lo + p.CH, Tb);
+    for (int t = lo + warp; t < hi; t += nwarps) {
+        const float *x = p.logits + ((size_t)t * p.B + b) * p.V;
+        float v[kMaxVPT];
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kMaxVPT; ++i) {
+            const int k = lane + 32 * i;
+            v[i] = k < p.V ? __ldg(x + k) : -INFINITY;
+            m = fmaxf(m, v[i]);
+        }
+        m = warp_max(m);
+        float e = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxVPT; ++i) e += (lane + 32 * i < p.V) ? expf(v[i] - m) : 0.f;
+        e = warp_sum(e);
+        const float lse = m + logf(e);
+        float *row = LY + (size_t)(t - lo) * p.VP;
+#pragma unroll
+        for (int i = 0; i < kMaxVPT; ++i) {
+            const int k = lane + 32 * i;
+            if (k < p.VP) row[k] = k < p.V ? v[i] - lse : -INFINITY;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(2 * kMaxGT, 1)
+ctc_loss_kernel(const Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int GT = p.GT, NT = 2 * GT;
+    const bool is_alpha = tid < GT;
+    const int gt = is_alpha ? tid : tid - GT;
+    const int RS = p.RS, CH = p.CH, V = p.V, VP = p.VP, blank = p.blank;
+
+    const SmemLayout L(p.Lmax, V, RS, CH, VP);
+    int *lab = reinterpret_cast<int *>(smem_raw + L.lab);
+    int *csr_start = reinterpret_cast<int *>(smem_raw + L.csr_start);
+    int *csr_pos = reinterpret_cast<int *>(smem_raw + L.csr_pos);
+    float *rowA = reinterpret_cast<float *>(smem_raw + L.rowA);   // alpha rows: state s at [s+2]
+    float *rowB = reinterpret_cast<float *>(smem_raw + L.rowB);   // primed beta rows: state s at [s]
+    float *Abuf = reinterpret_cast<float *>(smem_raw + L.A);      // [2][CH][RS], state s at [s+2]
+    float *LYbuf = reinterpret_cast<float *>(smem_raw + L.LY);    // [2][CH][VP]
+    float *red = reinterpret_cast<float *>(smem_raw + L.red);
+    int *flags = reinterpret_cast<int *>(red + 48);               // [0] bad label, [1] repeats
+
+    const int Tb = p.seq_len[b];
+    const int Ln = p.label_len[b];
+    const int S = 2 * Ln + 1;
+    float *grad_b = p.grad ? p.grad + (size_t)b * V : nullptr;    // row t at + t*B*V
+    const size_t gstride = (size_t)p.B * V;
+
+    // ---- setup: labels, validation ---------------------------------------------------------
+    if (tid < 2) flags[tid] = 0;
+    __syncthreads();
+    int status = CTCASR_CTC_OK;
+    if (Tb > p.T || Tb < 0 || Ln < 0 || Ln > p.Lmax) status = CTCASR_CTC_BAD_LENGTH;
+    if (status == CTCASR_CTC_OK) {
+        int bad = 0, rep = 0;
+        for (int i = tid; i < Ln; i += NT) {
+            const int v = p.labels[(size_t)b * p.lstride + i];
+            lab[i] = v;
+            if (v < 0 || v >= V || v == blank) bad = 1;
+            if (i > 0 && v == p.labels[(size_t)b * p.lstride + i - 1]) ++rep;
+        }
+        if (bad) atomicOr(&flags[0], 1);
+        if (rep) atomicAdd(&flags[1], rep);
+    }
+    __syncthreads();
+    if (status == CTCASR_CTC_OK) {
+        if (flags[0]) status = CTCASR_CTC_BAD_LABEL;
+        else if (Tb < Ln + flags[1]) status = CTCASR_CTC_INFEASIBLE;
+    }
+    // gradient rows the recursion never touches are zero (t >= T_b, or the whole utterance)
+    if (grad_b) {
+        const int t0 = (status == CTCASR_CTC_OK) ? Tb : 0;
+        for (int i = tid; i < (p.T - t0) * V; i += NT)
+            grad_b[(size_t)(t0 + i / V) * gstride + i % V] = 0.f;
+    }
+    if (status != CTCASR_CTC_OK || Tb == 0) {
+        if (tid == 0) {
+            p.status[b] = status;
+            p.loss[b] = status == CTCASR_CTC_OK ? 0.f : INFINITY;
+        }
+        return;
+    }
+
+    // ---- per-class position lists of the label states (odd s), built in label order ----------
+    if (tid == 0) {
+        for (int k = 0; k <= V; ++k) csr_start[k] = 0;
+        for (int i = 0; i < Ln; ++i) csr_start[lab[i] + 1]++;
+        for (int k = 0; k < V; ++k) csr_start[k + 1] += csr_start[k];
+    }
+    // guards: alpha rows [0],[1]; beta rows [S],[S+1]; every A row [0],[1]
+    for (int i = tid; i < 2 * RS; i += NT) { rowA[i] = -INFINITY; rowB[i] = -INFINITY; }
+    for (int i = tid; i < 2 * CH; i += NT) { Abuf[(size_t)i * RS] = -INFINITY; Abuf[(size_t)i * RS + 1] = -INFINITY; }
+    __syncthreads();
+    if (tid == 0) {
+        // csr_pos filled by a serial stable pass (deterministic summation order later)
+        int *cursor = reinterpret_cast<int *>(LYbuf);     // scratch (VP >= V ints); LY is rewritten before use
+        for (int k = 0; k < V; ++k) cursor[k] = csr_start[k];
+        for (int i = 0; i < Ln; ++i) csr_pos[cursor[lab[i]]++] = 2 * i + 1;
+    }
+    __syncthreads();
+
+    // per-thread lattice-state constants
+    int st_lp[kMaxSPT];
+    bool st_skA[kMaxSPT], st_skB[kMaxSPT];
+#pragma unroll
+    for (int q = 0; q < kMaxSPT; ++q) {
+        const int s = gt + q * GT;
+        st_lp[q] = blank; st_skA[q] = false; st_skB[q] = false;
+        if (s < S && (s & 1)) {
+            const int li = s >> 1;
+            st_lp[q] = lab[li];
+            st_skA[q] = li > 0 && lab[li] != lab[li - 1];
+            st_skB[q] = li + 1 < Ln && lab[li + 1] != lab[li];
+        }
+    }
+
+    const int NCH = (Tb + CH - 1) / CH;
+    float *ck_b = p.ckpt + (size_t)b * p.NCH * RS;
+    double *off_b = p.ckoff + (size_t)b * p.NCH;
+
+    // =========================== phase 1: alpha sweep with checkpoints =========================
+    double offA = 0.0;
+    int cur = 0;
+    if (is_alpha) {       // virtual row t = -1: {0, -inf, ...} reproduces TF's alpha init
+#pragma unroll
+        for (int q = 0; q < kMaxSPT; ++q) {
+            const int s = gt + q * GT;
+            if (s < S) rowA[cur * RS + s + 2] = s == 0 ? 0.f : -INFINITY;
+        }
+    }
+    for (int c = 0; c < NCH; ++c) {
+        float *LY = LYbuf + (size_t)(c & 1) * CH * VP;
+        compute_logy(p, b, Tb, c, LY);
+        __syncthreads();
+        if (is_alpha) {
+            // re-base the incoming row and checkpoint it
+            float m = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < kMaxSPT; ++q) {
+                const int s = gt + q * GT;
+                if (s < S) m = fmaxf(m, rowA[cur * RS + s + 2]);
+            }
+            m = group_max(m, red, gt, GT, 1);
+            offA += (double)m;
+#pragma unroll
+            for (int q = 0; q < kMaxSPT; ++q) {
+                const int s = gt + q * GT;
+                if (s < S) {
+                    const float v = rowA[cur * RS + s + 2] - m;
+                    rowA[cur * RS + s + 2] = v;
+                    ck_b[(size_t)c * RS + s] = v;
+                }
+            }
+            if (gt == 0) off_b[c] = offA;
+            group_bar(1, GT);
+            const int lo = c * CH, hi = min(lo + CH, Tb);
+            for (int t = lo; t < hi; ++t) {
+                const float *prev = rowA + cur * RS;
+                float *next = rowA + (cur ^ 1) * RS;
+                const float *ly = LY + (size_t)(t - lo) * VP;
+#pragma unroll
+                for (int q = 0; q < kMaxSPT; ++q) {
+                    const int s = gt + q * GT;
+                    if (s < S) {
+                        const float a0 = prev[s + 2], a1 = prev[s + 1];
+                        const float a2 = st_skA[q] ? prev[s] : -INFINITY;
+                        next[s + 2] = lse3(a0, a1, a2) + ly[st_lp[q]];
+                    }
+                }
+                cur ^= 1;
+                group_bar(1, GT);
+            }
+        }
+        __syncthreads();
+    }
+    // log p = offA + LSE(alpha[S-1], alpha[S-2]) at t = T_b - 1, shared through smem as a double
+    double *dsh = reinterpret_cast<double *>(red + 40);
+    if (tid == 0) {
+        const float a = rowA[cur * RS + (S - 1) + 2];
+        const float c2 = S > 1 ? rowA[cur * RS + (S - 2) + 2] : -INFINITY;
+        const float m = fmaxf(a, c2);
+        const double logp = m == -INFINITY ? -(double)INFINITY
+                                           : offA + (double)m + log(exp((double)(a - m)) + exp((double)(c2 - m)));
+        dsh[0] = logp;
+        p.loss[b] = (float)(-logp);
+        p.status[b] = CTCASR_CTC_OK;
+    }
+    if (!p.grad) return;
+    __syncthreads();
+    const double logp = dsh[0];
+
+    // =========================== phase 2: alpha re-compute || beta sweep =======================
+    double offB = 0.0;
+    int curB = 0;
+    if (!is_alpha) {      // virtual primed row t = T_b: {.., -inf, 0 at S-1}
+#pragma unroll
+        for (int q = 0; q < kMaxSPT; ++q) {
+            const int s = gt + q * GT;
+            if (s < S) rowB[curB * RS + s] = s == S - 1 ? 0.f : -INFINITY;
+        }
+    }
+    for (int r = 0; r <= NCH; ++r) {
+        const int ca = NCH - 1 - r;     // chunk the alpha group re-computes
+        const int cb = NCH - r;         // chunk the beta group sweeps
+        if (ca >= 0) compute_logy(p, b, Tb, ca, LYbuf + (size_t)(ca & 1) * CH * VP);
+        __syncthreads();
+        if (is_alpha) {
+            if (ca >= 0) {
+                const float *LY = LYbuf + (size_t)(ca & 1) * CH * VP;
+                float *A = Abuf + (size_t)(ca & 1) * CH * RS;
+                float *r0 = rowA;       // checkpoint row of chunk ca
+#pragma unroll
+                for (int q = 0; q < kMaxSPT; ++q) {
+                    const int s = gt + q * GT;
+                    if (s < S) r0[s + 2] = ck_b[(size_t)ca * RS + s];
+                }
+                group_bar(1, GT);
+                const int lo = ca * CH, hi = min(lo + CH, Tb);
+                for (int t = lo; t < hi; ++t) {
+                    const float *prev = t == lo ? r0 : A + (size_t)(t - lo - 1) * RS;
+                    float *next = A + (size_t)(t - lo) * RS;
+                    const float *ly = LY + (size_t)(t - lo) * VP;
+#pragma unroll
+                    for (int q = 0; q < kMaxSPT; ++q) {
+                        const int s = gt + q * GT;
+                        if (s < S) {
+                            const float a0 = prev[s + 2], a1 = prev[s + 1];
+                            const float a2 = st_skA[q] ? prev[s] : -INFINITY;
+                            next[s + 2] = lse3(a0, a1, a2) + ly[st_lp[q]];
+                        }
+                    }
+                    group_bar(1, GT);
+                }
+            }
+        } else if (cb < NCH) {
+            const float *LY = LYbuf + (size_t)(cb & 1) * CH * VP;
+            float *A = Abuf + (size_t)(cb & 1) * CH * RS;
+            // re-base the incoming primed row
+            float m = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < kMaxSPT; ++q) {
+                const int s = gt + q * GT;
+                if (s < S) m = fmaxf(m, rowB[curB * RS + s]);
+            }
+            m = group_max(m, red + 16, gt, GT, 2);
+            offB += (double)m;
+#pragma unroll
+            for (int q = 0; q < kMaxSPT; ++q) {
+                const int s = gt + q * GT;
+                if (s < S) rowB[curB * RS + s] -= m;
+            }
+            group_bar(2, GT);
+            const float Kc = (float)(off_b[cb] + offB - logp);
+            const int lo = cb * CH, hi = min(lo + CH, Tb);
+            for (int t = hi - 1; t >= lo; --t) {
+                const float *prev = rowB + curB * RS;
+                float *next = rowB + (curB ^ 1) * RS;
+                const float *ly = LY + (size_t)(t - lo) * VP;
+                float *arow = A + (size_t)(t - lo) * RS;
+#pragma unroll
+                for (int q = 0; q < kMaxSPT; ++q) {
+                    const int s = gt + q * GT;
+                    if (s < S) {
+                        const float b0 = prev[s], b1 = prev[s + 1];
+                        const float b2 = st_skB[q] ? prev[s + 2] : -INFINITY;
+                        const float v = lse3(b0, b1, b2);           // beta[s,t] (TF: excludes y_t)
+                        next[s] = v + ly[st_lp[q]];                 // primed for step t-1
+                        arow[s + 2] = __expf(arow[s + 2] + v + Kc); // posterior of state s at t
+                    }
+                }
+                curB ^= 1;
+                group_bar(2, GT);
+            }
+        }
+        __syncthreads();
+        // ---- gradient rows of chunk cb: y - sum_{s in class k} posterior ---------------------
+        if (cb < NCH) {
+            const float *LY = LYbuf + (size_t)(cb & 1) * CH * VP;
+            const float *A = Abuf + (size_t)(cb & 1) * CH * RS;
+            const int lo = cb * CH, hi = min(lo + CH, Tb);
+            const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
+            for (int t = lo + warp; t < hi; t += nwarps) {
+                const float *arow = A + (size_t)(t - lo) * RS + 2;
+                float pb = 0.f;                                     // blank states: even s
+                for (int i = lane; 2 * i < S; i += 32) pb += arow[2 * i];
+                pb = warp_sum(pb);
+                for (int k = lane; k < V; k += 32) {
+                    float acc = 0.f;
+                    if (k == blank) acc = pb;
+                    else for (int q = csr_start[k]; q < csr_start[k + 1]; ++q) acc += arow[csr_pos[q]];
+                    const float y = __expf(LY[(size_t)(t - lo) * VP + k]);
+                    grad_b[(size_t)t * gstride + k] = (y - acc) * p.grad_scale;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy decode: one warp per utterance, 32 frames per iteration
+// ------------------------------------------------------------------------------------------------
+__global__ void greedy_decode_kernel(const float *logits, int T, int B, int V, int blank,
+                                     const int *seq_len, int *out_ids, int *out_len)
+{
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int Tb = min(seq_len[b], T);
+    int n = 0, carry = -1;
+    for (int t0 = 0; t0 < Tb; t0 += 32) {
+        const int t = t0 + lane;
+        int am = -1;
+        if (t < Tb) {
+            const float *x = logits + ((size_t)t * B + b) * V;
+            float best = x[0];
+            am = 0;
+            for (int k = 1; k < V; ++k) {
+                const float v = x[k];
+                if (v > best) { best = v; am = k; }     // strict >: first max wins
+            }
+        }
+        int prev = __shfl_up_sync(0xffffffffu, am, 1);
+        if (lane == 0) prev = carry;
+        const bool emit = t < Tb && am != blank && am != prev;
+        const unsigned mask = __ballot_sync(0xffffffffu, emit);
+        if (emit) out_ids[(size_t)b * T + n + __popc(mask & ((1u << lane) - 1))] = am;
+        n += __popc(mask);
+        carry = __shfl_sync(0xffffffffu, am, 31);
+    }
+    for (int i = n + lane; i < T; i += 32) out_ids[(size_t)b * T + i] = -1;
+    if (lane == 0) out_len[b] = n;
+}
+
+struct Plan { int CH, RS, GT, NCH, VP; size_t smem, ws_ckpt, ws_total; };
+
+static int make_plan(int T, int B, int V, int Lmax, Plan *pl)
+{
+    const int S = 2 * Lmax + 1;
+    if (V < 1 || V > 32 * kMaxVPT) return fail(CTCASR_ERR_UNSUPPORTED, "ctc: num_classes %d > %d", V, 32 * kMaxVPT);
+    int GT = (S + 31) / 32 * 32;
+    if (GT > kMaxGT) GT = kMaxGT;
+    if (GT < 64) GT = 64;
+    if (S > kMaxSPT * GT) return fail(CTCASR_ERR_UNSUPPORTED, "ctc: label length %d too long", Lmax);
+    pl->GT = GT;
+    pl->RS = (S + 2 + 31) / 32 * 32;
+    pl->VP = (V + 31) / 32 * 32;
+    pl->CH = pl->RS <= 448 ? 16 : 8;
+    pl->NCH = T > 0 ? (T + pl->CH - 1) / pl->CH : 1;
+    pl->smem = SmemLayout(Lmax, V, pl->RS, pl->CH, pl->VP).total;
+    pl->ws_ckpt = align_up((size_t)B * pl->NCH * pl->RS * sizeof(float), 256);
+    pl->ws_total = pl->ws_ckpt + align_up((size_t)B * pl->NCH * sizeof(double), 256);
+    return CTCASR_OK;
+}
+
+}  // namespace ctc
+}  // namespace ctcasr
+
+using namespace ctcasr;
+
+extern "C" size_t ctcasr_ctc_workspace_bytes(int T, int B, int V, int max_label_len)
+{
+    ctc::Plan pl{};
+    if (ctc::make_plan(T, B, V, max_label_len, &pl) != CTCASR_OK) return 0;
+    return pl.ws_total;
+}
+
+extern "C" int ctcasr_ctc_loss(const float *logits, int T, int B, int V, int blank,
+                               const int32_t *labels, int label_stride, const int32_t *label_len,
+                               const int32_t *seq_len, float *loss, float *grad, float grad_scale,
+                               int32_t *status, int max_label_len, void *ws, size_t ws_bytes, void *stream)
+{
+    CTCASR_REQUIRE(logits && labels && label_len && seq_len && loss && status, "ctc: null pointer");
+    CTCASR_REQUIRE(T >= 0 && B >= 1 && blank >= 0 && blank < V && max_label_len >= 0 && label_stride >= 1,
+                   "ctc: bad dims T=%d B=%d V=%d blank=%d", T, B, V, blank);
+    ctc::Plan pl{};
+    int rc = ctc::make_plan(T, B, V, max_label_len, &pl);
+    if (rc != CTCASR_OK) return rc;
+    if (ws_bytes < pl.ws_total || !ws) return fail(CTCASR_ERR_WORKSPACE, "ctc: workspace %zu < %zu", ws_bytes, pl.ws_total);
+    ctc::Params p;
+    p.logits = logits; p.T = T; p.B = B; p.V = V; p.blank = blank;
+    p.labels = labels; p.lstride = label_stride; p.label_len = label_len; p.seq_len = seq_len;
+    p.loss = loss; p.grad = grad; p.grad_scale = grad_scale; p.status = status;
+    p.ckpt = reinterpret_cast<float *>(ws);
+    p.ckoff = reinterpret_cast<double *>(reinterpret_cast<char *>(ws) + pl.ws_ckpt);
+    p.CH = pl.CH; p.RS = pl.RS; p.GT = pl.GT; p.NCH = pl.NCH; p.Lmax = max_label_len; p.VP = pl.VP;
+    static size_t smem_set = 0;
+    if (pl.smem > smem_set) {
+        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(ctc::ctc_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        smem_set = pl.smem;
+    }
+    ctc::ctc_loss_kernel<<<B, 2 * pl.GT, pl.smem, (cudaStream_t)stream>>>(p);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+extern "C" int ctcasr_ctc_loss_host(const float *logits, int T, int B, int V, int blank,
+                                    const int32_t *labels, int label_stride, const int32_t *label_len,
+                                    const int32_t *seq_len, float *loss, float *grad, float grad_scale,
+                                    int32_t *status)
+{
+    CTCASR_REQUIRE(logits && labels && label_len && seq_len && loss && status, "ctc_host: null pointer");
+    int lmax = 0;
+    for (int b = 0; b < B; ++b) lmax = label_len[b] > lmax ? label_len[b] : lmax;
+    if (lmax > label_stride) lmax = label_stride;
+    const size_t nlog = (size_t)T * B * V * sizeof(float), nlab = (size_t)B * label_stride * sizeof(int32_t);
+    const size_t wsb = ctcasr_ctc_workspace_bytes(T, B, V, lmax);
+    if (wsb == 0) return CTCASR_ERR_UNSUPPORTED;
+    char *d = nullptr;
+    size_t off_logits = 0, off_grad = align_up(nlog, 256), off_lab = off_grad + align_up(nlog, 256);
+    size_t off_ll = off_lab + align_up(nlab, 256), off_sl = off_ll + align_up(B * 4, 256);
+    size_t off_loss = off_sl + align_up(B * 4, 256), off_st = off_loss + align_up(B * 4, 256);
+    size_t off_ws = off_st + align_up(B * 4, 256), total = off_ws + wsb;
+    CTCASR_CUDA_CHECK(cudaMalloc(&d, total));
+    cudaStream_t s = 0;
+    int rc = CTCASR_OK;
+    cudaError_t e = cudaSuccess;
+    e = cudaMemcpyAsync(d + off_logits, logits, nlog, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_lab, labels, nlab, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_ll, label_len, B * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_sl, seq_len, B * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess)
+        rc = ctcasr_ctc_loss((float *)(d + off_logits), T, B, V, blank, (int32_t *)(d + off_lab), label_stride,
+                             (int32_t *)(d + off_ll), (int32_t *)(d + off_sl), (float *)(d + off_loss),
+                             grad ? (float *)(d + off_grad) : nullptr, grad_scale, (int32_t *)(d + off_st), lmax,
+                             d + off_ws, wsb, s);
+    if (e == cudaSuccess && rc == CTCASR_OK) e = cudaMemcpyAsync(loss, d + off_loss, B * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && rc == CTCASR_OK) e = cudaMemcpyAsync(status, d + off_st, B * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && rc == CTCASR_OK && grad) e = cudaMemcpyAsync(grad, d + off_grad, nlog, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(CTCASR_ERR_CUDA, "ctc_host: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int ctcasr_greedy_decode(const float *logits, int T, int B, int V, int blank,
+                                    const int32_t *seq_len, int32_t *out_ids, int32_t *out_len, void *stream)
+{
+    CTCASR_REQUIRE(logits && seq_len && out_ids && out_len && T >= 0 && B >= 1 && V >= 1, "greedy_decode: bad args");
+    const int wpb = 4;
+    ctc::greedy_decode_kernel<<<ceil_div(B, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(logits, T, B, V, blank, seq_len,
+                                                                                       out_ids, out_len);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}

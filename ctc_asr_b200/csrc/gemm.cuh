@@ -1,0 +1,30 @@
+// gemm.cuh — GEMM argument block shared by the SIMT (gemm_simt.cu) and tcgen05 (gemm_tc.cu) paths.
+#pragma once
+#include "common.cuh"
+
+namespace ctcasr {
+
+struct GemmArgs {
+    const float *A[2] = {nullptr, nullptr};
+    const float *B[2] = {nullptr, nullptr};
+    float *C[2] = {nullptr, nullptr};
+    int nz = 1;                 // number of independent problems (1 or 2) sharing the shape
+    int M = 0, N = 0, K = 0;
+    int ta = 0, tb = 0;         // ta: A stored [K,M]; tb: B stored [N,K]
+    int lda = 0, ldb = 0, ldc = 0;
+    Epilogue epi;
+};
+
+int gemm_simt(const GemmArgs &g, cudaStream_t stream);
+// returns CTCASR_ERR_UNSUPPORTED (without touching C) when the shape/alignment is not eligible
+int gemm_tc(const GemmArgs &g, cudaStream_t stream);
+bool gemm_tc_eligible(const GemmArgs &g);
+// dispatch on `compute`: TF32 -> tcgen05 when eligible, otherwise the SIMT kernel
+int gemm(const GemmArgs &g, int compute, cudaStream_t stream);
+
+// pointwise.cu
+int colsum(const float *x, int M, int N, int ld, float *out, cudaStream_t stream);
+int mask_inplace(float *dy, const float *y, size_t M, int N, int act, float cutoff, float drop_rate,
+                 uint32_t seed, cudaStream_t stream);
+
+}  // namespace ctcasr

@@ -1,0 +1,92 @@
+// gemm_simt.cu — generic fp32 FFMA GEMM (CTCASR_COMPUTE_FP32): any shape, any leading dimension,
+// both operand orientations, fused epilogue.  This is the exact-fp32 parity path and the shape
+// fallback (K = 80 feature columns, N = 29 classes, H = 128 ...) for the tcgen05 kernels in
+// gemm_tc.cu; it is device code, not a CPU fallback.
+//
+// C[M,N] = op(A) op(B);  TA == false: A[m*lda + k], true: A[k*lda + m];
+//                        TB == false: B[k*ldb + n], true: B[n*ldb + k].
+// gridDim.z selects one of up to two independent problems (the fw / bw direction of a recurrent
+// step) that share shapes but not pointers.
+#include "gemm.cuh"
+
+namespace ctcasr {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g)
+{
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int z = blockIdx.z;
+    const float *__restrict__ A = g.A[z];
+    const float *__restrict__ B = g.B[z];
+    float *__restrict__ C = g.C[z];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[TM][TN] = {};
+
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+        for (int j = 0; j < (BM * BK) / 256; ++j) {
+            const int i = tid + j * 256;
+            int m, k;
+            if (TA) { k = i / BM; m = i % BM; } else { m = i / BK; k = i % BK; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < g.M && gk < g.K) v = TA ? A[(size_t)gk * g.lda + gm] : A[(size_t)gm * g.lda + gk];
+            As[k][m] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < (BN * BK) / 256; ++j) {
+            const int i = tid + j * 256;
+            int n, k;
+            if (TB) { n = i / BK; k = i % BK; } else { k = i / BN; n = i % BN; }
+            const int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < g.N && gk < g.K) v = TB ? B[(size_t)gn * g.ldb + gk] : B[(size_t)gk * g.ldb + gn];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= g.N) continue;
+            float *c = C + (size_t)m * g.ldc + n;
+            const float old = g.epi.accumulate ? *c : 0.f;
+            *c = epilogue_apply(g.epi, acc[i][j], m, n, g.N, old);
+        }
+    }
+}
+
+int gemm_simt(const GemmArgs &g, cudaStream_t stream)
+{
+    if (g.M <= 0 || g.N <= 0) return CTCASR_OK;
+    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.nz);
+    if (g.ta && g.tb) gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(g);
+    else if (g.ta) gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(g);
+    else if (g.tb) gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(g);
+    else gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(g);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+}  // namespace ctcasr

@@ -1,0 +1,217 @@
+// pointwise.cu — HBM-bound helpers around the GEMMs: layout transpose, bias gradient (column
+// sums), activation mask, recurrent cell math for the stepwise (SIMT) recurrent path, Adam.
+#include "gemm.cuh"
+#include "rnn.cuh"
+
+namespace ctcasr {
+
+// ---- [A,B,C] -> [B,A,C] ---------------------------------------------------------------------
+__global__ void transpose01_kernel(const float *__restrict__ in, float *__restrict__ out, int A, int B, int C)
+{
+    const size_t total = (size_t)A * B * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t r = i / C;            // output row = b*A + a
+        const int a = (int)(r % A), b = (int)(r / A);
+        out[i] = in[((size_t)a * B + b) * C + c];
+    }
+}
+
+// ---- column sums: out[n] = sum_m x[m*ld + n]  (bias gradients) --------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ x, int M, int N, int ld, float *__restrict__ out)
+{
+    __shared__ float red[8][33];
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (n < N)
+        for (int m = r; m < M; m += 8) acc += x[(size_t)m * ld + n];
+    red[r][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (r == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+        out[n] = s;
+    }
+}
+
+int colsum(const float *x, int M, int N, int ld, float *out, cudaStream_t stream)
+{
+    colsum_kernel<<<ceil_div(N, 32), 256, 0, stream>>>(x, M, N, ld, out);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+// ---- dz = dy * act'(y) * dropout mask, in place ----------------------------------------------
+__global__ void mask_inplace_kernel(float *__restrict__ dy, const float *__restrict__ y, size_t total, int N,
+                                    int act, float cutoff, float drop_rate, uint32_t seed)
+{
+    const float inv_keep = drop_rate > 0.f ? 1.f / (1.f - drop_rate) : 1.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        bool pass = drop_rate > 0.f ? drop_keep(seed, i, drop_rate) : true;
+        if (act == 1) { const float v = y[i]; pass = pass && v > 0.f && v < cutoff * inv_keep; }
+        dy[i] = pass ? dy[i] * inv_keep : 0.f;
+    }
+}
+
+int mask_inplace(float *dy, const float *y, size_t M, int N, int act, float cutoff, float drop_rate,
+                 uint32_t seed, cudaStream_t stream)
+{
+    if (act == 0 && drop_rate <= 0.f) return CTCASR_OK;
+    const size_t total = M * (size_t)N;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    mask_inplace_kernel<<<blocks, 256, 0, stream>>>(dy, y, total, N, act, cutoff, drop_rate, seed);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+// ---- recurrent cell math, stepwise path --------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+// gates: [T*B, 2*G*H] holding z = x Wx + b + h_prev Wh for frame t; replaced by activations.
+// grid (ceil(B*H/256), 2 directions); step index `i`: fw frame t = i, bw frame t = T-1-i.
+__global__ void rnn_cell_fwd_kernel(RnnStep s, int i)
+{
+    const int d = blockIdx.y;
+    const int t = d == 0 ? i : s.T - 1 - i;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.B * s.H) return;
+    const int b = idx / s.H, u = idx % s.H;
+    const int H = s.H, GH = s.G * H;
+    float *g = s.gates + ((size_t)t * s.B + b) * 2 * GH + (size_t)d * GH;
+    float *yo = s.y + ((size_t)t * s.B + b) * 2 * H + (size_t)d * H + u;
+    const bool live = !s.use_len || t < s.seq_len[b];
+    const int tp = d == 0 ? t - 1 : t + 1;
+    const bool has_prev = i > 0;
+    if (s.cell == CTCASR_CELL_LSTM) {
+        float *ct = s.cstate + ((size_t)t * s.B + b) * 2 * H + (size_t)d * H + u;
+        const float cp = has_prev ? s.cstate[((size_t)tp * s.B + b) * 2 * H + (size_t)d * H + u] : 0.f;
+        if (!live) { *yo = 0.f; *ct = cp; g[u] = 0.f; g[H + u] = 0.f; g[2 * H + u] = 0.f; g[3 * H + u] = 0.f; return; }
+        const float gi = sigmoidf_(g[u]), gj = tanhf(g[H + u]);
+        const float gf = sigmoidf_(g[2 * H + u] + s.forget_bias), go = sigmoidf_(g[3 * H + u]);
+        const float c = gf * cp + gi * gj;
+        g[u] = gi; g[H + u] = gj; g[2 * H + u] = gf; g[3 * H + u] = go;
+        *ct = c;
+        *yo = go * tanhf(c);
+    } else {
+        if (!live) { *yo = 0.f; g[u] = 0.f; return; }
+        const float z = g[u];
+        const float h = s.cell == CTCASR_CELL_RNN_TANH ? tanhf(z) : fmaxf(z, 0.f);
+        g[u] = h;
+        *yo = h;
+    }
+}
+
+// backward cell step: consumes dy[t], dh_rec (recurrent gradient from the step processed before),
+// dc carry; replaces the activations in `gates` by dz.  Same grid / step convention, but the
+// steps run in reverse processing order: i = T-1 .. 0.
+__global__ void rnn_cell_bwd_kernel(RnnStep s, int i)
+{
+    const int d = blockIdx.y;
+    const int t = d == 0 ? i : s.T - 1 - i;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.B * s.H) return;
+    const int b = idx / s.H, u = idx % s.H;
+    const int H = s.H, GH = s.G * H;
+    float *g = s.gates + ((size_t)t * s.B + b) * 2 * GH + (size_t)d * GH;
+    const bool live = !s.use_len || t < s.seq_len[b];
+    float *dhr = s.dh_rec + ((size_t)d * s.B + b) * H + u;
+    const float dh = s.dy[((size_t)t * s.B + b) * 2 * H + (size_t)d * H + u] + (i == s.T - 1 ? 0.f : *dhr);
+    const int tp = d == 0 ? t - 1 : t + 1;
+    const bool has_prev = i > 0;
+    if (s.cell == CTCASR_CELL_LSTM) {
+        float *dcc = s.dc_carry + ((size_t)d * s.B + b) * H + u;
+        if (!live) { g[u] = 0.f; g[H + u] = 0.f; g[2 * H + u] = 0.f; g[3 * H + u] = 0.f; *dcc = 0.f; return; }
+        const float gi = g[u], gj = g[H + u], gf = g[2 * H + u], go = g[3 * H + u];
+        const float c = s.cstate[((size_t)t * s.B + b) * 2 * H + (size_t)d * H + u];
+        const float cp = has_prev ? s.cstate[((size_t)tp * s.B + b) * 2 * H + (size_t)d * H + u] : 0.f;
+        const float tc = tanhf(c);
+        const float dc = dh * go * (1.f - tc * tc) + (i == s.T - 1 ? 0.f : *dcc);
+        g[u] = dc * gj * gi * (1.f - gi);
+        g[H + u] = dc * gi * (1.f - gj * gj);
+        g[2 * H + u] = dc * cp * gf * (1.f - gf);
+        g[3 * H + u] = dh * tc * go * (1.f - go);
+        *dcc = dc * gf;
+    } else {
+        if (!live) { g[u] = 0.f; return; }
+        const float h = g[u];
+        g[u] = s.cell == CTCASR_CELL_RNN_TANH ? dh * (1.f - h * h) : (h > 0.f ? dh : 0.f);
+    }
+}
+
+int rnn_cell_fwd(const RnnStep &s, int i, cudaStream_t stream)
+{
+    dim3 grid(ceil_div(s.B * s.H, 256), 2);
+    rnn_cell_fwd_kernel<<<grid, 256, 0, stream>>>(s, i);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+int rnn_cell_bwd(const RnnStep &s, int i, cudaStream_t stream)
+{
+    dim3 grid(ceil_div(s.B * s.H, 256), 2);
+    rnn_cell_bwd_kernel<<<grid, 256, 0, stream>>>(s, i);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+// ---- Adam (TF1 formulation), one pass over the flat buffers -----------------------------------
+__global__ void adam_kernel(float *__restrict__ p, float *__restrict__ m, float *__restrict__ v,
+                            const float *__restrict__ g, size_t n, float lr_t, float b1, float b2, float eps,
+                            float gscale)
+{
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4 *>(p)[i], mm = reinterpret_cast<float4 *>(m)[i];
+        float4 vv = reinterpret_cast<float4 *>(v)[i];
+        const float4 gg = reinterpret_cast<const float4 *>(g)[i];
+        float *pa = &pp.x, *ma = &mm.x, *va = &vv.x;
+        const float *ga = &gg.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gj = ga[j] * gscale;
+            ma[j] = b1 * ma[j] + (1.f - b1) * gj;
+            va[j] = b2 * va[j] + (1.f - b2) * gj * gj;
+            pa[j] -= lr_t * ma[j] / (sqrtf(va[j]) + eps);
+        }
+        reinterpret_cast<float4 *>(p)[i] = pp;
+        reinterpret_cast<float4 *>(m)[i] = mm;
+        reinterpret_cast<float4 *>(v)[i] = vv;
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+            const float gj = g[i] * gscale;
+            m[i] = b1 * m[i] + (1.f - b1) * gj;
+            v[i] = b2 * v[i] + (1.f - b2) * gj * gj;
+            p[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
+        }
+}
+
+}  // namespace ctcasr
+
+using namespace ctcasr;
+
+extern "C" int ctcasr_transpose01(const float *in, float *out, int A, int B, int C, void *stream)
+{
+    CTCASR_REQUIRE(in && out && A >= 0 && B >= 0 && C >= 1, "transpose01: bad args");
+    const size_t total = (size_t)A * B * C;
+    if (total == 0) return CTCASR_OK;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    transpose01_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, A, B, C);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+extern "C" int ctcasr_adam(float *p, float *m, float *v, const float *g, size_t n, int step,
+                           float lr, float beta1, float beta2, float eps, float grad_scale, void *stream)
+{
+    CTCASR_REQUIRE(p && m && v && g && step >= 1, "adam: bad args");
+    CTCASR_REQUIRE(((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) % 16 == 0, "adam: buffers must be 16-B aligned");
+    if (n == 0) return CTCASR_OK;
+    const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step)));
+    const size_t want = (n / 4 + 255) / 256;
+    const int blocks = (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, lr_t, beta1, beta2, eps, grad_scale);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}

@@ -1,0 +1,165 @@
+// rnn.cu — one bidirectional recurrent layer, forward and backward (C-ABI entry points).
+//
+// Replaces a layer of tfc.rnn.stack_bidirectional_dynamic_rnn (asr/model.py:176-183) /
+// tfc.cudnn_rnn.Cudnn* (asr/model.py:194-215).  Structure on the GPU:
+//   1. hoisted input GEMM   P[T*B, 2GH] = X[T*B, in] Wx[in, 2GH] + bias   (both directions at once)
+//   2. the recurrence       z_t = P_t + h_{t-1} Wh  ->  cell math, T strictly sequential steps,
+//                           fw and bw directions advancing together
+//   3. backward: reverse recurrence producing dz in place of the saved activations, then three
+//      large GEMMs (dWx = X^T dz, dWh = H_prev^T dz, dX = dz Wx^T) and a column sum (dbias).
+// Step 2 has two implementations: the stepwise one in this file (any shape / cell, two launches
+// per frame) and the persistent tcgen05 LSTM kernel in lstm_tc.cu (selected when eligible).
+#include "gemm.cuh"
+#include "rnn.cuh"
+#include "lstm_tc.cuh"
+
+using namespace ctcasr;
+
+namespace {
+struct Reserve { float *gates; float *cstate; size_t bytes; };
+Reserve carve_reserve(void *base, int T, int B, int H, int G)
+{
+    Reserve r;
+    const size_t ng = align_up((size_t)T * B * 2 * G * H * sizeof(float), 256);
+    const size_t nc = align_up((size_t)T * B * 2 * H * sizeof(float), 256);
+    r.gates = reinterpret_cast<float *>(base);
+    r.cstate = reinterpret_cast<float *>(reinterpret_cast<char *>(base) + ng);
+    r.bytes = ng + nc;
+    return r;
+}
+}  // namespace
+
+extern "C" size_t ctcasr_birnn_reserve_bytes(int T, int B, int in, int H, int cell)
+{
+    (void)in;
+    return carve_reserve(nullptr, T, B, H, num_gates(cell)).bytes;
+}
+
+extern "C" size_t ctcasr_birnn_workspace_bytes(int T, int B, int in, int H, int cell)
+{
+    (void)T; (void)in;
+    // dh_rec + dc_carry (stepwise) and the persistent kernel's h exchange / barrier area
+    return align_up((size_t)4 * B * H * sizeof(float), 256) + lstm_tc_workspace_bytes(B, H) + (cell == CTCASR_CELL_LSTM ? 0 : 0);
+}
+
+extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const float *wx, const float *wh,
+                                const float *bias, float *y, void *reserve,
+                                int T, int B, int in, int H, int cell, int use_len, float forget_bias,
+                                int compute, void *ws, size_t ws_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTCASR_REQUIRE(x && wx && wh && bias && y && reserve, "birnn_fwd: null pointer");
+    CTCASR_REQUIRE(T >= 1 && B >= 1 && in >= 1 && H >= 1, "birnn_fwd: bad dims");
+    CTCASR_REQUIRE(!use_len || seq_len, "birnn_fwd: use_len needs seq_len");
+    if (cell == CTCASR_CELL_GRU) return fail(CTCASR_ERR_UNSUPPORTED, "birnn: GRU cell not implemented yet");
+    CTCASR_REQUIRE(cell >= 0 && cell <= 2, "birnn_fwd: bad cell %d", cell);
+    if (ws_bytes < ctcasr_birnn_workspace_bytes(T, B, in, H, cell)) return fail(CTCASR_ERR_WORKSPACE, "birnn_fwd: workspace too small");
+    const int G = num_gates(cell), GH = G * H;
+    Reserve r = carve_reserve(reserve, T, B, H, G);
+
+    // 1. hoisted input GEMM with the bias folded into the epilogue
+    GemmArgs g;
+    g.A[0] = x; g.B[0] = wx; g.C[0] = r.gates;
+    g.M = T * B; g.N = 2 * GH; g.K = in; g.lda = in; g.ldb = 2 * GH; g.ldc = 2 * GH;
+    g.epi.mode = EPI_BIAS_ACT; g.epi.bias = bias; g.epi.act = 0;
+    int rc = gemm(g, compute, stream);
+    if (rc != CTCASR_OK) return rc;
+
+    // 2. recurrence
+    if (compute == CTCASR_COMPUTE_TF32 && lstm_tc_eligible(T, B, H, cell)) {
+        char *wsb = reinterpret_cast<char *>(ws) + align_up((size_t)4 * B * H * sizeof(float), 256);
+        return lstm_tc_fwd(seq_len, wh, r.gates, r.cstate, y, T, B, H, use_len, forget_bias, wsb, stream);
+    }
+    RnnStep s;
+    s.T = T; s.B = B; s.H = H; s.G = G; s.cell = cell; s.use_len = use_len; s.forget_bias = forget_bias;
+    s.seq_len = seq_len; s.gates = r.gates; s.cstate = r.cstate; s.y = y; s.dy = nullptr;
+    s.dh_rec = nullptr; s.dc_carry = nullptr;
+    for (int i = 0; i < T; ++i) {
+        if (i > 0) {
+            GemmArgs h;
+            h.nz = 2; h.M = B; h.N = GH; h.K = H; h.lda = 2 * H; h.ldb = GH; h.ldc = 2 * GH;
+            h.epi.accumulate = 1;
+            const int tf = i, tb = T - 1 - i;
+            h.A[0] = y + (size_t)(tf - 1) * B * 2 * H;            h.A[1] = y + (size_t)(tb + 1) * B * 2 * H + H;
+            h.B[0] = wh;                                          h.B[1] = wh + (size_t)H * GH;
+            h.C[0] = r.gates + (size_t)tf * B * 2 * GH;           h.C[1] = r.gates + (size_t)tb * B * 2 * GH + GH;
+            rc = gemm_simt(h, stream);
+            if (rc != CTCASR_OK) return rc;
+        }
+        rc = rnn_cell_fwd(s, i, stream);
+        if (rc != CTCASR_OK) return rc;
+    }
+    return CTCASR_OK;
+}
+
+extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const float *wx, const float *wh,
+                                const float *y, void *reserve, const float *dy,
+                                float *dx, float *dwx, float *dwh, float *dbias,
+                                int T, int B, int in, int H, int cell, int use_len,
+                                int compute, void *ws, size_t ws_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTCASR_REQUIRE(x && wx && wh && y && reserve && dy && dwx && dwh && dbias, "birnn_bwd: null pointer");
+    CTCASR_REQUIRE(T >= 1 && B >= 1 && in >= 1 && H >= 1, "birnn_bwd: bad dims");
+    if (cell == CTCASR_CELL_GRU) return fail(CTCASR_ERR_UNSUPPORTED, "birnn: GRU cell not implemented yet");
+    CTCASR_REQUIRE(cell >= 0 && cell <= 2, "birnn_bwd: bad cell %d", cell);
+    if (ws_bytes < ctcasr_birnn_workspace_bytes(T, B, in, H, cell)) return fail(CTCASR_ERR_WORKSPACE, "birnn_bwd: workspace too small");
+    const int G = num_gates(cell), GH = G * H;
+    Reserve r = carve_reserve(reserve, T, B, H, G);
+    int rc;
+
+    if (compute == CTCASR_COMPUTE_TF32 && lstm_tc_eligible(T, B, H, cell)) {
+        char *wsb = reinterpret_cast<char *>(ws) + align_up((size_t)4 * B * H * sizeof(float), 256);
+        rc = lstm_tc_bwd(seq_len, wh, r.gates, r.cstate, dy, T, B, H, use_len, wsb, stream);
+        if (rc != CTCASR_OK) return rc;
+    } else {
+        RnnStep s;
+        s.T = T; s.B = B; s.H = H; s.G = G; s.cell = cell; s.use_len = use_len; s.forget_bias = 0.f;
+        s.seq_len = seq_len; s.gates = r.gates; s.cstate = r.cstate; s.y = const_cast<float *>(y); s.dy = dy;
+        s.dh_rec = reinterpret_cast<float *>(ws);
+        s.dc_carry = s.dh_rec + (size_t)2 * B * H;
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)4 * B * H * sizeof(float), stream));
+        for (int i = T - 1; i >= 0; --i) {
+            rc = rnn_cell_bwd(s, i, stream);
+            if (rc != CTCASR_OK) return rc;
+            if (i > 0) {     // dh_rec[d] = dz_t[d] Wh[d]^T
+                GemmArgs h;
+                h.nz = 2; h.M = B; h.N = H; h.K = GH; h.tb = 1; h.lda = 2 * GH; h.ldb = GH; h.ldc = H;
+                const int tf = i, tb = T - 1 - i;
+                h.A[0] = r.gates + (size_t)tf * B * 2 * GH;       h.A[1] = r.gates + (size_t)tb * B * 2 * GH + GH;
+                h.B[0] = wh;                                      h.B[1] = wh + (size_t)H * GH;
+                h.C[0] = s.dh_rec;                                h.C[1] = s.dh_rec + (size_t)B * H;
+                rc = gemm_simt(h, stream);
+                if (rc != CTCASR_OK) return rc;
+            }
+        }
+    }
+    // r.gates now holds dz [T*B, 2GH]
+    rc = colsum(r.gates, T * B, 2 * GH, 2 * GH, dbias, stream);
+    if (rc != CTCASR_OK) return rc;
+    {   // dWx[in, 2GH] = X^T dz
+        GemmArgs g;
+        g.A[0] = x; g.B[0] = r.gates; g.C[0] = dwx; g.ta = 1;
+        g.M = in; g.N = 2 * GH; g.K = T * B; g.lda = in; g.ldb = 2 * GH; g.ldc = 2 * GH;
+        rc = gemm(g, compute, stream);
+        if (rc != CTCASR_OK) return rc;
+    }
+    if (T > 1) {   // dWh[d][H, GH] = H_prev^T dz_d ; fw: (y[t-1], dz[t]), bw: (y[t+1], dz[t])
+        GemmArgs g;
+        g.nz = 2; g.ta = 1; g.M = H; g.N = GH; g.K = (T - 1) * B; g.lda = 2 * H; g.ldb = 2 * GH; g.ldc = GH;
+        g.A[0] = y;                              g.B[0] = r.gates + (size_t)B * 2 * GH;   g.C[0] = dwh;
+        g.A[1] = y + (size_t)B * 2 * H + H;      g.B[1] = r.gates + GH;                   g.C[1] = dwh + (size_t)H * GH;
+        rc = gemm(g, compute, stream);
+        if (rc != CTCASR_OK) return rc;
+    } else {
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(dwh, 0, (size_t)2 * H * GH * sizeof(float), stream));
+    }
+    if (dx) {      // dX[T*B, in] = dz Wx^T
+        GemmArgs g;
+        g.A[0] = r.gates; g.B[0] = wx; g.C[0] = dx; g.tb = 1;
+        g.M = T * B; g.N = in; g.K = 2 * GH; g.lda = 2 * GH; g.ldb = 2 * GH; g.ldc = in;
+        rc = gemm(g, compute, stream);
+        if (rc != CTCASR_OK) return rc;
+    }
+    return CTCASR_OK;
+}

@@ -1,0 +1,146 @@
+/*
+ * ctcasr.h — C-ABI of libctcasr.so, the B200 (sm_100a) CTC training core.
+ *
+ * The reference (mdangschat/ctc-asr) has no native layer: its hot path is two Python functions
+ * that call TensorFlow library ops.  Each entry point below replaces one of those call sites
+ * (cited as asr/<file>:<line> of the reference) and is what a ctypes/cffi binding on the
+ * reference side would bind (see INTEGRATION.md for that stub).
+ *
+ * Conventions
+ *   - plain C, no torch types; all tensor pointers are DEVICE pointers owned by the caller,
+ *     fp32 row-major unless noted; activations are time-major ([T, B, C], row = t*B + b).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
+ *     nothing, and keeps no global mutable state apart from the last-error string and lazily
+ *     created tensor-map / attribute caches.
+ *   - return value: 0 = CTCASR_OK, negative = error (ctcasr_last_error() has the text).
+ *     Device-detected per-utterance conditions are reported through `status` arrays.
+ *   - `ws` is caller-provided scratch of at least *_workspace_bytes(...) bytes, 256-B aligned.
+ */
+#ifndef CTCASR_H
+#define CTCASR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTCASR_ABI_VERSION 1
+
+enum {
+    CTCASR_OK = 0,
+    CTCASR_ERR_INVALID = -1,      /* bad argument (shape, alignment, null pointer) */
+    CTCASR_ERR_UNSUPPORTED = -2,  /* legal but not implemented for this shape/cell */
+    CTCASR_ERR_WORKSPACE = -3,    /* ws_bytes too small */
+    CTCASR_ERR_CUDA = -4          /* a CUDA runtime/driver call failed */
+};
+
+/* rnn cell menu = asr/params.py:48-50 / asr/model.py:194-199 */
+enum { CTCASR_CELL_RNN_TANH = 0, CTCASR_CELL_RNN_RELU = 1, CTCASR_CELL_LSTM = 2, CTCASR_CELL_GRU = 3 };
+
+/* arithmetic of the GEMM-shaped work */
+enum {
+    CTCASR_COMPUTE_FP32 = 0,      /* SIMT FFMA, fp32 everywhere (parity mode, any shape) */
+    CTCASR_COMPUTE_TF32 = 1       /* tcgen05 kind::tf32, fp32 storage + fp32 accumulate in TMEM */
+};
+
+/* per-utterance CTC status words (TF raises InvalidArgumentError for 1..3) */
+enum { CTCASR_CTC_OK = 0, CTCASR_CTC_INFEASIBLE = 1, CTCASR_CTC_BAD_LABEL = 2, CTCASR_CTC_BAD_LENGTH = 3 };
+
+int ctcasr_abi_version(void);
+const char *ctcasr_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t ctcasr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * CTC loss forward-backward.  Replaces tf.nn.ctc_loss at asr/model.py:259-264
+ * (ctc_merge_repeated=True, preprocess_collapse_repeated=False, time_major=True) plus the
+ * 1/B of tf.reduce_mean (asr/model.py:267) through `grad_scale`.
+ *   logits        [T,B,V]   labels [B,label_stride] int32 (0-padded like asr/model.py:71 strips)
+ *   label_len[B], seq_len[B] int32;   blank = V-1 in the reference (asr/labels.py:6)
+ *   loss[B]       -log p(labels|logits) per utterance (+inf when status != 0)
+ *   grad          [T,B,V] or NULL:  grad_scale * d loss_b / d logits, zero for t >= seq_len[b]
+ *   status[B]     CTCASR_CTC_*
+ * -------------------------------------------------------------------------------------------- */
+size_t ctcasr_ctc_workspace_bytes(int T, int B, int V, int max_label_len);
+int ctcasr_ctc_loss(const float *logits, int T, int B, int V, int blank,
+                    const int32_t *labels, int label_stride, const int32_t *label_len,
+                    const int32_t *seq_len, float *loss, float *grad, float grad_scale,
+                    int32_t *status, int max_label_len, void *ws, size_t ws_bytes, void *stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies in, runs, copies out, synchronises.
+ * This is the drop-in for the reference's CPU-only CTCLoss kernel, which receives the logits by
+ * D2H copy every step. */
+int ctcasr_ctc_loss_host(const float *logits, int T, int B, int V, int blank,
+                         const int32_t *labels, int label_stride, const int32_t *label_len,
+                         const int32_t *seq_len, float *loss, float *grad, float grad_scale,
+                         int32_t *status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Greedy CTC decode (argmax, merge repeats, drop blank) — the parity-checked stand-in for
+ * decode_fn's tf.nn.ctc_beam_search_decoder call at asr/model.py:292-296.
+ *   out_ids [B,T] int32 (-1 padded), out_len[B]
+ * -------------------------------------------------------------------------------------------- */
+int ctcasr_greedy_decode(const float *logits, int T, int B, int V, int blank,
+                         const int32_t *seq_len, int32_t *out_ids, int32_t *out_len, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layer.  Replaces tf.layers.dense + tf.minimum + tf.layers.dropout at
+ * asr/util/tf_contrib.py:52-58 and asr/model.py:220-226,232.
+ *   y[M,N] = dropout( act( x[M,K] w[K,N] + bias[N] ) ),  act: 0 linear, 1 min(relu(.), cutoff)
+ *   dropout keep-mask = counter hash of (seed, m*N+n); rate 0 disables it.
+ * Backward: dy[M,N] -> dx[M,K] (nullable), dw[K,N], db[N] (overwritten).  `y` is the forward
+ * output (the activation/dropout mask is recovered from it).  dy is clobbered (becomes dz).
+ * -------------------------------------------------------------------------------------------- */
+int ctcasr_dense_fwd(const float *x, const float *w, const float *bias, float *y,
+                     int M, int K, int N, int act, float cutoff, float drop_rate, uint32_t seed,
+                     int compute, void *stream);
+int ctcasr_dense_bwd(const float *x, const float *w, const float *y, float *dy,
+                     float *dx, float *dw, float *db, int M, int K, int N,
+                     int act, float cutoff, float drop_rate, uint32_t seed,
+                     int compute, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One bidirectional recurrent layer.  Replaces one layer of
+ * tfc.rnn.stack_bidirectional_dynamic_rnn (asr/model.py:176-183, cells from
+ * asr/util/tf_contrib.py:183-189) / tfc.cudnn_rnn.Cudnn* (asr/model.py:194-215).
+ *   x [T,B,in]  ->  y [T,B,2H]  (fw | bw)
+ *   wx [in, 2*G*H] (fw gate columns | bw gate columns), wh [2][H, G*H], bias [2*G*H]
+ *   LSTM gate order i, j, f, o with forget_bias (TF LSTMCell); G = 4 (LSTM), 1 (tanh/relu)
+ *   use_len != 0: dynamic_rnn(sequence_length) semantics (zero output + frozen state past
+ *                 seq_len[b]; backward cell starts at seq_len[b]-1).  0: every frame (cuDNN path).
+ *   reserve: >= ctcasr_birnn_reserve_bytes(); written by fwd, consumed AND clobbered by bwd.
+ * Backward: dy [T,B,2H] -> dx [T,B,in] (nullable), dwx, dwh, dbias (overwritten).
+ * -------------------------------------------------------------------------------------------- */
+size_t ctcasr_birnn_reserve_bytes(int T, int B, int in, int H, int cell);
+size_t ctcasr_birnn_workspace_bytes(int T, int B, int in, int H, int cell);
+int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const float *wx, const float *wh,
+                     const float *bias, float *y, void *reserve,
+                     int T, int B, int in, int H, int cell, int use_len, float forget_bias,
+                     int compute, void *ws, size_t ws_bytes, void *stream);
+int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const float *wx, const float *wh,
+                     const float *y, void *reserve, const float *dy,
+                     float *dx, float *dwx, float *dwh, float *dbias,
+                     int T, int B, int in, int H, int cell, int use_len,
+                     int compute, void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Plumbing around the path
+ * -------------------------------------------------------------------------------------------- */
+/* [A,B,C] -> [B,A,C]: batch-major sequences (asr/model.py:129) <-> the time-major layout used
+ * internally and by the logits (asr/model.py:233) */
+int ctcasr_transpose01(const float *in, float *out, int A, int B, int C, void *stream);
+/* Adam, TF1 formulation (tf.train.AdamOptimizer, asr/model.py:79-83) on a flat buffer;
+ * grad_scale multiplies g first (e.g. 1/world_size after a sum all-reduce). */
+int ctcasr_adam(float *p, float *m, float *v, const float *g, size_t n, int step,
+                float lr, float beta1, float beta2, float eps, float grad_scale, void *stream);
+/* C[M,N] = op(A) op(B): generic GEMM used by the layers above, exposed for tests.
+ *   ta == 0: A is [M,K] row-major, ta != 0: A is [K,M];  tb == 0: B is [K,N], tb != 0: B is [N,K] */
+int ctcasr_gemm(const float *A, const float *B, float *C, int M, int N, int K,
+                int ta, int tb, int lda, int ldb, int ldc, int accumulate, int compute, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCASR_H */

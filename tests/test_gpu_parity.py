@@ -1,0 +1,305 @@
+"""GPU parity tests proper: every call goes through the C-ABI (libctcasr.so) and is checked against
+the CPU oracle (oracle/) on the same seeded inputs, against the committed golden vectors, and — at
+BASELINE.json's full sizes — through size-independent properties.
+
+Tolerances (north_star): integer/index work bit-exact; floating point within 1e-3 relative
+(gradients: max abs error normalised by max |oracle gradient|)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ctc_asr_b200 import _lib, ops, synthetic
+from ctc_asr_b200.params import ModelConfig
+from oracle import model_ref, ref
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ------------------------------------------------------------------------------------------ CTC
+def _ctc_gpu(logits, labels, ll, sl, blank=None, scale=1.0):
+    loss, grad, status = ops.ctc_loss(dev(logits, torch.float32), dev(labels, torch.int32), dev(ll, torch.int32),
+                                      dev(sl, torch.int32), blank=blank, grad_scale=scale)
+    torch.cuda.synchronize()
+    return loss.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy()
+
+
+def test_ctc_tf_known_answer(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "ctc_tf_known_answer.json")))
+    T, V, utts = g["T"], g["V"], g["utterances"]
+    B = len(utts)
+    logits = np.zeros((T, B, V), np.float32)
+    labels = np.zeros((B, 5), np.int32)
+    ll = np.zeros(B, np.int32)
+    for b, u in enumerate(utts):
+        logits[:, b] = np.log(np.asarray(u["probs"]))
+        labels[b, :len(u["labels"])] = u["labels"]
+        ll[b] = len(u["labels"])
+    loss, grad, status = _ctc_gpu(logits, labels, ll, np.full(B, T, np.int32), blank=g["blank"])
+    assert (status == 0).all()
+    for b, u in enumerate(utts):
+        assert abs(loss[b] - u["loss"]) < 1e-4 * u["loss"]
+    np.testing.assert_allclose(grad[0, 0], utts[0]["grad_row0"], atol=2e-5)
+
+
+def test_ctc_host_buffer_entry_point(golden_dir):
+    """ctcasr_ctc_loss_host: the drop-in for TF's CPU CTCLoss op (host logits in, host grad out)."""
+    rng = np.random.default_rng(1)
+    T, B, V = 40, 5, 29
+    logits = (rng.standard_normal((T, B, V)) * 2).astype(np.float32)
+    labels, ll = synthetic.make_labels(rng, B, np.array([3, 9, 1, 12, 5]), 40)
+    sl = np.array([40, 33, 7, 40, 21], np.int32)
+    loss, grad, status = np.zeros(B, np.float32), np.zeros_like(logits), np.zeros(B, np.int32)
+    lib = _lib.load()
+    vp = lambda a: a.ctypes.data_as(__import__("ctypes").c_void_p)
+    rc = lib.ctcasr_ctc_loss_host(vp(logits), T, B, V, V - 1, vp(labels), labels.shape[1], vp(ll), vp(sl),
+                                  vp(loss), vp(grad), 1.0, vp(status))
+    assert rc == 0, lib.ctcasr_last_error()
+    ol, og, _ = ref.ctc_loss(logits.astype(np.float64), labels, ll, sl)
+    assert rel_err(loss, ol) < RTOL and rel_err(grad, og) < RTOL
+
+
+@pytest.mark.parametrize("T,B,L", [(50, 7, 20), (200, 9, 30), (333, 4, 100)])
+def test_ctc_ragged_vs_oracle(T, B, L):
+    rng = np.random.default_rng(T)
+    V = 29
+    logits = (rng.standard_normal((T, B, V)) * 3).astype(np.float32)
+    sl = rng.integers(1, T + 1, B).astype(np.int32)
+    sl[0] = T
+    ll = np.minimum(rng.integers(0, L + 1, B), sl // 2).astype(np.int32)
+    labels, ll = synthetic.make_labels(rng, B, ll, sl, lmax=L)
+    loss, grad, status = _ctc_gpu(logits, labels, ll, sl, scale=0.25)
+    ol, og, ost = ref.ctc_loss(logits.astype(np.float64), labels, ll, sl)
+    assert (status == ost).all() and (status == 0).all()
+    assert rel_err(loss, ol) < RTOL
+    assert rel_err(grad, og * 0.25) < RTOL
+    for b in range(B):
+        assert not grad[sl[b]:, b].any()            # zero gradient past the utterance's length
+
+
+def test_ctc_long_labels_multi_state_per_thread():
+    """L = 422 is the corpus maximum (README.md:169): S = 845 > 480 threads per group."""
+    rng = np.random.default_rng(9)
+    T, B, V, L = 900, 2, 29, 422
+    logits = (rng.standard_normal((T, B, V)) * 2).astype(np.float32)
+    labels, ll = synthetic.make_labels(rng, B, np.array([422, 300]), T)
+    sl = np.array([900, 700], np.int32)
+    loss, grad, status = _ctc_gpu(logits, labels, ll, sl)
+    ol, og, _ = ref.ctc_loss(logits.astype(np.float64), labels, ll, sl)
+    assert (status == 0).all() and rel_err(loss, ol) < RTOL and rel_err(grad, og) < RTOL
+
+
+def test_ctc_bench_length_stays_within_tolerance():
+    """cfg5 geometry (T=1700, L=84): per-chunk re-basing keeps fp32 within 1e-3 of the fp64 oracle."""
+    rng = np.random.default_rng(5)
+    T, B, V = 1700, 3, 29
+    logits = (rng.standard_normal((T, B, V)) * 3).astype(np.float32)
+    labels, ll = synthetic.make_labels(rng, B, 84, T)
+    sl = np.full(B, T, np.int32)
+    loss, grad, status = _ctc_gpu(logits, labels, ll, sl)
+    ol, og, _ = ref.ctc_loss(logits.astype(np.float64), labels, ll, sl)
+    assert (status == 0).all() and rel_err(loss, ol) < 1e-5 and rel_err(grad, og) < RTOL
+
+
+def test_ctc_error_statuses_and_empty():
+    rng = np.random.default_rng(0)
+    T, B, V = 4, 5, 5
+    logits = rng.standard_normal((T, B, V)).astype(np.float32)
+    labels = np.array([[1, 1, 1], [4, 0, 0], [1, 2, 0], [1, 0, 0], [0, 0, 0]], np.int32)
+    ll = np.array([3, 1, 2, 1, 0], np.int32)
+    sl = np.array([4, 4, 9, 0, 0], np.int32)
+    loss, grad, status = _ctc_gpu(logits, labels, ll, sl, blank=4)
+    ol, og, ost = ref.ctc_loss(logits.astype(np.float64), labels, ll, sl, blank=4)
+    assert status.tolist() == ost.tolist() == [1, 2, 3, 1, 0]
+    assert np.isinf(loss[:4]).all() and loss[4] == 0.0 and not grad.any()
+
+
+def test_ctc_full_size_properties():
+    """cfg5 at full size (B=512, T=1700, L=84): per-frame gradient rows sum to 0 (softmax minus a
+    posterior that sums to 1) and a seeded sample of utterances matches the oracle."""
+    rng = np.random.default_rng(0)
+    T, B, V, L = 1700, 512, 29, 84
+    logits = (rng.standard_normal((T, B, V)) * 3).astype(np.float32)
+    labels, ll = synthetic.make_labels(rng, B, L, T)
+    sl = np.full(B, T, np.int32)
+    lg = dev(logits)
+    loss, grad, status = ops.ctc_loss(lg, dev(labels), dev(ll), dev(sl))
+    assert int(status.abs().sum()) == 0
+    rowsum = grad.sum(2).abs().max().item()
+    assert rowsum < 1e-4, rowsum
+    pick = [0, 17, 255, 511]
+    ol, og, _ = ref.ctc_loss(logits[:, pick].astype(np.float64), labels[pick], ll[pick], sl[pick])
+    assert rel_err(loss.cpu().numpy()[pick], ol) < 1e-5
+    assert rel_err(grad.cpu().numpy()[:, pick], og) < RTOL
+
+
+def test_greedy_decode_bit_exact():
+    rng = np.random.default_rng(2)
+    T, B, V = 300, 33, 29
+    logits = rng.standard_normal((T, B, V)).astype(np.float32)
+    logits[5, 0, 3] = logits[5, 0, 7] = 9.0          # exact tie: first max wins
+    logits[10:40, 1, :] = 0.0                        # all-equal frames -> class 0 repeated
+    sl = rng.integers(0, T + 1, B).astype(np.int32)
+    sl[0] = T
+    ids, n = ops.greedy_decode(dev(logits), dev(sl))
+    oi, on = ref.greedy_decode(logits, sl)
+    assert (n.cpu().numpy() == on).all()
+    assert (ids.cpu().numpy() == oi).all()
+
+
+# ------------------------------------------------------------------------------------ GEMM / dense
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_simt_all_orientations(ta, tb):
+    rng = np.random.default_rng(3)
+    M, N, K = 77, 45, 130
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    c = ops.gemm(dev(a), dev(b), ta=ta, tb=tb).cpu().numpy()
+    want = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    assert rel_err(c, want) < 1e-5
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.3])
+def test_dense_fwd_bwd_vs_oracle(rate):
+    rng = np.random.default_rng(4)
+    M, K, N = 150, 80, 96
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((K, N)) * 0.3).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    dy = rng.standard_normal((M, N)).astype(np.float32)
+    y = ops.dense_fwd(dev(x), dev(w), dev(b), act=1, cutoff=2.0, drop_rate=rate, seed=7)
+    oy = ref.dense_fwd(x.astype(np.float64), w, b, act=1, cutoff=2.0, drop_rate=rate, seed=7)
+    assert rel_err(y.cpu().numpy(), oy) < 1e-5
+    assert ((y.cpu().numpy() == 0) == (oy == 0)).mean() > 0.9999      # identical keep / clip masks
+    dw, db, dx = torch.empty(K, N).cuda(), torch.empty(N).cuda(), torch.empty(M, K).cuda()
+    ops.dense_bwd(dev(x), dev(w), y, dev(dy), dw, db, dx=dx, act=1, cutoff=2.0, drop_rate=rate, seed=7)
+    odx, odw, odb = ref.dense_bwd(x.astype(np.float64), w, oy, dy, act=1, cutoff=2.0, drop_rate=rate, seed=7)
+    assert rel_err(dw.cpu().numpy(), odw) < 1e-4
+    assert rel_err(db.cpu().numpy(), odb) < 1e-4
+    assert rel_err(dx.cpu().numpy(), odx) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ BiRNN
+@pytest.mark.parametrize("cell", ["rnn_tanh", "rnn_relu", "lstm"])
+@pytest.mark.parametrize("use_len", [True, False])
+def test_birnn_layer_vs_oracle(cell, use_len):
+    rng = np.random.default_rng(6)
+    T, B, nin, H = 23, 5, 12, 20
+    cid = ref.CELL_IDS[cell]
+    G = ref.NUM_GATES[cid]
+    x = rng.standard_normal((T, B, nin)).astype(np.float32)
+    sl = np.array([23, 20, 11, 3, 1], np.int32)
+    wx = (rng.standard_normal((nin, 2 * G * H)) * 0.3).astype(np.float32)
+    wh = (rng.standard_normal((2, H, G * H)) * 0.3).astype(np.float32)
+    bias = (rng.standard_normal(2 * G * H) * 0.1).astype(np.float32)
+    dy = rng.standard_normal((T, B, 2 * H)).astype(np.float32)
+    rb, _ = ops.birnn_sizes(T, B, nin, H, cid)
+    reserve = torch.empty(rb, dtype=torch.uint8, device="cuda")
+    y = torch.empty((T, B, 2 * H), device="cuda")
+    X, SL, WX, WH, BI = dev(x), dev(sl), dev(wx), dev(wh), dev(bias)
+    ops.birnn_fwd(X, SL, WX, WH, BI, y, reserve, cid, use_len)
+    oy, og, oc = ref.birnn_fwd(x.astype(np.float64), sl, wx, wh, bias, cid, use_len=use_len)
+    assert rel_err(y.cpu().numpy(), oy) < 1e-5
+    dx = torch.empty((T, B, nin), device="cuda")
+    dwx, dwh, db = torch.empty_like(WX), torch.empty_like(WH), torch.empty_like(BI)
+    ops.birnn_bwd(X, SL, WX, WH, y, reserve, dev(dy), dx, dwx, dwh, db, cid, use_len)
+    odx, odwx, odwh, odb = ref.birnn_bwd(x.astype(np.float64), sl, wx, wh, oy, og, oc, dy, cid, use_len=use_len)
+    for got, want, name in [(dx, odx, "dx"), (dwx, odwx, "dwx"), (dwh, odwh, "dwh"), (db, odb, "dbias")]:
+        assert rel_err(got.cpu().numpy(), want) < 1e-4, name
+
+
+def test_adam_vs_oracle():
+    rng = np.random.default_rng(8)
+    n = 1003
+    p, g = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    P, M, V, G = dev(p), dev(m), dev(v), dev(g)
+    po, mo, vo = p.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    for step in (1, 2, 3):
+        ops.adam(P, M, V, G, step, 1e-3, 0.9, 0.999, 1e-8)
+        ref.adam(po, mo, vo, g.astype(np.float64), step, lr=1e-3)
+    assert rel_err(P.cpu().numpy(), po) < 1e-6 and rel_err(V.cpu().numpy(), vo) < 1e-5
+
+
+# --------------------------------------------------------------------------------- whole hot path
+def _whole_path(cfg, B, T, L, ragged, seed=0):
+    from ctc_asr_b200.model import CTCModel
+    params = synthetic.init_params(cfg, seed=1)
+    rng = np.random.default_rng(seed)
+    for k in params:                                   # biases away from 0 so every term matters
+        if k.endswith("bias"):
+            params[k] = (rng.standard_normal(params[k].shape) * 0.05).astype(np.float32)
+    x, sl, lab, ll = synthetic.fixed_batch(B, T, L, F=cfg.num_features, seed=seed)
+    if ragged:
+        sl = np.maximum(T - 7 * np.arange(B), 2 * L + 2).astype(np.int32)
+        for b in range(B):
+            x[b, sl[b]:] = 0
+    model = CTCModel(cfg, params=params)
+    logits, _ = model.inference_fn(torch.from_numpy(x), torch.from_numpy(sl), training=False)
+    loss = model.loss_fn(logits, torch.from_numpy(sl), (torch.from_numpy(lab), torch.from_numpy(ll)))
+    model.backward()
+    torch.cuda.synchronize()
+    oloss, ograds, ologits, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll)
+    assert rel_err(logits.cpu().numpy(), ologits) < RTOL
+    assert abs(float(loss) - oloss) / abs(oloss) < RTOL
+    got = model.grads_numpy()
+    for k, want in ograds.items():
+        assert rel_err(got[k], want) < RTOL, k
+    # greedy ids on the SAME logits are bit-exact (integer work)
+    ids, n = ops.greedy_decode(logits, dev(sl))
+    oi, on = ref.greedy_decode(logits.cpu().numpy(), sl)
+    assert (n.cpu().numpy() == on).all() and (ids.cpu().numpy() == oi).all()
+    return model
+
+
+def test_cfg1_ds1_tanh_single_utterance():
+    """BASELINE cfg1: 2 dense + 1 BiRNN-128 (tanh), one 1 s utterance (99 frames), 80 mel bins."""
+    cfg = ModelConfig(num_layers_dense=2, num_units_dense=128, num_layers_rnn=1, num_units_rnn=128,
+                      rnn_cell="rnn_tanh", cudnn=False, dense_dropout_rate=0.0, compute="fp32")
+    _whole_path(cfg, B=1, T=99, L=16, ragged=False)
+
+
+@pytest.mark.parametrize("cudnn", [False, True])
+def test_small_3d2r2d_lstm_ragged(cudnn):
+    """The cfg2 layout (3 dense + 2 BiLSTM + 2 dense) at a size the oracle finishes in seconds."""
+    cfg = ModelConfig(num_layers_dense=3, num_units_dense=64, num_layers_rnn=2, num_units_rnn=32,
+                      rnn_cell="lstm", cudnn=cudnn, dense_dropout_rate=0.0, compute="fp32")
+    _whole_path(cfg, B=4, T=60, L=8, ragged=True)
+
+
+def test_train_step_decreases_loss_and_matches_oracle_adam():
+    from ctc_asr_b200.model import CTCModel
+    cfg = ModelConfig(num_layers_dense=2, num_units_dense=48, num_layers_rnn=1, num_units_rnn=24,
+                      rnn_cell="lstm", cudnn=False, dense_dropout_rate=0.0, learning_rate=1e-3, compute="fp32")
+    params = synthetic.init_params(cfg, seed=1)
+    x, sl, lab, ll = synthetic.fixed_batch(3, 40, 6, seed=3)
+    model = CTCModel(cfg, params=params)
+    batch = (torch.from_numpy(x), torch.from_numpy(sl), (torch.from_numpy(lab), torch.from_numpy(ll)))
+    l0 = float(model.train_step(*batch))
+    # one oracle step: same gradients -> same Adam update
+    _, og, _, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll)
+    for k in ("logits/dense/kernel", "rnn/l0/wh"):
+        p = params[k].astype(np.float64).ravel().copy()
+        m, v = np.zeros_like(p), np.zeros_like(p)
+        ref.adam(p, m, v, og[k].ravel().copy(), 1, lr=1e-3)
+        got = model.params_numpy()[k].ravel()
+        assert np.mean(np.abs(got - p) < 2e-5) > 0.99, k     # |g| ~ eps elements may differ
+    for _ in range(5):
+        l1 = float(model.train_step(*batch))
+    assert l1 < l0
