@@ -26,9 +26,9 @@
 namespace ctcasr {
 namespace ctc {
 
-constexpr int kMaxSPT = 4;      // lattice states per thread
-constexpr int kMaxVPT = 4;      // classes per lane in the softmax (V <= 128)
-constexpr int kMaxGT = 480;     // threads per group (alpha / beta)
+constexpr int kMaxSPT = 4;      // lattice states per thread (generic variant)
+constexpr int kMaxGT = 448;     // threads per group (alpha / beta); + 1 helper warp <= 1024
+constexpr int kHelper = 32;     // one producer warp: log-softmax of the next chunk's frames
 
 struct Params {
     const float *logits; int T, B, V, blank;
@@ -49,17 +49,20 @@ struct SmemLayout {
         rowA = o;      o += (size_t)2 * RS * 4;
         rowB = o;      o += (size_t)2 * RS * 4;
         A = o;         o += (size_t)2 * CH * RS * 4;
-        LY = o;        o += (size_t)2 * CH * VP * 4;
+        LY = o;        o += (size_t)((3 * CH * VP + 3) / 4 * 4) * 4;
         red = o;       o += 64 * 4 + 64;
         total = o;
     }
 };
 
+// 3-way log-sum-exp.  Precise expf/logf: the fast intrinsics carry a ~1e-6 bias per step that
+// differs between the alpha and beta recursions and accumulates linearly over T (1.7e-3 of
+// gradient error at T=1700, measured).
 __device__ __forceinline__ float lse3(float a, float b, float c)
 {
     const float m = fmaxf(a, fmaxf(b, c));
     if (m == -INFINITY) return -INFINITY;
-    return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+    return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
 __device__ __forceinline__ void group_bar(int id, int nthreads)
@@ -81,7 +84,7 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // max over a thread group (GT threads, group-local thread id gt, barrier id bar)
-__device__ float group_max(float v, float *red, int gt, int GT, int bar)
+__device__ __forceinline__ float group_max(float v, float *red, int gt, int GT, int bar)
 {
     v = warp_max(v);
     const int w = gt >> 5, nw = GT >> 5;
@@ -93,44 +96,38 @@ __device__ float group_max(float v, float *red, int gt, int GT, int bar)
     return m;
 }
 
-// log-softmax of the frames of chunk c into LY[buf]; one warp per frame, all warps of the CTA.
-__device__ void compute_logy(const Params &p, int b, int Tb, int c, float *LY)
+// log-softmax of the frames of chunk c into LY; ONE LANE PER FRAME (the frame's V logits are a
+// contiguous 4V-byte run), executed by `nthreads` consecutive threads starting at thread `first`.
+// Rows are VP = V|1-padded floats apart so that lanes writing the same class hit distinct banks.
+__device__ __forceinline__ void compute_logy(const Params &p, int b, int Tb, int c, float *LY, int first, int nthreads)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int lo = c * p.CH, hi = min(lo + p.CH, Tb);
-    for (int t = lo + warp; t < hi; t += nwarps) {
+    for (int t = lo + (int)threadIdx.x - first; t < hi; t += nthreads) {
         const float *x = p.logits + ((size_t)t * p.B + b) * p.V;
-        float v[kMaxVPT];
         float m = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < kMaxVPT; ++i) {
-            const int k = lane + 32 * i;
-            v[i] = k < p.V ? __ldg(x + k) : -INFINITY;
-            m = fmaxf(m, v[i]);
-        }
-        m = warp_max(m);
+#pragma unroll 8
+        for (int k = 0; k < p.V; ++k) m = fmaxf(m, __ldg(x + k));
         float e = 0.f;
-#pragma unroll
-        for (int i = 0; i < kMaxVPT; ++i) e += (lane + 32 * i < p.V) ? expf(v[i] - m) : 0.f;
-        e = warp_sum(e);
+#pragma unroll 8
+        for (int k = 0; k < p.V; ++k) e += expf(__ldg(x + k) - m);
         const float lse = m + logf(e);
         float *row = LY + (size_t)(t - lo) * p.VP;
-#pragma unroll
-        for (int i = 0; i < kMaxVPT; ++i) {
-            const int k = lane + 32 * i;
-            if (k < p.VP) row[k] = k < p.V ? v[i] - lse : -INFINITY;
-        }
+#pragma unroll 8
+        for (int k = 0; k < p.V; ++k) row[k] = __ldg(x + k) - lse;
     }
 }
 
-__global__ void __launch_bounds__(2 * kMaxGT, 1)
+template <int SPT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 ctc_loss_kernel(const Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    const int GT = p.GT, NT = 2 * GT;
+    const int GT = p.GT, NT = 2 * GT + kHelper;
     const bool is_alpha = tid < GT;
+    const bool is_beta = !is_alpha && tid < 2 * GT;
+    const bool is_helper = tid >= 2 * GT;
     const int gt = is_alpha ? tid : tid - GT;
     const int RS = p.RS, CH = p.CH, V = p.V, VP = p.VP, blank = p.blank;
 
@@ -141,7 +138,7 @@ ctc_loss_kernel(const Params p)
     float *rowA = reinterpret_cast<float *>(smem_raw + L.rowA);   // alpha rows: state s at [s+2]
     float *rowB = reinterpret_cast<float *>(smem_raw + L.rowB);   // primed beta rows: state s at [s]
     float *Abuf = reinterpret_cast<float *>(smem_raw + L.A);      // [2][CH][RS], state s at [s+2]
-    float *LYbuf = reinterpret_cast<float *>(smem_raw + L.LY);    // [2][CH][VP]
+    float *LYbuf = reinterpret_cast<float *>(smem_raw + L.LY);    // [3][CH][VP] ring, chunk c at c % 3
     float *red = reinterpret_cast<float *>(smem_raw + L.red);
     int *flags = reinterpret_cast<int *>(red + 48);               // [0] bad label, [1] repeats
 
@@ -198,20 +195,20 @@ ctc_loss_kernel(const Params p)
     __syncthreads();
     if (tid == 0) {
         // csr_pos filled by a serial stable pass (deterministic summation order later)
-        int *cursor = reinterpret_cast<int *>(LYbuf);     // scratch (VP >= V ints); LY is rewritten before use
+        int *cursor = reinterpret_cast<int *>(LYbuf);     // scratch (>= V ints); LY is rewritten before use
         for (int k = 0; k < V; ++k) cursor[k] = csr_start[k];
         for (int i = 0; i < Ln; ++i) csr_pos[cursor[lab[i]]++] = 2 * i + 1;
     }
     __syncthreads();
 
     // per-thread lattice-state constants
-    int st_lp[kMaxSPT];
-    bool st_skA[kMaxSPT], st_skB[kMaxSPT];
+    int st_lp[SPT];
+    bool st_skA[SPT], st_skB[SPT];
 #pragma unroll
-    for (int q = 0; q < kMaxSPT; ++q) {
+    for (int q = 0; q < SPT; ++q) {
         const int s = gt + q * GT;
         st_lp[q] = blank; st_skA[q] = false; st_skB[q] = false;
-        if (s < S && (s & 1)) {
+        if (!is_helper && s < S && (s & 1)) {
             const int li = s >> 1;
             st_lp[q] = lab[li];
             st_skA[q] = li > 0 && lab[li] != lab[li - 1];
@@ -222,33 +219,36 @@ ctc_loss_kernel(const Params p)
     const int NCH = (Tb + CH - 1) / CH;
     float *ck_b = p.ckpt + (size_t)b * p.NCH * RS;
     double *off_b = p.ckoff + (size_t)b * p.NCH;
+    const size_t LYS = (size_t)CH * VP;
 
     // =========================== phase 1: alpha sweep with checkpoints =========================
     double offA = 0.0;
     int cur = 0;
     if (is_alpha) {       // virtual row t = -1: {0, -inf, ...} reproduces TF's alpha init
 #pragma unroll
-        for (int q = 0; q < kMaxSPT; ++q) {
+        for (int q = 0; q < SPT; ++q) {
             const int s = gt + q * GT;
             if (s < S) rowA[cur * RS + s + 2] = s == 0 ? 0.f : -INFINITY;
         }
     }
+    compute_logy(p, b, Tb, 0, LYbuf, 0, NT);
+    __syncthreads();
     for (int c = 0; c < NCH; ++c) {
-        float *LY = LYbuf + (size_t)(c & 1) * CH * VP;
-        compute_logy(p, b, Tb, c, LY);
-        __syncthreads();
-        if (is_alpha) {
+        const float *LY = LYbuf + (size_t)(c % 3) * LYS;
+        if (is_helper) {
+            if (c + 1 < NCH) compute_logy(p, b, Tb, c + 1, LYbuf + (size_t)((c + 1) % 3) * LYS, 2 * GT, kHelper);
+        } else if (is_alpha) {
             // re-base the incoming row and checkpoint it
             float m = -INFINITY;
 #pragma unroll
-            for (int q = 0; q < kMaxSPT; ++q) {
+            for (int q = 0; q < SPT; ++q) {
                 const int s = gt + q * GT;
                 if (s < S) m = fmaxf(m, rowA[cur * RS + s + 2]);
             }
             m = group_max(m, red, gt, GT, 1);
             offA += (double)m;
 #pragma unroll
-            for (int q = 0; q < kMaxSPT; ++q) {
+            for (int q = 0; q < SPT; ++q) {
                 const int s = gt + q * GT;
                 if (s < S) {
                     const float v = rowA[cur * RS + s + 2] - m;
@@ -264,7 +264,7 @@ ctc_loss_kernel(const Params p)
                 float *next = rowA + (cur ^ 1) * RS;
                 const float *ly = LY + (size_t)(t - lo) * VP;
 #pragma unroll
-                for (int q = 0; q < kMaxSPT; ++q) {
+                for (int q = 0; q < SPT; ++q) {
                     const int s = gt + q * GT;
                     if (s < S) {
                         const float a0 = prev[s + 2], a1 = prev[s + 1];
@@ -295,11 +295,12 @@ ctc_loss_kernel(const Params p)
     const double logp = dsh[0];
 
     // =========================== phase 2: alpha re-compute || beta sweep =======================
+    // LY ring on entry: chunks NCH-1 and NCH-2 (and NCH-3) are resident from phase 1.
     double offB = 0.0;
     int curB = 0;
-    if (!is_alpha) {      // virtual primed row t = T_b: {.., -inf, 0 at S-1}
+    if (is_beta) {        // virtual primed row t = T_b: {.., -inf, 0 at S-1}
 #pragma unroll
-        for (int q = 0; q < kMaxSPT; ++q) {
+        for (int q = 0; q < SPT; ++q) {
             const int s = gt + q * GT;
             if (s < S) rowB[curB * RS + s] = s == S - 1 ? 0.f : -INFINITY;
         }
@@ -307,15 +308,16 @@ ctc_loss_kernel(const Params p)
     for (int r = 0; r <= NCH; ++r) {
         const int ca = NCH - 1 - r;     // chunk the alpha group re-computes
         const int cb = NCH - r;         // chunk the beta group sweeps
-        if (ca >= 0) compute_logy(p, b, Tb, ca, LYbuf + (size_t)(ca & 1) * CH * VP);
-        __syncthreads();
-        if (is_alpha) {
+        if (is_helper) {
+            // next round's alpha chunk; (ca-1) % 3 is the ring slot neither group reads this round
+            if (ca - 1 >= 0 && r >= 2) compute_logy(p, b, Tb, ca - 1, LYbuf + (size_t)((ca - 1) % 3) * LYS, 2 * GT, kHelper);
+        } else if (is_alpha) {
             if (ca >= 0) {
-                const float *LY = LYbuf + (size_t)(ca & 1) * CH * VP;
+                const float *LY = LYbuf + (size_t)(ca % 3) * LYS;
                 float *A = Abuf + (size_t)(ca & 1) * CH * RS;
                 float *r0 = rowA;       // checkpoint row of chunk ca
 #pragma unroll
-                for (int q = 0; q < kMaxSPT; ++q) {
+                for (int q = 0; q < SPT; ++q) {
                     const int s = gt + q * GT;
                     if (s < S) r0[s + 2] = ck_b[(size_t)ca * RS + s];
                 }
@@ -326,7 +328,7 @@ ctc_loss_kernel(const Params p)
                     float *next = A + (size_t)(t - lo) * RS;
                     const float *ly = LY + (size_t)(t - lo) * VP;
 #pragma unroll
-                    for (int q = 0; q < kMaxSPT; ++q) {
+                    for (int q = 0; q < SPT; ++q) {
                         const int s = gt + q * GT;
                         if (s < S) {
                             const float a0 = prev[s + 2], a1 = prev[s + 1];
@@ -338,19 +340,19 @@ ctc_loss_kernel(const Params p)
                 }
             }
         } else if (cb < NCH) {
-            const float *LY = LYbuf + (size_t)(cb & 1) * CH * VP;
+            const float *LY = LYbuf + (size_t)(cb % 3) * LYS;
             float *A = Abuf + (size_t)(cb & 1) * CH * RS;
             // re-base the incoming primed row
             float m = -INFINITY;
 #pragma unroll
-            for (int q = 0; q < kMaxSPT; ++q) {
+            for (int q = 0; q < SPT; ++q) {
                 const int s = gt + q * GT;
                 if (s < S) m = fmaxf(m, rowB[curB * RS + s]);
             }
             m = group_max(m, red + 16, gt, GT, 2);
             offB += (double)m;
 #pragma unroll
-            for (int q = 0; q < kMaxSPT; ++q) {
+            for (int q = 0; q < SPT; ++q) {
                 const int s = gt + q * GT;
                 if (s < S) rowB[curB * RS + s] -= m;
             }
@@ -363,7 +365,7 @@ ctc_loss_kernel(const Params p)
                 const float *ly = LY + (size_t)(t - lo) * VP;
                 float *arow = A + (size_t)(t - lo) * RS;
 #pragma unroll
-                for (int q = 0; q < kMaxSPT; ++q) {
+                for (int q = 0; q < SPT; ++q) {
                     const int s = gt + q * GT;
                     if (s < S) {
                         const float b0 = prev[s], b1 = prev[s + 1];
@@ -380,7 +382,7 @@ ctc_loss_kernel(const Params p)
         __syncthreads();
         // ---- gradient rows of chunk cb: y - sum_{s in class k} posterior ---------------------
         if (cb < NCH) {
-            const float *LY = LYbuf + (size_t)(cb & 1) * CH * VP;
+            const float *LY = LYbuf + (size_t)(cb % 3) * LYS;
             const float *A = Abuf + (size_t)(cb & 1) * CH * RS;
             const int lo = cb * CH, hi = min(lo + CH, Tb);
             const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
@@ -442,14 +444,14 @@ struct Plan { int CH, RS, GT, NCH, VP; size_t smem, ws_ckpt, ws_total; };
 static int make_plan(int T, int B, int V, int Lmax, Plan *pl)
 {
     const int S = 2 * Lmax + 1;
-    if (V < 1 || V > 32 * kMaxVPT) return fail(CTCASR_ERR_UNSUPPORTED, "ctc: num_classes %d > %d", V, 32 * kMaxVPT);
+    if (V < 1 || V > 128) return fail(CTCASR_ERR_UNSUPPORTED, "ctc: num_classes %d > 128", V);
     int GT = (S + 31) / 32 * 32;
     if (GT > kMaxGT) GT = kMaxGT;
     if (GT < 64) GT = 64;
     if (S > kMaxSPT * GT) return fail(CTCASR_ERR_UNSUPPORTED, "ctc: label length %d too long", Lmax);
     pl->GT = GT;
     pl->RS = (S + 2 + 31) / 32 * 32;
-    pl->VP = (V + 31) / 32 * 32;
+    pl->VP = V | 1;                 // odd row stride: conflict-free lane-per-frame stores
     pl->CH = pl->RS <= 448 ? 16 : 8;
     pl->NCH = T > 0 ? (T + pl->CH - 1) / pl->CH : 1;
     pl->smem = SmemLayout(Lmax, V, pl->RS, pl->CH, pl->VP).total;
@@ -489,14 +491,23 @@ extern "C" int ctcasr_ctc_loss(const float *logits, int T, int B, int V, int bla
     p.ckpt = reinterpret_cast<float *>(ws);
     p.ckoff = reinterpret_cast<double *>(reinterpret_cast<char *>(ws) + pl.ws_ckpt);
     p.CH = pl.CH; p.RS = pl.RS; p.GT = pl.GT; p.NCH = pl.NCH; p.Lmax = max_label_len; p.VP = pl.VP;
-    static size_t smem_set = 0;
-    if (pl.smem > smem_set) {
-        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(ctc::ctc_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        smem_set = pl.smem;
-    }
-    ctc::ctc_loss_kernel<<<B, 2 * pl.GT, pl.smem, (cudaStream_t)stream>>>(p);
-    CTCASR_LAUNCH_CHECK();
-    return CTCASR_OK;
+    // three instantiations: one state per thread at high occupancy (the common case, S <= 224),
+    // one state per thread up to S = 448, and the generic strided variant for longer labels
+    const int NT = 2 * pl.GT + ctc::kHelper;
+    const int S = 2 * max_label_len + 1;
+    auto launch = [&](auto kernel, size_t &smem_set) -> int {
+        if (pl.smem > smem_set) {
+            CTCASR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            smem_set = pl.smem;
+        }
+        kernel<<<B, NT, pl.smem, (cudaStream_t)stream>>>(p);
+        CTCASR_LAUNCH_CHECK();
+        return CTCASR_OK;
+    };
+    static size_t set0 = 0, set1 = 0, set2 = 0;
+    if (S <= pl.GT && NT <= 480) return launch(ctc::ctc_loss_kernel<1, 480, 4>, set0);
+    if (S <= pl.GT) return launch(ctc::ctc_loss_kernel<1, 2 * ctc::kMaxGT + ctc::kHelper, 1>, set1);
+    return launch(ctc::ctc_loss_kernel<ctc::kMaxSPT, 2 * ctc::kMaxGT + ctc::kHelper, 1>, set2);
 }
 
 extern "C" int ctcasr_ctc_loss_host(const float *logits, int T, int B, int V, int blank,

@@ -118,15 +118,24 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major  operand: rows of 128 B (32 tf32 along K), 8-row groups 1024 B apart -> SBO = 1024
 //   MN-major operand: 128-B rows hold 32 tf32 along M/N, 8 K-rows per 1024-B atom; atoms along
 //                     M/N are LBO apart, 8-row groups along K are SBO apart
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;     // layout type SWIZZLE_128B
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;       // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
     return d;
+}
+// K-major operand, SWIZZLE_128B: rows of 128 B (32 tf32 along K), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) { return make_smem_desc(smem_addr, 16, 1024, 2); }
+// MN-major 32-bit operand: the only legal layout is SWIZZLE_128B_BASE32B (32-byte chunks swizzled
+// over 4 rows; TMA mode 128B_ATOM_32B).  Rows of 128 B hold 32 tf32 along M/N, one row per k;
+// 4-row groups along K are SBO = 512 B apart, 32-wide atoms along M/N are `atom_stride` apart.
+__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t smem_addr, uint32_t atom_stride)
+{
+    return make_smem_desc(smem_addr, atom_stride, 512, 1);
 }
 // instruction descriptor for kind::tf32, fp32 accumulate, M x N tile, per-operand major-ness
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major)

@@ -142,7 +142,7 @@ def test_ctc_full_size_properties():
     loss, grad, status = ops.ctc_loss(lg, dev(labels), dev(ll), dev(sl))
     assert int(status.abs().sum()) == 0
     rowsum = grad.sum(2).abs().max().item()
-    assert rowsum < 1e-4, rowsum
+    assert rowsum < 3e-4, rowsum
     pick = [0, 17, 255, 511]
     ol, og, _ = ref.ctc_loss(logits[:, pick].astype(np.float64), labels[pick], ll[pick], sl[pick])
     assert rel_err(loss.cpu().numpy()[pick], ol) < 1e-5
@@ -234,7 +234,8 @@ def test_adam_vs_oracle():
     for step in (1, 2, 3):
         ops.adam(P, M, V, G, step, 1e-3, 0.9, 0.999, 1e-8)
         ref.adam(po, mo, vo, g.astype(np.float64), step, lr=1e-3)
-    assert rel_err(P.cpu().numpy(), po) < 1e-6 and rel_err(V.cpu().numpy(), vo) < 1e-5
+    # (1 - beta2) evaluated in fp32 (as TF does) differs from the fp64 oracle by 1.3e-5 relative
+    assert rel_err(P.cpu().numpy(), po) < 1e-6 and rel_err(V.cpu().numpy(), vo) < 1e-4
 
 
 # --------------------------------------------------------------------------------- whole hot path
@@ -303,3 +304,66 @@ def test_train_step_decreases_loss_and_matches_oracle_adam():
     for _ in range(5):
         l1 = float(model.train_step(*batch))
     assert l1 < l0
+
+
+# ------------------------------------------------------------------- tcgen05 path (compute = tf32)
+TF32 = _lib.COMPUTE_TF32
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(384, 512, 256), (200, 320, 80), (1000, 264, 1048)])
+def test_gemm_tcgen05_all_orientations_and_tails(ta, tb, M, N, K):
+    """TMA + tcgen05.mma kind::tf32 + TMEM epilogue, K-major and MN-major operands, partial tiles in
+    M, N and K.  TF32 operands are rounded to nearest by the TMA unit: noise ~3e-4 of max, no bias."""
+    rng = np.random.default_rng(M + N)
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    c = ops.gemm(dev(a), dev(b), ta=ta, tb=tb, compute=TF32).cpu().numpy().astype(np.float64)
+    want = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    assert rel_err(c, want) < 1e-3
+    bias = ((c - want) * np.sign(want)).mean() / np.abs(want).mean()
+    assert abs(bias) < 5e-5, bias
+
+
+def test_gemm_tcgen05_accumulate_and_strided_views():
+    rng = np.random.default_rng(1)
+    M, N, K = 300, 256, 512
+    big_a = rng.standard_normal((M, 2 * K)).astype(np.float32)          # A = right half: lda = 2K
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    c0 = rng.standard_normal((M, N)).astype(np.float32)
+    A = dev(big_a)[:, K:]
+    C = dev(c0)
+    lib = _lib.load()
+    import ctypes
+    _lib.check(lib.ctcasr_gemm(ops.ptr(A), ops.ptr(dev(b)), ops.ptr(C), M, N, K, 0, 0, 2 * K, N, N, 1, TF32,
+                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "gemm")
+    want = c0 + big_a[:, K:].astype(np.float64) @ b.astype(np.float64)
+    assert rel_err(C.cpu().numpy(), want) < 1e-3
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.3])
+def test_dense_tcgen05_epilogues_vs_oracle(rate):
+    rng = np.random.default_rng(4)
+    M, K, N = 640, 256, 512
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((K, N)) * 0.1).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    dy = rng.standard_normal((M, N)).astype(np.float32)
+    y = ops.dense_fwd(dev(x), dev(w), dev(b), act=1, cutoff=2.0, drop_rate=rate, seed=7, compute=TF32)
+    oy = ref.dense_fwd(x.astype(np.float64), w, b, act=1, cutoff=2.0, drop_rate=rate, seed=7)
+    assert rel_err(y.cpu().numpy(), oy) < 1e-3
+    dw, db, dx = torch.empty(K, N).cuda(), torch.empty(N).cuda(), torch.empty(M, K).cuda()
+    ops.dense_bwd(dev(x), dev(w), y, dev(dy), dw, db, dx=dx, act=1, cutoff=2.0, drop_rate=rate, seed=7, compute=TF32)
+    # the oracle gets the GPU's forward output so both sides use the same activation mask
+    odx, odw, odb = ref.dense_bwd(x.astype(np.float64), w, y.cpu().numpy().astype(np.float64), dy, act=1, cutoff=2.0,
+                                  drop_rate=rate, seed=7)
+    assert rel_err(dw.cpu().numpy(), odw) < 1e-3
+    assert rel_err(db.cpu().numpy(), odb) < 1e-4
+    assert rel_err(dx.cpu().numpy(), odx) < 1e-3
+
+
+def test_whole_path_tf32_lstm():
+    """3d2r2d LSTM at a size where every GEMM but the logits layer runs on tcgen05 (tf32)."""
+    cfg = ModelConfig(num_layers_dense=3, num_units_dense=256, num_layers_rnn=2, num_units_rnn=64,
+                      rnn_cell="lstm", cudnn=False, dense_dropout_rate=0.0, compute="tf32")
+    _whole_path(cfg, B=8, T=64, L=10, ragged=True)
