@@ -10,8 +10,8 @@ CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0
 CELL_RNN_TANH, CELL_RNN_RELU, CELL_LSTM, CELL_GRU = 0, 1, 2, 3
-COMPUTE_FP32, COMPUTE_TF32 = 0, 1
-COMPUTE_ID = {"fp32": COMPUTE_FP32, "tf32": COMPUTE_TF32}
+COMPUTE_FP32, COMPUTE_TF32, COMPUTE_BF16X3 = 0, 1, 2
+COMPUTE_ID = {"fp32": COMPUTE_FP32, "tf32": COMPUTE_TF32, "bf16x3": COMPUTE_BF16X3}
 
 _vp, _i, _f, _u32, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_uint32, ctypes.c_size_t
 
@@ -31,6 +31,8 @@ SIGNATURES = {
     "ctcasr_birnn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
     "ctcasr_birnn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ctcasr_set_scratch": (_i, [_vp, _sz]),
+    "ctcasr_scratch_needed": (_sz, []),
     "ctcasr_transpose01": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ctcasr_adam": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _f, _f, _f, _f, _f, _vp]),
     "ctcasr_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -9,7 +9,7 @@ std::atomic<uint64_t> g_launch_count{0};
 
 int gemm(const GemmArgs &g, int compute, cudaStream_t stream)
 {
-    if (compute == CTCASR_COMPUTE_TF32 && gemm_tc_eligible(g)) return gemm_tc(g, stream);
+    if (compute != CTCASR_COMPUTE_FP32 && gemm_tc_eligible(g)) return gemm_tc(g, compute, stream);
     return gemm_simt(g, stream);
 }
 }  // namespace ctcasr
@@ -40,6 +40,7 @@ extern "C" int ctcasr_dense_fwd(const float *x, const float *w, const float *bia
     g.A[0] = x; g.B[0] = w; g.C[0] = y; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = N; g.ldc = N;
     g.epi.mode = EPI_BIAS_ACT; g.epi.bias = bias; g.epi.act = act; g.epi.cutoff = cutoff;
     g.epi.drop_rate = drop_rate; g.epi.seed = seed;
+    g.precise = act != 0;       // pre-activations near the ReLU / clip kinks decide the backward mask
     return gemm(g, compute, (cudaStream_t)stream);
 }
 
@@ -51,6 +52,8 @@ extern "C" int ctcasr_dense_bwd(const float *x, const float *w, const float *y, 
     cudaStream_t stream = (cudaStream_t)stream_;
     CTCASR_REQUIRE(x && w && dy && dw && db && M >= 0 && K >= 1 && N >= 1, "dense_bwd: bad args");
     CTCASR_REQUIRE(act == 0 || y, "dense_bwd: activation mask needs the forward output y");
+    if (int rcs = gemm_scratch_check(compute, 1, K, N, M)) return rcs;
+    if (int rcs = gemm_scratch_check(compute, 1, M, K, N)) return rcs;
     int rc = mask_inplace(dy, y, (size_t)M, N, act, cutoff, drop_rate, seed, stream);   // dy -> dz
     if (rc != CTCASR_OK) return rc;
     rc = colsum(dy, M, N, N, db, stream);

@@ -12,13 +12,15 @@ struct GemmArgs {
     int M = 0, N = 0, K = 0;
     int ta = 0, tb = 0;         // ta: A stored [K,M]; tb: B stored [N,K]
     int lda = 0, ldb = 0, ldc = 0;
+    int precise = 0;            // BF16X3: use the 3-piece / 6-product split (output feeds a ReLU kink)
     Epilogue epi;
 };
 
 int gemm_simt(const GemmArgs &g, cudaStream_t stream);
 // returns CTCASR_ERR_UNSUPPORTED (without touching C) when the shape/alignment is not eligible
-int gemm_tc(const GemmArgs &g, cudaStream_t stream);
+int gemm_tc(const GemmArgs &g, int compute, cudaStream_t stream);
 bool gemm_tc_eligible(const GemmArgs &g);
+int gemm_scratch_check(int compute, int nz, int M, int N, int K);
 // dispatch on `compute`: TF32 -> tcgen05 when eligible, otherwise the SIMT kernel
 int gemm(const GemmArgs &g, int compute, cudaStream_t stream);
 

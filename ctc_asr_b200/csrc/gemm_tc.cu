@@ -1,28 +1,40 @@
-// gemm_tc.cu — tcgen05 / TMA / TMEM GEMM for sm_100a (CTCASR_COMPUTE_TF32).
+// gemm_tc.cu — tcgen05 / TMA / TMEM GEMM for sm_100a (CTCASR_COMPUTE_TF32, CTCASR_COMPUTE_BF16X3).
 //
-// C[M,N] = op(A) op(B) with fp32 operands read as TF32 by the tensor cores and fp32 accumulation
-// in tensor memory.  Used for every GEMM-shaped piece of the path: the dense layers
-// (asr/util/tf_contrib.py:52-58, asr/model.py:220-232), the hoisted RNN input projection and the
-// three backward GEMMs per layer (dgrad, wgrad) — in the reference these are cuBLAS sgemm calls
-// issued by TensorFlow.
+// C[M,N] = op(A) op(B), fp32 in HBM, fp32 accumulation in tensor memory.  Used for every GEMM-shaped
+// piece of the path: the dense layers (asr/util/tf_contrib.py:52-58, asr/model.py:220-232), the
+// hoisted RNN input projection and the backward GEMMs (dgrad, wgrad) — in the reference these are
+// cuBLAS sgemm calls issued by TensorFlow.
+//
+// Arithmetic modes (template parameter MODE):
+//   TF32    tcgen05.mma kind::tf32 straight on the fp32 operands (the TMA unit rounds fp32 -> tf32 on
+//           the way into shared memory).  Fastest; 2^-11 operand rounding (3e-4 of max per GEMM), which
+//           flips ReLU masks in the dense stack and costs up to 3e-2 of max-norm gradient error.
+//   BF16X3  fp32-accurate emulation: a pre-pass splits each operand into bf16 pieces a = a1 + a2
+//           (+ a3); the kernel issues kind::f16 MMAs for a1b1 + a1b2 + a2b1 (3 products, error
+//           ~2^-16) or, for layers whose output goes through a ReLU kink (`precise`), the 6 products
+//           of a 3-piece split (error ~2^-23) — all accumulated in the same fp32 TMEM tile.
+//           Same bytes per element as fp32 (2 x 2 B), 1.5x the tensor time of TF32.
 //
 // Structure (persistent, one CTA per SM, 192 threads):
-//   warp 4      TMA producer: cp.async.bulk.tensor 2-D boxes of 32 fp32 (128 B, SWIZZLE_128B) into a
-//               4-stage shared-memory ring (A 128x32, B 256x32 per stage = 48 KB), mbarrier expect_tx
-//   warp 5      MMA issuer: one elected lane issues 4 x tcgen05.mma.kind::tf32 (128 x 256 x 8) per
-//               stage; tcgen05.commit releases the stage / publishes the accumulator
+//   warp 4      TMA producer: cp.async.bulk.tensor boxes into a shared-memory ring
+//               (per stage and piece: A 128 x 32, B 256 x 32), mbarrier expect_tx
+//   warp 5      MMA issuer: one elected lane issues the tcgen05.mma's of a stage (128 x 256 x 8|16
+//               each); tcgen05.commit releases the stage / publishes the accumulator
 //   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / clipped ReLU / dropout /
 //               activation mask / accumulate -> 128-bit global stores.  Two 256-column TMEM
 //               accumulators, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Both operand orientations are handled in the descriptors, not by transposing data:
-//   K-major  (A[m][k], B[n][k]): one box [rows x 32 k];        smem desc SBO = 1024 B
-//   MN-major (A[k][m], B[k][n]): boxes [32 k x 32 m|n] 4 KB apart, TMA swizzle 128B_ATOM_32B;
-//                                smem desc SWIZZLE_128B_BASE32B, LBO = 4096 B, SBO = 512 B
+//   K-major  (A[m][k], B[n][k]): one box [rows x 32 k] per piece
+//              tf32: SWIZZLE_128B, SBO 1024          bf16: SWIZZLE_64B, SBO 512
+//   MN-major (A[k][m], B[k][n]): boxes [32 k x 128 B of m|n], 4 KB apart (LBO)
+//              tf32: TMA 128B_ATOM_32B / desc SWIZZLE_128B_BASE32B, SBO 512 (the only legal layout
+//                    for 32-bit MN-major operands)   bf16: SWIZZLE_128B, SBO 1024
 // Tiles are walked in groups of 16 row-tiles x all column-tiles so that the ~148 tiles in flight
 // share A and B panels through L2.
 #include "gemm.cuh"
 #include "ptx.cuh"
 
+#include <cuda_bf16.h>
 #include <mutex>
 #include <stdlib.h>
 
@@ -30,11 +42,30 @@ namespace ctcasr {
 namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 32;
-constexpr int NSTAGE = 4, NACC = 2;
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NACC = 2;
 constexpr int GROUP_M = 16;
 constexpr int NTHREADS = 192;
+
+enum { MODE_TF32 = 1, MODE_BF16X3 = 2, MODE_BF16X6 = 3 };     // bf16 modes: value = pieces per operand
+
+template <int MODE>
+struct Cfg {
+    static constexpr bool kBf16 = MODE != MODE_TF32;
+    static constexpr int NP = kBf16 ? MODE : 1;                 // pieces per operand
+    static constexpr int ESZ = kBf16 ? 2 : 4;
+    static constexpr int A_PIECE = BM * BK * ESZ, B_PIECE = BN * BK * ESZ;
+    static constexpr int STAGE_BYTES = NP * (A_PIECE + B_PIECE);
+    static constexpr int NSTAGE = MODE == MODE_BF16X6 ? 2 : 4;
+    static constexpr int UMMA_K = kBf16 ? 16 : 8;
+    static constexpr int KSTEPS = BK / UMMA_K;
+    static constexpr int MN_BOX = 128 / ESZ;                    // m|n elements per 128-B row
+    static constexpr int MN_BOX_BYTES = BK * 128;               // one MN-major box: 32 k-rows x 128 B
+    static constexpr int NPROD = MODE == MODE_TF32 ? 1 : (MODE == MODE_BF16X3 ? 3 : 6);
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    // per k-step advance of the descriptor start address (bytes)
+    static constexpr int KMAJ_STEP = UMMA_K * ESZ;              // inside the swizzled row
+    static constexpr int MNMAJ_STEP = UMMA_K * 128;             // UMMA_K rows of 128 B
+};
 
 struct Params {
     int M, N, K, nz, ta, tb, ldc;
@@ -57,13 +88,26 @@ __device__ __forceinline__ void decode_tile(const Params &p, int t, int &z, int 
     nb = r / gm;
 }
 
+template <int MODE>
+__device__ __forceinline__ uint64_t operand_desc(uint32_t addr, bool mn_major)
+{
+    if (MODE == MODE_TF32)
+        return mn_major ? ptx::make_smem_desc(addr, Cfg<MODE>::MN_BOX_BYTES, 512, 1)     // SWIZZLE_128B_BASE32B
+                        : ptx::make_smem_desc(addr, 16, 1024, 2);                        // SWIZZLE_128B
+    return mn_major ? ptx::make_smem_desc(addr, Cfg<MODE>::MN_BOX_BYTES, 1024, 2)        // SWIZZLE_128B
+                    : ptx::make_smem_desc(addr, 16, 512, 4);                             // SWIZZLE_64B
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
                const Params p)
 {
+    using C_ = Cfg<MODE>;
+    constexpr int NSTAGE = C_::NSTAGE, STAGE_BYTES = C_::STAGE_BYTES, NP = C_::NP;
     extern __shared__ unsigned char smem_raw[];
-    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B: 1024-B aligned
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle atoms: 1024-B aligned
     const uint32_t bar_base = smem_base + NSTAGE * STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
@@ -72,6 +116,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 2 * NACC);
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+    // stage layout: A pieces, then B pieces
+    auto a_addr = [&](int stage, int piece) { return smem_base + stage * STAGE_BYTES + piece * C_::A_PIECE; };
+    auto b_addr = [&](int stage, int piece) { return smem_base + stage * STAGE_BYTES + NP * C_::A_PIECE + piece * C_::B_PIECE; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -102,20 +149,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                     ptx::mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    if (!p.ta) {
-                        ptx::tma_load_2d(sa, ma, kb * BK, mb * BM, full_bar(stage));
-                    } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 32; ++j)
-                            ptx::tma_load_2d(sa + j * 4096, ma, mb * BM + j * 32, kb * BK, full_bar(stage));
-                    }
-                    if (p.tb) {
-                        ptx::tma_load_2d(sb, mbp, kb * BK, nb * BN, full_bar(stage));
-                    } else {
+                    for (int pc = 0; pc < NP; ++pc) {
+                        if (!p.ta) {
+                            ptx::tma_load_3d(a_addr(stage, pc), ma, kb * BK, mb * BM, pc, full_bar(stage));
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j)
-                            ptx::tma_load_2d(sb + j * 4096, mbp, nb * BN + j * 32, kb * BK, full_bar(stage));
+                            for (int j = 0; j < BM / C_::MN_BOX; ++j)
+                                ptx::tma_load_3d(a_addr(stage, pc) + j * C_::MN_BOX_BYTES, ma, mb * BM + j * C_::MN_BOX,
+                                                 kb * BK, pc, full_bar(stage));
+                        }
+                        if (p.tb) {
+                            ptx::tma_load_3d(b_addr(stage, pc), mbp, kb * BK, nb * BN, pc, full_bar(stage));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / C_::MN_BOX; ++j)
+                                ptx::tma_load_3d(b_addr(stage, pc) + j * C_::MN_BOX_BYTES, mbp, nb * BN + j * C_::MN_BOX,
+                                                 kb * BK, pc, full_bar(stage));
+                        }
                     }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
@@ -124,11 +175,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else if (warp == 5) {
         // ====================================== MMA issuer =======================================
         if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_tf32(BM, BN, p.ta ? 1 : 0, p.tb ? 0 : 1);
-            // per k-step (8 tf32 = 32 B along K): K-major advances 32 B inside the swizzle row,
-            // MN-major advances one 8-row group (1024 B)
-            const uint32_t a_step = p.ta ? (1024u >> 4) : (32u >> 4);
-            const uint32_t b_step = p.tb ? (32u >> 4) : (1024u >> 4);
+            const uint32_t idesc = C_::kBf16 ? ptx::make_idesc_bf16(BM, BN, p.ta ? 1 : 0, p.tb ? 0 : 1)
+                                             : ptx::make_idesc_tf32(BM, BN, p.ta ? 1 : 0, p.tb ? 0 : 1);
+            const uint32_t a_step = (p.ta ? C_::MNMAJ_STEP : C_::KMAJ_STEP) >> 4;
+            const uint32_t b_step = (p.tb ? C_::KMAJ_STEP : C_::MNMAJ_STEP) >> 4;
+            // products of the split operands, largest first: a1b1, a1b2, a2b1, (a1b3, a2b2, a3b1)
+            constexpr int PA[6] = {0, 0, 1, 0, 1, 2};
+            constexpr int PB[6] = {0, 1, 0, 2, 1, 0};
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -138,13 +191,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    const uint64_t adesc = p.ta ? ptx::make_desc_mnmajor(sa, 4096) : ptx::make_desc_kmajor(sa);
-                    const uint64_t bdesc = p.tb ? ptx::make_desc_kmajor(sb) : ptx::make_desc_mnmajor(sb, 4096);
 #pragma unroll
-                    for (int j = 0; j < BK / 8; ++j)
-                        ptx::mma_tf32(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc,
-                                      (kb | j) != 0);
+                    for (int q = 0; q < C_::NPROD; ++q) {
+                        const uint64_t adesc = operand_desc<MODE>(a_addr(stage, PA[q]), p.ta != 0);
+                        const uint64_t bdesc = operand_desc<MODE>(b_addr(stage, PB[q]), p.tb == 0);
+#pragma unroll
+                        for (int j = 0; j < C_::KSTEPS; ++j) {
+                            const uint32_t accum = (kb | q | j) != 0;
+                            if (C_::kBf16) ptx::mma_bf16(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc, accum);
+                            else           ptx::mma_tf32(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc, accum);
+                        }
+                    }
                     ptx::mma_commit(empty_bar(stage));          // stage reusable once these MMAs retire
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
@@ -174,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int n = n0 + 4 * q;
-                        if (n < p.N) {        // N % 4 == 0 (eligibility), so a float4 is all-in or all-out
+                        if (n < p.N) {        // N % 8 == 0 (eligibility), so a float4 is all-in or all-out
                             float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (p.epi.mode == EPI_STORE && p.epi.accumulate) old = *reinterpret_cast<const float4 *>(crow + 4 * q);
                             float4 o;
@@ -199,6 +256,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (warp == 5) ptx::tmem_dealloc(tmem_base, NACC * BN);
 }
 
+// ---- operand split pre-pass: fp32 [rows][ld] -> NP bf16 matrices [NP][rows][ldo] ---------------------
+// piece 1 = bf16(a), piece 2 = bf16(a - piece 1), piece 3 = bf16(a - piece 1 - piece 2); the
+// subtractions are exact in fp32.  HBM-bound: 4 B in, 2*NP B out per element.
+template <int NP>
+__global__ void split_bf16_kernel(const float *__restrict__ x, int rows, int cols, int ld,
+                                  __nv_bfloat16 *__restrict__ out, int ldo)
+{
+    const int c4 = cols / 4;
+    const size_t total = (size_t)rows * c4;
+    const size_t piece = (size_t)rows * ldo;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / c4), c = (int)(i % c4) * 4;
+        const float4 v = *reinterpret_cast<const float4 *>(x + (size_t)r * ld + c);
+        float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int pc = 0; pc < NP; ++pc) {
+            __nv_bfloat16 h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(f[j]); f[j] -= __bfloat162float(h[j]); }
+            uint2 pk;
+            pk.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+            pk.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+            *reinterpret_cast<uint2 *>(out + pc * piece + (size_t)r * ldo + c) = pk;
+        }
+    }
+}
+
 // ---- host side: tensor maps ---------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -218,55 +302,84 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-// 2-D fp32 tensor [outer][inner] with row pitch ld (elements); box = [box_outer][32] (128-B rows)
-static int encode_map(CUtensorMap *map, const float *base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
-                      bool mn_major)
+// 3-D tensor [piece][outer][inner] (row pitch ld elements, piece pitch `piece_elems`), box =
+// [1][box_outer][box_inner].  The piece dimension keeps boxes at the K / M / N tails from running
+// into the next piece: out-of-range rows are zero-filled per dimension.
+static int encode_map(CUtensorMap *map, const void *base, bool bf16, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint64_t npiece, uint64_t piece_elems, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail(CTCASR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {ld * sizeof(float)};
-    cuuint32_t box[2] = {32, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    // element type TFLOAT32: the TMA unit converts fp32 -> tf32 while copying, so the tensor cores
-    // see rounded operands instead of truncating the low 13 mantissa bits themselves
+    const uint64_t esz = bf16 ? 2 : 4;
+    cuuint64_t dims[3] = {inner, outer, npiece};
+    cuuint64_t strides[2] = {ld * esz, (npiece > 1 ? piece_elems : outer * ld) * esz};
+    cuuint32_t box[3] = {box_inner, box_outer, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    // fp32 operands use element type TFLOAT32: the TMA unit converts fp32 -> tf32 (round to nearest)
+    // while copying, so the tensor cores do not truncate the low 13 mantissa bits themselves
     // (truncation measured as a systematic -7e-4 relative bias per GEMM).  CTCASR_TMA_F32=1 disables.
     static const bool plain_f32 = getenv("CTCASR_TMA_F32") != nullptr;
-    CUresult r = fn(map, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
-                    const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+    const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                        : (plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
+    CUresult r = fn(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CTCASR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu", (int)r,
                                       (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
     return CTCASR_OK;
 }
 
-}  // namespace tc
+// ---- scratch arena for the split operands (set by the caller: the library allocates nothing) -------
+static char *g_scratch = nullptr;
+static size_t g_scratch_bytes = 0, g_scratch_needed = 0;
 
-bool gemm_tc_eligible(const GemmArgs &g)
+template <int MODE>
+static int launch(const GemmArgs &g, cudaStream_t stream)
 {
-    if (g.M < 1 || g.N < 64 || g.K < 8) return false;
-    if ((g.N % 4) || (g.lda % 4) || (g.ldb % 4) || (g.ldc % 4)) return false;      // TMA 16-B pitches, float4 stores
-    if ((double)g.M * g.N * g.K < 4.0e6) return false;                             // not worth a persistent launch
-    for (int z = 0; z < g.nz; ++z)
-        if (((uintptr_t)g.A[z] | (uintptr_t)g.B[z] | (uintptr_t)g.C[z]) & 15) return false;
-    if (g.epi.mode == EPI_MASK && ((g.epi.ldm % 4) || ((uintptr_t)g.epi.mask_y & 15))) return false;
-    return true;
-}
-
-int gemm_tc(const GemmArgs &g, cudaStream_t stream)
-{
-    using namespace tc;
-    if (!gemm_tc_eligible(g)) return fail(CTCASR_ERR_UNSUPPORTED, "gemm_tc: shape not eligible");
+    using C_ = Cfg<MODE>;
+    constexpr int NP = C_::NP;
+    const void *Abase[2] = {g.A[0], g.nz > 1 ? g.A[1] : g.A[0]};
+    const void *Bbase[2] = {g.B[0], g.nz > 1 ? g.B[1] : g.B[0]};
+    // stored shapes: A is [M][K] (or [K][M] when ta), B is [K][N] (or [N][K] when tb)
+    const int a_rows = g.ta ? g.K : g.M, a_cols = g.ta ? g.M : g.K;
+    const int b_rows = g.tb ? g.N : g.K, b_cols = g.tb ? g.K : g.N;
+    int lda = g.lda, ldb = g.ldb;
+    size_t a_piece = 0, b_piece = 0;
+    if (C_::kBf16) {
+        const int ldoa = (a_cols + 7) / 8 * 8, ldob = (b_cols + 7) / 8 * 8;
+        a_piece = (size_t)a_rows * ldoa; b_piece = (size_t)b_rows * ldob;
+        const size_t a_bytes = align_up(a_piece * NP * 2, 1024), b_bytes = align_up(b_piece * NP * 2, 1024);
+        const size_t need = (size_t)g.nz * (a_bytes + b_bytes);
+        if (need > g_scratch_bytes) {
+            g_scratch_needed = need;
+            return fail(CTCASR_ERR_WORKSPACE, "gemm_tc: split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)",
+                        g_scratch_bytes, need);
+        }
+        char *cur = g_scratch;
+        for (int z = 0; z < g.nz; ++z) {
+            __nv_bfloat16 *sa = reinterpret_cast<__nv_bfloat16 *>(cur); cur += a_bytes;
+            __nv_bfloat16 *sb = reinterpret_cast<__nv_bfloat16 *>(cur); cur += b_bytes;
+            const size_t ta4 = (size_t)a_rows * (a_cols / 4), tb4 = (size_t)b_rows * (b_cols / 4);
+            const int ga = (int)((ta4 + 255) / 256 < 148 * 16 ? (ta4 + 255) / 256 : 148 * 16);
+            const int gb = (int)((tb4 + 255) / 256 < 148 * 16 ? (tb4 + 255) / 256 : 148 * 16);
+            split_bf16_kernel<NP><<<ga, 256, 0, stream>>>(g.A[z], a_rows, a_cols, g.lda, sa, ldoa);
+            CTCASR_LAUNCH_CHECK();
+            split_bf16_kernel<NP><<<gb, 256, 0, stream>>>(g.B[z], b_rows, b_cols, g.ldb, sb, ldob);
+            CTCASR_LAUNCH_CHECK();
+            Abase[z] = sa; Bbase[z] = sb;
+        }
+        if (g.nz == 1) { Abase[1] = Abase[0]; Bbase[1] = Bbase[0]; }
+        lda = ldoa; ldb = ldob;
+    }
     CUtensorMap maps[4];
+    const CUtensorMapSwizzle sw_k = C_::kBf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle sw_mn = C_::kBf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     for (int z = 0; z < 2; ++z) {
-        const int zz = z < g.nz ? z : 0;
         int rc;
-        if (!g.ta) rc = encode_map(&maps[2 * z], g.A[zz], g.K, g.M, g.lda, BM, false);      // A[m][k]: inner k
-        else       rc = encode_map(&maps[2 * z], g.A[zz], g.M, g.K, g.lda, 32, true);       // A[k][m]: inner m
+        if (!g.ta) rc = encode_map(&maps[2 * z], Abase[z], C_::kBf16, g.K, g.M, lda, NP, a_piece, BK, BM, sw_k);             // A[m][k]
+        else       rc = encode_map(&maps[2 * z], Abase[z], C_::kBf16, g.M, g.K, lda, NP, a_piece, C_::MN_BOX, BK, sw_mn);    // A[k][m]
         if (rc != CTCASR_OK) return rc;
-        if (g.tb)  rc = encode_map(&maps[2 * z + 1], g.B[zz], g.K, g.N, g.ldb, BN, false);  // B[n][k]: inner k
-        else       rc = encode_map(&maps[2 * z + 1], g.B[zz], g.N, g.K, g.ldb, 32, true);   // B[k][n]: inner n
+        if (g.tb)  rc = encode_map(&maps[2 * z + 1], Bbase[z], C_::kBf16, g.K, g.N, ldb, NP, b_piece, BK, BN, sw_k);         // B[n][k]
+        else       rc = encode_map(&maps[2 * z + 1], Bbase[z], C_::kBf16, g.N, g.K, ldb, NP, b_piece, C_::MN_BOX, BK, sw_mn); // B[k][n]
         if (rc != CTCASR_OK) return rc;
     }
     Params p;
@@ -276,16 +389,67 @@ int gemm_tc(const GemmArgs &g, cudaStream_t stream)
     p.tiles_m = ceil_div(g.M, BM); p.tiles_n = ceil_div(g.N, BN); p.kblocks = ceil_div(g.K, BK);
     p.num_tiles = p.tiles_m * p.tiles_n * g.nz;
     static int num_sms = 0;
+    static bool attr_set = false;
     if (!num_sms) {
         int dev = 0;
         CTCASR_CUDA_CHECK(cudaGetDevice(&dev));
         CTCASR_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    }
+    if (!attr_set) {
+        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        attr_set = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    gemm_tc_kernel<MODE><<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
     CTCASR_LAUNCH_CHECK();
     return CTCASR_OK;
 }
 
+}  // namespace tc
+
+bool gemm_tc_eligible(const GemmArgs &g)
+{
+    if (g.M < 1 || g.N < 64 || g.K < 8) return false;
+    if ((g.M % 8) || (g.N % 8) || (g.K % 8)) return false;                         // 16-B rows of the bf16 pieces
+    if ((g.lda % 4) || (g.ldb % 4) || (g.ldc % 4)) return false;                   // TMA 16-B pitches, float4 stores
+    if ((double)g.M * g.N * g.K < 4.0e6) return false;                             // not worth a persistent launch
+    for (int z = 0; z < g.nz; ++z)
+        if (((uintptr_t)g.A[z] | (uintptr_t)g.B[z] | (uintptr_t)g.C[z]) & 15) return false;
+    if (g.epi.mode == EPI_MASK && ((g.epi.ldm % 4) || ((uintptr_t)g.epi.mask_y & 15))) return false;
+    return true;
+}
+
+// Upper bound of the split-operand scratch a GEMM of this shape can need (3 pieces, padded rows).
+// Composite entry points check it BEFORE launching anything, so a too-small arena never leaves
+// half-updated buffers behind.
+int gemm_scratch_check(int compute, int nz, int M, int N, int K)
+{
+    if (compute != CTCASR_COMPUTE_BF16X3) return CTCASR_OK;
+    auto pad = [](int v) { return (size_t)((v + 7) / 8 * 8); };
+    const size_t need = (size_t)nz * (align_up(6 * pad(M) * pad(K), 1024) + align_up(6 * pad(K) * pad(N), 1024));
+    if (need > tc::g_scratch_bytes) {
+        if (need > tc::g_scratch_needed) tc::g_scratch_needed = need;
+        return fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", tc::g_scratch_bytes, need);
+    }
+    return CTCASR_OK;
+}
+
+int gemm_tc(const GemmArgs &g, int compute, cudaStream_t stream)
+{
+    if (!gemm_tc_eligible(g)) return fail(CTCASR_ERR_UNSUPPORTED, "gemm_tc: shape not eligible");
+    if (compute == CTCASR_COMPUTE_TF32) return tc::launch<tc::MODE_TF32>(g, stream);
+    if (compute == CTCASR_COMPUTE_BF16X3)
+        return g.precise ? tc::launch<tc::MODE_BF16X6>(g, stream) : tc::launch<tc::MODE_BF16X3>(g, stream);
+    return fail(CTCASR_ERR_INVALID, "gemm_tc: compute mode %d", compute);
+}
+
 }  // namespace ctcasr
+
+extern "C" int ctcasr_set_scratch(void *ptr, size_t bytes)
+{
+    if (bytes && (!ptr || ((uintptr_t)ptr & 1023))) return ctcasr::fail(CTCASR_ERR_INVALID, "set_scratch: need a 1024-B aligned device pointer");
+    ctcasr::tc::g_scratch = reinterpret_cast<char *>(ptr);
+    ctcasr::tc::g_scratch_bytes = bytes;
+    return CTCASR_OK;
+}
+extern "C" size_t ctcasr_scratch_needed(void) { return ctcasr::tc::g_scratch_needed; }

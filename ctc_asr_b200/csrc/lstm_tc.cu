@@ -1,8 +1,602 @@
-// placeholder until the persistent tcgen05 LSTM kernel lands
+// lstm_tc.cu — persistent tcgen05 LSTM recurrence (forward and backward) for sm_100a.
+//
+// Replaces the T-step while-loop of tfc.rnn.stack_bidirectional_dynamic_rnn / CudnnLSTM
+// (asr/model.py:176-183, :194-215; cell = TF LSTMCell, gate order i, j, f, o) for one layer, both
+// directions at once.  The input projection is hoisted (rnn.cu); this kernel runs the strictly
+// sequential part  z_t = P_t + h_{t-1} Wh  ->  gates -> (c_t, h_t)  and its reverse.
+//
+// One cooperative launch per layer and pass; grid = 2 directions x H/32 CTAs, one CTA per SM,
+// all T steps inside the kernel (no per-step launches).  CTA (d, c) owns hidden units
+// [32c, 32c+32) of direction d for the whole sequence:
+//   forward   D[128 gate rows (4 gates x 32 units), 32 batch] = Wp_slice[128, H] . h_{t-1}^T
+//             (swap-AB: the gate rows fill the MMA M dimension, the batch is N)
+//   backward  D[32 batch (+96 unused lanes), 32 units] = dz_{t+1}[32, 4H] . Wh[units, 4H]^T
+// Arithmetic: bf16x3 — weights are pre-split into two bf16 pieces (same bytes as fp32), h / dz are
+// split by the epilogue that produces them, three tcgen05.mma kind::f16 products per k-step
+// accumulate in fp32 TMEM (error ~2^-16 per product; see gemm_tc.cu).
+// Warp roles: 0-3 cell math (TMEM -> registers -> smem gate exchange -> c/h update, c kept in
+// registers across steps), 4 weight-tile TMA producer (runs ahead across step boundaries: weights
+// do not depend on the recurrence), 5 state-tile TMA producer (gated by the per-direction step
+// barrier), 6 MMA issuer.
+// Cross-CTA step barrier: every CTA publishes its slice of h_t (bf16 pieces, global memory) and
+// bumps a per-direction counter (release); the state producer acquires counter >= CPD * step.
+// The recurrent weights (2 x 64 MiB in two bf16 pieces at H = 2048) do not fit on chip and are
+// streamed every step: the kernel is bound by L2/HBM weight streaming, not by the tensor pipe.
 #include "lstm_tc.cuh"
+#include "ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <mutex>
+
 namespace ctcasr {
-bool lstm_tc_eligible(int, int, int, int) { return false; }
-size_t lstm_tc_workspace_bytes(int, int) { return 0; }
-int lstm_tc_fwd(const int *, const float *, float *, float *, float *, int, int, int, int, float, void *, cudaStream_t) { return fail(CTCASR_ERR_UNSUPPORTED, "lstm_tc: not built"); }
-int lstm_tc_bwd(const int *, const float *, float *, const float *, const float *, int, int, int, int, void *, cudaStream_t) { return fail(CTCASR_ERR_UNSUPPORTED, "lstm_tc: not built"); }
+namespace lstm {
+
+constexpr int UPC = 32;                 // hidden units per CTA
+constexpr int NB = 32;                  // batch rows per MMA (N forward, real M rows backward)
+constexpr int BK = 64;                  // bf16 k-elements per stage row (128 B, SWIZZLE_128B)
+constexpr int NTHREADS = 224;           // 7 warps
+constexpr int EPI_THREADS = 128;
+
+// ---- forward smem ring: per stage A = 2 pieces x [128 x 64] bf16 (16 KB each), B = 2 x [32 x 64] (4 KB each)
+constexpr int F_A_PIECE = 128 * BK * 2, F_B_PIECE = NB * BK * 2;
+constexpr int F_STAGE = 2 * F_A_PIECE + 2 * F_B_PIECE;          // 40 KB
+constexpr int F_NSTAGE = 4;
+constexpr int F_XCH = 4 * NB * UPC * 4;                         // gate exchange [4][32 b][32 u] fp32
+constexpr int F_SMEM = F_NSTAGE * F_STAGE + F_XCH + 1024 + 256;
+// ---- backward ring: per stage Z = 2 pieces x [32 x 64] (dz), W = 2 x [32 x 64] (weights); the MMA reads
+// the Z tile as 128 rows (16 KB), so Z tiles are spaced 16 KB apart and the ring is padded at the end
+constexpr int B_Z_SLOT = 128 * BK * 2, B_W_PIECE = UPC * BK * 2;
+constexpr int B_STAGE = 2 * B_W_PIECE;                          // weights: 8 KB per stage
+constexpr int B_NSTAGE = 6;
+constexpr int B_ZSTAGE = 2 * 4096;                              // dz: 2 pieces x 4 KB actually loaded
+constexpr int B_XCH = NB * (UPC + 1) * 4;
+constexpr int B_SMEM = B_NSTAGE * (B_STAGE + B_ZSTAGE) + B_Z_SLOT /*over-read pad*/ + B_XCH + 1024 + 256;
+
+struct Params {
+    int T, B, H, CPD, use_len;
+    float forget_bias;
+    const int *seq_len;
+    float *gates;            // [T*B, 8H]  fwd: P -> activations;  bwd: activations -> dz
+    float *cstate;           // [T*B, 2H]
+    float *y;                // [T*B, 2H]  (fwd out)
+    const float *dy;         // [T*B, 2H]  (bwd in)
+    __nv_bfloat16 *xbuf;     // fwd: hbuf [2 pieces][2 dirs][2 parity][32][H]; bwd: dzbuf [2][2][2][32][4H]
+    unsigned int *counters;  // [2] step counters, [2] = error flag
+};
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+__device__ __forceinline__ void wait_counter(const unsigned int *ctr, unsigned int target, unsigned int *err)
+{
+    unsigned int v, spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+        if (++spins > (1u << 22)) { *err = 1; printf("ctcasr lstm: step barrier timed out (block %d, target %u, have %u)\n", blockIdx.x, target, v); __trap(); }
+    }
 }
+__device__ __forceinline__ void signal_counter(unsigned int *ctr)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void split2(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
+{
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// ================================================ forward =========================================
+__global__ void __launch_bounds__(NTHREADS, 1)
+lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH, const Params p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    const uint32_t xch_base = smem_base + F_NSTAGE * F_STAGE;
+    float *zs = reinterpret_cast<float *>(smem_gen + F_NSTAGE * F_STAGE);        // [4][32 b][32 u]
+    const uint32_t bar_base = xch_base + F_XCH;
+    auto fullA = [&](int s) { return bar_base + 8u * s; };
+    auto fullB = [&](int s) { return bar_base + 8u * (F_NSTAGE + s); };
+    auto empty = [&](int s) { return bar_base + 8u * (2 * F_NSTAGE + s); };
+    const uint32_t tfull = bar_base + 8u * (3 * F_NSTAGE), tempty = tfull + 8;
+    const uint32_t tmem_slot = tempty + 8;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+    auto a_addr = [&](int s, int pc) { return smem_base + s * F_STAGE + pc * F_A_PIECE; };
+    auto b_addr = [&](int s, int pc) { return smem_base + s * F_STAGE + 2 * F_A_PIECE + pc * F_B_PIECE; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x / p.CPD, c = blockIdx.x % p.CPD;
+    const int T = p.T, B = p.B, H = p.H, KB = H / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 1); ptx::mbar_init(fullB(s), 1); ptx::mbar_init(empty(s), 1); }
+        ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 4);
+        ptx::mbar_fence_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapH); }
+    if (warp == 6) ptx::tmem_alloc(tmem_slot, 32);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        // ---- weight tiles: independent of the recurrence, runs ahead across step boundaries ----
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const int row0 = (d * p.CPD + c) * 128;
+            for (int i = 0; i < T; ++i)
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(empty(stage), phase ^ 1);
+                    ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
+                    ptx::tma_load_3d(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage));
+                    ptx::tma_load_3d(a_addr(stage, 1), &mapW, kb * BK, row0, 1, fullA(stage));
+                    if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 5) {
+        // ---- h_{t-1} tiles: gated by the step barrier of this direction ------------------------
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int i = 0; i < T; ++i) {
+                wait_counter(p.counters + d, (unsigned)(p.CPD * i), p.counters + 2);
+                ptx::fence_proxy_async();
+                const int row0 = (d * 2 + (i & 1)) * NB;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(empty(stage), phase ^ 1);
+                    ptx::mbar_expect_tx(fullB(stage), 2 * F_B_PIECE);
+                    ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullB(stage));
+                    ptx::tma_load_3d(b_addr(stage, 1), &mapH, kb * BK, row0, 1, fullB(stage));
+                    if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ---- MMA issuer -------------------------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
+            constexpr int PA[3] = {0, 0, 1}, PB[3] = {0, 1, 0};
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (int i = 0; i < T; ++i) {
+                ptx::mbar_wait(tempty, tphase ^ 1);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(fullA(stage), phase);
+                    ptx::mbar_wait(fullB(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const uint64_t ad = ptx::make_smem_desc(a_addr(stage, PA[q]), 16, 1024, 2);
+                        const uint64_t bd = ptx::make_smem_desc(b_addr(stage, PB[q]), 16, 1024, 2);
+#pragma unroll
+                        for (int j = 0; j < BK / 16; ++j)
+                            ptx::mma_bf16(tmem_d, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (kb | q | j) != 0);
+                    }
+                    ptx::mma_commit(empty(stage));
+                    if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit(tfull);
+                tphase ^= 1;
+            }
+        }
+    } else {
+        // ---- cell math: warp = gate for the TMEM read, then thread = (unit, 8 batch rows) -------
+        const int g = warp, ul = lane;
+        const int tid = threadIdx.x, cu = tid & 31, bg = tid >> 5;         // cell ownership
+        const int ucol = c * UPC;                                           // first unit of this CTA
+        float creg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) creg[j] = 0.f;
+        int len8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int b = bg * 8 + j; len8[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
+        uint32_t tphase = 0;
+        const size_t GW = (size_t)8 * H;                                    // gates row pitch
+        for (int i = 0; i < T; ++i) {
+            const int tt = d == 0 ? i : T - 1 - i;
+            // pre-activations of my gate row for all batch rows (independent of the recurrence)
+            float pz[NB];
+            const float *prow = p.gates + (size_t)tt * B * GW + (size_t)d * 4 * H + (size_t)g * H + ucol + ul;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) pz[b] = b < B ? __ldg(prow + (size_t)b * GW) : 0.f;
+            ptx::mbar_wait(tfull, tphase);
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty);
+            tphase ^= 1;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) zs[(g * NB + b) * UPC + ul] = __uint_as_float(r[b]) + pz[b];
+            epi_bar();
+            __nv_bfloat16 *hb = p.xbuf + ((size_t)(d * 2 + ((i + 1) & 1)) * NB) * H + ucol + cu;
+            const size_t piece = (size_t)2 * 2 * NB * H;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = bg * 8 + j;
+                const float zi = zs[(0 * NB + b) * UPC + cu], zj = zs[(1 * NB + b) * UPC + cu];
+                const float zf = zs[(2 * NB + b) * UPC + cu], zo = zs[(3 * NB + b) * UPC + cu];
+                const bool live = tt < len8[j];
+                float gi = 0.f, gj = 0.f, gf = 0.f, go = 0.f, h = 0.f;
+                if (live) {
+                    gi = sigmoidf_(zi); gj = tanhf(zj); gf = sigmoidf_(zf + p.forget_bias); go = sigmoidf_(zo);
+                    creg[j] = gf * creg[j] + gi * gj;
+                    h = go * tanhf(creg[j]);
+                }
+                if (b < B) {
+                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    grow[0] = gi; grow[H] = gj; grow[2 * (size_t)H] = gf; grow[3 * (size_t)H] = go;
+                    p.cstate[((size_t)tt * B + b) * 2 * H + (size_t)d * H + ucol + cu] = creg[j];
+                    p.y[((size_t)tt * B + b) * 2 * H + (size_t)d * H + ucol + cu] = h;
+                }
+                __nv_bfloat16 hi, lo;
+                split2(h, hi, lo);
+                hb[(size_t)b * H] = hi;
+                hb[piece + (size_t)b * H] = lo;
+            }
+            __threadfence();
+            ptx::fence_proxy_async();
+            epi_bar();
+            if (tid == 0) signal_counter(p.counters + d);
+        }
+    }
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 6) ptx::tmem_dealloc(tmem_d, 32);
+}
+
+// ================================================ backward ========================================
+__global__ void __launch_bounds__(NTHREADS, 1)
+lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ, const Params p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    // layout: [W ring: B_NSTAGE x 8 KB][Z ring: B_NSTAGE x 8 KB][16 KB over-read pad][exchange][barriers]
+    const uint32_t w_base = smem_base, z_base = smem_base + B_NSTAGE * B_STAGE;
+    const uint32_t xch_off = B_NSTAGE * (B_STAGE + B_ZSTAGE) + B_Z_SLOT;
+    float *dhs = reinterpret_cast<float *>(smem_gen + xch_off);                   // [32 b][33]
+    const uint32_t bar_base = smem_base + xch_off + B_XCH;
+    auto fullW = [&](int s) { return bar_base + 8u * s; };
+    auto fullZ = [&](int s) { return bar_base + 8u * (B_NSTAGE + s); };
+    auto empty = [&](int s) { return bar_base + 8u * (2 * B_NSTAGE + s); };
+    const uint32_t tfull = bar_base + 8u * (3 * B_NSTAGE), tempty = tfull + 8;
+    const uint32_t tmem_slot = tempty + 8;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+    auto w_addr = [&](int s, int pc) { return w_base + s * B_STAGE + pc * B_W_PIECE; };
+    auto z_addr = [&](int s, int pc) { return z_base + s * B_ZSTAGE + pc * 4096; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x / p.CPD, c = blockIdx.x % p.CPD;
+    const int T = p.T, B = p.B, H = p.H, KB = 4 * H / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < B_NSTAGE; ++s) { ptx::mbar_init(fullW(s), 1); ptx::mbar_init(fullZ(s), 1); ptx::mbar_init(empty(s), 1); }
+        ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 1);
+        ptx::mbar_fence_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapZ); }
+    if (warp == 6) ptx::tmem_alloc(tmem_slot, 32);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {        // weight rows of my 32 units: Wh[d][u][0..4H), K-major as stored
+            int stage = 0; uint32_t phase = 0;
+            const int row0 = d * H + c * UPC;
+            for (int n = 0; n < T; ++n)
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(empty(stage), phase ^ 1);
+                    ptx::mbar_expect_tx(fullW(stage), 2 * B_W_PIECE);
+                    ptx::tma_load_3d(w_addr(stage, 0), &mapW, kb * BK, row0, 0, fullW(stage));
+                    ptx::tma_load_3d(w_addr(stage, 1), &mapW, kb * BK, row0, 1, fullW(stage));
+                    if (++stage == B_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {        // dz of the step processed before (all 4H gate columns of this direction)
+            int stage = 0; uint32_t phase = 0;
+            for (int n = 0; n < T; ++n) {
+                wait_counter(p.counters + d, (unsigned)(p.CPD * n), p.counters + 2);
+                ptx::fence_proxy_async();
+                const int row0 = (d * 2 + (n & 1)) * NB;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(empty(stage), phase ^ 1);
+                    ptx::mbar_expect_tx(fullZ(stage), 2 * 4096);
+                    ptx::tma_load_3d(z_addr(stage, 0), &mapZ, kb * BK, row0, 0, fullZ(stage));
+                    ptx::tma_load_3d(z_addr(stage, 1), &mapZ, kb * BK, row0, 1, fullZ(stage));
+                    if (++stage == B_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            // A = dz [128 lanes of which 32 batch rows are real], B = weights [32 units], K = 4H
+            const uint32_t idesc = ptx::make_idesc_bf16(128, UPC, 0, 0);
+            constexpr int PA[3] = {0, 0, 1}, PB[3] = {0, 1, 0};
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (int n = 0; n < T; ++n) {
+                ptx::mbar_wait(tempty, tphase ^ 1);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(fullW(stage), phase);
+                    ptx::mbar_wait(fullZ(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const uint64_t ad = ptx::make_smem_desc(z_addr(stage, PA[q]), 16, 1024, 2);
+                        const uint64_t bd = ptx::make_smem_desc(w_addr(stage, PB[q]), 16, 1024, 2);
+#pragma unroll
+                        for (int j = 0; j < BK / 16; ++j)
+                            ptx::mma_bf16(tmem_d, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (kb | q | j) != 0);
+                    }
+                    ptx::mma_commit(empty(stage));
+                    if (++stage == B_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit(tfull);
+                tphase ^= 1;
+            }
+        }
+    } else {
+        const int tid = threadIdx.x, cu = tid & 31, bg = tid >> 5;
+        const int ucol = c * UPC;
+        float dcreg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dcreg[j] = 0.f;
+        int len8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int b = bg * 8 + j; len8[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
+        uint32_t tphase = 0;
+        const size_t GW = (size_t)8 * H;
+        for (int n = 0; n < T; ++n) {
+            const int i = T - 1 - n;                       // processing step of the forward pass
+            const int tt = d == 0 ? i : T - 1 - i;
+            const int tp = d == 0 ? tt - 1 : tt + 1;       // frame processed before tt in the forward pass
+            // everything the cell needs that does not depend on the recurrence
+            float gi[8], gj[8], gf[8], go[8], cc[8], cp[8], dyv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = bg * 8 + j;
+                gi[j] = gj[j] = gf[j] = go[j] = cc[j] = cp[j] = dyv[j] = 0.f;
+                if (b < B) {
+                    const float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    gi[j] = grow[0]; gj[j] = grow[H]; gf[j] = grow[2 * (size_t)H]; go[j] = grow[3 * (size_t)H];
+                    const size_t so = (size_t)d * H + ucol + cu;
+                    cc[j] = p.cstate[((size_t)tt * B + b) * 2 * H + so];
+                    if (i > 0) cp[j] = p.cstate[((size_t)tp * B + b) * 2 * H + so];
+                    dyv[j] = p.dy[((size_t)tt * B + b) * 2 * H + so];
+                }
+            }
+            ptx::mbar_wait(tfull, tphase);
+            ptx::tc_fence_after();
+            if (warp == 0) {                                // lanes 0..31 of TMEM hold the 32 batch rows
+                uint32_t r[32];
+                ptx::tmem_ld32(tmem_d, r);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+#pragma unroll
+                for (int u = 0; u < UPC; ++u) dhs[lane * (UPC + 1) + u] = __uint_as_float(r[u]);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty);
+            }
+            tphase ^= 1;
+            epi_bar();
+            __nv_bfloat16 *zb = p.xbuf + ((size_t)(d * 2 + ((n + 1) & 1)) * NB) * 4 * H + ucol + cu;
+            const size_t piece = (size_t)2 * 2 * NB * 4 * H;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = bg * 8 + j;
+                const bool live = tt < len8[j];
+                float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+                if (live) {
+                    const float dh = dyv[j] + dhs[b * (UPC + 1) + cu];
+                    const float tc = tanhf(cc[j]);
+                    const float dc = dh * go[j] * (1.f - tc * tc) + dcreg[j];
+                    dzi = dc * gj[j] * gi[j] * (1.f - gi[j]);
+                    dzj = dc * gi[j] * (1.f - gj[j] * gj[j]);
+                    dzf = dc * cp[j] * gf[j] * (1.f - gf[j]);
+                    dzo = dh * tc * go[j] * (1.f - go[j]);
+                    dcreg[j] = dc * gf[j];
+                } else {
+                    dcreg[j] = 0.f;
+                }
+                if (b < B) {
+                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    grow[0] = dzi; grow[H] = dzj; grow[2 * (size_t)H] = dzf; grow[3 * (size_t)H] = dzo;
+                }
+                const float dzv[4] = {dzi, dzj, dzf, dzo};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    __nv_bfloat16 hi, lo;
+                    split2(dzv[q], hi, lo);
+                    zb[(size_t)b * 4 * H + (size_t)q * H] = hi;
+                    zb[piece + (size_t)b * 4 * H + (size_t)q * H] = lo;
+                }
+            }
+            __threadfence();
+            ptx::fence_proxy_async();
+            epi_bar();
+            if (tid == 0) signal_counter(p.counters + d);
+        }
+    }
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 6) ptx::tmem_dealloc(tmem_d, 32);
+}
+
+// ---- weight pre-packs --------------------------------------------------------------------------------
+// forward: Wh fp32 [2][H][4H] -> Wp bf16 [2 pieces][2*4H rows][H], row (d, c, g, ul) = gate column
+// g*H + 32c + ul of direction d, K (= h index) contiguous: the K-major A operand of the swap-AB MMA.
+__global__ void pack_wh_fwd_kernel(const float *__restrict__ wh, __nv_bfloat16 *__restrict__ wp, int H)
+{
+    __shared__ float tile[32][33];
+    const int d = blockIdx.z, k0 = blockIdx.y * 32, col0 = blockIdx.x * 32;     // col in [0, 4H)
+    const int tx = threadIdx.x, ty = threadIdx.y;                                // 32 x 8
+    const size_t GH = (size_t)4 * H;
+    for (int j = ty; j < 32; j += 8) tile[j][tx] = wh[((size_t)d * H + k0 + j) * GH + col0 + tx];
+    __syncthreads();
+    const size_t piece = (size_t)2 * GH * H;
+    for (int j = ty; j < 32; j += 8) {
+        const int col = col0 + j;                  // gate column g*H + u
+        const int g = col / H, u = col % H;
+        const size_t row = (size_t)d * GH + (size_t)(u / UPC) * 128 + g * UPC + (u % UPC);
+        __nv_bfloat16 hi, lo;
+        split2(tile[tx][j], hi, lo);
+        wp[row * H + k0 + tx] = hi;
+        wp[piece + row * H + k0 + tx] = lo;
+    }
+}
+// backward: plain 2-piece split of Wh viewed as [2H rows][4H]
+__global__ void split2_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        __nv_bfloat16 hi, lo;
+        split2(x[i], hi, lo);
+        out[i] = hi;
+        out[n + i] = lo;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+// bf16 [pieces][rows][inner], box [1][box_rows][64], SWIZZLE_128B
+static int make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t rows, uint32_t box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(CTCASR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {inner, rows, 2};
+    cuuint64_t strides[2] = {inner * 2, rows * inner * 2};
+    cuuint32_t box[3] = {BK, box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CTCASR_ERR_CUDA, "lstm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CTCASR_OK;
+}
+
+struct WsLayout { size_t wpack, xbuf, counters, total; };
+static WsLayout ws_layout(int H)
+{
+    WsLayout w;
+    w.wpack = 0;
+    const size_t wbytes = align_up((size_t)2 * 2 * 4 * H * H * 2, 1024);                // 2 pieces x [2*4H][H] bf16
+    w.xbuf = wbytes;
+    const size_t xbytes = align_up((size_t)2 * 2 * 2 * NB * 4 * H * 2, 1024);           // dzbuf is the larger user
+    w.counters = w.xbuf + xbytes;
+    w.total = w.counters + 1024;
+    return w;
+}
+
+static int check_coop(const void *kernel, int smem, int grid)
+{
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    CTCASR_CUDA_CHECK(cudaGetDevice(&dev));
+    CTCASR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CTCASR_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    CTCASR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CTCASR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NTHREADS, smem));
+    if (!coop || per_sm * sms < grid)
+        return fail(CTCASR_ERR_UNSUPPORTED, "lstm_tc: %d CTAs cannot be co-resident (%d SMs x %d)", grid, sms, per_sm);
+    return CTCASR_OK;
+}
+
+}  // namespace lstm
+
+bool lstm_tc_eligible(int T, int B, int H, int cell)
+{
+    return cell == CTCASR_CELL_LSTM && T >= 1 && B >= 1 && B <= lstm::NB && H >= 64 && H % 64 == 0 && 2 * (H / lstm::UPC) <= 148;
+}
+
+size_t lstm_tc_workspace_bytes(int B, int H)
+{
+    (void)B;
+    if (H < 64 || H % 64) return 0;
+    return lstm::ws_layout(H).total + 1024;
+}
+
+int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate, float *y,
+                int T, int B, int H, int use_len, float forget_bias, void *ws, cudaStream_t stream)
+{
+    using namespace lstm;
+    char *base = reinterpret_cast<char *>(align_up((size_t)(uintptr_t)ws, 1024));
+    const WsLayout L = ws_layout(H);
+    __nv_bfloat16 *wp = reinterpret_cast<__nv_bfloat16 *>(base + L.wpack);
+    __nv_bfloat16 *hbuf = reinterpret_cast<__nv_bfloat16 *>(base + L.xbuf);
+    unsigned int *ctr = reinterpret_cast<unsigned int *>(base + L.counters);
+    const int CPD = H / UPC, grid = 2 * CPD;
+    static int checked_grid = 0;
+    if (checked_grid != grid) { int rc = check_coop((const void *)lstm_fwd_kernel, F_SMEM, grid); if (rc) return rc; checked_grid = grid; }
+
+    pack_wh_fwd_kernel<<<dim3(4 * H / 32, H / 32, 2), dim3(32, 8), 0, stream>>>(wh, wp, H);
+    CTCASR_LAUNCH_CHECK();
+    CTCASR_CUDA_CHECK(cudaMemsetAsync(hbuf, 0, (size_t)2 * 2 * 2 * NB * H * 2, stream));      // h_{-1} = 0, padded batch rows = 0
+    CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
+    CUtensorMap mapW, mapH;
+    int rc = make_map(&mapW, wp, H, (uint64_t)2 * 4 * H, 128);
+    if (rc) return rc;
+    rc = make_map(&mapH, hbuf, H, (uint64_t)2 * 2 * NB, NB);
+    if (rc) return rc;
+    Params p;
+    p.T = T; p.B = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = forget_bias; p.seq_len = seq_len;
+    p.gates = gates; p.cstate = cstate; p.y = y; p.dy = nullptr; p.xbuf = hbuf; p.counters = ctr;
+    void *args[] = {&mapW, &mapH, &p};
+    CTCASR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)lstm_fwd_kernel, dim3(grid), dim3(NTHREADS), args, F_SMEM, stream));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return CTCASR_OK;
+}
+
+int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *cstate, const float *dy,
+                int T, int B, int H, int use_len, void *ws, cudaStream_t stream)
+{
+    using namespace lstm;
+    char *base = reinterpret_cast<char *>(align_up((size_t)(uintptr_t)ws, 1024));
+    const WsLayout L = ws_layout(H);
+    __nv_bfloat16 *wq = reinterpret_cast<__nv_bfloat16 *>(base + L.wpack);
+    __nv_bfloat16 *zbuf = reinterpret_cast<__nv_bfloat16 *>(base + L.xbuf);
+    unsigned int *ctr = reinterpret_cast<unsigned int *>(base + L.counters);
+    const int CPD = H / UPC, grid = 2 * CPD;
+    static int checked_grid = 0;
+    if (checked_grid != grid) { int rc = check_coop((const void *)lstm_bwd_kernel, B_SMEM, grid); if (rc) return rc; checked_grid = grid; }
+
+    const size_t nw = (size_t)2 * H * 4 * H;
+    split2_kernel<<<148 * 8, 256, 0, stream>>>(wh, wq, nw);
+    CTCASR_LAUNCH_CHECK();
+    CTCASR_CUDA_CHECK(cudaMemsetAsync(zbuf, 0, (size_t)2 * 2 * 2 * NB * 4 * H * 2, stream));  // no recurrent gradient into the last step
+    CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
+    CUtensorMap mapW, mapZ;
+    int rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC);
+    if (rc) return rc;
+    rc = make_map(&mapZ, zbuf, (uint64_t)4 * H, (uint64_t)2 * 2 * NB, NB);
+    if (rc) return rc;
+    Params p;
+    p.T = T; p.B = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = 0.f; p.seq_len = seq_len;
+    p.gates = gates; p.cstate = const_cast<float *>(cstate); p.y = nullptr; p.dy = dy; p.xbuf = zbuf; p.counters = ctr;
+    void *args[] = {&mapW, &mapZ, &p};
+    CTCASR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)lstm_bwd_kernel, dim3(grid), dim3(NTHREADS), args, B_SMEM, stream));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return CTCASR_OK;
+}
+
+}  // namespace ctcasr

@@ -55,6 +55,7 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
     CTCASR_REQUIRE(cell >= 0 && cell <= 2, "birnn_fwd: bad cell %d", cell);
     if (ws_bytes < ctcasr_birnn_workspace_bytes(T, B, in, H, cell)) return fail(CTCASR_ERR_WORKSPACE, "birnn_fwd: workspace too small");
     const int G = num_gates(cell), GH = G * H;
+    if (int rcs = gemm_scratch_check(compute, 1, T * B, 2 * GH, in)) return rcs;
     Reserve r = carve_reserve(reserve, T, B, H, G);
 
     // 1. hoisted input GEMM with the bias folded into the epilogue
@@ -62,11 +63,12 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
     g.A[0] = x; g.B[0] = wx; g.C[0] = r.gates;
     g.M = T * B; g.N = 2 * GH; g.K = in; g.lda = in; g.ldb = 2 * GH; g.ldc = 2 * GH;
     g.epi.mode = EPI_BIAS_ACT; g.epi.bias = bias; g.epi.act = 0;
+    g.precise = cell == CTCASR_CELL_RNN_RELU;      // the ReLU cell has a kink at 0; tanh / LSTM are smooth
     int rc = gemm(g, compute, stream);
     if (rc != CTCASR_OK) return rc;
 
     // 2. recurrence
-    if (compute == CTCASR_COMPUTE_TF32 && lstm_tc_eligible(T, B, H, cell)) {
+    if (compute != CTCASR_COMPUTE_FP32 && lstm_tc_eligible(T, B, H, cell)) {
         char *wsb = reinterpret_cast<char *>(ws) + align_up((size_t)4 * B * H * sizeof(float), 256);
         return lstm_tc_fwd(seq_len, wh, r.gates, r.cstate, y, T, B, H, use_len, forget_bias, wsb, stream);
     }
@@ -105,10 +107,13 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
     CTCASR_REQUIRE(cell >= 0 && cell <= 2, "birnn_bwd: bad cell %d", cell);
     if (ws_bytes < ctcasr_birnn_workspace_bytes(T, B, in, H, cell)) return fail(CTCASR_ERR_WORKSPACE, "birnn_bwd: workspace too small");
     const int G = num_gates(cell), GH = G * H;
+    if (int rcs = gemm_scratch_check(compute, 1, in, 2 * GH, T * B)) return rcs;
+    if (int rcs = gemm_scratch_check(compute, 2, H, GH, T * B)) return rcs;
+    if (int rcs = gemm_scratch_check(compute, 1, T * B, in, 2 * GH)) return rcs;
     Reserve r = carve_reserve(reserve, T, B, H, G);
     int rc;
 
-    if (compute == CTCASR_COMPUTE_TF32 && lstm_tc_eligible(T, B, H, cell)) {
+    if (compute != CTCASR_COMPUTE_FP32 && lstm_tc_eligible(T, B, H, cell)) {
         char *wsb = reinterpret_cast<char *>(ws) + align_up((size_t)4 * B * H * sizeof(float), 256);
         rc = lstm_tc_bwd(seq_len, wh, r.gates, r.cstate, dy, T, B, H, use_len, wsb, stream);
         if (rc != CTCASR_OK) return rc;

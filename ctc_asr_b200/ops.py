@@ -24,6 +24,23 @@ def _i32(t, name):
 
 
 _ws_cache = {}
+_scratch = {}
+
+
+def _call(fn, what, *args):
+    """Run a C-ABI call; when it asks for a bigger split-operand scratch arena, grow it and retry."""
+    lib = _lib.load()
+    rc = fn(*args)
+    if rc == -3 and lib.ctcasr_scratch_needed() > 0 and b"scratch" in lib.ctcasr_last_error():
+        need = int(lib.ctcasr_scratch_needed() * 1.25) + (1 << 20)
+        dev = torch.cuda.current_device()
+        _scratch[dev] = None
+        buf = torch.empty(need, dtype=torch.uint8, device="cuda")
+        _scratch[dev] = buf
+        torch.cuda.current_stream().synchronize()
+        check(lib.ctcasr_set_scratch(ptr(buf), buf.numel()), "set_scratch")
+        rc = fn(*args)
+    check(rc, what)
 
 
 def workspace(nbytes, device, tag="default"):
@@ -92,8 +109,8 @@ def dense_fwd(x, w, b, act=1, cutoff=20.0, drop_rate=0.0, seed=0, compute=_lib.C
     if w.shape[0] != K:
         raise ValueError("dense: x [%d,%d] and w %s do not match" % (M, K, tuple(w.shape)))
     y = torch.empty((M, N), dtype=torch.float32, device=x.device) if out is None else out
-    check(lib.ctcasr_dense_fwd(ptr(x), ptr(w), ptr(b), ptr(y), M, K, N, act, cutoff, drop_rate, seed, compute,
-                               _stream()), "dense_fwd")
+    _call(lib.ctcasr_dense_fwd, "dense_fwd", ptr(x), ptr(w), ptr(b), ptr(y), M, K, N, act, cutoff, drop_rate, seed,
+          compute, _stream())
     return y
 
 
@@ -103,8 +120,8 @@ def dense_bwd(x, w, y, dy, dw, db, dx=None, act=1, cutoff=20.0, drop_rate=0.0, s
     lib = _lib.load()
     M, K = x.shape
     N = w.shape[1]
-    check(lib.ctcasr_dense_bwd(ptr(x), ptr(w), ptr(y), ptr(dy), ptr(dx), ptr(dw), ptr(db), M, K, N, act, cutoff,
-                               drop_rate, seed, compute, _stream()), "dense_bwd")
+    _call(lib.ctcasr_dense_bwd, "dense_bwd", ptr(x), ptr(w), ptr(y), ptr(dy), ptr(dx), ptr(dw), ptr(db), M, K, N, act,
+          cutoff, drop_rate, seed, compute, _stream())
 
 
 def birnn_sizes(T, B, nin, H, cell):
@@ -120,9 +137,8 @@ def birnn_fwd(x, seq_len, wx, wh, bias, y, reserve, cell, use_len, forget_bias=1
     H = wh.shape[1]
     _, wsb = birnn_sizes(T, B, nin, H, cell)
     ws = workspace(wsb, x.device, "rnn")
-    check(lib.ctcasr_birnn_fwd(ptr(x), ptr(seq_len), ptr(wx), ptr(wh), ptr(bias), ptr(y), ptr(reserve),
-                               T, B, nin, H, cell, int(use_len), forget_bias, compute, ptr(ws), ws.numel(),
-                               _stream()), "birnn_fwd")
+    _call(lib.ctcasr_birnn_fwd, "birnn_fwd", ptr(x), ptr(seq_len), ptr(wx), ptr(wh), ptr(bias), ptr(y), ptr(reserve),
+          T, B, nin, H, cell, int(use_len), forget_bias, compute, ptr(ws), ws.numel(), _stream())
     return y
 
 
@@ -133,9 +149,9 @@ def birnn_bwd(x, seq_len, wx, wh, y, reserve, dy, dx, dwx, dwh, dbias, cell, use
     H = wh.shape[1]
     _, wsb = birnn_sizes(T, B, nin, H, cell)
     ws = workspace(wsb, x.device, "rnn")
-    check(lib.ctcasr_birnn_bwd(ptr(x), ptr(seq_len), ptr(wx), ptr(wh), ptr(y), ptr(reserve), ptr(dy), ptr(dx),
-                               ptr(dwx), ptr(dwh), ptr(dbias), T, B, nin, H, cell, int(use_len), compute,
-                               ptr(ws), ws.numel(), _stream()), "birnn_bwd")
+    _call(lib.ctcasr_birnn_bwd, "birnn_bwd", ptr(x), ptr(seq_len), ptr(wx), ptr(wh), ptr(y), ptr(reserve), ptr(dy),
+          ptr(dx), ptr(dwx), ptr(dwh), ptr(dbias), T, B, nin, H, cell, int(use_len), compute, ptr(ws), ws.numel(),
+          _stream())
 
 
 def adam(p, m, v, g, step, lr, beta1, beta2, eps, grad_scale=1.0):
@@ -151,6 +167,6 @@ def gemm(a, b, ta=False, tb=False, out=None, accumulate=False, compute=_lib.COMP
     K = a.shape[0] if ta else a.shape[1]
     N = b.shape[0] if tb else b.shape[1]
     c = torch.empty((M, N), dtype=torch.float32, device=a.device) if out is None else out
-    check(lib.ctcasr_gemm(ptr(a), ptr(b), ptr(c), M, N, K, int(ta), int(tb), a.stride(0), b.stride(0),
-                          c.stride(0), int(accumulate), compute, _stream()), "gemm")
+    _call(lib.ctcasr_gemm, "gemm", ptr(a), ptr(b), ptr(c), M, N, K, int(ta), int(tb), a.stride(0), b.stride(0),
+          c.stride(0), int(accumulate), compute, _stream())
     return c

@@ -49,17 +49,19 @@ class ModelConfig:
     num_features: int = NUM_FEATURES
     lstm_forget_bias: float = 1.0       # tf.nn.rnn_cell.LSTMCell default
     # --- B200 execution choices (not in the reference) ---------------------------------------
-    # 'fp32': SIMT FFMA kernels everywhere (exact-order fp32, parity mode)
-    # 'tf32': tcgen05 kind::tf32 on fp32-stored operands (fp32 accumulate)
-    compute: str = "tf32"
+    # 'fp32'  : SIMT FFMA kernels everywhere (exact-order fp32)
+    # 'bf16x3': tcgen05 kind::f16 on bf16-split operands, 3 (6 for ReLU-kinked layers) products
+    #           accumulated in fp32 TMEM: fp32-level accuracy at tensor-core speed (default)
+    # 'tf32'  : tcgen05 kind::tf32 on the fp32 operands: fastest, 2^-11 operand rounding
+    compute: str = "bf16x3"
 
     def __post_init__(self):
         if self.used_model != "ds1":
             raise ValueError('Unsupported model "{}" in flags.'.format(self.used_model))  # asr/model.py:163
         if self.rnn_cell not in RNN_CELLS:
             raise ValueError("rnn_cell must be one of {}".format(RNN_CELLS))
-        if self.compute not in ("fp32", "tf32"):
-            raise ValueError("compute must be 'fp32' or 'tf32'")
+        if self.compute not in ("fp32", "tf32", "bf16x3"):
+            raise ValueError("compute must be 'fp32', 'bf16x3' or 'tf32'")
 
     def replace(self, **kw):
         return dataclasses.replace(self, **kw)

@@ -42,7 +42,9 @@ enum { CTCASR_CELL_RNN_TANH = 0, CTCASR_CELL_RNN_RELU = 1, CTCASR_CELL_LSTM = 2,
 /* arithmetic of the GEMM-shaped work */
 enum {
     CTCASR_COMPUTE_FP32 = 0,      /* SIMT FFMA, fp32 everywhere (parity mode, any shape) */
-    CTCASR_COMPUTE_TF32 = 1       /* tcgen05 kind::tf32, fp32 storage + fp32 accumulate in TMEM */
+    CTCASR_COMPUTE_TF32 = 1,      /* tcgen05 kind::tf32, fp32 storage + fp32 accumulate in TMEM */
+    CTCASR_COMPUTE_BF16X3 = 2     /* tcgen05 kind::f16 on bf16-split operands (a = a1 + a2 [+ a3]),
+                                     3 or 6 products accumulated in fp32 TMEM: fp32-level accuracy */
 };
 
 /* per-utterance CTC status words (TF raises InvalidArgumentError for 1..3) */
@@ -128,6 +130,11 @@ int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const float *wx, co
 /* ---------------------------------------------------------------------------------------------
  * Plumbing around the path
  * -------------------------------------------------------------------------------------------- */
+/* Scratch arena for the bf16-split operand copies of CTCASR_COMPUTE_BF16X3 (device memory owned by the
+ * caller, 1024-B aligned).  A call that needs more returns CTCASR_ERR_WORKSPACE and
+ * ctcasr_scratch_needed() tells how much. */
+int ctcasr_set_scratch(void *ptr, size_t bytes);
+size_t ctcasr_scratch_needed(void);
 /* [A,B,C] -> [B,A,C]: batch-major sequences (asr/model.py:129) <-> the time-major layout used
  * internally and by the logits (asr/model.py:233) */
 int ctcasr_transpose01(const float *in, float *out, int A, int B, int C, void *stream);

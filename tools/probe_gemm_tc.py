@@ -8,6 +8,8 @@ import torch
 from ctc_asr_b200 import ops, _lib
 
 TF32, FP32 = _lib.COMPUTE_TF32, _lib.COMPUTE_FP32
+MODE = {'tf32': _lib.COMPUTE_TF32, 'bf16x3': _lib.COMPUTE_BF16X3}[os.environ.get('PROBE_MODE', 'bf16x3')]
+print('mode', os.environ.get('PROBE_MODE', 'bf16x3'))
 
 
 def case(M, N, K, ta, tb, seed=0):
@@ -16,7 +18,7 @@ def case(M, N, K, ta, tb, seed=0):
     b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
     A, B = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     try:
-        c = ops.gemm(A, B, ta=ta, tb=tb, compute=TF32)
+        c = ops.gemm(A, B, ta=ta, tb=tb, compute=MODE)
         torch.cuda.synchronize()
     except Exception as e:  # noqa
         print("M=%d N=%d K=%d ta=%d tb=%d  EXCEPTION %s" % (M, N, K, ta, tb, e)); return
@@ -50,12 +52,12 @@ if __name__ == "__main__":
         c = torch.empty((M, N), device="cuda")
         try:
             for _ in range(2):
-                ops.gemm(a, b, ta=bool(ta), tb=bool(tb), out=c, compute=TF32)
+                ops.gemm(a, b, ta=bool(ta), tb=bool(tb), out=c, compute=MODE)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(5):
-                ops.gemm(a, b, ta=bool(ta), tb=bool(tb), out=c, compute=TF32)
+                ops.gemm(a, b, ta=bool(ta), tb=bool(tb), out=c, compute=MODE)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             torch.backends.cuda.matmul.allow_tf32 = True
