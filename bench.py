@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "ctc"])
-    ap.add_argument("--compute", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--compute", default="bf16x3", choices=["bf16x3", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=CFG2_B)
     ap.add_argument("--frames", type=int, default=CFG2_T)
     ap.add_argument("--units", type=int, default=2048, help="debug: shrink D and H")
@@ -227,8 +227,10 @@ def run_ours(args):
     e2e = frames * K / (ms_e2e * 1e-3)
     flops_step = 3.0 * flops_per_frame_fwd(cfg) * B * T            # per GPU
     tflops = flops_step * K / (ms * 1e-3) / 1e12
-    # tensor roofline of the step: tf32 runs at half the measured bf16 rate (no tf32 peak measured)
-    peak = peaks["bf16_tflops_sustained"] / 2.0 if args.compute == "tf32" else 2 * 148 * 128 * 1.9e-3
+    # tensor roofline of the step: bf16x3 issues 3 bf16 MMAs per algorithmic MAC (peak = bf16 / 3),
+    # tf32 runs at half the measured bf16 rate (no tf32 peak was measured), fp32 = SIMT FFMA peak
+    peak = {"bf16x3": peaks["bf16_tflops_sustained"] / 3.0, "tf32": peaks["bf16_tflops_sustained"] / 2.0,
+            "fp32": 2 * 148 * 128 * 1.9e-3}[args.compute]
     line = {
         "metric": "audio-frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -244,7 +246,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
                      "traffic": None,
-                     "note": "whole-step GEMM FLOPs (3 x fwd) / step time; peak = %s bf16 sustained / 2 for tf32" % peaks["source"]},
+                     "note": "whole-step algorithmic GEMM FLOPs (3 x fwd) / step time; peak = %s bf16 sustained / 3 (bf16x3 issues 3 MMAs per MAC), / 2 for tf32" % peaks["source"]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ccfg = cfg.replace(dense_dropout_rate=0.0)
