@@ -27,6 +27,7 @@
 
 #include <cuda_bf16.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace ctcasr {
 namespace lstm {
@@ -432,6 +433,201 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
     if (warp == 6) ptx::tmem_dealloc(tmem_d, 32);
 }
 
+// ================================== backward, 4-CTA cluster split-K ================================
+// dh_{t-1}[b, u] = sum over the 4H gate columns of dz_t[b, :] Wh[u, :].  A cluster of 4 CTAs owns 128
+// hidden units; CTA q contracts the H columns of gate q with a full M = 128 tile
+//   D_q[128 units, 32 batch] = Wh[units, q*H .. (q+1)*H) . dz_t[:, q*H .. (q+1)*H)^T
+// (the same pipeline shape as the forward kernel), then warp w of every CTA ships its 32 unit rows
+// to CTA w of the cluster through distributed shared memory, and CTA w adds the four partials and
+// runs the cell backward for those 32 units.  Per step and CTA: 1 MB of weights (streamed), 256 KB
+// of dz (L2), 384 MMAs — a quarter of what the single-CTA formulation below needs.
+constexpr int C_XCH = 4 * NB * UPC * 4;                          // slots [4 sources][32 b][32 u] fp32
+constexpr int C_SMEM = F_NSTAGE * F_STAGE + C_XCH + 1024 + 256;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ, const Params p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    const uint32_t xch_base = smem_base + F_NSTAGE * F_STAGE;
+    const float *slots = reinterpret_cast<const float *>(smem_gen + F_NSTAGE * F_STAGE);   // [4][32 b][32 u]
+    const uint32_t bar_base = xch_base + C_XCH;
+    auto fullA = [&](int s) { return bar_base + 8u * s; };
+    auto fullB = [&](int s) { return bar_base + 8u * (F_NSTAGE + s); };
+    auto empty = [&](int s) { return bar_base + 8u * (2 * F_NSTAGE + s); };
+    const uint32_t tfull = bar_base + 8u * (3 * F_NSTAGE), tempty = tfull + 8, xfull = tempty + 8;
+    const uint32_t tmem_slot = xfull + 8;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+    auto a_addr = [&](int s, int pc) { return smem_base + s * F_STAGE + pc * F_A_PIECE; };
+    auto b_addr = [&](int s, int pc) { return smem_base + s * F_STAGE + 2 * F_A_PIECE + pc * F_B_PIECE; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = (int)ptx::cluster_ctarank();                  // gate / K-range of this CTA
+    const int cid = blockIdx.x >> 2;
+    const int UBD = p.H / 128;                                  // unit blocks per direction
+    const int d = cid / UBD, ub = cid % UBD;
+    const int T = p.T, B = p.B, H = p.H, KB = H / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 1); ptx::mbar_init(fullB(s), 1); ptx::mbar_init(empty(s), 1); }
+        ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
+        ptx::mbar_fence_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapZ); }
+    if (warp == 6) ptx::tmem_alloc(tmem_slot, 32);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();            // every CTA's barriers exist before anyone arrives remotely
+    ptx::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {        // Wh[d][128 units of the cluster][columns of gate q], K-major as stored
+            int stage = 0; uint32_t phase = 0;
+            const int row0 = d * H + ub * 128;
+            for (int n = 0; n < T; ++n)
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(empty(stage), phase ^ 1);
+                    ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
+                    ptx::tma_load_3d(a_addr(stage, 0), &mapW, q * H + kb * BK, row0, 0, fullA(stage));
+                    ptx::tma_load_3d(a_addr(stage, 1), &mapW, q * H + kb * BK, row0, 1, fullA(stage));
+                    if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {        // dz of the step processed before, gate-q columns, all batch rows
+            int stage = 0; uint32_t phase = 0;
+            for (int n = 0; n < T; ++n) {
+                wait_counter(p.counters + d, (unsigned)(p.CPD * n), p.counters + 2);
+                ptx::fence_proxy_async();
+                const int row0 = (d * 2 + (n & 1)) * NB;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(empty(stage), phase ^ 1);
+                    ptx::mbar_expect_tx(fullB(stage), 2 * F_B_PIECE);
+                    ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * H + kb * BK, row0, 0, fullB(stage));
+                    ptx::tma_load_3d(b_addr(stage, 1), &mapZ, q * H + kb * BK, row0, 1, fullB(stage));
+                    if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
+            constexpr int PA[3] = {0, 0, 1}, PB[3] = {0, 1, 0};
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (int n = 0; n < T; ++n) {
+                ptx::mbar_wait(tempty, tphase ^ 1);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(fullA(stage), phase);
+                    ptx::mbar_wait(fullB(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int pr = 0; pr < 3; ++pr) {
+                        const uint64_t ad = ptx::make_smem_desc(a_addr(stage, PA[pr]), 16, 1024, 2);
+                        const uint64_t bd = ptx::make_smem_desc(b_addr(stage, PB[pr]), 16, 1024, 2);
+#pragma unroll
+                        for (int j = 0; j < BK / 16; ++j)
+                            ptx::mma_bf16(tmem_d, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (kb | pr | j) != 0);
+                    }
+                    ptx::mma_commit(empty(stage));
+                    if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit(tfull);
+                tphase ^= 1;
+            }
+        }
+    } else {
+        const int tid = threadIdx.x, cu = tid & 31, bg = tid >> 5;
+        const int ucol = ub * 128 + q * UPC;                        // the 32 units whose cells this CTA owns
+        float dcreg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dcreg[j] = 0.f;
+        int len8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int b = bg * 8 + j; len8[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
+        uint32_t tphase = 0;
+        const size_t GW = (size_t)8 * H;
+        // destination of my TMEM rows: CTA `warp` of the cluster, slot q, [b][lane]
+        const uint32_t remote_slot = ptx::mapa(xch_base + (uint32_t)(q * NB * UPC) * 4u, (uint32_t)warp);
+        const uint32_t remote_bar = ptx::mapa(xfull, (uint32_t)warp);
+        for (int n = 0; n < T; ++n) {
+            const int i = T - 1 - n;
+            const int tt = d == 0 ? i : T - 1 - i;
+            const int tp = d == 0 ? tt - 1 : tt + 1;
+            float gi[8], gj[8], gf[8], go[8], cc[8], cp[8], dyv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = bg * 8 + j;
+                gi[j] = gj[j] = gf[j] = go[j] = cc[j] = cp[j] = dyv[j] = 0.f;
+                if (b < B) {
+                    const float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    gi[j] = grow[0]; gj[j] = grow[H]; gf[j] = grow[2 * (size_t)H]; go[j] = grow[3 * (size_t)H];
+                    const size_t so = (size_t)d * H + ucol + cu;
+                    cc[j] = p.cstate[((size_t)tt * B + b) * 2 * H + so];
+                    if (i > 0) cp[j] = p.cstate[((size_t)tp * B + b) * 2 * H + so];
+                    dyv[j] = p.dy[((size_t)tt * B + b) * 2 * H + so];
+                }
+            }
+            ptx::mbar_wait(tfull, tphase);
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);      // rows = units 32*warp + lane of the block
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+#pragma unroll
+            for (int b = 0; b < NB; ++b) ptx::st_cluster_f32(remote_slot + (uint32_t)(b * UPC + lane) * 4u, __uint_as_float(r[b]));
+            __syncwarp();
+            if (lane == 0) { ptx::mbar_arrive(tempty); ptx::mbar_arrive_remote(remote_bar); }
+            ptx::mbar_wait_cluster(xfull, tphase);                          // the four partials of my units have landed
+            tphase ^= 1;
+            __nv_bfloat16 *zb = p.xbuf + ((size_t)(d * 2 + ((n + 1) & 1)) * NB) * 4 * H + ucol + cu;
+            const size_t piece = (size_t)2 * 2 * NB * 4 * H;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = bg * 8 + j;
+                const bool live = tt < len8[j];
+                float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+                if (live) {
+                    const int o = b * UPC + cu;
+                    const float dh = dyv[j] + ((slots[o] + slots[NB * UPC + o]) + (slots[2 * NB * UPC + o] + slots[3 * NB * UPC + o]));
+                    const float tc = tanhf(cc[j]);
+                    const float dc = dh * go[j] * (1.f - tc * tc) + dcreg[j];
+                    dzi = dc * gj[j] * gi[j] * (1.f - gi[j]);
+                    dzj = dc * gi[j] * (1.f - gj[j] * gj[j]);
+                    dzf = dc * cp[j] * gf[j] * (1.f - gf[j]);
+                    dzo = dh * tc * go[j] * (1.f - go[j]);
+                    dcreg[j] = dc * gf[j];
+                } else {
+                    dcreg[j] = 0.f;
+                }
+                if (b < B) {
+                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    grow[0] = dzi; grow[H] = dzj; grow[2 * (size_t)H] = dzf; grow[3 * (size_t)H] = dzo;
+                }
+                const float dzv[4] = {dzi, dzj, dzf, dzo};
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    __nv_bfloat16 hi, lo;
+                    split2(dzv[g4], hi, lo);
+                    zb[(size_t)b * 4 * H + (size_t)g4 * H] = hi;
+                    zb[piece + (size_t)b * 4 * H + (size_t)g4 * H] = lo;
+                }
+            }
+            __threadfence();
+            ptx::fence_proxy_async();
+            epi_bar();
+            if (tid == 0) signal_counter(p.counters + d);
+        }
+    }
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();            // no CTA exits while a peer may still write into its shared memory
+    if (warp == 6) ptx::tmem_dealloc(tmem_d, 32);
+}
+
 // ---- weight pre-packs --------------------------------------------------------------------------------
 // forward: Wh fp32 [2][H][4H] -> Wp bf16 [2 pieces][2*4H rows][H], row (d, c, g, ul) = gate column
 // g*H + 32c + ul of direction d, K (= h index) contiguous: the K-major A operand of the swap-AB MMA.
@@ -577,22 +773,47 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     __nv_bfloat16 *zbuf = reinterpret_cast<__nv_bfloat16 *>(base + L.xbuf);
     unsigned int *ctr = reinterpret_cast<unsigned int *>(base + L.counters);
     const int CPD = H / UPC, grid = 2 * CPD;
-    static int checked_grid = 0;
-    if (checked_grid != grid) { int rc = check_coop((const void *)lstm_bwd_kernel, B_SMEM, grid); if (rc) return rc; checked_grid = grid; }
-
     const size_t nw = (size_t)2 * H * 4 * H;
     split2_kernel<<<148 * 8, 256, 0, stream>>>(wh, wq, nw);
     CTCASR_LAUNCH_CHECK();
     CTCASR_CUDA_CHECK(cudaMemsetAsync(zbuf, 0, (size_t)2 * 2 * 2 * NB * 4 * H * 2, stream));  // no recurrent gradient into the last step
     CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
-    CUtensorMap mapW, mapZ;
-    int rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC);
-    if (rc) return rc;
-    rc = make_map(&mapZ, zbuf, (uint64_t)4 * H, (uint64_t)2 * 2 * NB, NB);
-    if (rc) return rc;
     Params p;
     p.T = T; p.B = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = 0.f; p.seq_len = seq_len;
     p.gates = gates; p.cstate = const_cast<float *>(cstate); p.y = nullptr; p.dy = dy; p.xbuf = zbuf; p.counters = ctr;
+    CUtensorMap mapW, mapZ;
+    int rc = make_map(&mapZ, zbuf, (uint64_t)4 * H, (uint64_t)2 * 2 * NB, NB);
+    if (rc) return rc;
+
+    // preferred: 4-CTA cluster split-K kernel (needs H % 128 == 0 and all clusters co-resident)
+    static int cluster_ok_grid = 0, cluster_bad_grid = 0;
+    const bool no_cluster = getenv("CTCASR_LSTM_NO_CLUSTER") != nullptr;
+    if (H % 128 == 0 && cluster_bad_grid != grid && !no_cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C_SMEM; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cluster_ok_grid != grid) {
+            CTCASR_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
+            int nclusters = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, lstm_bwd_cluster_kernel, &cfg);
+            if (e == cudaSuccess && nclusters * 4 >= grid) cluster_ok_grid = grid;
+            else { cluster_bad_grid = grid; (void)cudaGetLastError(); }
+        }
+        if (cluster_ok_grid == grid) {
+            rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, 128);
+            if (rc) return rc;
+            CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel, mapW, mapZ, p));
+            g_launch_count.fetch_add(1, std::memory_order_relaxed);
+            return CTCASR_OK;
+        }
+    }
+    static int checked_grid = 0;
+    if (checked_grid != grid) { rc = check_coop((const void *)lstm_bwd_kernel, B_SMEM, grid); if (rc) return rc; checked_grid = grid; }
+    rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC);
+    if (rc) return rc;
     void *args[] = {&mapW, &mapZ, &p};
     CTCASR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)lstm_bwd_kernel, dim3(grid), dim3(NTHREADS), args, B_SMEM, stream));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
