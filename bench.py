@@ -212,12 +212,17 @@ def run_ours(args):
         loss = model.train_step(a, b, (c, d), global_batch=gb, allreduce=allreduce)
         return float(loss)          # D2H read of the step's result
 
+    import ctypes
     for _ in range(W):
         step_resident()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = lib.ctcasr_launch_count()
+    lib.ctcasr_profile_enable(1)            # CUDA events around the hot kernels, on the launching stream
     ms = timed(step_resident, K)
+    prof_ms, prof_n = (ctypes.c_double * 5)(), (ctypes.c_int * 5)()
+    lib.ctcasr_profile_collect(prof_ms, prof_n, 5)
+    lib.ctcasr_profile_enable(0)
     launches = lib.ctcasr_launch_count() - l0
     clocks = sampler.finish()
     ms_e2e = timed(step_e2e, K)
@@ -225,12 +230,28 @@ def run_ours(args):
     frames = B * T * world
     value = frames * K / (ms * 1e-3)
     e2e = frames * K / (ms_e2e * 1e-3)
+    H, D = cfg.num_units_rnn, cfg.num_units_dense
     flops_step = 3.0 * flops_per_frame_fwd(cfg) * B * T            # per GPU
-    tflops = flops_step * K / (ms * 1e-3) / 1e12
-    # tensor roofline of the step: bf16x3 issues 3 bf16 MMAs per algorithmic MAC (peak = bf16 / 3),
-    # tf32 runs at half the measured bf16 rate (no tf32 peak was measured), fp32 = SIMT FFMA peak
-    peak = {"bf16x3": peaks["bf16_tflops_sustained"] / 3.0, "tf32": peaks["bf16_tflops_sustained"] / 2.0,
-            "fp32": 2 * 148 * 128 * 1.9e-3}[args.compute]
+    # ---- roofline of the dominant kernel: the persistent LSTM recurrence (fwd + bwd launches) ----------
+    # algorithmic bytes per time step and layer = the recurrent weights of both directions, which the
+    # kernel has to stream once per step because they do not fit on chip (two bf16 pieces = 4 B per
+    # weight) + the step's slice of P/gates (read + write) and c, y / dy
+    w_bytes = 2 * H * 4 * H * 4
+    act_bytes = B * 8 * H * 4 * 2 + B * 2 * H * 4 * 2
+    lstm_launches = prof_n[0] + prof_n[1]
+    lstm_ms = prof_ms[0] + prof_ms[1]
+    lstm_bytes = (w_bytes + act_bytes) * T * lstm_launches
+    lstm_gbs = lstm_bytes / (lstm_ms * 1e-3) / 1e9 if lstm_ms > 0 else 0.0
+    # ---- second class: the tcgen05 GEMMs (everything GEMM-shaped but the recurrence and the 29-class layer)
+    rec_flops = 2 * (cfg.num_layers_rnn * 2 * 2 * H * 4 * H)      # recurrent matvec fwd + bwd, per frame
+    tc_flops = (3.0 * flops_per_frame_fwd(cfg) - rec_flops - 3 * 2 * D * cfg.num_classes) * B * T * K
+    gemm_tflops = tc_flops / (prof_ms[2] * 1e-3) / 1e12 if prof_ms[2] > 0 else 0.0
+    mma_per_mac = {"bf16x3": 3.0, "tf32": 2.0, "fp32": 1.0}[args.compute]
+    gemm_peak = peaks["bf16_tflops_sustained"] / mma_per_mac
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "lstm_dram_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     line = {
         "metric": "audio-frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -239,14 +260,28 @@ def run_ours(args):
                                "L=%d labels, fwd + CTC + bwd + %sAdam, dense dropout 0.1" % (
                                    args.units, B, T, L, "NCCL all-reduce + " if world > 1 else ""),
                    "global_batch": gb, "params": model.num_params,
+                   "arithmetic": {"bf16x3": "fp32 storage; GEMMs and recurrence as 3 (6 for ReLU-kinked layers) bf16 tcgen05 products "
+                                            "of split operands, fp32 TMEM accumulation (fp32-level accuracy)",
+                                  "tf32": "fp32 storage; tcgen05 kind::tf32", "fp32": "SIMT FFMA"}[args.compute],
                    "l2_policy": "inputs larger than L2 (>=7 GB of activations per step), no explicit flush"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(x.nbytes + sl.nbytes + lab.nbytes + ll.nbytes),
                 "d2h_bytes_per_step": 4 + 4 * B},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
-                     "traffic": None,
-                     "note": "whole-step algorithmic GEMM FLOPs (3 x fwd) / step time; peak = %s bf16 sustained / 3 (bf16x3 issues 3 MMAs per MAC), / 2 for tf32" % peaks["source"]},
+        "roofline": {"kernel": "lstm_fwd_kernel + lstm_bwd_cluster_kernel (persistent recurrence, %d launches)" % lstm_launches,
+                     "bound": "hbm", "achieved": lstm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": lstm_gbs / peaks["hbm_gbs"], "traffic": traffic,
+                     "ms_per_launch": lstm_ms / max(lstm_launches, 1), "share_of_step": lstm_ms / ms,
+                     "note": "algorithmic bytes = per time step the recurrent weights of both directions (streamed: 128 MiB "
+                             "does not fit on chip) + gate/state slices; peak of %s" % peaks["source"]},
+        "roofline_gemm": {"kernel": "gemm_tc_kernel (%d launches)" % prof_n[2], "bound": "tensor", "achieved": gemm_tflops,
+                          "peak": gemm_peak, "unit": "TFLOP/s", "frac": gemm_tflops / gemm_peak if gemm_peak else None,
+                          "share_of_step": prof_ms[2] / ms,
+                          "note": "algorithmic GEMM FLOPs / event time; peak = %s bf16 sustained / %g MMAs per MAC" % (
+                              peaks["source"], mma_per_mac)},
+        "kernel_ms_per_step": {"lstm_fwd": prof_ms[0] / K, "lstm_bwd": prof_ms[1] / K, "gemm_tc": prof_ms[2] / K,
+                               "ctc": prof_ms[3] / K, "operand_split": prof_ms[4] / K},
+        "step_tflops": flops_step * K / (ms * 1e-3) / 1e12,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ccfg = cfg.replace(dense_dropout_rate=0.0)

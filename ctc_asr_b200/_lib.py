@@ -31,6 +31,8 @@ SIGNATURES = {
     "ctcasr_birnn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
     "ctcasr_birnn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ctcasr_profile_enable": (_i, [_i]),
+    "ctcasr_profile_collect": (_i, [_vp, _vp, _i]),
     "ctcasr_set_scratch": (_i, [_vp, _sz]),
     "ctcasr_scratch_needed": (_sz, []),
     "ctcasr_transpose01": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -3,9 +3,43 @@
 // library-level bookkeeping (version, last error, launch counter).
 #include "gemm.cuh"
 
+#include <utility>
+#include <vector>
+
 namespace ctcasr {
 thread_local char g_last_error[512] = "";
 std::atomic<uint64_t> g_launch_count{0};
+
+// ---- profiling: event pairs recorded around the hot kernels when enabled ---------------------------
+namespace {
+struct ProfState {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairs[PROF_NTAGS];
+    cudaEvent_t open_start[PROF_NTAGS] = {};
+    size_t used = 0;
+    cudaEvent_t get()
+    {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+} g_prof;
+}  // namespace
+void prof_begin(int tag, cudaStream_t s)
+{
+    if (!g_prof.on) return;
+    cudaEvent_t e = g_prof.get();
+    cudaEventRecord(e, s);
+    g_prof.open_start[tag] = e;
+}
+void prof_end(int tag, cudaStream_t s)
+{
+    if (!g_prof.on || !g_prof.open_start[tag]) return;
+    cudaEvent_t e = g_prof.get();
+    cudaEventRecord(e, s);
+    g_prof.pairs[tag].push_back({g_prof.open_start[tag], e});
+    g_prof.open_start[tag] = nullptr;
+}
 
 int gemm(const GemmArgs &g, int compute, cudaStream_t stream)
 {
@@ -19,6 +53,32 @@ using namespace ctcasr;
 extern "C" int ctcasr_abi_version(void) { return CTCASR_ABI_VERSION; }
 extern "C" const char *ctcasr_last_error(void) { return g_last_error; }
 extern "C" uint64_t ctcasr_launch_count(void) { return g_launch_count.load(); }
+
+namespace ctcasr { void lstm_tc_set_trace(unsigned long long *buf); }
+// debugging aid (not in ctcasr.h): device buffer [grid][64][8] of globaltimer stamps written by the LSTM forward kernel
+extern "C" int ctcasr_debug_lstm_trace(void *buf) { ctcasr::lstm_tc_set_trace(reinterpret_cast<unsigned long long *>(buf)); return 0; }
+
+extern "C" int ctcasr_profile_enable(int on)
+{
+    g_prof.on = on != 0;
+    if (on) { g_prof.used = 0; for (auto &v : g_prof.pairs) v.clear(); }
+    return CTCASR_OK;
+}
+// Synchronises the device and returns, per kernel class, the summed event time (ms) and the count.
+extern "C" int ctcasr_profile_collect(double *ms, int *count, int ntags)
+{
+    CTCASR_REQUIRE(ms && count && ntags >= 1, "profile_collect: bad args");
+    CTCASR_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int t = 0; t < ntags; ++t) {
+        ms[t] = 0.0; count[t] = 0;
+        if (t >= PROF_NTAGS) continue;
+        for (auto &pr : g_prof.pairs[t]) {
+            float v = 0.f;
+            if (cudaEventElapsedTime(&v, pr.first, pr.second) == cudaSuccess) { ms[t] += v; count[t]++; }
+        }
+    }
+    return CTCASR_OK;
+}
 
 extern "C" int ctcasr_gemm(const float *A, const float *B, float *C, int M, int N, int K,
                            int ta, int tb, int lda, int ldb, int ldc, int accumulate, int compute, void *stream)

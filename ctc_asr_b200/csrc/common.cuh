@@ -44,6 +44,16 @@ inline int fail(int code, const char *fmt, ...)
         CTCASR_CUDA_CHECK(cudaGetLastError());                                                    \
     } while (0)
 
+// ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline) ---
+enum ProfTag : int { PROF_LSTM_FWD = 0, PROF_LSTM_BWD = 1, PROF_GEMM_TC = 2, PROF_CTC = 3, PROF_SPLIT = 4, PROF_NTAGS = 5 };
+void prof_begin(int tag, cudaStream_t s);
+void prof_end(int tag, cudaStream_t s);
+struct ProfScope {
+    int tag; cudaStream_t s;
+    ProfScope(int t, cudaStream_t st) : tag(t), s(st) { prof_begin(tag, s); }
+    ~ProfScope() { prof_end(tag, s); }
+};
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

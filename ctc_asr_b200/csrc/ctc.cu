@@ -500,6 +500,7 @@ extern "C" int ctcasr_ctc_loss(const float *logits, int T, int B, int V, int bla
             CTCASR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
             smem_set = pl.smem;
         }
+        ProfScope prof(PROF_CTC, (cudaStream_t)stream);
         kernel<<<B, NT, pl.smem, (cudaStream_t)stream>>>(p);
         CTCASR_LAUNCH_CHECK();
         return CTCASR_OK;

@@ -361,6 +361,7 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
             const size_t ta4 = (size_t)a_rows * (a_cols / 4), tb4 = (size_t)b_rows * (b_cols / 4);
             const int ga = (int)((ta4 + 255) / 256 < 148 * 16 ? (ta4 + 255) / 256 : 148 * 16);
             const int gb = (int)((tb4 + 255) / 256 < 148 * 16 ? (tb4 + 255) / 256 : 148 * 16);
+            ProfScope prof_split(PROF_SPLIT, stream);
             split_bf16_kernel<NP><<<ga, 256, 0, stream>>>(g.A[z], a_rows, a_cols, g.lda, sa, ldoa);
             CTCASR_LAUNCH_CHECK();
             split_bf16_kernel<NP><<<gb, 256, 0, stream>>>(g.B[z], b_rows, b_cols, g.ldb, sb, ldob);
@@ -400,6 +401,7 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
         attr_set = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    ProfScope prof_gemm(PROF_GEMM_TC, stream);
     gemm_tc_kernel<MODE><<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
     CTCASR_LAUNCH_CHECK();
     return CTCASR_OK;

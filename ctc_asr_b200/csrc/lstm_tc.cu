@@ -41,7 +41,7 @@ constexpr int EPI_THREADS = 128;
 // ---- forward smem ring: per stage A = 2 pieces x [128 x 64] bf16 (16 KB each), B = 2 x [32 x 64] (4 KB each)
 constexpr int F_A_PIECE = 128 * BK * 2, F_B_PIECE = NB * BK * 2;
 constexpr int F_STAGE = 2 * F_A_PIECE + 2 * F_B_PIECE;          // 40 KB
-constexpr int F_NSTAGE = 4;
+constexpr int F_NSTAGE = 5;
 constexpr int F_XCH = 4 * NB * UPC * 4;                         // gate exchange [4][32 b][32 u] fp32
 constexpr int F_SMEM = F_NSTAGE * F_STAGE + F_XCH + 1024 + 256;
 // ---- backward ring: per stage Z = 2 pieces x [32 x 64] (dz), W = 2 x [32 x 64] (weights); the MMA reads
@@ -63,6 +63,10 @@ struct Params {
     const float *dy;         // [T*B, 2H]  (bwd in)
     __nv_bfloat16 *xbuf;     // fwd: hbuf [2 pieces][2 dirs][2 parity][32][H]; bwd: dzbuf [2][2][2][32][4H]
     unsigned int *counters;  // [2] step counters, [2] = error flag
+    unsigned long long *trace;  // optional [grid][64 steps][8 slots] globaltimer stamps (tools/lstm_trace.py)
+    int stagger_ns;          // start delay of direction 1
+    int nprod;               // timing experiments only: number of split products issued (3 = correct)
+    int kb_keep;             // weight k-blocks [0, kb_keep) are loaded with L2 evict_last, the rest evict_first
 };
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
@@ -79,6 +83,24 @@ __device__ __forceinline__ void wait_counter(const unsigned int *ctr, unsigned i
 __device__ __forceinline__ void signal_counter(unsigned int *ctr)
 {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+__device__ __forceinline__ void stamp(const Params &p, int step, int slot)
+{
+    if (p.trace && step < 64) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[((size_t)blockIdx.x * 64 + step) * 8 + slot] = t;
+    }
+}
+// The two directions are independent recurrences that share the memory system: starting one of them
+// half a step late makes one direction stream weights while the other is in its serial phase
+// (MMA tail, cell math, fence, step barrier) instead of both pulling at the same time.
+__device__ __forceinline__ void stagger_wait(int ns)
+{
+    if (ns <= 0) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < (unsigned long long)ns);
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -128,22 +150,27 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const int row0 = (d * p.CPD + c) * 128;
+            const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int i = 0; i < T; ++i)
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
                     ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
-                    ptx::tma_load_3d(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage));
-                    ptx::tma_load_3d(a_addr(stage, 1), &mapW, kb * BK, row0, 1, fullA(stage));
+                    const uint64_t pol = kb < p.kb_keep ? keep : stream;
+                    ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage), pol);
+                    ptx::tma_load_3d_hint(a_addr(stage, 1), &mapW, kb * BK, row0, 1, fullA(stage), pol);
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
+                    if (kb == KB - 1) stamp(p, i, 6);
                 }
         }
     } else if (warp == 5) {
         // ---- h_{t-1} tiles: gated by the step barrier of this direction ------------------------
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            if (d == 1) stagger_wait(p.stagger_ns);
             for (int i = 0; i < T; ++i) {
                 wait_counter(p.counters + d, (unsigned)(p.CPD * i), p.counters + 2);
                 ptx::fence_proxy_async();
+                stamp(p, i, 0);
                 const int row0 = (d * 2 + (i & 1)) * NB;
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
@@ -152,6 +179,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     ptx::tma_load_3d(b_addr(stage, 1), &mapH, kb * BK, row0, 1, fullB(stage));
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
+                stamp(p, i, 1);
             }
         }
     } else if (warp == 6) {
@@ -169,6 +197,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     ptx::tc_fence_after();
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
+                        if (q >= p.nprod) break;
                         const uint64_t ad = ptx::make_smem_desc(a_addr(stage, PA[q]), 16, 1024, 2);
                         const uint64_t bd = ptx::make_smem_desc(b_addr(stage, PB[q]), 16, 1024, 2);
 #pragma unroll
@@ -179,6 +208,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 ptx::mma_commit(tfull);
+                stamp(p, i, 2);
                 tphase ^= 1;
             }
         }
@@ -203,6 +233,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
 #pragma unroll
             for (int b = 0; b < NB; ++b) pz[b] = b < B ? __ldg(prow + (size_t)b * GW) : 0.f;
             ptx::mbar_wait(tfull, tphase);
+            if (tid == 0) stamp(p, i, 3);
             ptx::tc_fence_after();
             uint32_t r[32];
             ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);
@@ -216,6 +247,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             epi_bar();
             __nv_bfloat16 *hb = p.xbuf + ((size_t)(d * 2 + ((i + 1) & 1)) * NB) * H + ucol + cu;
             const size_t piece = (size_t)2 * 2 * NB * H;
+            float o_gi[8], o_gj[8], o_gf[8], o_go[8], o_h[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int b = bg * 8 + j;
@@ -228,21 +260,29 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     creg[j] = gf * creg[j] + gi * gj;
                     h = go * tanhf(creg[j]);
                 }
-                if (b < B) {
-                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
-                    grow[0] = gi; grow[H] = gj; grow[2 * (size_t)H] = gf; grow[3 * (size_t)H] = go;
-                    p.cstate[((size_t)tt * B + b) * 2 * H + (size_t)d * H + ucol + cu] = creg[j];
-                    p.y[((size_t)tt * B + b) * 2 * H + (size_t)d * H + ucol + cu] = h;
-                }
+                o_gi[j] = gi; o_gj[j] = gj; o_gf[j] = gf; o_go[j] = go; o_h[j] = h;
+                // h_t is the only thing the other CTAs wait for: publish it first
                 __nv_bfloat16 hi, lo;
                 split2(h, hi, lo);
                 hb[(size_t)b * H] = hi;
                 hb[piece + (size_t)b * H] = lo;
             }
+            if (tid == 0) stamp(p, i, 4);
             __threadfence();
             ptx::fence_proxy_async();
             epi_bar();
-            if (tid == 0) signal_counter(p.counters + d);
+            if (tid == 0) { signal_counter(p.counters + d); stamp(p, i, 5); }
+            // bulk stores (activations for the backward pass, layer output) after the signal
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = bg * 8 + j;
+                if (b < B) {
+                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    grow[0] = o_gi[j]; grow[H] = o_gj[j]; grow[2 * (size_t)H] = o_gf[j]; grow[3 * (size_t)H] = o_go[j];
+                    p.cstate[((size_t)tt * B + b) * 2 * H + (size_t)d * H + ucol + cu] = creg[j];
+                    p.y[((size_t)tt * B + b) * 2 * H + (size_t)d * H + ucol + cu] = o_h[j];
+                }
+            }
         }
     }
     __syncwarp();
@@ -486,18 +526,21 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
         if (lane == 0) {        // Wh[d][128 units of the cluster][columns of gate q], K-major as stored
             int stage = 0; uint32_t phase = 0;
             const int row0 = d * H + ub * 128;
+            const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int n = 0; n < T; ++n)
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
                     ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
-                    ptx::tma_load_3d(a_addr(stage, 0), &mapW, q * H + kb * BK, row0, 0, fullA(stage));
-                    ptx::tma_load_3d(a_addr(stage, 1), &mapW, q * H + kb * BK, row0, 1, fullA(stage));
+                    const uint64_t pol = kb < p.kb_keep ? keep : stream;
+                    ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, q * H + kb * BK, row0, 0, fullA(stage), pol);
+                    ptx::tma_load_3d_hint(a_addr(stage, 1), &mapW, q * H + kb * BK, row0, 1, fullA(stage), pol);
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
         }
     } else if (warp == 5) {
         if (lane == 0) {        // dz of the step processed before, gate-q columns, all batch rows
             int stage = 0; uint32_t phase = 0;
+            if (d == 1) stagger_wait(p.stagger_ns);
             for (int n = 0; n < T; ++n) {
                 wait_counter(p.counters + d, (unsigned)(p.CPD * n), p.counters + 2);
                 ptx::fence_proxy_async();
@@ -584,6 +627,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
             tphase ^= 1;
             __nv_bfloat16 *zb = p.xbuf + ((size_t)(d * 2 + ((n + 1) & 1)) * NB) * 4 * H + ucol + cu;
             const size_t piece = (size_t)2 * 2 * NB * 4 * H;
+            float o_dz[8][4];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int b = bg * 8 + j;
@@ -602,15 +646,11 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                 } else {
                     dcreg[j] = 0.f;
                 }
-                if (b < B) {
-                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
-                    grow[0] = dzi; grow[H] = dzj; grow[2 * (size_t)H] = dzf; grow[3 * (size_t)H] = dzo;
-                }
-                const float dzv[4] = {dzi, dzj, dzf, dzo};
+                o_dz[j][0] = dzi; o_dz[j][1] = dzj; o_dz[j][2] = dzf; o_dz[j][3] = dzo;
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
+                for (int g4 = 0; g4 < 4; ++g4) {        // the bf16 pieces are what the other CTAs wait for
                     __nv_bfloat16 hi, lo;
-                    split2(dzv[g4], hi, lo);
+                    split2(o_dz[j][g4], hi, lo);
                     zb[(size_t)b * 4 * H + (size_t)g4 * H] = hi;
                     zb[piece + (size_t)b * 4 * H + (size_t)g4 * H] = lo;
                 }
@@ -619,6 +659,14 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
             ptx::fence_proxy_async();
             epi_bar();
             if (tid == 0) signal_counter(p.counters + d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {               // fp32 dz for the weight-gradient GEMMs, after the signal
+                const int b = bg * 8 + j;
+                if (b < B) {
+                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    grow[0] = o_dz[j][0]; grow[H] = o_dz[j][1]; grow[2 * (size_t)H] = o_dz[j][2]; grow[3 * (size_t)H] = o_dz[j][3];
+                }
+            }
         }
     }
     __syncwarp();
@@ -692,6 +740,7 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t r
     return CTCASR_OK;
 }
 
+static unsigned long long *g_trace = nullptr;
 struct WsLayout { size_t wpack, xbuf, counters, total; };
 static WsLayout ws_layout(int H)
 {
@@ -703,6 +752,20 @@ static WsLayout ws_layout(int H)
     w.counters = w.xbuf + xbytes;
     w.total = w.counters + 1024;
     return w;
+}
+
+// How many of the H/64 weight k-blocks per CTA are loaded with the L2 evict_last policy.  The two
+// directions' recurrent weights are 16 H^2 bytes (128 MiB at H = 2048) against ~126 MB of L2, so only a
+// share can stay resident across time steps; the rest streams from HBM with evict_first so that it
+// does not push the resident share out.  CTCASR_LSTM_L2_KEEP_MB overrides the resident budget.
+static int keep_kblocks(int H)
+{
+    const char *e = getenv("CTCASR_LSTM_L2_KEEP_MB");
+    const double budget_mb = e ? atof(e) : 32.0;
+    const double total_mb = 16.0 * H * H / 1048576.0;
+    const int KB = H / BK;
+    int k = (int)(KB * budget_mb / total_mb);
+    return k < 0 ? 0 : (k > KB ? KB : k);
 }
 
 static int check_coop(const void *kernel, int smem, int grid)
@@ -719,6 +782,8 @@ static int check_coop(const void *kernel, int smem, int grid)
 }
 
 }  // namespace lstm
+
+void lstm_tc_set_trace(unsigned long long *buf) { lstm::g_trace = buf; }
 
 bool lstm_tc_eligible(int T, int B, int H, int cell)
 {
@@ -757,8 +822,17 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
     Params p;
     p.T = T; p.B = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = forget_bias; p.seq_len = seq_len;
     p.gates = gates; p.cstate = cstate; p.y = y; p.dy = nullptr; p.xbuf = hbuf; p.counters = ctr;
-    void *args[] = {&mapW, &mapH, &p};
-    CTCASR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)lstm_fwd_kernel, dim3(grid), dim3(NTHREADS), args, F_SMEM, stream));
+    p.kb_keep = keep_kblocks(H);
+    p.trace = g_trace;
+    p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
+    p.nprod = getenv("CTCASR_LSTM_NPROD") ? atoi(getenv("CTCASR_LSTM_NPROD")) : 3;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = F_SMEM; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ProfScope prof(PROF_LSTM_FWD, stream);
+    CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel, mapW, mapH, p));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return CTCASR_OK;
 }
@@ -781,6 +855,10 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     Params p;
     p.T = T; p.B = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = 0.f; p.seq_len = seq_len;
     p.gates = gates; p.cstate = const_cast<float *>(cstate); p.y = nullptr; p.dy = dy; p.xbuf = zbuf; p.counters = ctr;
+    p.kb_keep = keep_kblocks(H);
+    p.trace = g_trace;
+    p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
+    p.nprod = getenv("CTCASR_LSTM_NPROD") ? atoi(getenv("CTCASR_LSTM_NPROD")) : 3;
     CUtensorMap mapW, mapZ;
     int rc = make_map(&mapZ, zbuf, (uint64_t)4 * H, (uint64_t)2 * 2 * NB, NB);
     if (rc) return rc;
@@ -791,7 +869,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     if (H % 128 == 0 && cluster_bad_grid != grid && !no_cluster) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C_SMEM; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
@@ -805,6 +883,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
         if (cluster_ok_grid == grid) {
             rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, 128);
             if (rc) return rc;
+            ProfScope prof(PROF_LSTM_BWD, stream);
             CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel, mapW, mapZ, p));
             g_launch_count.fetch_add(1, std::memory_order_relaxed);
             return CTCASR_OK;
@@ -815,6 +894,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC);
     if (rc) return rc;
     void *args[] = {&mapW, &mapZ, &p};
+    ProfScope prof(PROF_LSTM_BWD, stream);
     CTCASR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)lstm_bwd_kernel, dim3(grid), dim3(NTHREADS), args, B_SMEM, stream));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return CTCASR_OK;

@@ -130,6 +130,11 @@ int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const float *wx, co
 /* ---------------------------------------------------------------------------------------------
  * Plumbing around the path
  * -------------------------------------------------------------------------------------------- */
+/* Optional timing of the hot kernels with CUDA events recorded on the launching stream.
+ * classes: 0 LSTM recurrence fwd, 1 LSTM recurrence bwd, 2 tcgen05 GEMM, 3 CTC, 4 operand split.
+ * collect() synchronises the device and returns summed milliseconds and launch counts per class. */
+int ctcasr_profile_enable(int on);
+int ctcasr_profile_collect(double *ms, int *count, int ntags);
 /* Scratch arena for the bf16-split operand copies of CTCASR_COMPUTE_BF16X3 (device memory owned by the
  * caller, 1024-B aligned).  A call that needs more returns CTCASR_ERR_WORKSPACE and
  * ctcasr_scratch_needed() tells how much. */
