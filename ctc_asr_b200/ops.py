@@ -35,10 +35,12 @@ def _call(fn, what, *args):
         need = int(lib.ctcasr_scratch_needed() * 1.25) + (1 << 20)
         dev = torch.cuda.current_device()
         _scratch[dev] = None
-        buf = torch.empty(need, dtype=torch.uint8, device="cuda")
+        buf = torch.empty(need + 1024, dtype=torch.uint8, device="cuda")
         _scratch[dev] = buf
         torch.cuda.current_stream().synchronize()
-        check(lib.ctcasr_set_scratch(ptr(buf), buf.numel()), "set_scratch")
+        import ctypes
+        base = (buf.data_ptr() + 1023) // 1024 * 1024          # the arena must be 1024-B aligned (swizzle atoms)
+        check(lib.ctcasr_set_scratch(ctypes.c_void_p(base), need), "set_scratch")
         rc = fn(*args)
     check(rc, what)
 
