@@ -1,0 +1,50 @@
+"""Data parallelism for the hot path: one process per GPU, equal shards, ONE all-reduce (sum) of the
+flat gradient buffer per step.  The reference is single-device
+(`train_distribute=None`, asr/train.py:41); this is the only collective the path needs, so the
+plumbing is `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) and nothing else.
+
+Equal shard sizes make mean-of-shard-means equal the global mean; each rank scales its CTC gradient
+by 1/global_batch (`CTCModel.loss_fn(..., global_batch=...)`) so the summed gradient is exactly the
+gradient of the global mean loss (asr/model.py:267).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch, rank, world):
+    """[lo, hi) of this rank's utterances.  The global batch must divide evenly (like the reference's
+    drop_remainder=True batching, asr/input_functions.py:100-103)."""
+    if global_batch % world:
+        raise ValueError("global batch %d is not divisible by world size %d" % (global_batch, world))
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def shard_batch(sequences, seq_length, labels, label_length, rank, world):
+    lo, hi = shard_bounds(sequences.shape[0], rank, world)
+    return sequences[lo:hi], seq_length[lo:hi], labels[lo:hi], label_length[lo:hi]
+
+
+def allreduce_gradients(flat_grad, group=None):
+    """Sum the flat gradient over all ranks, in place."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
+def allreduce_mean_loss(local_loss_sum_over_global_batch, group=None):
+    """Each rank holds sum(per-utterance loss)/global_batch; the sum over ranks is the global mean."""
+    t = local_loss_sum_over_global_batch.detach().clone().reshape(1)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t[0]
+
+
+def train_step(model, sequences, seq_length, labels, label_length, group=None):
+    """One data-parallel step of `CTCModel` on this rank's shard of the global batch."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    gb = sequences.shape[0]
+    x, sl, lab, ll = shard_batch(sequences, seq_length, labels, label_length, rank, world)
+    loss = model.train_step(x, sl, (lab, ll), global_batch=gb, allreduce=lambda g: allreduce_gradients(g, group))
+    return allreduce_mean_loss(loss, group)

@@ -1,0 +1,67 @@
+"""World-size-2 gloo test (CPU) of the data-parallel host logic: equal shards, CTC gradient scaled by
+1/global_batch, one all-reduce (sum) of the flat gradient == the single-process gradient of the
+global mean loss (SURVEY.md §8e correctness test).  The per-shard arithmetic comes from the CPU oracle
+(this is a test of the plumbing; the CUDA path is exercised by the gpu-marked tests and bench.py)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ctc_asr_b200 import parallel, synthetic
+from ctc_asr_b200.params import ModelConfig, param_offsets
+from oracle import model_ref
+
+CFG = ModelConfig(num_layers_dense=2, num_units_dense=16, num_layers_rnn=1, num_units_rnn=8, rnn_cell="lstm",
+                  cudnn=False, dense_dropout_rate=0.0, num_features=6)
+
+
+def _flat(cfg, grads):
+    offs, n = param_offsets(cfg)
+    flat = np.zeros(n)
+    for k, (o, shape) in offs.items():
+        flat[o:o + grads[k].size] = grads[k].ravel()
+    return flat
+
+
+def _worker(rank, world, port, x, sl, lab, ll, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = synthetic.init_params(CFG, seed=1, dtype=np.float64)
+    xs, sls, labs, lls = parallel.shard_batch(x, sl, lab, ll, rank, world)
+    gb = x.shape[0]
+    loss, grads, _, _ = model_ref.loss_and_grads(CFG, params, xs, sls, labs, lls)
+    # loss_and_grads averages over the SHARD; rescale to 1/global_batch like loss_fn(global_batch=gb)
+    scale = xs.shape[0] / gb
+    flat = torch.from_numpy(_flat(CFG, grads) * scale)
+    parallel.allreduce_gradients(flat)
+    mean_loss = parallel.allreduce_mean_loss(torch.tensor(loss * scale))
+    if rank == 0:
+        out["flat"], out["loss"] = flat.numpy().copy(), float(mean_loss)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_equals_single_process():
+    x, sl, lab, ll = synthetic.fixed_batch(4, 14, 3, F=CFG.num_features, seed=5)
+    sl[1], sl[3] = 11, 9
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, x, sl, lab, ll, out), nprocs=2, join=True)
+    params = synthetic.init_params(CFG, seed=1, dtype=np.float64)
+    loss, grads, _, _ = model_ref.loss_and_grads(CFG, params, x, sl, lab, ll)
+    np.testing.assert_allclose(out["loss"], loss, rtol=1e-12)
+    np.testing.assert_allclose(out["flat"], _flat(CFG, grads), atol=1e-12)
+
+
+def test_shard_bounds_reject_ragged_split():
+    assert parallel.shard_bounds(256, 3, 8) == (96, 128)
+    try:
+        parallel.shard_bounds(30, 0, 4)
+    except ValueError:
+        return
+    raise AssertionError("uneven shards must be rejected")
