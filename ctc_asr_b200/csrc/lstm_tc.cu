@@ -54,7 +54,7 @@ constexpr int B_XCH = NB * (UPC + 1) * 4;
 constexpr int B_SMEM = B_NSTAGE * (B_STAGE + B_ZSTAGE) + B_Z_SLOT /*over-read pad*/ + B_XCH + 1024 + 256;
 
 struct Params {
-    int T, B, H, CPD, use_len;
+    int T, B, BS, H, CPD, use_len;       // B: batch rows of this launch (<= 32); BS: batch rows per frame in the buffers
     float forget_bias;
     const int *seq_len;
     float *gates;            // [T*B, 8H]  fwd: P -> activations;  bwd: activations -> dz
@@ -229,7 +229,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             const int tt = d == 0 ? i : T - 1 - i;
             // pre-activations of my gate row for all batch rows (independent of the recurrence)
             float pz[NB];
-            const float *prow = p.gates + (size_t)tt * B * GW + (size_t)d * 4 * H + (size_t)g * H + ucol + ul;
+            const float *prow = p.gates + (size_t)tt * p.BS * GW + (size_t)d * 4 * H + (size_t)g * H + ucol + ul;
 #pragma unroll
             for (int b = 0; b < NB; ++b) pz[b] = b < B ? __ldg(prow + (size_t)b * GW) : 0.f;
             ptx::mbar_wait(tfull, tphase);
@@ -277,10 +277,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             for (int j = 0; j < 8; ++j) {
                 const int b = bg * 8 + j;
                 if (b < B) {
-                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
                     grow[0] = o_gi[j]; grow[H] = o_gj[j]; grow[2 * (size_t)H] = o_gf[j]; grow[3 * (size_t)H] = o_go[j];
-                    p.cstate[((size_t)tt * B + b) * 2 * H + (size_t)d * H + ucol + cu] = creg[j];
-                    p.y[((size_t)tt * B + b) * 2 * H + (size_t)d * H + ucol + cu] = o_h[j];
+                    p.cstate[((size_t)tt * p.BS + b) * 2 * H + (size_t)d * H + ucol + cu] = creg[j];
+                    p.y[((size_t)tt * p.BS + b) * 2 * H + (size_t)d * H + ucol + cu] = o_h[j];
                 }
             }
         }
@@ -407,12 +407,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                 const int b = bg * 8 + j;
                 gi[j] = gj[j] = gf[j] = go[j] = cc[j] = cp[j] = dyv[j] = 0.f;
                 if (b < B) {
-                    const float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    const float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
                     gi[j] = grow[0]; gj[j] = grow[H]; gf[j] = grow[2 * (size_t)H]; go[j] = grow[3 * (size_t)H];
                     const size_t so = (size_t)d * H + ucol + cu;
-                    cc[j] = p.cstate[((size_t)tt * B + b) * 2 * H + so];
-                    if (i > 0) cp[j] = p.cstate[((size_t)tp * B + b) * 2 * H + so];
-                    dyv[j] = p.dy[((size_t)tt * B + b) * 2 * H + so];
+                    cc[j] = p.cstate[((size_t)tt * p.BS + b) * 2 * H + so];
+                    if (i > 0) cp[j] = p.cstate[((size_t)tp * p.BS + b) * 2 * H + so];
+                    dyv[j] = p.dy[((size_t)tt * p.BS + b) * 2 * H + so];
                 }
             }
             ptx::mbar_wait(tfull, tphase);
@@ -449,7 +449,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     dcreg[j] = 0.f;
                 }
                 if (b < B) {
-                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
                     grow[0] = dzi; grow[H] = dzj; grow[2 * (size_t)H] = dzf; grow[3 * (size_t)H] = dzo;
                 }
                 const float dzv[4] = {dzi, dzj, dzf, dzo};
@@ -605,12 +605,12 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                 const int b = bg * 8 + j;
                 gi[j] = gj[j] = gf[j] = go[j] = cc[j] = cp[j] = dyv[j] = 0.f;
                 if (b < B) {
-                    const float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    const float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
                     gi[j] = grow[0]; gj[j] = grow[H]; gf[j] = grow[2 * (size_t)H]; go[j] = grow[3 * (size_t)H];
                     const size_t so = (size_t)d * H + ucol + cu;
-                    cc[j] = p.cstate[((size_t)tt * B + b) * 2 * H + so];
-                    if (i > 0) cp[j] = p.cstate[((size_t)tp * B + b) * 2 * H + so];
-                    dyv[j] = p.dy[((size_t)tt * B + b) * 2 * H + so];
+                    cc[j] = p.cstate[((size_t)tt * p.BS + b) * 2 * H + so];
+                    if (i > 0) cp[j] = p.cstate[((size_t)tp * p.BS + b) * 2 * H + so];
+                    dyv[j] = p.dy[((size_t)tt * p.BS + b) * 2 * H + so];
                 }
             }
             ptx::mbar_wait(tfull, tphase);
@@ -663,7 +663,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
             for (int j = 0; j < 8; ++j) {               // fp32 dz for the weight-gradient GEMMs, after the signal
                 const int b = bg * 8 + j;
                 if (b < B) {
-                    float *grow = p.gates + ((size_t)tt * B + b) * GW + (size_t)d * 4 * H + ucol + cu;
+                    float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
                     grow[0] = o_dz[j][0]; grow[H] = o_dz[j][1]; grow[2 * (size_t)H] = o_dz[j][2]; grow[3 * (size_t)H] = o_dz[j][3];
                 }
             }
@@ -787,7 +787,7 @@ void lstm_tc_set_trace(unsigned long long *buf) { lstm::g_trace = buf; }
 
 bool lstm_tc_eligible(int T, int B, int H, int cell)
 {
-    return cell == CTCASR_CELL_LSTM && T >= 1 && B >= 1 && B <= lstm::NB && H >= 64 && H % 64 == 0 && 2 * (H / lstm::UPC) <= 148;
+    return cell == CTCASR_CELL_LSTM && T >= 1 && B >= 1 && H >= 64 && H % 64 == 0 && 2 * (H / lstm::UPC) <= 148;
 }
 
 size_t lstm_tc_workspace_bytes(int B, int H)
@@ -812,28 +812,33 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
 
     pack_wh_fwd_kernel<<<dim3(4 * H / 32, H / 32, 2), dim3(32, 8), 0, stream>>>(wh, wp, H);
     CTCASR_LAUNCH_CHECK();
-    CTCASR_CUDA_CHECK(cudaMemsetAsync(hbuf, 0, (size_t)2 * 2 * 2 * NB * H * 2, stream));      // h_{-1} = 0, padded batch rows = 0
-    CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
     CUtensorMap mapW, mapH;
     int rc = make_map(&mapW, wp, H, (uint64_t)2 * 4 * H, 128);
     if (rc) return rc;
     rc = make_map(&mapH, hbuf, H, (uint64_t)2 * 2 * NB, NB);
     if (rc) return rc;
-    Params p;
-    p.T = T; p.B = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = forget_bias; p.seq_len = seq_len;
-    p.gates = gates; p.cstate = cstate; p.y = y; p.dy = nullptr; p.xbuf = hbuf; p.counters = ctr;
-    p.kb_keep = keep_kblocks(H);
-    p.trace = g_trace;
-    p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
-    p.nprod = getenv("CTCASR_LSTM_NPROD") ? atoi(getenv("CTCASR_LSTM_NPROD")) : 3;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = F_SMEM; cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    ProfScope prof(PROF_LSTM_FWD, stream);
-    CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel, mapW, mapH, p));
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    // batches above 32 rows run as consecutive launches over 32-row slices of the same buffers
+    for (int b0 = 0; b0 < B; b0 += NB) {
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(hbuf, 0, (size_t)2 * 2 * 2 * NB * H * 2, stream));  // h_{-1} = 0, padded batch rows = 0
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
+        Params p;
+        p.T = T; p.B = B - b0 < NB ? B - b0 : NB; p.BS = B; p.H = H; p.CPD = CPD; p.use_len = use_len;
+        p.forget_bias = forget_bias; p.seq_len = seq_len ? seq_len + b0 : nullptr;
+        p.gates = gates + (size_t)b0 * 8 * H; p.cstate = cstate + (size_t)b0 * 2 * H; p.y = y + (size_t)b0 * 2 * H;
+        p.dy = nullptr; p.xbuf = hbuf; p.counters = ctr;
+        p.kb_keep = keep_kblocks(H);
+        p.trace = g_trace;
+        p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
+        p.nprod = getenv("CTCASR_LSTM_NPROD") ? atoi(getenv("CTCASR_LSTM_NPROD")) : 3;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = F_SMEM; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        ProfScope prof(PROF_LSTM_FWD, stream);
+        CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel, mapW, mapH, p));
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    }
     return CTCASR_OK;
 }
 
@@ -850,26 +855,18 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     const size_t nw = (size_t)2 * H * 4 * H;
     split2_kernel<<<148 * 8, 256, 0, stream>>>(wh, wq, nw);
     CTCASR_LAUNCH_CHECK();
-    CTCASR_CUDA_CHECK(cudaMemsetAsync(zbuf, 0, (size_t)2 * 2 * 2 * NB * 4 * H * 2, stream));  // no recurrent gradient into the last step
-    CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
-    Params p;
-    p.T = T; p.B = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = 0.f; p.seq_len = seq_len;
-    p.gates = gates; p.cstate = const_cast<float *>(cstate); p.y = nullptr; p.dy = dy; p.xbuf = zbuf; p.counters = ctr;
-    p.kb_keep = keep_kblocks(H);
-    p.trace = g_trace;
-    p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
-    p.nprod = getenv("CTCASR_LSTM_NPROD") ? atoi(getenv("CTCASR_LSTM_NPROD")) : 3;
     CUtensorMap mapW, mapZ;
     int rc = make_map(&mapZ, zbuf, (uint64_t)4 * H, (uint64_t)2 * 2 * NB, NB);
     if (rc) return rc;
 
     // preferred: 4-CTA cluster split-K kernel (needs H % 128 == 0 and all clusters co-resident)
-    static int cluster_ok_grid = 0, cluster_bad_grid = 0;
+    static int cluster_ok_grid = 0, cluster_bad_grid = 0, checked_grid = 0;
     const bool no_cluster = getenv("CTCASR_LSTM_NO_CLUSTER") != nullptr;
+    bool use_cluster = false;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
     if (H % 128 == 0 && cluster_bad_grid != grid && !no_cluster) {
-        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C_SMEM; cfg.stream = stream;
-        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
@@ -880,23 +877,36 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
             if (e == cudaSuccess && nclusters * 4 >= grid) cluster_ok_grid = grid;
             else { cluster_bad_grid = grid; (void)cudaGetLastError(); }
         }
-        if (cluster_ok_grid == grid) {
-            rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, 128);
-            if (rc) return rc;
-            ProfScope prof(PROF_LSTM_BWD, stream);
-            CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel, mapW, mapZ, p));
-            g_launch_count.fetch_add(1, std::memory_order_relaxed);
-            return CTCASR_OK;
-        }
+        use_cluster = cluster_ok_grid == grid;
     }
-    static int checked_grid = 0;
-    if (checked_grid != grid) { rc = check_coop((const void *)lstm_bwd_kernel, B_SMEM, grid); if (rc) return rc; checked_grid = grid; }
-    rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC);
+    if (use_cluster) {
+        rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, 128);
+    } else {
+        if (checked_grid != grid) { rc = check_coop((const void *)lstm_bwd_kernel, B_SMEM, grid); if (rc) return rc; checked_grid = grid; }
+        rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC);
+    }
     if (rc) return rc;
-    void *args[] = {&mapW, &mapZ, &p};
-    ProfScope prof(PROF_LSTM_BWD, stream);
-    CTCASR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)lstm_bwd_kernel, dim3(grid), dim3(NTHREADS), args, B_SMEM, stream));
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    for (int b0 = 0; b0 < B; b0 += NB) {
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(zbuf, 0, (size_t)2 * 2 * 2 * NB * 4 * H * 2, stream));  // no recurrent gradient into the last step
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
+        Params p;
+        p.T = T; p.B = B - b0 < NB ? B - b0 : NB; p.BS = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = 0.f;
+        p.seq_len = seq_len ? seq_len + b0 : nullptr;
+        p.gates = gates + (size_t)b0 * 8 * H; p.cstate = const_cast<float *>(cstate) + (size_t)b0 * 2 * H; p.y = nullptr;
+        p.dy = dy + (size_t)b0 * 2 * H; p.xbuf = zbuf; p.counters = ctr;
+        p.kb_keep = keep_kblocks(H);
+        p.trace = nullptr;
+        p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
+        p.nprod = 3;
+        ProfScope prof(PROF_LSTM_BWD, stream);
+        if (use_cluster) {
+            CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel, mapW, mapZ, p));
+        } else {
+            void *args[] = {&mapW, &mapZ, &p};
+            CTCASR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)lstm_bwd_kernel, dim3(grid), dim3(NTHREADS), args, B_SMEM, stream));
+        }
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    }
     return CTCASR_OK;
 }
 
