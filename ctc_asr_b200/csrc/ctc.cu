@@ -14,10 +14,10 @@
 //            and write the gradient rows.
 //   HBM traffic is therefore the algorithmic one: logits in (re-read from L2 in phase 2),
 //   gradient out, plus T/CH checkpoint rows.
-//   alpha/beta are log-domain fp32 but re-based per chunk (offsets accumulated in fp64) so that
-//   values stay O(chunk) instead of O(T): un-normalised fp32 rows of magnitude ~3e3 carry ~1e-2
+//   alpha/beta are base-2 log-domain values carried as (hi, lo) float pairs (error-free TwoSum
+//   accumulation): a plain fp32 recursion rounds at ulp(alpha) ~ 1e-3 per step and carries ~1e-2
 //   of gradient noise at T=1700 (tests/test_oracle_ctc.py), which would eat the 1e-3 budget.
-//   Each recursion step is one shared-memory row read + a 3-way log-sum-exp (MUFU ex2/lg2) + one
+//   Each recursion step is one shared-memory row read + a 3-way log-sum-exp (3 ex2 + 1 lg2 MUFU) + one
 //   named barrier per warp group; alpha and beta groups run on separate barriers.
 #include "common.cuh"
 
@@ -34,7 +34,7 @@ struct Params {
     const float *logits; int T, B, V, blank;
     const int *labels; int lstride; const int *label_len; const int *seq_len;
     float *loss; float *grad; float grad_scale; int *status;
-    float *ckpt; double *ckoff;     // [B][NCH][RS], [B][NCH]
+    float2 *ckpt;                   // [B][NCH][RS] alpha checkpoint rows (hi, lo)
     int CH, RS, GT, NCH, Lmax, VP;
 };
 
@@ -46,30 +46,46 @@ struct SmemLayout {
         lab = o;       o += (size_t)((Lmax + 3) / 4 * 4 + 4) * 4;
         csr_start = o; o += (size_t)((V + 1 + 3) / 4 * 4) * 4;
         csr_pos = o;   o += (size_t)((Lmax + 3) / 4 * 4 + 4) * 4;
-        rowA = o;      o += (size_t)2 * RS * 4;
-        rowB = o;      o += (size_t)2 * RS * 4;
-        A = o;         o += (size_t)2 * CH * RS * 4;
+        rowA = o;      o += (size_t)2 * RS * 8;
+        rowB = o;      o += (size_t)2 * RS * 8;
+        A = o;         o += (size_t)2 * CH * RS * 8;
         LY = o;        o += (size_t)((3 * CH * VP + 3) / 4 * 4) * 4;
         red = o;       o += 64 * 4 + 64;
         total = o;
     }
 };
 
-// 3-way log-sum-exp.  Precise expf/logf: the fast intrinsics carry a ~1e-6 bias per step that
-// differs between the alpha and beta recursions and accumulates linearly over T (1.7e-3 of
-// gradient error at T=1700, measured).
-__device__ __forceinline__ float lse3(float a, float b, float c)
+// ---- lattice arithmetic ---------------------------------------------------------------------------
+// Values are base-2 logarithms held as an unevaluated sum hi + lo of two floats.  A plain fp32
+// log-domain recursion rounds every step at ulp(|alpha|): with |alpha| growing to ~1e4 over 1700
+// frames that is 1e-3 per step and the gradient ends up ~1e-2 off (the TF kernel does exactly this);
+// re-basing rows to their maximum still leaves the states that carry the posterior ~150 below it
+// (2e-3 measured).  Carrying the rounding error of each addition in `lo` (error-free TwoSum) keeps
+// ~48 bits for the accumulated part, so only the O(1)-sized per-step increments are rounded.
+// Base 2 makes exp/log single MUFU instructions (ex2.approx / lg2.approx).
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ float2 two_sum(float a, float b)      // a + b = s + e exactly
 {
-    const float m = fmaxf(a, fmaxf(b, c));
-    if (m == -INFINITY) return -INFINITY;
-    return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+    const float s = a + b, bb = s - a;
+    return make_float2(s, (a - (s - bb)) + (b - bb));
+}
+// log2( 2^a0 + 2^a1 + 2^a2 ) + inc, all operands (hi, lo) pairs, -inf = log zero
+__device__ __forceinline__ float2 lse3_add(float2 a0, float2 a1, float2 a2, float inc)
+{
+    float2 m = a0.x >= a1.x ? a0 : a1;
+    m = m.x >= a2.x ? m : a2;
+    if (m.x == -INFINITY) return make_float2(-INFINITY, 0.f);
+    const float d0 = (a0.x - m.x) + (a0.y - m.y), d1 = (a1.x - m.x) + (a1.y - m.y), d2 = (a2.x - m.x) + (a2.y - m.y);
+    const float lg = lg2f(ex2f(d0) + ex2f(d1) + ex2f(d2));      // sum in [1, 3]
+    return two_sum(m.x, (lg + inc) + m.y);
 }
 
 __device__ __forceinline__ void group_bar(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-
 __device__ __forceinline__ float warp_max(float v)
 {
 #pragma unroll
@@ -83,37 +99,33 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-// max over a thread group (GT threads, group-local thread id gt, barrier id bar)
-__device__ __forceinline__ float group_max(float v, float *red, int gt, int GT, int bar)
-{
-    v = warp_max(v);
-    const int w = gt >> 5, nw = GT >> 5;
-    if ((gt & 31) == 0) red[w] = v;
-    group_bar(bar, GT);
-    float m = -INFINITY;
-    for (int i = 0; i < nw; ++i) m = fmaxf(m, red[i]);
-    group_bar(bar, GT);        // red[] may be reused immediately afterwards
-    return m;
-}
-
-// log-softmax of the frames of chunk c into LY; ONE LANE PER FRAME (the frame's V logits are a
-// contiguous 4V-byte run), executed by `nthreads` consecutive threads starting at thread `first`.
-// Rows are VP = V|1-padded floats apart so that lanes writing the same class hit distinct banks.
+// base-2 log-softmax of the frames of chunk c into LY, FOUR LANES PER FRAME (a frame's V logits are a
+// contiguous 4V-byte run; the 4 lanes take classes k = sub, sub+4, ... and combine with two
+// shuffles), executed by `nthreads` (a multiple of 32) consecutive threads starting at `first`.
+// Values are re-read from L1 instead of being held in registers (V up to 128).
+// Rows are VP = V|1 floats apart to spread the banks.
 __device__ __forceinline__ void compute_logy(const Params &p, int b, int Tb, int c, float *LY, int first, int nthreads)
 {
+    const float kLog2e = 1.4426950408889634f;
+    const int lt = (int)threadIdx.x - first, sub = lt & 3, rpp = nthreads >> 2;
     const int lo = c * p.CH, hi = min(lo + p.CH, Tb);
-    for (int t = lo + (int)threadIdx.x - first; t < hi; t += nthreads) {
-        const float *x = p.logits + ((size_t)t * p.B + b) * p.V;
+    for (int t0 = lo; t0 < hi; t0 += rpp) {            // uniform trip count: shuffles need the whole warp
+        const int t = t0 + (lt >> 2);
+        const bool valid = t < hi;
+        const float *x = p.logits + ((size_t)(valid ? t : lo) * p.B + b) * p.V;
         float m = -INFINITY;
-#pragma unroll 8
-        for (int k = 0; k < p.V; ++k) m = fmaxf(m, __ldg(x + k));
+        for (int k = sub; k < p.V; k += 4) m = fmaxf(m, __ldg(x + k));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
         float e = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < p.V; ++k) e += expf(__ldg(x + k) - m);
-        const float lse = m + logf(e);
-        float *row = LY + (size_t)(t - lo) * p.VP;
-#pragma unroll 8
-        for (int k = 0; k < p.V; ++k) row[k] = __ldg(x + k) - lse;
+        for (int k = sub; k < p.V; k += 4) e += ex2f((__ldg(x + k) - m) * kLog2e);
+        e += __shfl_xor_sync(0xffffffffu, e, 1);
+        e += __shfl_xor_sync(0xffffffffu, e, 2);
+        const float lse2 = m * kLog2e + lg2f(e);        // log2 sum_k 2^(x_k log2 e)
+        if (valid) {
+            float *row = LY + (size_t)(t - lo) * p.VP;
+            for (int k = sub; k < p.V; k += 4) row[k] = __ldg(x + k) * kLog2e - lse2;
+        }
     }
 }
 
@@ -130,22 +142,23 @@ ctc_loss_kernel(const Params p)
     const bool is_helper = tid >= 2 * GT;
     const int gt = is_alpha ? tid : tid - GT;
     const int RS = p.RS, CH = p.CH, V = p.V, VP = p.VP, blank = p.blank;
+    const float2 kNegInf = make_float2(-INFINITY, 0.f);
 
     const SmemLayout L(p.Lmax, V, RS, CH, VP);
     int *lab = reinterpret_cast<int *>(smem_raw + L.lab);
     int *csr_start = reinterpret_cast<int *>(smem_raw + L.csr_start);
     int *csr_pos = reinterpret_cast<int *>(smem_raw + L.csr_pos);
-    float *rowA = reinterpret_cast<float *>(smem_raw + L.rowA);   // alpha rows: state s at [s+2]
-    float *rowB = reinterpret_cast<float *>(smem_raw + L.rowB);   // primed beta rows: state s at [s]
-    float *Abuf = reinterpret_cast<float *>(smem_raw + L.A);      // [2][CH][RS], state s at [s+2]
-    float *LYbuf = reinterpret_cast<float *>(smem_raw + L.LY);    // [3][CH][VP] ring, chunk c at c % 3
+    float2 *rowA = reinterpret_cast<float2 *>(smem_raw + L.rowA);   // alpha rows: state s at [s+2]
+    float2 *rowB = reinterpret_cast<float2 *>(smem_raw + L.rowB);   // beta rows (incl. y_t): state s at [s]
+    float2 *Abuf = reinterpret_cast<float2 *>(smem_raw + L.A);      // [2][CH][RS], state s at [s+2]
+    float *LYbuf = reinterpret_cast<float *>(smem_raw + L.LY);      // [3][CH][VP] ring, chunk c at c % 3
     float *red = reinterpret_cast<float *>(smem_raw + L.red);
-    int *flags = reinterpret_cast<int *>(red + 48);               // [0] bad label, [1] repeats
+    int *flags = reinterpret_cast<int *>(red + 48);                 // [0] bad label, [1] repeats
 
     const int Tb = p.seq_len[b];
     const int Ln = p.label_len[b];
     const int S = 2 * Ln + 1;
-    float *grad_b = p.grad ? p.grad + (size_t)b * V : nullptr;    // row t at + t*B*V
+    float *grad_b = p.grad ? p.grad + (size_t)b * V : nullptr;      // row t at + t*B*V
     const size_t gstride = (size_t)p.B * V;
 
     // ---- setup: labels, validation ---------------------------------------------------------
@@ -190,8 +203,8 @@ ctc_loss_kernel(const Params p)
         for (int k = 0; k < V; ++k) csr_start[k + 1] += csr_start[k];
     }
     // guards: alpha rows [0],[1]; beta rows [S],[S+1]; every A row [0],[1]
-    for (int i = tid; i < 2 * RS; i += NT) { rowA[i] = -INFINITY; rowB[i] = -INFINITY; }
-    for (int i = tid; i < 2 * CH; i += NT) { Abuf[(size_t)i * RS] = -INFINITY; Abuf[(size_t)i * RS + 1] = -INFINITY; }
+    for (int i = tid; i < 2 * RS; i += NT) { rowA[i] = kNegInf; rowB[i] = kNegInf; }
+    for (int i = tid; i < 2 * CH; i += NT) { Abuf[(size_t)i * RS] = kNegInf; Abuf[(size_t)i * RS + 1] = kNegInf; }
     __syncthreads();
     if (tid == 0) {
         // csr_pos filled by a serial stable pass (deterministic summation order later)
@@ -217,18 +230,16 @@ ctc_loss_kernel(const Params p)
     }
 
     const int NCH = (Tb + CH - 1) / CH;
-    float *ck_b = p.ckpt + (size_t)b * p.NCH * RS;
-    double *off_b = p.ckoff + (size_t)b * p.NCH;
+    float2 *ck_b = p.ckpt + (size_t)b * p.NCH * RS;
     const size_t LYS = (size_t)CH * VP;
 
     // =========================== phase 1: alpha sweep with checkpoints =========================
-    double offA = 0.0;
     int cur = 0;
     if (is_alpha) {       // virtual row t = -1: {0, -inf, ...} reproduces TF's alpha init
 #pragma unroll
         for (int q = 0; q < SPT; ++q) {
             const int s = gt + q * GT;
-            if (s < S) rowA[cur * RS + s + 2] = s == 0 ? 0.f : -INFINITY;
+            if (s < S) rowA[cur * RS + s + 2] = s == 0 ? make_float2(0.f, 0.f) : kNegInf;
         }
     }
     compute_logy(p, b, Tb, 0, LYbuf, 0, NT);
@@ -238,39 +249,21 @@ ctc_loss_kernel(const Params p)
         if (is_helper) {
             if (c + 1 < NCH) compute_logy(p, b, Tb, c + 1, LYbuf + (size_t)((c + 1) % 3) * LYS, 2 * GT, kHelper);
         } else if (is_alpha) {
-            // re-base the incoming row and checkpoint it
-            float m = -INFINITY;
+            // checkpoint: the row before the chunk's first frame
 #pragma unroll
             for (int q = 0; q < SPT; ++q) {
                 const int s = gt + q * GT;
-                if (s < S) m = fmaxf(m, rowA[cur * RS + s + 2]);
+                if (s < S) ck_b[(size_t)c * RS + s] = rowA[cur * RS + s + 2];
             }
-            m = group_max(m, red, gt, GT, 1);
-            offA += (double)m;
-#pragma unroll
-            for (int q = 0; q < SPT; ++q) {
-                const int s = gt + q * GT;
-                if (s < S) {
-                    const float v = rowA[cur * RS + s + 2] - m;
-                    rowA[cur * RS + s + 2] = v;
-                    ck_b[(size_t)c * RS + s] = v;
-                }
-            }
-            if (gt == 0) off_b[c] = offA;
-            group_bar(1, GT);
             const int lo = c * CH, hi = min(lo + CH, Tb);
             for (int t = lo; t < hi; ++t) {
-                const float *prev = rowA + cur * RS;
-                float *next = rowA + (cur ^ 1) * RS;
+                const float2 *prev = rowA + cur * RS;
+                float2 *next = rowA + (cur ^ 1) * RS;
                 const float *ly = LY + (size_t)(t - lo) * VP;
 #pragma unroll
                 for (int q = 0; q < SPT; ++q) {
                     const int s = gt + q * GT;
-                    if (s < S) {
-                        const float a0 = prev[s + 2], a1 = prev[s + 1];
-                        const float a2 = st_skA[q] ? prev[s] : -INFINITY;
-                        next[s + 2] = lse3(a0, a1, a2) + ly[st_lp[q]];
-                    }
+                    if (s < S) next[s + 2] = lse3_add(prev[s + 2], prev[s + 1], st_skA[q] ? prev[s] : kNegInf, ly[st_lp[q]]);
                 }
                 cur ^= 1;
                 group_bar(1, GT);
@@ -278,31 +271,29 @@ ctc_loss_kernel(const Params p)
         }
         __syncthreads();
     }
-    // log p = offA + LSE(alpha[S-1], alpha[S-2]) at t = T_b - 1, shared through smem as a double
-    double *dsh = reinterpret_cast<double *>(red + 40);
+    // log2 p = LSE2(alpha[S-1], alpha[S-2]) at t = T_b - 1 as a (hi, lo) pair shared through smem
+    float2 *psh = reinterpret_cast<float2 *>(red + 40);
     if (tid == 0) {
-        const float a = rowA[cur * RS + (S - 1) + 2];
-        const float c2 = S > 1 ? rowA[cur * RS + (S - 2) + 2] : -INFINITY;
-        const float m = fmaxf(a, c2);
-        const double logp = m == -INFINITY ? -(double)INFINITY
-                                           : offA + (double)m + log(exp((double)(a - m)) + exp((double)(c2 - m)));
-        dsh[0] = logp;
-        p.loss[b] = (float)(-logp);
+        const float2 a = rowA[cur * RS + (S - 1) + 2];
+        const float2 c2 = S > 1 ? rowA[cur * RS + (S - 2) + 2] : kNegInf;
+        const float2 lp2 = lse3_add(a, c2, kNegInf, 0.f);
+        psh[0] = lp2;
+        p.loss[b] = (float)(-((double)lp2.x + (double)lp2.y) * 0.6931471805599453);
         p.status[b] = CTCASR_CTC_OK;
     }
     if (!p.grad) return;
     __syncthreads();
-    const double logp = dsh[0];
+    const float2 lp2 = psh[0];
 
     // =========================== phase 2: alpha re-compute || beta sweep =======================
-    // LY ring on entry: chunks NCH-1 and NCH-2 (and NCH-3) are resident from phase 1.
-    double offB = 0.0;
+    // LY ring on entry: chunks NCH-1, NCH-2 (and NCH-3) are resident from phase 1.
+    // beta here INCLUDES y_t (Graves' convention); the posterior subtracts log y_t once.
     int curB = 0;
-    if (is_beta) {        // virtual primed row t = T_b: {.., -inf, 0 at S-1}
+    if (is_beta) {        // virtual row t = T_b: {.., -inf, 0 at S-1}
 #pragma unroll
         for (int q = 0; q < SPT; ++q) {
             const int s = gt + q * GT;
-            if (s < S) rowB[curB * RS + s] = s == S - 1 ? 0.f : -INFINITY;
+            if (s < S) rowB[curB * RS + s] = s == S - 1 ? make_float2(0.f, 0.f) : kNegInf;
         }
     }
     for (int r = 0; r <= NCH; ++r) {
@@ -314,8 +305,8 @@ ctc_loss_kernel(const Params p)
         } else if (is_alpha) {
             if (ca >= 0) {
                 const float *LY = LYbuf + (size_t)(ca % 3) * LYS;
-                float *A = Abuf + (size_t)(ca & 1) * CH * RS;
-                float *r0 = rowA;       // checkpoint row of chunk ca
+                float2 *A = Abuf + (size_t)(ca & 1) * CH * RS;
+                float2 *r0 = rowA;      // checkpoint row of chunk ca
 #pragma unroll
                 for (int q = 0; q < SPT; ++q) {
                     const int s = gt + q * GT;
@@ -324,55 +315,41 @@ ctc_loss_kernel(const Params p)
                 group_bar(1, GT);
                 const int lo = ca * CH, hi = min(lo + CH, Tb);
                 for (int t = lo; t < hi; ++t) {
-                    const float *prev = t == lo ? r0 : A + (size_t)(t - lo - 1) * RS;
-                    float *next = A + (size_t)(t - lo) * RS;
+                    const float2 *prev = t == lo ? r0 : A + (size_t)(t - lo - 1) * RS;
+                    float2 *next = A + (size_t)(t - lo) * RS;
                     const float *ly = LY + (size_t)(t - lo) * VP;
 #pragma unroll
                     for (int q = 0; q < SPT; ++q) {
                         const int s = gt + q * GT;
-                        if (s < S) {
-                            const float a0 = prev[s + 2], a1 = prev[s + 1];
-                            const float a2 = st_skA[q] ? prev[s] : -INFINITY;
-                            next[s + 2] = lse3(a0, a1, a2) + ly[st_lp[q]];
-                        }
+                        if (s < S) next[s + 2] = lse3_add(prev[s + 2], prev[s + 1], st_skA[q] ? prev[s] : kNegInf, ly[st_lp[q]]);
                     }
                     group_bar(1, GT);
                 }
             }
         } else if (cb < NCH) {
             const float *LY = LYbuf + (size_t)(cb % 3) * LYS;
-            float *A = Abuf + (size_t)(cb & 1) * CH * RS;
-            // re-base the incoming primed row
-            float m = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < SPT; ++q) {
-                const int s = gt + q * GT;
-                if (s < S) m = fmaxf(m, rowB[curB * RS + s]);
-            }
-            m = group_max(m, red + 16, gt, GT, 2);
-            offB += (double)m;
-#pragma unroll
-            for (int q = 0; q < SPT; ++q) {
-                const int s = gt + q * GT;
-                if (s < S) rowB[curB * RS + s] -= m;
-            }
-            group_bar(2, GT);
-            const float Kc = (float)(off_b[cb] + offB - logp);
+            float2 *A = Abuf + (size_t)(cb & 1) * CH * RS;
             const int lo = cb * CH, hi = min(lo + CH, Tb);
             for (int t = hi - 1; t >= lo; --t) {
-                const float *prev = rowB + curB * RS;
-                float *next = rowB + (curB ^ 1) * RS;
+                const float2 *prev = rowB + curB * RS;
+                float2 *next = rowB + (curB ^ 1) * RS;
                 const float *ly = LY + (size_t)(t - lo) * VP;
-                float *arow = A + (size_t)(t - lo) * RS;
+                float2 *arow = A + (size_t)(t - lo) * RS;
 #pragma unroll
                 for (int q = 0; q < SPT; ++q) {
                     const int s = gt + q * GT;
                     if (s < S) {
-                        const float b0 = prev[s], b1 = prev[s + 1];
-                        const float b2 = st_skB[q] ? prev[s + 2] : -INFINITY;
-                        const float v = lse3(b0, b1, b2);           // beta[s,t] (TF: excludes y_t)
-                        next[s] = v + ly[st_lp[q]];                 // primed for step t-1
-                        arow[s + 2] = __expf(arow[s + 2] + v + Kc); // posterior of state s at t
+                        const float lys = ly[st_lp[q]];
+                        const float2 bt = lse3_add(prev[s], prev[s + 1], st_skB[q] ? prev[s + 2] : kNegInf, lys);
+                        next[s] = bt;
+                        // posterior of state s at t: 2^(alpha + beta - log2 y - log2 p), sums done error-free
+                        const float2 al = arow[s + 2];
+                        float post = 0.f;
+                        if (al.x != -INFINITY && bt.x != -INFINITY) {
+                            const float2 ab = two_sum(al.x, bt.x);
+                            post = ex2f((ab.x - lp2.x) + (((ab.y + al.y) + bt.y) - lp2.y - lys));
+                        }
+                        arow[s + 2].x = post;
                     }
                 }
                 curB ^= 1;
@@ -383,19 +360,19 @@ ctc_loss_kernel(const Params p)
         // ---- gradient rows of chunk cb: y - sum_{s in class k} posterior ---------------------
         if (cb < NCH) {
             const float *LY = LYbuf + (size_t)(cb % 3) * LYS;
-            const float *A = Abuf + (size_t)(cb & 1) * CH * RS;
+            const float2 *A = Abuf + (size_t)(cb & 1) * CH * RS;
             const int lo = cb * CH, hi = min(lo + CH, Tb);
             const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
             for (int t = lo + warp; t < hi; t += nwarps) {
-                const float *arow = A + (size_t)(t - lo) * RS + 2;
+                const float2 *arow = A + (size_t)(t - lo) * RS + 2;
                 float pb = 0.f;                                     // blank states: even s
-                for (int i = lane; 2 * i < S; i += 32) pb += arow[2 * i];
+                for (int i = lane; 2 * i < S; i += 32) pb += arow[2 * i].x;
                 pb = warp_sum(pb);
                 for (int k = lane; k < V; k += 32) {
                     float acc = 0.f;
                     if (k == blank) acc = pb;
-                    else for (int q = csr_start[k]; q < csr_start[k + 1]; ++q) acc += arow[csr_pos[q]];
-                    const float y = __expf(LY[(size_t)(t - lo) * VP + k]);
+                    else for (int q = csr_start[k]; q < csr_start[k + 1]; ++q) acc += arow[csr_pos[q]].x;
+                    const float y = ex2f(LY[(size_t)(t - lo) * VP + k]);
                     grad_b[(size_t)t * gstride + k] = (y - acc) * p.grad_scale;
                 }
             }
@@ -439,7 +416,7 @@ __global__ void greedy_decode_kernel(const float *logits, int T, int B, int V, i
     if (lane == 0) out_len[b] = n;
 }
 
-struct Plan { int CH, RS, GT, NCH, VP; size_t smem, ws_ckpt, ws_total; };
+struct Plan { int CH, RS, GT, NCH, VP; size_t smem, ws_total; };
 
 static int make_plan(int T, int B, int V, int Lmax, Plan *pl)
 {
@@ -452,11 +429,12 @@ static int make_plan(int T, int B, int V, int Lmax, Plan *pl)
     pl->GT = GT;
     pl->RS = (S + 2 + 31) / 32 * 32;
     pl->VP = V | 1;                 // odd row stride: conflict-free lane-per-frame stores
-    pl->CH = pl->RS <= 448 ? 16 : 8;
+    // chunk length: lattice rows are (hi, lo) pairs, 2 x CH x RS x 8 B of shared memory; many utterances
+    // favour a short chunk (4 CTAs per SM), few a long one (less per-chunk overhead)
+    pl->CH = pl->RS <= 448 ? (B >= 296 && pl->RS <= 224 ? 8 : 16) : 8;
     pl->NCH = T > 0 ? (T + pl->CH - 1) / pl->CH : 1;
     pl->smem = SmemLayout(Lmax, V, pl->RS, pl->CH, pl->VP).total;
-    pl->ws_ckpt = align_up((size_t)B * pl->NCH * pl->RS * sizeof(float), 256);
-    pl->ws_total = pl->ws_ckpt + align_up((size_t)B * pl->NCH * sizeof(double), 256);
+    pl->ws_total = align_up((size_t)B * pl->NCH * pl->RS * sizeof(float2), 256);
     return CTCASR_OK;
 }
 
@@ -488,8 +466,7 @@ extern "C" int ctcasr_ctc_loss(const float *logits, int T, int B, int V, int bla
     p.logits = logits; p.T = T; p.B = B; p.V = V; p.blank = blank;
     p.labels = labels; p.lstride = label_stride; p.label_len = label_len; p.seq_len = seq_len;
     p.loss = loss; p.grad = grad; p.grad_scale = grad_scale; p.status = status;
-    p.ckpt = reinterpret_cast<float *>(ws);
-    p.ckoff = reinterpret_cast<double *>(reinterpret_cast<char *>(ws) + pl.ws_ckpt);
+    p.ckpt = reinterpret_cast<float2 *>(ws);
     p.CH = pl.CH; p.RS = pl.RS; p.GT = pl.GT; p.NCH = pl.NCH; p.Lmax = max_label_len; p.VP = pl.VP;
     // three instantiations: one state per thread at high occupancy (the common case, S <= 224),
     // one state per thread up to S = 448, and the generic strided variant for longer labels

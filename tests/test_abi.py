@@ -37,7 +37,7 @@ def test_abi_version_and_workspace_queries(lib):
     assert lib.ctcasr_abi_version() == 1
     # cfg5: B=512, T=1700, L=84, V=29 -> checkpoints only, never the [T,S] alpha table
     ws = lib.ctcasr_ctc_workspace_bytes(1700, 512, 29, 84)
-    assert 0 < ws < 512 * 1700 * 169 * 4 / 8
+    assert 0 < ws < 512 * 1700 * 169 * 8 / 4        # (hi, lo) checkpoint rows every 8 frames, not the table
     assert lib.ctcasr_ctc_workspace_bytes(10, 1, 500, 4) == 0          # V > 128 is unsupported
     rb = lib.ctcasr_birnn_reserve_bytes(1000, 32, 2048, 2048, _lib.CELL_LSTM)
     assert rb >= 1000 * 32 * (2 * 4 * 2048 + 2 * 2048) * 4

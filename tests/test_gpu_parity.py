@@ -106,11 +106,9 @@ def test_ctc_long_labels_multi_state_per_thread():
 
 
 def test_ctc_bench_length_stays_within_tolerance():
-    """cfg5 geometry (T=1700, L=84) with flat random logits, the hardest case for log-domain fp32:
-    the lattice states that carry the posterior sit ~150 nats below the row maximum the kernel
-    re-bases to, so every step rounds at ulp(150) ~ 1e-5 and 1700 steps accumulate to ~2e-3 of
-    gradient error (TF's own un-rebased fp32 recursion: 1e-2, tests/test_oracle_ctc.py).  The loss
-    itself is good to 1e-7.  Shorter utterances (T <= 900 above) meet 1e-3."""
+    """cfg5 geometry (T=1700, L=84) with flat random logits, the hardest case for a log-domain fp32
+    recursion (TF's own: 1e-2 of gradient error, tests/test_oracle_ctc.py).  The kernel carries
+    alpha/beta as (hi, lo) float pairs with error-free additions and stays within 1e-3."""
     rng = np.random.default_rng(5)
     T, B, V = 1700, 3, 29
     logits = (rng.standard_normal((T, B, V)) * 3).astype(np.float32)
@@ -118,7 +116,7 @@ def test_ctc_bench_length_stays_within_tolerance():
     sl = np.full(B, T, np.int32)
     loss, grad, status = _ctc_gpu(logits, labels, ll, sl)
     ol, og, _ = ref.ctc_loss(logits.astype(np.float64), labels, ll, sl)
-    assert (status == 0).all() and rel_err(loss, ol) < 1e-5 and rel_err(grad, og) < 3e-3
+    assert (status == 0).all() and rel_err(loss, ol) < 1e-5 and rel_err(grad, og) < RTOL
 
 
 def test_ctc_error_statuses_and_empty():
@@ -146,11 +144,11 @@ def test_ctc_full_size_properties():
     loss, grad, status = ops.ctc_loss(lg, dev(labels), dev(ll), dev(sl))
     assert int(status.abs().sum()) == 0
     rowsum = grad.sum(2).abs().max().item()
-    assert rowsum < 5e-3, rowsum
+    assert rowsum < 1e-4, rowsum
     pick = [0, 17, 255, 511]
     ol, og, _ = ref.ctc_loss(logits[:, pick].astype(np.float64), labels[pick], ll[pick], sl[pick])
     assert rel_err(loss.cpu().numpy()[pick], ol) < 1e-5
-    assert rel_err(grad.cpu().numpy()[:, pick], og) < 3e-3       # see test_ctc_bench_length_stays_within_tolerance
+    assert rel_err(grad.cpu().numpy()[:, pick], og) < RTOL
 
 
 def test_greedy_decode_bit_exact():
