@@ -84,6 +84,20 @@ __global__ void rnn_cell_fwd_kernel(RnnStep s, int i)
     const bool live = !s.use_len || t < s.seq_len[b];
     const int tp = d == 0 ? t - 1 : t + 1;
     const bool has_prev = i > 0;
+    if (s.cell == CTCASR_CELL_GRU) {
+        float *qt = s.cstate + ((size_t)t * s.B + b) * 2 * H + (size_t)d * H + u;
+        if (!live) { *yo = 0.f; *qt = 0.f; g[u] = 0.f; g[H + u] = 0.f; g[2 * H + u] = 0.f; return; }
+        const float *rh = s.rh + ((size_t)d * s.B + b) * 3 * H;
+        const float rr = has_prev ? rh[u] : 0.f, rz = has_prev ? rh[H + u] : 0.f, rn = has_prev ? rh[2 * H + u] : 0.f;
+        const float hp = has_prev ? s.y[((size_t)tp * s.B + b) * 2 * H + (size_t)d * H + u] : 0.f;
+        const float q = rn + s.bias_rn[d * H + u];
+        const float gr = sigmoidf_(g[u] + rr), gz = sigmoidf_(g[H + u] + rz);
+        const float gn = tanhf(g[2 * H + u] + gr * q);
+        g[u] = gr; g[H + u] = gz; g[2 * H + u] = gn;
+        *qt = q;
+        *yo = (1.f - gz) * gn + gz * hp;
+        return;
+    }
     if (s.cell == CTCASR_CELL_LSTM) {
         float *ct = s.cstate + ((size_t)t * s.B + b) * 2 * H + (size_t)d * H + u;
         const float cp = has_prev ? s.cstate[((size_t)tp * s.B + b) * 2 * H + (size_t)d * H + u] : 0.f;
@@ -120,6 +134,22 @@ __global__ void rnn_cell_bwd_kernel(RnnStep s, int i)
     const float dh = s.dy[((size_t)t * s.B + b) * 2 * H + (size_t)d * H + u] + (i == s.T - 1 ? 0.f : *dhr);
     const int tp = d == 0 ? t - 1 : t + 1;
     const bool has_prev = i > 0;
+    if (s.cell == CTCASR_CELL_GRU) {
+        float *dhd = s.dc_carry + ((size_t)d * s.B + b) * H + u;
+        float *zr = s.dzr + ((size_t)t * s.B + b) * 2 * GH + (size_t)d * GH;
+        if (!live) { g[u] = 0.f; g[H + u] = 0.f; g[2 * H + u] = 0.f; zr[u] = 0.f; zr[H + u] = 0.f; zr[2 * H + u] = 0.f; *dhd = 0.f; return; }
+        const float gr = g[u], gz = g[H + u], gn = g[2 * H + u];
+        const float q = s.cstate[((size_t)t * s.B + b) * 2 * H + (size_t)d * H + u];
+        const float hp = has_prev ? s.y[((size_t)tp * s.B + b) * 2 * H + (size_t)d * H + u] : 0.f;
+        const float dht = dh + (i == s.T - 1 ? 0.f : *dhd);
+        const float dn_pre = dht * (1.f - gz) * (1.f - gn * gn);
+        const float dz_pre = dht * (hp - gn) * gz * (1.f - gz);
+        const float dr_pre = dn_pre * q * gr * (1.f - gr);
+        g[u] = dr_pre; g[H + u] = dz_pre; g[2 * H + u] = dn_pre;
+        zr[u] = dr_pre; zr[H + u] = dz_pre; zr[2 * H + u] = dn_pre * gr;
+        *dhd = dht * gz;
+        return;
+    }
     if (s.cell == CTCASR_CELL_LSTM) {
         float *dcc = s.dc_carry + ((size_t)d * s.B + b) * H + u;
         if (!live) { g[u] = 0.f; g[H + u] = 0.f; g[2 * H + u] = 0.f; g[3 * H + u] = 0.f; *dcc = 0.f; return; }

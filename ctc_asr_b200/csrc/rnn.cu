@@ -16,7 +16,7 @@
 using namespace ctcasr;
 
 namespace {
-struct Reserve { float *gates; float *cstate; size_t bytes; };
+struct Reserve { float *gates; float *cstate; float *dzr; size_t bytes; };
 Reserve carve_reserve(void *base, int T, int B, int H, int G)
 {
     Reserve r;
@@ -24,9 +24,12 @@ Reserve carve_reserve(void *base, int T, int B, int H, int G)
     const size_t nc = align_up((size_t)T * B * 2 * H * sizeof(float), 256);
     r.gates = reinterpret_cast<float *>(base);
     r.cstate = reinterpret_cast<float *>(reinterpret_cast<char *>(base) + ng);
-    r.bytes = ng + nc;
+    r.dzr = reinterpret_cast<float *>(reinterpret_cast<char *>(base) + ng + nc);     // GRU only (G == 3)
+    r.bytes = ng + nc + (G == 3 ? ng : 0);
     return r;
 }
+// stepwise-path scratch at the start of ws: dh_rec [2,B,H], dc_carry [2,B,H], rh [2,B,3H] (GRU)
+size_t step_ws_bytes(int B, int H) { return align_up((size_t)(4 + 6) * B * H * sizeof(float), 256); }
 }  // namespace
 
 extern "C" size_t ctcasr_birnn_reserve_bytes(int T, int B, int in, int H, int cell)
@@ -39,7 +42,8 @@ extern "C" size_t ctcasr_birnn_workspace_bytes(int T, int B, int in, int H, int 
 {
     (void)T; (void)in;
     // dh_rec + dc_carry (stepwise) and the persistent kernel's h exchange / barrier area
-    return align_up((size_t)4 * B * H * sizeof(float), 256) + lstm_tc_workspace_bytes(B, H) + (cell == CTCASR_CELL_LSTM ? 0 : 0);
+    (void)cell;
+    return step_ws_bytes(B, H) + lstm_tc_workspace_bytes(B, H);
 }
 
 extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const float *wx, const float *wh,
@@ -51,8 +55,7 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
     CTCASR_REQUIRE(x && wx && wh && bias && y && reserve, "birnn_fwd: null pointer");
     CTCASR_REQUIRE(T >= 1 && B >= 1 && in >= 1 && H >= 1, "birnn_fwd: bad dims");
     CTCASR_REQUIRE(!use_len || seq_len, "birnn_fwd: use_len needs seq_len");
-    if (cell == CTCASR_CELL_GRU) return fail(CTCASR_ERR_UNSUPPORTED, "birnn: GRU cell not implemented yet");
-    CTCASR_REQUIRE(cell >= 0 && cell <= 2, "birnn_fwd: bad cell %d", cell);
+    CTCASR_REQUIRE(cell >= 0 && cell <= 3, "birnn_fwd: bad cell %d", cell);
     if (ws_bytes < ctcasr_birnn_workspace_bytes(T, B, in, H, cell)) return fail(CTCASR_ERR_WORKSPACE, "birnn_fwd: workspace too small");
     const int G = num_gates(cell), GH = G * H;
     if (int rcs = gemm_scratch_check(compute, 1, T * B, 2 * GH, in)) return rcs;
@@ -69,13 +72,15 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
 
     // 2. recurrence
     if (compute != CTCASR_COMPUTE_FP32 && lstm_tc_eligible(T, B, H, cell)) {
-        char *wsb = reinterpret_cast<char *>(ws) + align_up((size_t)4 * B * H * sizeof(float), 256);
+        char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
         return lstm_tc_fwd(seq_len, wh, r.gates, r.cstate, y, T, B, H, use_len, forget_bias, wsb, stream);
     }
     RnnStep s;
     s.T = T; s.B = B; s.H = H; s.G = G; s.cell = cell; s.use_len = use_len; s.forget_bias = forget_bias;
     s.seq_len = seq_len; s.gates = r.gates; s.cstate = r.cstate; s.y = y; s.dy = nullptr;
     s.dh_rec = nullptr; s.dc_carry = nullptr;
+    const bool gru = cell == CTCASR_CELL_GRU;
+    s.rh = reinterpret_cast<float *>(ws) + (size_t)4 * B * H; s.dzr = nullptr; s.bias_rn = bias + 2 * GH;
     for (int i = 0; i < T; ++i) {
         if (i > 0) {
             GemmArgs h;
@@ -85,6 +90,10 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
             h.A[0] = y + (size_t)(tf - 1) * B * 2 * H;            h.A[1] = y + (size_t)(tb + 1) * B * 2 * H + H;
             h.B[0] = wh;                                          h.B[1] = wh + (size_t)H * GH;
             h.C[0] = r.gates + (size_t)tf * B * 2 * GH;           h.C[1] = r.gates + (size_t)tb * B * 2 * GH + GH;
+            if (gru) {      // the candidate gate multiplies h Rn by r: keep h Wh apart from the input projection
+                h.epi.accumulate = 0; h.ldc = GH;
+                h.C[0] = s.rh; h.C[1] = s.rh + (size_t)B * GH;
+            }
             rc = gemm_simt(h, stream);
             if (rc != CTCASR_OK) return rc;
         }
@@ -103,8 +112,7 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
     cudaStream_t stream = (cudaStream_t)stream_;
     CTCASR_REQUIRE(x && wx && wh && y && reserve && dy && dwx && dwh && dbias, "birnn_bwd: null pointer");
     CTCASR_REQUIRE(T >= 1 && B >= 1 && in >= 1 && H >= 1, "birnn_bwd: bad dims");
-    if (cell == CTCASR_CELL_GRU) return fail(CTCASR_ERR_UNSUPPORTED, "birnn: GRU cell not implemented yet");
-    CTCASR_REQUIRE(cell >= 0 && cell <= 2, "birnn_bwd: bad cell %d", cell);
+    CTCASR_REQUIRE(cell >= 0 && cell <= 3, "birnn_bwd: bad cell %d", cell);
     if (ws_bytes < ctcasr_birnn_workspace_bytes(T, B, in, H, cell)) return fail(CTCASR_ERR_WORKSPACE, "birnn_bwd: workspace too small");
     const int G = num_gates(cell), GH = G * H;
     if (int rcs = gemm_scratch_check(compute, 1, in, 2 * GH, T * B)) return rcs;
@@ -114,7 +122,7 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
     int rc;
 
     if (compute != CTCASR_COMPUTE_FP32 && lstm_tc_eligible(T, B, H, cell)) {
-        char *wsb = reinterpret_cast<char *>(ws) + align_up((size_t)4 * B * H * sizeof(float), 256);
+        char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
         rc = lstm_tc_bwd(seq_len, wh, r.gates, r.cstate, dy, T, B, H, use_len, wsb, stream);
         if (rc != CTCASR_OK) return rc;
     } else {
@@ -123,6 +131,7 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
         s.seq_len = seq_len; s.gates = r.gates; s.cstate = r.cstate; s.y = const_cast<float *>(y); s.dy = dy;
         s.dh_rec = reinterpret_cast<float *>(ws);
         s.dc_carry = s.dh_rec + (size_t)2 * B * H;
+        s.rh = nullptr; s.dzr = r.dzr; s.bias_rn = nullptr;
         CTCASR_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)4 * B * H * sizeof(float), stream));
         for (int i = T - 1; i >= 0; --i) {
             rc = rnn_cell_bwd(s, i, stream);
@@ -131,7 +140,8 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
                 GemmArgs h;
                 h.nz = 2; h.M = B; h.N = H; h.K = GH; h.tb = 1; h.lda = 2 * GH; h.ldb = GH; h.ldc = H;
                 const int tf = i, tb = T - 1 - i;
-                h.A[0] = r.gates + (size_t)tf * B * 2 * GH;       h.A[1] = r.gates + (size_t)tb * B * 2 * GH + GH;
+                const float *dzh = cell == CTCASR_CELL_GRU ? r.dzr : r.gates;
+                h.A[0] = dzh + (size_t)tf * B * 2 * GH;           h.A[1] = dzh + (size_t)tb * B * 2 * GH + GH;
                 h.B[0] = wh;                                      h.B[1] = wh + (size_t)H * GH;
                 h.C[0] = s.dh_rec;                                h.C[1] = s.dh_rec + (size_t)B * H;
                 rc = gemm_simt(h, stream);
@@ -139,9 +149,15 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
             }
         }
     }
-    // r.gates now holds dz [T*B, 2GH]
+    // r.gates now holds dz [T*B, 2GH] (wrt the input-side pre-activations); GRU: r.dzr wrt h Wh
+    const float *dzh = cell == CTCASR_CELL_GRU ? r.dzr : r.gates;
     rc = colsum(r.gates, T * B, 2 * GH, 2 * GH, dbias, stream);
     if (rc != CTCASR_OK) return rc;
+    if (cell == CTCASR_CELL_GRU)
+        for (int d = 0; d < 2; ++d) {       // b_rn gradient: column sums of the n block of dzr
+            rc = colsum(r.dzr + (size_t)d * GH + 2 * H, T * B, H, 2 * GH, dbias + 2 * GH + d * H, stream);
+            if (rc != CTCASR_OK) return rc;
+        }
     {   // dWx[in, 2GH] = X^T dz
         GemmArgs g;
         g.A[0] = x; g.B[0] = r.gates; g.C[0] = dwx; g.ta = 1;
@@ -152,8 +168,8 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
     if (T > 1) {   // dWh[d][H, GH] = H_prev^T dz_d ; fw: (y[t-1], dz[t]), bw: (y[t+1], dz[t])
         GemmArgs g;
         g.nz = 2; g.ta = 1; g.M = H; g.N = GH; g.K = (T - 1) * B; g.lda = 2 * H; g.ldb = 2 * GH; g.ldc = GH;
-        g.A[0] = y;                              g.B[0] = r.gates + (size_t)B * 2 * GH;   g.C[0] = dwh;
-        g.A[1] = y + (size_t)B * 2 * H + H;      g.B[1] = r.gates + GH;                   g.C[1] = dwh + (size_t)H * GH;
+        g.A[0] = y;                              g.B[0] = dzh + (size_t)B * 2 * GH;       g.C[0] = dwh;
+        g.A[1] = y + (size_t)B * 2 * H + H;      g.B[1] = dzh + GH;                       g.C[1] = dwh + (size_t)H * GH;
         rc = gemm(g, compute, stream);
         if (rc != CTCASR_OK) return rc;
     } else {

@@ -101,7 +101,8 @@ def param_specs(cfg: ModelConfig):
     for l in range(cfg.num_layers_rnn):
         specs.append(("rnn/l%d/wx" % l, (nin, 2 * G * H), ("glorot", nin + H, G * H)))
         specs.append(("rnn/l%d/wh" % l, (2, H, G * H), ("glorot", nin + H, G * H)))
-        specs.append(("rnn/l%d/bias" % l, (2 * G * H,), "zeros"))
+        # GRU: + b_rn [2, H], the recurrent bias of the candidate gate (cuDNN formulation)
+        specs.append(("rnn/l%d/bias" % l, (2 * G * H + (2 * H if cfg.rnn_cell == "gru" else 0),), "zeros"))
         nin = 2 * H
     specs.append(("dense4/dense/kernel", (nin, D), "truncnorm"))
     specs.append(("dense4/dense/bias", (D,), "zeros"))

@@ -109,7 +109,10 @@ int ctcasr_dense_bwd(const float *x, const float *w, const float *y, float *dy,
  * asr/util/tf_contrib.py:183-189) / tfc.cudnn_rnn.Cudnn* (asr/model.py:194-215).
  *   x [T,B,in]  ->  y [T,B,2H]  (fw | bw)
  *   wx [in, 2*G*H] (fw gate columns | bw gate columns), wh [2][H, G*H], bias [2*G*H]
- *   LSTM gate order i, j, f, o with forget_bias (TF LSTMCell); G = 4 (LSTM), 1 (tanh/relu)
+ *   LSTM gate order i, j, f, o with forget_bias (TF LSTMCell); G = 4 (LSTM), 3 (GRU), 1 (tanh/relu)
+ *   GRU: cuDNN formulation (what CudnnGRU computes, asr/model.py:197), gate order r, z, n;
+ *        bias / dbias carry 2*H extra entries after the 2*G*H input-side ones: b_rn [2][H], the
+ *        recurrent bias of the candidate gate  n = tanh(x Wn + bn + r * (h Rn + b_rn))
  *   use_len != 0: dynamic_rnn(sequence_length) semantics (zero output + frozen state past
  *                 seq_len[b]; backward cell starts at seq_len[b]-1).  0: every frame (cuDNN path).
  *   reserve: >= ctcasr_birnn_reserve_bytes(); written by fwd, consumed AND clobbered by bwd.

@@ -247,6 +247,10 @@ int SUF(oracle_dense_bwd)(const REAL *x, const REAL *w, const REAL *y, const REA
  *   cell 0: h' = tanh(x Wx + h Wh + b)         cell 1: h' = relu(...)
  *   cell 2: TF LSTMCell, gate order i, j, f, o; c' = sig(f + forget_bias) c + sig(i) tanh(j);
  *           h' = sig(o) tanh(c')
+ *   cell 3: GRU in the cuDNN formulation the reference reaches through CudnnGRU (asr/model.py:197),
+ *           gate order r, z, n:  r = sig(x Wr + h Rr + br), z = sig(x Wz + h Rz + bz),
+ *           n = tanh(x Wn + bn + r * (h Rn + b_rn)),  h' = (1 - z) n + z h.
+ *           bias then has 2*3H input-side entries followed by b_rn [2*H]; `cstate` stores h Rn + b_rn.
  *   use_len != 0: dynamic_rnn(sequence_length): for t >= len_b output row is zero and the state
  *           is carried through; the backward direction starts at t = len_b - 1 with zero state
  *           (reverse_sequence semantics).  use_len == 0: cuDNN-path behaviour, all T frames.
@@ -264,7 +268,6 @@ int SUF(oracle_birnn_fwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                           int T, int B, int in, int H, int cell, int use_len, REAL forget_bias)
 {
     const int G = SUF(ngates)(cell), GH = G * H;
-    if (cell == 3) return -1; /* GRU not restated yet */
     memset(y, 0, sizeof(REAL) * (size_t)T * B * 2 * H);
     memset(gates, 0, sizeof(REAL) * (size_t)2 * T * B * GH);
     if (cstate) memset(cstate, 0, sizeof(REAL) * (size_t)2 * T * B * H);
@@ -285,13 +288,33 @@ int SUF(oracle_birnn_fwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                     const REAL *wr = wx + (size_t)k * 2 * GH + d * GH;
                     for (int g = 0; g < GH; ++g) z[g] += xv * wr[g];
                 }
+                REAL *gt = gates + (((size_t)d * T + t) * B + b) * GH;
+                REAL *yt = y + ((size_t)t * B + b) * 2 * H + d * H;
+                if (cell == 3) {
+                    /* recurrent part kept apart: the candidate gate multiplies it by r */
+                    REAL *rh = (REAL *)calloc(GH, sizeof(REAL));
+                    for (int k = 0; k < H; ++k) {
+                        const REAL hv = h[k];
+                        const REAL *wr = whd + (size_t)k * GH;
+                        for (int g = 0; g < GH; ++g) rh[g] += hv * wr[g];
+                    }
+                    REAL *qt = cstate + (((size_t)d * T + t) * B + b) * H;
+                    for (int u = 0; u < H; ++u) {
+                        const REAL q = rh[2 * H + u] + bias[2 * GH + d * H + u];
+                        const REAL gr = SUF(sigm)(z[u] + rh[u]), gz = SUF(sigm)(z[H + u] + rh[H + u]);
+                        const REAL gn = (REAL)tanh((double)(z[2 * H + u] + gr * q));
+                        gt[u] = gr; gt[H + u] = gz; gt[2 * H + u] = gn; qt[u] = q;
+                        h[u] = (1 - gz) * gn + gz * h[u];
+                        yt[u] = h[u];
+                    }
+                    free(rh);
+                    continue;
+                }
                 for (int k = 0; k < H; ++k) {
                     const REAL hv = h[k];
                     const REAL *wr = whd + (size_t)k * GH;
                     for (int g = 0; g < GH; ++g) z[g] += hv * wr[g];
                 }
-                REAL *gt = gates + (((size_t)d * T + t) * B + b) * GH;
-                REAL *yt = y + ((size_t)t * B + b) * 2 * H + d * H;
                 if (cell == 2) {
                     REAL *ct = cstate + (((size_t)d * T + t) * B + b) * H;
                     for (int u = 0; u < H; ++u) {
@@ -323,8 +346,8 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                           int T, int B, int in, int H, int cell, int use_len)
 {
     const int G = SUF(ngates)(cell), GH = G * H;
-    if (cell == 3) return -1;
-    REAL *dz = (REAL *)calloc((size_t)2 * T * B * GH, sizeof(REAL));   /* [2][T,B,GH] */
+    REAL *dz = (REAL *)calloc((size_t)2 * T * B * GH, sizeof(REAL));   /* [2][T,B,GH]: gradient wrt the input-side pre-activations */
+    REAL *dzr = cell == 3 ? (REAL *)calloc((size_t)2 * T * B * GH, sizeof(REAL)) : dz;  /* GRU: wrt h R (n columns scaled by r) */
 #pragma omp parallel for collapse(2)
     for (int d = 0; d < 2; ++d) {
         for (int b = 0; b < B; ++b) {
@@ -339,6 +362,29 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                 const REAL *gt = gates + (((size_t)d * T + t) * B + b) * GH;
                 REAL *dzt = dz + (((size_t)d * T + t) * B + b) * GH;
                 const REAL *dyt = dy + ((size_t)t * B + b) * 2 * H + d * H;
+                if (cell == 3) {
+                    const REAL *qt = cstate + (((size_t)d * T + t) * B + b) * H;
+                    REAL *dzrt = dzr + (((size_t)d * T + t) * B + b) * GH;
+                    REAL *dhd = dc;     /* direct path z * dh into h_{t-1}, added after the matvec below */
+                    for (int u = 0; u < H; ++u) {
+                        const REAL gr = gt[u], gz = gt[H + u], gn = gt[2 * H + u];
+                        const REAL hp = has_prev ? y[((size_t)tp * B + b) * 2 * H + d * H + u] : 0;
+                        const REAL dht = dyt[u] + dh[u];
+                        const REAL dn_pre = dht * (1 - gz) * (1 - gn * gn);
+                        const REAL dz_pre = dht * (hp - gn) * gz * (1 - gz);
+                        const REAL dr_pre = dn_pre * qt[u] * gr * (1 - gr);
+                        dzt[u] = dr_pre; dzt[H + u] = dz_pre; dzt[2 * H + u] = dn_pre;
+                        dzrt[u] = dr_pre; dzrt[H + u] = dz_pre; dzrt[2 * H + u] = dn_pre * gr;
+                        dhd[u] = dht * gz;
+                    }
+                    for (int k = 0; k < H; ++k) {
+                        const REAL *wr = whd + (size_t)k * GH;
+                        REAL s = 0;
+                        for (int g = 0; g < GH; ++g) s += dzrt[g] * wr[g];
+                        dh[k] = s + dhd[k];
+                    }
+                    continue;
+                }
                 if (cell == 2) {
                     const REAL *ct = cstate + (((size_t)d * T + t) * B + b) * H;
                     const REAL *cp = has_prev ? cstate + (((size_t)d * T + tp) * B + b) * H : NULL;
@@ -373,7 +419,7 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
     /* parameter and input gradients from dz */
     memset(dwx, 0, sizeof(REAL) * (size_t)in * 2 * GH);
     memset(dwh, 0, sizeof(REAL) * (size_t)2 * H * GH);
-    memset(dbias, 0, sizeof(REAL) * (size_t)2 * GH);
+    memset(dbias, 0, sizeof(REAL) * ((size_t)2 * GH + (cell == 3 ? 2 * H : 0)));
     if (dx) memset(dx, 0, sizeof(REAL) * (size_t)T * B * in);
     for (int d = 0; d < 2; ++d) {
         for (int t = 0; t < T; ++t) for (int b = 0; b < B; ++b) {
@@ -381,6 +427,10 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
             if (t >= len) continue;
             const REAL *dzt = dz + (((size_t)d * T + t) * B + b) * GH;
             for (int g = 0; g < GH; ++g) dbias[d * GH + g] += dzt[g];
+            if (cell == 3) {
+                const REAL *dzrt = dzr + (((size_t)d * T + t) * B + b) * GH;
+                for (int u = 0; u < H; ++u) dbias[2 * GH + d * H + u] += dzrt[2 * H + u];
+            }
         }
 #pragma omp parallel for
         for (int k = 0; k < in; ++k) {
@@ -399,7 +449,7 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                     const int t = d == 0 ? step : len - 1 - step;
                     const int tp = d == 0 ? t - 1 : t + 1;
                     const REAL hv = y[((size_t)tp * B + b) * 2 * H + d * H + k];
-                    const REAL *dzt = dz + (((size_t)d * T + t) * B + b) * GH;
+                    const REAL *dzt = dzr + (((size_t)d * T + t) * B + b) * GH;
                     REAL *o = dwh + ((size_t)d * H + k) * GH;
                     for (int g = 0; g < GH; ++g) o[g] += hv * dzt[g];
                 }
@@ -418,6 +468,7 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
             }
         }
     }
+    if (dzr != dz) free(dzr);
     free(dz);
     return 0;
 }

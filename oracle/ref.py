@@ -123,7 +123,8 @@ def birnn_fwd(x, seq_len, wx, wh, bias, cell, use_len=True, forget_bias=1.0):
     T, B, nin = x.shape
     H = wh.shape[1]
     G = NUM_GATES[cell]
-    assert wx.shape == (nin, 2 * G * H) and wh.shape == (2, H, G * H) and bias.shape == (2 * G * H,)
+    nb = 2 * G * H + (2 * H if cell == 3 else 0)       # GRU: + b_rn [2, H] after the input-side biases
+    assert wx.shape == (nin, 2 * G * H) and wh.shape == (2, H, G * H) and bias.shape == (nb,)
     y = np.zeros((T, B, 2 * H), dtype)
     gates = np.zeros((2, T, B, G * H), dtype)
     cst = np.zeros((2, T, B, H), dtype)
@@ -144,7 +145,7 @@ def birnn_bwd(x, seq_len, wx, wh, y, gates, cst, dy, cell, use_len=True, want_dx
     dx = np.zeros((T, B, nin), dtype) if want_dx else None
     dwx = np.zeros((nin, 2 * G * H), dtype)
     dwh = np.zeros((2, H, G * H), dtype)
-    db = np.zeros(2 * G * H, dtype)
+    db = np.zeros(2 * G * H + (2 * H if cell == 3 else 0), dtype)
     rc = getattr(lib(), "oracle_birnn_bwd" + suf)(
         _p(x), _p(_c(seq_len, np.int32)), _p(wx), _p(wh), _p(y), _p(gates), _p(cst), _p(dy),
         _p(dx), _p(dwx), _p(dwh), _p(db), T, B, nin, H, cell, int(use_len))

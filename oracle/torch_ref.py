@@ -42,8 +42,20 @@ def _dynamic_rnn(cfg, x, lengths, kernel, bias):
     c = x.new_zeros(B, H)
     outs = []
     for t in range(T):
-        z = torch.cat([x[t], h], 1) @ kernel + bias
-        if cfg.rnn_cell == "lstm":
+        if cfg.rnn_cell == "gru":                         # cuDNN GRU: r, z, n; bias = input-side [3H] + b_rn [H]
+            nin = x.shape[2]
+            px = x[t] @ kernel[:nin] + bias[:3 * H]
+            rh = h @ kernel[nin:]
+            r = torch.sigmoid(px[:, :H] + rh[:, :H])
+            zg = torch.sigmoid(px[:, H:2 * H] + rh[:, H:2 * H])
+            n = torch.tanh(px[:, 2 * H:] + r * (rh[:, 2 * H:] + bias[3 * H:]))
+            h_new, c_new = (1 - zg) * n + zg * h, c
+            z = None
+        else:
+            z = torch.cat([x[t], h], 1) @ kernel + bias
+        if cfg.rnn_cell == "gru":
+            pass
+        elif cfg.rnn_cell == "lstm":
             i, j, f, o = z.split(H, 1)                    # TF LSTMCell gate order
             c_new = torch.sigmoid(f + cfg.lstm_forget_bias) * c + torch.sigmoid(i) * torch.tanh(j)
             h_new = torch.sigmoid(o) * torch.tanh(c_new)
@@ -75,9 +87,13 @@ def inference(cfg, p, sequences, seq_length):
         GH = G * H
         k_fw = torch.cat([wx[:, :GH], wh[0]], 0)
         k_bw = torch.cat([wx[:, GH:], wh[1]], 0)
-        fw = _dynamic_rnn(cfg, x, lengths, k_fw, b[:GH])
+        if cfg.rnn_cell == "gru":
+            b_fw, b_bw = torch.cat([b[:GH], b[2 * GH:2 * GH + H]]), torch.cat([b[GH:2 * GH], b[2 * GH + H:]])
+        else:
+            b_fw, b_bw = b[:GH], b[GH:]
+        fw = _dynamic_rnn(cfg, x, lengths, k_fw, b_fw)
         rl = seq_length if lengths is not None else full
-        bw = _reverse_sequence(_dynamic_rnn(cfg, _reverse_sequence(x, rl), lengths, k_bw, b[GH:]), rl)
+        bw = _reverse_sequence(_dynamic_rnn(cfg, _reverse_sequence(x, rl), lengths, k_bw, b_bw), rl)
         x = torch.cat([fw, bw], 2)
     x = torch.clamp(torch.relu(x @ p["dense4/dense/kernel"] + p["dense4/dense/bias"]), max=cfg.relu_cutoff)
     return x @ p["logits/dense/kernel"] + p["logits/dense/bias"]

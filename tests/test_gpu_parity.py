@@ -198,7 +198,7 @@ def test_dense_fwd_bwd_vs_oracle(rate):
 
 
 # ------------------------------------------------------------------------------------------ BiRNN
-@pytest.mark.parametrize("cell", ["rnn_tanh", "rnn_relu", "lstm"])
+@pytest.mark.parametrize("cell", ["rnn_tanh", "rnn_relu", "lstm", "gru"])
 @pytest.mark.parametrize("use_len", [True, False])
 def test_birnn_layer_vs_oracle(cell, use_len):
     rng = np.random.default_rng(6)
@@ -209,7 +209,7 @@ def test_birnn_layer_vs_oracle(cell, use_len):
     sl = np.array([23, 20, 11, 3, 1], np.int32)
     wx = (rng.standard_normal((nin, 2 * G * H)) * 0.3).astype(np.float32)
     wh = (rng.standard_normal((2, H, G * H)) * 0.3).astype(np.float32)
-    bias = (rng.standard_normal(2 * G * H) * 0.1).astype(np.float32)
+    bias = (rng.standard_normal(2 * G * H + (2 * H if cell == "gru" else 0)) * 0.1).astype(np.float32)
     dy = rng.standard_normal((T, B, 2 * H)).astype(np.float32)
     rb, _ = ops.birnn_sizes(T, B, nin, H, cid)
     reserve = torch.empty(rb, dtype=torch.uint8, device="cuda")
@@ -285,6 +285,14 @@ def test_small_3d2r2d_lstm_ragged(cudnn):
     cfg = ModelConfig(num_layers_dense=3, num_units_dense=64, num_layers_rnn=2, num_units_rnn=32,
                       rnn_cell="lstm", cudnn=cudnn, dense_dropout_rate=0.0, compute="fp32")
     _whole_path(cfg, B=4, T=60, L=8, ragged=True)
+
+
+@pytest.mark.parametrize("cell", ["gru", "rnn_relu"])
+def test_whole_path_other_cells(cell):
+    """The rest of the reference's rnn_cell menu (asr/params.py:48-50): GRU and the default ReLU RNN."""
+    cfg = ModelConfig(num_layers_dense=2, num_units_dense=64, num_layers_rnn=2, num_units_rnn=24,
+                      rnn_cell=cell, cudnn=True, dense_dropout_rate=0.0, compute="fp32")
+    _whole_path(cfg, B=3, T=30, L=5, ragged=False)
 
 
 def test_train_step_decreases_loss_and_matches_oracle_adam():

@@ -29,7 +29,7 @@ def _batch(cfg, B=3, T=12, seed=0, ragged=True):
     return x, sl, lab, ll
 
 
-@pytest.mark.parametrize("cell", ["rnn_tanh", "rnn_relu", "lstm"])
+@pytest.mark.parametrize("cell", ["rnn_tanh", "rnn_relu", "lstm", "gru"])
 @pytest.mark.parametrize("cudnn", [False, True])
 def test_whole_path_vs_torch_autograd(cell, cudnn):
     cfg = _small_cfg(cell, cudnn)
@@ -144,3 +144,39 @@ def test_adam_tf1_formula():
         ref.adam(p2, m2, v2, g * step, step=step, lr=1e-3)
     # TF1's epsilon placement differs from torch's by O(eps): agreement to ~1e-6 relative
     np.testing.assert_allclose(p2, tp.detach().numpy(), rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("use_len", [True, False])
+def test_gru_layer_vs_torch_nn_gru(use_len):
+    """cuDNN-formulation GRU (what the reference's CudnnGRU computes, asr/model.py:197) == torch.nn.GRU."""
+    rng = np.random.default_rng(0)
+    T, B, nin, H = 7, 3, 5, 4
+    x = rng.standard_normal((T, B, nin))
+    sl = np.array([7, 5, 2], np.int32)
+    wx = rng.standard_normal((nin, 6 * H)) * 0.5
+    wh = rng.standard_normal((2, H, 3 * H)) * 0.5
+    bias = rng.standard_normal(8 * H) * 0.3
+    y, g, q = ref.birnn_fwd(x, sl, wx, wh, bias, 3, use_len=use_len)
+    gru = torch.nn.GRU(nin, H, bidirectional=True).double()
+    with torch.no_grad():
+        for d, suf in enumerate(["", "_reverse"]):
+            getattr(gru, "weight_ih_l0" + suf).copy_(torch.tensor(wx[:, d * 3 * H:(d + 1) * 3 * H].T.copy()))
+            getattr(gru, "weight_hh_l0" + suf).copy_(torch.tensor(wh[d].T.copy()))
+            getattr(gru, "bias_ih_l0" + suf).copy_(torch.tensor(bias[d * 3 * H:(d + 1) * 3 * H]))
+            bhh = np.zeros(3 * H)
+            bhh[2 * H:] = bias[6 * H + d * H:6 * H + (d + 1) * H]
+            getattr(gru, "bias_hh_l0" + suf).copy_(torch.tensor(bhh))
+    xt = torch.tensor(x, requires_grad=True)
+    if use_len:
+        packed = torch.nn.utils.rnn.pack_padded_sequence(xt, torch.tensor(sl, dtype=torch.long))
+        out, _ = torch.nn.utils.rnn.pad_packed_sequence(gru(packed)[0], total_length=T)
+    else:
+        out, _ = gru(xt)
+    np.testing.assert_allclose(y, out.detach().numpy(), atol=1e-12)
+    dy = rng.standard_normal(y.shape)
+    out.backward(torch.tensor(dy))
+    dx, dwx, dwh, db = ref.birnn_bwd(x, sl, wx, wh, y, g, q, dy, 3, use_len=use_len)
+    np.testing.assert_allclose(dx, xt.grad.numpy(), atol=1e-12)
+    np.testing.assert_allclose(dwh[0], gru.weight_hh_l0.grad.numpy().T, atol=1e-12)
+    np.testing.assert_allclose(dwx[:, 3 * H:], gru.weight_ih_l0_reverse.grad.numpy().T, atol=1e-12)
+    np.testing.assert_allclose(db[6 * H:7 * H], gru.bias_hh_l0.grad.numpy()[2 * H:], atol=1e-12)
