@@ -78,7 +78,8 @@ class CTCModel:
 
     # ---- asr/model.py:123-236 -----------------------------------------------------------------
     def inference_fn(self, sequences, seq_length, training=True):
-        """sequences [B,T,F] float32, seq_length [B] int32 -> (logits [T,B,V], seq_length)."""
+        """sequences [B,T,F] float32, seq_length [B] int32 -> (logits [T,B,V], seq_length).
+        The returned logits are a view of a buffer that the next inference_fn call reuses."""
         cfg = self.cfg
         if sequences.dim() != 3 or sequences.shape[2] != cfg.num_features:
             raise ValueError("sequences must be [batch_size, time, %d]" % cfg.num_features)

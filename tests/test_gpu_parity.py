@@ -457,3 +457,71 @@ def test_lstm_persistent_tcgen05_layer_vs_oracle(use_len, T, B, nin, H):
     odx, odwx, odwh, odb = ref.birnn_bwd(x.astype(np.float64), sl, wx, wh, oy, og, oc, dy, 2, use_len=use_len)
     for got, want, name in [(dx, odx, "dx"), (dwx, odwx, "dwx"), (dwh, odwh, "dwh"), (db, odb, "dbias")]:
         assert rel_err(got.cpu().numpy(), want) < RTOL, name
+
+
+# ----------------------------------------------- full-size properties (BASELINE cfg2: B=32, T=1000)
+@pytest.fixture(scope="module")
+def cfg2_model():
+    from ctc_asr_b200.model import CTCModel
+    cfg = ModelConfig(num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_units_rnn=2048,
+                      rnn_cell="lstm", cudnn=False, dense_dropout_rate=0.0, compute="bf16x3")
+    model = CTCModel(cfg, seed=1)
+    x, sl, lab, ll = synthetic.fixed_batch(32, 1000, 160, seed=0)
+    sl[5], sl[17] = 700, 431                     # two shorter utterances exercise the masking at scale
+    x[5, 700:] = 0
+    x[17, 431:] = 0
+    return model, tuple(torch.from_numpy(a).cuda() for a in (x, sl, lab, ll))
+
+
+def _loss_and_grad(model, batch, rows=slice(None), global_batch=None):
+    x, sl, lab, ll = batch
+    logits, _ = model.inference_fn(x[rows], sl[rows], training=False)
+    loss = model.loss_fn(logits, sl[rows], (lab[rows], ll[rows]), global_batch=global_batch)
+    model.backward()
+    return float(loss), model.grad_flat.clone(), logits.clone()      # logits live in a buffer the next call reuses
+
+
+def test_cfg2_full_size_gradient_is_the_derivative_of_the_loss(cfg2_model):
+    """Size-independent property at the benchmarked size: the backward pass (LSTM cluster kernel,
+    dgrad / wgrad GEMMs, CTC gradient) is the derivative of the forward pass —
+    (L(p + e d) - L(p - e d)) / 2e == <grad, d> along a random direction d."""
+    model, batch = cfg2_model
+    loss0, grad, _ = _loss_and_grad(model, batch)
+    assert np.isfinite(loss0)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    d = torch.randn(model.flat.shape, device="cuda", generator=gen)
+    d *= grad.abs().mean() / (d.abs().mean() + 1e-30)
+    d = grad + d                                   # mostly along the gradient so the signal is large
+    d /= d.norm()
+    analytic = float((grad.double() * d.double()).sum())
+    p0 = model.flat.clone()
+    eps = 2e-4                                     # |grad| ~ 2e4: stay in the linear regime, above fp32 loss resolution
+    model.flat.copy_(p0 + eps * d)
+    lp, _, _ = _loss_and_grad(model, batch)
+    model.flat.copy_(p0 - eps * d)
+    lm, _, _ = _loss_and_grad(model, batch)
+    model.flat.copy_(p0)
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - analytic) / abs(analytic) < 2e-2, (fd, analytic)
+
+
+def test_cfg2_full_size_shards_add_up(cfg2_model):
+    """Data-parallel property on one GPU: gradients of two half batches, each scaled by 1/global_batch,
+    sum to the full-batch gradient (what the NCCL all-reduce relies on); per-utterance results do not
+    depend on which other utterances share the batch."""
+    model, batch = cfg2_model
+    loss, grad, logits = _loss_and_grad(model, batch)
+    per_utt = model.last_per_utterance_loss.clone()
+    la, ga, logits_a = _loss_and_grad(model, batch, slice(0, 16), global_batch=32)
+    pa = model.last_per_utterance_loss.clone()
+    lb, gb, _ = _loss_and_grad(model, batch, slice(16, 32), global_batch=32)
+    assert abs((la + lb) - loss) / abs(loss) < 1e-5
+    err = (ga + gb - grad).abs().max().item() / grad.abs().max().item()
+    assert err < 1e-3, err
+    assert torch.allclose(pa, per_utt[:16], rtol=1e-5)
+    # same utterance, different batch composition: identical greedy transcript (integer work)
+    ids_full, n_full = ops.greedy_decode(logits, batch[1])
+    ids_half, n_half = ops.greedy_decode(logits_a, batch[1][:16].contiguous())
+    assert (n_full[:16] == n_half).all()
+    for b in range(16):
+        assert torch.equal(ids_full[b, :n_full[b]], ids_half[b, :n_half[b]])
