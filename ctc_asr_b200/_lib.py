@@ -24,6 +24,7 @@ SIGNATURES = {
     "ctcasr_ctc_loss": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _i, _vp, _sz, _vp]),
     "ctcasr_ctc_loss_host": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp]),
     "ctcasr_greedy_decode": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ctcasr_edit_distance": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "ctcasr_dense_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _u32, _i, _vp]),
     "ctcasr_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _u32, _i, _vp]),
     "ctcasr_birnn_reserve_bytes": (_sz, [_i, _i, _i, _i, _i]),

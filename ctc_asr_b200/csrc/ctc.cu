@@ -416,6 +416,43 @@ __global__ void greedy_decode_kernel(const float *logits, int T, int B, int V, i
     if (lane == 0) out_len[b] = n;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Levenshtein distance between label sequences (tf.edit_distance, asr/model.py:338): one CTA per
+// pair, anti-diagonal wavefront over three rolling diagonals in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void edit_distance_kernel(const int *hyp, int hstride, const int *hyp_len, const int *truth, int tstride,
+                                     const int *truth_len, int normalize, float *out)
+{
+    extern __shared__ int ed_smem[];
+    const int b = blockIdx.x;
+    const int n = hyp_len[b], m = truth_len[b];
+    const int *h = hyp + (size_t)b * hstride, *t = truth + (size_t)b * tstride;
+    int *d0 = ed_smem, *d1 = d0 + (n + 2), *d2 = d1 + (n + 2);       // diagonals k-2, k-1, k indexed by i
+    // D[i][j], i in [0,n], j in [0,m]; cell (i, j) lies on diagonal k = i + j
+    for (int k = 0; k <= n + m; ++k) {
+        const int ilo = max(0, k - m), ihi = min(n, k);
+        for (int i = ilo + (int)threadIdx.x; i <= ihi; i += blockDim.x) {
+            const int j = k - i;
+            int v;
+            if (i == 0) v = j;
+            else if (j == 0) v = i;
+            else {
+                const int sub = d0[i - 1] + (h[i - 1] != t[j - 1] ? 1 : 0);
+                v = min(sub, min(d1[i - 1] + 1, d1[i] + 1));          // (i-1, j) and (i, j-1) are on diagonal k-1
+            }
+            d2[i] = v;
+        }
+        __syncthreads();
+        int *tmp = d0; d0 = d1; d1 = d2; d2 = tmp;
+    }
+    if (threadIdx.x == 0) {
+        const int dist = d1[n];
+        float r = (float)dist;
+        if (normalize) r = m > 0 ? (float)dist / (float)m : (n > 0 ? INFINITY : 0.f);
+        out[b] = r;
+    }
+}
+
 struct Plan { int CH, RS, GT, NCH, VP; size_t smem, ws_total; };
 
 static int make_plan(int T, int B, int V, int Lmax, Plan *pl)
@@ -534,6 +571,24 @@ extern "C" int ctcasr_greedy_decode(const float *logits, int T, int B, int V, in
     const int wpb = 4;
     ctc::greedy_decode_kernel<<<ceil_div(B, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(logits, T, B, V, blank, seq_len,
                                                                                        out_ids, out_len);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+extern "C" int ctcasr_edit_distance(const int32_t *hyp, int hyp_stride, const int32_t *hyp_len,
+                                    const int32_t *truth, int truth_stride, const int32_t *truth_len,
+                                    int B, int max_hyp_len, int normalize, float *out, void *stream)
+{
+    CTCASR_REQUIRE(hyp && hyp_len && truth && truth_len && out && B >= 1 && max_hyp_len >= 0, "edit_distance: bad args");
+    const size_t smem = (size_t)3 * (max_hyp_len + 2) * sizeof(int);
+    if (smem > 200 * 1024) return fail(CTCASR_ERR_UNSUPPORTED, "edit_distance: hypothesis too long (%d)", max_hyp_len);
+    static size_t smem_set = 0;
+    if (smem > smem_set && smem > 48 * 1024) {
+        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(ctc::edit_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    ctc::edit_distance_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(hyp, hyp_stride, hyp_len, truth, truth_stride, truth_len,
+                                                                    normalize, out);
     CTCASR_LAUNCH_CHECK();
     return CTCASR_OK;
 }

@@ -94,6 +94,16 @@ def greedy_decode(logits, seq_len, blank=None):
     return ids[:, :T], n
 
 
+def edit_distance(hyp, hyp_len, truth, truth_len, normalize=True):
+    lib = _lib.load()
+    _i32(hyp, "hyp"); _i32(hyp_len, "hyp_len"); _i32(truth, "truth"); _i32(truth_len, "truth_len")
+    B = hyp.shape[0]
+    out = torch.empty(B, dtype=torch.float32, device=hyp.device)
+    check(lib.ctcasr_edit_distance(ptr(hyp), hyp.stride(0), ptr(hyp_len), ptr(truth), truth.stride(0), ptr(truth_len),
+                                   B, hyp.shape[1], int(normalize), ptr(out), _stream()), "edit_distance")
+    return out
+
+
 def transpose01(x, out=None):
     lib = _lib.load()
     _f32(x, "x")

@@ -87,6 +87,13 @@ int ctcasr_ctc_loss_host(const float *logits, int T, int B, int V, int blank,
 int ctcasr_greedy_decode(const float *logits, int T, int B, int V, int blank,
                          const int32_t *seq_len, int32_t *out_ids, int32_t *out_len, void *stream);
 
+/* Levenshtein distance between label sequences — tf.edit_distance(decoded, labels) at
+ * asr/model.py:338 (normalize: divided by the truth length; empty truth -> 0 or +inf like TF).
+ *   hyp [B,hyp_stride], truth [B,truth_stride] int32 (only the first *_len[b] entries are read) */
+int ctcasr_edit_distance(const int32_t *hyp, int hyp_stride, const int32_t *hyp_len,
+                         const int32_t *truth, int truth_stride, const int32_t *truth_len,
+                         int B, int max_hyp_len, int normalize, float *out, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Dense layer.  Replaces tf.layers.dense + tf.minimum + tf.layers.dropout at
  * asr/util/tf_contrib.py:52-58 and asr/model.py:220-226,232.

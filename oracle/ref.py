@@ -160,3 +160,12 @@ def adam(p, m, v, g, step, lr=1e-5, b1=0.9, b2=0.999, eps=1e-8):
     assert all(a.flags.c_contiguous and a.dtype == dtype for a in (p, m, v, g))
     getattr(lib(), "oracle_adam" + suf)(_p(p), _p(m), _p(v), _p(g), ctypes.c_size_t(p.size), step,
                                         cr(lr), cr(b1), cr(b2), cr(eps))
+
+
+def edit_distance(hyp, hyp_len, truth, truth_len, normalize=True):
+    hyp, truth = _c(hyp, np.int32), _c(truth, np.int32)
+    B = hyp.shape[0]
+    out = np.zeros(B, np.float32)
+    lib().oracle_edit_distance(_p(hyp), hyp.shape[1], _p(_c(hyp_len, np.int32)), _p(truth), truth.shape[1],
+                               _p(_c(truth_len, np.int32)), B, int(normalize), _p(out))
+    return out

@@ -525,3 +525,20 @@ def test_cfg2_full_size_shards_add_up(cfg2_model):
     assert (n_full[:16] == n_half).all()
     for b in range(16):
         assert torch.equal(ids_full[b, :n_full[b]], ids_half[b, :n_half[b]])
+
+
+def test_edit_distance_bit_exact():
+    """tf.edit_distance(decoded, labels) (asr/model.py:338): integer work, bit-exact vs the oracle,
+    up to the corpus' longest label (422, README.md:169)."""
+    from ctc_asr_b200 import metrics
+    rng = np.random.default_rng(1)
+    B, Lh, Lt = 40, 430, 422
+    hl, tl = rng.integers(0, Lh + 1, B).astype(np.int32), rng.integers(0, Lt + 1, B).astype(np.int32)
+    hl[0], tl[0] = 0, 0
+    hl[1], tl[1] = 7, 0
+    hl[2], tl[2] = Lh, Lt
+    hyp, truth = rng.integers(1, 28, (B, Lh)).astype(np.int32), rng.integers(1, 28, (B, Lt)).astype(np.int32)
+    for norm in (False, True):
+        got = metrics.edit_distance(dev(hyp), dev(hl), dev(truth), dev(tl), normalize=norm).cpu().numpy()
+        want = ref.edit_distance(hyp, hl, truth, tl, normalize=norm)
+        assert np.array_equal(got, want)
