@@ -64,6 +64,9 @@ struct Params {
     __nv_bfloat16 *xbuf;     // fwd: hbuf [2 pieces][2 dirs][2 parity][32][H]; bwd: dzbuf [2][2][2][32][4H]
     unsigned int *counters;  // [2] step counters, [2] = error flag
     unsigned long long *trace;  // optional [grid][64 steps][8 slots] globaltimer stamps (tools/lstm_trace.py)
+    int kres;                // weight k-blocks [0, kres) of every CTA stay resident in tensor memory (<= 7)
+    const __nv_bfloat16 *wpack; // packed weights [2 pieces][rows][K] the resident share is read from
+    int wrows, wk;           // rows and K (row pitch) of wpack
     int stagger_ns;          // start delay of direction 1
     int nprod;               // timing experiments only: number of split products issued (3 = correct)
     int kb_keep;             // weight k-blocks [0, kb_keep) are loaded with L2 evict_last, the rest evict_first
@@ -139,11 +142,29 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapH); }
-    if (warp == 6) ptx::tmem_alloc(tmem_slot, 32);
+    const uint32_t tmem_cols = p.kres > 0 ? 512u : 32u;  // 32 accumulator columns (+ up to 448 of resident weights)
+    if (warp == 6) ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot_ptr;
+    const uint32_t tmem_w = tmem_d + 32;                  // resident weights: k-block kb, piece pc at column (kb*2+pc)*32
+    if (warp < 4 && p.kres > 0) {
+        // my gate row's weights for k in [0, 64*kres): 32 columns (= 64 bf16) per k-block and piece
+        const int row = (d * p.CPD + c) * 128 + warp * 32 + lane;
+        for (int kb = 0; kb < p.kres; ++kb)
+            for (int pc = 0; pc < 2; ++pc) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wpack + ((size_t)pc * p.wrows + row) * p.wk + (size_t)kb * BK);
+                uint32_t r[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __ldg(src + j);
+                ptx::tmem_st32(tmem_w + ((uint32_t)(warp * 32) << 16) + (uint32_t)((kb * 2 + pc) * 32), r);
+            }
+        ptx::tmem_st_wait();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
 
     if (warp == 4) {
         // ---- weight tiles: independent of the recurrence, runs ahead across step boundaries ----
@@ -154,10 +175,13 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             for (int i = 0; i < T; ++i)
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
-                    ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
-                    const uint64_t pol = kb < p.kb_keep ? keep : stream;
-                    ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage), pol);
-                    ptx::tma_load_3d_hint(a_addr(stage, 1), &mapW, kb * BK, row0, 1, fullA(stage), pol);
+                    if (kb < p.kres) {
+                        ptx::mbar_arrive(fullA(stage));     // resident in tensor memory: nothing to load, keep the phases in step
+                    } else {
+                        ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
+                        const uint64_t pol = kb < p.kb_keep ? keep : stream;
+                        ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage), pol);   // both pieces in one box
+                    }
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                     if (kb == KB - 1) stamp(p, i, 6);
                 }
@@ -175,8 +199,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
                     ptx::mbar_expect_tx(fullB(stage), 2 * F_B_PIECE);
-                    ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullB(stage));
-                    ptx::tma_load_3d(b_addr(stage, 1), &mapH, kb * BK, row0, 1, fullB(stage));
+                    ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullB(stage));   // both pieces in one box
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 stamp(p, i, 1);
@@ -198,11 +221,18 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         if (q >= p.nprod) break;
-                        const uint64_t ad = ptx::make_smem_desc(a_addr(stage, PA[q]), 16, 1024, 2);
                         const uint64_t bd = ptx::make_smem_desc(b_addr(stage, PB[q]), 16, 1024, 2);
+                        if (kb < p.kres) {          // A from tensor memory: 8 columns per 16-wide k-step
+                            const uint32_t ta = tmem_w + (uint32_t)((kb * 2 + PA[q]) * 32);
 #pragma unroll
-                        for (int j = 0; j < BK / 16; ++j)
-                            ptx::mma_bf16(tmem_d, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (kb | q | j) != 0);
+                            for (int j = 0; j < BK / 16; ++j)
+                                ptx::mma_bf16_ts(tmem_d, ta + 8 * j, bd + (uint64_t)(2 * j), idesc, (kb | q | j) != 0);
+                        } else {
+                            const uint64_t ad = ptx::make_smem_desc(a_addr(stage, PA[q]), 16, 1024, 2);
+#pragma unroll
+                            for (int j = 0; j < BK / 16; ++j)
+                                ptx::mma_bf16(tmem_d, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (kb | q | j) != 0);
+                        }
                     }
                     ptx::mma_commit(empty(stage));
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
@@ -288,7 +318,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
     __syncwarp();
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 6) ptx::tmem_dealloc(tmem_d, 32);
+    if (warp == 6) ptx::tmem_dealloc(tmem_d, tmem_cols);
 }
 
 // ================================================ backward ========================================
@@ -532,8 +562,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                     ptx::mbar_wait(empty(stage), phase ^ 1);
                     ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
                     const uint64_t pol = kb < p.kb_keep ? keep : stream;
-                    ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, q * H + kb * BK, row0, 0, fullA(stage), pol);
-                    ptx::tma_load_3d_hint(a_addr(stage, 1), &mapW, q * H + kb * BK, row0, 1, fullA(stage), pol);
+                    ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, q * H + kb * BK, row0, 0, fullA(stage), pol);   // both pieces
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
         }
@@ -548,8 +577,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
                     ptx::mbar_expect_tx(fullB(stage), 2 * F_B_PIECE);
-                    ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * H + kb * BK, row0, 0, fullB(stage));
-                    ptx::tma_load_3d(b_addr(stage, 1), &mapZ, q * H + kb * BK, row0, 1, fullB(stage));
+                    ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * H + kb * BK, row0, 0, fullB(stage));   // both pieces
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
@@ -725,13 +753,13 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 // bf16 [pieces][rows][inner], box [1][box_rows][64], SWIZZLE_128B
-static int make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t rows, uint32_t box_rows)
+static int make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t rows, uint32_t box_rows, uint32_t box_pieces = 2)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(CTCASR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {inner, rows, 2};
     cuuint64_t strides[2] = {inner * 2, rows * inner * 2};
-    cuuint32_t box[3] = {BK, box_rows, 1};
+    cuuint32_t box[3] = {BK, box_rows, box_pieces};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -827,6 +855,14 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
         p.gates = gates + (size_t)b0 * 8 * H; p.cstate = cstate + (size_t)b0 * 2 * H; p.y = y + (size_t)b0 * 2 * H;
         p.dy = nullptr; p.xbuf = hbuf; p.counters = ctr;
         p.kb_keep = keep_kblocks(H);
+        {
+            const char *e = getenv("CTCASR_LSTM_KRES");
+            int kres = e ? atoi(e) : 0;
+            if (kres > 7) kres = 7;
+            if (kres > H / BK) kres = H / BK;
+            p.kres = kres < 0 ? 0 : kres;
+        }
+        p.wpack = wp; p.wrows = 2 * 4 * H; p.wk = H;
         p.trace = g_trace;
         p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
         p.nprod = getenv("CTCASR_LSTM_NPROD") ? atoi(getenv("CTCASR_LSTM_NPROD")) : 3;
@@ -856,8 +892,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     split2_kernel<<<148 * 8, 256, 0, stream>>>(wh, wq, nw);
     CTCASR_LAUNCH_CHECK();
     CUtensorMap mapW, mapZ;
-    int rc = make_map(&mapZ, zbuf, (uint64_t)4 * H, (uint64_t)2 * 2 * NB, NB);
-    if (rc) return rc;
+    int rc = CTCASR_OK;
 
     // preferred: 4-CTA cluster split-K kernel (needs H % 128 == 0 and all clusters co-resident)
     static int cluster_ok_grid = 0, cluster_bad_grid = 0, checked_grid = 0;
@@ -879,11 +914,13 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
         }
         use_cluster = cluster_ok_grid == grid;
     }
+    rc = make_map(&mapZ, zbuf, (uint64_t)4 * H, (uint64_t)2 * 2 * NB, NB, use_cluster ? 2 : 1);
+    if (rc) return rc;
     if (use_cluster) {
         rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, 128);
     } else {
         if (checked_grid != grid) { rc = check_coop((const void *)lstm_bwd_kernel, B_SMEM, grid); if (rc) return rc; checked_grid = grid; }
-        rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC);
+        rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC, 1);
     }
     if (rc) return rc;
     for (int b0 = 0; b0 < B; b0 += NB) {
@@ -895,6 +932,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
         p.gates = gates + (size_t)b0 * 8 * H; p.cstate = const_cast<float *>(cstate) + (size_t)b0 * 2 * H; p.y = nullptr;
         p.dy = dy + (size_t)b0 * 2 * H; p.xbuf = zbuf; p.counters = ctr;
         p.kb_keep = keep_kblocks(H);
+        p.kres = 0; p.wpack = wq; p.wrows = 2 * H; p.wk = 4 * H;
         p.trace = nullptr;
         p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
         p.nprod = 3;
