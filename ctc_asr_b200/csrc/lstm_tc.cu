@@ -68,6 +68,7 @@ struct Params {
     const __nv_bfloat16 *wpack; // packed weights [2 pieces][rows][K] the resident share is read from
     int wrows, wk;           // rows and K (row pitch) of wpack
     int stagger_ns;          // start delay of direction 1
+    int skip;                // timing experiments only: 1 = do not load weight tiles, 2 = do not load state tiles
     int nprod;               // timing experiments only: number of split products issued (3 = correct)
     int kb_keep;             // weight k-blocks [0, kb_keep) are loaded with L2 evict_last, the rest evict_first
 };
@@ -137,18 +138,18 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
     const int T = p.T, B = p.B, H = p.H, KB = H / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 1); ptx::mbar_init(fullB(s), 1); ptx::mbar_init(empty(s), 1); }
+        for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
         ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 4);
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapH); }
-    const uint32_t tmem_cols = p.kres > 0 ? 512u : 32u;  // 32 accumulator columns (+ up to 448 of resident weights)
+    const uint32_t tmem_cols = p.kres > 0 ? 512u : 64u;  // 64 accumulator columns (+ up to 448 of resident weights)
     if (warp == 6) ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot_ptr;
-    const uint32_t tmem_w = tmem_d + 32;                  // resident weights: k-block kb, piece pc at column (kb*2+pc)*32
+    const uint32_t tmem_w = tmem_d + 64;                  // resident weights: k-block kb, piece pc at column (kb*2+pc)*32
     if (warp < 4 && p.kres > 0) {
         // my gate row's weights for k in [0, 64*kres): 32 columns (= 64 bf16) per k-block and piece
         const int row = (d * p.CPD + c) * 128 + warp * 32 + lane;
@@ -175,7 +176,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             for (int i = 0; i < T; ++i)
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
-                    if (kb < p.kres) {
+                    if (kb < p.kres || (p.skip & 1)) {
                         ptx::mbar_arrive(fullA(stage));     // resident in tensor memory: nothing to load, keep the phases in step
                     } else {
                         ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
@@ -198,8 +199,9 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                 const int row0 = (d * 2 + (i & 1)) * NB;
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
-                    ptx::mbar_expect_tx(fullB(stage), 2 * F_B_PIECE);
-                    ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullB(stage));   // both pieces in one box
+                    if (p.skip & 2) { ptx::mbar_arrive(fullA(stage)); if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; } continue; }
+                    ptx::mbar_expect_tx(fullA(stage), 2 * F_B_PIECE);
+                    ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullA(stage));   // both pieces in one box
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 stamp(p, i, 1);
@@ -208,30 +210,34 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
     } else if (warp == 6) {
         // ---- MMA issuer -------------------------------------------------------------------------
         if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
-            constexpr int PA[3] = {0, 0, 1}, PB[3] = {0, 1, 0};
+            const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
             int stage = 0; uint32_t phase = 0, tphase = 0;
             for (int i = 0; i < T; ++i) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(fullA(stage), phase);
-                    ptx::mbar_wait(fullB(stage), phase);
                     ptx::tc_fence_after();
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        if (q >= p.nprod) break;
-                        const uint64_t bd = ptx::make_smem_desc(b_addr(stage, PB[q]), 16, 1024, 2);
+                    // bf16x3 with 2 MMAs per k-step: the two pieces of h are consecutive rows of one K-major tile,
+                    // so  A_hi x [B_hi; B_lo]  is ONE N = 64 MMA (columns 0-31: hi*hi, 32-63: hi*lo) and
+                    // A_lo x B_hi  accumulates into columns 0-31; the epilogue adds the two column groups.
+                    const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
+                    if (p.nprod > 0) {
                         if (kb < p.kres) {          // A from tensor memory: 8 columns per 16-wide k-step
-                            const uint32_t ta = tmem_w + (uint32_t)((kb * 2 + PA[q]) * 32);
+                            const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
 #pragma unroll
-                            for (int j = 0; j < BK / 16; ++j)
-                                ptx::mma_bf16_ts(tmem_d, ta + 8 * j, bd + (uint64_t)(2 * j), idesc, (kb | q | j) != 0);
+                            for (int j = 0; j < BK / 16; ++j) {
+                                ptx::mma_bf16_ts(tmem_d, ta_hi + 8 * j, bd + (uint64_t)(2 * j), idesc64, (kb | j) != 0);
+                                ptx::mma_bf16_ts(tmem_d, ta_lo + 8 * j, bd + (uint64_t)(2 * j), idesc32, 1);
+                            }
                         } else {
-                            const uint64_t ad = ptx::make_smem_desc(a_addr(stage, PA[q]), 16, 1024, 2);
+                            const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+                            const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
 #pragma unroll
-                            for (int j = 0; j < BK / 16; ++j)
-                                ptx::mma_bf16(tmem_d, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (kb | q | j) != 0);
+                            for (int j = 0; j < BK / 16; ++j) {
+                                ptx::mma_bf16(tmem_d, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, (kb | j) != 0);
+                                ptx::mma_bf16(tmem_d, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
+                            }
                         }
                     }
                     ptx::mma_commit(empty(stage));
@@ -265,15 +271,16 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             ptx::mbar_wait(tfull, tphase);
             if (tid == 0) stamp(p, i, 3);
             ptx::tc_fence_after();
-            uint32_t r[32];
-            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);
+            uint32_t r[32], r2[32];
+            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);          // hi*hi + lo*hi
+            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, r2);    // hi*lo
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty);
             tphase ^= 1;
 #pragma unroll
-            for (int b = 0; b < NB; ++b) zs[(g * NB + b) * UPC + ul] = __uint_as_float(r[b]) + pz[b];
+            for (int b = 0; b < NB; ++b) zs[(g * NB + b) * UPC + ul] = (__uint_as_float(r[b]) + __uint_as_float(r2[b])) + pz[b];
             epi_bar();
             __nv_bfloat16 *hb = p.xbuf + ((size_t)(d * 2 + ((i + 1) & 1)) * NB) * H + ucol + cu;
             const size_t piece = (size_t)2 * 2 * NB * H;
@@ -540,12 +547,12 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
     const int T = p.T, B = p.B, H = p.H, KB = H / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 1); ptx::mbar_init(fullB(s), 1); ptx::mbar_init(empty(s), 1); }
+        for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
         ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapZ); }
-    if (warp == 6) ptx::tmem_alloc(tmem_slot, 32);
+    if (warp == 6) ptx::tmem_alloc(tmem_slot, 64);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();            // every CTA's barriers exist before anyone arrives remotely
@@ -576,31 +583,31 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                 const int row0 = (d * 2 + (n & 1)) * NB;
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(empty(stage), phase ^ 1);
-                    ptx::mbar_expect_tx(fullB(stage), 2 * F_B_PIECE);
-                    ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * H + kb * BK, row0, 0, fullB(stage));   // both pieces
+                    ptx::mbar_expect_tx(fullA(stage), 2 * F_B_PIECE);
+                    ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * H + kb * BK, row0, 0, fullA(stage));   // both pieces
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 6) {
         if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
-            constexpr int PA[3] = {0, 0, 1}, PB[3] = {0, 1, 0};
+            const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
             int stage = 0; uint32_t phase = 0, tphase = 0;
             for (int n = 0; n < T; ++n) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(fullA(stage), phase);
-                    ptx::mbar_wait(fullB(stage), phase);
                     ptx::tc_fence_after();
+                    {   // 2 MMAs per k-step, see the forward kernel
+                        const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
+                        const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+                        const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
 #pragma unroll
-                    for (int pr = 0; pr < 3; ++pr) {
-                        const uint64_t ad = ptx::make_smem_desc(a_addr(stage, PA[pr]), 16, 1024, 2);
-                        const uint64_t bd = ptx::make_smem_desc(b_addr(stage, PB[pr]), 16, 1024, 2);
-#pragma unroll
-                        for (int j = 0; j < BK / 16; ++j)
-                            ptx::mma_bf16(tmem_d, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (kb | pr | j) != 0);
+                        for (int j = 0; j < BK / 16; ++j) {
+                            ptx::mma_bf16(tmem_d, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, (kb | j) != 0);
+                            ptx::mma_bf16(tmem_d, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
+                        }
                     }
                     ptx::mma_commit(empty(stage));
                     if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
@@ -643,12 +650,14 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
             }
             ptx::mbar_wait(tfull, tphase);
             ptx::tc_fence_after();
-            uint32_t r[32];
+            uint32_t r[32], r2[32];
             ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);      // rows = units 32*warp + lane of the block
+            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, r2);
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
 #pragma unroll
-            for (int b = 0; b < NB; ++b) ptx::st_cluster_f32(remote_slot + (uint32_t)(b * UPC + lane) * 4u, __uint_as_float(r[b]));
+            for (int b = 0; b < NB; ++b)
+                ptx::st_cluster_f32(remote_slot + (uint32_t)(b * UPC + lane) * 4u, __uint_as_float(r[b]) + __uint_as_float(r2[b]));
             __syncwarp();
             if (lane == 0) { ptx::mbar_arrive(tempty); ptx::mbar_arrive_remote(remote_bar); }
             ptx::mbar_wait_cluster(xfull, tphase);                          // the four partials of my units have landed
@@ -701,7 +710,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();            // no CTA exits while a peer may still write into its shared memory
-    if (warp == 6) ptx::tmem_dealloc(tmem_d, 32);
+    if (warp == 6) ptx::tmem_dealloc(tmem_d, 64);
 }
 
 // ---- weight pre-packs --------------------------------------------------------------------------------
@@ -866,6 +875,7 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
         p.trace = g_trace;
         p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
         p.nprod = getenv("CTCASR_LSTM_NPROD") ? atoi(getenv("CTCASR_LSTM_NPROD")) : 3;
+        p.skip = getenv("CTCASR_LSTM_SKIP") ? atoi(getenv("CTCASR_LSTM_SKIP")) : 0;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = F_SMEM; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -935,7 +945,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
         p.kres = 0; p.wpack = wq; p.wrows = 2 * H; p.wk = 4 * H;
         p.trace = nullptr;
         p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
-        p.nprod = 3;
+        p.nprod = 3; p.skip = 0;
         ProfScope prof(PROF_LSTM_BWD, stream);
         if (use_cluster) {
             CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel, mapW, mapZ, p));
