@@ -35,7 +35,7 @@ namespace lstm {
 constexpr int UPC = 32;                 // hidden units per CTA
 constexpr int NB = 32;                  // batch rows per MMA (N forward, real M rows backward)
 constexpr int BK = 64;                  // bf16 k-elements per stage row (128 B, SWIZZLE_128B)
-constexpr int NTHREADS = 224;           // 7 warps
+constexpr int NTHREADS = 256;           // 8 warps: 0-3 cell math, 4 weight tiles, 5 state tiles, 6-7 MMA issuers
 constexpr int EPI_THREADS = 128;
 
 // ---- forward smem ring: per stage A = 2 pieces x [128 x 64] bf16 (16 KB each), B = 2 x [32 x 64] (4 KB each)
@@ -64,7 +64,7 @@ struct Params {
     __nv_bfloat16 *xbuf;     // fwd: hbuf [2 pieces][2 dirs][2 parity][32][H]; bwd: dzbuf [2][2][2][32][4H]
     unsigned int *counters;  // [2] step counters, [2] = error flag
     unsigned long long *trace;  // optional [grid][64 steps][8 slots] globaltimer stamps (tools/lstm_trace.py)
-    int kres;                // weight k-blocks [0, kres) of every CTA stay resident in tensor memory (<= 7)
+    int kres;                // weight k-blocks [0, kres) of every CTA stay resident in tensor memory (<= 6)
     const __nv_bfloat16 *wpack; // packed weights [2 pieces][rows][K] the resident share is read from
     int wrows, wk;           // rows and K (row pitch) of wpack
     int stagger_ns;          // start delay of direction 1
@@ -139,17 +139,17 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
-        ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 4);
+        ptx::mbar_init(tfull, 2); ptx::mbar_init(tempty, 4);
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapH); }
-    const uint32_t tmem_cols = p.kres > 0 ? 512u : 64u;  // 64 accumulator columns (+ up to 448 of resident weights)
+    const uint32_t tmem_cols = p.kres > 0 ? 512u : 128u; // 2 x 64 accumulator columns (+ up to 384 of resident weights)
     if (warp == 6) ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot_ptr;
-    const uint32_t tmem_w = tmem_d + 64;                  // resident weights: k-block kb, piece pc at column (kb*2+pc)*32
+    const uint32_t tmem_w = tmem_d + 128;                 // resident weights: k-block kb, piece pc at column (kb*2+pc)*32
     if (warp < 4 && p.kres > 0) {
         // my gate row's weights for k in [0, 64*kres): 32 columns (= 64 bf16) per k-block and piece
         const int row = (d * p.CPD + c) * 128 + warp * 32 + lane;
@@ -207,48 +207,55 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                 stamp(p, i, 1);
             }
         }
-    } else if (warp == 6) {
-        // ---- MMA issuer -------------------------------------------------------------------------
+    } else if (warp == 6 || warp == 7) {
+        // ---- two MMA issuers: even / odd k-blocks into separate accumulators.  The per-k-block cost
+        // of one issuing thread (barrier wait + descriptor set-up + 8 small MMAs + commit) is what paces
+        // the streaming phase, so it is split over two threads; the epilogue adds the accumulators.
         if (lane == 0) {
+            const int me = warp - 6;
             const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
-            int stage = 0; uint32_t phase = 0, tphase = 0;
+            const uint32_t acc = tmem_d + (uint32_t)(me * 2 * NB);
+            uint32_t tphase = 0;
             for (int i = 0; i < T; ++i) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb = me; kb < KB; kb += 2) {
+                    const int gk = i * KB + kb;
+                    const int stage = gk % F_NSTAGE;
+                    const uint32_t phase = (uint32_t)(gk / F_NSTAGE) & 1u;
+                    const int first = kb == me;
                     ptx::mbar_wait(fullA(stage), phase);
                     ptx::tc_fence_after();
                     // bf16x3 with 2 MMAs per k-step: the two pieces of h are consecutive rows of one K-major tile,
                     // so  A_hi x [B_hi; B_lo]  is ONE N = 64 MMA (columns 0-31: hi*hi, 32-63: hi*lo) and
-                    // A_lo x B_hi  accumulates into columns 0-31; the epilogue adds the two column groups.
+                    // A_lo x B_hi  accumulates into columns 0-31; the epilogue adds the column groups.
                     const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
                     if (p.nprod > 0) {
                         if (kb < p.kres) {          // A from tensor memory: 8 columns per 16-wide k-step
                             const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
 #pragma unroll
                             for (int j = 0; j < BK / 16; ++j) {
-                                ptx::mma_bf16_ts(tmem_d, ta_hi + 8 * j, bd + (uint64_t)(2 * j), idesc64, (kb | j) != 0);
-                                ptx::mma_bf16_ts(tmem_d, ta_lo + 8 * j, bd + (uint64_t)(2 * j), idesc32, 1);
+                                ptx::mma_bf16_ts(acc, ta_hi + 8 * j, bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                                ptx::mma_bf16_ts(acc, ta_lo + 8 * j, bd + (uint64_t)(2 * j), idesc32, 1);
                             }
                         } else {
                             const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
                             const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
 #pragma unroll
                             for (int j = 0; j < BK / 16; ++j) {
-                                ptx::mma_bf16(tmem_d, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, (kb | j) != 0);
-                                ptx::mma_bf16(tmem_d, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
+                                ptx::mma_bf16(acc, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                                ptx::mma_bf16(acc, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
                             }
                         }
                     }
                     ptx::mma_commit(empty(stage));
-                    if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 ptx::mma_commit(tfull);
-                stamp(p, i, 2);
+                if (me == 0) stamp(p, i, 2);
                 tphase ^= 1;
             }
         }
-    } else {
+    } else if (warp < 4) {
         // ---- cell math: warp = gate for the TMEM read, then thread = (unit, 8 batch rows) -------
         const int g = warp, ul = lane;
         const int tid = threadIdx.x, cu = tid & 31, bg = tid >> 5;         // cell ownership
@@ -272,9 +279,20 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             if (tid == 0) stamp(p, i, 3);
             ptx::tc_fence_after();
             uint32_t r[32], r2[32];
-            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);          // hi*hi + lo*hi
-            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, r2);    // hi*lo
+            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);          // issuer 0: hi*hi + lo*hi
+            ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, r2);    //           hi*lo
             ptx::tmem_ld_wait();
+            if (KB > 1) {                                                       // issuer 1 (odd k-blocks)
+                uint32_t r3[32], r4[32];
+                ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 64, r3);
+                ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 96, r4);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    r[b] = __float_as_uint(__uint_as_float(r[b]) + __uint_as_float(r3[b]));
+                    r2[b] = __float_as_uint(__uint_as_float(r2[b]) + __uint_as_float(r4[b]));
+                }
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty);
@@ -422,7 +440,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                 tphase ^= 1;
             }
         }
-    } else {
+    } else if (warp < 4) {
         const int tid = threadIdx.x, cu = tid & 31, bg = tid >> 5;
         const int ucol = c * UPC;
         float dcreg[8];
@@ -548,11 +566,11 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
-        ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
+        ptx::mbar_init(tfull, 2); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapZ); }
-    if (warp == 6) ptx::tmem_alloc(tmem_slot, 64);
+    if (warp == 6) ptx::tmem_alloc(tmem_slot, 128);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();            // every CTA's barriers exist before anyone arrives remotely
@@ -589,34 +607,37 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                 }
             }
         }
-    } else if (warp == 6) {
-        if (lane == 0) {
+    } else if (warp == 6 || warp == 7) {
+        if (lane == 0) {        // two MMA issuers (even / odd k-blocks, separate accumulators), see the forward kernel
+            const int me = warp - 6;
             const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
-            int stage = 0; uint32_t phase = 0, tphase = 0;
+            const uint32_t acc = tmem_d + (uint32_t)(me * 2 * NB);
+            uint32_t tphase = 0;
             for (int n = 0; n < T; ++n) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb = me; kb < KB; kb += 2) {
+                    const int gk = n * KB + kb;
+                    const int stage = gk % F_NSTAGE;
+                    const uint32_t phase = (uint32_t)(gk / F_NSTAGE) & 1u;
+                    const int first = kb == me;
                     ptx::mbar_wait(fullA(stage), phase);
                     ptx::tc_fence_after();
-                    {   // 2 MMAs per k-step, see the forward kernel
-                        const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
-                        const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
-                        const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
+                    const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
+                    const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+                    const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
 #pragma unroll
-                        for (int j = 0; j < BK / 16; ++j) {
-                            ptx::mma_bf16(tmem_d, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, (kb | j) != 0);
-                            ptx::mma_bf16(tmem_d, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
-                        }
+                    for (int j = 0; j < BK / 16; ++j) {
+                        ptx::mma_bf16(acc, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                        ptx::mma_bf16(acc, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
                     }
                     ptx::mma_commit(empty(stage));
-                    if (++stage == F_NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 ptx::mma_commit(tfull);
                 tphase ^= 1;
             }
         }
-    } else {
+    } else if (warp < 4) {
         const int tid = threadIdx.x, cu = tid & 31, bg = tid >> 5;
         const int ucol = ub * 128 + q * UPC;                        // the 32 units whose cells this CTA owns
         float dcreg[8];
@@ -654,6 +675,17 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
             ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);      // rows = units 32*warp + lane of the block
             ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, r2);
             ptx::tmem_ld_wait();
+            if (KB > 1) {
+                uint32_t r3[32], r4[32];
+                ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 64, r3);
+                ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 96, r4);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    r[b] = __float_as_uint(__uint_as_float(r[b]) + __uint_as_float(r3[b]));
+                    r2[b] = __float_as_uint(__uint_as_float(r2[b]) + __uint_as_float(r4[b]));
+                }
+            }
             ptx::tc_fence_before();
 #pragma unroll
             for (int b = 0; b < NB; ++b)
@@ -710,7 +742,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();            // no CTA exits while a peer may still write into its shared memory
-    if (warp == 6) ptx::tmem_dealloc(tmem_d, 64);
+    if (warp == 6) ptx::tmem_dealloc(tmem_d, 128);
 }
 
 // ---- weight pre-packs --------------------------------------------------------------------------------
@@ -867,7 +899,7 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
         {
             const char *e = getenv("CTCASR_LSTM_KRES");
             int kres = e ? atoi(e) : 0;
-            if (kres > 7) kres = 7;
+            if (kres > 6) kres = 6;
             if (kres > H / BK) kres = H / BK;
             p.kres = kres < 0 ? 0 : kres;
         }
