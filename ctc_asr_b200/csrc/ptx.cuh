@@ -49,7 +49,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+#ifdef CTCASR_DEBUG_WAIT
+        if (++spins > (1u << 19)) { printf("ctcasr: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity); __trap(); }
+#else
         if (++spins > (1u << 24)) { printf("ctcasr: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+#endif
     }
 }
 
@@ -83,7 +87,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
             "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#ifdef CTCASR_DEBUG_WAIT
+        if (!ok && ++spins > (1u << 19)) { printf("ctcasr: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity); __trap(); }
+#else
         if (!ok && ++spins > (1u << 24)) { printf("ctcasr: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+#endif
     }
 }
 __device__ __forceinline__ void cluster_sync_all()

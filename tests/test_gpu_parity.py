@@ -502,6 +502,7 @@ def test_cfg2_full_size_gradient_is_the_derivative_of_the_loss(cfg2_model):
     lm, _, _ = _loss_and_grad(model, batch)
     model.flat.copy_(p0)
     fd = (lp - lm) / (2 * eps)
+    print("cfg2 directional derivative: finite difference %.4f, analytic %.4f, loss %.4f" % (fd, analytic, loss0))
     assert abs(fd - analytic) / abs(analytic) < 2e-2, (fd, analytic)
 
 
@@ -517,6 +518,7 @@ def test_cfg2_full_size_shards_add_up(cfg2_model):
     lb, gb, _ = _loss_and_grad(model, batch, slice(16, 32), global_batch=32)
     assert abs((la + lb) - loss) / abs(loss) < 1e-5
     err = (ga + gb - grad).abs().max().item() / grad.abs().max().item()
+    print("cfg2 shard sum: loss err %.2e, grad err %.2e" % (abs((la + lb) - loss) / abs(loss), err))
     assert err < 1e-3, err
     assert torch.allclose(pa, per_utt[:16], rtol=1e-5)
     # same utterance, different batch composition: identical greedy transcript (integer work)
