@@ -205,7 +205,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                         ptx::mbar_arrive(fullA(stage));     // resident in tensor memory: nothing to load, keep the phases in step
                     } else {
                         ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
-                        const uint64_t pol = kb < p.kb_keep ? keep : stream;
+                        const uint64_t pol = kb - p.kres < p.kb_keep ? keep : stream;
                         ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage), pol);   // both pieces in one box
                     }
                     r.advance();
@@ -607,12 +607,29 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapZ); }
-    if (warp == 6) ptx::tmem_alloc(tmem_slot, 128);
+    const uint32_t tmem_cols = p.kres > 0 ? 512u : 128u;
+    if (warp == 6) ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();            // every CTA's barriers exist before anyone arrives remotely
     ptx::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot_ptr;
+    const uint32_t tmem_w = tmem_d + 128;                 // resident weights, as in the forward kernel
+    if (warp < 4 && p.kres > 0) {
+        const int row = d * H + ub * 128 + warp * 32 + lane;
+        for (int kb = 0; kb < p.kres; ++kb)
+            for (int pc = 0; pc < 2; ++pc) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wpack + ((size_t)pc * p.wrows + row) * p.wk + (size_t)q * H + (size_t)kb * BK);
+                uint32_t r[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __ldg(src + j);
+                ptx::tmem_st32(tmem_w + ((uint32_t)(warp * 32) << 16) + (uint32_t)((kb * 2 + pc) * 32), r);
+            }
+        ptx::tmem_st_wait();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
 
     if (warp == 4) {
         if (lane == 0) {        // Wh[d][128 units of the cluster][columns of gate q], K-major as stored
@@ -624,9 +641,13 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                     SubRing &r = ring[kb & 1];
                     const int stage = r.slot();
                     ptx::mbar_wait(empty(stage), r.phase ^ 1);
-                    ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
-                    const uint64_t pol = kb < p.kb_keep ? keep : stream;
-                    ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, q * H + kb * BK, row0, 0, fullA(stage), pol);   // both pieces
+                    if (kb < p.kres) {
+                        ptx::mbar_arrive(fullA(stage));     // resident in tensor memory
+                    } else {
+                        ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
+                        const uint64_t pol = kb - p.kres < p.kb_keep ? keep : stream;
+                        ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, q * H + kb * BK, row0, 0, fullA(stage), pol);   // both pieces
+                    }
                     r.advance();
                 }
         }
@@ -664,12 +685,21 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                     ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
                     const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
-                    const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
-                    const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
+                    if (kb < p.kres) {
+                        const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
 #pragma unroll
-                    for (int j = 0; j < BK / 16; ++j) {
-                        ptx::mma_bf16(acc, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
-                        ptx::mma_bf16(acc, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
+                        for (int j = 0; j < BK / 16; ++j) {
+                            ptx::mma_bf16_ts(acc, ta_hi + 8 * j, bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                            ptx::mma_bf16_ts(acc, ta_lo + 8 * j, bd + (uint64_t)(2 * j), idesc32, 1);
+                        }
+                    } else {
+                        const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+                        const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
+#pragma unroll
+                        for (int j = 0; j < BK / 16; ++j) {
+                            ptx::mma_bf16(acc, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                            ptx::mma_bf16(acc, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
+                        }
                     }
                     ptx::mma_commit(empty(stage));
                     ring.advance();
@@ -786,7 +816,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();            // no CTA exits while a peer may still write into its shared memory
-    if (warp == 6) ptx::tmem_dealloc(tmem_d, 128);
+    if (warp == 6) ptx::tmem_dealloc(tmem_d, tmem_cols);
 }
 
 // ---- weight pre-packs --------------------------------------------------------------------------------
@@ -874,11 +904,22 @@ static WsLayout ws_layout(int H)
 static int keep_kblocks(int H)
 {
     const char *e = getenv("CTCASR_LSTM_L2_KEEP_MB");
-    const double budget_mb = e ? atof(e) : 32.0;
-    const double total_mb = 16.0 * H * H / 1048576.0;
+    const double budget_mb = e ? atof(e) : 64.0;
+    const double total_mb = 32.0 * H * H / 1048576.0;       // both directions, two bf16 pieces per weight
     const int KB = H / BK;
     int k = (int)(KB * budget_mb / total_mb);
     return k < 0 ? 0 : (k > KB ? KB : k);
+}
+
+// Tensor-memory-resident weight share: 384 of the 512 columns next to the accumulators hold the first 6
+// k-blocks (192 KB) of every CTA's weight slice for the whole sequence, read by the MMA as a TMEM A operand.
+static int resident_kblocks(int H)
+{
+    const char *e = getenv("CTCASR_LSTM_KRES");
+    int kres = e ? atoi(e) : 6;
+    if (kres > 6) kres = 6;
+    if (kres > H / BK) kres = H / BK;
+    return kres < 0 ? 0 : kres;
 }
 
 static int check_coop(const void *kernel, int smem, int grid)
@@ -940,16 +981,7 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
         p.gates = gates + (size_t)b0 * 8 * H; p.cstate = cstate + (size_t)b0 * 2 * H; p.y = y + (size_t)b0 * 2 * H;
         p.dy = nullptr; p.xbuf = hbuf; p.counters = ctr;
         p.kb_keep = keep_kblocks(H);
-        {
-            // tensor-memory-resident weight share: correct for kres <= 2, hangs for larger values since the
-            // second MMA issuer was added (not yet understood); it did not change the step time, so it is off
-            const char *e = getenv("CTCASR_LSTM_KRES");
-            int kres = e ? atoi(e) : 0;
-            if (kres > 2) kres = 2;
-            if (kres > 6) kres = 6;
-            if (kres > H / BK) kres = H / BK;
-            p.kres = kres < 0 ? 0 : kres;
-        }
+        p.kres = resident_kblocks(H);
         p.wpack = wp; p.wrows = 2 * 4 * H; p.wk = H;
         p.trace = g_trace;
         p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
@@ -1021,7 +1053,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
         p.gates = gates + (size_t)b0 * 8 * H; p.cstate = const_cast<float *>(cstate) + (size_t)b0 * 2 * H; p.y = nullptr;
         p.dy = dy + (size_t)b0 * 2 * H; p.xbuf = zbuf; p.counters = ctr;
         p.kb_keep = keep_kblocks(H);
-        p.kres = 0; p.wpack = wq; p.wrows = 2 * H; p.wk = 4 * H;
+        p.kres = use_cluster ? resident_kblocks(H) : 0; p.wpack = wq; p.wrows = 2 * H; p.wk = 4 * H;
         p.trace = nullptr;
         p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
         p.nprod = 3; p.skip = 0;

@@ -1,1 +1,8 @@
-for cfg in "0 32 11000" "6 32 9000" "6 48 9000" "6 56 9000" "0 32 9000" "0 32 7000"; do set -- $cfg; echo "KRES=$1 KEEP=$2 STAGGER=$3"; CTCASR_LSTM_KRES=$1 CTCASR_LSTM_L2_KEEP_MB=$2 CTCASR_LSTM_STAGGER_NS=$3 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum --clock-control none -k regex:lstm_ -s 2 -c 2 python tools/profile_target.py lstm 300 2>&1 | grep -E "gpu__time|dram__bytes" | awk '{printf "%s ", $NF}'; echo; done
+#!/bin/bash
+# sweep of the persistent-LSTM tuning knobs (tensor-memory-resident k-blocks, L2 keep share, direction stagger);
+# every configuration is also checked for bit-exact reproducibility by tools/lstm_check.py
+for cfg in "$@"; do
+  set -- $(echo $cfg | tr ',' ' ')
+  echo -n "KRES=$1 KEEP_MB=$2 STAGGER_NS=$3: "
+  CTCASR_LSTM_KRES=$1 CTCASR_LSTM_L2_KEEP_MB=$2 CTCASR_LSTM_STAGGER_NS=$3 timeout 200 python tools/lstm_check.py ${T:-600} ${R:-4} 2>&1 | tail -1 | cut -c1-200
+done
