@@ -21,6 +21,20 @@ int gemm_simt(const GemmArgs &g, cudaStream_t stream);
 int gemm_tc(const GemmArgs &g, int compute, cudaStream_t stream);
 bool gemm_tc_eligible(const GemmArgs &g);
 int gemm_scratch_check(int compute, int nz, int M, int N, int K);
+// Split scope: between begin and end the bf16 pieces of an operand are computed ONCE and shared by every
+// GEMM that reads the same fp32 matrix or a sub-view of it (birnn_bwd reads dz in three GEMMs).  The caller
+// guarantees that the fp32 operands are not written while the scope is open.  `elems[i]` = rows * padded
+// columns of the distinct operands that will be split; begin() fails (before anything is launched) when
+// their pieces do not fit in the scratch arena together.
+int split_scope_begin(int compute, const size_t *elems, int n);
+void split_scope_end();
+struct SplitScope {
+    bool open = false;
+    ~SplitScope() { if (open) split_scope_end(); }
+};
+// Free space of the caller's scratch arena behind the cached splits (not reserved: valid until the next
+// GEMM call on the stream), or nullptr when `bytes` do not fit.
+void *scratch_free(size_t bytes);
 // dispatch on `compute`: TF32 -> tcgen05 when eligible, otherwise the SIMT kernel
 int gemm(const GemmArgs &g, int compute, cudaStream_t stream);
 

@@ -332,6 +332,54 @@ static int encode_map(CUtensorMap *map, const void *base, bool bf16, uint64_t in
 static char *g_scratch = nullptr;
 static size_t g_scratch_bytes = 0, g_scratch_needed = 0;
 
+// ---- split cache (see split_scope_begin in gemm.cuh) -----------------------------------------------------
+struct SplitEntry {
+    const float *base; int rows, cols, ld, np;      // the fp32 matrix that was split
+    __nv_bfloat16 *out; int ldo; size_t piece;      // its pieces in the arena
+};
+static SplitEntry g_split[16];
+static int g_nsplit = 0;
+static bool g_scope = false;
+static size_t g_cursor = 0;                          // arena bytes in use (reset per GEMM outside a scope)
+
+// bf16 pieces of the fp32 matrix x [rows][cols] (pitch ld): from the cache when x lies inside a matrix that
+// was split in this scope, otherwise split now.  Returns the pointer to piece 0, its pitch and the piece stride.
+template <int NP>
+static int acquire_split(const float *x, int rows, int cols, int ld, cudaStream_t stream,
+                         const __nv_bfloat16 **out, int *ldo, size_t *piece)
+{
+    if (g_scope)
+        for (int i = 0; i < g_nsplit; ++i) {
+            const SplitEntry &e = g_split[i];
+            if (e.np != NP || e.ld != ld || x < e.base) continue;
+            const size_t off = (size_t)(x - e.base);
+            const size_t r0 = off / (size_t)ld, c0 = off % (size_t)ld;
+            if (r0 + rows > (size_t)e.rows || c0 + cols > (size_t)e.cols || (c0 & 7)) continue;
+            *out = e.out + r0 * e.ldo + c0; *ldo = e.ldo; *piece = e.piece;
+            return CTCASR_OK;
+        }
+    const int lo = (cols + 7) / 8 * 8;
+    const size_t pc = (size_t)rows * lo;
+    const size_t bytes = align_up(pc * NP * 2, 1024);
+    if (g_cursor + bytes > g_scratch_bytes) {
+        g_scratch_needed = g_cursor + bytes;
+        return fail(CTCASR_ERR_WORKSPACE, "gemm_tc: split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)",
+                    g_scratch_bytes, g_scratch_needed);
+    }
+    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(g_scratch + g_cursor);
+    g_cursor += bytes;
+    const size_t n4 = (size_t)rows * (cols / 4);
+    const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    {
+        ProfScope prof_split(PROF_SPLIT, stream);
+        split_bf16_kernel<NP><<<grid, 256, 0, stream>>>(x, rows, cols, ld, dst, lo);
+        CTCASR_LAUNCH_CHECK();
+    }
+    if (g_scope && g_nsplit < 16) g_split[g_nsplit++] = SplitEntry{x, rows, cols, ld, NP, dst, lo, pc};
+    *out = dst; *ldo = lo; *piece = pc;
+    return CTCASR_OK;
+}
+
 template <int MODE>
 static int launch(const GemmArgs &g, cudaStream_t stream)
 {
@@ -345,31 +393,19 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
     int lda = g.lda, ldb = g.ldb;
     size_t a_piece = 0, b_piece = 0;
     if (C_::kBf16) {
-        const int ldoa = (a_cols + 7) / 8 * 8, ldob = (b_cols + 7) / 8 * 8;
-        a_piece = (size_t)a_rows * ldoa; b_piece = (size_t)b_rows * ldob;
-        const size_t a_bytes = align_up(a_piece * NP * 2, 1024), b_bytes = align_up(b_piece * NP * 2, 1024);
-        const size_t need = (size_t)g.nz * (a_bytes + b_bytes);
-        if (need > g_scratch_bytes) {
-            g_scratch_needed = need;
-            return fail(CTCASR_ERR_WORKSPACE, "gemm_tc: split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)",
-                        g_scratch_bytes, need);
-        }
-        char *cur = g_scratch;
+        if (!g_scope) g_cursor = 0;
         for (int z = 0; z < g.nz; ++z) {
-            __nv_bfloat16 *sa = reinterpret_cast<__nv_bfloat16 *>(cur); cur += a_bytes;
-            __nv_bfloat16 *sb = reinterpret_cast<__nv_bfloat16 *>(cur); cur += b_bytes;
-            const size_t ta4 = (size_t)a_rows * (a_cols / 4), tb4 = (size_t)b_rows * (b_cols / 4);
-            const int ga = (int)((ta4 + 255) / 256 < 148 * 16 ? (ta4 + 255) / 256 : 148 * 16);
-            const int gb = (int)((tb4 + 255) / 256 < 148 * 16 ? (tb4 + 255) / 256 : 148 * 16);
-            ProfScope prof_split(PROF_SPLIT, stream);
-            split_bf16_kernel<NP><<<ga, 256, 0, stream>>>(g.A[z], a_rows, a_cols, g.lda, sa, ldoa);
-            CTCASR_LAUNCH_CHECK();
-            split_bf16_kernel<NP><<<gb, 256, 0, stream>>>(g.B[z], b_rows, b_cols, g.ldb, sb, ldob);
-            CTCASR_LAUNCH_CHECK();
-            Abase[z] = sa; Bbase[z] = sb;
+            const __nv_bfloat16 *sa, *sb;
+            int la, lb;
+            size_t pa, pb;
+            if (int rc = acquire_split<NP>(g.A[z], a_rows, a_cols, g.lda, stream, &sa, &la, &pa)) return rc;
+            if (int rc = acquire_split<NP>(g.B[z], b_rows, b_cols, g.ldb, stream, &sb, &lb, &pb)) return rc;
+            // the two problems of a batched GEMM share one tensor-map geometry
+            if (z > 0 && (la != lda || lb != ldb || pa != a_piece || pb != b_piece))
+                return fail(CTCASR_ERR_INVALID, "gemm_tc: batched operands with different split layouts");
+            Abase[z] = sa; Bbase[z] = sb; lda = la; ldb = lb; a_piece = pa; b_piece = pb;
         }
         if (g.nz == 1) { Abase[1] = Abase[0]; Bbase[1] = Bbase[0]; }
-        lda = ldoa; ldb = ldob;
     }
     CUtensorMap maps[4];
     const CUtensorMapSwizzle sw_k = C_::kBf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
@@ -434,6 +470,27 @@ int gemm_scratch_check(int compute, int nz, int M, int N, int K)
         return fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", tc::g_scratch_bytes, need);
     }
     return CTCASR_OK;
+}
+
+int split_scope_begin(int compute, const size_t *elems, int n)
+{
+    if (compute != CTCASR_COMPUTE_BF16X3) return CTCASR_OK;
+    size_t need = 0;
+    for (int i = 0; i < n; ++i) need += align_up(6 * elems[i], 1024);
+    if (need > tc::g_scratch_bytes) {
+        if (need > tc::g_scratch_needed) tc::g_scratch_needed = need;
+        return fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", tc::g_scratch_bytes, need);
+    }
+    tc::g_scope = true; tc::g_nsplit = 0; tc::g_cursor = 0;
+    return CTCASR_OK;
+}
+void split_scope_end() { tc::g_scope = false; tc::g_nsplit = 0; tc::g_cursor = 0; }
+
+void *scratch_free(size_t bytes)
+{
+    const size_t used = tc::g_scope ? tc::g_cursor : 0;
+    if (!tc::g_scratch || used + bytes > tc::g_scratch_bytes) return nullptr;
+    return tc::g_scratch + used;
 }
 
 int gemm_tc(const GemmArgs &g, int compute, cudaStream_t stream)

@@ -85,6 +85,8 @@ struct Params {
     int skip;                // timing experiments only: 1 = do not load weight tiles, 2 = do not load state tiles
     int nprod;               // timing experiments only: number of split products issued (3 = correct)
     int kb_keep;             // weight k-blocks [0, kb_keep) are loaded with L2 evict_last, the rest evict_first
+    float *dbias;            // bwd (cluster kernel): [8H] column sums of dz, or null
+    int db_accum;            // add to dbias instead of storing (batch slices after the first)
 };
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
@@ -715,6 +717,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
         const int cu = e & 31, bg = e >> 5;                                 // cell ownership: rows bg*4 .. bg*4+3
         const int ucol = ub * 128 + q * UPC;                                // the 32 units whose cells this CTA owns
         float dcreg[4];
+        float dbacc[4] = {0.f, 0.f, 0.f, 0.f};                              // bias gradient: sum of dz over time and my rows
         int len4[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int b = bg * 4 + j; dcreg[j] = 0.f; len4[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
@@ -790,6 +793,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                     dcreg[j] = 0.f;
                 }
                 o_dz[j][0] = dzi; o_dz[j][1] = dzj; o_dz[j][2] = dzf; o_dz[j][3] = dzo;
+                dbacc[0] += dzi; dbacc[1] += dzj; dbacc[2] += dzf; dbacc[3] += dzo;
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {        // the bf16 pieces are what the other CTAs wait for
                     __nv_bfloat16 hi, lo;
@@ -809,6 +813,22 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                     float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
                     grow[0] = o_dz[j][0]; grow[H] = o_dz[j][1]; grow[2 * (size_t)H] = o_dz[j][2]; grow[3 * (size_t)H] = o_dz[j][3];
                 }
+            }
+        }
+        if (p.dbias) {
+            // column sums of dz for my 32 units x 4 gates: the 8 row groups meet in the (now idle) exchange slots
+            float *red = const_cast<float *>(slots);                        // [8 bg][4 gates][32 cu]
+            cell_bar();
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) red[(bg * 4 + g4) * UPC + cu] = dbacc[g4];
+            cell_bar();
+            if (e < 4 * UPC) {
+                const int g4 = e >> 5;
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v += red[(k * 4 + g4) * UPC + cu];
+                float *dst = p.dbias + (size_t)d * 4 * H + (size_t)g4 * H + ucol + cu;
+                *dst = p.db_accum ? *dst + v : v;
             }
         }
     }
@@ -981,6 +1001,7 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
         p.gates = gates + (size_t)b0 * 8 * H; p.cstate = cstate + (size_t)b0 * 2 * H; p.y = y + (size_t)b0 * 2 * H;
         p.dy = nullptr; p.xbuf = hbuf; p.counters = ctr;
         p.kb_keep = keep_kblocks(H);
+        p.dbias = nullptr; p.db_accum = 0;
         p.kres = resident_kblocks(H);
         p.wpack = wp; p.wrows = 2 * 4 * H; p.wk = H;
         p.trace = g_trace;
@@ -1000,7 +1021,7 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
 }
 
 int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *cstate, const float *dy,
-                int T, int B, int H, int use_len, void *ws, cudaStream_t stream)
+                float *dbias, int *dbias_done, int T, int B, int H, int use_len, void *ws, cudaStream_t stream)
 {
     using namespace lstm;
     char *base = reinterpret_cast<char *>(align_up((size_t)(uintptr_t)ws, 1024));
@@ -1054,6 +1075,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
         p.dy = dy + (size_t)b0 * 2 * H; p.xbuf = zbuf; p.counters = ctr;
         p.kb_keep = keep_kblocks(H);
         p.kres = use_cluster ? resident_kblocks(H) : 0; p.wpack = wq; p.wrows = 2 * H; p.wk = 4 * H;
+        p.dbias = use_cluster ? dbias : nullptr; p.db_accum = b0 > 0;
         p.trace = nullptr;
         p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
         p.nprod = 3; p.skip = 0;
@@ -1066,6 +1088,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
         }
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
     }
+    if (dbias_done) *dbias_done = use_cluster && dbias;      // the cluster kernel sums dz over time itself
     return CTCASR_OK;
 }
 

@@ -115,15 +115,20 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
     CTCASR_REQUIRE(cell >= 0 && cell <= 3, "birnn_bwd: bad cell %d", cell);
     if (ws_bytes < ctcasr_birnn_workspace_bytes(T, B, in, H, cell)) return fail(CTCASR_ERR_WORKSPACE, "birnn_bwd: workspace too small");
     const int G = num_gates(cell), GH = G * H;
-    if (int rcs = gemm_scratch_check(compute, 1, in, 2 * GH, T * B)) return rcs;
-    if (int rcs = gemm_scratch_check(compute, 2, H, GH, T * B)) return rcs;
-    if (int rcs = gemm_scratch_check(compute, 1, T * B, in, 2 * GH)) return rcs;
     Reserve r = carve_reserve(reserve, T, B, H, G);
-    int rc;
+    int rc, dbias_done = 0;
+    // dz is read by three GEMMs (dWx, dWh, dX): its bf16 pieces are made once and shared
+    auto pad8 = [](int v) { return (size_t)((v + 7) / 8 * 8); };
+    const size_t TB = (size_t)T * B;
+    const size_t operands[6] = {TB * pad8(in), TB * pad8(2 * GH), TB * pad8(H), TB * pad8(H), (size_t)in * pad8(2 * GH),
+                                cell == CTCASR_CELL_GRU ? TB * pad8(2 * GH) : 0};       // GRU: dWh reads a second dz (dzr)
+    SplitScope scope;
+    if (int rcs = split_scope_begin(compute, operands, 6)) return rcs;
+    scope.open = true;
 
     if (compute != CTCASR_COMPUTE_FP32 && lstm_tc_eligible(T, B, H, cell)) {
         char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
-        rc = lstm_tc_bwd(seq_len, wh, r.gates, r.cstate, dy, T, B, H, use_len, wsb, stream);
+        rc = lstm_tc_bwd(seq_len, wh, r.gates, r.cstate, dy, dbias, &dbias_done, T, B, H, use_len, wsb, stream);
         if (rc != CTCASR_OK) return rc;
     } else {
         RnnStep s;
@@ -151,8 +156,10 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
     }
     // r.gates now holds dz [T*B, 2GH] (wrt the input-side pre-activations); GRU: r.dzr wrt h Wh
     const float *dzh = cell == CTCASR_CELL_GRU ? r.dzr : r.gates;
-    rc = colsum(r.gates, T * B, 2 * GH, 2 * GH, dbias, stream);
-    if (rc != CTCASR_OK) return rc;
+    if (!dbias_done) {
+        rc = colsum(r.gates, T * B, 2 * GH, 2 * GH, dbias, stream);
+        if (rc != CTCASR_OK) return rc;
+    }
     if (cell == CTCASR_CELL_GRU)
         for (int d = 0; d < 2; ++d) {       // b_rn gradient: column sums of the n block of dzr
             rc = colsum(r.dzr + (size_t)d * GH + 2 * H, T * B, H, 2 * GH, dbias + 2 * GH + d * H, stream);

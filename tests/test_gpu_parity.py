@@ -177,6 +177,27 @@ def test_gemm_simt_all_orientations(ta, tb):
     assert rel_err(c, want) < 1e-5
 
 
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_simt_split_k_long_contraction(accumulate):
+    """The logits-layer weight gradient shape: few output tiles, a very long K.  With a scratch arena
+    present the SIMT kernel slices K over CTAs and adds the slices in a fixed order (bit-reproducible)."""
+    rng = np.random.default_rng(31)
+    ops.gemm(dev(rng.standard_normal((256, 256)).astype(np.float32)), dev(rng.standard_normal((256, 256)).astype(np.float32)),
+             compute=_lib.COMPUTE_BF16X3)                     # makes ops allocate the arena
+    M, N, K = 200, 29, 9000
+    a = rng.standard_normal((K, M)).astype(np.float32)
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    c0 = rng.standard_normal((M, N)).astype(np.float32)
+    outs = []
+    for _ in range(2):
+        out = dev(c0.copy())
+        ops.gemm(dev(a), dev(b), ta=True, out=out, accumulate=accumulate)
+        outs.append(out.cpu().numpy())
+    want = a.T.astype(np.float64) @ b.astype(np.float64) + (c0 if accumulate else 0.0)
+    assert rel_err(outs[0], want) < 1e-5
+    assert np.array_equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("rate", [0.0, 0.3])
 def test_dense_fwd_bwd_vs_oracle(rate):
     rng = np.random.default_rng(4)
