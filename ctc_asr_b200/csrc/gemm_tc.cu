@@ -344,24 +344,40 @@ static size_t g_cursor = 0;                          // arena bytes in use (rese
 
 // bf16 pieces of the fp32 matrix x [rows][cols] (pitch ld): from the cache when x lies inside a matrix that
 // was split in this scope, otherwise split now.  Returns the pointer to piece 0, its pitch and the piece stride.
+static const SplitEntry *find_split(const float *x, int rows, int cols, int ld, int np, size_t *r0, size_t *c0)
+{
+    if (!g_scope) return nullptr;
+    for (int i = 0; i < g_nsplit; ++i) {
+        const SplitEntry &e = g_split[i];
+        if (e.np != np || e.ld != ld || x < e.base) continue;
+        const size_t off = (size_t)(x - e.base);
+        *r0 = off / (size_t)ld; *c0 = off % (size_t)ld;
+        if (*r0 + rows > (size_t)e.rows || *c0 + cols > (size_t)e.cols || (*c0 & 7)) continue;
+        return &e;
+    }
+    return nullptr;
+}
+// arena bytes a split of this operand takes (0 when it is served from the cache)
+static size_t split_bytes(const float *x, int rows, int cols, int ld, int np)
+{
+    size_t r0, c0;
+    if (find_split(x, rows, cols, ld, np, &r0, &c0)) return 0;
+    return align_up((size_t)rows * ((cols + 7) / 8 * 8) * np * 2, 1024);
+}
+
 template <int NP>
 static int acquire_split(const float *x, int rows, int cols, int ld, cudaStream_t stream,
                          const __nv_bfloat16 **out, int *ldo, size_t *piece)
 {
-    if (g_scope)
-        for (int i = 0; i < g_nsplit; ++i) {
-            const SplitEntry &e = g_split[i];
-            if (e.np != NP || e.ld != ld || x < e.base) continue;
-            const size_t off = (size_t)(x - e.base);
-            const size_t r0 = off / (size_t)ld, c0 = off % (size_t)ld;
-            if (r0 + rows > (size_t)e.rows || c0 + cols > (size_t)e.cols || (c0 & 7)) continue;
-            *out = e.out + r0 * e.ldo + c0; *ldo = e.ldo; *piece = e.piece;
-            return CTCASR_OK;
-        }
+    size_t r0, c0;
+    if (const SplitEntry *e = find_split(x, rows, cols, ld, NP, &r0, &c0)) {
+        *out = e->out + r0 * e->ldo + c0; *ldo = e->ldo; *piece = e->piece;
+        return CTCASR_OK;
+    }
     const int lo = (cols + 7) / 8 * 8;
     const size_t pc = (size_t)rows * lo;
     const size_t bytes = align_up(pc * NP * 2, 1024);
-    if (g_cursor + bytes > g_scratch_bytes) {
+    if (g_cursor + bytes > g_scratch_bytes) {       // launch() checks the whole GEMM first: not reached from there
         g_scratch_needed = g_cursor + bytes;
         return fail(CTCASR_ERR_WORKSPACE, "gemm_tc: split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)",
                     g_scratch_bytes, g_scratch_needed);
@@ -394,6 +410,14 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
     size_t a_piece = 0, b_piece = 0;
     if (C_::kBf16) {
         if (!g_scope) g_cursor = 0;
+        size_t need = g_cursor;                      // everything this GEMM will split, checked before the first launch
+        for (int z = 0; z < g.nz; ++z)
+            need += split_bytes(g.A[z], a_rows, a_cols, g.lda, NP) + split_bytes(g.B[z], b_rows, b_cols, g.ldb, NP);
+        if (need > g_scratch_bytes) {
+            g_scratch_needed = need;
+            return fail(CTCASR_ERR_WORKSPACE, "gemm_tc: split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)",
+                        g_scratch_bytes, need);
+        }
         for (int z = 0; z < g.nz; ++z) {
             const __nv_bfloat16 *sa, *sb;
             int la, lb;

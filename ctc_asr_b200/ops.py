@@ -31,7 +31,9 @@ def _call(fn, what, *args):
     """Run a C-ABI call; when it asks for a bigger split-operand scratch arena, grow it and retry."""
     lib = _lib.load()
     rc = fn(*args)
-    if rc == -3 and lib.ctcasr_scratch_needed() > 0 and b"scratch" in lib.ctcasr_last_error():
+    for _ in range(3):
+        if not (rc == -3 and lib.ctcasr_scratch_needed() > 0 and b"scratch" in lib.ctcasr_last_error()):
+            break
         need = int(lib.ctcasr_scratch_needed() * 1.25) + (1 << 20)
         dev = torch.cuda.current_device()
         _scratch[dev] = None

@@ -198,6 +198,20 @@ def test_gemm_simt_split_k_long_contraction(accumulate):
     assert np.array_equal(outs[0], outs[1])
 
 
+def test_gemm_bf16x3_scratch_arena_grows_for_both_operands():
+    """Starting without an arena, one call must report the need of BOTH operands' pieces (a need reported
+    operand by operand made the single grow-and-retry of the host wrapper fail on large first calls)."""
+    import ctypes
+    lib = _lib.load()
+    _lib.check(lib.ctcasr_set_scratch(ctypes.c_void_p(0), 0), "set_scratch")
+    ops._scratch.clear()
+    rng = np.random.default_rng(32)
+    a = rng.standard_normal((1024, 1536)).astype(np.float32)
+    b = rng.standard_normal((1536, 1024)).astype(np.float32)
+    c = ops.gemm(dev(a), dev(b), compute=_lib.COMPUTE_BF16X3).cpu().numpy()
+    assert rel_err(c, a.astype(np.float64) @ b.astype(np.float64)) < 2e-5
+
+
 @pytest.mark.parametrize("rate", [0.0, 0.3])
 def test_dense_fwd_bwd_vs_oracle(rate):
     rng = np.random.default_rng(4)
