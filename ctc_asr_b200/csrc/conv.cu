@@ -1,0 +1,193 @@
+// conv.cu — the 2-D convolution layers of the 'ds2' front-end (asr/util/tf_contrib.py:64-146):
+// tf.layers.conv2d(padding='SAME', activation=relu) + tf.minimum(., relu_cutoff), forward and backward.
+//
+// Formulation: a convolution layer is a dense layer over the patch matrix.  `im2col_kernel` gathers,
+// for every output position (to, b, fo), its kt x kf x C input patch into one row of `col`
+// [To*B*Fo, Kp] (HBM-bound gather, coalesced along the patch: a (jf, c) run is contiguous in x);
+// the product with the kernel [Kp, N] (TF's HWIO layout flattened: row = (it*kf + jf)*C + c) then
+// runs on the tcgen05 GEMM with the bias + clipped-ReLU epilogue of the dense layers.  Backward:
+// dW = col^T dz and dcol = dz W^T on the same GEMM, and `col2im_kernel` folds dcol back onto the
+// input as a GATHER (every input element sums the taps that touched it, fixed order: deterministic,
+// no atomics).  The patch matrix is re-built in the backward pass instead of being kept (9.5 GB for
+// the second layer at B=32 x 10 s): one buffer serves col and then dcol.
+//
+// Layout: activations [T, B, F, pitch] time-major (row = (t*B + b)*F + f), `pitch` >= channels so
+// that the GEMM's N (>= 64, multiple of 8) can be wider than the layer's filter count: the pad
+// channels of y are exact zeros (zero kernel columns and bias) and are skipped by the next im2col.
+#include "gemm.cuh"
+
+namespace ctcasr {
+namespace conv {
+
+struct Geom {
+    int T, B, F, C, xpitch;
+    int kt, kf, st, sf;
+    int To, Fo, pt, pf;
+    int K, Kp;
+};
+
+static void same_pad(int in, int k, int s, int *out, int *pad0)
+{
+    *out = (in + s - 1) / s;
+    int total = (*out - 1) * s + k - in;
+    if (total < 0) total = 0;
+    *pad0 = total / 2;          // TF 'SAME': the odd unit goes after
+}
+
+static int make_geom(int T, int B, int F, int C, int xpitch, int kt, int kf, int st, int sf, Geom *g)
+{
+    CTCASR_REQUIRE(T >= 1 && B >= 1 && F >= 1 && C >= 1 && xpitch >= C, "conv2d: bad dims T=%d B=%d F=%d C=%d pitch=%d", T, B, F, C, xpitch);
+    CTCASR_REQUIRE(kt >= 1 && kf >= 1 && st >= 1 && sf >= 1, "conv2d: bad kernel %dx%d / stride %dx%d", kt, kf, st, sf);
+    g->T = T; g->B = B; g->F = F; g->C = C; g->xpitch = xpitch;
+    g->kt = kt; g->kf = kf; g->st = st; g->sf = sf;
+    same_pad(T, kt, st, &g->To, &g->pt);
+    same_pad(F, kf, sf, &g->Fo, &g->pf);
+    g->K = kt * kf * C;
+    g->Kp = (g->K + 7) / 8 * 8;
+    return CTCASR_OK;
+}
+
+// one CTA per output position (grid-stride), threads along the patch
+__global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ x, float *__restrict__ col, const Geom g, size_t rows)
+{
+    for (size_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int fo = (int)(r % g.Fo);
+        const size_t q = r / g.Fo;
+        const int b = (int)(q % g.B), to = (int)(q / g.B);
+        const int t0 = to * g.st - g.pt, f0 = fo * g.sf - g.pf;
+        float *crow = col + r * g.Kp;
+        for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
+            float v = 0.f;
+            if (k < g.K) {
+                const int c = k % g.C, q2 = k / g.C;
+                const int jf = q2 % g.kf, it = q2 / g.kf;
+                const int t = t0 + it, f = f0 + jf;
+                if (t >= 0 && t < g.T && f >= 0 && f < g.F)
+                    v = __ldg(x + (((size_t)t * g.B + b) * g.F + f) * g.xpitch + c);
+            }
+            crow[k] = v;
+        }
+    }
+}
+
+// one thread per input element (t, b, f, c'), c' over the whole pitch (pad channels get 0)
+__global__ void __launch_bounds__(256) col2im_kernel(const float *__restrict__ dcol, float *__restrict__ dx, const Geom g, size_t total)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % g.xpitch);
+        const size_t r = i / g.xpitch;
+        float s = 0.f;
+        if (c < g.C) {
+            const int f = (int)(r % g.F);
+            const size_t q = r / g.F;
+            const int b = (int)(q % g.B), t = (int)(q / g.B);
+            for (int it = 0; it < g.kt; ++it) {
+                const int tn = t + g.pt - it;
+                if (tn < 0) break;
+                if (tn % g.st) continue;
+                const int to = tn / g.st;
+                if (to >= g.To) continue;
+                for (int jf = 0; jf < g.kf; ++jf) {
+                    const int fn = f + g.pf - jf;
+                    if (fn < 0) break;
+                    if (fn % g.sf) continue;
+                    const int fo = fn / g.sf;
+                    if (fo >= g.Fo) continue;
+                    s += __ldg(dcol + (((size_t)to * g.B + b) * g.Fo + fo) * g.Kp + (it * g.kf + jf) * g.C + c);
+                }
+            }
+        }
+        dx[i] = s;
+    }
+}
+
+static int grid_for(size_t work_items)
+{
+    const size_t cap = (size_t)148 * 16;
+    return (int)(work_items < cap ? (work_items ? work_items : 1) : cap);
+}
+
+}  // namespace conv
+}  // namespace ctcasr
+
+using namespace ctcasr;
+
+extern "C" int ctcasr_conv2d_out_dims(int T, int F, int kt, int kf, int st, int sf, int *To, int *Fo)
+{
+    CTCASR_REQUIRE(To && Fo && T >= 1 && F >= 1 && kt >= 1 && kf >= 1 && st >= 1 && sf >= 1, "conv2d_out_dims: bad args");
+    int p;
+    conv::same_pad(T, kt, st, To, &p);
+    conv::same_pad(F, kf, sf, Fo, &p);
+    return CTCASR_OK;
+}
+
+extern "C" size_t ctcasr_conv2d_workspace_bytes(int T, int B, int F, int C, int kt, int kf, int st, int sf)
+{
+    conv::Geom g{};
+    if (conv::make_geom(T, B, F, C, C, kt, kf, st, sf, &g) != CTCASR_OK) return 0;
+    return align_up((size_t)g.To * B * g.Fo * g.Kp * sizeof(float), 256);
+}
+
+extern "C" int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, const float *bias, float *y,
+                                 int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
+                                 int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTCASR_REQUIRE(x && w && y && N >= 1, "conv2d_fwd: bad args");
+    conv::Geom g{};
+    if (int rc = conv::make_geom(T, B, F, C, x_pitch, kt, kf, st, sf, &g)) return rc;
+    const size_t rows = (size_t)g.To * B * g.Fo;
+    CTCASR_REQUIRE(rows <= 0x7fffffff, "conv2d_fwd: %zu output positions", rows);
+    const size_t need = align_up(rows * g.Kp * sizeof(float), 256);
+    if (!ws || ws_bytes < need) return fail(CTCASR_ERR_WORKSPACE, "conv2d_fwd: workspace %zu < %zu", ws_bytes, need);
+    if (int rcs = gemm_scratch_check(compute, 1, (int)rows, N, g.Kp)) return rcs;
+    float *col = reinterpret_cast<float *>(ws);
+    conv::im2col_kernel<<<conv::grid_for(rows), 256, 0, stream>>>(x, col, g, rows);
+    CTCASR_LAUNCH_CHECK();
+    GemmArgs a;
+    a.A[0] = col; a.B[0] = w; a.C[0] = y; a.M = (int)rows; a.N = N; a.K = g.Kp; a.lda = g.Kp; a.ldb = N; a.ldc = N;
+    a.epi.mode = EPI_BIAS_ACT; a.epi.bias = bias; a.epi.act = act; a.epi.cutoff = cutoff;
+    a.precise = act != 0;
+    return gemm(a, compute, stream);
+}
+
+extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, const float *y, float *dy,
+                                 float *dx, float *dw, float *db,
+                                 int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
+                                 int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTCASR_REQUIRE(x && w && dy && dw && db && N >= 1, "conv2d_bwd: bad args");
+    CTCASR_REQUIRE(act == 0 || y, "conv2d_bwd: activation mask needs the forward output y");
+    conv::Geom g{};
+    if (int rc = conv::make_geom(T, B, F, C, x_pitch, kt, kf, st, sf, &g)) return rc;
+    const size_t rows = (size_t)g.To * B * g.Fo;
+    CTCASR_REQUIRE(rows <= 0x7fffffff, "conv2d_bwd: %zu output positions", rows);
+    const size_t need = align_up(rows * g.Kp * sizeof(float), 256);
+    if (!ws || ws_bytes < need) return fail(CTCASR_ERR_WORKSPACE, "conv2d_bwd: workspace %zu < %zu", ws_bytes, need);
+    if (int rcs = gemm_scratch_check(compute, 1, g.Kp, N, (int)rows)) return rcs;
+    if (dx) if (int rcs = gemm_scratch_check(compute, 1, (int)rows, g.Kp, N)) return rcs;
+    float *col = reinterpret_cast<float *>(ws);
+    int rc = mask_inplace(dy, y, rows, N, act, cutoff, 0.f, 0u, stream);       // dy -> dz
+    if (rc != CTCASR_OK) return rc;
+    rc = colsum(dy, (int)rows, N, N, db, stream);
+    if (rc != CTCASR_OK) return rc;
+    conv::im2col_kernel<<<conv::grid_for(rows), 256, 0, stream>>>(x, col, g, rows);
+    CTCASR_LAUNCH_CHECK();
+    {   // dW[Kp,N] = col^T dz   (rows K..Kp of col^T are zero -> the pad rows of dW are zero)
+        GemmArgs a;
+        a.A[0] = col; a.B[0] = dy; a.C[0] = dw; a.ta = 1; a.M = g.Kp; a.N = N; a.K = (int)rows; a.lda = g.Kp; a.ldb = N; a.ldc = N;
+        rc = gemm(a, compute, stream);
+        if (rc != CTCASR_OK) return rc;
+    }
+    if (dx) {   // dcol[rows,Kp] = dz W^T into the buffer col occupied (stream order: dW has consumed it)
+        GemmArgs a;
+        a.A[0] = dy; a.B[0] = w; a.C[0] = col; a.tb = 1; a.M = (int)rows; a.N = g.Kp; a.K = N; a.lda = N; a.ldb = N; a.ldc = g.Kp;
+        rc = gemm(a, compute, stream);
+        if (rc != CTCASR_OK) return rc;
+        const size_t total = (size_t)T * B * F * x_pitch;
+        conv::col2im_kernel<<<conv::grid_for((total + 255) / 256), 256, 0, stream>>>(col, dx, g, total);
+        CTCASR_LAUNCH_CHECK();
+    }
+    return CTCASR_OK;
+}

@@ -18,27 +18,56 @@ __global__ void transpose01_kernel(const float *__restrict__ in, float *__restri
 }
 
 // ---- column sums: out[n] = sum_m x[m*ld + n]  (bias gradients) --------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ x, int M, int N, int ld, float *__restrict__ out)
+// Two deterministic stages: the rows are cut into `parts` equal slabs (grid.y), every CTA sums its slab
+// for 32 columns, and the slab sums are added in slab order.  One stage (parts = 1) for short matrices.
+constexpr int kColsumMaxParts = 64, kColsumMaxN = 16384;
+__device__ float g_colsum_partial[kColsumMaxParts * kColsumMaxN];
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ x, int M, int N, int ld, float *__restrict__ out,
+                                                     int rows_per_part, int to_partial)
 {
     __shared__ float red[8][33];
     const int n = blockIdx.x * 32 + (threadIdx.x & 31);
     const int r = threadIdx.x >> 5;
+    const int m0 = blockIdx.y * rows_per_part, m1 = min(M, m0 + rows_per_part);
     float acc = 0.f;
     if (n < N)
-        for (int m = r; m < M; m += 8) acc += x[(size_t)m * ld + n];
+        for (int m = m0 + r; m < m1; m += 8) acc += x[(size_t)m * ld + n];
     red[r][threadIdx.x & 31] = acc;
     __syncthreads();
     if (r == 0 && n < N) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-        out[n] = s;
+        if (to_partial) g_colsum_partial[(size_t)blockIdx.y * N + n] = s;
+        else out[n] = s;
     }
+}
+
+__global__ void colsum_finish_kernel(float *__restrict__ out, int N, int parts)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int p = 0; p < parts; ++p) s += g_colsum_partial[(size_t)p * N + n];
+    out[n] = s;
 }
 
 int colsum(const float *x, int M, int N, int ld, float *out, cudaStream_t stream)
 {
-    colsum_kernel<<<ceil_div(N, 32), 256, 0, stream>>>(x, M, N, ld, out);
+    const int nb = ceil_div(N, 32);
+    int parts = ceil_div(2 * 148, nb);
+    if (parts > kColsumMaxParts) parts = kColsumMaxParts;
+    if (parts > M / 256) parts = M / 256;
+    if (parts < 2 || N > kColsumMaxN) {
+        colsum_kernel<<<dim3(nb, 1), 256, 0, stream>>>(x, M, N, ld, out, M, 0);
+        CTCASR_LAUNCH_CHECK();
+        return CTCASR_OK;
+    }
+    const int rpp = ceil_div(M, parts);
+    colsum_kernel<<<dim3(nb, parts), 256, 0, stream>>>(x, M, N, ld, out, rpp, 1);
+    CTCASR_LAUNCH_CHECK();
+    colsum_finish_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(out, N, parts);
     CTCASR_LAUNCH_CHECK();
     return CTCASR_OK;
 }

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib, labels as _labels, ops
-from .params import CELL_ID, FLAGS, ModelConfig, param_offsets, param_specs
+from .params import CELL_ID, FLAGS, ModelConfig, conv_plan, param_offsets, param_specs, storage_shape
 
 
 class CTCModel:
@@ -31,8 +31,10 @@ class CTCModel:
         self.adam_m = torch.zeros_like(self.flat)
         self.adam_v = torch.zeros_like(self.flat)
         self.global_step = 0
-        self.p = {k: self._view(self.flat, k) for k in self.offsets}
+        self.p = {k: self._view(self.flat, k) for k in self.offsets}          # reference-shaped views
         self.g = {k: self._view(self.grad_flat, k) for k in self.offsets}
+        self.ps = {k: self._view(self.flat, k, storage=True) for k in self.offsets}       # as the kernels read them
+        self.gs = {k: self._view(self.grad_flat, k, storage=True) for k in self.offsets}
         if params is None:
             from .synthetic import init_params
             params = init_params(config, seed=seed)
@@ -42,10 +44,18 @@ class CTCModel:
         self.dropout_seed = int(config.random_seed)
 
     # ---- parameter plumbing -------------------------------------------------------------------
-    def _view(self, flat, name):
+    def _view(self, flat, name, storage=False):
         off, shape = self.offsets[name]
-        n = int(np.prod(shape))
-        return flat[off:off + n].view(*shape)
+        st = storage_shape(self.cfg, name, shape)
+        n = int(np.prod(st))
+        block = flat[off:off + n].view(*st)
+        if storage or tuple(st) == tuple(shape):
+            return block
+        if len(shape) == 1:                              # conv bias [filters] inside [N]
+            return block[:shape[0]]
+        kt, kf, C, filt = shape                          # conv kernel HWIO inside the zero-padded [Kp, N] operand
+        N = st[1]
+        return block.as_strided((kt, kf, C, filt), (kf * C * N, C * N, N, 1))
 
     def load_params(self, params):
         for name, shape, _ in param_specs(self.cfg):
@@ -76,6 +86,9 @@ class CTCModel:
     def _dense_names(self):
         return ["dense/dense" if i == 0 else "dense/dense_%d" % i for i in range(self.cfg.num_layers_dense)]
 
+    def _conv_names(self):
+        return ["conv/conv2d" if i == 0 else "conv/conv2d_%d" % i for i in range(len(self.cfg.conv_filters))]
+
     # ---- asr/model.py:123-236 -----------------------------------------------------------------
     def inference_fn(self, sequences, seq_length, training=True):
         """sequences [B,T,F] float32, seq_length [B] int32 -> (logits [T,B,V], seq_length).
@@ -94,12 +107,29 @@ class CTCModel:
 
         x = ops.transpose01(sequences, out=self._buf("xT", (T, B, F))).view(T * B, F)
         h = x
-        for li, name in enumerate(self._dense_names()):
-            y = ops.dense_fwd(h, self.p[name + "/kernel"], self.p[name + "/bias"], act=1, cutoff=cfg.relu_cutoff,
-                              drop_rate=rate, seed=seed + li, compute=self.compute,
-                              out=self._buf("dense%d" % li, (T * B, cfg.num_units_dense)))
-            saved["dense"].append((h, y))
-            h = y
+        if cfg.used_model == "ds2":
+            # conv front-end (asr/model.py:154-161, asr/util/tf_contrib.py:123-144); [T,B,F] is [T,B,F,1]
+            saved["conv"] = []
+            xin, pitch = x, 1
+            for li, d in enumerate(conv_plan(cfg, T)):
+                name = self._conv_names()[li]
+                y = self._buf("conv%d" % li, (d["To"] * B * d["Fo"], d["N"]))
+                ops.conv2d_fwd(xin, pitch, self.ps[name + "/kernel"], self.ps[name + "/bias"], y, d["T"], B, d["F"],
+                               d["C"], d["kt"], d["kf"], d["st"], d["sf"], act=1, cutoff=cfg.relu_cutoff,
+                               compute=self.compute)
+                saved["conv"].append((xin, pitch, y, d))
+                xin, pitch = y, d["N"]
+            T = d["To"]                                   # every utterance is stretched to the conv length of
+            seq_length = torch.full_like(seq_length, T)   # the longest one (asr/util/tf_contrib.py:141-144)
+            saved["T"], saved["seq_length"] = T, seq_length
+            h = xin.view(T * B, d["Fo"] * d["N"])         # [T', B, Fo*filters]: the reshape at tf_contrib.py:138
+        else:
+            for li, name in enumerate(self._dense_names()):
+                y = ops.dense_fwd(h, self.p[name + "/kernel"], self.p[name + "/bias"], act=1, cutoff=cfg.relu_cutoff,
+                                  drop_rate=rate, seed=seed + li, compute=self.compute,
+                                  out=self._buf("dense%d" % li, (T * B, cfg.num_units_dense)))
+                saved["dense"].append((h, y))
+                h = y
         cell = CELL_ID[cfg.rnn_cell]
         use_len = not cfg.cudnn
         H = cfg.num_units_rnn
@@ -209,6 +239,16 @@ class CTCModel:
                           y, reserve, dy, dx, self.g["rnn/l%d/wx" % l], self.g["rnn/l%d/wh" % l],
                           self.g["rnn/l%d/bias" % l], cell, use_len, self.compute)
             dy = dx
+        if cfg.used_model == "ds2":
+            names = self._conv_names()
+            for li in reversed(range(len(names))):
+                xin, pitch, y, d = s["conv"][li]
+                dx = self._buf("g_conv%d" % (li % 2), (d["T"] * B * d["F"], pitch)) if li > 0 else None
+                ops.conv2d_bwd(xin, pitch, self.ps[names[li] + "/kernel"], y, dy, dx, self.gs[names[li] + "/kernel"],
+                               self.gs[names[li] + "/bias"], d["T"], B, d["F"], d["C"], d["kt"], d["kf"], d["st"], d["sf"],
+                               act=1, cutoff=cfg.relu_cutoff, compute=self.compute)
+                dy = dx
+            return self.grad_flat
         names = self._dense_names()
         for li in reversed(range(len(names))):
             x, y = s["dense"][li]

@@ -18,6 +18,10 @@ WIN_STEP = 0.010            # asr/params.py:147
 MIN_EXAMPLE_LENGTH = 0.7    # asr/params.py:142
 MAX_EXAMPLE_LENGTH = 17.0   # asr/params.py:143
 
+# asr/util/tf_contrib.py:66-67 (defaults of conv_layers; height = time, width = features)
+CONV_KERNEL_SIZES = ((11, 41), (11, 21), (11, 21))
+CONV_STRIDES = ((2, 2), (1, 2), (1, 2))
+
 RNN_CELLS = ("rnn_relu", "rnn_tanh", "lstm", "gru")     # asr/model.py:194-199
 NUM_GATES = {"rnn_relu": 1, "rnn_tanh": 1, "lstm": 4, "gru": 3}
 CELL_ID = {"rnn_tanh": 0, "rnn_relu": 1, "lstm": 2, "gru": 3}   # ctcasr.h CTCASR_CELL_*
@@ -26,9 +30,10 @@ CELL_ID = {"rnn_tanh": 0, "rnn_relu": 1, "lstm": 2, "gru": 3}   # ctcasr.h CTCAS
 @dataclass(frozen=True)
 class ModelConfig:
     # --- names and defaults of asr/params.py -------------------------------------------------
-    used_model: str = "ds1"             # reference default 'ds2' (conv front-end) is a "next" row
+    used_model: str = "ds1"             # :31  'ds1' dense front-end | 'ds2' conv front-end (reference default)
     num_units_dense: int = 2048         # :35
     relu_cutoff: float = 20.0           # :37
+    conv_filters: tuple = (32, 32, 96)  # :40
     num_layers_rnn: int = 4             # :43
     num_units_rnn: int = 2048           # :45
     rnn_cell: str = "rnn_relu"          # :48
@@ -56,8 +61,17 @@ class ModelConfig:
     compute: str = "bf16x3"
 
     def __post_init__(self):
-        if self.used_model != "ds1":
+        if self.used_model not in ("ds1", "ds2"):
             raise ValueError('Unsupported model "{}" in flags.'.format(self.used_model))  # asr/model.py:163
+        object.__setattr__(self, "conv_filters", tuple(int(f) for f in self.conv_filters))
+        if self.used_model == "ds2":
+            if len(self.conv_filters) != len(CONV_KERNEL_SIZES):     # asr/util/tf_contrib.py:118-120
+                raise ValueError("conv_layers(): Arguments filters, kernel_size, and strides must contain "
+                                 "the same number of elements.")
+            # the last layer's output is the RNN input [T', B, Fo*filters] as it stands in memory, so its
+            # filter count is also its channel pitch: a legal tcgen05 GEMM width (the reference's is 96)
+            if self.conv_filters[-1] < 64 or self.conv_filters[-1] % 8:
+                raise ValueError("conv_filters[-1] must be a multiple of 8 and >= 64")
         if self.rnn_cell not in RNN_CELLS:
             raise ValueError("rnn_cell must be one of {}".format(RNN_CELLS))
         if self.compute not in ("fp32", "tf32", "bf16x3"):
@@ -78,6 +92,34 @@ class ModelConfig:
 FLAGS = ModelConfig()
 
 
+def same_out(n, k, s):
+    """tf 'SAME' padding: (output size, pad_before)."""
+    out = -(-n // s)
+    return out, max((out - 1) * s + k - n, 0) // 2
+
+
+def conv_plan(cfg: ModelConfig, T=None):
+    """Per conv layer of the ds2 front-end: dict(kt, kf, st, sf, C, filters, N, K, Kp, F, Fo[, T, To]).
+    N = channel pitch of the layer's output = GEMM width: max(64, roundup(filters, 8))."""
+    plan, F, C = [], cfg.num_features, 1
+    for filt, (kt, kf), (st, sf) in zip(cfg.conv_filters, CONV_KERNEL_SIZES, CONV_STRIDES):
+        K = kt * kf * C
+        d = dict(kt=kt, kf=kf, st=st, sf=sf, C=C, filters=filt, N=max(64, (filt + 7) // 8 * 8), K=K,
+                 Kp=(K + 7) // 8 * 8, F=F, Fo=same_out(F, kf, sf)[0])
+        if T is not None:
+            d["T"], d["To"] = T, same_out(T, kt, st)[0]
+            T = d["To"]
+        plan.append(d)
+        F, C = d["Fo"], filt
+    return plan
+
+
+def conv_out_frames(cfg: ModelConfig, T):
+    """Frames the RNN sees for T input frames (asr/util/tf_contrib.py:141-144: every utterance's
+    seq_length becomes this number)."""
+    return conv_plan(cfg, T)[-1]["To"] if cfg.used_model == "ds2" else T
+
+
 def param_specs(cfg: ModelConfig):
     """Ordered (name, shape, init) of every trainable tensor in the flat parameter buffer.
 
@@ -93,11 +135,22 @@ def param_specs(cfg: ModelConfig):
     specs = []
     D, H, G, V = cfg.num_units_dense, cfg.num_units_rnn, cfg.num_gates, cfg.num_classes
     nin = cfg.num_features
-    for i in range(cfg.num_layers_dense):
-        scope = "dense/dense" if i == 0 else "dense/dense_%d" % i
-        specs.append((scope + "/kernel", (nin, D), "truncnorm"))
-        specs.append((scope + "/bias", (D,), "zeros"))
-        nin = D
+    if cfg.used_model == "ds2":
+        # scope 'conv' (asr/model.py:155): tf.layers.conv2d names conv2d, conv2d_1, ...; HWIO kernels,
+        # glorot_normal (asr/util/tf_contrib.py:68): truncated normal, var = 2 / (fan_in + fan_out)
+        for i, d in enumerate(conv_plan(cfg)):
+            scope = "conv/conv2d" if i == 0 else "conv/conv2d_%d" % i
+            rf = d["kt"] * d["kf"]
+            specs.append((scope + "/kernel", (d["kt"], d["kf"], d["C"], d["filters"]),
+                          ("glorot_normal", rf * d["C"], rf * d["filters"])))
+            specs.append((scope + "/bias", (d["filters"],), "zeros"))
+            nin = d["Fo"] * d["filters"]
+    else:
+        for i in range(cfg.num_layers_dense):
+            scope = "dense/dense" if i == 0 else "dense/dense_%d" % i
+            specs.append((scope + "/kernel", (nin, D), "truncnorm"))
+            specs.append((scope + "/bias", (D,), "zeros"))
+            nin = D
     for l in range(cfg.num_layers_rnn):
         specs.append(("rnn/l%d/wx" % l, (nin, 2 * G * H), ("glorot", nin + H, G * H)))
         specs.append(("rnn/l%d/wh" % l, (2, H, G * H), ("glorot", nin + H, G * H)))
@@ -111,13 +164,24 @@ def param_specs(cfg: ModelConfig):
     return specs
 
 
+def storage_shape(cfg: ModelConfig, name, shape):
+    """Shape a tensor occupies in the flat buffer.  Conv kernels are stored as the zero-padded GEMM
+    operand [Kp, N] the kernels read (include/ctcasr.h, ctcasr_conv2d_fwd), conv biases as [N]; the
+    reference-shaped tensor is a strided view of that block.  Everything else is stored as is."""
+    if name.startswith("conv/"):
+        i = 0 if "_" not in name.split("/")[1] else int(name.split("/")[1].rsplit("_", 1)[1])
+        d = conv_plan(cfg)[i]
+        return (d["Kp"], d["N"]) if name.endswith("/kernel") else (d["N"],)
+    return tuple(shape)
+
+
 def param_offsets(cfg: ModelConfig, align=64):
     """name -> (offset, shape) in elements inside the flat buffer; every tensor starts on an
     `align`-element (256 B) boundary so TMA descriptors and float4 accesses are always legal."""
     out, off = {}, 0
     for name, shape, _ in param_specs(cfg):
         n = 1
-        for s in shape:
+        for s in storage_shape(cfg, name, shape):
             n *= s
         out[name] = (off, shape)
         off += (n + align - 1) // align * align
@@ -127,6 +191,19 @@ def param_offsets(cfg: ModelConfig, align=64):
 def flops_per_frame_fwd(cfg: ModelConfig):
     """GEMM FLOPs per input frame, forward (2 FLOP/MAC) — the figure of BASELINE.md §4."""
     F, D, H, G, V = cfg.num_features, cfg.num_units_dense, cfg.num_units_rnn, cfg.num_gates, cfg.num_classes
+    if cfg.used_model == "ds2":
+        # per INPUT frame: conv MACs per output position, output positions per input frame (time strides)
+        f, per_in, nin = 0.0, 1.0, None
+        for d in conv_plan(cfg):
+            per_in /= d["st"]
+            f += 2.0 * d["K"] * d["filters"] * d["Fo"] * per_in
+            nin = d["Fo"] * d["filters"]
+        rest = 0
+        for _ in range(cfg.num_layers_rnn):
+            rest += 2 * 2 * (nin + H) * G * H
+            nin = 2 * H
+        rest += 2 * nin * D + 2 * D * V
+        return f + rest * per_in
     f = 2 * F * D + (cfg.num_layers_dense - 1) * 2 * D * D
     nin = D
     for _ in range(cfg.num_layers_rnn):

@@ -33,6 +33,14 @@ def init_params(cfg: ModelConfig, seed=1, dtype=np.float32):
                 a[bad] = rng.standard_normal(int(bad.sum()))
                 bad = np.abs(a) > 2.0
             a = (a * 0.046875).astype(dtype)
+        elif init[0] == "glorot_normal":
+            _, fan_in, fan_out = init
+            a = rng.standard_normal(shape)
+            bad = np.abs(a) > 2.0
+            while bad.any():
+                a[bad] = rng.standard_normal(int(bad.sum()))
+                bad = np.abs(a) > 2.0
+            a = (a * (math.sqrt(2.0 / (fan_in + fan_out)) / 0.87962566103423978)).astype(dtype)
         else:
             _, fan_in, fan_out = init
             lim = math.sqrt(6.0 / (fan_in + fan_out))

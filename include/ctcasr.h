@@ -138,6 +138,31 @@ int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const float *wx, co
                      int compute, void *ws, size_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 2-D convolution layer of the 'ds2' front-end.  Replaces one iteration of the loop at
+ * asr/util/tf_contrib.py:123-134: tf.layers.conv2d(padding='SAME', activation=relu) followed by
+ * tf.minimum(., relu_cutoff); the image height is TIME and its width the feature axis
+ * (asr/model.py:157-158).  Conv dropout (rate 0.0, asr/params.py:89) is not implemented.
+ *   x  [T, B, F, x_pitch]   time-major, the C real channels first in every x_pitch-float pixel
+ *   w  [Kp, N]              TF's HWIO kernel [kt, kf, C, filters] flattened to rows
+ *                           (it*kf + jf)*C + c and zero-padded to Kp = roundup(kt*kf*C, 8) rows and
+ *                           N >= filters columns (N = the pitch of y; pad entries must be zero)
+ *   y  [To, B, Fo, N]       To = ceil(T/st), Fo = ceil(F/sf) (ctcasr_conv2d_out_dims)
+ *   act: 0 linear, 1 min(relu, cutoff).
+ * Backward: dy [To,B,Fo,N] (clobbered: becomes dz) -> dx [T,B,F,x_pitch] (nullable; pad channels
+ * are written as zeros), dw [Kp,N], db [N] (overwritten).
+ * ws: >= ctcasr_conv2d_workspace_bytes() (the patch matrix; rebuilt in the backward pass).
+ * -------------------------------------------------------------------------------------------- */
+int ctcasr_conv2d_out_dims(int T, int F, int kt, int kf, int st, int sf, int *To, int *Fo);
+size_t ctcasr_conv2d_workspace_bytes(int T, int B, int F, int C, int kt, int kf, int st, int sf);
+int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, const float *bias, float *y,
+                      int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
+                      int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream);
+int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, const float *y, float *dy,
+                      float *dx, float *dw, float *db,
+                      int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
+                      int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Plumbing around the path
  * -------------------------------------------------------------------------------------------- */
 /* Optional timing of the hot kernels with CUDA events recorded on the launching stream.

@@ -13,6 +13,13 @@ import numpy as np
 from . import ref
 
 _CELL = {"rnn_tanh": 0, "rnn_relu": 1, "lstm": 2, "gru": 3}
+# defaults of conv_layers (asr/util/tf_contrib.py:66-67); height = time, width = features
+CONV_KERNEL_SIZES = ((11, 41), (11, 21), (11, 21))
+CONV_STRIDES = ((2, 2), (1, 2), (1, 2))
+
+
+def _conv_names(cfg):
+    return ["conv/conv2d" if i == 0 else "conv/conv2d_%d" % i for i in range(len(cfg.conv_filters))]
 
 
 def _dense_names(cfg):
@@ -25,13 +32,25 @@ def forward(cfg, params, sequences, seq_length, training=False, seed=0, dtype=np
     T, B, _ = x.shape
     seq_length = np.asarray(seq_length, np.int32)
     rate = cfg.dense_dropout_rate if training else 0.0
-    cache = {"acts": [], "rnn": []}
+    cache = {"acts": [], "rnn": [], "conv": []}
     h = x.reshape(T * B, -1)
-    for li, name in enumerate(_dense_names(cfg)):
-        w, b = params[name + "/kernel"].astype(dtype), params[name + "/bias"].astype(dtype)
-        y = ref.dense_fwd(h, w, b, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + li)
-        cache["acts"].append((h, y))
-        h = y
+    if getattr(cfg, "used_model", "ds1") == "ds2":
+        # asr/model.py:154-161: expand_dims(sequences, 3) -> conv_layers; asr/util/tf_contrib.py:123-144
+        x4 = x.reshape(T, B, -1, 1)
+        for name, strides in zip(_conv_names(cfg), CONV_STRIDES):
+            w, b = params[name + "/kernel"].astype(dtype), params[name + "/bias"].astype(dtype)
+            y = ref.conv2d_fwd(x4, w, b, strides, act=1, cutoff=cfg.relu_cutoff)
+            cache["conv"].append((x4, y))
+            x4 = y
+        T = x4.shape[0]
+        seq_length = np.full(B, T, np.int32)     # tf.tile([shape(output)[1]], [batch]) (tf_contrib.py:144)
+        h = x4.reshape(T * B, -1)                # [T', B, Fo * filters] (tf_contrib.py:138)
+    else:
+        for li, name in enumerate(_dense_names(cfg)):
+            w, b = params[name + "/kernel"].astype(dtype), params[name + "/bias"].astype(dtype)
+            y = ref.dense_fwd(h, w, b, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + li)
+            cache["acts"].append((h, y))
+            h = y
     cell = _CELL[cfg.rnn_cell]
     use_len = not cfg.cudnn
     for l in range(cfg.num_layers_rnn):
@@ -48,6 +67,7 @@ def forward(cfg, params, sequences, seq_length, training=False, seed=0, dtype=np
     logits = ref.dense_fwd(y4, w, b, act=0)
     cache["lg"] = (y4,)
     cache["meta"] = (T, B, rate, seed)
+    cache["seq_length"] = seq_length
     return logits.reshape(T, B, -1), cache
 
 
@@ -57,7 +77,7 @@ def loss_and_grads(cfg, params, sequences, seq_length, labels, label_len, traini
     differentiates, asr/model.py:83).  Returns (loss, grads dict, logits, dlogits)."""
     logits, cache = forward(cfg, params, sequences, seq_length, training, seed, dtype)
     T, B, rate, seed = cache["meta"]
-    seq_length = np.asarray(seq_length, np.int32)
+    seq_length = cache["seq_length"]             # ds2: the conv length for every utterance
     loss_b, g, status = ref.ctc_loss(logits, labels, label_len, seq_length, blank=cfg.num_classes - 1)
     assert (status == 0).all(), status
     loss = loss_b.mean()
@@ -81,6 +101,14 @@ def loss_and_grads(cfg, params, sequences, seq_length, labels, label_len, traini
                                          dy.reshape(T, B, -1), cell, use_len=use_len)
         grads["rnn/l%d/wx" % l], grads["rnn/l%d/wh" % l], grads["rnn/l%d/bias" % l] = dwx, dwh, db
         dy = dx.reshape(T * B, -1)
+    if getattr(cfg, "used_model", "ds1") == "ds2":
+        names = _conv_names(cfg)
+        for li in reversed(range(len(names))):
+            x4, y = cache["conv"][li]
+            w = params[names[li] + "/kernel"].astype(dtype)
+            dy, grads[names[li] + "/kernel"], grads[names[li] + "/bias"] = ref.conv2d_bwd(
+                x4, w, y, dy.reshape(y.shape), CONV_STRIDES[li], act=1, cutoff=cfg.relu_cutoff, want_dx=li > 0)
+        return loss, grads, logits, dlogits
     names = _dense_names(cfg)
     for li in reversed(range(len(names))):
         h, y = cache["acts"][li]

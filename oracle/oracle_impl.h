@@ -490,3 +490,135 @@ int SUF(oracle_adam)(REAL *p, REAL *m, REAL *v, const REAL *g, size_t n, int ste
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * 2-D convolution layer of the 'ds2' front-end.  tf.layers.conv2d(padding='SAME',
+ * activation=relu) + tf.minimum(., relu_cutoff) as composed at asr/util/tf_contrib.py:123-134
+ * (conv dropout: rate 0.0 by default, asr/params.py:89 — not restated).
+ *
+ * The reference feeds [batch, time, features, 1] (asr/model.py:157-158): the image height is
+ * TIME, its width the feature axis.  Here activations are time-major like everywhere else in
+ * this oracle:  x [T, B, F, C]  ->  y [To, B, Fo, N],  kernel w [kt, kf, C, N] (TF's HWIO).
+ * TF 'SAME' padding [TF-RECALL, SURVEY.md Appendix A]: out = ceil(in / stride),
+ * pad_total = max((out - 1) * stride + k - in, 0), pad_before = pad_total / 2 (the odd unit goes
+ * after).
+ * ------------------------------------------------------------------------------------------ */
+static void SUF(conv_geom)(int in, int k, int s, int *out, int *pad0)
+{
+    *out = (in + s - 1) / s;
+    int total = (*out - 1) * s + k - in;
+    if (total < 0) total = 0;
+    *pad0 = total / 2;
+}
+
+int SUF(oracle_conv2d_fwd)(const REAL *x, const REAL *w, const REAL *bias, REAL *y,
+                           int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
+                           int act, REAL cutoff)
+{
+    int To, Fo, pt, pf;
+    SUF(conv_geom)(T, kt, st, &To, &pt);
+    SUF(conv_geom)(F, kf, sf, &Fo, &pf);
+#pragma omp parallel for collapse(2)
+    for (int to = 0; to < To; ++to)
+        for (int b = 0; b < B; ++b)
+            for (int fo = 0; fo < Fo; ++fo) {
+                REAL *yr = y + (((size_t)to * B + b) * Fo + fo) * N;
+                for (int n = 0; n < N; ++n) yr[n] = bias ? bias[n] : 0;
+                for (int it = 0; it < kt; ++it) {
+                    const int t = to * st - pt + it;
+                    if (t < 0 || t >= T) continue;
+                    for (int jf = 0; jf < kf; ++jf) {
+                        const int f = fo * sf - pf + jf;
+                        if (f < 0 || f >= F) continue;
+                        const REAL *xr = x + (((size_t)t * B + b) * F + f) * C;
+                        const REAL *wr = w + ((size_t)it * kf + jf) * C * N;
+                        for (int c = 0; c < C; ++c) {
+                            const REAL xv = xr[c];
+                            for (int n = 0; n < N; ++n) yr[n] += xv * wr[(size_t)c * N + n];
+                        }
+                    }
+                }
+                if (act == 1)
+                    for (int n = 0; n < N; ++n) {
+                        REAL v = yr[n];
+                        v = v > 0 ? v : 0;
+                        yr[n] = v < cutoff ? v : cutoff;
+                    }
+            }
+    return 0;
+}
+
+/* Backward given the layer's output y (mask 0 < y < cutoff): dy [To,B,Fo,N] -> dx [T,B,F,C]
+ * (nullable), dw [kt,kf,C,N], db [N]; all overwritten. */
+int SUF(oracle_conv2d_bwd)(const REAL *x, const REAL *w, const REAL *y, const REAL *dy,
+                           REAL *dx, REAL *dw, REAL *db,
+                           int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
+                           int act, REAL cutoff)
+{
+    int To, Fo, pt, pf;
+    SUF(conv_geom)(T, kt, st, &To, &pt);
+    SUF(conv_geom)(F, kf, sf, &Fo, &pf);
+    const size_t rows = (size_t)To * B * Fo;
+    REAL *dz = (REAL *)malloc(sizeof(REAL) * rows * N);
+    for (size_t i = 0; i < rows * N; ++i) {
+        REAL g = dy[i];
+        if (act == 1 && !(y[i] > 0 && y[i] < cutoff)) g = 0;
+        dz[i] = g;
+    }
+    for (int n = 0; n < N; ++n) {
+        REAL s = 0;
+        for (size_t r = 0; r < rows; ++r) s += dz[r * N + n];
+        db[n] = s;
+    }
+    /* dw: one (it, jf) tap per thread -> disjoint outputs, deterministic */
+#pragma omp parallel for collapse(2)
+    for (int it = 0; it < kt; ++it)
+        for (int jf = 0; jf < kf; ++jf) {
+            REAL *dwr = dw + ((size_t)it * kf + jf) * C * N;
+            for (size_t i = 0; i < (size_t)C * N; ++i) dwr[i] = 0;
+            for (int to = 0; to < To; ++to) {
+                const int t = to * st - pt + it;
+                if (t < 0 || t >= T) continue;
+                for (int b = 0; b < B; ++b)
+                    for (int fo = 0; fo < Fo; ++fo) {
+                        const int f = fo * sf - pf + jf;
+                        if (f < 0 || f >= F) continue;
+                        const REAL *xr = x + (((size_t)t * B + b) * F + f) * C;
+                        const REAL *gz = dz + (((size_t)to * B + b) * Fo + fo) * N;
+                        for (int c = 0; c < C; ++c)
+                            for (int n = 0; n < N; ++n) dwr[(size_t)c * N + n] += xr[c] * gz[n];
+                    }
+            }
+        }
+    if (dx) {
+        /* gather form: every input element sums the taps that touched it */
+#pragma omp parallel for collapse(2)
+        for (int t = 0; t < T; ++t)
+            for (int b = 0; b < B; ++b)
+                for (int f = 0; f < F; ++f) {
+                    REAL *dxr = dx + (((size_t)t * B + b) * F + f) * C;
+                    for (int c = 0; c < C; ++c) dxr[c] = 0;
+                    for (int it = 0; it < kt; ++it) {
+                        const int tn = t + pt - it;
+                        if (tn < 0 || tn % st) continue;
+                        const int to = tn / st;
+                        if (to >= To) continue;
+                        for (int jf = 0; jf < kf; ++jf) {
+                            const int fn = f + pf - jf;
+                            if (fn < 0 || fn % sf) continue;
+                            const int fo = fn / sf;
+                            if (fo >= Fo) continue;
+                            const REAL *gz = dz + (((size_t)to * B + b) * Fo + fo) * N;
+                            const REAL *wr = w + ((size_t)it * kf + jf) * C * N;
+                            for (int c = 0; c < C; ++c) {
+                                REAL s = 0;
+                                for (int n = 0; n < N; ++n) s += gz[n] * wr[(size_t)c * N + n];
+                                dxr[c] += s;
+                            }
+                        }
+                    }
+                }
+    }
+    free(dz);
+    return 0;
+}

@@ -153,6 +153,42 @@ def birnn_bwd(x, seq_len, wx, wh, y, gates, cst, dy, cell, use_len=True, want_dx
     return dx, dwx, dwh, db
 
 
+def conv_out_size(n, k, s):
+    """TF 'SAME': (output size, pad_before)."""
+    out = -(-n // s)
+    return out, max((out - 1) * s + k - n, 0) // 2
+
+
+def conv2d_fwd(x, w, b, strides, act=1, cutoff=20.0):
+    """x [T,B,F,C], w [kt,kf,C,N] (TF HWIO, height = time), 'SAME' -> y [To,B,Fo,N]."""
+    dtype = x.dtype
+    suf, cr = _suf(dtype)
+    x, w = _c(x, dtype), _c(w, dtype)
+    b = _c(b, dtype) if b is not None else None
+    T, B, F, C = x.shape
+    kt, kf, C2, N = w.shape
+    assert C2 == C
+    To, Fo = conv_out_size(T, kt, strides[0])[0], conv_out_size(F, kf, strides[1])[0]
+    y = np.zeros((To, B, Fo, N), dtype)
+    getattr(lib(), "oracle_conv2d_fwd" + suf)(_p(x), _p(w), _p(b), _p(y), T, B, F, C, kt, kf, strides[0], strides[1],
+                                              N, act, cr(cutoff))
+    return y
+
+
+def conv2d_bwd(x, w, y, dy, strides, act=1, cutoff=20.0, want_dx=True):
+    dtype = x.dtype
+    suf, cr = _suf(dtype)
+    x, w, y, dy = (_c(a, dtype) for a in (x, w, y, dy))
+    T, B, F, C = x.shape
+    kt, kf, _, N = w.shape
+    dx = np.zeros_like(x) if want_dx else None
+    dw = np.zeros_like(w)
+    db = np.zeros(N, dtype)
+    getattr(lib(), "oracle_conv2d_bwd" + suf)(_p(x), _p(w), _p(y), _p(dy), _p(dx), _p(dw), _p(db), T, B, F, C, kt, kf,
+                                              strides[0], strides[1], N, act, cr(cutoff))
+    return dx, dw, db
+
+
 def adam(p, m, v, g, step, lr=1e-5, b1=0.9, b2=0.999, eps=1e-8):
     """In-place TF1 Adam on flat arrays."""
     dtype = p.dtype

@@ -73,11 +73,40 @@ def _dynamic_rnn(cfg, x, lengths, kernel, bias):
     return torch.stack(outs, 0)
 
 
+CONV_STRIDES = ((2, 2), (1, 2), (1, 2))                  # asr/util/tf_contrib.py:67
+
+
+def _conv_same(x, w, b, strides):
+    """tf.layers.conv2d(padding='SAME') on NCHW x [B,C,T,F] with an HWIO kernel w [kt,kf,C,N]."""
+    kt, kf = w.shape[0], w.shape[1]
+    pads = []
+    for n, k, s in ((x.shape[3], kf, strides[1]), (x.shape[2], kt, strides[0])):     # F.pad: last dim first
+        out = -(-n // s)
+        total = max((out - 1) * s + k - n, 0)
+        pads += [total // 2, total - total // 2]
+    return F.conv2d(F.pad(x, pads), w.permute(3, 2, 0, 1), b, stride=strides)
+
+
+def conv_front_end(cfg, p, sequences):
+    """asr/model.py:154-161 + asr/util/tf_contrib.py:123-144: [B,T,F] -> ([T',B,Fo*filters], T')."""
+    x = sequences.unsqueeze(1)                            # [B,1,T,F]: height = time, width = features
+    for i in range(len(cfg.conv_filters)):
+        name = "conv/conv2d" if i == 0 else "conv/conv2d_%d" % i
+        x = torch.clamp(torch.relu(_conv_same(x, p[name + "/kernel"], p[name + "/bias"], CONV_STRIDES[i])),
+                        max=cfg.relu_cutoff)
+    B, C, T, Fo = x.shape
+    return x.permute(2, 0, 3, 1).reshape(T, B, Fo * C), T      # NHWC reshape [B,T,Fo*C], then time-major
+
+
 def inference(cfg, p, sequences, seq_length):
     """sequences [B,T,F] -> logits [T,B,V] (dropout off; parity / eval mode)."""
-    x = sequences.transpose(0, 1)                         # time-major inside, like our layout
-    for name in _dense_names(cfg):
-        x = torch.clamp(torch.relu(x @ p[name + "/kernel"] + p[name + "/bias"]), max=cfg.relu_cutoff)
+    if getattr(cfg, "used_model", "ds1") == "ds2":
+        x, T = conv_front_end(cfg, p, sequences)
+        seq_length = torch.full_like(seq_length, T)
+    else:
+        x = sequences.transpose(0, 1)                     # time-major inside, like our layout
+        for name in _dense_names(cfg):
+            x = torch.clamp(torch.relu(x @ p[name + "/kernel"] + p[name + "/bias"]), max=cfg.relu_cutoff)
     lengths = None if cfg.cudnn else seq_length
     H, G = cfg.num_units_rnn, {"lstm": 4, "gru": 3}.get(cfg.rnn_cell, 1)
     T = x.shape[0]
@@ -109,6 +138,8 @@ def loss(cfg, logits, seq_length, labels, label_len):
 
 def train_step_grads(cfg, p, sequences, seq_length, labels, label_len):
     logits = inference(cfg, p, sequences, seq_length)
+    if getattr(cfg, "used_model", "ds1") == "ds2":
+        seq_length = torch.full_like(seq_length, logits.shape[0])
     mean_loss, _ = loss(cfg, logits, seq_length, labels, label_len)
     for v in p.values():
         v.grad = None

@@ -289,11 +289,12 @@ def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL):
         for b in range(B):
             x[b, sl[b]:] = 0
     model = CTCModel(cfg, params=params)
-    logits, _ = model.inference_fn(torch.from_numpy(x), torch.from_numpy(sl), training=False)
-    loss = model.loss_fn(logits, torch.from_numpy(sl), (torch.from_numpy(lab), torch.from_numpy(ll)))
+    logits, sl_out = model.inference_fn(torch.from_numpy(x), torch.from_numpy(sl), training=False)
+    loss = model.loss_fn(logits, sl_out, (torch.from_numpy(lab), torch.from_numpy(ll)))
     model.backward()
     torch.cuda.synchronize()
     oloss, ograds, ologits, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll)
+    sl = sl_out.cpu().numpy()                          # ds2: the conv length for every utterance
     assert rel_err(logits.cpu().numpy(), ologits) < RTOL
     assert abs(float(loss) - oloss) / abs(oloss) < RTOL
     got = model.grads_numpy()

@@ -180,3 +180,50 @@ def test_gru_layer_vs_torch_nn_gru(use_len):
     np.testing.assert_allclose(dwh[0], gru.weight_hh_l0.grad.numpy().T, atol=1e-12)
     np.testing.assert_allclose(dwx[:, 3 * H:], gru.weight_ih_l0_reverse.grad.numpy().T, atol=1e-12)
     np.testing.assert_allclose(db[6 * H:7 * H], gru.bias_hh_l0.grad.numpy()[2 * H:], atol=1e-12)
+
+
+# ---- ds2 conv front-end (asr/util/tf_contrib.py:64-146) -------------------------------------------
+@pytest.mark.parametrize("dims", [(13, 2, 10, 1, 4, 11, 5, 2, 2), (9, 3, 8, 3, 5, 3, 5, 1, 2), (7, 1, 7, 2, 3, 11, 21, 1, 2),
+                                  (20, 2, 80, 1, 4, 11, 41, 2, 2)])
+def test_conv2d_same_vs_torch_conv2d(dims):
+    """The C conv layer (fwd + bwd) against torch F.conv2d + autograd with TF 'SAME' padding made
+    explicit (odd pad unit after), incl. the reference's (11,41)/(2,2) and (11,21)/(1,2) geometries."""
+    import torch.nn.functional as Fn
+    T, B, F, C, N, kt, kf, st, sf = dims
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((T, B, F, C)); w = rng.standard_normal((kt, kf, C, N)) * 0.3; b = rng.standard_normal(N) * 0.1
+    y = ref.conv2d_fwd(x, w, b, (st, sf), cutoff=1.0)
+    assert 0.05 < (y >= 1.0).mean() < 0.95 and (y <= 0).any()          # both kinks are exercised
+    dy = rng.standard_normal(y.shape)
+    dx, dw, db = ref.conv2d_bwd(x, w, y, dy, (st, sf), cutoff=1.0)
+    xt = torch.tensor(x).permute(1, 3, 0, 2).requires_grad_(True)       # [B,C,T,F]
+    wt = torch.tensor(w).requires_grad_(True)
+    bt = torch.tensor(b).requires_grad_(True)
+    yt = torch.clamp(torch.relu(torch_ref._conv_same(xt, wt, bt, (st, sf))), max=1.0).permute(2, 0, 3, 1)
+    assert tuple(yt.shape) == y.shape == (-(-T // st), B, -(-F // sf), N)
+    np.testing.assert_allclose(y, yt.detach().numpy(), atol=1e-12)
+    (yt * torch.tensor(dy)).sum().backward()
+    np.testing.assert_allclose(dx, xt.grad.permute(2, 0, 3, 1).numpy(), atol=1e-12)
+    np.testing.assert_allclose(dw, wt.grad.numpy(), atol=1e-11)
+    np.testing.assert_allclose(db, bt.grad.numpy(), atol=1e-11)
+
+
+def test_ds2_whole_path_vs_torch_autograd():
+    cfg = ModelConfig(used_model="ds2", conv_filters=(3, 4, 64), num_units_dense=24, num_units_rnn=16, num_layers_rnn=2,
+                      rnn_cell="lstm", num_features=12, cudnn=False, dense_dropout_rate=0.0)
+    params = synthetic.init_params(cfg, seed=1, dtype=np.float64)
+    assert params["conv/conv2d/kernel"].shape == (11, 41, 1, 3) and params["conv/conv2d_2/kernel"].shape == (11, 21, 4, 64)
+    assert params["rnn/l0/wx"].shape[0] == 2 * 64                      # 12 features -> 6 -> 3 -> 2 bins x 64 filters
+    for k in params:
+        if k.endswith("bias"):
+            params[k] = np.random.default_rng(5).standard_normal(params[k].shape) * 0.1
+    x, sl, lab, ll = _batch(cfg, B=3, T=15)
+    loss, grads, logits, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll)
+    assert logits.shape == (8, 3, 29)                                  # ceil(15 / 2) frames reach the RNN and CTC
+    p = torch_ref.params_to_torch(params, torch.float64)
+    tloss, tgrads, tlogits = torch_ref.train_step_grads(
+        cfg, p, torch.tensor(x), torch.tensor(sl), torch.tensor(lab), torch.tensor(ll))
+    np.testing.assert_allclose(logits, tlogits.numpy(), atol=1e-10)
+    np.testing.assert_allclose(loss, float(tloss), rtol=1e-10)
+    for k in params:
+        np.testing.assert_allclose(grads[k], tgrads[k].numpy(), atol=1e-9, err_msg=k)
