@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=CFG2_B)
     ap.add_argument("--frames", type=int, default=CFG2_T)
     ap.add_argument("--units", type=int, default=2048, help="debug: shrink D and H")
+    ap.add_argument("--model", default="ds1", choices=["ds1", "ds2"],
+                    help="front-end: ds1 = 3 dense layers (BASELINE configs[1], the default), ds2 = 3 conv layers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames per utterance in the CPU sample (0 = auto)")
     return ap.parse_args()
@@ -175,8 +177,11 @@ def run_ours(args):
     if args.workload == "ctc":
         return run_ctc(args, torch, lib, ops, synthetic, peaks, rank, world)
 
-    cfg = ModelConfig(**dict(CFG2, num_units_dense=args.units, num_units_rnn=args.units, compute=args.compute))
+    cfg = ModelConfig(**dict(CFG2, num_units_dense=args.units, num_units_rnn=args.units, compute=args.compute,
+                             used_model=args.model))
     B, T, L = args.batch, args.frames, min(CFG2_L, max(1, args.frames // 4))
+    from ctc_asr_b200.params import conv_out_frames
+    T_rnn = conv_out_frames(cfg, T)                      # ds2: the conv stack halves the frame rate
     model = CTCModel(cfg, seed=1)
     x, sl, lab, ll = synthetic.fixed_batch(B, T, L, seed=rank)
     hx, hsl = torch.from_numpy(x).pin_memory(), torch.from_numpy(sl).pin_memory()
@@ -240,11 +245,11 @@ def run_ours(args):
     act_bytes = B * 8 * H * 4 * 2 + B * 2 * H * 4 * 2
     lstm_launches = prof_n[0] + prof_n[1]
     lstm_ms = prof_ms[0] + prof_ms[1]
-    lstm_bytes = (w_bytes + act_bytes) * T * lstm_launches
+    lstm_bytes = (w_bytes + act_bytes) * T_rnn * lstm_launches
     lstm_gbs = lstm_bytes / (lstm_ms * 1e-3) / 1e9 if lstm_ms > 0 else 0.0
     # ---- second class: the tcgen05 GEMMs (everything GEMM-shaped but the recurrence and the 29-class layer)
-    rec_flops = 2 * (cfg.num_layers_rnn * 2 * 2 * H * 4 * H)      # recurrent matvec fwd + bwd, per frame
-    tc_flops = (3.0 * flops_per_frame_fwd(cfg) - rec_flops - 3 * 2 * D * cfg.num_classes) * B * T * K
+    rec_flops = 2 * (cfg.num_layers_rnn * 2 * 2 * H * 4 * H) * T_rnn / T     # recurrent matvec fwd + bwd, per input frame
+    tc_flops = (3.0 * flops_per_frame_fwd(cfg) - rec_flops - 3 * 2 * D * cfg.num_classes * T_rnn / T) * B * T * K
     gemm_tflops = tc_flops / (prof_ms[2] * 1e-3) / 1e12 if prof_ms[2] > 0 else 0.0
     mma_per_mac = {"bf16x3": 3.0, "tf32": 2.0, "fp32": 1.0}[args.compute]
     gemm_peak = peaks["bf16_tflops_sustained"] / mma_per_mac
@@ -256,9 +261,11 @@ def run_ours(args):
         "metric": "audio-frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.compute, "data": "synthetic",
-        "config": {"workload": "cfg2: 3 dense + 2 BiLSTM-%d + 2 dense (3d2r2d), per-GPU B=%d x T=%d frames x 80 features, "
+        "config": {"workload": "cfg2: %s + 2 BiLSTM-%d + 2 dense (3%s2r2d), per-GPU B=%d x T=%d frames x 80 features, "
                                "L=%d labels, fwd + CTC + bwd + %sAdam, dense dropout 0.1" % (
-                                   args.units, B, T, L, "NCCL all-reduce + " if world > 1 else ""),
+                                   "3 dense" if args.model == "ds1" else "3 conv (ds2 front-end, RNN at %d frames)" % T_rnn,
+                                   args.units, "d" if args.model == "ds1" else "c", B, T, L,
+                                   "NCCL all-reduce + " if world > 1 else ""),
                    "global_batch": gb, "params": model.num_params,
                    "arithmetic": {"bf16x3": "fp32 storage; GEMMs and recurrence as 3 (6 for ReLU-kinked layers) bf16 tcgen05 products "
                                             "of split operands, fp32 TMEM accumulation (fp32-level accuracy)",

@@ -88,10 +88,12 @@ struct Epilogue {
     int ldm = 0;
 };
 
-__device__ __forceinline__ float epilogue_apply(const Epilogue &e, float acc, int m, int n, int N,
-                                                float c_old)
+// MODE is a compile-time copy of e.mode so that a caller that has already branched on it (the tcgen05
+// epilogue) gets straight-line code; epilogue_apply() is the run-time dispatch used by the SIMT kernels.
+template <int MODE>
+__device__ __forceinline__ float epilogue_apply_m(const Epilogue &e, float acc, int m, int n, int N, float c_old)
 {
-    if (e.mode == EPI_BIAS_ACT) {
+    if (MODE == EPI_BIAS_ACT) {
         float v = acc + (e.bias ? e.bias[n] : 0.f);
         if (e.act == 1) v = fminf(fmaxf(v, 0.f), e.cutoff);
         if (e.drop_rate > 0.f) {
@@ -100,7 +102,7 @@ __device__ __forceinline__ float epilogue_apply(const Epilogue &e, float acc, in
         }
         return v;
     }
-    if (e.mode == EPI_MASK) {
+    if (MODE == EPI_MASK) {
         const float inv_keep = e.drop_rate > 0.f ? 1.f / (1.f - e.drop_rate) : 1.f;
         const float y = e.mask_y[(size_t)m * e.ldm + n];
         bool pass = e.drop_rate > 0.f ? drop_keep(e.seed, (uint64_t)m * N + n, e.drop_rate) : true;
@@ -108,6 +110,14 @@ __device__ __forceinline__ float epilogue_apply(const Epilogue &e, float acc, in
         return pass ? acc * inv_keep : 0.f;
     }
     return e.accumulate ? acc + c_old : acc;
+}
+
+__device__ __forceinline__ float epilogue_apply(const Epilogue &e, float acc, int m, int n, int N,
+                                                float c_old)
+{
+    if (e.mode == EPI_BIAS_ACT) return epilogue_apply_m<EPI_BIAS_ACT>(e, acc, m, n, N, c_old);
+    if (e.mode == EPI_MASK) return epilogue_apply_m<EPI_MASK>(e, acc, m, n, N, c_old);
+    return epilogue_apply_m<EPI_STORE>(e, acc, m, n, N, c_old);
 }
 
 }  // namespace ctcasr

@@ -47,64 +47,128 @@ static int make_geom(int T, int B, int F, int C, int xpitch, int kt, int kf, int
     return CTCASR_OK;
 }
 
-// one CTA per output position (grid-stride), threads along the patch
-__global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ x, float *__restrict__ col, const Geom g, size_t rows)
+// exact n / d for n, d < 2^16 (one IMAD.HI): mul = ceil(2^32 / d)
+struct FastDiv { uint32_t mul, d; };
+static FastDiv make_fastdiv(int d)
 {
-    for (size_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    FastDiv f;
+    f.d = (uint32_t)d;
+    f.mul = d <= 1 ? 0u : (uint32_t)(0xffffffffull / (uint64_t)d) + 1u;
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) { return f.d <= 1 ? n : __umulhi(n, f.mul); }
+
+// One warp per output position (grid-stride), lanes along the patch in units of four columns: one 16-B
+// store per lane and iteration.  VEC (C and the input pitch multiples of 4): the four columns are four
+// channels of one tap -> one 16-B load; otherwise four scalar gathers.
+template <bool VEC>
+__global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ x, float *__restrict__ col, const Geom g, size_t rows,
+                                                     const FastDiv dC, const FastDiv dkf)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+    const int kq = g.Kp >> 2;
+    for (size_t r = warp0; r < rows; r += nwarps) {
         const int fo = (int)(r % g.Fo);
         const size_t q = r / g.Fo;
         const int b = (int)(q % g.B), to = (int)(q / g.B);
         const int t0 = to * g.st - g.pt, f0 = fo * g.sf - g.pf;
-        float *crow = col + r * g.Kp;
-        for (int k = threadIdx.x; k < g.Kp; k += blockDim.x) {
-            float v = 0.f;
-            if (k < g.K) {
-                const int c = k % g.C, q2 = k / g.C;
-                const int jf = q2 % g.kf, it = q2 / g.kf;
-                const int t = t0 + it, f = f0 + jf;
-                if (t >= 0 && t < g.T && f >= 0 && f < g.F)
-                    v = __ldg(x + (((size_t)t * g.B + b) * g.F + f) * g.xpitch + c);
+        float4 *crow = reinterpret_cast<float4 *>(col + r * g.Kp);
+        for (int j = lane; j < kq; j += 32) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint32_t k = 4u * j;
+            if (VEC) {
+                if (k < (uint32_t)g.K) {
+                    const uint32_t q2 = fdiv(k, dC), c = k - q2 * g.C;
+                    const uint32_t it = fdiv(q2, dkf), jf = q2 - it * g.kf;
+                    const int t = t0 + (int)it, f = f0 + (int)jf;
+                    if (t >= 0 && t < g.T && f >= 0 && f < g.F) {
+                        const float4 w = __ldg(reinterpret_cast<const float4 *>(x + (((size_t)t * g.B + b) * g.F + f) * g.xpitch + c));
+                        v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t ke = k + e;
+                    if (ke < (uint32_t)g.K) {
+                        const uint32_t q2 = fdiv(ke, dC), c = ke - q2 * g.C;
+                        const uint32_t it = fdiv(q2, dkf), jf = q2 - it * g.kf;
+                        const int t = t0 + (int)it, f = f0 + (int)jf;
+                        if (t >= 0 && t < g.T && f >= 0 && f < g.F) v[e] = __ldg(x + (((size_t)t * g.B + b) * g.F + f) * g.xpitch + c);
+                    }
+                }
             }
-            crow[k] = v;
+            crow[j] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
 
-// one thread per input element (t, b, f, c'), c' over the whole pitch (pad channels get 0)
+// One thread per W consecutive channels of an input pixel (t, b, f) over the whole pitch (pad channels
+// get 0): it sums, in a fixed order, the taps (it, jf) whose output position (to, fo) exists.
+template <int W>
 __global__ void __launch_bounds__(256) col2im_kernel(const float *__restrict__ dcol, float *__restrict__ dx, const Geom g, size_t total)
 {
+    const int cq = g.xpitch / W;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % g.xpitch);
-        const size_t r = i / g.xpitch;
-        float s = 0.f;
+        const int c = (int)(i % cq) * W;
+        const size_t r = i / cq;
+        float s[W];
+#pragma unroll
+        for (int e = 0; e < W; ++e) s[e] = 0.f;
         if (c < g.C) {
             const int f = (int)(r % g.F);
             const size_t q = r / g.F;
             const int b = (int)(q % g.B), t = (int)(q / g.B);
-            for (int it = 0; it < g.kt; ++it) {
-                const int tn = t + g.pt - it;
-                if (tn < 0) break;
-                if (tn % g.st) continue;
-                const int to = tn / g.st;
+            const int tn0 = t + g.pt, fn0 = f + g.pf;
+            for (int it = tn0 % g.st; it < g.kt && it <= tn0; it += g.st) {
+                const int to = (tn0 - it) / g.st;
                 if (to >= g.To) continue;
-                for (int jf = 0; jf < g.kf; ++jf) {
-                    const int fn = f + g.pf - jf;
-                    if (fn < 0) break;
-                    if (fn % g.sf) continue;
-                    const int fo = fn / g.sf;
+                const int jf0 = fn0 % g.sf;
+                int fo = (fn0 - jf0) / g.sf;
+                const float *base = dcol + ((size_t)to * g.B + b) * g.Fo * g.Kp + (size_t)it * g.kf * g.C + c;
+                for (int jf = jf0; jf < g.kf && fo >= 0; jf += g.sf, --fo) {
                     if (fo >= g.Fo) continue;
-                    s += __ldg(dcol + (((size_t)to * g.B + b) * g.Fo + fo) * g.Kp + (it * g.kf + jf) * g.C + c);
+                    const float *p = base + (size_t)fo * g.Kp + jf * g.C;
+                    if (W == 4) {
+                        const float4 w = __ldg(reinterpret_cast<const float4 *>(p));
+                        s[0] += w.x; s[1] += w.y; s[2] += w.z; s[3] += w.w;
+                    } else {
+                        s[0] += __ldg(p);
+                    }
                 }
             }
         }
-        dx[i] = s;
+        if (W == 4) *reinterpret_cast<float4 *>(dx + r * g.xpitch + c) = make_float4(s[0], s[1], s[2], s[3]);
+        else dx[r * g.xpitch + c] = s[0];
     }
 }
 
-static int grid_for(size_t work_items)
+static int launch_im2col(const float *x, float *col, const Geom &g, size_t rows, cudaStream_t stream)
 {
-    const size_t cap = (size_t)148 * 16;
-    return (int)(work_items < cap ? (work_items ? work_items : 1) : cap);
+    CTCASR_REQUIRE(g.Kp < 65536, "conv2d: patch of %d elements", g.K);
+    const size_t blocks = (rows + 7) / 8;
+    const int grid = (int)(blocks < (size_t)148 * 16 ? blocks : (size_t)148 * 16);
+    const FastDiv dC = make_fastdiv(g.C), dkf = make_fastdiv(g.kf);
+    if (g.C % 4 == 0 && g.xpitch % 4 == 0 && ((uintptr_t)x & 15) == 0)
+        im2col_kernel<true><<<grid, 256, 0, stream>>>(x, col, g, rows, dC, dkf);
+    else
+        im2col_kernel<false><<<grid, 256, 0, stream>>>(x, col, g, rows, dC, dkf);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+static int launch_col2im(const float *dcol, float *dx, const Geom &g, cudaStream_t stream)
+{
+    const bool vec = g.C % 4 == 0 && g.xpitch % 4 == 0 && ((uintptr_t)dx & 15) == 0;
+    const size_t total = (size_t)g.T * g.B * g.F * (g.xpitch / (vec ? 4 : 1));
+    const size_t blocks = (total + 255) / 256;
+    const int grid = (int)(blocks < (size_t)148 * 32 ? (blocks ? blocks : 1) : (size_t)148 * 32);
+    if (vec) col2im_kernel<4><<<grid, 256, 0, stream>>>(dcol, dx, g, total);
+    else col2im_kernel<1><<<grid, 256, 0, stream>>>(dcol, dx, g, total);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
 }
 
 }  // namespace conv
@@ -142,8 +206,7 @@ extern "C" int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, co
     if (!ws || ws_bytes < need) return fail(CTCASR_ERR_WORKSPACE, "conv2d_fwd: workspace %zu < %zu", ws_bytes, need);
     if (int rcs = gemm_scratch_check(compute, 1, (int)rows, N, g.Kp)) return rcs;
     float *col = reinterpret_cast<float *>(ws);
-    conv::im2col_kernel<<<conv::grid_for(rows), 256, 0, stream>>>(x, col, g, rows);
-    CTCASR_LAUNCH_CHECK();
+    if (int rc = conv::launch_im2col(x, col, g, rows, stream)) return rc;
     GemmArgs a;
     a.A[0] = col; a.B[0] = w; a.C[0] = y; a.M = (int)rows; a.N = N; a.K = g.Kp; a.lda = g.Kp; a.ldb = N; a.ldc = N;
     a.epi.mode = EPI_BIAS_ACT; a.epi.bias = bias; a.epi.act = act; a.epi.cutoff = cutoff;
@@ -172,8 +235,7 @@ extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, co
     if (rc != CTCASR_OK) return rc;
     rc = colsum(dy, (int)rows, N, N, db, stream);
     if (rc != CTCASR_OK) return rc;
-    conv::im2col_kernel<<<conv::grid_for(rows), 256, 0, stream>>>(x, col, g, rows);
-    CTCASR_LAUNCH_CHECK();
+    if ((rc = conv::launch_im2col(x, col, g, rows, stream)) != CTCASR_OK) return rc;
     {   // dW[Kp,N] = col^T dz   (rows K..Kp of col^T are zero -> the pad rows of dW are zero)
         GemmArgs a;
         a.A[0] = col; a.B[0] = dy; a.C[0] = dw; a.ta = 1; a.M = g.Kp; a.N = N; a.K = (int)rows; a.lda = g.Kp; a.ldb = N; a.ldc = N;
@@ -185,9 +247,7 @@ extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, co
         a.A[0] = dy; a.B[0] = w; a.C[0] = col; a.tb = 1; a.M = (int)rows; a.N = g.Kp; a.K = N; a.lda = N; a.ldb = N; a.ldc = g.Kp;
         rc = gemm(a, compute, stream);
         if (rc != CTCASR_OK) return rc;
-        const size_t total = (size_t)T * B * F * x_pitch;
-        conv::col2im_kernel<<<conv::grid_for((total + 255) / 256), 256, 0, stream>>>(col, dx, g, total);
-        CTCASR_LAUNCH_CHECK();
+        if ((rc = conv::launch_col2im(col, dx, g, stream)) != CTCASR_OK) return rc;
     }
     return CTCASR_OK;
 }

@@ -128,11 +128,17 @@ int gemm_simt(const GemmArgs &g, cudaStream_t stream)
     else if (g.tb) gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(g, sk);
     else gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(g, sk);
     CTCASR_LAUNCH_CHECK();
-    if (sk.S > 1) {
-        const size_t total = (size_t)g.M * g.N * g.nz;
-        splitk_reduce_kernel<<<(int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, stream>>>(g, sk);
-        CTCASR_LAUNCH_CHECK();
-    }
+    if (sk.S > 1) return splitk_reduce(g, sk.S, sk.part, stream);
+    return CTCASR_OK;
+}
+
+int splitk_reduce(const GemmArgs &g, int S, float *part, cudaStream_t stream)
+{
+    SplitK sk;
+    sk.S = S; sk.part = part;
+    const size_t total = (size_t)g.M * g.N * g.nz;
+    splitk_reduce_kernel<<<(int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, stream>>>(g, sk);
+    CTCASR_LAUNCH_CHECK();
     return CTCASR_OK;
 }
 

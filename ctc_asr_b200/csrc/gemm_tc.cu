@@ -45,6 +45,8 @@ constexpr int BM = 128, BN = 256, BK = 32;
 constexpr int NACC = 2;
 constexpr int GROUP_M = 16;
 constexpr int NTHREADS = 192;
+constexpr int STG_LD = 36;                                      // epilogue staging tile: 32 rows x 36 floats per warp
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
 
 enum { MODE_TF32 = 1, MODE_BF16X3 = 2, MODE_BF16X6 = 3 };     // bf16 modes: value = pieces per operand
 
@@ -61,7 +63,7 @@ struct Cfg {
     static constexpr int MN_BOX = 128 / ESZ;                    // m|n elements per 128-B row
     static constexpr int MN_BOX_BYTES = BK * 128;               // one MN-major box: 32 k-rows x 128 B
     static constexpr int NPROD = MODE == MODE_TF32 ? 1 : (MODE == MODE_BF16X3 ? 3 : 6);
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
     // per k-step advance of the descriptor start address (bytes)
     static constexpr int KMAJ_STEP = UMMA_K * ESZ;              // inside the swizzled row
     static constexpr int MNMAJ_STEP = UMMA_K * 128;             // UMMA_K rows of 128 B
@@ -72,6 +74,10 @@ struct Params {
     float *C[2];
     Epilogue epi;
     int tiles_m, tiles_n, kblocks, num_tiles;
+    // split-K (few output tiles, long contraction): work unit u = slice * num_tiles + tile; slice s covers
+    // k-blocks [s * kb_per_split, ...) and stores its raw partial tile to part[s][z][M][N]
+    int splits, kb_per_split;
+    float *part;
 };
 
 __device__ __forceinline__ void decode_tile(const Params &p, int t, int &z, int &mb, int &nb)
@@ -98,6 +104,37 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t addr, bool mn_major)
                     : ptx::make_smem_desc(addr, 16, 512, 4);                             // SWIZZLE_64B
 }
 
+// Epilogue store of one 32 x 32 accumulator block from its staging tile: this lane owns columns
+// n .. n+3 of rows sub_r, sub_r + 4, ...
+enum { EK_RAW = 0, EK_ACC = 1, EK_BIAS_ACT = 2, EK_MASK = 3 };
+template <int EK>
+__device__ __forceinline__ void store_rows(const Params &p, const float *stg, float *base, int ld, int m0, int n, int sub_r, int sub_n)
+{
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + sub_r, m = m0 + rr;
+        if (m >= p.M) break;
+        const float4 v = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
+        float *cp = base + (size_t)m * ld + n;
+        float4 o = v;
+        if (EK == EK_ACC) {
+            const float4 old = *reinterpret_cast<const float4 *>(cp);
+            o = make_float4(v.x + old.x, v.y + old.y, v.z + old.z, v.w + old.w);
+        } else if (EK == EK_BIAS_ACT) {
+            o.x = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.x, m, n + 0, p.N, 0.f);
+            o.y = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.y, m, n + 1, p.N, 0.f);
+            o.z = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.z, m, n + 2, p.N, 0.f);
+            o.w = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.w, m, n + 3, p.N, 0.f);
+        } else if (EK == EK_MASK) {
+            o.x = epilogue_apply_m<EPI_MASK>(p.epi, v.x, m, n + 0, p.N, 0.f);
+            o.y = epilogue_apply_m<EPI_MASK>(p.epi, v.y, m, n + 1, p.N, 0.f);
+            o.z = epilogue_apply_m<EPI_MASK>(p.epi, v.z, m, n + 2, p.N, 0.f);
+            o.w = epilogue_apply_m<EPI_MASK>(p.epi, v.w, m, n + 3, p.N, 0.f);
+        }
+        *reinterpret_cast<float4 *>(cp) = o;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
@@ -116,6 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 2 * NACC);
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+    float *stg = reinterpret_cast<float *>(smem_raw + (bar_base + 256 - ptx::smem_u32(smem_raw))) + (threadIdx.x >> 5 & 3) * 32 * STG_LD;
     // stage layout: A pieces, then B pieces
     auto a_addr = [&](int stage, int piece) { return smem_base + stage * STAGE_BYTES + piece * C_::A_PIECE; };
     auto b_addr = [&](int stage, int piece) { return smem_base + stage * STAGE_BYTES + NP * C_::A_PIECE + piece * C_::B_PIECE; };
@@ -141,12 +179,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // ===================================== TMA producer ======================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < p.num_tiles * p.splits; u += gridDim.x) {
                 int z, mb, nb;
-                decode_tile(p, t, z, mb, nb);
+                const int slice = u / p.num_tiles;
+                decode_tile(p, u - slice * p.num_tiles, z, mb, nb);
                 const CUtensorMap *ma = z ? &mapA1 : &mapA0;
                 const CUtensorMap *mbp = z ? &mapB1 : &mapB0;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
+                const int kb0 = slice * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                     ptx::mbar_expect_tx(full_bar(stage), STAGE_BYTES);
 #pragma unroll
@@ -175,8 +215,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else if (warp == 5) {
         // ====================================== MMA issuer =======================================
         if (lane == 0) {
-            const uint32_t idesc = C_::kBf16 ? ptx::make_idesc_bf16(BM, BN, p.ta ? 1 : 0, p.tb ? 0 : 1)
-                                             : ptx::make_idesc_tf32(BM, BN, p.ta ? 1 : 0, p.tb ? 0 : 1);
             const uint32_t a_step = (p.ta ? C_::MNMAJ_STEP : C_::KMAJ_STEP) >> 4;
             const uint32_t b_step = (p.tb ? C_::KMAJ_STEP : C_::MNMAJ_STEP) >> 4;
             // products of the split operands, largest first: a1b1, a1b2, a2b1, (a1b3, a2b2, a3b1)
@@ -184,11 +222,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             constexpr int PB[6] = {0, 1, 0, 2, 1, 0};
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < p.num_tiles * p.splits; u += gridDim.x) {
+                int z, mb, nb;
+                const int slice = u / p.num_tiles;
+                decode_tile(p, u - slice * p.num_tiles, z, mb, nb);
+                // instruction N = the columns this tile really has (multiple of 16): a narrow output
+                // (conv layers: 64 / 96 filters) does not pay for 256 columns of tensor time
+                const int n_eff = min(BN, (p.N - nb * BN + 15) & ~15);
+                const uint32_t idesc = C_::kBf16 ? ptx::make_idesc_bf16(BM, n_eff, p.ta ? 1 : 0, p.tb ? 0 : 1)
+                                                 : ptx::make_idesc_tf32(BM, n_eff, p.ta ? 1 : 0, p.tb ? 0 : 1);
+                const int kb0 = slice * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
                 ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
 #pragma unroll
@@ -197,7 +244,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const uint64_t bdesc = operand_desc<MODE>(b_addr(stage, PB[q]), p.tb == 0);
 #pragma unroll
                         for (int j = 0; j < C_::KSTEPS; ++j) {
-                            const uint32_t accum = (kb | q | j) != 0;
+                            const uint32_t accum = ((kb - kb0) | q | j) != 0;
                             if (C_::kBf16) ptx::mma_bf16(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc, accum);
                             else           ptx::mma_tf32(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc, accum);
                         }
@@ -212,37 +259,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else {
         // ======================================= epilogue ========================================
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        for (int u = blockIdx.x; u < p.num_tiles * p.splits; u += gridDim.x) {
             int z, mb, nb;
-            decode_tile(p, t, z, mb, nb);
+            const int slice = u / p.num_tiles;
+            decode_tile(p, u - slice * p.num_tiles, z, mb, nb);
             float *C = p.C[z];
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            const int m = mb * BM + warp * 32 + lane;
+            const int m0 = mb * BM + warp * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
+            const int nchunks = min(BN / 32, (p.N - nb * BN + 31) / 32);      // the columns the MMAs wrote
+            // tcgen05.ld hands lane l the 32 columns of ROW l; storing that straight out would touch 32
+            // different rows per instruction.  The 32 x 32 block is turned through a padded shared-memory
+            // tile so that every store (and mask / accumulate load) instruction covers four whole 128-B rows.
+            const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < nchunks; ++c) {
                 uint32_t r[32];
                 ptx::tmem_ld32(taddr + c * 32, r);
                 ptx::tmem_ld_wait();
-                const int n0 = nb * BN + c * 32;
-                if (m < p.M && n0 < p.N) {
-                    float *crow = C + (size_t)m * p.ldc + n0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int n = n0 + 4 * q;
-                        if (n < p.N) {        // N % 8 == 0 (eligibility), so a float4 is all-in or all-out
-                            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.epi.mode == EPI_STORE && p.epi.accumulate) old = *reinterpret_cast<const float4 *>(crow + 4 * q);
-                            float4 o;
-                            o.x = epilogue_apply(p.epi, __uint_as_float(r[4 * q + 0]), m, n + 0, p.N, old.x);
-                            o.y = epilogue_apply(p.epi, __uint_as_float(r[4 * q + 1]), m, n + 1, p.N, old.y);
-                            o.z = epilogue_apply(p.epi, __uint_as_float(r[4 * q + 2]), m, n + 2, p.N, old.z);
-                            o.w = epilogue_apply(p.epi, __uint_as_float(r[4 * q + 3]), m, n + 3, p.N, old.w);
-                            *reinterpret_cast<float4 *>(crow + 4 * q) = o;
-                        }
-                    }
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
+                        make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                __syncwarp();
+                const int n = nb * BN + c * 32 + sub_n;
+                if (n < p.N) {                // N % 8 == 0 (eligibility), so a float4 is all-in or all-out
+                    // one straight-line variant per epilogue kind (a single epilogue warp per scheduler has
+                    // nobody to hide its latency behind: instruction count is what the K = 64 GEMMs pay for)
+                    if (p.splits > 1)   // raw partial sums; splitk_reduce adds the slices and applies the epilogue
+                        store_rows<EK_RAW>(p, stg, p.part + ((size_t)slice * p.nz + z) * p.M * p.N, p.N, m0, n, sub_r, sub_n);
+                    else if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    else if (p.epi.mode == EPI_MASK) store_rows<EK_MASK>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    else if (p.epi.accumulate) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    else store_rows<EK_RAW>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
                 }
+                __syncwarp();
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -460,10 +513,30 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
         CTCASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
         attr_set = true;
     }
-    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    ProfScope prof_gemm(PROF_GEMM_TC, stream);
-    gemm_tc_kernel<MODE><<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
-    CTCASR_LAUNCH_CHECK();
+    // split-K: under half a wave of output tiles on a long contraction (conv weight gradients: [Kp, 64]
+    // outputs contracting 10^5..10^6 patch rows) -> ~2 waves of (slice, tile) units, >= 32 k-blocks per slice
+    p.splits = 1; p.kb_per_split = p.kblocks; p.part = nullptr;
+    if (p.num_tiles <= num_sms / 2 && p.kblocks >= 128) {
+        int S = (2 * num_sms) / p.num_tiles;
+        if (S > p.kblocks / 32) S = p.kblocks / 32;
+        if (S > 1) {
+            const int per = ceil_div(p.kblocks, S);
+            S = ceil_div(p.kblocks, per);
+            const size_t bytes = (size_t)S * g.nz * g.M * g.N * sizeof(float);
+            const size_t used = align_up(C_::kBf16 || g_scope ? g_cursor : 0, 1024);
+            if (S > 1 && g_scratch && used + bytes <= g_scratch_bytes) {      // no room: unsplit (slower, same result class)
+                p.splits = S; p.kb_per_split = per; p.part = reinterpret_cast<float *>(g_scratch + used);
+            }
+        }
+    }
+    const int units = p.num_tiles * p.splits;
+    const int grid = units < num_sms ? units : num_sms;
+    {
+        ProfScope prof_gemm(PROF_GEMM_TC, stream);
+        gemm_tc_kernel<MODE><<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+        CTCASR_LAUNCH_CHECK();
+    }
+    if (p.splits > 1) return splitk_reduce(g, p.splits, p.part, stream);
     return CTCASR_OK;
 }
 

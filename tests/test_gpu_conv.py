@@ -146,3 +146,23 @@ def test_ds2_full_size_properties():
     fd = (lp - lm) / (2 * eps)
     print("ds2 directional derivative: finite difference %.4f, analytic %.4f" % (fd, analytic))
     assert abs(fd - analytic) / abs(analytic) < 2e-2, (fd, analytic)
+
+
+@pytest.mark.parametrize("compute,tol", [("bf16x3", 2e-5), ("tf32", 2e-3)])
+@pytest.mark.parametrize("M,N,K,ta,tb", [
+    (456, 64, 64000, True, False),      # conv weight gradient: 4 output tiles, long contraction -> split-K
+    (7392, 96, 20000, True, False),     # 58 tiles x 5 slices
+    (1000, 64, 456, False, False),      # conv forward: instruction N = 64 of the 256-column tile
+    (1000, 96, 7392, False, False),
+    (1000, 456, 64, False, True),       # conv dgrad: K = 64
+    (264, 328, 9000, False, True),      # last N tile narrower (72 -> 80 columns), K-major B
+])
+def test_gemm_tcgen05_narrow_n_and_split_k(M, N, K, ta, tb, compute, tol):
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    c = ops.gemm(dev(a), dev(b), ta=ta, tb=tb, compute=_lib.COMPUTE_ID[compute])
+    c2 = ops.gemm(dev(a), dev(b), ta=ta, tb=tb, compute=_lib.COMPUTE_ID[compute])
+    assert torch.equal(c, c2)                                          # slices are added in a fixed order
+    want = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    assert rel_err(c.cpu().numpy(), want) < tol

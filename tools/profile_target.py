@@ -2,6 +2,7 @@
   python tools/profile_target.py lstm [T]     one BiLSTM-2048 layer, B=32: recurrence fwd + bwd kernels
   python tools/profile_target.py gemm         the cfg2 GEMM shapes in the default arithmetic
   python tools/profile_target.py ctc          cfg5 CTC forward-backward
+  python tools/profile_target.py convgemm     the conv layers' GEMM shapes
 """
 import os
 import sys
@@ -30,6 +31,16 @@ if what == "lstm":
     for _ in range(2):
         ops.birnn_fwd(x, sl, wx, wh, bias, y, reserve, 2, True, compute=C)
         ops.birnn_bwd(x, sl, wx, wh, y, reserve, dy, dx, dwx, dwh, db, 2, True, compute=C)
+    torch.cuda.synchronize()
+elif what == "convgemm":
+    # the conv layers' GEMM shapes (second layer, B=32 x 10 s): dgrad (K = 64), forward (N = 64), wgrad (split-K)
+    for (M, N, K, ta, tb) in [(320000, 7392, 64, 0, 1), (320000, 64, 7392, 0, 0), (7392, 64, 320000, 1, 0)]:
+        a = torch.randn((K, M) if ta else (M, K), device="cuda")
+        b = torch.randn((N, K) if tb else (K, N), device="cuda")
+        c = torch.empty(M, N, device="cuda")
+        for _ in range(2):
+            ops.gemm(a, b, ta=bool(ta), tb=bool(tb), out=c, compute=C)
+        del a, b, c
     torch.cuda.synchronize()
 elif what == "gemm":
     for (M, N, K, ta, tb) in [(32000, 16384, 4096, 0, 0), (4096, 16384, 32000, 1, 0), (32000, 4096, 16384, 0, 1)]:
