@@ -197,10 +197,21 @@ class CTCModel:
         self.last_per_utterance_loss = per_utt
         return per_utt.sum() / gb if global_batch is not None else per_utt.mean()
 
-    # ---- asr/model.py:271-309 (greedy variant; beam search is a "next" row) ---------------------
-    def decode_fn(self, logits, seq_len, originals=None):
-        """-> (decoded ids as a list of int32 tensors, plaintexts, plaintext summary rows)."""
-        ids, n = ops.greedy_decode(logits, seq_len.to(self.device, torch.int32).contiguous(), blank=self.cfg.blank)
+    # ---- asr/model.py:271-309 ------------------------------------------------------------------
+    def decode_fn(self, logits, seq_len, originals=None, decoder=None):
+        """-> (decoded ids as a list of int32 tensors, plaintexts, plaintext summary rows).
+        decoder: 'beam_search' (the reference: tf.nn.ctc_beam_search_decoder, beam_width=FLAGS.beam_width,
+        top_paths=1, merge_repeated=False, asr/model.py:292-296) or 'greedy' (the decoder the reference's
+        comment at :290 mentions as the faster alternative); default `config.decoder`."""
+        decoder = self.cfg.decoder if decoder is None else decoder
+        seq_len = seq_len.to(self.device, torch.int32).contiguous()
+        if decoder == "beam_search":
+            ids, n, _ = ops.beam_search(logits, seq_len, beam_width=self.cfg.beam_width, merge_repeated=False,
+                                        blank=self.cfg.blank)
+        elif decoder == "greedy":
+            ids, n = ops.greedy_decode(logits, seq_len, blank=self.cfg.blank)
+        else:
+            raise ValueError("decoder must be 'beam_search' or 'greedy'")
         ids_h, n_h = ids.cpu(), n.cpu().tolist()
         decoded = [ids_h[b, :n_h[b]] for b in range(len(n_h))]
         plaintext = [_labels.ids_to_text(d.tolist()) for d in decoded]

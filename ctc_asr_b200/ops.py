@@ -96,6 +96,25 @@ def greedy_decode(logits, seq_len, blank=None):
     return ids[:, :T], n
 
 
+def beam_search(logits, seq_len, beam_width=1024, merge_repeated=False, blank=None):
+    """tf.nn.ctc_beam_search_decoder(top_paths=1) (asr/model.py:292-296) -> (ids [B,T] -1 padded, lengths [B],
+    log-score of the best path [B])."""
+    lib = _lib.load()
+    _f32(logits, "logits"); _i32(seq_len, "seq_len")
+    T, B, V = logits.shape
+    blank = V - 1 if blank is None else blank
+    ids = torch.empty((B, max(T, 1)), dtype=torch.int32, device=logits.device)
+    n = torch.empty(B, dtype=torch.int32, device=logits.device)
+    lp = torch.empty(B, dtype=torch.float32, device=logits.device)
+    wsb = lib.ctcasr_beam_search_workspace_bytes(T, B, V, int(beam_width))
+    if wsb == 0:
+        raise ValueError("beam_search: unsupported shape (num_classes %d <= 32, beam_width %d <= 1024)" % (V, beam_width))
+    ws = workspace(wsb, logits.device, "beam")
+    check(lib.ctcasr_beam_search(ptr(logits), T, B, V, blank, ptr(seq_len), int(beam_width), int(merge_repeated),
+                                 ptr(ids), ptr(n), ptr(lp), ptr(ws), ws.numel(), _stream()), "beam_search")
+    return ids[:, :T], n, lp
+
+
 def edit_distance(hyp, hyp_len, truth, truth_len, normalize=True):
     lib = _lib.load()
     _i32(hyp, "hyp"); _i32(hyp_len, "hyp_len"); _i32(truth, "truth"); _i32(truth_len, "truth_len")

@@ -59,6 +59,7 @@ class ModelConfig:
     #           accumulated in fp32 TMEM: fp32-level accuracy at tensor-core speed (default)
     # 'tf32'  : tcgen05 kind::tf32 on the fp32 operands: fastest, 2^-11 operand rounding
     compute: str = "bf16x3"
+    decoder: str = "beam_search"        # decode_fn: 'beam_search' (asr/model.py:292-296) | 'greedy'
 
     def __post_init__(self):
         if self.used_model not in ("ds1", "ds2"):

@@ -138,6 +138,22 @@ int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const float *wx, co
                      int compute, void *ws, size_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * CTC prefix beam search.  Replaces tf.nn.ctc_beam_search_decoder(inputs=logits, sequence_length,
+ * beam_width=FLAGS.beam_width, top_paths=1, merge_repeated=False) at asr/model.py:292-296
+ * (beam_width default 1024, asr/params.py:85).  No language-model scorer, like the reference.
+ *   logits [T,B,V] time-major; blank must be V-1 (TF's convention, asr/labels.py:6); V <= 32;
+ *   1 <= beam_width <= 1024; frames t >= seq_len[b] are not read.
+ *   out_ids [B,T] (row b: the best path's labels, then -1), out_len [B],
+ *   out_logp [B] (nullable): log-score of the best path (frame scores relative to the frame maximum,
+ *   as TF r1.12's Step() computes them).
+ * Exactly equal scores at the beam boundary are ordered by candidate index (TF: heap order).
+ * -------------------------------------------------------------------------------------------- */
+size_t ctcasr_beam_search_workspace_bytes(int T, int B, int V, int beam_width);
+int ctcasr_beam_search(const float *logits, int T, int B, int V, int blank, const int32_t *seq_len,
+                       int beam_width, int merge_repeated, int32_t *out_ids, int32_t *out_len,
+                       float *out_logp, void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * 2-D convolution layer of the 'ds2' front-end.  Replaces one iteration of the loop at
  * asr/util/tf_contrib.py:123-134: tf.layers.conv2d(padding='SAME', activation=relu) followed by
  * tf.minimum(., relu_cutoff); the image height is TIME and its width the feature axis

@@ -21,7 +21,7 @@ def build(force=False):
     """Compile oracle.c with the committed Makefile (gcc only, seconds)."""
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-            for f in ("oracle.c", "oracle_impl.h", "Makefile")):
+            for f in ("oracle.c", "oracle_impl.h", "beam_search.h", "Makefile")):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
@@ -205,3 +205,19 @@ def edit_distance(hyp, hyp_len, truth, truth_len, normalize=True):
     lib().oracle_edit_distance(_p(hyp), hyp.shape[1], _p(_c(hyp_len, np.int32)), _p(truth), truth.shape[1],
                                _p(_c(truth_len, np.int32)), B, int(normalize), _p(out))
     return out
+
+
+def ctc_beam_search(logits, seq_len, beam_width=1024, merge_repeated=False, blank=None, reoffer_wipe=False):
+    """tf.nn.ctc_beam_search_decoder(top_paths=1) as called at asr/model.py:292-296.
+    logits [T,B,V] float32 -> (ids [B,T] -1 padded, lengths [B], log-probability of the best leaf [B]).
+    reoffer_wipe=True reproduces the order-dependent artifact of TF's Step() (oracle/beam_search.h)."""
+    logits = _c(logits, np.float32)
+    T, B, V = logits.shape
+    blank = V - 1 if blank is None else blank
+    ids = np.zeros((B, max(T, 1)), np.int32)
+    n = np.zeros(B, np.int32)
+    lp = np.zeros(B, np.float32)
+    rc = lib().oracle_ctc_beam_search(_p(logits), T, B, V, blank, _p(_c(seq_len, np.int32)), int(beam_width),
+                                      int(merge_repeated), int(reoffer_wipe), _p(ids), _p(n), _p(lp))
+    assert rc == 0
+    return ids[:, :T], n, lp
