@@ -34,6 +34,10 @@ SIGNATURES = {
                               _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "ctcasr_beam_search_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ctcasr_beam_search": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ctcasr_feature_frames": (_i, [_i, _i]),
+    "ctcasr_feature_filterbank_bins": (_i, [_i, _i, _vp]),
+    "ctcasr_featurize_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "ctcasr_featurize": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "ctcasr_conv2d_out_dims": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ctcasr_conv2d_workspace_bytes": (_sz, [_i] * 8),
     "ctcasr_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 10 + [_f, _i, _vp, _sz, _vp]),

@@ -179,6 +179,27 @@ int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, const float *
                       int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Feature extraction.  Replaces the arithmetic of load_sample (asr/input_functions.py:156-262) from
+ * the decoded samples on: python_speech_features' mfcc + delta (:264-294) or logfbank (:297-318) with
+ * the reference's parameters (25 ms / 10 ms frames, pre-emphasis 0.97, nfft 1024, `num_features` mel
+ * filters from 64 Hz to Nyquist; MFCC: num_features/2 cepstra, lifter 22, c0 := log energy, + deltas
+ * over +-2 frames) and __feature_normalization (:321-349).  Reading the WAV file stays on the host.
+ *   audio [B, max_samples] int16 (DEVICE), utterance b in its first num_samples_host[b] samples;
+ *   num_samples_host [B]: HOST array (the caller knows its file lengths; each must be >= 401, the
+ *   reference's own lower bound, :213-214);
+ *   feature_type 0 'mel' | 1 'mfcc';  normalization 0 'none' | 1 'local' | 2 'local_scalar';
+ *   features [B, Tmax, num_features] float32 (DEVICE), zero past each utterance's frames — the
+ *   `sequences` layout of asr/model.py:129;  num_frames [B] (DEVICE).
+ * -------------------------------------------------------------------------------------------- */
+int ctcasr_feature_frames(int num_samples, int sampling_rate);
+int ctcasr_feature_filterbank_bins(int sampling_rate, int num_filters, int32_t *bins_host);
+size_t ctcasr_featurize_workspace_bytes(int B, int max_samples, int sampling_rate, int num_features);
+int ctcasr_featurize(const int16_t *audio, int B, int max_samples, const int32_t *num_samples_host,
+                     int feature_type, int normalization, int drop_every_second_frame,
+                     int sampling_rate, int num_features,
+                     float *features, int Tmax, int32_t *num_frames, void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Plumbing around the path
  * -------------------------------------------------------------------------------------------- */
 /* Optional timing of the hot kernels with CUDA events recorded on the launching stream.
