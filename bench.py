@@ -29,6 +29,9 @@ CFG2 = dict(num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_unit
             cudnn=False, dense_dropout_rate=0.1)
 CFG2_B, CFG2_T, CFG2_L = 32, 1000, 160
 CFG5 = dict(B=512, T=1700, L=84, V=29)
+# CPU arm: frames per utterance in the bounded sample (of 1000).  32 frames x B=32 is ~3.5 s per step on 16-24
+# host cores: 1 warm-up + 2 timed steps stay near 10 s, and a driver-chosen --steps 20 --warmup 5 under two minutes.
+CPU_SAMPLE_FRAMES = 32
 
 
 def parse_args():
@@ -136,7 +139,7 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = ModelConfig(**dict(CFG2, num_units_dense=args.units, num_units_rnn=args.units, dense_dropout_rate=0.0))
-    sample_T = args.cpu_sample_frames or 8
+    sample_T = args.cpu_sample_frames or CPU_SAMPLE_FRAMES
     L = max(1, min(CFG2_L, sample_T // 4))
     t0 = time.perf_counter()
     fps, dt, cores = cpu_reference_frames_per_s(cfg, args.batch, sample_T, L, steps=args.steps, warmup=args.warmup)
@@ -292,7 +295,7 @@ def run_ours(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ccfg = cfg.replace(dense_dropout_rate=0.0)
-        sT = args.cpu_sample_frames or 8
+        sT = args.cpu_sample_frames or CPU_SAMPLE_FRAMES
         fps, dt, cores = cpu_reference_frames_per_s(ccfg, B, sT, max(1, min(L, sT // 4)), steps=2, warmup=1)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "B=%d x %d frames per step (of %d), 1 warm-up + 2 timed steps, torch-CPU "

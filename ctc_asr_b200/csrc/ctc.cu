@@ -14,11 +14,14 @@
 //            and write the gradient rows.
 //   HBM traffic is therefore the algorithmic one: logits in (re-read from L2 in phase 2),
 //   gradient out, plus T/CH checkpoint rows.
-//   alpha/beta are base-2 log-domain values carried as (hi, lo) float pairs (error-free TwoSum
-//   accumulation): a plain fp32 recursion rounds at ulp(alpha) ~ 1e-3 per step and carries ~1e-2
-//   of gradient noise at T=1700 (tests/test_oracle_ctc.py), which would eat the 1e-3 budget.
-//   Each recursion step is one shared-memory row read + a 3-way log-sum-exp (3 ex2 + 1 lg2 MUFU) + one
-//   named barrier per warp group; alpha and beta groups run on separate barriers.
+//   alpha/beta are carried as extended-range numbers m * 2^e (m a float in [1, 2), e a 32-bit integer):
+//   the recursion  alpha_t(s) = y * (alpha(s) + alpha(s-1) + alpha(s-2))  is then two additions and one
+//   multiplication per state with 2^-24 relative rounding each (~1e-5 after 1700 frames) and no transcendental
+//   at all; the softmax helper warp turns each frame's log-softmax into (m, e) pairs once per (t, class).
+//   A plain fp32 LOG-domain recursion (what the TF kernel does) rounds every step at ulp(|alpha|) ~ 1e-3 and
+//   carries ~1e-2 of gradient noise at T=1700 (tests/test_oracle_ctc.py); a linear-domain recursion with one
+//   scale per row underflows the states that carry the posterior.  Each step is one shared-memory row
+//   read + the (m, e) arithmetic + one named barrier per warp group (alpha and beta on separate barriers).
 #include "common.cuh"
 
 #include <math.h>
@@ -49,38 +52,42 @@ struct SmemLayout {
         rowA = o;      o += (size_t)2 * RS * 8;
         rowB = o;      o += (size_t)2 * RS * 8;
         A = o;         o += (size_t)2 * CH * RS * 8;
-        LY = o;        o += (size_t)((3 * CH * VP + 3) / 4 * 4) * 4;
+        LY = o;        o += (size_t)((3 * CH * VP + 3) / 4 * 4) * 8;        // (m, e) pairs
         red = o;       o += 64 * 4 + 64;
         total = o;
     }
 };
 
 // ---- lattice arithmetic ---------------------------------------------------------------------------
-// Values are base-2 logarithms held as an unevaluated sum hi + lo of two floats.  A plain fp32
-// log-domain recursion rounds every step at ulp(|alpha|): with |alpha| growing to ~1e4 over 1700
-// frames that is 1e-3 per step and the gradient ends up ~1e-2 off (the TF kernel does exactly this);
-// re-basing rows to their maximum still leaves the states that carry the posterior ~150 below it
-// (2e-3 measured).  Carrying the rounding error of each addition in `lo` (error-free TwoSum) keeps
-// ~48 bits for the accumulated part, so only the O(1)-sized per-step increments are rounded.
-// Base 2 makes exp/log single MUFU instructions (ex2.approx / lg2.approx).
+// A lattice value is m * 2^e stored as float2 {m, bits of the int e}: m in [1, 2), or m = 0 (then e = kZE)
+// for probability zero.  Sums align the operands to the largest exponent with exact power-of-two factors
+// built from integer bits; the product with y re-normalises the mantissa with two integer instructions.
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-__device__ __forceinline__ float2 two_sum(float a, float b)      // a + b = s + e exactly
+constexpr int kZE = -(1 << 29);
+__device__ __forceinline__ float2 xf_make(float m, int e) { return make_float2(m, __int_as_float(e)); }
+__device__ __forceinline__ int xf_e(const float2 v) { return __float_as_int(v.y); }
+// 2^d for d <= 0 (0 below 2^-126: such a term is below the rounding of its partners by > 100 binades)
+__device__ __forceinline__ float pow2_le0(int d) { return __int_as_float(max(d + 127, 0) << 23); }
+// 2^e clamped to the normal range (posteriors and y are <= 1 up to rounding)
+__device__ __forceinline__ float pow2_clamp(int e) { return __int_as_float(min(max(e + 127, 0), 254) << 23); }
+
+// (a0 + a1 + a2) * y
+__device__ __forceinline__ float2 xf_sum3_mul(const float2 a0, const float2 a1, const float2 a2, const float2 y)
 {
-    const float s = a + b, bb = s - a;
-    return make_float2(s, (a - (s - bb)) + (b - bb));
+    const int e0 = xf_e(a0), e1 = xf_e(a1), e2 = xf_e(a2);
+    const int em = max(e0, max(e1, e2));
+    float s = a0.x * pow2_le0(e0 - em);
+    s = fmaf(a1.x, pow2_le0(e1 - em), s);
+    s = fmaf(a2.x, pow2_le0(e2 - em), s);
+    s *= y.x;                                       // [0, 12)
+    if (s == 0.f) return xf_make(0.f, kZE);
+    const int bits = __float_as_int(s);
+    return xf_make(__int_as_float((bits & 0x007fffff) | 0x3f800000), em + xf_e(y) + (bits >> 23) - 127);
 }
-// log2( 2^a0 + 2^a1 + 2^a2 ) + inc, all operands (hi, lo) pairs, -inf = log zero
-__device__ __forceinline__ float2 lse3_add(float2 a0, float2 a1, float2 a2, float inc)
-{
-    float2 m = a0.x >= a1.x ? a0 : a1;
-    m = m.x >= a2.x ? m : a2;
-    if (m.x == -INFINITY) return make_float2(-INFINITY, 0.f);
-    const float d0 = (a0.x - m.x) + (a0.y - m.y), d1 = (a1.x - m.x) + (a1.y - m.y), d2 = (a2.x - m.x) + (a2.y - m.y);
-    const float lg = lg2f(ex2f(d0) + ex2f(d1) + ex2f(d2));      // sum in [1, 3]
-    return two_sum(m.x, (lg + inc) + m.y);
-}
+// log2 of a lattice value, in double (loss only)
+__device__ __forceinline__ double xf_log2(const float2 v) { return v.x == 0.f ? -INFINITY : log2((double)v.x) + (double)xf_e(v); }
 
 __device__ __forceinline__ void group_bar(int id, int nthreads)
 {
@@ -99,12 +106,12 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-// base-2 log-softmax of the frames of chunk c into LY, FOUR LANES PER FRAME (a frame's V logits are a
+// softmax of the frames of chunk c into LY as (m, e) pairs, FOUR LANES PER FRAME (a frame's V logits are a
 // contiguous 4V-byte run; the 4 lanes take classes k = sub, sub+4, ... and combine with two
 // shuffles), executed by `nthreads` (a multiple of 32) consecutive threads starting at `first`.
 // Values are re-read from L1 instead of being held in registers (V up to 128).
-// Rows are VP = V|1 floats apart to spread the banks.
-__device__ __forceinline__ void compute_logy(const Params &p, int b, int Tb, int c, float *LY, int first, int nthreads)
+// Rows are VP = V|1 entries apart to spread the banks.
+__device__ __forceinline__ void compute_logy(const Params &p, int b, int Tb, int c, float2 *LY, int first, int nthreads)
 {
     const float kLog2e = 1.4426950408889634f;
     const int lt = (int)threadIdx.x - first, sub = lt & 3, rpp = nthreads >> 2;
@@ -121,10 +128,14 @@ __device__ __forceinline__ void compute_logy(const Params &p, int b, int Tb, int
         for (int k = sub; k < p.V; k += 4) e += ex2f((__ldg(x + k) - m) * kLog2e);
         e += __shfl_xor_sync(0xffffffffu, e, 1);
         e += __shfl_xor_sync(0xffffffffu, e, 2);
-        const float lse2 = m * kLog2e + lg2f(e);        // log2 sum_k 2^(x_k log2 e)
+        const float lg = lg2f(e);                       // log2 sum_k 2^((x_k - max) log2 e), in [0, log2 V]
         if (valid) {
-            float *row = LY + (size_t)(t - lo) * p.VP;
-            for (int k = sub; k < p.V; k += 4) row[k] = __ldg(x + k) * kLog2e - lse2;
+            float2 *row = LY + (size_t)(t - lo) * p.VP;
+            for (int k = sub; k < p.V; k += 4) {
+                const float l2 = (__ldg(x + k) - m) * kLog2e - lg;      // log2 softmax_k <= 0, small near the maximum
+                const float fl = floorf(l2);
+                row[k] = l2 > -1e9f ? xf_make(ex2f(l2 - fl), (int)fl) : xf_make(0.f, kZE);
+            }
         }
     }
 }
@@ -142,7 +153,8 @@ ctc_loss_kernel(const Params p)
     const bool is_helper = tid >= 2 * GT;
     const int gt = is_alpha ? tid : tid - GT;
     const int RS = p.RS, CH = p.CH, V = p.V, VP = p.VP, blank = p.blank;
-    const float2 kNegInf = make_float2(-INFINITY, 0.f);
+    const float2 kNegInf = xf_make(0.f, kZE);                        // probability zero
+    const float2 kOne = xf_make(1.f, 0);
 
     const SmemLayout L(p.Lmax, V, RS, CH, VP);
     int *lab = reinterpret_cast<int *>(smem_raw + L.lab);
@@ -151,7 +163,7 @@ ctc_loss_kernel(const Params p)
     float2 *rowA = reinterpret_cast<float2 *>(smem_raw + L.rowA);   // alpha rows: state s at [s+2]
     float2 *rowB = reinterpret_cast<float2 *>(smem_raw + L.rowB);   // beta rows (incl. y_t): state s at [s]
     float2 *Abuf = reinterpret_cast<float2 *>(smem_raw + L.A);      // [2][CH][RS], state s at [s+2]
-    float *LYbuf = reinterpret_cast<float *>(smem_raw + L.LY);      // [3][CH][VP] ring, chunk c at c % 3
+    float2 *LYbuf = reinterpret_cast<float2 *>(smem_raw + L.LY);    // [3][CH][VP] ring of (m, e), chunk c at c % 3
     float *red = reinterpret_cast<float *>(smem_raw + L.red);
     int *flags = reinterpret_cast<int *>(red + 48);                 // [0] bad label, [1] repeats
 
@@ -239,13 +251,13 @@ ctc_loss_kernel(const Params p)
 #pragma unroll
         for (int q = 0; q < SPT; ++q) {
             const int s = gt + q * GT;
-            if (s < S) rowA[cur * RS + s + 2] = s == 0 ? make_float2(0.f, 0.f) : kNegInf;
+            if (s < S) rowA[cur * RS + s + 2] = s == 0 ? kOne : kNegInf;
         }
     }
     compute_logy(p, b, Tb, 0, LYbuf, 0, NT);
     __syncthreads();
     for (int c = 0; c < NCH; ++c) {
-        const float *LY = LYbuf + (size_t)(c % 3) * LYS;
+        const float2 *LY = LYbuf + (size_t)(c % 3) * LYS;
         if (is_helper) {
             if (c + 1 < NCH) compute_logy(p, b, Tb, c + 1, LYbuf + (size_t)((c + 1) % 3) * LYS, 2 * GT, kHelper);
         } else if (is_alpha) {
@@ -259,11 +271,11 @@ ctc_loss_kernel(const Params p)
             for (int t = lo; t < hi; ++t) {
                 const float2 *prev = rowA + cur * RS;
                 float2 *next = rowA + (cur ^ 1) * RS;
-                const float *ly = LY + (size_t)(t - lo) * VP;
+                const float2 *ly = LY + (size_t)(t - lo) * VP;
 #pragma unroll
                 for (int q = 0; q < SPT; ++q) {
                     const int s = gt + q * GT;
-                    if (s < S) next[s + 2] = lse3_add(prev[s + 2], prev[s + 1], st_skA[q] ? prev[s] : kNegInf, ly[st_lp[q]]);
+                    if (s < S) next[s + 2] = xf_sum3_mul(prev[s + 2], prev[s + 1], st_skA[q] ? prev[s] : kNegInf, ly[st_lp[q]]);
                 }
                 cur ^= 1;
                 group_bar(1, GT);
@@ -271,14 +283,14 @@ ctc_loss_kernel(const Params p)
         }
         __syncthreads();
     }
-    // log2 p = LSE2(alpha[S-1], alpha[S-2]) at t = T_b - 1 as a (hi, lo) pair shared through smem
+    // p = alpha[S-1] + alpha[S-2] at t = T_b - 1, shared through smem
     float2 *psh = reinterpret_cast<float2 *>(red + 40);
     if (tid == 0) {
         const float2 a = rowA[cur * RS + (S - 1) + 2];
         const float2 c2 = S > 1 ? rowA[cur * RS + (S - 2) + 2] : kNegInf;
-        const float2 lp2 = lse3_add(a, c2, kNegInf, 0.f);
-        psh[0] = lp2;
-        p.loss[b] = (float)(-((double)lp2.x + (double)lp2.y) * 0.6931471805599453);
+        const float2 pp = xf_sum3_mul(a, c2, kNegInf, kOne);
+        psh[0] = pp;
+        p.loss[b] = (float)(-xf_log2(pp) * 0.6931471805599453);
         p.status[b] = CTCASR_CTC_OK;
     }
     if (!p.grad) return;
@@ -293,7 +305,7 @@ ctc_loss_kernel(const Params p)
 #pragma unroll
         for (int q = 0; q < SPT; ++q) {
             const int s = gt + q * GT;
-            if (s < S) rowB[curB * RS + s] = s == S - 1 ? make_float2(0.f, 0.f) : kNegInf;
+            if (s < S) rowB[curB * RS + s] = s == S - 1 ? kOne : kNegInf;
         }
     }
     for (int r = 0; r <= NCH; ++r) {
@@ -304,7 +316,7 @@ ctc_loss_kernel(const Params p)
             if (ca - 1 >= 0 && r >= 2) compute_logy(p, b, Tb, ca - 1, LYbuf + (size_t)((ca - 1) % 3) * LYS, 2 * GT, kHelper);
         } else if (is_alpha) {
             if (ca >= 0) {
-                const float *LY = LYbuf + (size_t)(ca % 3) * LYS;
+                const float2 *LY = LYbuf + (size_t)(ca % 3) * LYS;
                 float2 *A = Abuf + (size_t)(ca & 1) * CH * RS;
                 float2 *r0 = rowA;      // checkpoint row of chunk ca
 #pragma unroll
@@ -317,38 +329,38 @@ ctc_loss_kernel(const Params p)
                 for (int t = lo; t < hi; ++t) {
                     const float2 *prev = t == lo ? r0 : A + (size_t)(t - lo - 1) * RS;
                     float2 *next = A + (size_t)(t - lo) * RS;
-                    const float *ly = LY + (size_t)(t - lo) * VP;
+                    const float2 *ly = LY + (size_t)(t - lo) * VP;
 #pragma unroll
                     for (int q = 0; q < SPT; ++q) {
                         const int s = gt + q * GT;
-                        if (s < S) next[s + 2] = lse3_add(prev[s + 2], prev[s + 1], st_skA[q] ? prev[s] : kNegInf, ly[st_lp[q]]);
+                        if (s < S) next[s + 2] = xf_sum3_mul(prev[s + 2], prev[s + 1], st_skA[q] ? prev[s] : kNegInf, ly[st_lp[q]]);
                     }
                     group_bar(1, GT);
                 }
             }
         } else if (cb < NCH) {
-            const float *LY = LYbuf + (size_t)(cb % 3) * LYS;
+            const float2 *LY = LYbuf + (size_t)(cb % 3) * LYS;
             float2 *A = Abuf + (size_t)(cb & 1) * CH * RS;
             const int lo = cb * CH, hi = min(lo + CH, Tb);
+            const float inv_pm = 1.f / lp2.x;
+            const int pe = xf_e(lp2);
             for (int t = hi - 1; t >= lo; --t) {
                 const float2 *prev = rowB + curB * RS;
                 float2 *next = rowB + (curB ^ 1) * RS;
-                const float *ly = LY + (size_t)(t - lo) * VP;
+                const float2 *ly = LY + (size_t)(t - lo) * VP;
                 float2 *arow = A + (size_t)(t - lo) * RS;
 #pragma unroll
                 for (int q = 0; q < SPT; ++q) {
                     const int s = gt + q * GT;
                     if (s < S) {
-                        const float lys = ly[st_lp[q]];
-                        const float2 bt = lse3_add(prev[s], prev[s + 1], st_skB[q] ? prev[s + 2] : kNegInf, lys);
+                        const float2 lys = ly[st_lp[q]];
+                        const float2 bt = xf_sum3_mul(prev[s], prev[s + 1], st_skB[q] ? prev[s + 2] : kNegInf, lys);
                         next[s] = bt;
-                        // posterior of state s at t: 2^(alpha + beta - log2 y - log2 p), sums done error-free
+                        // posterior of state s at t: alpha * beta / (y * p)   (beta includes y_t)
                         const float2 al = arow[s + 2];
                         float post = 0.f;
-                        if (al.x != -INFINITY && bt.x != -INFINITY) {
-                            const float2 ab = two_sum(al.x, bt.x);
-                            post = ex2f((ab.x - lp2.x) + (((ab.y + al.y) + bt.y) - lp2.y - lys));
-                        }
+                        if (al.x != 0.f && bt.x != 0.f)
+                            post = __fdividef(al.x * bt.x, lys.x) * inv_pm * pow2_clamp(xf_e(al) + xf_e(bt) - xf_e(lys) - pe);
                         arow[s + 2].x = post;
                     }
                 }
@@ -359,7 +371,7 @@ ctc_loss_kernel(const Params p)
         __syncthreads();
         // ---- gradient rows of chunk cb: y - sum_{s in class k} posterior ---------------------
         if (cb < NCH) {
-            const float *LY = LYbuf + (size_t)(cb % 3) * LYS;
+            const float2 *LY = LYbuf + (size_t)(cb % 3) * LYS;
             const float2 *A = Abuf + (size_t)(cb & 1) * CH * RS;
             const int lo = cb * CH, hi = min(lo + CH, Tb);
             const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
@@ -372,7 +384,8 @@ ctc_loss_kernel(const Params p)
                     float acc = 0.f;
                     if (k == blank) acc = pb;
                     else for (int q = csr_start[k]; q < csr_start[k + 1]; ++q) acc += arow[csr_pos[q]].x;
-                    const float y = ex2f(LY[(size_t)(t - lo) * VP + k]);
+                    const float2 yk = LY[(size_t)(t - lo) * VP + k];
+                    const float y = yk.x * pow2_clamp(xf_e(yk));
                     grad_b[(size_t)t * gstride + k] = (y - acc) * p.grad_scale;
                 }
             }
@@ -453,13 +466,19 @@ __global__ void edit_distance_kernel(const int *hyp, int hstride, const int *hyp
     }
 }
 
-struct Plan { int CH, RS, GT, NCH, VP; size_t smem, ws_total; };
+struct Plan { int CH, RS, GT, NCH, VP, SPT; size_t smem, ws_total; };
 
 static int make_plan(int T, int B, int V, int Lmax, Plan *pl)
 {
     const int S = 2 * Lmax + 1;
     if (V < 1 || V > 128) return fail(CTCASR_ERR_UNSUPPORTED, "ctc: num_classes %d > 128", V);
+    // Many utterances (more CTAs than SMs): the kernel is bound by instruction issue, so two lattice states
+    // per thread — half the warps, the per-step addressing / barrier / loop overhead shared by two states,
+    // and 64 registers per thread at 4 CTAs per SM instead of 32 with spills.  Few utterances: one state per
+    // thread keeps the per-step latency lowest.
+    pl->SPT = 1;
     int GT = (S + 31) / 32 * 32;
+    if (B >= 148 && S > 64 && S <= 256) { pl->SPT = 2; GT = ((S + 1) / 2 + 31) / 32 * 32; }
     if (GT > kMaxGT) GT = kMaxGT;
     if (GT < 64) GT = 64;
     if (S > kMaxSPT * GT) return fail(CTCASR_ERR_UNSUPPORTED, "ctc: label length %d too long", Lmax);
@@ -519,7 +538,8 @@ extern "C" int ctcasr_ctc_loss(const float *logits, int T, int B, int V, int bla
         CTCASR_LAUNCH_CHECK();
         return CTCASR_OK;
     };
-    static size_t set0 = 0, set1 = 0, set2 = 0;
+    static size_t set0 = 0, set1 = 0, set2 = 0, set3 = 0;
+    if (pl.SPT == 2 && S <= 2 * pl.GT && NT <= 288) return launch(ctc::ctc_loss_kernel<2, 288, 4>, set3);
     if (S <= pl.GT && NT <= 480) return launch(ctc::ctc_loss_kernel<1, 480, 4>, set0);
     if (S <= pl.GT) return launch(ctc::ctc_loss_kernel<1, 2 * ctc::kMaxGT + ctc::kHelper, 1>, set1);
     return launch(ctc::ctc_loss_kernel<ctc::kMaxSPT, 2 * ctc::kMaxGT + ctc::kHelper, 1>, set2);

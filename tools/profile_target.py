@@ -3,6 +3,8 @@
   python tools/profile_target.py gemm         the cfg2 GEMM shapes in the default arithmetic
   python tools/profile_target.py ctc          cfg5 CTC forward-backward
   python tools/profile_target.py convgemm     the conv layers' GEMM shapes
+  python tools/profile_target.py conv         second conv layer forward + backward (im2col / col2im kernels)
+  python tools/profile_target.py beam         prefix beam search, 32 x 300 frames, width 1024
 """
 import os
 import sys
@@ -41,6 +43,27 @@ elif what == "convgemm":
         for _ in range(2):
             ops.gemm(a, b, ta=bool(ta), tb=bool(tb), out=c, compute=C)
         del a, b, c
+    torch.cuda.synchronize()
+elif what == "conv":
+    # second conv layer of the ds2 front-end at B=32 x 10 s: [500,32,40,32 (pitch 64)] -> [500,32,20,32 (pitch 64)], 11x21 / (1,2)
+    T, B, F, Cc, pitch, N, kt, kf, st, sf = 500, 32, 40, 32, 64, 64, 11, 21, 1, 2
+    x = torch.randn(T * B * F, pitch, device="cuda")
+    w = torch.randn(kt * kf * Cc, N, device="cuda") * 0.01
+    bias = torch.zeros(N, device="cuda")
+    y = torch.empty(T * B * 20, N, device="cuda")
+    dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(bias)
+    for _ in range(2):
+        ops.conv2d_fwd(x, pitch, w, bias, y, T, B, F, Cc, kt, kf, st, sf, compute=C)
+        dy = torch.randn_like(y)
+        ops.conv2d_bwd(x, pitch, w, y, dy, dx, dw, db, T, B, F, Cc, kt, kf, st, sf, compute=C)
+    torch.cuda.synchronize()
+elif what == "beam":
+    T, B, V = 300, 32, 29
+    rng = np.random.default_rng(0)
+    logits = torch.from_numpy((rng.standard_normal((T, B, V)) * 3).astype(np.float32)).cuda()
+    sl = torch.full((B,), T, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        ops.beam_search(logits, sl, beam_width=1024)
     torch.cuda.synchronize()
 elif what == "gemm":
     for (M, N, K, ta, tb) in [(32000, 16384, 4096, 0, 0), (4096, 16384, 32000, 1, 0), (32000, 4096, 16384, 0, 1)]:
