@@ -345,6 +345,10 @@ def run_ctc(args, torch, lib, ops, synthetic, peaks, rank, world):
     ms_e2e = (time.perf_counter() - t0) * 1e3 / K
     alg_bytes = B * (2 * T * V * 4 + L * 4 + 12)
     gbs = alg_bytes / (ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ctc_dram_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     line = {
         "metric": "audio-frames/s (CTC forward-backward only)", "value": B * T / (ms * 1e-3), "unit": "frames/s",
         "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -354,7 +358,9 @@ def run_ctc(args, torch, lib, ops, synthetic, peaks, rank, world):
                 "d2h_bytes_per_step": int(logits.numel() * 4)},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": gbs / peaks["hbm_gbs"], "traffic": None, "note": "peak of %s" % peaks["source"]},
+                     "frac": gbs / peaks["hbm_gbs"], "traffic": traffic, "kernel": "ctc_loss_kernel",
+                     "note": "algorithmic bytes = logits in + gradient out + labels (SURVEY 8d); the kernel is bound by instruction "
+                             "issue of the alpha/beta recursion (3 sweeps of 2L+1 states x T frames), not by HBM; peak of %s" % peaks["source"]},
     }
     if rank == 0:
         print(json.dumps(line))
