@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "ctc"])
-    ap.add_argument("--compute", default="bf16x3", choices=["bf16x3", "tf32", "fp32"])
+    ap.add_argument("--compute", default="bf16x3", choices=["bf16x3", "tf32", "fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=CFG2_B)
     ap.add_argument("--frames", type=int, default=CFG2_T)
     ap.add_argument("--units", type=int, default=2048, help="debug: shrink D and H")
@@ -254,7 +254,7 @@ def run_ours(args):
     rec_flops = 2 * (cfg.num_layers_rnn * 2 * 2 * H * 4 * H) * T_rnn / T     # recurrent matvec fwd + bwd, per input frame
     tc_flops = (3.0 * flops_per_frame_fwd(cfg) - rec_flops - 3 * 2 * D * cfg.num_classes * T_rnn / T) * B * T * K
     gemm_tflops = tc_flops / (prof_ms[2] * 1e-3) / 1e12 if prof_ms[2] > 0 else 0.0
-    mma_per_mac = {"bf16x3": 3.0, "tf32": 2.0, "fp32": 1.0}[args.compute]
+    mma_per_mac = {"bf16x3": 3.0, "tf32": 2.0, "fp32": 1.0, "bf16": 1.0}[args.compute]
     gemm_peak = peaks["bf16_tflops_sustained"] / mma_per_mac
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "lstm_dram_traffic.json")
@@ -272,7 +272,9 @@ def run_ours(args):
                    "global_batch": gb, "params": model.num_params,
                    "arithmetic": {"bf16x3": "fp32 storage; GEMMs and recurrence as 3 (6 for ReLU-kinked layers) bf16 tcgen05 products "
                                             "of split operands, fp32 TMEM accumulation (fp32-level accuracy)",
-                                  "tf32": "fp32 storage; tcgen05 kind::tf32", "fp32": "SIMT FFMA"}[args.compute],
+                                  "tf32": "fp32 storage; tcgen05 kind::tf32", "fp32": "SIMT FFMA",
+                                  "bf16": "BASELINE cfg3 arithmetic: GEMM operands rounded to bf16, one tcgen05 product, fp32 accumulation, "
+                                          "fp32 master weights and CTC; LSTM recurrence bf16x3"}[args.compute],
                    "l2_policy": "inputs larger than L2 (>=7 GB of activations per step), no explicit flush"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(x.nbytes + sl.nbytes + lab.nbytes + ll.nbytes),
                 "d2h_bytes_per_step": 4 + 4 * B},

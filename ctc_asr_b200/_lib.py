@@ -10,8 +10,8 @@ CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0
 CELL_RNN_TANH, CELL_RNN_RELU, CELL_LSTM, CELL_GRU = 0, 1, 2, 3
-COMPUTE_FP32, COMPUTE_TF32, COMPUTE_BF16X3 = 0, 1, 2
-COMPUTE_ID = {"fp32": COMPUTE_FP32, "tf32": COMPUTE_TF32, "bf16x3": COMPUTE_BF16X3}
+COMPUTE_FP32, COMPUTE_TF32, COMPUTE_BF16X3, COMPUTE_BF16 = 0, 1, 2, 3
+COMPUTE_ID = {"fp32": COMPUTE_FP32, "tf32": COMPUTE_TF32, "bf16x3": COMPUTE_BF16X3, "bf16": COMPUTE_BF16}
 
 _vp, _i, _f, _u32, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_uint32, ctypes.c_size_t
 

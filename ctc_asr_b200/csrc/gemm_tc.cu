@@ -14,6 +14,8 @@
 //           ~2^-16) or, for layers whose output goes through a ReLU kink (`precise`), the 6 products
 //           of a 3-piece split (error ~2^-23) — all accumulated in the same fp32 TMEM tile.
 //           Same bytes per element as fp32 (2 x 2 B), 1.5x the tensor time of TF32.
+//   BF16    one bf16 piece per operand, one product (CTCASR_COMPUTE_BF16): plain bf16 tensor-core arithmetic
+//           with fp32 accumulation — BASELINE cfg3's "bf16" arithmetic, 2^-9 operand rounding, 3x fewer MMAs.
 //
 // Structure (persistent, one CTA per SM, 192 threads):
 //   warp 4      TMA producer: cp.async.bulk.tensor boxes into a shared-memory ring
@@ -48,21 +50,21 @@ constexpr int NTHREADS = 192;
 constexpr int STG_LD = 36;                                      // epilogue staging tile: 32 rows x 36 floats per warp
 constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
 
-enum { MODE_TF32 = 1, MODE_BF16X3 = 2, MODE_BF16X6 = 3 };     // bf16 modes: value = pieces per operand
+enum { MODE_TF32 = 1, MODE_BF16X3 = 2, MODE_BF16X6 = 3, MODE_BF16X1 = 4 };   // X3 / X6: value = pieces per operand
 
 template <int MODE>
 struct Cfg {
     static constexpr bool kBf16 = MODE != MODE_TF32;
-    static constexpr int NP = kBf16 ? MODE : 1;                 // pieces per operand
+    static constexpr int NP = (kBf16 && MODE != MODE_BF16X1) ? MODE : 1;     // pieces per operand
     static constexpr int ESZ = kBf16 ? 2 : 4;
     static constexpr int A_PIECE = BM * BK * ESZ, B_PIECE = BN * BK * ESZ;
     static constexpr int STAGE_BYTES = NP * (A_PIECE + B_PIECE);
-    static constexpr int NSTAGE = MODE == MODE_BF16X6 ? 2 : 4;
+    static constexpr int NSTAGE = MODE == MODE_BF16X6 ? 2 : (MODE == MODE_BF16X1 ? 6 : 4);
     static constexpr int UMMA_K = kBf16 ? 16 : 8;
     static constexpr int KSTEPS = BK / UMMA_K;
     static constexpr int MN_BOX = 128 / ESZ;                    // m|n elements per 128-B row
     static constexpr int MN_BOX_BYTES = BK * 128;               // one MN-major box: 32 k-rows x 128 B
-    static constexpr int NPROD = MODE == MODE_TF32 ? 1 : (MODE == MODE_BF16X3 ? 3 : 6);
+    static constexpr int NPROD = (MODE == MODE_TF32 || MODE == MODE_BF16X1) ? 1 : (MODE == MODE_BF16X3 ? 3 : 6);
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
     // per k-step advance of the descriptor start address (bytes)
     static constexpr int KMAJ_STEP = UMMA_K * ESZ;              // inside the swizzled row
@@ -559,7 +561,7 @@ bool gemm_tc_eligible(const GemmArgs &g)
 // half-updated buffers behind.
 int gemm_scratch_check(int compute, int nz, int M, int N, int K)
 {
-    if (compute != CTCASR_COMPUTE_BF16X3) return CTCASR_OK;
+    if (compute != CTCASR_COMPUTE_BF16X3 && compute != CTCASR_COMPUTE_BF16) return CTCASR_OK;
     auto pad = [](int v) { return (size_t)((v + 7) / 8 * 8); };
     const size_t need = (size_t)nz * (align_up(6 * pad(M) * pad(K), 1024) + align_up(6 * pad(K) * pad(N), 1024));
     if (need > tc::g_scratch_bytes) {
@@ -571,7 +573,7 @@ int gemm_scratch_check(int compute, int nz, int M, int N, int K)
 
 int split_scope_begin(int compute, const size_t *elems, int n)
 {
-    if (compute != CTCASR_COMPUTE_BF16X3) return CTCASR_OK;
+    if (compute != CTCASR_COMPUTE_BF16X3 && compute != CTCASR_COMPUTE_BF16) return CTCASR_OK;
     size_t need = 0;
     for (int i = 0; i < n; ++i) need += align_up(6 * elems[i], 1024);
     if (need > tc::g_scratch_bytes) {
@@ -594,6 +596,7 @@ int gemm_tc(const GemmArgs &g, int compute, cudaStream_t stream)
 {
     if (!gemm_tc_eligible(g)) return fail(CTCASR_ERR_UNSUPPORTED, "gemm_tc: shape not eligible");
     if (compute == CTCASR_COMPUTE_TF32) return tc::launch<tc::MODE_TF32>(g, stream);
+    if (compute == CTCASR_COMPUTE_BF16) return tc::launch<tc::MODE_BF16X1>(g, stream);
     if (compute == CTCASR_COMPUTE_BF16X3)
         return g.precise ? tc::launch<tc::MODE_BF16X6>(g, stream) : tc::launch<tc::MODE_BF16X3>(g, stream);
     return fail(CTCASR_ERR_INVALID, "gemm_tc: compute mode %d", compute);

@@ -57,7 +57,9 @@ class ModelConfig:
     # 'fp32'  : SIMT FFMA kernels everywhere (exact-order fp32)
     # 'bf16x3': tcgen05 kind::f16 on bf16-split operands, 3 (6 for ReLU-kinked layers) products
     #           accumulated in fp32 TMEM: fp32-level accuracy at tensor-core speed (default)
-    # 'tf32'  : tcgen05 kind::tf32 on the fp32 operands: fastest, 2^-11 operand rounding
+    # 'tf32'  : tcgen05 kind::tf32 on the fp32 operands, 2^-11 operand rounding
+    # 'bf16'  : BASELINE cfg3: GEMM operands rounded to bf16 (one product), fp32 accumulation, fp32 master weights
+    #           and fp32 CTC; the LSTM recurrence stays bf16x3.  Fastest; gradients within ~2e-2 of fp32
     compute: str = "bf16x3"
     decoder: str = "beam_search"        # decode_fn: 'beam_search' (asr/model.py:292-296) | 'greedy'
 
@@ -75,8 +77,8 @@ class ModelConfig:
                 raise ValueError("conv_filters[-1] must be a multiple of 8 and >= 64")
         if self.rnn_cell not in RNN_CELLS:
             raise ValueError("rnn_cell must be one of {}".format(RNN_CELLS))
-        if self.compute not in ("fp32", "tf32", "bf16x3"):
-            raise ValueError("compute must be 'fp32', 'bf16x3' or 'tf32'")
+        if self.compute not in ("fp32", "tf32", "bf16x3", "bf16"):
+            raise ValueError("compute must be 'fp32', 'bf16x3', 'tf32' or 'bf16'")
 
     def replace(self, **kw):
         return dataclasses.replace(self, **kw)

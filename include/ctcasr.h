@@ -43,8 +43,10 @@ enum { CTCASR_CELL_RNN_TANH = 0, CTCASR_CELL_RNN_RELU = 1, CTCASR_CELL_LSTM = 2,
 enum {
     CTCASR_COMPUTE_FP32 = 0,      /* SIMT FFMA, fp32 everywhere (parity mode, any shape) */
     CTCASR_COMPUTE_TF32 = 1,      /* tcgen05 kind::tf32, fp32 storage + fp32 accumulate in TMEM */
-    CTCASR_COMPUTE_BF16X3 = 2     /* tcgen05 kind::f16 on bf16-split operands (a = a1 + a2 [+ a3]),
+    CTCASR_COMPUTE_BF16X3 = 2,    /* tcgen05 kind::f16 on bf16-split operands (a = a1 + a2 [+ a3]),
                                      3 or 6 products accumulated in fp32 TMEM: fp32-level accuracy */
+    CTCASR_COMPUTE_BF16 = 3       /* GEMMs: operands rounded to bf16, one tcgen05 kind::f16 product, fp32 accumulate
+                                     (fp32 master weights, fp32 CTC; the LSTM recurrence keeps the bf16x3 kernel) */
 };
 
 /* per-utterance CTC status words (TF raises InvalidArgumentError for 1..3) */

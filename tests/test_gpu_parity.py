@@ -276,7 +276,7 @@ def test_adam_vs_oracle():
 
 
 # --------------------------------------------------------------------------------- whole hot path
-def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL):
+def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL, ltol=RTOL):
     from ctc_asr_b200.model import CTCModel
     params = synthetic.init_params(cfg, seed=1)
     rng = np.random.default_rng(seed)
@@ -295,8 +295,8 @@ def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL):
     torch.cuda.synchronize()
     oloss, ograds, ologits, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll)
     sl = sl_out.cpu().numpy()                          # ds2: the conv length for every utterance
-    assert rel_err(logits.cpu().numpy(), ologits) < RTOL
-    assert abs(float(loss) - oloss) / abs(oloss) < RTOL
+    assert rel_err(logits.cpu().numpy(), ologits) < ltol
+    assert abs(float(loss) - oloss) / abs(oloss) < ltol
     got = model.grads_numpy()
     errs = {k: rel_err(got[k], want) for k, want in ograds.items()}
     print("gradient max-rel-err per tensor:", {k: "%.2e" % v for k, v in errs.items()})
@@ -419,6 +419,32 @@ def test_whole_path_tf32_lstm():
     # the lowest layers at a few 1e-2 (measured 3.4e-2).  tf32 is the optional fast mode; the 1e-3
     # bar of north_star is met by compute='bf16x3' (default, benchmarked) and compute='fp32'.
     _whole_path(cfg, B=8, T=64, L=10, ragged=True, gtol=6e-2)
+
+
+def test_whole_path_bf16_cfg3_arithmetic():
+    """BASELINE cfg3 ("DS2 bf16"): GEMM operands rounded to bf16 (one tcgen05 product, fp32 accumulation), fp32
+    master weights, fp32 CTC, bf16x3 recurrence.  This is reduced precision by construction: the tolerance
+    written here is bf16's (2^-9 operand rounding per GEMM input, mask flips in the dense stack), not the
+    1e-3 bar, which compute='bf16x3' and 'fp32' meet."""
+    cfg = ModelConfig(num_layers_dense=3, num_units_dense=256, num_layers_rnn=2, num_units_rnn=64,
+                      rnn_cell="lstm", cudnn=False, dense_dropout_rate=0.0, compute="bf16")
+    _whole_path(cfg, B=8, T=64, L=10, ragged=True, gtol=2e-1, ltol=2e-2)     # measured: 1.2e-1 (first dense kernel), 4e-3 (RNN)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, True)])
+def test_gemm_bf16_single_product(ta, tb):
+    rng = np.random.default_rng(9)
+    M, N, K = 1000, 264, 1048
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    c = ops.gemm(dev(a), dev(b), ta=ta, tb=tb, compute=_lib.COMPUTE_BF16).cpu().numpy().astype(np.float64)
+    # exact reference of what the kernel computes: operands rounded to bf16, products summed in high precision
+    ar = torch.from_numpy(a).to(torch.bfloat16).to(torch.float64).numpy()
+    br = torch.from_numpy(b).to(torch.bfloat16).to(torch.float64).numpy()
+    want = (ar.T if ta else ar) @ (br.T if tb else br)
+    assert rel_err(c, want) < 1e-5                       # only the fp32 accumulation order differs
+    full = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    assert 1e-4 < rel_err(c, full) < 1e-2                # and it really is bf16 arithmetic
 
 
 # ------------------------------------------------- tcgen05 path, fp32-accurate (compute = bf16x3)
