@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--units", type=int, default=2048, help="debug: shrink D and H")
     ap.add_argument("--model", default="ds1", choices=["ds1", "ds2"],
                     help="front-end: ds1 = 3 dense layers (BASELINE configs[1], the default), ds2 = 3 conv layers")
+    ap.add_argument("--cell", default="lstm", choices=["lstm", "gru", "rnn_relu", "rnn_tanh"],
+                    help="rnn_cell of the reference's menu (asr/params.py:48); the metric is quoted on lstm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames per utterance in the CPU sample (0 = auto)")
     return ap.parse_args()
@@ -181,7 +183,7 @@ def run_ours(args):
         return run_ctc(args, torch, lib, ops, synthetic, peaks, rank, world)
 
     cfg = ModelConfig(**dict(CFG2, num_units_dense=args.units, num_units_rnn=args.units, compute=args.compute,
-                             used_model=args.model))
+                             used_model=args.model, rnn_cell=args.cell, cudnn=args.cell != "lstm"))
     B, T, L = args.batch, args.frames, min(CFG2_L, max(1, args.frames // 4))
     from ctc_asr_b200.params import conv_out_frames
     T_rnn = conv_out_frames(cfg, T)                      # ds2: the conv stack halves the frame rate
@@ -264,9 +266,10 @@ def run_ours(args):
         "metric": "audio-frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.compute, "data": "synthetic",
-        "config": {"workload": "cfg2: %s + 2 BiLSTM-%d + 2 dense (3%s2r2d), per-GPU B=%d x T=%d frames x 80 features, "
+        "config": {"workload": "cfg2: %s + 2 Bi%s-%d + 2 dense (3%s2r2d), per-GPU B=%d x T=%d frames x 80 features, "
                                "L=%d labels, fwd + CTC + bwd + %sAdam, dense dropout 0.1" % (
                                    "3 dense" if args.model == "ds1" else "3 conv (ds2 front-end, RNN at %d frames)" % T_rnn,
+                                   {"lstm": "LSTM", "gru": "GRU", "rnn_relu": "RNN(relu)", "rnn_tanh": "RNN(tanh)"}[args.cell],
                                    args.units, "d" if args.model == "ds1" else "c", B, T, L,
                                    "NCCL all-reduce + " if world > 1 else ""),
                    "global_batch": gb, "params": model.num_params,

@@ -17,6 +17,8 @@ struct GemmArgs {
 };
 
 int gemm_simt(const GemmArgs &g, cudaStream_t stream);
+// small-M (batch rows) product of one recurrence step, both directions; falls back to gemm_simt (step_gemm.cu)
+int step_gemm(const GemmArgs &g, cudaStream_t stream);
 // C = epilogue(sum over the S raw partial results part[s][z][M][N], added in slice order: deterministic)
 int splitk_reduce(const GemmArgs &g, int S, float *part, cudaStream_t stream);
 // returns CTCASR_ERR_UNSUPPORTED (without touching C) when the shape/alignment is not eligible

@@ -94,7 +94,7 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
                 h.epi.accumulate = 0; h.ldc = GH;
                 h.C[0] = s.rh; h.C[1] = s.rh + (size_t)B * GH;
             }
-            rc = gemm_simt(h, stream);
+            rc = step_gemm(h, stream);
             if (rc != CTCASR_OK) return rc;
         }
         rc = rnn_cell_fwd(s, i, stream);
@@ -149,7 +149,7 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
                 h.A[0] = dzh + (size_t)tf * B * 2 * GH;           h.A[1] = dzh + (size_t)tb * B * 2 * GH + GH;
                 h.B[0] = wh;                                      h.B[1] = wh + (size_t)H * GH;
                 h.C[0] = s.dh_rec;                                h.C[1] = s.dh_rec + (size_t)B * H;
-                rc = gemm_simt(h, stream);
+                rc = step_gemm(h, stream);
                 if (rc != CTCASR_OK) return rc;
             }
         }

@@ -235,15 +235,19 @@ def test_dense_fwd_bwd_vs_oracle(rate):
 # ------------------------------------------------------------------------------------------ BiRNN
 @pytest.mark.parametrize("cell", ["rnn_tanh", "rnn_relu", "lstm", "gru"])
 @pytest.mark.parametrize("use_len", [True, False])
-def test_birnn_layer_vs_oracle(cell, use_len):
+@pytest.mark.parametrize("shape", [(23, 5, 12, 20), (17, 7, 16, 64), (9, 40, 8, 128)])
+def test_birnn_layer_vs_oracle(cell, use_len, shape):
+    """Stepwise recurrent path (fp32): H = 20 runs the generic SIMT product per frame, H = 64 / 128 the
+    double-buffered small-batch kernel (step_gemm.cu); B = 40 spans two 32-row blocks."""
     rng = np.random.default_rng(6)
-    T, B, nin, H = 23, 5, 12, 20
+    T, B, nin, H = shape
     cid = ref.CELL_IDS[cell]
     G = ref.NUM_GATES[cid]
     x = rng.standard_normal((T, B, nin)).astype(np.float32)
-    sl = np.array([23, 20, 11, 3, 1], np.int32)
+    sl = np.maximum(1, T - (5 * np.arange(B)) % T).astype(np.int32)
+    sl[-1] = 1
     wx = (rng.standard_normal((nin, 2 * G * H)) * 0.3).astype(np.float32)
-    wh = (rng.standard_normal((2, H, G * H)) * 0.3).astype(np.float32)
+    wh = (rng.standard_normal((2, H, G * H)) * (0.3 if H <= 32 else 1.0 / np.sqrt(H))).astype(np.float32)
     bias = (rng.standard_normal(2 * G * H + (2 * H if cell == "gru" else 0)) * 0.1).astype(np.float32)
     dy = rng.standard_normal((T, B, 2 * H)).astype(np.float32)
     rb, _ = ops.birnn_sizes(T, B, nin, H, cid)
