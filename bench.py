@@ -141,7 +141,10 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = ModelConfig(**dict(CFG2, num_units_dense=args.units, num_units_rnn=args.units, dense_dropout_rate=0.0))
-    sample_T = args.cpu_sample_frames or CPU_SAMPLE_FRAMES
+    # bounded sample: keep the whole --steps K --warmup W run near two minutes (~0.11 s per frame of a B=32 step on
+    # 16-24 host cores), between 4 and CPU_SAMPLE_FRAMES frames per utterance
+    auto_T = max(4, min(CPU_SAMPLE_FRAMES, int(120.0 / (0.11 * (args.steps + args.warmup)))))
+    sample_T = args.cpu_sample_frames or auto_T
     L = max(1, min(CFG2_L, sample_T // 4))
     t0 = time.perf_counter()
     fps, dt, cores = cpu_reference_frames_per_s(cfg, args.batch, sample_T, L, steps=args.steps, warmup=args.warmup)

@@ -19,6 +19,17 @@ struct GemmArgs {
 int gemm_simt(const GemmArgs &g, cudaStream_t stream);
 // small-M (batch rows) product of one recurrence step, both directions; falls back to gemm_simt (step_gemm.cu)
 int step_gemm(const GemmArgs &g, cudaStream_t stream);
+// the same product with the cell math of a one-gate cell (tanh / ReLU RNN) in its epilogue
+struct StepCell {
+    int mode = 0;                 // 1 forward, 2 backward
+    int cell = 0, use_len = 0;
+    const int *seq_len = nullptr;
+    int t[2] = {0, 0};            // frame of the forward / backward direction this step computes
+    float *y[2] = {nullptr, nullptr};         // forward: layer output rows of those frames (column offset of the direction applied)
+    const float *dy[2] = {nullptr, nullptr};  // backward: upstream gradient rows
+    int ldy = 0;
+};
+int step_gemm_cell(const GemmArgs &g, const StepCell &sc, cudaStream_t stream);
 // C = epilogue(sum over the S raw partial results part[s][z][M][N], added in slice order: deterministic)
 int splitk_reduce(const GemmArgs &g, int S, float *part, cudaStream_t stream);
 // returns CTCASR_ERR_UNSUPPORTED (without touching C) when the shape/alignment is not eligible

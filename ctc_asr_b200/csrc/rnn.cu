@@ -81,6 +81,7 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
     s.dh_rec = nullptr; s.dc_carry = nullptr;
     const bool gru = cell == CTCASR_CELL_GRU;
     s.rh = reinterpret_cast<float *>(ws) + (size_t)4 * B * H; s.dzr = nullptr; s.bias_rn = bias + 2 * GH;
+    const bool one_gate = cell == CTCASR_CELL_RNN_TANH || cell == CTCASR_CELL_RNN_RELU;
     for (int i = 0; i < T; ++i) {
         if (i > 0) {
             GemmArgs h;
@@ -90,6 +91,14 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
             h.A[0] = y + (size_t)(tf - 1) * B * 2 * H;            h.A[1] = y + (size_t)(tb + 1) * B * 2 * H + H;
             h.B[0] = wh;                                          h.B[1] = wh + (size_t)H * GH;
             h.C[0] = r.gates + (size_t)tf * B * 2 * GH;           h.C[1] = r.gates + (size_t)tb * B * 2 * GH + GH;
+            if (one_gate) {     // product + cell math in one launch
+                StepCell sc;
+                sc.mode = 1; sc.cell = cell; sc.use_len = use_len; sc.seq_len = seq_len; sc.t[0] = tf; sc.t[1] = tb;
+                sc.y[0] = y + (size_t)tf * B * 2 * H; sc.y[1] = y + (size_t)tb * B * 2 * H + H; sc.ldy = 2 * H;
+                rc = step_gemm_cell(h, sc, stream);
+                if (rc == CTCASR_OK) continue;
+                if (rc != CTCASR_ERR_UNSUPPORTED) return rc;
+            }
             if (gru) {      // the candidate gate multiplies h Rn by r: keep h Wh apart from the input projection
                 h.epi.accumulate = 0; h.ldc = GH;
                 h.C[0] = s.rh; h.C[1] = s.rh + (size_t)B * GH;
@@ -138,9 +147,13 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
         s.dc_carry = s.dh_rec + (size_t)2 * B * H;
         s.rh = nullptr; s.dzr = r.dzr; s.bias_rn = nullptr;
         CTCASR_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)4 * B * H * sizeof(float), stream));
+        const bool one_gate = cell == CTCASR_CELL_RNN_TANH || cell == CTCASR_CELL_RNN_RELU;
+        bool fused_ok = one_gate;           // frame i's cell math rides in the epilogue of the product that feeds it
         for (int i = T - 1; i >= 0; --i) {
-            rc = rnn_cell_bwd(s, i, stream);
-            if (rc != CTCASR_OK) return rc;
+            if (!(fused_ok && i < T - 1)) {
+                rc = rnn_cell_bwd(s, i, stream);
+                if (rc != CTCASR_OK) return rc;
+            }
             if (i > 0) {     // dh_rec[d] = dz_t[d] Wh[d]^T
                 GemmArgs h;
                 h.nz = 2; h.M = B; h.N = H; h.K = GH; h.tb = 1; h.lda = 2 * GH; h.ldb = GH; h.ldc = H;
@@ -149,6 +162,19 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
                 h.A[0] = dzh + (size_t)tf * B * 2 * GH;           h.A[1] = dzh + (size_t)tb * B * 2 * GH + GH;
                 h.B[0] = wh;                                      h.B[1] = wh + (size_t)H * GH;
                 h.C[0] = s.dh_rec;                                h.C[1] = s.dh_rec + (size_t)B * H;
+                if (fused_ok) {     // writes dz of frame i-1 (processing order) straight into its gates slot
+                    GemmArgs f = h;
+                    const int pf = i - 1, pb = T - i;
+                    f.ldc = 2 * GH;
+                    f.C[0] = r.gates + (size_t)pf * B * 2 * GH;   f.C[1] = r.gates + (size_t)pb * B * 2 * GH + GH;
+                    StepCell sc;
+                    sc.mode = 2; sc.cell = cell; sc.use_len = use_len; sc.seq_len = seq_len; sc.t[0] = pf; sc.t[1] = pb;
+                    sc.dy[0] = dy + (size_t)pf * B * 2 * H; sc.dy[1] = dy + (size_t)pb * B * 2 * H + H; sc.ldy = 2 * H;
+                    rc = step_gemm_cell(f, sc, stream);
+                    if (rc == CTCASR_OK) continue;
+                    if (rc != CTCASR_ERR_UNSUPPORTED) return rc;
+                    fused_ok = false;       // not eligible (decided at the first product): two launches per frame
+                }
                 rc = step_gemm(h, stream);
                 if (rc != CTCASR_OK) return rc;
             }
