@@ -22,6 +22,21 @@ NORMALIZATIONS = {"none": 0, "local": 1, "local_scalar": 2}  # :194
 SAMPLING_RATE = 16000                                       # asr/params.py:102
 
 
+_pinned = {}
+
+
+def _pinned_i16(n):
+    """Grow-only pinned staging buffer for the PCM (allocating pinned memory costs milliseconds per call)."""
+    ev = _pinned.get("copied")
+    if ev is not None:
+        ev.synchronize()                                  # the previous call's H2D copy has read the buffer
+    buf = _pinned.get("pcm")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1 << 20), dtype=torch.int16).pin_memory()
+        _pinned["pcm"] = buf
+    return buf[:n]
+
+
 def num_frames(num_samples, sampling_rate=SAMPLING_RATE):
     return _lib.load().ctcasr_feature_frames(int(num_samples), int(sampling_rate))
 
@@ -44,10 +59,13 @@ def featurize(audio, feature_type="mfcc", feature_normalization="local", drop_ev
     B = len(audio)
     lens = np.array([len(a) for a in audio], np.int32)
     nmax = int(lens.max())
-    host = torch.zeros((B, nmax), dtype=torch.int16).pin_memory()
+    host = _pinned_i16(B * nmax).view(B, nmax)
     for b, a in enumerate(audio):
         host[b, :len(a)] = torch.from_numpy(a)
+        host[b, len(a):] = 0
     dev_audio = host.to(device, non_blocking=True)
+    _pinned["copied"] = torch.cuda.Event()
+    _pinned["copied"].record()
     tl = num_frames(nmax, sampling_rate)
     tmax = (tl + 1) // 2 if drop_every_second_frame else tl
     out = torch.empty((B, tmax, num_features), dtype=torch.float32, device=device)
