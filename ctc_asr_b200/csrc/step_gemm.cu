@@ -8,19 +8,27 @@
 #include "gemm.cuh"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace ctcasr {
 namespace stepg {
 namespace cg = cooperative_groups;
 
-constexpr int KSPLIT = 4;       // CTAs per cluster: each takes a quarter of K, partial sums meet through DSMEM
+constexpr int BM = 32, BKC = 32, LDS_ = BKC + 4;               // 36-float rows: 16-B aligned, conflict-light
 
-constexpr int BM = 32, BN = 64, BKC = 32, LDS_ = BKC + 4;      // 36-float rows: 16-B aligned, conflict-light
-constexpr int LDW_ = BN + 4;                                    // W rows in the [k][n] layout
-constexpr int NSTAGE = 4;                                       // chunks in flight
-constexpr int A_FLOATS = BM * LDS_;                             // A chunk [32 m][32 k]
-constexpr int STAGE_FLOATS = A_FLOATS + 64 * LDS_;              // + W chunk: [64 n][32 k] (TB) or [32 k][64 n] (2176 <= 2304)
-constexpr int SMEM_BYTES = NSTAGE * STAGE_FLOATS * 4;           // 55,296 B: four CTAs per SM
+// NW warps per CTA, NC output columns per lane (tile = 32 rows x 32 NC columns), KS CTAs per cluster (K split)
+template <int NW, int NC, int KS>
+struct Cfg {
+    static constexpr int NT = 32 * NW, BN = 32 * NC, LDW = BN + 4;
+    static constexpr int A_FLOATS = BM * LDS_;
+    static constexpr int W_FLOATS = BN * LDS_ > BKC * LDW ? BN * LDS_ : BKC * LDW;   // [BN n][32 k] (TB) or [32 k][BN n]
+    static constexpr int STAGE_FLOATS = A_FLOATS + W_FLOATS;
+    static constexpr int NSTAGE = NC == 1 ? 6 : 4;              // 55,296 B either way
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_FLOATS * 4;
+    static constexpr int QW = 8 / NW;                           // groups of four k per warp and chunk
+    static constexpr int RLD = BN + 1;
+    static_assert(NW * BM * RLD * 4 <= SMEM_BYTES, "reduction tile must fit in the pipeline buffers");
+};
 
 __device__ __forceinline__ void cp16(void *smem, const void *gmem)
 {
@@ -34,56 +42,58 @@ __device__ __forceinline__ void cp16(void *smem, const void *gmem)
 //   1 forward   C holds the input projection P_t;  h = act(P_t + acc) -> C (saved activation) and y
 //   2 backward  C holds the saved activation h_t;  dz = (dy_t + acc) act'(h_t) -> C
 // (rows past an utterance's length produce zeros: dynamic_rnn(sequence_length) semantics, rnn.cu)
-// Thread = two output columns (lane, lane + 32), all 32 batch rows in registers: per group of four k the warp
-// reads the W values of its columns and the 32 A rows as BROADCAST 16-B loads — 34 shared-memory instructions
-// per 256 FMAs (a 16-B shared load costs four issue cycles even when broadcast: with a 2 x 2 register tile, or
-// with one column per thread, the kernel was bound by the shared-memory pipe at 40-50 us a frame).  The four
-// warps of the CTA split every 32-k chunk between them; partial sums are added in a fixed order.
-// One SM's worth of this product (a 32 x 32 tile over all of K) is only four warps: to fill the FMA pipes the
-// K range is cut over a cluster of four CTAs (4 x as many resident warps per SM to hide the shared-memory
-// latency); rank 0 adds the 16 partial tiles (cluster rank, then warp: fixed order) out of its peers'
-// shared memory and runs the epilogue.
-template <bool TB, int MODE>
-__global__ void __cluster_dims__(1, 1, KSPLIT) __launch_bounds__(128) step_gemm_kernel(const GemmArgs g, const StepCell sc)
+//
+// A lane owns NC output columns and keeps all 32 batch rows in registers: per group of four k the warp reads
+// the W values of its columns and the 32 A rows as BROADCAST 16-B loads.  The warps of a CTA split every 32-k
+// chunk between them, the K range is cut over a cluster of KS CTAs (more resident warps per SM to hide the
+// shared-memory latency), and rank 0 adds the KS x NW partial tiles out of its peers' shared memory in a
+// fixed order (deterministic) before the epilogue.
+template <bool TB, int MODE, int NW, int NC, int KS>
+__global__ void __cluster_dims__(1, 1, KS) __launch_bounds__(32 * NW) step_gemm_kernel(const GemmArgs g, const StepCell sc)
 {
+    using C_ = Cfg<NW, NC, KS>;
+    constexpr int NT = C_::NT, BN = C_::BN, LDW = C_::LDW, NSTAGE = C_::NSTAGE, STAGE_FLOATS = C_::STAGE_FLOATS;
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int krank = (int)cluster.block_rank();
-    const int z = blockIdx.z / KSPLIT, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int z = blockIdx.z / KS, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const float *__restrict__ A = g.A[z] + (size_t)m0 * g.lda;
     const float *__restrict__ W = g.B[z];
+    const int lda = g.lda, ldb = g.ldb;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rows = min(BM, g.M - m0);
     // rows >= M of the A chunks are never loaded: zero them once
-    for (int i = tid; i < NSTAGE * STAGE_FLOATS; i += 128) smem[i] = 0.f;
+    for (int i = tid; i < NSTAGE * STAGE_FLOATS; i += NT) smem[i] = 0.f;
     __syncthreads();
-    // per chunk every thread moves two 16-B pieces of A (rows lr, lr + 16) and four of W
-    const int lr = tid >> 3, lc4 = (tid & 7) * 4;
-    const float *a_src = A + (size_t)lr * g.lda + lc4;
     auto load = [&](int chunk) {
         float *st = smem + (chunk % NSTAGE) * STAGE_FLOATS;
-        if (lr < rows) cp16(st + lr * LDS_ + lc4, a_src + (size_t)chunk * BKC);
-        if (lr + 16 < rows) cp16(st + (lr + 16) * LDS_ + lc4, a_src + (size_t)16 * g.lda + (size_t)chunk * BKC);
-        float *ws = st + A_FLOATS;
-        if (TB) {       // W[n][k]: 64 rows (n) of 32 k
+        float *ws = st + C_::A_FLOATS;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = lr + 16 * j;
-                cp16(ws + r * LDS_ + lc4, W + (size_t)(n0 + r) * g.ldb + (size_t)chunk * BKC + lc4);
+        for (int i = tid; i < BM * 8; i += NT) {
+            const int r = i >> 3, c4 = (i & 7) * 4;
+            if (r < rows) cp16(st + r * LDS_ + c4, A + (size_t)r * lda + (size_t)chunk * BKC + c4);
+        }
+        if (TB) {       // W[n][k]: BN rows (n) of 32 k
+#pragma unroll
+            for (int i = tid; i < BN * 8; i += NT) {
+                const int r = i >> 3, c4 = (i & 7) * 4;
+                cp16(ws + r * LDS_ + c4, W + (size_t)(n0 + r) * ldb + (size_t)chunk * BKC + c4);
             }
-        } else {        // W[k][n]: 32 rows (k) of 64 n: 16 pieces per row
+        } else {        // W[k][n]: 32 rows (k) of BN n
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = tid + 128 * j, r = i >> 4, c4 = (i & 15) * 4;
-                cp16(ws + r * LDW_ + c4, W + ((size_t)chunk * BKC + r) * g.ldb + n0 + c4);
+            for (int i = tid; i < BKC * (BN / 4); i += NT) {
+                const int r = i / (BN / 4), c4 = (i % (BN / 4)) * 4;
+                cp16(ws + r * LDW + c4, W + ((size_t)chunk * BKC + r) * ldb + n0 + c4);
             }
         }
     };
 
-    float acc0[BM], acc1[BM];                                   // columns lane and lane + 32
+    float acc[NC][BM];
 #pragma unroll
-    for (int m = 0; m < BM; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
-    const int nk = g.K / BKC / KSPLIT, c0 = krank * nk;           // this CTA's chunks: [c0, c0 + nk)
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int m = 0; m < BM; ++m) acc[c][m] = 0.f;
+    const int nk = g.K / BKC / KS, c0 = krank * nk;              // this CTA's chunks: [c0, c0 + nk)
     for (int c = 0; c < NSTAGE - 1; ++c) {
         if (c < nk) load(c0 + c);
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -93,60 +103,59 @@ __global__ void __cluster_dims__(1, 1, KSPLIT) __launch_bounds__(128) step_gemm_
         __syncthreads();                                                           // ... for everyone; chunk it-1 is consumed
         if (it + NSTAGE - 1 < nk) load(c0 + it + NSTAGE - 1);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const float *As = smem + ((c0 + it) % NSTAGE) * STAGE_FLOATS, *Ws = As + A_FLOATS;
+        const float *As = smem + ((c0 + it) % NSTAGE) * STAGE_FLOATS, *Ws = As + C_::A_FLOATS;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int k0 = (2 * warp + q) * 4;
-            float4 w0, w1;
-            if (TB) {
-                w0 = *reinterpret_cast<const float4 *>(Ws + lane * LDS_ + k0);
-                w1 = *reinterpret_cast<const float4 *>(Ws + (lane + 32) * LDS_ + k0);
-            } else {
-                w0 = make_float4(Ws[k0 * LDW_ + lane], Ws[(k0 + 1) * LDW_ + lane], Ws[(k0 + 2) * LDW_ + lane], Ws[(k0 + 3) * LDW_ + lane]);
-                w1 = make_float4(Ws[k0 * LDW_ + lane + 32], Ws[(k0 + 1) * LDW_ + lane + 32], Ws[(k0 + 2) * LDW_ + lane + 32],
-                                 Ws[(k0 + 3) * LDW_ + lane + 32]);
+        for (int q = 0; q < C_::QW; ++q) {
+            const int k0 = (warp * C_::QW + q) * 4;
+            float4 w[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int nl = lane + 32 * c;
+                if (TB) w[c] = *reinterpret_cast<const float4 *>(Ws + nl * LDS_ + k0);
+                else w[c] = make_float4(Ws[k0 * LDW + nl], Ws[(k0 + 1) * LDW + nl], Ws[(k0 + 2) * LDW + nl], Ws[(k0 + 3) * LDW + nl]);
             }
 #pragma unroll
             for (int m = 0; m < BM; ++m) {
                 const float4 a = *reinterpret_cast<const float4 *>(As + m * LDS_ + k0);      // same address in every lane
-                acc0[m] = fmaf(a.x, w0.x, acc0[m]); acc1[m] = fmaf(a.x, w1.x, acc1[m]);
-                acc0[m] = fmaf(a.y, w0.y, acc0[m]); acc1[m] = fmaf(a.y, w1.y, acc1[m]);
-                acc0[m] = fmaf(a.z, w0.z, acc0[m]); acc1[m] = fmaf(a.z, w1.z, acc1[m]);
-                acc0[m] = fmaf(a.w, w0.w, acc0[m]); acc1[m] = fmaf(a.w, w1.w, acc1[m]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    acc[c][m] = fmaf(a.x, w[c].x, acc[c][m]); acc[c][m] = fmaf(a.y, w[c].y, acc[c][m]);
+                    acc[c][m] = fmaf(a.z, w[c].z, acc[c][m]); acc[c][m] = fmaf(a.w, w[c].w, acc[c][m]);
+                }
             }
         }
     }
-    // ---- partial tiles of the four warps into this CTA's shared memory; rank 0 adds all 16 (cluster rank, then warp)
+    // ---- partial tiles of the warps into this CTA's shared memory; rank 0 adds all KS x NW (cluster rank, then warp)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    float *red = smem;                                          // [4 warps][32 m][65]
-    constexpr int RLD = BN + 1;
+    float *red = smem;                                          // [NW][32 m][RLD]
+    constexpr int RLD = C_::RLD;
 #pragma unroll
-    for (int m = 0; m < BM; ++m) {
-        red[(warp * BM + m) * RLD + lane] = acc0[m];
-        red[(warp * BM + m) * RLD + lane + 32] = acc1[m];
-    }
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int m = 0; m < BM; ++m) red[(warp * BM + m) * RLD + lane + 32 * c] = acc[c][m];
     cluster.sync();
     if (krank != 0) { cluster.sync(); return; }                 // peers keep their tiles alive until rank 0 has read them
-    const float *peer[KSPLIT];
+    const float *peer[KS];
 #pragma unroll
-    for (int r = 0; r < KSPLIT; ++r) peer[r] = cluster.map_shared_rank(red, r);
-    float *C = g.C[z];
-    float vsum[16];                                             // rows warp*8 .. +7, columns lane and lane + 32
+    for (int r = 0; r < KS; ++r) peer[r] = cluster.map_shared_rank(red, r);
+    constexpr int OUT = BM * BN / NT;                           // outputs per thread: o = tid + j * NT -> (o / BN, o % BN)
+    float vsum[OUT];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int ml = warp * 8 + (j >> 1), nl = lane + 32 * (j & 1);
+    for (int j = 0; j < OUT; ++j) {
+        const int o = tid + j * NT, ml = o / BN, nl = o % BN;
         float v = 0.f;
 #pragma unroll
-        for (int r = 0; r < KSPLIT; ++r)
+        for (int r = 0; r < KS; ++r)
 #pragma unroll
-            for (int w = 0; w < 4; ++w) v += peer[r][(w * BM + ml) * RLD + nl];
+            for (int w2 = 0; w2 < NW; ++w2) v += peer[r][(w2 * BM + ml) * RLD + nl];
         vsum[j] = v;
     }
     cluster.sync();
+    float *C = g.C[z];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int ml = warp * 8 + (j >> 1), m = m0 + ml, n = n0 + lane + 32 * (j & 1);
+    for (int j = 0; j < OUT; ++j) {
+        const int o = tid + j * NT, ml = o / BN, m = m0 + ml, n = n0 + o % BN;
         if (m >= g.M) break;
         const float v = vsum[j];
         const bool live = MODE == 0 || !sc.use_len || sc.t[z] < sc.seq_len[m];
@@ -166,41 +175,53 @@ __global__ void __cluster_dims__(1, 1, KSPLIT) __launch_bounds__(128) step_gemm_
     }
 }
 
-}  // namespace stepg
-
-static int set_smem_once()
+// variant 0: 4 warps, 2 columns per lane, K over 4 CTAs;  variant 1: 8 warps, 1 column per lane, K over 2 CTAs
+// (twice the resident warps per SM).  CTCASR_STEP_VARIANT selects (measurement aid).
+static int variant()
 {
-    static bool done = false;
-    if (done) return CTCASR_OK;
-    CTCASR_CUDA_CHECK(cudaFuncSetAttribute(stepg::step_gemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, stepg::SMEM_BYTES));
-    CTCASR_CUDA_CHECK(cudaFuncSetAttribute(stepg::step_gemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, stepg::SMEM_BYTES));
-    CTCASR_CUDA_CHECK(cudaFuncSetAttribute(stepg::step_gemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, stepg::SMEM_BYTES));
-    CTCASR_CUDA_CHECK(cudaFuncSetAttribute(stepg::step_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, stepg::SMEM_BYTES));
-    done = true;
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CTCASR_STEP_VARIANT"); v = e ? atoi(e) : 0; if (v != 1) v = 0; }
+    return v;
+}
+
+template <bool TB, int MODE, int NW, int NC, int KS>
+static int launch(const GemmArgs &g, const StepCell &sc, cudaStream_t stream)
+{
+    using C_ = Cfg<NW, NC, KS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(step_gemm_kernel<TB, MODE, NW, NC, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid(g.N / C_::BN, ceil_div(g.M, BM), g.nz * KS);
+    step_gemm_kernel<TB, MODE, NW, NC, KS><<<grid, C_::NT, C_::SMEM_BYTES, stream>>>(g, sc);
+    CTCASR_LAUNCH_CHECK();
     return CTCASR_OK;
 }
 
+template <bool TB, int MODE>
+static int launch_variant(const GemmArgs &g, const StepCell &sc, cudaStream_t stream)
+{
+    return variant() == 1 ? launch<TB, MODE, 8, 1, 2>(g, sc, stream) : launch<TB, MODE, 4, 2, 4>(g, sc, stream);
+}
+
+}  // namespace stepg
+
 static bool eligible(const GemmArgs &g)
 {
-    bool ok = g.epi.mode == EPI_STORE && !g.ta && g.M >= 1 && g.N % stepg::BN == 0 && g.K % (32 * stepg::KSPLIT) == 0 &&
-              g.lda % 4 == 0 && g.ldb % 4 == 0;
+    bool ok = g.epi.mode == EPI_STORE && !g.ta && g.M >= 1 && g.N % 64 == 0 && g.K % 128 == 0 && g.lda % 4 == 0 && g.ldb % 4 == 0;
     for (int z = 0; z < g.nz && ok; ++z)
         ok = (((uintptr_t)g.A[z] | (uintptr_t)g.B[z]) & 15) == 0;
     return ok;
 }
 
 // Falls back to the generic SIMT GEMM when the shape is not the recurrence's (plain store / accumulate epilogue,
-// A not transposed, N % 32 == 0, K % 64 == 0, 16-B aligned rows).
+// A not transposed, N % 64 == 0, K % 128 == 0, 16-B aligned rows).
 int step_gemm(const GemmArgs &g, cudaStream_t stream)
 {
     if (!eligible(g)) return gemm_simt(g, stream);
-    if (int rc = set_smem_once()) return rc;
-    dim3 grid(g.N / stepg::BN, ceil_div(g.M, stepg::BM), g.nz * stepg::KSPLIT);
     const StepCell none{};
-    if (g.tb) stepg::step_gemm_kernel<true, 0><<<grid, 128, stepg::SMEM_BYTES, stream>>>(g, none);
-    else stepg::step_gemm_kernel<false, 0><<<grid, 128, stepg::SMEM_BYTES, stream>>>(g, none);
-    CTCASR_LAUNCH_CHECK();
-    return CTCASR_OK;
+    return g.tb ? stepg::launch_variant<true, 0>(g, none, stream) : stepg::launch_variant<false, 0>(g, none, stream);
 }
 
 // One frame of a one-gate cell, product + cell math in one launch (sc.mode 1 forward: g.tb == 0, 2 backward:
@@ -209,12 +230,7 @@ int step_gemm(const GemmArgs &g, cudaStream_t stream)
 int step_gemm_cell(const GemmArgs &g, const StepCell &sc, cudaStream_t stream)
 {
     if (!eligible(g) || g.nz != 2 || (sc.mode != 1 && sc.mode != 2) || (sc.mode == 1) == (g.tb != 0)) return CTCASR_ERR_UNSUPPORTED;
-    if (int rc = set_smem_once()) return rc;
-    dim3 grid(g.N / stepg::BN, ceil_div(g.M, stepg::BM), g.nz * stepg::KSPLIT);
-    if (sc.mode == 1) stepg::step_gemm_kernel<false, 1><<<grid, 128, stepg::SMEM_BYTES, stream>>>(g, sc);
-    else stepg::step_gemm_kernel<true, 2><<<grid, 128, stepg::SMEM_BYTES, stream>>>(g, sc);
-    CTCASR_LAUNCH_CHECK();
-    return CTCASR_OK;
+    return sc.mode == 1 ? stepg::launch_variant<false, 1>(g, sc, stream) : stepg::launch_variant<true, 2>(g, sc, stream);
 }
 
 }  // namespace ctcasr
