@@ -20,9 +20,20 @@ def shard_bounds(global_batch, rank, world):
     return rank * per, (rank + 1) * per
 
 
-def shard_batch(sequences, seq_length, labels, label_length, rank, world):
-    lo, hi = shard_bounds(sequences.shape[0], rank, world)
-    return sequences[lo:hi], seq_length[lo:hi], labels[lo:hi], label_length[lo:hi]
+def shard_indices(global_batch, rank, world, interleave=False):
+    """Utterance indices of this rank's shard.  interleave=False: a contiguous block.  interleave=True:
+    rank, rank + world, rank + 2 world, ... — for the reference's length-bucketed batches, whose utterances are
+    sorted by duration inside a bucket (asr/util/csv_helper.py:29-38), this gives every GPU the same count AND
+    the same mix of lengths, so the ranks' step times stay balanced."""
+    lo, hi = shard_bounds(global_batch, rank, world)
+    if not interleave:
+        return slice(lo, hi)
+    return slice(rank, global_batch, world)
+
+
+def shard_batch(sequences, seq_length, labels, label_length, rank, world, interleave=False):
+    idx = shard_indices(sequences.shape[0], rank, world, interleave)
+    return sequences[idx], seq_length[idx], labels[idx], label_length[idx]
 
 
 def allreduce_gradients(flat_grad, group=None):
@@ -40,11 +51,11 @@ def allreduce_mean_loss(local_loss_sum_over_global_batch, group=None):
     return t[0]
 
 
-def train_step(model, sequences, seq_length, labels, label_length, group=None):
+def train_step(model, sequences, seq_length, labels, label_length, group=None, interleave=False):
     """One data-parallel step of `CTCModel` on this rank's shard of the global batch."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     gb = sequences.shape[0]
-    x, sl, lab, ll = shard_batch(sequences, seq_length, labels, label_length, rank, world)
+    x, sl, lab, ll = shard_batch(sequences, seq_length, labels, label_length, rank, world, interleave)
     loss = model.train_step(x, sl, (lab, ll), global_batch=gb, allreduce=lambda g: allreduce_gradients(g, group))
     return allreduce_mean_loss(loss, group)

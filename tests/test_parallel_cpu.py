@@ -26,11 +26,11 @@ def _flat(cfg, grads):
     return flat
 
 
-def _worker(rank, world, port, x, sl, lab, ll, out):
+def _worker(rank, world, port, x, sl, lab, ll, out, interleave=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     params = synthetic.init_params(CFG, seed=1, dtype=np.float64)
-    xs, sls, labs, lls = parallel.shard_batch(x, sl, lab, ll, rank, world)
+    xs, sls, labs, lls = parallel.shard_batch(x, sl, lab, ll, rank, world, interleave)
     gb = x.shape[0]
     loss, grads, _, _ = model_ref.loss_and_grads(CFG, params, xs, sls, labs, lls)
     # loss_and_grads averages over the SHARD; rescale to 1/global_batch like loss_fn(global_batch=gb)
@@ -52,6 +52,29 @@ def test_two_rank_gradient_equals_single_process():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, x, sl, lab, ll, out), nprocs=2, join=True)
+    params = synthetic.init_params(CFG, seed=1, dtype=np.float64)
+    loss, grads, _, _ = model_ref.loss_and_grads(CFG, params, x, sl, lab, ll)
+    np.testing.assert_allclose(out["loss"], loss, rtol=1e-12)
+    np.testing.assert_allclose(out["flat"], _flat(CFG, grads), atol=1e-12)
+
+
+def test_interleaved_shards_of_a_bucketed_batch_balance_lengths_and_sum_to_the_same_gradient():
+    """cfg4 across GPUs: a length-sorted (bucketed) batch cut into contiguous halves gives one rank all the long
+    utterances; interleaved shards have the same length mix, and the all-reduced gradient is still exactly the
+    single-process gradient of the global mean loss."""
+    x, sl, lab, ll = synthetic.fixed_batch(6, 20, 3, F=CFG.num_features, seed=6)
+    sl[:] = np.array([8, 10, 12, 15, 17, 20], np.int32)                 # sorted by duration, like a bucket
+    for b in range(6):
+        x[b, sl[b]:] = 0
+    contiguous = [int(sl[parallel.shard_indices(6, r, 2)].sum()) for r in range(2)]
+    interleaved = [int(sl[parallel.shard_indices(6, r, 2, interleave=True)].sum()) for r in range(2)]
+    assert max(interleaved) - min(interleaved) < max(contiguous) - min(contiguous)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, x, sl, lab, ll, out, True), nprocs=2, join=True)
     params = synthetic.init_params(CFG, seed=1, dtype=np.float64)
     loss, grads, _, _ = model_ref.loss_and_grads(CFG, params, x, sl, lab, ll)
     np.testing.assert_allclose(out["loss"], loss, rtol=1e-12)
