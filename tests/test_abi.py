@@ -56,3 +56,42 @@ def test_sass_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_host_side_queries_of_the_entry_points_added_for_the_next_rows(lib):
+    """conv / beam-search / feature entry points: everything that does not need a device."""
+    to, fo = ctypes.c_int(), ctypes.c_int()
+    # the reference's three conv layers on a 10 s clip (asr/util/tf_contrib.py:66-67): 999x80 -> 500x40 -> 500x20 -> 500x10
+    for (T, F, kt, kf, st, sf), want in [((999, 80, 11, 41, 2, 2), (500, 40)), ((500, 40, 11, 21, 1, 2), (500, 20)),
+                                         ((500, 20, 11, 21, 1, 2), (500, 10))]:
+        assert lib.ctcasr_conv2d_out_dims(T, F, kt, kf, st, sf, ctypes.byref(to), ctypes.byref(fo)) == 0
+        assert (to.value, fo.value) == want
+    # patch matrix of layer 2 at B=32: 500*32*20 positions x roundup8(11*21*32) floats
+    assert lib.ctcasr_conv2d_workspace_bytes(500, 32, 40, 32, 11, 21, 1, 2) == 500 * 32 * 20 * 7392 * 4
+    assert lib.ctcasr_feature_frames(160000, 16000) == 999 and lib.ctcasr_feature_frames(401, 16000) == 2
+    bins = (ctypes.c_int32 * 82)()
+    assert lib.ctcasr_feature_filterbank_bins(16000, 80, bins) == 0
+    assert bins[0] == 4 and bins[81] == 512 and all(bins[i] <= bins[i + 1] for i in range(81))
+    assert lib.ctcasr_beam_search_workspace_bytes(1000, 32, 29, 1024) > 32 * 1000 * 1024 * 8
+    assert lib.ctcasr_beam_search_workspace_bytes(1000, 32, 64, 1024) == 0         # V > 32 unsupported
+    assert lib.ctcasr_beam_search_workspace_bytes(1000, 32, 29, 2048) == 0         # beam_width > 1024 unsupported
+
+
+def test_argument_validation_of_the_new_entry_points_needs_no_gpu(lib):
+    one = ctypes.c_void_p(16)            # any non-null pointer: validation must fail before it is touched
+    rc = lib.ctcasr_beam_search(one, 10, 1, 29, 5, one, 16, 0, one, one, None, one, 1 << 20, None)
+    assert rc == -1 and b"blank" in lib.ctcasr_last_error()                         # TF: blank = num_classes - 1
+    rc = lib.ctcasr_beam_search(one, 10, 1, 29, 28, one, 4096, 0, one, one, None, one, 1 << 20, None)
+    assert rc == -1 and b"beam_width" in lib.ctcasr_last_error()
+    n = (ctypes.c_int32 * 1)(400)
+    rc = lib.ctcasr_featurize(one, 1, 400, n, 1, 1, 0, 16000, 80, one, 1, one, one, 1 << 20, None)
+    assert rc == -1 and b"to short" in lib.ctcasr_last_error()                      # asr/input_functions.py:213-214
+    n[0] = 16000
+    rc = lib.ctcasr_featurize(one, 1, 16000, n, 2, 1, 0, 16000, 80, one, 99, one, one, 1 << 20, None)
+    assert rc == -1 and b"isn't supported" in lib.ctcasr_last_error()               # :196
+    rc = lib.ctcasr_featurize(one, 1, 16000, n, 1, 1, 0, 16000, 80, one, 50, one, one, 1 << 20, None)
+    assert rc == -1 and b"99" in lib.ctcasr_last_error()                            # output too short for 99 frames
+    rc = lib.ctcasr_conv2d_fwd(one, 1, one, one, one, 10, 1, 8, 2, 3, 3, 1, 1, 64, 1, 20.0, 0, None, 0, None)
+    assert rc == -1                                                                 # pitch 1 < 2 channels
+    rc = lib.ctcasr_conv2d_fwd(one, 2, one, one, one, 10, 1, 8, 2, 3, 3, 1, 1, 64, 1, 20.0, 0, None, 0, None)
+    assert rc == -3 and b"workspace" in lib.ctcasr_last_error()
