@@ -114,14 +114,29 @@ __global__ void __cluster_dims__(1, 1, KS) __launch_bounds__(32 * NW) step_gemm_
                 if (TB) w[c] = *reinterpret_cast<const float4 *>(Ws + nl * LDS_ + k0);
                 else w[c] = make_float4(Ws[k0 * LDW + nl], Ws[(k0 + 1) * LDW + nl], Ws[(k0 + 2) * LDW + nl], Ws[(k0 + 3) * LDW + nl]);
             }
+            // eight rows at a time, one k at a time: consecutive FMAs belong to different accumulators, so the
+            // four-deep dependent chain of an accumulator is spread over 8 NC independent instructions
 #pragma unroll
-            for (int m = 0; m < BM; ++m) {
-                const float4 a = *reinterpret_cast<const float4 *>(As + m * LDS_ + k0);      // same address in every lane
+            for (int mg = 0; mg < BM; mg += 8) {
+                float4 a[8];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    acc[c][m] = fmaf(a.x, w[c].x, acc[c][m]); acc[c][m] = fmaf(a.y, w[c].y, acc[c][m]);
-                    acc[c][m] = fmaf(a.z, w[c].z, acc[c][m]); acc[c][m] = fmaf(a.w, w[c].w, acc[c][m]);
-                }
+                for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4 *>(As + (mg + i) * LDS_ + k0);   // broadcast loads
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) acc[c][mg + i] = fmaf(a[i].x, w[c].x, acc[c][mg + i]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) acc[c][mg + i] = fmaf(a[i].y, w[c].y, acc[c][mg + i]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) acc[c][mg + i] = fmaf(a[i].z, w[c].z, acc[c][mg + i]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) acc[c][mg + i] = fmaf(a[i].w, w[c].w, acc[c][mg + i]);
             }
         }
     }
