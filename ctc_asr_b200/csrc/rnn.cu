@@ -12,6 +12,7 @@
 #include "gemm.cuh"
 #include "rnn.cuh"
 #include "lstm_tc.cuh"
+#include "rec_tc.cuh"
 
 using namespace ctcasr;
 
@@ -74,6 +75,10 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
     if (compute != CTCASR_COMPUTE_FP32 && lstm_tc_eligible(T, B, H, cell)) {
         char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
         return lstm_tc_fwd(seq_len, wh, r.gates, r.cstate, y, T, B, H, use_len, forget_bias, wsb, stream);
+    }
+    if (compute != CTCASR_COMPUTE_FP32 && rec_tc_eligible(T, B, H, cell)) {     // one-gate cells: resident-weight kernel
+        char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
+        return rec_tc_fwd(seq_len, wh, r.gates, y, T, B, H, cell, use_len, wsb, stream);
     }
     RnnStep s;
     s.T = T; s.B = B; s.H = H; s.G = G; s.cell = cell; s.use_len = use_len; s.forget_bias = forget_bias;
@@ -139,6 +144,11 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
         char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
         rc = lstm_tc_bwd(seq_len, wh, r.gates, r.cstate, dy, dbias, &dbias_done, T, B, H, use_len, wsb, stream);
         if (rc != CTCASR_OK) return rc;
+    } else if (compute != CTCASR_COMPUTE_FP32 && rec_tc_eligible(T, B, H, cell)) {
+        char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
+        rc = rec_tc_bwd(seq_len, wh, r.gates, dy, dbias, T, B, H, cell, use_len, wsb, stream);
+        if (rc != CTCASR_OK) return rc;
+        dbias_done = 1;
     } else {
         RnnStep s;
         s.T = T; s.B = B; s.H = H; s.G = G; s.cell = cell; s.use_len = use_len; s.forget_bias = 0.f;
