@@ -25,7 +25,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG2 = dict(num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_units_rnn=2048, rnn_cell="lstm",
+CFG2 = dict(used_model="ds1", num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_units_rnn=2048, rnn_cell="lstm",
             cudnn=False, dense_dropout_rate=0.1)
 CFG2_B, CFG2_T, CFG2_L = 32, 1000, 160
 CFG5 = dict(B=512, T=1700, L=84, V=29)

@@ -23,28 +23,40 @@
 // The recurrent weights (2 x 64 MiB in two bf16 pieces at H = 2048) do not fit on chip and are
 // streamed every step: the kernel is bound by L2/HBM weight streaming, not by the tensor pipe.
 #include "lstm_tc.cuh"
-#include "ptx.cuh"
+#include "rec_common.cuh"
 
-#include <cuda_bf16.h>
-#include <mutex>
 #include <stdlib.h>
 
 namespace ctcasr {
 namespace lstm {
 
+using rec::BK;
+using rec::sigmoidf_;
+using rec::split2;
+using rec::wait_counter;
+using rec::signal_counter;
+using rec::make_map;
+
 constexpr int UPC = 32;                 // hidden units per CTA
 constexpr int NB = 32;                  // batch rows per MMA (N forward, real M rows backward)
-constexpr int BK = 64;                  // bf16 k-elements per stage row (128 B, SWIZZLE_128B)
 constexpr int NTHREADS = 384;           // 12 warps: 0-3 TMEM readers + cell math, 4 weight tiles, 5 state tiles,
                                         //           6-7 MMA issuers, 8-11 cell math
-constexpr int EPI_THREADS = 128;
+constexpr int CELL_L = CTCASR_CELL_LSTM, CELL_G = CTCASR_CELL_GRU;
 
-// ---- forward smem ring: per stage A = 2 pieces x [128 x 64] bf16 (16 KB each), B = 2 x [32 x 64] (4 KB each)
+// ---- smem ring: per stage A = PIECES x [128 x 64] bf16 (16 KB each), B = PIECES x [32 x 64] (4 KB each).
+// PIECES = 2: bf16x3 arithmetic (operands split hi + lo, three products); PIECES = 1: plain bf16 operands, one
+// product (compute = 'bf16', BASELINE cfg3) — half the weight bytes, so most of a CTA's slice stays in tensor memory.
 constexpr int F_A_PIECE = 128 * BK * 2, F_B_PIECE = NB * BK * 2;
-constexpr int F_STAGE = 2 * F_A_PIECE + 2 * F_B_PIECE;          // 40 KB
-constexpr int F_NSTAGE = 5;
-// The two MMA issuers take alternate k-blocks.  Each owns a private sub-ring of stages (issuer 0: stages
-// 0-2, issuer 1: stages 3-4) so that every full/empty barrier has its phases consumed by ONE thread in
+template <int PIECES> struct Ring {
+    static constexpr int STAGE = PIECES * (F_A_PIECE + F_B_PIECE);           // 40 KB / 20 KB
+    static constexpr int NSTAGE = PIECES == 2 ? 5 : 9;
+    static constexpr int ACC_COLS = 2 * PIECES * NB;                         // two issuers x (PIECES x 32) accumulator columns
+    static constexpr int KRES_MAX = (512 - ACC_COLS) / (PIECES * 32);        // weight k-blocks resident in tensor memory: 6 / 14
+    static constexpr int XCH = 4 * NB * UPC * 4;                             // gate exchange [4][32 b][32 u] fp32
+    static constexpr int SMEM = NSTAGE * STAGE + XCH + 1024 + 256;
+};
+// The two MMA issuers take alternate k-blocks.  Each owns a private sub-ring of stages (issuer 0 the first
+// ceil(n/2) stages, issuer 1 the rest) so that every full/empty barrier has its phases consumed by ONE thread in
 // order.  With a shared ring of odd depth the successive fills of a stage alternate between the issuers,
 // and an issuer that runs ahead (TMA completions are out of order: L2 hits overtake HBM misses) can reach
 // a stage whose previous fill has not landed yet — its parity wait then passes on the older phase and the
@@ -52,14 +64,13 @@ constexpr int F_NSTAGE = 5;
 struct SubRing {
     int first, n, stage;
     uint32_t phase;
-    __device__ SubRing(int issuer) : first(issuer ? 3 : 0), n(issuer ? 2 : 3), stage(0), phase(0) {}
+    __device__ SubRing(int issuer, int nstage) : first(issuer ? (nstage + 1) / 2 : 0), n(issuer ? nstage / 2 : (nstage + 1) / 2), stage(0), phase(0) {}
     __device__ int slot() const { return first + stage; }
     __device__ void advance() { if (++stage == n) { stage = 0; phase ^= 1; } }
 };
-constexpr int F_XCH = 4 * NB * UPC * 4;                         // gate exchange [4][32 b][32 u] fp32
-constexpr int F_SMEM = F_NSTAGE * F_STAGE + F_XCH + 1024 + 256;
-// ---- backward ring: per stage Z = 2 pieces x [32 x 64] (dz), W = 2 x [32 x 64] (weights); the MMA reads
-// the Z tile as 128 rows (16 KB), so Z tiles are spaced 16 KB apart and the ring is padded at the end
+// ---- single-CTA backward (LSTM, two pieces; shapes the cluster kernel does not take): per stage Z = 2 pieces x
+// [32 x 64] (dz), W = 2 x [32 x 64] (weights); the MMA reads the Z tile as 128 rows (16 KB), so Z tiles are
+// spaced 16 KB apart and the ring is padded at the end
 constexpr int B_Z_SLOT = 128 * BK * 2, B_W_PIECE = UPC * BK * 2;
 constexpr int B_STAGE = 2 * B_W_PIECE;                          // weights: 8 KB per stage
 constexpr int B_NSTAGE = 6;
@@ -71,44 +82,24 @@ struct Params {
     int T, B, BS, H, CPD, use_len;       // B: batch rows of this launch (<= 32); BS: batch rows per frame in the buffers
     float forget_bias;
     const int *seq_len;
-    float *gates;            // [T*B, 8H]  fwd: P -> activations;  bwd: activations -> dz
-    float *cstate;           // [T*B, 2H]
-    float *y;                // [T*B, 2H]  (fwd out)
-    const float *dy;         // [T*B, 2H]  (bwd in)
-    __nv_bfloat16 *xbuf;     // fwd: hbuf [2 pieces][2 dirs][2 parity][32][H]; bwd: dzbuf [2][2][2][32][4H]
+    float *gates;            // [T*B, 2GH]  fwd: P -> activations;  bwd: activations -> dz
+    float *cstate;           // [T*B, 2H]   LSTM: c;  GRU: q = h Rn + b_rn
+    float *y;                // [T*B, 2H]   fwd out; GRU bwd reads h_{t-1} from it
+    const float *dy;         // [T*B, 2H]   (bwd in)
+    float *dzr;              // GRU bwd: [T*B, 2*3H] gradient wrt h R (n columns scaled by r), the dWh operand
+    const float *bias_rn;    // GRU: [2, H] recurrent bias of the candidate gate
+    __nv_bfloat16 *xbuf;     // fwd: hbuf [PIECES][2 dirs][2 parity][32][H]; bwd: dzbuf [PIECES][2][2][32][GH]
     unsigned int *counters;  // [2] step counters, [2] = error flag
     unsigned long long *trace;  // optional [grid][64 steps][8 slots] globaltimer stamps (tools/lstm_trace.py)
-    int kres;                // weight k-blocks [0, kres) of every CTA stay resident in tensor memory (<= 6)
-    const __nv_bfloat16 *wpack; // packed weights [2 pieces][rows][K] the resident share is read from
+    int kres;                // weight k-blocks [0, kres) of every CTA stay resident in tensor memory
+    const __nv_bfloat16 *wpack; // packed weights [PIECES][rows][K] the resident share is read from
     int wrows, wk;           // rows and K (row pitch) of wpack
     int stagger_ns;          // start delay of direction 1
-    int skip;                // timing experiments only: 1 = do not load weight tiles, 2 = do not load state tiles
-    int nprod;               // timing experiments only: number of split products issued (3 = correct)
     int kb_keep;             // weight k-blocks [0, kb_keep) are loaded with L2 evict_last, the rest evict_first
-    float *dbias;            // bwd (cluster kernel): [8H] column sums of dz, or null
+    float *dbias;            // bwd (cluster kernel): [2GH (+2H GRU)] column sums of dz, or null
     int db_accum;            // add to dbias instead of storing (batch slices after the first)
 };
 
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
-
-__device__ __forceinline__ void wait_counter(const unsigned int *ctr, unsigned int target, unsigned int *err)
-{
-    unsigned int v, spins = 0;
-    for (;;) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        if (v >= target) break;
-#ifdef CTCASR_DEBUG_WAIT
-        constexpr unsigned int LIMIT = 1u << 26;        // let the stuck CTA's own mbarrier waits report first
-#else
-        constexpr unsigned int LIMIT = 1u << 22;
-#endif
-        if (++spins > LIMIT) { *err = 1; printf("ctcasr lstm: step barrier timed out (block %d, target %u, have %u)\n", blockIdx.x, target, v); __trap(); }
-    }
-}
-__device__ __forceinline__ void signal_counter(unsigned int *ctr)
-{
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-}
 __device__ __forceinline__ void stamp(const Params &p, int step, int slot)
 {
     if (p.trace && step < 64) {
@@ -130,61 +121,61 @@ __device__ __forceinline__ void stagger_wait(int ns)
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }      // single-CTA backward kernel
 __device__ __forceinline__ void cell_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // 8 cell-math warps
 
-__device__ __forceinline__ void split2(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
-{
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-
 // ================================================ forward =========================================
+// CELL = LSTM: rows of a CTA tile = 4 gates (i, j, f, o) x 32 units.  CELL = GRU (cuDNN formulation, gate order
+// r, z, n): 3 gates x 32 units, the fourth 32-row group of the tile is zero weights; the recurrent product of the
+// candidate gate is kept apart from its input projection (n = tanh(P_n + r (h Rn + b_rn))).
+template <int CELL, int PIECES>
 __global__ void __launch_bounds__(NTHREADS, 1)
-lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH, const Params p)
+gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH, const Params p)
 {
+    using R = Ring<PIECES>;
+    constexpr int G = CELL == CELL_G ? 3 : 4;
+    constexpr int NSTAGE = R::NSTAGE, STAGE = R::STAGE;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-    const uint32_t xch_base = smem_base + F_NSTAGE * F_STAGE;
-    float *zs = reinterpret_cast<float *>(smem_gen + F_NSTAGE * F_STAGE);        // [4][32 b][32 u]
-    const uint32_t bar_base = xch_base + F_XCH;
+    const uint32_t xch_base = smem_base + NSTAGE * STAGE;
+    float *zs = reinterpret_cast<float *>(smem_gen + NSTAGE * STAGE);        // [4][32 b][32 u]
+    const uint32_t bar_base = xch_base + R::XCH;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
-    auto fullB = [&](int s) { return bar_base + 8u * (F_NSTAGE + s); };
-    auto empty = [&](int s) { return bar_base + 8u * (2 * F_NSTAGE + s); };
-    const uint32_t tfull = bar_base + 8u * (3 * F_NSTAGE), tempty = tfull + 8;
+    auto empty = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+    const uint32_t tfull = bar_base + 8u * (2 * NSTAGE), tempty = tfull + 8;
     const uint32_t tmem_slot = tempty + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
-    auto a_addr = [&](int s, int pc) { return smem_base + s * F_STAGE + pc * F_A_PIECE; };
-    auto b_addr = [&](int s, int pc) { return smem_base + s * F_STAGE + 2 * F_A_PIECE + pc * F_B_PIECE; };
+    auto a_addr = [&](int s, int pc) { return smem_base + s * STAGE + pc * F_A_PIECE; };
+    auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * F_B_PIECE; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = blockIdx.x / p.CPD, c = blockIdx.x % p.CPD;
     const int T = p.T, B = p.B, H = p.H, KB = H / BK;
-#ifdef CTCASR_DEBUG_WAIT
-    if (blockIdx.x == 0 && threadIdx.x == 0) printf("fwd bar_base %u (full +8s, empty +%d+8s, tfull +%d, tempty +%d)\n", bar_base, 16 * F_NSTAGE, 24 * F_NSTAGE, 24 * F_NSTAGE + 8);
-#endif
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
         ptx::mbar_init(tfull, 2); ptx::mbar_init(tempty, 4);
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapH); }
-    const uint32_t tmem_cols = p.kres > 0 ? 512u : 128u; // 2 x 64 accumulator columns (+ up to 384 of resident weights)
+    const uint32_t tmem_cols = p.kres > 0 ? 512u : (uint32_t)R::ACC_COLS;   // accumulators (+ resident weights)
     if (warp == 6) ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot_ptr;
-    const uint32_t tmem_w = tmem_d + 128;                 // resident weights: k-block kb, piece pc at column (kb*2+pc)*32
+    const uint32_t tmem_w = tmem_d + R::ACC_COLS;         // resident weights: k-block kb, piece pc at column (kb*PIECES+pc)*32
     if (warp < 4 && p.kres > 0) {
         // my gate row's weights for k in [0, 64*kres): 32 columns (= 64 bf16) per k-block and piece
         const int row = (d * p.CPD + c) * 128 + warp * 32 + lane;
         for (int kb = 0; kb < p.kres; ++kb)
-            for (int pc = 0; pc < 2; ++pc) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wpack + ((size_t)pc * p.wrows + row) * p.wk + (size_t)kb * BK);
+            for (int pc = 0; pc < PIECES; ++pc) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.wpack + ((size_t)pc * p.wrows + row) * p.wk + (size_t)kb * BK);
                 uint32_t r[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = __ldg(src + j);
-                ptx::tmem_st32(tmem_w + ((uint32_t)(warp * 32) << 16) + (uint32_t)((kb * 2 + pc) * 32), r);
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 v = __ldg(src + j);
+                    r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+                }
+                ptx::tmem_st32(tmem_w + ((uint32_t)(warp * 32) << 16) + (uint32_t)((kb * PIECES + pc) * 32), r);
             }
         ptx::tmem_st_wait();
     }
@@ -195,7 +186,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
     if (warp == 4) {
         // ---- weight tiles: independent of the recurrence, runs ahead across step boundaries ----
         if (lane == 0) {
-            SubRing ring[2] = {SubRing(0), SubRing(1)};
+            SubRing ring[2] = {SubRing(0, NSTAGE), SubRing(1, NSTAGE)};
             const int row0 = (d * p.CPD + c) * 128;
             const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int i = 0; i < T; ++i)
@@ -203,12 +194,12 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     SubRing &r = ring[kb & 1];
                     const int stage = r.slot();
                     ptx::mbar_wait(empty(stage), r.phase ^ 1);
-                    if (kb < p.kres || (p.skip & 1)) {
+                    if (kb < p.kres) {
                         ptx::mbar_arrive(fullA(stage));     // resident in tensor memory: nothing to load, keep the phases in step
                     } else {
-                        ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
+                        ptx::mbar_expect_tx(fullA(stage), PIECES * F_A_PIECE);
                         const uint64_t pol = kb - p.kres < p.kb_keep ? keep : stream;
-                        ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage), pol);   // both pieces in one box
+                        ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage), pol);   // all pieces in one box
                     }
                     r.advance();
                     if (kb == KB - 1) stamp(p, i, 6);
@@ -217,7 +208,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
     } else if (warp == 5) {
         // ---- h_{t-1} tiles: gated by the step barrier of this direction ------------------------
         if (lane == 0) {
-            SubRing ring[2] = {SubRing(0), SubRing(1)};
+            SubRing ring[2] = {SubRing(0, NSTAGE), SubRing(1, NSTAGE)};
             if (d == 1) stagger_wait(p.stagger_ns);
             for (int i = 0; i < T; ++i) {
                 wait_counter(p.counters + d, (unsigned)(p.CPD * i), p.counters + 2);
@@ -228,9 +219,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     SubRing &r = ring[kb & 1];
                     const int stage = r.slot();
                     ptx::mbar_wait(empty(stage), r.phase ^ 1);
-                    if (p.skip & 2) { ptx::mbar_arrive(fullA(stage)); r.advance(); continue; }
-                    ptx::mbar_expect_tx(fullA(stage), 2 * F_B_PIECE);
-                    ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullA(stage));   // both pieces in one box
+                    ptx::mbar_expect_tx(fullA(stage), PIECES * F_B_PIECE);
+                    ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullA(stage));   // all pieces in one box
                     r.advance();
                 }
                 stamp(p, i, 1);
@@ -238,14 +228,14 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
         }
     } else if (warp == 6 || warp == 7) {
         // ---- two MMA issuers: even / odd k-blocks into separate accumulators.  The per-k-block cost
-        // of one issuing thread (barrier wait + descriptor set-up + 8 small MMAs + commit) is what paces
+        // of one issuing thread (barrier wait + descriptor set-up + small MMAs + commit) is what paces
         // the streaming phase, so it is split over two threads; the epilogue adds the accumulators.
         if (lane == 0) {
             const int me = warp - 6;
             const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
-            const uint32_t acc = tmem_d + (uint32_t)(me * 2 * NB);
+            const uint32_t acc = tmem_d + (uint32_t)(me * PIECES * NB);
             uint32_t tphase = 0;
-            SubRing ring(me);
+            SubRing ring(me, NSTAGE);
             for (int i = 0; i < T; ++i) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
@@ -254,11 +244,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     const int first = kb == me;
                     ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
-                    // bf16x3 with 2 MMAs per k-step: the two pieces of h are consecutive rows of one K-major tile,
-                    // so  A_hi x [B_hi; B_lo]  is ONE N = 64 MMA (columns 0-31: hi*hi, 32-63: hi*lo) and
-                    // A_lo x B_hi  accumulates into columns 0-31; the epilogue adds the column groups.
                     const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
-                    if (p.nprod > 0) {
+                    if (PIECES == 2) {
+                        // bf16x3 with 2 MMAs per k-step: the two pieces of h are consecutive rows of one K-major tile,
+                        // so  A_hi x [B_hi; B_lo]  is ONE N = 64 MMA (columns 0-31: hi*hi, 32-63: hi*lo) and
+                        // A_lo x B_hi  accumulates into columns 0-31; the epilogue adds the column groups.
                         if (kb < p.kres) {          // A from tensor memory: 8 columns per 16-wide k-step
                             const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
 #pragma unroll
@@ -275,6 +265,18 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                                 ptx::mma_bf16(acc, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
                             }
                         }
+                    } else {
+                        if (kb < p.kres) {
+                            const uint32_t ta = tmem_w + (uint32_t)(kb * 32);
+#pragma unroll
+                            for (int j = 0; j < BK / 16; ++j)
+                                ptx::mma_bf16_ts(acc, ta + 8 * j, bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
+                        } else {
+                            const uint64_t ad = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+#pragma unroll
+                            for (int j = 0; j < BK / 16; ++j)
+                                ptx::mma_bf16(acc, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
+                        }
                     }
                     ptx::mma_commit(empty(stage));
                     ring.advance();
@@ -285,75 +287,115 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             }
         }
     } else if (warp < 4 || warp >= 8) {
-        // ---- cell math.  Warps 0-3 (warp = gate) also read the accumulators and add the input projection;
-        // then all 8 cell warps own (unit, 4 batch rows) cells with c kept in registers across steps.
+        // ---- cell math.  Warps 0-3 (warp = gate) also read the accumulators (LSTM: and add the input projection);
+        // then all 8 cell warps own (unit, 4 batch rows) cells with the state kept in registers across steps.
         const bool reader = warp < 4;
         const int g = warp, ul = lane;
         const int tid = threadIdx.x;
         const int e = reader ? tid : tid - 128;                              // 0..255
         const int cu = e & 31, bg = e >> 5;                                  // cell ownership: rows bg*4 .. bg*4+3
         const int ucol = c * UPC;                                            // first unit of this CTA
-        float creg[4];
+        float sreg[4];                                                       // LSTM: c;  GRU: h
         int len4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int b = bg * 4 + j; creg[j] = 0.f; len4[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
+        for (int j = 0; j < 4; ++j) { const int b = bg * 4 + j; sreg[j] = 0.f; len4[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
+        const float brn = CELL == CELL_G ? p.bias_rn[d * H + ucol + cu] : 0.f;
         uint32_t tphase = 0;
-        const size_t GW = (size_t)8 * H;                                     // gates row pitch
+        const size_t GW = (size_t)2 * G * H;                                 // gates row pitch
         for (int i = 0; i < T; ++i) {
             const int tt = d == 0 ? i : T - 1 - i;
-            if (reader) {
-                // pre-activations of my gate row for all batch rows (independent of the recurrence)
-                float pz[NB];
-                const float *prow = p.gates + (size_t)tt * p.BS * GW + (size_t)d * 4 * H + (size_t)g * H + ucol + ul;
+            float pin[CELL == CELL_G ? 12 : 1];                              // GRU: input projections of my cells
+            if (CELL == CELL_G) {
 #pragma unroll
-                for (int b = 0; b < NB; ++b) pz[b] = b < B ? __ldg(prow + (size_t)b * GW) : 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    const int b = bg * 4 + j;
+                    const float *prow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * G * H + ucol + cu;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) pin[j * 3 + q] = b < B ? __ldg(prow + (size_t)q * H) : 0.f;
+                }
+            }
+            if (reader) {
+                // LSTM: pre-activations of my gate row for all batch rows (independent of the recurrence)
+                float pz[NB];
+                if (CELL == CELL_L) {
+                    const float *prow = p.gates + (size_t)tt * p.BS * GW + (size_t)d * G * H + (size_t)g * H + ucol + ul;
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) pz[b] = b < B ? __ldg(prow + (size_t)b * GW) : 0.f;
+                } else {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) pz[b] = 0.f;
+                }
                 ptx::mbar_wait(tfull, tphase);
                 if (tid == 0) stamp(p, i, 3);
                 ptx::tc_fence_after();
-                uint32_t r[32], r2[32];
-                ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);          // issuer 0: hi*hi + lo*hi
-                ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, r2);    //           hi*lo
-                ptx::tmem_ld_wait();
-                if (KB > 1) {                                                       // issuer 1 (odd k-blocks)
-                    uint32_t r3[32], r4[32];
-                    ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 64, r3);
-                    ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 96, r4);
+                if (g < G) {
+                    uint32_t r[32], r3[32];
+                    const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
+                    ptx::tmem_ld32(lane_base, r);                                       // issuer 0: hi*hi + lo*hi  (or the single product)
+                    ptx::tmem_ld32(lane_base + PIECES * NB, r3);                        // issuer 1 (odd k-blocks)
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        r[b] = __float_as_uint(__uint_as_float(r[b]) + __uint_as_float(r3[b]));
-                        r2[b] = __float_as_uint(__uint_as_float(r2[b]) + __uint_as_float(r4[b]));
+                    for (int b = 0; b < NB; ++b) pz[b] += __uint_as_float(r[b]) + (KB > 1 ? __uint_as_float(r3[b]) : 0.f);
+                    if (PIECES == 2) {
+                        ptx::tmem_ld32(lane_base + 32, r);                              // hi*lo of both issuers
+                        ptx::tmem_ld32(lane_base + 96, r3);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) pz[b] += __uint_as_float(r[b]) + (KB > 1 ? __uint_as_float(r3[b]) : 0.f);
                     }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty);
                 tphase ^= 1;
+                if (g < G) {
 #pragma unroll
-                for (int b = 0; b < NB; ++b) zs[(g * NB + b) * UPC + ul] = (__uint_as_float(r[b]) + __uint_as_float(r2[b])) + pz[b];
+                    for (int b = 0; b < NB; ++b) zs[(g * NB + b) * UPC + ul] = pz[b];
+                }
             }
             cell_bar();
             __nv_bfloat16 *hb = p.xbuf + ((size_t)(d * 2 + ((i + 1) & 1)) * NB) * H + ucol + cu;
             const size_t piece = (size_t)2 * 2 * NB * H;
-            float o_gi[4], o_gj[4], o_gf[4], o_go[4], o_h[4];
+            float o_g[4][4], o_s[4], o_h[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int b = bg * 4 + j;
-                const float zi = zs[(0 * NB + b) * UPC + cu], zj = zs[(1 * NB + b) * UPC + cu];
-                const float zf = zs[(2 * NB + b) * UPC + cu], zo = zs[(3 * NB + b) * UPC + cu];
                 const bool live = tt < len4[j];
-                float gi = 0.f, gj = 0.f, gf = 0.f, go = 0.f, h = 0.f;
-                if (live) {
-                    gi = sigmoidf_(zi); gj = tanhf(zj); gf = sigmoidf_(zf + p.forget_bias); go = sigmoidf_(zo);
-                    creg[j] = gf * creg[j] + gi * gj;
-                    h = go * tanhf(creg[j]);
+                float h = 0.f;
+                o_g[j][0] = o_g[j][1] = o_g[j][2] = o_g[j][3] = 0.f;
+                if (CELL == CELL_L) {
+                    const float zi = zs[(0 * NB + b) * UPC + cu], zj = zs[(1 * NB + b) * UPC + cu];
+                    const float zf = zs[(2 * NB + b) * UPC + cu], zo = zs[(3 * NB + b) * UPC + cu];
+                    if (live) {
+                        const float gi = sigmoidf_(zi), gj = tanhf(zj), gf = sigmoidf_(zf + p.forget_bias), go = sigmoidf_(zo);
+                        sreg[j] = gf * sreg[j] + gi * gj;
+                        h = go * tanhf(sreg[j]);
+                        o_g[j][0] = gi; o_g[j][1] = gj; o_g[j][2] = gf; o_g[j][3] = go;
+                    }
+                    o_s[j] = sreg[j];
+                } else {
+                    const float ur = zs[(0 * NB + b) * UPC + cu], uz = zs[(1 * NB + b) * UPC + cu], un = zs[(2 * NB + b) * UPC + cu];
+                    o_s[j] = 0.f;
+                    if (live) {
+                        const float q = un + brn;
+                        const float gr = sigmoidf_(pin[j * 3 + 0] + ur), gz = sigmoidf_(pin[j * 3 + 1] + uz);
+                        const float gn = tanhf(pin[j * 3 + 2] + gr * q);
+                        h = (1.f - gz) * gn + gz * sreg[j];
+                        sreg[j] = h;
+                        o_g[j][0] = gr; o_g[j][1] = gz; o_g[j][2] = gn;
+                        o_s[j] = q;
+                    }
                 }
-                o_gi[j] = gi; o_gj[j] = gj; o_gf[j] = gf; o_go[j] = go; o_h[j] = h;
+                o_h[j] = h;
                 // h_t is the only thing the other CTAs wait for: publish it first
-                __nv_bfloat16 hi, lo;
-                split2(h, hi, lo);
-                hb[(size_t)b * H] = hi;
-                hb[piece + (size_t)b * H] = lo;
+                if (PIECES == 2) {
+                    __nv_bfloat16 hi, lo;
+                    split2(h, hi, lo);
+                    hb[(size_t)b * H] = hi;
+                    hb[piece + (size_t)b * H] = lo;
+                } else {
+                    hb[(size_t)b * H] = __float2bfloat16_rn(h);
+                }
             }
             if (tid == 0) stamp(p, i, 4);
             // every writing thread orders its own h pieces for the other CTAs' TMA (async proxy) reads: a single
@@ -368,9 +410,10 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
                 const int b = bg * 4 + j;
                 if (b < B) {
-                    float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
-                    grow[0] = o_gi[j]; grow[H] = o_gj[j]; grow[2 * (size_t)H] = o_gf[j]; grow[3 * (size_t)H] = o_go[j];
-                    p.cstate[((size_t)tt * p.BS + b) * 2 * H + (size_t)d * H + ucol + cu] = creg[j];
+                    float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * G * H + ucol + cu;
+#pragma unroll
+                    for (int q = 0; q < G; ++q) grow[(size_t)q * H] = o_g[j][q];
+                    p.cstate[((size_t)tt * p.BS + b) * 2 * H + (size_t)d * H + ucol + cu] = o_s[j];
                     p.y[((size_t)tt * p.BS + b) * 2 * H + (size_t)d * H + ucol + cu] = o_h[j];
                 }
             }
@@ -565,67 +608,67 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
 }
 
 // ================================== backward, 4-CTA cluster split-K ================================
-// dh_{t-1}[b, u] = sum over the 4H gate columns of dz_t[b, :] Wh[u, :].  A cluster of 4 CTAs owns 128
-// hidden units; CTA q contracts the H columns of gate q with a full M = 128 tile
-//   D_q[128 units, 32 batch] = Wh[units, q*H .. (q+1)*H) . dz_t[:, q*H .. (q+1)*H)^T
+// dh_{t-1}[b, u] = sum over the G*H gate columns of dz_t[b, :] Wh[u, :].  A cluster of 4 CTAs owns 128
+// hidden units; CTA q contracts the K-quarter [q GH/4, (q+1) GH/4) with a full M = 128 tile
+//   D_q[128 units, 32 batch] = Wh[units, K-quarter] . dz_t[:, K-quarter]^T
 // (the same pipeline shape as the forward kernel), then warp w of every CTA ships its 32 unit rows
 // to CTA w of the cluster through distributed shared memory, and CTA w adds the four partials and
-// runs the cell backward for those 32 units.  Per step and CTA: 1 MB of weights (streamed), 256 KB
-// of dz (L2), 384 MMAs — a quarter of what the single-CTA formulation below needs.
-constexpr int C_XCH = 4 * NB * UPC * 4;                          // slots [4 sources][32 b][32 u] fp32
-constexpr int C_SMEM = F_NSTAGE * F_STAGE + C_XCH + 1024 + 256;
-
+// runs the cell backward for those 32 units.  Per step and CTA (LSTM, H = 2048): 1 MB of weights (streamed), 256 KB
+// of dz (L2), 384 MMAs.  GRU: dz_t here is the gradient wrt h R (the n columns scaled by r).
+template <int CELL, int PIECES>
 __global__ void __launch_bounds__(NTHREADS, 1)
-lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ, const Params p)
+gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ, const Params p)
 {
+    using R = Ring<PIECES>;
+    constexpr int G = CELL == CELL_G ? 3 : 4;
+    constexpr int NSTAGE = R::NSTAGE, STAGE = R::STAGE;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-    const uint32_t xch_base = smem_base + F_NSTAGE * F_STAGE;
-    const float *slots = reinterpret_cast<const float *>(smem_gen + F_NSTAGE * F_STAGE);   // [4][32 b][32 u]
-    const uint32_t bar_base = xch_base + C_XCH;
+    const uint32_t xch_base = smem_base + NSTAGE * STAGE;
+    const float *slots = reinterpret_cast<const float *>(smem_gen + NSTAGE * STAGE);   // [4][32 b][32 u]
+    const uint32_t bar_base = xch_base + R::XCH;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
-    auto fullB = [&](int s) { return bar_base + 8u * (F_NSTAGE + s); };
-    auto empty = [&](int s) { return bar_base + 8u * (2 * F_NSTAGE + s); };
-    const uint32_t tfull = bar_base + 8u * (3 * F_NSTAGE), tempty = tfull + 8, xfull = tempty + 8;
+    auto empty = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+    const uint32_t tfull = bar_base + 8u * (2 * NSTAGE), tempty = tfull + 8, xfull = tempty + 8;
     const uint32_t tmem_slot = xfull + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
-    auto a_addr = [&](int s, int pc) { return smem_base + s * F_STAGE + pc * F_A_PIECE; };
-    auto b_addr = [&](int s, int pc) { return smem_base + s * F_STAGE + 2 * F_A_PIECE + pc * F_B_PIECE; };
+    auto a_addr = [&](int s, int pc) { return smem_base + s * STAGE + pc * F_A_PIECE; };
+    auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * F_B_PIECE; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = (int)ptx::cluster_ctarank();                  // gate / K-range of this CTA
+    const int q = (int)ptx::cluster_ctarank();                  // K-quarter of this CTA
     const int cid = blockIdx.x >> 2;
     const int UBD = p.H / 128;                                  // unit blocks per direction
     const int d = cid / UBD, ub = cid % UBD;
-    const int T = p.T, B = p.B, H = p.H, KB = H / BK;
-#ifdef CTCASR_DEBUG_WAIT
-    if (blockIdx.x == 0 && threadIdx.x == 0) printf("bwd bar_base %u (full +8s, empty +%d+8s, tfull +%d, tempty +%d, xfull +%d)\n", bar_base, 16 * F_NSTAGE, 24 * F_NSTAGE, 24 * F_NSTAGE + 8, 24 * F_NSTAGE + 16);
-#endif
+    const int T = p.T, B = p.B, H = p.H, GH = G * H, KQ = GH / 4, KB = KQ / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
         ptx::mbar_init(tfull, 2); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapZ); }
-    const uint32_t tmem_cols = p.kres > 0 ? 512u : 128u;
+    const uint32_t tmem_cols = p.kres > 0 ? 512u : (uint32_t)R::ACC_COLS;
     if (warp == 6) ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();            // every CTA's barriers exist before anyone arrives remotely
     ptx::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot_ptr;
-    const uint32_t tmem_w = tmem_d + 128;                 // resident weights, as in the forward kernel
+    const uint32_t tmem_w = tmem_d + R::ACC_COLS;         // resident weights, as in the forward kernel
     if (warp < 4 && p.kres > 0) {
         const int row = d * H + ub * 128 + warp * 32 + lane;
         for (int kb = 0; kb < p.kres; ++kb)
-            for (int pc = 0; pc < 2; ++pc) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wpack + ((size_t)pc * p.wrows + row) * p.wk + (size_t)q * H + (size_t)kb * BK);
+            for (int pc = 0; pc < PIECES; ++pc) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.wpack + ((size_t)pc * p.wrows + row) * p.wk + (size_t)q * KQ + (size_t)kb * BK);
                 uint32_t r[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = __ldg(src + j);
-                ptx::tmem_st32(tmem_w + ((uint32_t)(warp * 32) << 16) + (uint32_t)((kb * 2 + pc) * 32), r);
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 v = __ldg(src + j);
+                    r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+                }
+                ptx::tmem_st32(tmem_w + ((uint32_t)(warp * 32) << 16) + (uint32_t)((kb * PIECES + pc) * 32), r);
             }
         ptx::tmem_st_wait();
     }
@@ -634,8 +677,8 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
     ptx::tc_fence_after();
 
     if (warp == 4) {
-        if (lane == 0) {        // Wh[d][128 units of the cluster][columns of gate q], K-major as stored
-            SubRing ring[2] = {SubRing(0), SubRing(1)};
+        if (lane == 0) {        // Wh[d][128 units of the cluster][K-quarter], K-major as stored
+            SubRing ring[2] = {SubRing(0, NSTAGE), SubRing(1, NSTAGE)};
             const int row0 = d * H + ub * 128;
             const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int n = 0; n < T; ++n)
@@ -646,16 +689,16 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                     if (kb < p.kres) {
                         ptx::mbar_arrive(fullA(stage));     // resident in tensor memory
                     } else {
-                        ptx::mbar_expect_tx(fullA(stage), 2 * F_A_PIECE);
+                        ptx::mbar_expect_tx(fullA(stage), PIECES * F_A_PIECE);
                         const uint64_t pol = kb - p.kres < p.kb_keep ? keep : stream;
-                        ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, q * H + kb * BK, row0, 0, fullA(stage), pol);   // both pieces
+                        ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, q * KQ + kb * BK, row0, 0, fullA(stage), pol);   // all pieces
                     }
                     r.advance();
                 }
         }
     } else if (warp == 5) {
-        if (lane == 0) {        // dz of the step processed before, gate-q columns, all batch rows
-            SubRing ring[2] = {SubRing(0), SubRing(1)};
+        if (lane == 0) {        // dz of the step processed before, my K-quarter of the gate columns, all batch rows
+            SubRing ring[2] = {SubRing(0, NSTAGE), SubRing(1, NSTAGE)};
             if (d == 1) stagger_wait(p.stagger_ns);
             for (int n = 0; n < T; ++n) {
                 wait_counter(p.counters + d, (unsigned)(p.CPD * n), p.counters + 2);
@@ -665,8 +708,8 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                     SubRing &r = ring[kb & 1];
                     const int stage = r.slot();
                     ptx::mbar_wait(empty(stage), r.phase ^ 1);
-                    ptx::mbar_expect_tx(fullA(stage), 2 * F_B_PIECE);
-                    ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * H + kb * BK, row0, 0, fullA(stage));   // both pieces
+                    ptx::mbar_expect_tx(fullA(stage), PIECES * F_B_PIECE);
+                    ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * KQ + kb * BK, row0, 0, fullA(stage));   // all pieces
                     r.advance();
                 }
             }
@@ -675,9 +718,9 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
         if (lane == 0) {        // two MMA issuers (even / odd k-blocks, separate accumulators), see the forward kernel
             const int me = warp - 6;
             const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
-            const uint32_t acc = tmem_d + (uint32_t)(me * 2 * NB);
+            const uint32_t acc = tmem_d + (uint32_t)(me * PIECES * NB);
             uint32_t tphase = 0;
-            SubRing ring(me);
+            SubRing ring(me, NSTAGE);
             for (int n = 0; n < T; ++n) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
@@ -687,20 +730,34 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                     ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
                     const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
-                    if (kb < p.kres) {
-                        const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
+                    if (PIECES == 2) {
+                        if (kb < p.kres) {
+                            const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
 #pragma unroll
-                        for (int j = 0; j < BK / 16; ++j) {
-                            ptx::mma_bf16_ts(acc, ta_hi + 8 * j, bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
-                            ptx::mma_bf16_ts(acc, ta_lo + 8 * j, bd + (uint64_t)(2 * j), idesc32, 1);
+                            for (int j = 0; j < BK / 16; ++j) {
+                                ptx::mma_bf16_ts(acc, ta_hi + 8 * j, bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                                ptx::mma_bf16_ts(acc, ta_lo + 8 * j, bd + (uint64_t)(2 * j), idesc32, 1);
+                            }
+                        } else {
+                            const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+                            const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
+#pragma unroll
+                            for (int j = 0; j < BK / 16; ++j) {
+                                ptx::mma_bf16(acc, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                                ptx::mma_bf16(acc, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
+                            }
                         }
                     } else {
-                        const uint64_t ad_hi = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
-                        const uint64_t ad_lo = ptx::make_smem_desc(a_addr(stage, 1), 16, 1024, 2);
+                        if (kb < p.kres) {
+                            const uint32_t ta = tmem_w + (uint32_t)(kb * 32);
 #pragma unroll
-                        for (int j = 0; j < BK / 16; ++j) {
-                            ptx::mma_bf16(acc, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
-                            ptx::mma_bf16(acc, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
+                            for (int j = 0; j < BK / 16; ++j)
+                                ptx::mma_bf16_ts(acc, ta + 8 * j, bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
+                        } else {
+                            const uint64_t ad = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+#pragma unroll
+                            for (int j = 0; j < BK / 16; ++j)
+                                ptx::mma_bf16(acc, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
                         }
                     }
                     ptx::mma_commit(empty(stage));
@@ -716,13 +773,13 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
         const int e = reader ? tid : tid - 128;                             // 0..255
         const int cu = e & 31, bg = e >> 5;                                 // cell ownership: rows bg*4 .. bg*4+3
         const int ucol = ub * 128 + q * UPC;                                // the 32 units whose cells this CTA owns
-        float dcreg[4];
-        float dbacc[4] = {0.f, 0.f, 0.f, 0.f};                              // bias gradient: sum of dz over time and my rows
+        float carry[4];                                                     // LSTM: dc carried to the previous frame; GRU: z * dh
+        float dbacc[4] = {0.f, 0.f, 0.f, 0.f};                              // bias gradient: sum of dz over time and my rows (GRU [3]: b_rn)
         int len4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int b = bg * 4 + j; dcreg[j] = 0.f; len4[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
+        for (int j = 0; j < 4; ++j) { const int b = bg * 4 + j; carry[j] = 0.f; len4[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
         uint32_t tphase = 0;
-        const size_t GW = (size_t)8 * H;
+        const size_t GW = (size_t)2 * GH;
         // destination of my TMEM rows: CTA `warp` of the cluster, slot q, [b][lane]
         const uint32_t remote_slot = ptx::mapa(xch_base + (uint32_t)(q * NB * UPC) * 4u, (uint32_t)(warp & 3));
         const uint32_t remote_bar = ptx::mapa(xfull, (uint32_t)(warp & 3));
@@ -730,77 +787,99 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
             const int i = T - 1 - n;
             const int tt = d == 0 ? i : T - 1 - i;
             const int tp = d == 0 ? tt - 1 : tt + 1;
-            float gi[4], gj[4], gf[4], go[4], cc[4], cp[4], dyv[4];
+            // everything the cell needs that does not depend on the recurrence
+            float ga[4][4], sc[4], sp[4], dyv[4];            // gate activations; LSTM: c_t, c_{t-1};  GRU: q_t, h_{t-1}
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int b = bg * 4 + j;
-                gi[j] = gj[j] = gf[j] = go[j] = cc[j] = cp[j] = dyv[j] = 0.f;
+                ga[j][0] = ga[j][1] = ga[j][2] = ga[j][3] = sc[j] = sp[j] = dyv[j] = 0.f;
                 if (b < B) {
-                    const float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
-                    gi[j] = grow[0]; gj[j] = grow[H]; gf[j] = grow[2 * (size_t)H]; go[j] = grow[3 * (size_t)H];
+                    const float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
+#pragma unroll
+                    for (int k = 0; k < G; ++k) ga[j][k] = grow[(size_t)k * H];
                     const size_t so = (size_t)d * H + ucol + cu;
-                    cc[j] = p.cstate[((size_t)tt * p.BS + b) * 2 * H + so];
-                    if (i > 0) cp[j] = p.cstate[((size_t)tp * p.BS + b) * 2 * H + so];
+                    sc[j] = p.cstate[((size_t)tt * p.BS + b) * 2 * H + so];
+                    if (i > 0) sp[j] = CELL == CELL_L ? p.cstate[((size_t)tp * p.BS + b) * 2 * H + so] : p.y[((size_t)tp * p.BS + b) * 2 * H + so];
                     dyv[j] = p.dy[((size_t)tt * p.BS + b) * 2 * H + so];
                 }
             }
             if (reader) {
                 ptx::mbar_wait(tfull, tphase);
                 ptx::tc_fence_after();
-                uint32_t r[32], r2[32];
-                ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);      // rows = units 32*warp + lane of the block
-                ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, r2);
-                ptx::tmem_ld_wait();
-                if (KB > 1) {
-                    uint32_t r3[32], r4[32];
-                    ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 64, r3);
-                    ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 96, r4);
+                float part[NB];
+                {
+                    uint32_t r[32], r3[32];
+                    const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);      // rows = units 32*warp + lane of the block
+                    ptx::tmem_ld32(lane_base, r);
+                    ptx::tmem_ld32(lane_base + PIECES * NB, r3);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        r[b] = __float_as_uint(__uint_as_float(r[b]) + __uint_as_float(r3[b]));
-                        r2[b] = __float_as_uint(__uint_as_float(r2[b]) + __uint_as_float(r4[b]));
+                    for (int b = 0; b < NB; ++b) part[b] = __uint_as_float(r[b]) + (KB > 1 ? __uint_as_float(r3[b]) : 0.f);
+                    if (PIECES == 2) {
+                        ptx::tmem_ld32(lane_base + 32, r);
+                        ptx::tmem_ld32(lane_base + 96, r3);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) part[b] += __uint_as_float(r[b]) + (KB > 1 ? __uint_as_float(r3[b]) : 0.f);
                     }
                 }
                 ptx::tc_fence_before();
 #pragma unroll
                 for (int b = 0; b < NB; ++b)
-                    ptx::st_cluster_f32(remote_slot + (uint32_t)(b * UPC + lane) * 4u, __uint_as_float(r[b]) + __uint_as_float(r2[b]));
+                    ptx::st_cluster_f32(remote_slot + (uint32_t)(b * UPC + lane) * 4u, part[b]);
                 __syncwarp();
                 if (lane == 0) { ptx::mbar_arrive(tempty); ptx::mbar_arrive_remote(remote_bar); }
             }
             ptx::mbar_wait_cluster(xfull, tphase);                          // the four partials of my units have landed
             tphase ^= 1;
-            __nv_bfloat16 *zb = p.xbuf + ((size_t)(d * 2 + ((n + 1) & 1)) * NB) * 4 * H + ucol + cu;
-            const size_t piece = (size_t)2 * 2 * NB * 4 * H;
-            float o_dz[4][4];
+            __nv_bfloat16 *zb = p.xbuf + ((size_t)(d * 2 + ((n + 1) & 1)) * NB) * GH + ucol + cu;
+            const size_t piece = (size_t)2 * 2 * NB * GH;
+            float o_dz[4][4], o_zr[4];                                      // o_zr (GRU): dn_pre * r, the n column of dzr
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int b = bg * 4 + j;
                 const bool live = tt < len4[j];
-                float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+                o_dz[j][0] = o_dz[j][1] = o_dz[j][2] = o_dz[j][3] = 0.f;
+                o_zr[j] = 0.f;
                 if (live) {
                     const int o = b * UPC + cu;
                     const float dh = dyv[j] + ((slots[o] + slots[NB * UPC + o]) + (slots[2 * NB * UPC + o] + slots[3 * NB * UPC + o]));
-                    const float tc = tanhf(cc[j]);
-                    const float dc = dh * go[j] * (1.f - tc * tc) + dcreg[j];
-                    dzi = dc * gj[j] * gi[j] * (1.f - gi[j]);
-                    dzj = dc * gi[j] * (1.f - gj[j] * gj[j]);
-                    dzf = dc * cp[j] * gf[j] * (1.f - gf[j]);
-                    dzo = dh * tc * go[j] * (1.f - go[j]);
-                    dcreg[j] = dc * gf[j];
+                    if (CELL == CELL_L) {
+                        const float gi = ga[j][0], gj = ga[j][1], gf = ga[j][2], go = ga[j][3];
+                        const float tc = tanhf(sc[j]);
+                        const float dc = dh * go * (1.f - tc * tc) + carry[j];
+                        o_dz[j][0] = dc * gj * gi * (1.f - gi);
+                        o_dz[j][1] = dc * gi * (1.f - gj * gj);
+                        o_dz[j][2] = dc * sp[j] * gf * (1.f - gf);
+                        o_dz[j][3] = dh * tc * go * (1.f - go);
+                        carry[j] = dc * gf;
+                    } else {
+                        const float gr = ga[j][0], gz = ga[j][1], gn = ga[j][2];
+                        const float dht = dh + carry[j];
+                        const float dn_pre = dht * (1.f - gz) * (1.f - gn * gn);
+                        o_dz[j][0] = dn_pre * sc[j] * gr * (1.f - gr);
+                        o_dz[j][1] = dht * (sp[j] - gn) * gz * (1.f - gz);
+                        o_dz[j][2] = dn_pre;
+                        o_zr[j] = dn_pre * gr;
+                        carry[j] = dht * gz;
+                    }
                 } else {
-                    dcreg[j] = 0.f;
+                    carry[j] = 0.f;
                 }
-                o_dz[j][0] = dzi; o_dz[j][1] = dzj; o_dz[j][2] = dzf; o_dz[j][3] = dzo;
-                dbacc[0] += dzi; dbacc[1] += dzj; dbacc[2] += dzf; dbacc[3] += dzo;
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {        // the bf16 pieces are what the other CTAs wait for
-                    __nv_bfloat16 hi, lo;
-                    split2(o_dz[j][g4], hi, lo);
-                    zb[(size_t)b * 4 * H + (size_t)g4 * H] = hi;
-                    zb[piece + (size_t)b * 4 * H + (size_t)g4 * H] = lo;
+                for (int g4 = 0; g4 < G; ++g4) {        // the bf16 pieces are what the other CTAs wait for
+                    const float v = (CELL == CELL_G && g4 == 2) ? o_zr[j] : o_dz[j][g4];
+                    dbacc[g4] += o_dz[j][g4];
+                    if (PIECES == 2) {
+                        __nv_bfloat16 hi, lo;
+                        split2(v, hi, lo);
+                        zb[(size_t)b * GH + (size_t)g4 * H] = hi;
+                        zb[piece + (size_t)b * GH + (size_t)g4 * H] = lo;
+                    } else {
+                        zb[(size_t)b * GH + (size_t)g4 * H] = __float2bfloat16_rn(v);
+                    }
                 }
+                if (CELL == CELL_G) dbacc[3] += o_zr[j];
             }
             __threadfence();                // per-thread fences: see the forward kernel
             ptx::fence_proxy_async();
@@ -810,14 +889,19 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
             for (int j = 0; j < 4; ++j) {               // fp32 dz for the weight-gradient GEMMs, after the signal
                 const int b = bg * 4 + j;
                 if (b < B) {
-                    float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * 4 * H + ucol + cu;
-                    grow[0] = o_dz[j][0]; grow[H] = o_dz[j][1]; grow[2 * (size_t)H] = o_dz[j][2]; grow[3 * (size_t)H] = o_dz[j][3];
+                    float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
+#pragma unroll
+                    for (int k = 0; k < G; ++k) grow[(size_t)k * H] = o_dz[j][k];
+                    if (CELL == CELL_G) {
+                        float *zrow = p.dzr + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
+                        zrow[0] = o_dz[j][0]; zrow[H] = o_dz[j][1]; zrow[2 * (size_t)H] = o_zr[j];
+                    }
                 }
             }
         }
         if (p.dbias) {
-            // column sums of dz for my 32 units x 4 gates: the 8 row groups meet in the (now idle) exchange slots
-            float *red = const_cast<float *>(slots);                        // [8 bg][4 gates][32 cu]
+            // column sums of dz for my 32 units x 4 sums: the 8 row groups meet in the (now idle) exchange slots
+            float *red = const_cast<float *>(slots);                        // [8 bg][4][32 cu]
             cell_bar();
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) red[(bg * 4 + g4) * UPC + cu] = dbacc[g4];
@@ -827,7 +911,9 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
                 float v = 0.f;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v += red[(k * 4 + g4) * UPC + cu];
-                float *dst = p.dbias + (size_t)d * 4 * H + (size_t)g4 * H + ucol + cu;
+                // LSTM: 4 gate blocks of [2][4H];  GRU: 3 gate blocks of [2][3H], then b_rn [2][H]
+                float *dst = (CELL == CELL_G && g4 == 3) ? p.dbias + (size_t)2 * GH + (size_t)d * H + ucol + cu
+                                                         : p.dbias + (size_t)d * GH + (size_t)g4 * H + ucol + cu;
                 *dst = p.db_accum ? *dst + v : v;
             }
         }
@@ -840,67 +926,45 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_c
 }
 
 // ---- weight pre-packs --------------------------------------------------------------------------------
-// forward: Wh fp32 [2][H][4H] -> Wp bf16 [2 pieces][2*4H rows][H], row (d, c, g, ul) = gate column
+// forward: Wh fp32 [2][H][G*H] -> Wp bf16 [pieces][2*4H rows][H], row (d, c, g, ul) = gate column
 // g*H + 32c + ul of direction d, K (= h index) contiguous: the K-major A operand of the swap-AB MMA.
-__global__ void pack_wh_fwd_kernel(const float *__restrict__ wh, __nv_bfloat16 *__restrict__ wp, int H)
+// A CTA tile always has four 32-row gate groups; with G = 3 (GRU) the fourth stays zero (the buffer is cleared).
+__global__ void pack_wh_fwd_kernel(const float *__restrict__ wh, __nv_bfloat16 *__restrict__ wp, int H, int G, int pieces)
 {
     __shared__ float tile[32][33];
-    const int d = blockIdx.z, k0 = blockIdx.y * 32, col0 = blockIdx.x * 32;     // col in [0, 4H)
+    const int d = blockIdx.z, k0 = blockIdx.y * 32, col0 = blockIdx.x * 32;     // col in [0, GH)
     const int tx = threadIdx.x, ty = threadIdx.y;                                // 32 x 8
-    const size_t GH = (size_t)4 * H;
+    const size_t GH = (size_t)G * H, R4 = (size_t)4 * H;
     for (int j = ty; j < 32; j += 8) tile[j][tx] = wh[((size_t)d * H + k0 + j) * GH + col0 + tx];
     __syncthreads();
-    const size_t piece = (size_t)2 * GH * H;
+    const size_t piece = (size_t)2 * R4 * H;
     for (int j = ty; j < 32; j += 8) {
         const int col = col0 + j;                  // gate column g*H + u
         const int g = col / H, u = col % H;
-        const size_t row = (size_t)d * GH + (size_t)(u / UPC) * 128 + g * UPC + (u % UPC);
-        __nv_bfloat16 hi, lo;
-        split2(tile[tx][j], hi, lo);
-        wp[row * H + k0 + tx] = hi;
-        wp[piece + row * H + k0 + tx] = lo;
+        const size_t row = (size_t)d * R4 + (size_t)(u / UPC) * 128 + g * UPC + (u % UPC);
+        if (pieces == 2) {
+            __nv_bfloat16 hi, lo;
+            split2(tile[tx][j], hi, lo);
+            wp[row * H + k0 + tx] = hi;
+            wp[piece + row * H + k0 + tx] = lo;
+        } else {
+            wp[row * H + k0 + tx] = __float2bfloat16_rn(tile[tx][j]);
+        }
     }
 }
-// backward: plain 2-piece split of Wh viewed as [2H rows][4H]
-__global__ void split2_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, size_t n)
+// backward: bf16 pieces of Wh viewed as [2H rows][GH]
+__global__ void split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, size_t n, int pieces)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        __nv_bfloat16 hi, lo;
-        split2(x[i], hi, lo);
-        out[i] = hi;
-        out[n + i] = lo;
+        if (pieces == 2) {
+            __nv_bfloat16 hi, lo;
+            split2(x[i], hi, lo);
+            out[i] = hi;
+            out[n + i] = lo;
+        } else {
+            out[i] = __float2bfloat16_rn(x[i]);
+        }
     }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    });
-    return fn;
-}
-// bf16 [pieces][rows][inner], box [1][box_rows][64], SWIZZLE_128B
-static int make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t rows, uint32_t box_rows, uint32_t box_pieces = 2)
-{
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return fail(CTCASR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[3] = {inner, rows, 2};
-    cuuint64_t strides[2] = {inner * 2, rows * inner * 2};
-    cuuint32_t box[3] = {BK, box_rows, box_pieces};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(CTCASR_ERR_CUDA, "lstm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return CTCASR_OK;
 }
 
 static unsigned long long *g_trace = nullptr;
@@ -917,29 +981,34 @@ static WsLayout ws_layout(int H)
     return w;
 }
 
-// How many of the H/64 weight k-blocks per CTA are loaded with the L2 evict_last policy.  The two
-// directions' recurrent weights are 16 H^2 bytes (128 MiB at H = 2048) against ~126 MB of L2, so only a
-// share can stay resident across time steps; the rest streams from HBM with evict_first so that it
-// does not push the resident share out.  CTCASR_LSTM_L2_KEEP_MB overrides the resident budget.
-static int keep_kblocks(int H)
+static int env_int(const char *name, int dflt)
 {
-    const char *e = getenv("CTCASR_LSTM_L2_KEEP_MB");
-    const double budget_mb = e ? atof(e) : 64.0;
-    const double total_mb = 32.0 * H * H / 1048576.0;       // both directions, two bf16 pieces per weight
-    const int KB = H / BK;
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// How many of the streamed weight k-blocks per CTA are loaded with the L2 evict_last policy.  The two
+// directions' recurrent weights are 16 H^2 bytes as two bf16 pieces (128 MiB at H = 2048) against ~126 MB of
+// L2, so only a share can stay resident across time steps; the rest streams from HBM with evict_first so that
+// it does not push the resident share out.  With one piece (64 MiB) everything stays.
+// CTCASR_LSTM_L2_KEEP_MB overrides the resident budget.
+static int keep_kblocks(int H, int G, int pieces, int KB)
+{
+    static const double budget_mb = (double)env_int("CTCASR_LSTM_L2_KEEP_MB", 64);
+    const double total_mb = 2.0 * H * G * H * 2.0 * pieces / 1048576.0;
     int k = (int)(KB * budget_mb / total_mb);
     return k < 0 ? 0 : (k > KB ? KB : k);
 }
 
-// Tensor-memory-resident weight share: 384 of the 512 columns next to the accumulators hold the first 6
-// k-blocks (192 KB) of every CTA's weight slice for the whole sequence, read by the MMA as a TMEM A operand.
-static int resident_kblocks(int H)
+// Tensor-memory-resident weight share: the columns next to the accumulators hold the first k-blocks of every
+// CTA's weight slice for the whole sequence (6 with two pieces, 14 with one), read by the MMA as a TMEM A operand.
+static int resident_kblocks(int KB, int pieces)
 {
-    const char *e = getenv("CTCASR_LSTM_KRES");
-    int kres = e ? atoi(e) : 6;
-    if (kres > 6) kres = 6;
-    if (kres > H / BK) kres = H / BK;
-    return kres < 0 ? 0 : kres;
+    static const int env = env_int("CTCASR_LSTM_KRES", -1);
+    const int kmax = pieces == 2 ? Ring<2>::KRES_MAX : Ring<1>::KRES_MAX;
+    int kres = env >= 0 ? env : kmax;
+    if (kres > kmax) kres = kmax;
+    return kres > KB ? KB : kres;
 }
 
 static int check_coop(const void *kernel, int smem, int grid)
@@ -955,13 +1024,28 @@ static int check_coop(const void *kernel, int smem, int grid)
     return CTCASR_OK;
 }
 
+typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
+static KernelFn fwd_kernel(int cell, int pieces)
+{
+    if (cell == CELL_G) return pieces == 2 ? gated_fwd_kernel<CELL_G, 2> : gated_fwd_kernel<CELL_G, 1>;
+    return pieces == 2 ? gated_fwd_kernel<CELL_L, 2> : gated_fwd_kernel<CELL_L, 1>;
+}
+static KernelFn bwd_kernel(int cell, int pieces)
+{
+    if (cell == CELL_G) return pieces == 2 ? gated_bwd_cluster_kernel<CELL_G, 2> : gated_bwd_cluster_kernel<CELL_G, 1>;
+    return pieces == 2 ? gated_bwd_cluster_kernel<CELL_L, 2> : gated_bwd_cluster_kernel<CELL_L, 1>;
+}
+
 }  // namespace lstm
 
 void lstm_tc_set_trace(unsigned long long *buf) { lstm::g_trace = buf; }
 
 bool lstm_tc_eligible(int T, int B, int H, int cell)
 {
-    return cell == CTCASR_CELL_LSTM && T >= 1 && B >= 1 && H >= 64 && H % 64 == 0 && 2 * (H / lstm::UPC) <= 148;
+    if (T < 1 || B < 1 || 2 * (H / lstm::UPC) > 148) return false;
+    if (cell == CTCASR_CELL_LSTM) return H >= 64 && H % 64 == 0;
+    if (cell == CTCASR_CELL_GRU) return H >= 256 && H % 256 == 0;       // K-quarters of 3H in whole k-blocks
+    return false;
 }
 
 size_t lstm_tc_workspace_bytes(int B, int H)
@@ -971,8 +1055,8 @@ size_t lstm_tc_workspace_bytes(int B, int H)
     return lstm::ws_layout(H).total + 1024;
 }
 
-int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate, float *y,
-                int T, int B, int H, int use_len, float forget_bias, void *ws, cudaStream_t stream)
+int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate, float *y, const float *bias_rn,
+                int T, int B, int H, int cell, int pieces, int use_len, float forget_bias, void *ws, cudaStream_t stream)
 {
     using namespace lstm;
     char *base = reinterpret_cast<char *>(align_up((size_t)(uintptr_t)ws, 1024));
@@ -980,48 +1064,52 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
     __nv_bfloat16 *wp = reinterpret_cast<__nv_bfloat16 *>(base + L.wpack);
     __nv_bfloat16 *hbuf = reinterpret_cast<__nv_bfloat16 *>(base + L.xbuf);
     unsigned int *ctr = reinterpret_cast<unsigned int *>(base + L.counters);
-    const int CPD = H / UPC, grid = 2 * CPD;
-    static int checked_grid = 0;
-    if (checked_grid != grid) { int rc = check_coop((const void *)lstm_fwd_kernel, F_SMEM, grid); if (rc) return rc; checked_grid = grid; }
+    const int G = cell == CELL_G ? 3 : 4;
+    const int CPD = H / UPC, grid = 2 * CPD, KB = H / BK;
+    const int smem = pieces == 2 ? Ring<2>::SMEM : Ring<1>::SMEM;
+    KernelFn kernel = fwd_kernel(cell, pieces);
+    static int checked_grid[2][2] = {{0, 0}, {0, 0}};
+    int &chk = checked_grid[cell == CELL_G][pieces - 1];
+    if (chk != grid) { int rc = check_coop((const void *)kernel, smem, grid); if (rc) return rc; chk = grid; }
 
-    pack_wh_fwd_kernel<<<dim3(4 * H / 32, H / 32, 2), dim3(32, 8), 0, stream>>>(wh, wp, H);
+    if (G == 3) CTCASR_CUDA_CHECK(cudaMemsetAsync(wp, 0, (size_t)pieces * 2 * 4 * H * H * 2, stream));     // the unused fourth gate group
+    pack_wh_fwd_kernel<<<dim3(G * H / 32, H / 32, 2), dim3(32, 8), 0, stream>>>(wh, wp, H, G, pieces);
     CTCASR_LAUNCH_CHECK();
     CUtensorMap mapW, mapH;
-    int rc = make_map(&mapW, wp, H, (uint64_t)2 * 4 * H, 128);
+    int rc = make_map(&mapW, wp, H, (uint64_t)2 * 4 * H, 128, pieces, pieces);
     if (rc) return rc;
-    rc = make_map(&mapH, hbuf, H, (uint64_t)2 * 2 * NB, NB);
+    rc = make_map(&mapH, hbuf, H, (uint64_t)2 * 2 * NB, NB, pieces, pieces);
     if (rc) return rc;
+    static const int stagger = env_int("CTCASR_LSTM_STAGGER_NS", 11000);
     // batches above 32 rows run as consecutive launches over 32-row slices of the same buffers
     for (int b0 = 0; b0 < B; b0 += NB) {
-        CTCASR_CUDA_CHECK(cudaMemsetAsync(hbuf, 0, (size_t)2 * 2 * 2 * NB * H * 2, stream));  // h_{-1} = 0, padded batch rows = 0
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(hbuf, 0, (size_t)pieces * 2 * 2 * NB * H * 2, stream));  // h_{-1} = 0, padded batch rows = 0
         CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
-        Params p;
+        Params p = {};
         p.T = T; p.B = B - b0 < NB ? B - b0 : NB; p.BS = B; p.H = H; p.CPD = CPD; p.use_len = use_len;
         p.forget_bias = forget_bias; p.seq_len = seq_len ? seq_len + b0 : nullptr;
-        p.gates = gates + (size_t)b0 * 8 * H; p.cstate = cstate + (size_t)b0 * 2 * H; p.y = y + (size_t)b0 * 2 * H;
-        p.dy = nullptr; p.xbuf = hbuf; p.counters = ctr;
-        p.kb_keep = keep_kblocks(H);
-        p.dbias = nullptr; p.db_accum = 0;
-        p.kres = resident_kblocks(H);
+        p.gates = gates + (size_t)b0 * 2 * G * H; p.cstate = cstate + (size_t)b0 * 2 * H; p.y = y + (size_t)b0 * 2 * H;
+        p.bias_rn = bias_rn; p.xbuf = hbuf; p.counters = ctr;
+        p.kres = resident_kblocks(KB, pieces);
+        p.kb_keep = keep_kblocks(H, 4, pieces, KB);
         p.wpack = wp; p.wrows = 2 * 4 * H; p.wk = H;
         p.trace = g_trace;
-        p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
-        p.nprod = getenv("CTCASR_LSTM_NPROD") ? atoi(getenv("CTCASR_LSTM_NPROD")) : 3;
-        p.skip = getenv("CTCASR_LSTM_SKIP") ? atoi(getenv("CTCASR_LSTM_SKIP")) : 0;
+        p.stagger_ns = stagger;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = F_SMEM; cfg.stream = stream;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         ProfScope prof(PROF_LSTM_FWD, stream);
-        CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel, mapW, mapH, p));
+        CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, mapW, mapH, p));
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
     }
     return CTCASR_OK;
 }
 
-int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *cstate, const float *dy,
-                float *dbias, int *dbias_done, int T, int B, int H, int use_len, void *ws, cudaStream_t stream)
+int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *cstate, const float *y, const float *dy,
+                float *dzr, float *dbias, int *dbias_done, int T, int B, int H, int cell, int pieces, int use_len,
+                void *ws, cudaStream_t stream)
 {
     using namespace lstm;
     char *base = reinterpret_cast<char *>(align_up((size_t)(uintptr_t)ws, 1024));
@@ -1029,59 +1117,69 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     __nv_bfloat16 *wq = reinterpret_cast<__nv_bfloat16 *>(base + L.wpack);
     __nv_bfloat16 *zbuf = reinterpret_cast<__nv_bfloat16 *>(base + L.xbuf);
     unsigned int *ctr = reinterpret_cast<unsigned int *>(base + L.counters);
+    const int G = cell == CELL_G ? 3 : 4, GH = G * H;
     const int CPD = H / UPC, grid = 2 * CPD;
-    const size_t nw = (size_t)2 * H * 4 * H;
-    split2_kernel<<<148 * 8, 256, 0, stream>>>(wh, wq, nw);
-    CTCASR_LAUNCH_CHECK();
+    const size_t nw = (size_t)2 * H * GH;
     CUtensorMap mapW, mapZ;
     int rc = CTCASR_OK;
 
     // preferred: 4-CTA cluster split-K kernel (needs H % 128 == 0 and all clusters co-resident)
-    static int cluster_ok_grid = 0, cluster_bad_grid = 0, checked_grid = 0;
-    const bool no_cluster = getenv("CTCASR_LSTM_NO_CLUSTER") != nullptr;
+    static int cluster_ok_grid[2][2] = {{0, 0}, {0, 0}}, cluster_bad_grid = 0, checked_grid = 0;
+    static const bool no_cluster = getenv("CTCASR_LSTM_NO_CLUSTER") != nullptr;
     bool use_cluster = false;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    if (H % 128 == 0 && cluster_bad_grid != grid && !no_cluster) {
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C_SMEM; cfg.stream = stream;
+    KernelFn ckernel = bwd_kernel(cell, pieces);
+    const int csmem = pieces == 2 ? Ring<2>::SMEM : Ring<1>::SMEM;
+    if (H % 128 == 0 && cluster_bad_grid != grid && (!no_cluster || cell == CELL_G)) {
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = csmem; cfg.stream = stream;
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (cluster_ok_grid != grid) {
-            CTCASR_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
+        int &okg = cluster_ok_grid[cell == CELL_G][pieces - 1];
+        if (okg != grid) {
+            CTCASR_CUDA_CHECK(cudaFuncSetAttribute(ckernel, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem));
             int nclusters = 0;
-            cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, lstm_bwd_cluster_kernel, &cfg);
-            if (e == cudaSuccess && nclusters * 4 >= grid) cluster_ok_grid = grid;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, ckernel, &cfg);
+            if (e == cudaSuccess && nclusters * 4 >= grid) okg = grid;
             else { cluster_bad_grid = grid; (void)cudaGetLastError(); }
         }
-        use_cluster = cluster_ok_grid == grid;
+        use_cluster = okg == grid;
     }
-    rc = make_map(&mapZ, zbuf, (uint64_t)4 * H, (uint64_t)2 * 2 * NB, NB, use_cluster ? 2 : 1);
+    if (!use_cluster) {
+        if (cell != CELL_L) return fail(CTCASR_ERR_UNSUPPORTED, "lstm_tc: the GRU backward pass needs the cluster kernel");
+        pieces = 2;                                       // the single-CTA kernel is two-piece only
+    }
+    split_kernel<<<148 * 8, 256, 0, stream>>>(wh, wq, nw, pieces);
+    CTCASR_LAUNCH_CHECK();
+    rc = make_map(&mapZ, zbuf, (uint64_t)GH, (uint64_t)2 * 2 * NB, NB, use_cluster ? pieces : 1, pieces);
     if (rc) return rc;
     if (use_cluster) {
-        rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, 128);
+        rc = make_map(&mapW, wq, (uint64_t)GH, (uint64_t)2 * H, 128, pieces, pieces);
     } else {
         if (checked_grid != grid) { rc = check_coop((const void *)lstm_bwd_kernel, B_SMEM, grid); if (rc) return rc; checked_grid = grid; }
-        rc = make_map(&mapW, wq, (uint64_t)4 * H, (uint64_t)2 * H, UPC, 1);
+        rc = make_map(&mapW, wq, (uint64_t)GH, (uint64_t)2 * H, UPC, 1);
     }
     if (rc) return rc;
+    static const int stagger = env_int("CTCASR_LSTM_STAGGER_NS", 11000);
+    const int KB = GH / 4 / BK;
     for (int b0 = 0; b0 < B; b0 += NB) {
-        CTCASR_CUDA_CHECK(cudaMemsetAsync(zbuf, 0, (size_t)2 * 2 * 2 * NB * 4 * H * 2, stream));  // no recurrent gradient into the last step
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(zbuf, 0, (size_t)pieces * 2 * 2 * NB * GH * 2, stream));  // no recurrent gradient into the last step
         CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
-        Params p;
+        Params p = {};
         p.T = T; p.B = B - b0 < NB ? B - b0 : NB; p.BS = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = 0.f;
         p.seq_len = seq_len ? seq_len + b0 : nullptr;
-        p.gates = gates + (size_t)b0 * 8 * H; p.cstate = const_cast<float *>(cstate) + (size_t)b0 * 2 * H; p.y = nullptr;
-        p.dy = dy + (size_t)b0 * 2 * H; p.xbuf = zbuf; p.counters = ctr;
-        p.kb_keep = keep_kblocks(H);
-        p.kres = use_cluster ? resident_kblocks(H) : 0; p.wpack = wq; p.wrows = 2 * H; p.wk = 4 * H;
+        p.gates = gates + (size_t)b0 * 2 * GH; p.cstate = const_cast<float *>(cstate) + (size_t)b0 * 2 * H;
+        p.y = const_cast<float *>(y) + (size_t)b0 * 2 * H;
+        p.dy = dy + (size_t)b0 * 2 * H; p.dzr = dzr ? dzr + (size_t)b0 * 2 * GH : nullptr; p.xbuf = zbuf; p.counters = ctr;
+        p.kres = use_cluster ? resident_kblocks(KB, pieces) : 0; p.wpack = wq; p.wrows = 2 * H; p.wk = GH;
+        p.kb_keep = keep_kblocks(H, G, pieces, KB);
         p.dbias = use_cluster ? dbias : nullptr; p.db_accum = b0 > 0;
         p.trace = nullptr;
-        p.stagger_ns = getenv("CTCASR_LSTM_STAGGER_NS") ? atoi(getenv("CTCASR_LSTM_STAGGER_NS")) : 11000;
-        p.nprod = 3; p.skip = 0;
+        p.stagger_ns = stagger;
         ProfScope prof(PROF_LSTM_BWD, stream);
         if (use_cluster) {
-            CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel, mapW, mapZ, p));
+            CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ckernel, mapW, mapZ, p));
         } else {
             void *args[] = {&mapW, &mapZ, &p};
             CTCASR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)lstm_bwd_kernel, dim3(grid), dim3(NTHREADS), args, B_SMEM, stream));

@@ -74,7 +74,8 @@ extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const fl
     // 2. recurrence
     if (compute != CTCASR_COMPUTE_FP32 && lstm_tc_eligible(T, B, H, cell)) {
         char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
-        return lstm_tc_fwd(seq_len, wh, r.gates, r.cstate, y, T, B, H, use_len, forget_bias, wsb, stream);
+        const int pieces = compute == CTCASR_COMPUTE_BF16 ? 1 : 2;
+        return lstm_tc_fwd(seq_len, wh, r.gates, r.cstate, y, bias + 2 * GH, T, B, H, cell, pieces, use_len, forget_bias, wsb, stream);
     }
     if (compute != CTCASR_COMPUTE_FP32 && rec_tc_eligible(T, B, H, cell)) {     // one-gate cells: resident-weight kernel
         char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
@@ -142,7 +143,9 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
 
     if (compute != CTCASR_COMPUTE_FP32 && lstm_tc_eligible(T, B, H, cell)) {
         char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
-        rc = lstm_tc_bwd(seq_len, wh, r.gates, r.cstate, dy, dbias, &dbias_done, T, B, H, use_len, wsb, stream);
+        const int pieces = compute == CTCASR_COMPUTE_BF16 ? 1 : 2;
+        rc = lstm_tc_bwd(seq_len, wh, r.gates, r.cstate, y, dy, cell == CTCASR_CELL_GRU ? r.dzr : nullptr, dbias, &dbias_done,
+                         T, B, H, cell, pieces, use_len, wsb, stream);
         if (rc != CTCASR_OK) return rc;
     } else if (compute != CTCASR_COMPUTE_FP32 && rec_tc_eligible(T, B, H, cell)) {
         char *wsb = reinterpret_cast<char *>(ws) + step_ws_bytes(B, H);
@@ -196,7 +199,7 @@ extern "C" int ctcasr_birnn_bwd(const float *x, const int32_t *seq_len, const fl
         rc = colsum(r.gates, T * B, 2 * GH, 2 * GH, dbias, stream);
         if (rc != CTCASR_OK) return rc;
     }
-    if (cell == CTCASR_CELL_GRU)
+    if (cell == CTCASR_CELL_GRU && !dbias_done)
         for (int d = 0; d < 2; ++d) {       // b_rn gradient: column sums of the n block of dzr
             rc = colsum(r.dzr + (size_t)d * GH + 2 * H, T * B, H, 2 * GH, dbias + 2 * GH + d * H, stream);
             if (rc != CTCASR_OK) return rc;

@@ -40,6 +40,7 @@ class CTCModel:
             params = init_params(config, seed=seed)
         self.load_params(params)
         self._saved = None
+        self._pending, self._host_check = None, None
         self._bufs = {}
         self.dropout_seed = int(config.random_seed)
 
@@ -94,11 +95,12 @@ class CTCModel:
         """sequences [B,T,F] float32, seq_length [B] int32 -> (logits [T,B,V], seq_length).
         The returned logits are a view of a buffer that the next inference_fn call reuses."""
         cfg = self.cfg
+        sequences = torch.as_tensor(sequences)
         if sequences.dim() != 3 or sequences.shape[2] != cfg.num_features:
             raise ValueError("sequences must be [batch_size, time, %d]" % cfg.num_features)
         B, T, F = sequences.shape
-        sequences = sequences.to(self.device, torch.float32).contiguous()
-        seq_length = seq_length.to(self.device, torch.int32).contiguous()
+        sequences = torch.as_tensor(sequences).to(self.device, torch.float32).contiguous()
+        seq_length = torch.as_tensor(seq_length).to(self.device, torch.int32).contiguous()
         if seq_length.numel() != B:
             raise ValueError("seq_length must be [batch_size]")
         rate = cfg.dense_dropout_rate if training else 0.0
@@ -139,7 +141,7 @@ class CTCModel:
             reserve = self._buf("rnn_reserve%d" % l, (rb,), torch.uint8)
             y = self._buf("rnn_y%d" % l, (T, B, 2 * H))
             ops.birnn_fwd(h.view(T, B, nin), seq_length, self.p["rnn/l%d/wx" % l], self.p["rnn/l%d/wh" % l],
-                          self.p["rnn/l%d/bias" % l], y, reserve, cell, use_len, cfg.lstm_forget_bias, self.compute)
+                          self.p["rnn/l%d/bias" % l], y, reserve, cell, use_len, cfg.forget_bias, self.compute)
             saved["rnn"].append((h, y, reserve))
             h = y.view(T * B, 2 * H)
         y4 = ops.dense_fwd(h, self.p["dense4/dense/kernel"], self.p["dense4/dense/bias"], act=1,
@@ -159,8 +161,9 @@ class CTCModel:
         """Accept what the reference passes (an int32 SparseTensor, asr/model.py:71) as a torch
         sparse COO tensor, or (padded [B,Lmax], lengths [B]), or a 0-padded dense [B,Lmax]."""
         if isinstance(labels, (tuple, list)):
-            padded, lengths = labels
+            padded, lengths = (torch.as_tensor(a) for a in labels)      # numpy (the input pipeline) or torch
             return (padded.to(device, torch.int32).contiguous(), lengths.to(device, torch.int32).contiguous())
+        labels = torch.as_tensor(labels)
         if labels.is_sparse:
             labels = labels.coalesce()
             idx, val = labels.indices(), labels.values()
@@ -174,28 +177,35 @@ class CTCModel:
         lengths = (padded != _labels.PAD_ID).sum(1).to(torch.int32)   # dense_to_sparse(eos_token=0)
         return padded, lengths.contiguous()
 
-    def loss_fn(self, logits, seq_length, labels, global_batch=None):
+    def loss_fn(self, logits, seq_length, labels, global_batch=None, defer_check=False):
         """Mean CTC loss over the batch (asr/model.py:259-267).  Also leaves d loss / d logits in
         the model for `backward()`.  `global_batch` (data parallel): number of utterances the mean
-        runs over across all ranks; defaults to this batch."""
+        runs over across all ranks; defaults to this batch.  defer_check: do not read the per-utterance
+        status words back here (no host synchronisation); `train_step` checks them with the loss."""
         padded, lengths = self._labels_to_padded(labels, self.device)
         T, B, V = logits.shape
-        seq_length = seq_length.to(self.device, torch.int32).contiguous()
+        seq_length = torch.as_tensor(seq_length).to(self.device, torch.int32).contiguous()
         gb = B if global_batch is None else global_batch
         per_utt, dlogits, status = ops.ctc_loss(logits, padded, lengths, seq_length, blank=self.cfg.blank,
                                                 grad=True, grad_scale=1.0 / gb,
                                                 out_grad=self._buf("dlogits", (T, B, V)))
-        bad = int((status != 0).sum().item())            # the reference's op raises InvalidArgumentError
-        if bad:
-            st = status.cpu().tolist()
-            raise ValueError("ctc_loss: %d utterance(s) rejected, status per utterance %s "
-                             "(1: not enough time for target transition sequence, 2: label out of range, "
-                             "3: sequence_length > max_time)" % (bad, st))
+        self.last_status = status
+        if not defer_check:
+            self._raise_on_status(status)                # the reference's op raises InvalidArgumentError
         if self._saved is not None and self._saved.get("logits") is not None \
                 and self._saved["logits"].data_ptr() == logits.data_ptr():
             self._saved["dlogits"] = dlogits
         self.last_per_utterance_loss = per_utt
         return per_utt.sum() / gb if global_batch is not None else per_utt.mean()
+
+    @staticmethod
+    def _raise_on_status(status):
+        st = status.cpu().tolist()
+        bad = sum(1 for v in st if v != 0)
+        if bad:
+            raise ValueError("ctc_loss: %d utterance(s) rejected, status per utterance %s "
+                             "(1: not enough time for target transition sequence, 2: label out of range, "
+                             "3: sequence_length > max_time)" % (bad, st))
 
     # ---- asr/model.py:271-309 ------------------------------------------------------------------
     def decode_fn(self, logits, seq_len, originals=None, decoder=None):
@@ -278,13 +288,34 @@ class CTCModel:
                  cfg.adam_beta1, cfg.adam_beta2, cfg.adam_epsilon, grad_scale)
 
     def train_step(self, sequences, seq_length, labels, global_batch=None, allreduce=None):
-        """model_fn's TRAIN branch (asr/model.py:53-54, 74, 79-83) on one batch."""
+        """model_fn's TRAIN branch (asr/model.py:53-54, 74, 79-83) on one batch.  Returns the loss as a 0-d device
+        tensor.  Nothing in the step waits for the GPU: the checks the reference makes on its values (CTCLoss's
+        InvalidArgumentError, NanTensorHook(loss) at asr/model.py:368) are made on the previous step's results when the
+        next step starts, or by `check_step()`."""
+        self.check_step()
         logits, seq_length = self.inference_fn(sequences, seq_length, training=True)
-        loss = self.loss_fn(logits, seq_length, labels, global_batch=global_batch)
+        loss = self.loss_fn(logits, seq_length, labels, global_batch=global_batch, defer_check=True)
         self.backward()
         if allreduce is not None:
             allreduce(self.grad_flat)
         self.apply_gradients()
-        if not math.isfinite(float(loss)):                 # NanTensorHook(loss), asr/model.py:368
-            raise FloatingPointError("Model diverged with loss = NaN/Inf")
+        # loss + "any utterance rejected" travel to a pinned host slot behind the step's kernels
+        if self._host_check is None:
+            self._host_check = torch.empty(2, dtype=torch.float32).pin_memory()
+        dev = torch.stack([loss.reshape(()), (self.last_status != 0).any().to(torch.float32)])
+        self._host_check.copy_(dev, non_blocking=True)
+        self._pending = (torch.cuda.Event(), self.last_status)
+        self._pending[0].record()
         return loss
+
+    def check_step(self):
+        """Raise what the reference raises for the last `train_step` (waits for that step to finish)."""
+        if self._pending is None:
+            return
+        ev, status = self._pending
+        self._pending = None
+        ev.synchronize()
+        if self._host_check[1] != 0:
+            self._raise_on_status(status)
+        if not math.isfinite(float(self._host_check[0])):  # NanTensorHook(loss), asr/model.py:368
+            raise FloatingPointError("Model diverged with loss = NaN/Inf")

@@ -30,7 +30,7 @@ CELL_ID = {"rnn_tanh": 0, "rnn_relu": 1, "lstm": 2, "gru": 3}   # ctcasr.h CTCAS
 @dataclass(frozen=True)
 class ModelConfig:
     # --- names and defaults of asr/params.py -------------------------------------------------
-    used_model: str = "ds1"             # :31  'ds1' dense front-end | 'ds2' conv front-end (reference default)
+    used_model: str = "ds2"             # :31  'ds1' dense front-end | 'ds2' conv front-end
     num_units_dense: int = 2048         # :35
     relu_cutoff: float = 20.0           # :37
     conv_filters: tuple = (32, 32, 96)  # :40
@@ -43,7 +43,8 @@ class ModelConfig:
     adam_beta2: float = 0.999           # :79
     adam_epsilon: float = 1e-8          # :81
     beam_width: int = 1024              # :85
-    rnn_dropout_rate: float = 0.0       # :91
+    conv_dropout_rate: float = 0.0      # :89  (only 0.0 is implemented, see __post_init__)
+    rnn_dropout_rate: float = 0.0       # :91  (only 0.0 is implemented)
     dense_dropout_rate: float = 0.1     # :93
     num_buckets: int = 96               # :97
     num_classes: int = _labels.num_classes()    # :100  (29, blank = 28)
@@ -52,7 +53,9 @@ class ModelConfig:
     # --- knobs the reference hard-codes ------------------------------------------------------
     num_layers_dense: int = 3           # asr/util/tf_contrib.py:35 (num_layers=3)
     num_features: int = NUM_FEATURES
-    lstm_forget_bias: float = 1.0       # tf.nn.rnn_cell.LSTMCell default
+    # forget-gate bias of the TF path's LSTMCell (tf.nn.rnn_cell.LSTMCell default 1.0).  Applies to cudnn=False
+    # only: CudnnLSTM (asr/model.py:194-216, the reference's only LSTM) adds none, see `forget_bias`.
+    lstm_forget_bias: float = 1.0
     # --- B200 execution choices (not in the reference) ---------------------------------------
     # 'fp32'  : SIMT FFMA kernels everywhere (exact-order fp32)
     # 'bf16x3': tcgen05 kind::f16 on bf16-split operands, 3 (6 for ReLU-kinked layers) products
@@ -77,11 +80,22 @@ class ModelConfig:
                 raise ValueError("conv_filters[-1] must be a multiple of 8 and >= 64")
         if self.rnn_cell not in RNN_CELLS:
             raise ValueError("rnn_cell must be one of {}".format(RNN_CELLS))
+        # asr/util/tf_contrib.py:135,190-194 / asr/params.py:89-91: the reference's defaults are 0.0 and only that is
+        # implemented; a silent no-op would train a different model from the reference
+        if self.rnn_dropout_rate != 0.0 or self.conv_dropout_rate != 0.0:
+            raise NotImplementedError("rnn_dropout_rate / conv_dropout_rate other than 0.0 (the reference's defaults) "
+                                      "are not implemented")
         if self.compute not in ("fp32", "tf32", "bf16x3", "bf16"):
             raise ValueError("compute must be 'fp32', 'bf16x3', 'tf32' or 'bf16'")
 
     def replace(self, **kw):
         return dataclasses.replace(self, **kw)
+
+    @property
+    def forget_bias(self):
+        """What is added to the forget-gate pre-activation: TF LSTMCell's forget_bias on the TF path (cudnn=False),
+        nothing on the cuDNN path (cuDNN's LSTM has no such term; its biases are plain parameters)."""
+        return 0.0 if self.cudnn else self.lstm_forget_bias
 
     @property
     def num_gates(self):

@@ -57,7 +57,7 @@ def forward(cfg, params, sequences, seq_length, training=False, seed=0, dtype=np
         wx, wh, bias = (params["rnn/l%d/%s" % (l, k)].astype(dtype) for k in ("wx", "wh", "bias"))
         xin = h.reshape(T, B, -1)
         y, gates, cst = ref.birnn_fwd(xin, seq_length, wx, wh, bias, cell, use_len=use_len,
-                                      forget_bias=cfg.lstm_forget_bias)
+                                      forget_bias=cfg.forget_bias)
         cache["rnn"].append((xin, y, gates, cst))
         h = y.reshape(T * B, -1)
     w, b = params["dense4/dense/kernel"].astype(dtype), params["dense4/dense/bias"].astype(dtype)

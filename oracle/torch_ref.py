@@ -57,7 +57,7 @@ def _dynamic_rnn(cfg, x, lengths, kernel, bias):
             pass
         elif cfg.rnn_cell == "lstm":
             i, j, f, o = z.split(H, 1)                    # TF LSTMCell gate order
-            c_new = torch.sigmoid(f + cfg.lstm_forget_bias) * c + torch.sigmoid(i) * torch.tanh(j)
+            c_new = torch.sigmoid(f + cfg.forget_bias) * c + torch.sigmoid(i) * torch.tanh(j)
             h_new = torch.sigmoid(o) * torch.tanh(c_new)
         else:
             h_new = torch.tanh(z) if cfg.rnn_cell == "rnn_tanh" else torch.relu(z)

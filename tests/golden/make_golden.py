@@ -25,9 +25,9 @@ from ctc_asr_b200.params import ModelConfig                      # noqa: E402
 from oracle import features_ref, ref, torch_ref                  # noqa: E402
 
 CASES = {
-    "cfg1": dict(cfg=dict(num_layers_dense=2, num_units_dense=128, num_layers_rnn=1, num_units_rnn=128, rnn_cell="rnn_tanh",
+    "cfg1": dict(cfg=dict(used_model="ds1", num_layers_dense=2, num_units_dense=128, num_layers_rnn=1, num_units_rnn=128, rnn_cell="rnn_tanh",
                           cudnn=False, dense_dropout_rate=0.0), B=1, T=99, L=16),
-    "lstm": dict(cfg=dict(num_layers_dense=3, num_units_dense=64, num_layers_rnn=2, num_units_rnn=32, rnn_cell="lstm",
+    "lstm": dict(cfg=dict(used_model="ds1", num_layers_dense=3, num_units_dense=64, num_layers_rnn=2, num_units_rnn=32, rnn_cell="lstm",
                           cudnn=False, dense_dropout_rate=0.0), B=4, T=60, L=8),
     "ds2": dict(cfg=dict(used_model="ds2", conv_filters=(8, 8, 64), num_units_dense=64, num_layers_rnn=1, num_units_rnn=32,
                          rnn_cell="lstm", num_features=20, cudnn=False, dense_dropout_rate=0.0), B=3, T=41, L=5),

@@ -73,7 +73,7 @@ def test_decode_fn_uses_the_reference_decoder_at_full_size():
     assert torch.equal(n, gn)
     for b in range(B):
         assert torch.equal(ids[b, :n[b]], gi[b, :gn[b]])
-    cfg = ModelConfig(num_layers_rnn=1, num_units_rnn=64, num_units_dense=64, compute="fp32")
+    cfg = ModelConfig(used_model="ds1", num_layers_rnn=1, num_units_rnn=64, num_units_dense=64, compute="fp32")
     model = CTCModel(cfg, seed=1)
     decoded, plaintext, summary = model.decode_fn(logits, seq, originals=["x"] * B)
     assert len(decoded) == B and all(torch.equal(decoded[b], ids[b, :n[b]].cpu()) for b in range(B))

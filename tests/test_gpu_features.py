@@ -82,7 +82,7 @@ def test_features_feed_the_model_at_cfg2_size():
     assert tuple(seq.shape) == (32, 999, 80) and int(frames.min()) == 999
     assert bool(torch.isfinite(seq).all())
     assert float(seq.mean(1).abs().max()) < 1e-3 and float((seq.std(1, unbiased=False) - 1).abs().max()) < 1e-3
-    cfg = ModelConfig(num_layers_dense=3, num_units_dense=128, num_layers_rnn=1, num_units_rnn=64, rnn_cell="lstm",
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=3, num_units_dense=128, num_layers_rnn=1, num_units_rnn=64, rnn_cell="lstm",
                       cudnn=False, compute="fp32")
     model = CTCModel(cfg, seed=1)
     logits, sl = model.inference_fn(seq, frames, training=False)

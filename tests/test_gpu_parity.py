@@ -314,7 +314,7 @@ def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL, ltol=RTOL):
 
 def test_cfg1_ds1_tanh_single_utterance():
     """BASELINE cfg1: 2 dense + 1 BiRNN-128 (tanh), one 1 s utterance (99 frames), 80 mel bins."""
-    cfg = ModelConfig(num_layers_dense=2, num_units_dense=128, num_layers_rnn=1, num_units_rnn=128,
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=2, num_units_dense=128, num_layers_rnn=1, num_units_rnn=128,
                       rnn_cell="rnn_tanh", cudnn=False, dense_dropout_rate=0.0, compute="fp32")
     _whole_path(cfg, B=1, T=99, L=16, ragged=False)
 
@@ -322,7 +322,7 @@ def test_cfg1_ds1_tanh_single_utterance():
 @pytest.mark.parametrize("cudnn", [False, True])
 def test_small_3d2r2d_lstm_ragged(cudnn):
     """The cfg2 layout (3 dense + 2 BiLSTM + 2 dense) at a size the oracle finishes in seconds."""
-    cfg = ModelConfig(num_layers_dense=3, num_units_dense=64, num_layers_rnn=2, num_units_rnn=32,
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=3, num_units_dense=64, num_layers_rnn=2, num_units_rnn=32,
                       rnn_cell="lstm", cudnn=cudnn, dense_dropout_rate=0.0, compute="fp32")
     _whole_path(cfg, B=4, T=60, L=8, ragged=True)
 
@@ -330,14 +330,14 @@ def test_small_3d2r2d_lstm_ragged(cudnn):
 @pytest.mark.parametrize("cell", ["gru", "rnn_relu"])
 def test_whole_path_other_cells(cell):
     """The rest of the reference's rnn_cell menu (asr/params.py:48-50): GRU and the default ReLU RNN."""
-    cfg = ModelConfig(num_layers_dense=2, num_units_dense=64, num_layers_rnn=2, num_units_rnn=24,
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=2, num_units_dense=64, num_layers_rnn=2, num_units_rnn=24,
                       rnn_cell=cell, cudnn=True, dense_dropout_rate=0.0, compute="fp32")
     _whole_path(cfg, B=3, T=30, L=5, ragged=False)
 
 
 def test_train_step_decreases_loss_and_matches_oracle_adam():
     from ctc_asr_b200.model import CTCModel
-    cfg = ModelConfig(num_layers_dense=2, num_units_dense=48, num_layers_rnn=1, num_units_rnn=24,
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=2, num_units_dense=48, num_layers_rnn=1, num_units_rnn=24,
                       rnn_cell="lstm", cudnn=False, dense_dropout_rate=0.0, learning_rate=1e-3, compute="fp32")
     params = synthetic.init_params(cfg, seed=1)
     x, sl, lab, ll = synthetic.fixed_batch(3, 40, 6, seed=3)
@@ -415,7 +415,7 @@ def test_dense_tcgen05_epilogues_vs_oracle(rate):
 
 def test_whole_path_tf32_lstm():
     """3d2r2d LSTM at a size where every GEMM but the logits layer runs on tcgen05 (tf32)."""
-    cfg = ModelConfig(num_layers_dense=3, num_units_dense=256, num_layers_rnn=2, num_units_rnn=64,
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=3, num_units_dense=256, num_layers_rnn=2, num_units_rnn=64,
                       rnn_cell="lstm", cudnn=False, dense_dropout_rate=0.0, compute="tf32")
     # TF32 operands carry 2^-11 relative rounding noise per GEMM input (measured 3e-4 of max per
     # GEMM output); seven chained GEMMs plus the CTC posterior's sensitivity to the logits put the
@@ -430,7 +430,7 @@ def test_whole_path_bf16_cfg3_arithmetic():
     master weights, fp32 CTC, bf16x3 recurrence.  This is reduced precision by construction: the tolerance
     written here is bf16's (2^-9 operand rounding per GEMM input, mask flips in the dense stack), not the
     1e-3 bar, which compute='bf16x3' and 'fp32' meet."""
-    cfg = ModelConfig(num_layers_dense=3, num_units_dense=256, num_layers_rnn=2, num_units_rnn=64,
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=3, num_units_dense=256, num_layers_rnn=2, num_units_rnn=64,
                       rnn_cell="lstm", cudnn=False, dense_dropout_rate=0.0, compute="bf16")
     _whole_path(cfg, B=8, T=64, L=10, ragged=True, gtol=2e-1, ltol=2e-2)     # measured: 1.2e-1 (first dense kernel), 4e-3 (RNN)
 
@@ -493,7 +493,7 @@ def test_dense_bf16x3_vs_oracle(rate):
 @pytest.mark.parametrize("cudnn", [False, True])
 def test_whole_path_bf16x3_lstm(cudnn):
     """The benchmarked arithmetic (bf16x3 on tcgen05) meets the same 1e-3 bar as the fp32 SIMT path."""
-    cfg = ModelConfig(num_layers_dense=3, num_units_dense=256, num_layers_rnn=2, num_units_rnn=64,
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=3, num_units_dense=256, num_layers_rnn=2, num_units_rnn=64,
                       rnn_cell="lstm", cudnn=cudnn, dense_dropout_rate=0.0, compute="bf16x3")
     _whole_path(cfg, B=8, T=64, L=10, ragged=True)
 
@@ -529,7 +529,7 @@ def test_lstm_persistent_tcgen05_layer_vs_oracle(use_len, T, B, nin, H):
 @pytest.fixture(scope="module")
 def cfg2_model():
     from ctc_asr_b200.model import CTCModel
-    cfg = ModelConfig(num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_units_rnn=2048,
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_units_rnn=2048,
                       rnn_cell="lstm", cudnn=False, dense_dropout_rate=0.0, compute="bf16x3")
     model = CTCModel(cfg, seed=1)
     x, sl, lab, ll = synthetic.fixed_batch(32, 1000, 160, seed=0)

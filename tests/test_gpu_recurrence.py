@@ -73,3 +73,21 @@ def test_full_width_layer_vs_oracle(cell):
     """One H = 2048 layer per cell (the benchmarked width: 128 CTAs, every k-block path, L2 policies)
     against the fp64 oracle."""
     _layer(cell, T=6, B=32, nin=64, H=2048, use_len=True, seed=5)
+
+
+@pytest.mark.parametrize("use_len", [True, False])
+@pytest.mark.parametrize("T,B,nin,H", [(23, 5, 24, 256), (12, 32, 64, 512), (9, 40, 32, 256)])
+def test_gru_persistent_layer_vs_oracle(use_len, T, B, nin, H):
+    """GRU (cuDNN formulation, asr/model.py:197) on the persistent kernels of lstm_tc.cu: forward with 3 gate
+    groups per CTA tile, backward with the 4-CTA clusters splitting K = 3H."""
+    fl, bl = _layer("gru", T, B, nin, H, use_len, seed=T * 13 + B)
+    assert fl < 14 + 2 * ((B + 31) // 32) and bl < 48, (fl, bl)
+
+
+@pytest.mark.parametrize("cell,T,B,nin,H", [("lstm", 40, 32, 64, 128), ("lstm", 19, 70, 32, 256), ("lstm", 7, 3, 16, 192),
+                                            ("gru", 12, 32, 64, 256), ("lstm", 6, 32, 64, 2048)])
+def test_single_piece_bf16_recurrence(cell, T, B, nin, H):
+    """compute = 'bf16' (BASELINE cfg3): operands rounded to bf16, ONE product per k-step, most of the weight
+    slice resident in tensor memory.  Against the exact oracle the difference is the bf16 operand rounding
+    (2^-9 per operand); the bf16-rounded-operand oracle comparison at 1e-3 is in test_gpu_bf16_oracle.py."""
+    _layer(cell, T, B, nin, H, True, seed=T + B, compute=_lib.COMPUTE_BF16, tol=5e-2, ytol=2e-2)

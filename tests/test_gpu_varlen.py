@@ -24,7 +24,7 @@ def _bucketed(n_utts, batch_size, which):
 def test_cfg4_bucketed_batch_vs_oracle(compute, which):
     """One batch of 64 from the shortest / the longest bucket, small layers (oracle speed): loss, every
     gradient tensor and the greedy transcripts.  Frames past each utterance's length must not matter."""
-    cfg = ModelConfig(num_layers_dense=3, num_units_dense=64, num_layers_rnn=2, num_units_rnn=64, rnn_cell="lstm",
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=3, num_units_dense=64, num_layers_rnn=2, num_units_rnn=64, rnn_cell="lstm",
                       cudnn=False, dense_dropout_rate=0.0, compute=compute)
     x, sl, lab, ll = _bucketed(6144, 64, which)
     assert x.shape[0] == 64 and sl.min() < sl.max() and x.shape[1] == sl.max()
@@ -60,7 +60,7 @@ def test_cfg4_bucketed_batch_vs_oracle(compute, which):
 def test_cfg4_full_size_longest_bucket():
     """B=64 x up to 17 s on the cfg2 layers (two 32-row slices per LSTM launch): the step runs, finite,
     deterministic; per-utterance losses equal those of the same utterances in a batch of 32."""
-    cfg = ModelConfig(num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_units_rnn=2048, rnn_cell="lstm",
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=3, num_units_dense=2048, num_layers_rnn=2, num_units_rnn=2048, rnn_cell="lstm",
                       cudnn=False, dense_dropout_rate=0.0, compute="bf16x3")
     model = CTCModel(cfg, seed=1)
     x, sl, lab, ll = _bucketed(6144, 64, -1)

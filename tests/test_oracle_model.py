@@ -15,7 +15,7 @@ from oracle import model_ref, ref, torch_ref
 
 
 def _small_cfg(cell, cudnn, layers=2):
-    return ModelConfig(num_units_dense=24, num_units_rnn=16, num_layers_rnn=layers, rnn_cell=cell,
+    return ModelConfig(used_model="ds1", num_units_dense=24, num_units_rnn=16, num_layers_rnn=layers, rnn_cell=cell,
                        num_layers_dense=2, num_features=10, cudnn=cudnn, dense_dropout_rate=0.0)
 
 

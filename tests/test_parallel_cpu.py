@@ -14,7 +14,7 @@ from ctc_asr_b200 import parallel, synthetic
 from ctc_asr_b200.params import ModelConfig, param_offsets
 from oracle import model_ref
 
-CFG = ModelConfig(num_layers_dense=2, num_units_dense=16, num_layers_rnn=1, num_units_rnn=8, rnn_cell="lstm",
+CFG = ModelConfig(used_model="ds1", num_layers_dense=2, num_units_dense=16, num_layers_rnn=1, num_units_rnn=8, rnn_cell="lstm",
                   cudnn=False, dense_dropout_rate=0.0, num_features=6)
 
 
