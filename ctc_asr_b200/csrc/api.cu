@@ -54,9 +54,9 @@ extern "C" int ctcasr_abi_version(void) { return CTCASR_ABI_VERSION; }
 extern "C" const char *ctcasr_last_error(void) { return g_last_error; }
 extern "C" uint64_t ctcasr_launch_count(void) { return g_launch_count.load(); }
 
-namespace ctcasr { void lstm_tc_set_trace(unsigned long long *buf); }
+namespace ctcasr { void lstm_tc_set_trace(unsigned long long *buf); void rec_tc_set_trace(unsigned long long *buf); }
 // debugging aid (not in ctcasr.h): device buffer [grid][64][8] of globaltimer stamps written by the LSTM forward kernel
-extern "C" int ctcasr_debug_lstm_trace(void *buf) { ctcasr::lstm_tc_set_trace(reinterpret_cast<unsigned long long *>(buf)); return 0; }
+extern "C" int ctcasr_debug_lstm_trace(void *buf) { ctcasr::lstm_tc_set_trace(reinterpret_cast<unsigned long long *>(buf)); ctcasr::rec_tc_set_trace(reinterpret_cast<unsigned long long *>(buf)); return 0; }
 
 extern "C" int ctcasr_profile_enable(int on)
 {

@@ -53,8 +53,16 @@ template <int PIECES> struct Ring {
     static constexpr int ACC_COLS = 2 * PIECES * NB;                         // two issuers x (PIECES x 32) accumulator columns
     static constexpr int KRES_MAX = (512 - ACC_COLS) / (PIECES * 32);        // weight k-blocks resident in tensor memory: 6 / 14
     static constexpr int XCH = 4 * NB * UPC * 4;                             // gate exchange [4][32 b][32 u] fp32
-    static constexpr int SMEM = NSTAGE * STAGE + XCH + 1024 + 256;
+    static constexpr int BARS = 1024;
+    static constexpr int SMEM = NSTAGE * STAGE + XCH + 1024 + BARS;
 };
+// PIECES = 1 runs two rings: NSA stages of streamed weight tiles (16 KB each; the k-blocks resident in tensor memory
+// never enter it, so the producer prefetches a whole ring of the next step's tiles during the serial tail of this
+// one) and NSB stages of state tiles (4 KB).  A step visits the streamed k-blocks first, then the resident ones.
+// (One shared ring, or all state tiles in one burst with a 5-stage weight ring, kept too few bytes in flight: the step
+// was bound by TMA latency per ring turn, 7.2 of 12.6 us at H = 2048.)
+constexpr int NSA = 10, NSB = 12;
+constexpr int SPLIT_SMEM = NSA * F_A_PIECE + NSB * F_B_PIECE + Ring<1>::XCH + 1024 + Ring<1>::BARS;
 // The two MMA issuers take alternate k-blocks.  Each owns a private sub-ring of stages (issuer 0 the first
 // ceil(n/2) stages, issuer 1 the rest) so that every full/empty barrier has its phases consumed by ONE thread in
 // order.  With a shared ring of odd depth the successive fills of a stage alternate between the issuers,
@@ -131,19 +139,24 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
 {
     using R = Ring<PIECES>;
     constexpr int G = CELL == CELL_G ? 3 : 4;
-    constexpr int NSTAGE = R::NSTAGE, STAGE = R::STAGE;
+    constexpr bool FULLB = PIECES == 1;
+    constexpr int STAGE = R::STAGE;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-    const uint32_t xch_base = smem_base + NSTAGE * STAGE;
-    float *zs = reinterpret_cast<float *>(smem_gen + NSTAGE * STAGE);        // [4][32 b][32 u]
+    constexpr int NSTAGE = FULLB ? NSA : R::NSTAGE;
+    const uint32_t bbuf = smem_base + (uint32_t)NSA * F_A_PIECE;                    // FULLB: ring of state tiles
+    const uint32_t xch_base = FULLB ? bbuf + (uint32_t)NSB * F_B_PIECE : smem_base + NSTAGE * STAGE;
+    float *zs = reinterpret_cast<float *>(smem_gen + (xch_base - smem_base));        // [4][32 b][32 u]
     const uint32_t bar_base = xch_base + R::XCH;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
-    auto empty = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
-    const uint32_t tfull = bar_base + 8u * (2 * NSTAGE), tempty = tfull + 8;
+    auto empty = [&](int s) { return bar_base + 8u * (10 + s); };
+    auto fullB = [&](int s) { return bar_base + 8u * (20 + s); };                  // FULLB only: state-tile ring
+    auto emptyB = [&](int s) { return bar_base + 8u * (32 + s); };
+    const uint32_t tfull = bar_base + 8u * 44, tempty = tfull + 8;
     const uint32_t tmem_slot = tempty + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
-    auto a_addr = [&](int s, int pc) { return smem_base + s * STAGE + pc * F_A_PIECE; };
+    auto a_addr = [&](int s, int pc) { return FULLB ? smem_base + s * F_A_PIECE : smem_base + s * STAGE + pc * F_A_PIECE; };
     auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * F_B_PIECE; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,7 +164,8 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     const int T = p.T, B = p.B, H = p.H, KB = H / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), FULLB ? 1 : 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
+        if (FULLB) for (int s = 0; s < NSB; ++s) { ptx::mbar_init(fullB(s), 1); ptx::mbar_init(emptyB(s), 1); }
         ptx::mbar_init(tfull, 2); ptx::mbar_init(tempty, 4);
         ptx::mbar_fence_init();
     }
@@ -190,8 +204,10 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             const int row0 = (d * p.CPD + c) * 128;
             const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int i = 0; i < T; ++i)
-                for (int kb = 0; kb < KB; ++kb) {
-                    SubRing &r = ring[kb & 1];
+                for (int m = 0; m < KB; ++m) {
+                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;      // FULLB: streamed k-blocks first
+                    if (FULLB && kb < p.kres) continue;             // resident in tensor memory: no ring traffic at all
+                    SubRing &r = ring[m & 1];
                     const int stage = r.slot();
                     ptx::mbar_wait(empty(stage), r.phase ^ 1);
                     if (kb < p.kres) {
@@ -202,26 +218,39 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage), pol);   // all pieces in one box
                     }
                     r.advance();
-                    if (kb == KB - 1) stamp(p, i, 6);
+                    if (m == KB - 1 || (FULLB && m == KB - p.kres - 1)) stamp(p, i, 6);
                 }
         }
     } else if (warp == 5) {
         // ---- h_{t-1} tiles: gated by the step barrier of this direction ------------------------
         if (lane == 0) {
             SubRing ring[2] = {SubRing(0, NSTAGE), SubRing(1, NSTAGE)};
+            SubRing ringB[2] = {SubRing(0, NSB), SubRing(1, NSB)};
             if (d == 1) stagger_wait(p.stagger_ns);
             for (int i = 0; i < T; ++i) {
                 wait_counter(p.counters + d, (unsigned)(p.CPD * i), p.counters + 2);
                 ptx::fence_proxy_async();
                 stamp(p, i, 0);
                 const int row0 = (d * 2 + (i & 1)) * NB;
-                for (int kb = 0; kb < KB; ++kb) {
-                    SubRing &r = ring[kb & 1];
-                    const int stage = r.slot();
-                    ptx::mbar_wait(empty(stage), r.phase ^ 1);
-                    ptx::mbar_expect_tx(fullA(stage), PIECES * F_B_PIECE);
-                    ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullA(stage));   // all pieces in one box
-                    r.advance();
+                if (FULLB) {        // own ring of 4-KB tiles, in the step's visiting order
+                    for (int m = 0; m < KB; ++m) {
+                        const int kb = m < KB - p.kres ? p.kres + m : m - (KB - p.kres);
+                        SubRing &r = ringB[m & 1];
+                        const int stage = r.slot();
+                        ptx::mbar_wait(emptyB(stage), r.phase ^ 1);
+                        ptx::mbar_expect_tx(fullB(stage), F_B_PIECE);
+                        ptx::tma_load_3d(bbuf + (uint32_t)stage * F_B_PIECE, &mapH, kb * BK, row0, 0, fullB(stage));
+                        r.advance();
+                    }
+                } else {
+                    for (int kb = 0; kb < KB; ++kb) {
+                        SubRing &r = ring[kb & 1];
+                        const int stage = r.slot();
+                        ptx::mbar_wait(empty(stage), r.phase ^ 1);
+                        ptx::mbar_expect_tx(fullA(stage), PIECES * F_B_PIECE);
+                        ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullA(stage));   // all pieces in one box
+                        r.advance();
+                    }
                 }
                 stamp(p, i, 1);
             }
@@ -235,16 +264,19 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
             const uint32_t acc = tmem_d + (uint32_t)(me * PIECES * NB);
             uint32_t tphase = 0;
-            SubRing ring(me, NSTAGE);
+            SubRing ring(me, NSTAGE), ringB(me, NSB);
             for (int i = 0; i < T; ++i) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
-                for (int kb = me; kb < KB; kb += 2) {
-                    const int stage = ring.slot();
-                    const int first = kb == me;
-                    ptx::mbar_wait(fullA(stage), ring.phase);
+                for (int m = me; m < KB; m += 2) {
+                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;
+                    const int stage = ring.slot(), stageB = ringB.slot();
+                    const int first = m == me;
+                    const bool ringed = !FULLB || kb >= p.kres;             // this k-block's weights go through the ring
+                    if (FULLB) ptx::mbar_wait(fullB(stageB), ringB.phase);
+                    if (ringed) ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
-                    const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
+                    const uint64_t bd = ptx::make_smem_desc(FULLB ? bbuf + (uint32_t)stageB * F_B_PIECE : b_addr(stage, 0), 16, 1024, 2);
                     if (PIECES == 2) {
                         // bf16x3 with 2 MMAs per k-step: the two pieces of h are consecutive rows of one K-major tile,
                         // so  A_hi x [B_hi; B_lo]  is ONE N = 64 MMA (columns 0-31: hi*hi, 32-63: hi*lo) and
@@ -278,8 +310,8 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                                 ptx::mma_bf16(acc, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
                         }
                     }
-                    ptx::mma_commit(empty(stage));
-                    ring.advance();
+                    if (ringed) { ptx::mma_commit(empty(stage)); ring.advance(); }
+                    if (FULLB) { ptx::mma_commit(emptyB(stageB)); ringB.advance(); }
                 }
                 ptx::mma_commit(tfull);
                 if (me == 0) stamp(p, i, 2);
@@ -621,19 +653,24 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
 {
     using R = Ring<PIECES>;
     constexpr int G = CELL == CELL_G ? 3 : 4;
-    constexpr int NSTAGE = R::NSTAGE, STAGE = R::STAGE;
+    constexpr bool FULLB = PIECES == 1;
+    constexpr int STAGE = R::STAGE;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-    const uint32_t xch_base = smem_base + NSTAGE * STAGE;
-    const float *slots = reinterpret_cast<const float *>(smem_gen + NSTAGE * STAGE);   // [4][32 b][32 u]
+    constexpr int NSTAGE = FULLB ? NSA : R::NSTAGE;
+    const uint32_t bbuf = smem_base + (uint32_t)NSA * F_A_PIECE;                    // FULLB: ring of state tiles
+    const uint32_t xch_base = FULLB ? bbuf + (uint32_t)NSB * F_B_PIECE : smem_base + NSTAGE * STAGE;
+    const float *slots = reinterpret_cast<const float *>(smem_gen + (xch_base - smem_base));   // [4][32 b][32 u]
     const uint32_t bar_base = xch_base + R::XCH;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
-    auto empty = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
-    const uint32_t tfull = bar_base + 8u * (2 * NSTAGE), tempty = tfull + 8, xfull = tempty + 8;
+    auto empty = [&](int s) { return bar_base + 8u * (10 + s); };
+    auto fullB = [&](int s) { return bar_base + 8u * (20 + s); };                  // FULLB only: state-tile ring
+    auto emptyB = [&](int s) { return bar_base + 8u * (32 + s); };
+    const uint32_t tfull = bar_base + 8u * 44, tempty = tfull + 8, xfull = tempty + 8;
     const uint32_t tmem_slot = xfull + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
-    auto a_addr = [&](int s, int pc) { return smem_base + s * STAGE + pc * F_A_PIECE; };
+    auto a_addr = [&](int s, int pc) { return FULLB ? smem_base + s * F_A_PIECE : smem_base + s * STAGE + pc * F_A_PIECE; };
     auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * F_B_PIECE; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -644,7 +681,8 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     const int T = p.T, B = p.B, H = p.H, GH = G * H, KQ = GH / 4, KB = KQ / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), FULLB ? 1 : 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
+        if (FULLB) for (int s = 0; s < NSB; ++s) { ptx::mbar_init(fullB(s), 1); ptx::mbar_init(emptyB(s), 1); }
         ptx::mbar_init(tfull, 2); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
         ptx::mbar_fence_init();
     }
@@ -682,8 +720,10 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
             const int row0 = d * H + ub * 128;
             const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int n = 0; n < T; ++n)
-                for (int kb = 0; kb < KB; ++kb) {
-                    SubRing &r = ring[kb & 1];
+                for (int m = 0; m < KB; ++m) {
+                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;      // FULLB: streamed k-blocks first
+                    if (FULLB && kb < p.kres) continue;             // resident in tensor memory: no ring traffic at all
+                    SubRing &r = ring[m & 1];
                     const int stage = r.slot();
                     ptx::mbar_wait(empty(stage), r.phase ^ 1);
                     if (kb < p.kres) {
@@ -699,18 +739,31 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     } else if (warp == 5) {
         if (lane == 0) {        // dz of the step processed before, my K-quarter of the gate columns, all batch rows
             SubRing ring[2] = {SubRing(0, NSTAGE), SubRing(1, NSTAGE)};
+            SubRing ringB[2] = {SubRing(0, NSB), SubRing(1, NSB)};
             if (d == 1) stagger_wait(p.stagger_ns);
             for (int n = 0; n < T; ++n) {
                 wait_counter(p.counters + d, (unsigned)(p.CPD * n), p.counters + 2);
                 ptx::fence_proxy_async();
                 const int row0 = (d * 2 + (n & 1)) * NB;
-                for (int kb = 0; kb < KB; ++kb) {
-                    SubRing &r = ring[kb & 1];
-                    const int stage = r.slot();
-                    ptx::mbar_wait(empty(stage), r.phase ^ 1);
-                    ptx::mbar_expect_tx(fullA(stage), PIECES * F_B_PIECE);
-                    ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * KQ + kb * BK, row0, 0, fullA(stage));   // all pieces
-                    r.advance();
+                if (FULLB) {        // own ring of 4-KB tiles, in the step's visiting order
+                    for (int m = 0; m < KB; ++m) {
+                        const int kb = m < KB - p.kres ? p.kres + m : m - (KB - p.kres);
+                        SubRing &r = ringB[m & 1];
+                        const int stage = r.slot();
+                        ptx::mbar_wait(emptyB(stage), r.phase ^ 1);
+                        ptx::mbar_expect_tx(fullB(stage), F_B_PIECE);
+                        ptx::tma_load_3d(bbuf + (uint32_t)stage * F_B_PIECE, &mapZ, q * KQ + kb * BK, row0, 0, fullB(stage));
+                        r.advance();
+                    }
+                } else {
+                    for (int kb = 0; kb < KB; ++kb) {
+                        SubRing &r = ring[kb & 1];
+                        const int stage = r.slot();
+                        ptx::mbar_wait(empty(stage), r.phase ^ 1);
+                        ptx::mbar_expect_tx(fullA(stage), PIECES * F_B_PIECE);
+                        ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * KQ + kb * BK, row0, 0, fullA(stage));   // all pieces
+                        r.advance();
+                    }
                 }
             }
         }
@@ -720,16 +773,19 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
             const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
             const uint32_t acc = tmem_d + (uint32_t)(me * PIECES * NB);
             uint32_t tphase = 0;
-            SubRing ring(me, NSTAGE);
+            SubRing ring(me, NSTAGE), ringB(me, NSB);
             for (int n = 0; n < T; ++n) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
-                for (int kb = me; kb < KB; kb += 2) {
-                    const int stage = ring.slot();
-                    const int first = kb == me;
-                    ptx::mbar_wait(fullA(stage), ring.phase);
+                for (int m = me; m < KB; m += 2) {
+                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;
+                    const int stage = ring.slot(), stageB = ringB.slot();
+                    const int first = m == me;
+                    const bool ringed = !FULLB || kb >= p.kres;             // this k-block's weights go through the ring
+                    if (FULLB) ptx::mbar_wait(fullB(stageB), ringB.phase);
+                    if (ringed) ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
-                    const uint64_t bd = ptx::make_smem_desc(b_addr(stage, 0), 16, 1024, 2);
+                    const uint64_t bd = ptx::make_smem_desc(FULLB ? bbuf + (uint32_t)stageB * F_B_PIECE : b_addr(stage, 0), 16, 1024, 2);
                     if (PIECES == 2) {
                         if (kb < p.kres) {
                             const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
@@ -760,8 +816,8 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                                 ptx::mma_bf16(acc, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
                         }
                     }
-                    ptx::mma_commit(empty(stage));
-                    ring.advance();
+                    if (ringed) { ptx::mma_commit(empty(stage)); ring.advance(); }
+                    if (FULLB) { ptx::mma_commit(emptyB(stageB)); ringB.advance(); }
                 }
                 ptx::mma_commit(tfull);
                 tphase ^= 1;
@@ -1066,7 +1122,7 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
     unsigned int *ctr = reinterpret_cast<unsigned int *>(base + L.counters);
     const int G = cell == CELL_G ? 3 : 4;
     const int CPD = H / UPC, grid = 2 * CPD, KB = H / BK;
-    const int smem = pieces == 2 ? Ring<2>::SMEM : Ring<1>::SMEM;
+    const int smem = pieces == 2 ? Ring<2>::SMEM : SPLIT_SMEM;
     KernelFn kernel = fwd_kernel(cell, pieces);
     static int checked_grid[2][2] = {{0, 0}, {0, 0}};
     int &chk = checked_grid[cell == CELL_G][pieces - 1];
@@ -1130,7 +1186,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     KernelFn ckernel = bwd_kernel(cell, pieces);
-    const int csmem = pieces == 2 ? Ring<2>::SMEM : Ring<1>::SMEM;
+    const int csmem = pieces == 2 ? Ring<2>::SMEM : SPLIT_SMEM;
     if (H % 128 == 0 && cluster_bad_grid != grid && (!no_cluster || cell == CELL_G)) {
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = csmem; cfg.stream = stream;
         attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -44,17 +44,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 // Bounded wait: a protocol bug must end in a trapped kernel (an error the host sees), never in a
-// GPU that hangs until the box is reclaimed.
+// GPU that hangs until the box is reclaimed.  The first probe is a bare try_wait + branch: a wait that is already
+// satisfied costs ~90 cycles of the issuing thread this way, against ~215 with the predicate materialised in a
+// register and a spin counter around it (tools/ubench/mma_loop.cu) — it is paid once per k-block by the
+// single MMA-issuing thread of the recurrence kernels, whose MMAs take ~45 cycles each.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
+    uint32_t timed_out = 0;
 #ifdef CTCASR_DEBUG_WAIT
-        if (++spins > (1u << 19)) { printf("ctcasr: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity); __trap(); }
+    const uint32_t limit = 1u << 19;
 #else
-        if (++spins > (1u << 24)) { printf("ctcasr: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    const uint32_t limit = 1u << 24;
 #endif
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "MBAR_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "@p bra MBAR_WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, %3;\n\t"
+        "@p bra MBAR_WAIT_LOOP;\n\t"
+        "mov.u32 %0, 1;\n\t"
+        "MBAR_WAIT_DONE:\n\t}"
+        : "+r"(timed_out) : "r"(bar), "r"(parity), "r"(limit) : "memory");
+    if (timed_out) { printf("ctcasr: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity); __trap(); }
 }
 
 // ---- thread-block clusters / distributed shared memory ----------------------------------------------

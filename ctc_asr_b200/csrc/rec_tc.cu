@@ -43,7 +43,17 @@ struct Params {
     const __nv_bfloat16 *wpack; // [2 pieces][2H rows][H]
     float *dbias;               // bwd: [2H] column sums of dz, or null
     int db_accum;
+    unsigned long long *trace;  // optional [grid][64 steps][8 slots] globaltimer stamps (tools/lstm_trace.py)
 };
+
+__device__ __forceinline__ void stamp(const Params &p, int step, int slot)
+{
+    if (p.trace && step < 64) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[((size_t)blockIdx.x * 64 + step) * 8 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ void cell_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -79,7 +89,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     const int d = cid / UBD, ub = cid % UBD;
 
     if (threadIdx.x == 0) {
-        for (int kb = 0; kb < NKB; ++kb) ptx::mbar_init(fullB(kb), 1);
+        for (int g = 0; g < (NKB + 3) / 4; ++g) ptx::mbar_init(fullB(g), 1);
         ptx::mbar_init(wres, 1); ptx::mbar_init(bfree, 1);
         ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
         ptx::mbar_fence_init();
@@ -123,12 +133,16 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             for (int n = 0; n < T; ++n) {
                 rec::wait_counter(p.counters + d, (unsigned)(p.CPD * n), p.counters + 2);
                 ptx::fence_proxy_async();
+                stamp(p, n, 0);
                 if (n > 0) ptx::mbar_wait(bfree, (uint32_t)((n - 1) & 1));      // the previous step's MMAs have read the tiles
                 const int row0 = (d * 2 + (n & 1)) * NB;
+                // one barrier per group of 4 k-blocks: a satisfied mbarrier wait costs the MMA-issuing thread as much as
+                // two of its MMAs (tools/ubench/mma_loop.cu)
                 for (int kb = 0; kb < NKB; ++kb) {
-                    ptx::mbar_expect_tx(fullB(kb), B_TILE);
-                    ptx::tma_load_3d(b_base + (uint32_t)kb * B_TILE, &mapX, q * KQ + kb * BK, row0, 0, fullB(kb));   // both pieces
+                    if ((kb & 3) == 0) ptx::mbar_expect_tx(fullB(kb >> 2), (uint32_t)((NKB - kb < 4 ? NKB - kb : 4) * B_TILE));
+                    ptx::tma_load_3d(b_base + (uint32_t)kb * B_TILE, &mapX, q * KQ + kb * BK, row0, 0, fullB(kb >> 2));   // both pieces
                 }
+                stamp(p, n, 1);
             }
         }
     } else if (warp == 6) {
@@ -139,8 +153,10 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                 ptx::mbar_wait(tempty, (uint32_t)((n & 1) ^ 1));
                 ptx::tc_fence_after();
                 for (int kb = 0; kb < NKB; ++kb) {
-                    ptx::mbar_wait(fullB(kb), (uint32_t)(n & 1));
-                    ptx::tc_fence_after();
+                    if ((kb & 3) == 0) {
+                        ptx::mbar_wait(fullB(kb >> 2), (uint32_t)(n & 1));
+                        ptx::tc_fence_after();
+                    }
                     // bf16x3 with 2 MMAs per k-step: the two pieces of x are consecutive rows of one K-major tile, so
                     // A_hi x [x_hi; x_lo] is ONE N = 64 MMA (columns 0-31: hi*hi, 32-63: hi*lo) and A_lo x x_hi
                     // accumulates into columns 0-31; the epilogue adds the column groups.
@@ -164,6 +180,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                 }
                 ptx::mma_commit(bfree);
                 ptx::mma_commit(tfull);
+                stamp(p, n, 2);
             }
         }
     } else if (warp < 4 || warp >= 8) {
@@ -199,6 +216,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             }
             if (reader) {
                 ptx::mbar_wait(tfull, tphase);
+                if (tid == 0) stamp(p, n, 3);
                 ptx::tc_fence_after();
                 uint32_t r[32], r2[32];
                 ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);      // rows = units 32*warp + lane of the block
@@ -212,6 +230,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                 if (lane == 0) { ptx::mbar_arrive(tempty); ptx::mbar_arrive_remote(remote_bar); }
             }
             ptx::mbar_wait_cluster(xfull, tphase);                          // the four partials of my units have landed
+            if (tid == 0) stamp(p, n, 4);
             __nv_bfloat16 *xb = p.xbuf + ((size_t)(d * 2 + ((n + 1) & 1)) * NB) * H + unit;
             float out[4];
 #pragma unroll
@@ -238,10 +257,11 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                 xb[piece + (size_t)b * H] = lo;
             }
             // every writing thread orders its own pieces for the other CTAs' TMA (async proxy) reads (see lstm_tc.cu)
+            if (tid == 0) stamp(p, n, 5);
             __threadfence();
             ptx::fence_proxy_async();
             cell_bar();
-            if (tid == 0) rec::signal_counter(p.counters + d);
+            if (tid == 0) { rec::signal_counter(p.counters + d); stamp(p, n, 6); }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {               // fp32 results for the other passes, after the signal
                 const int b = bg * 4 + j;
@@ -301,6 +321,7 @@ __global__ void split2_kernel(const float *__restrict__ x, __nv_bfloat16 *__rest
     }
 }
 
+static unsigned long long *g_trace = nullptr;
 struct WsLayout { size_t wpack, xbuf, counters, total; };
 static WsLayout ws_layout(int H)
 {
@@ -356,6 +377,7 @@ static int launch(const int *seq_len, const float *wh, float *gates, float *y, c
         p.seq_len = seq_len ? seq_len + b0 : nullptr;
         p.gates = gates + (size_t)b0 * 2 * H; p.y = y ? y + (size_t)b0 * 2 * H : nullptr; p.dy = dy ? dy + (size_t)b0 * 2 * H : nullptr;
         p.xbuf = xbuf; p.counters = ctr; p.wpack = wp; p.dbias = dbias; p.db_accum = b0 > 0;
+        p.trace = FWD ? g_trace : nullptr;
         ProfScope prof(FWD ? PROF_LSTM_FWD : PROF_LSTM_BWD, stream);
         CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, mapW, mapX, p));
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -364,6 +386,8 @@ static int launch(const int *seq_len, const float *wh, float *gates, float *y, c
 }
 
 }  // namespace rnn1
+
+void rec_tc_set_trace(unsigned long long *buf) { rnn1::g_trace = buf; }
 
 bool rec_tc_eligible(int T, int B, int H, int cell)
 {
