@@ -29,6 +29,7 @@ SIGNATURES = {
     "ctcasr_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _u32, _i, _vp]),
     "ctcasr_birnn_reserve_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "ctcasr_birnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "ctcasr_birnn_stream_bytes": (ctypes.c_double, [_i, _i, _i, _i, _i, _i]),
     "ctcasr_birnn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
     "ctcasr_birnn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),

@@ -1104,6 +1104,18 @@ bool lstm_tc_eligible(int T, int B, int H, int cell)
     return false;
 }
 
+// Bytes one launch pulls through TMA from L2 / HBM: the weight tiles that are not resident in tensor memory and the
+// state tiles of every step, over all CTAs (what the L2-streaming bound of bench.py is computed from).
+double lstm_tc_stream_bytes(int T, int H, int cell, int pieces, int backward)
+{
+    using namespace lstm;
+    const int G = cell == CELL_G ? 3 : 4;
+    const int KB = backward ? G * H / 4 / BK : H / BK;
+    const int kres = (backward && H % 128) ? 0 : resident_kblocks(KB, pieces);
+    const double per_step = (double)(KB - kres) * pieces * F_A_PIECE + (double)KB * pieces * F_B_PIECE;
+    return per_step * (2.0 * H / UPC) * T;
+}
+
 size_t lstm_tc_workspace_bytes(int B, int H)
 {
     (void)B;

@@ -6,6 +6,7 @@ namespace ctcasr {
 
 bool lstm_tc_eligible(int T, int B, int H, int cell);           // cell: LSTM or GRU
 size_t lstm_tc_workspace_bytes(int B, int H);
+double lstm_tc_stream_bytes(int T, int H, int cell, int pieces, int backward);
 // gates [T*B, 2*G*H] holds P = x Wx + b on entry and the gate activations on exit;
 // cstate [T*B, 2H] (LSTM: c; GRU: q = h Rn + b_rn); y [T*B, 2H]; bias_rn [2, H] (GRU).
 // pieces: 2 = bf16x3 arithmetic (operands split hi + lo), 1 = plain bf16 operands (compute 'bf16').

@@ -395,6 +395,13 @@ bool rec_tc_eligible(int T, int B, int H, int cell)
            H >= 256 && H % 256 == 0 && H / 256 <= rnn1::MAX_KB && H / 16 <= 148;
 }
 
+// state tiles of every step over all CTAs (the weights are loaded once per launch: 8 H^2 bytes)
+double rec_tc_stream_bytes(int T, int H)
+{
+    const int NKB = H / 4 / rnn1::BK;
+    return ((double)NKB * rnn1::B_TILE * T + (double)NKB * 2 * rnn1::A_PIECE) * (H / 16.0);
+}
+
 size_t rec_tc_workspace_bytes(int H)
 {
     if (H < 256 || H % 256) return 0;

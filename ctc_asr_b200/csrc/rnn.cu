@@ -47,6 +47,15 @@ extern "C" size_t ctcasr_birnn_workspace_bytes(int T, int B, int in, int H, int 
     return step_ws_bytes(B, H) + lstm_tc_workspace_bytes(B, H);
 }
 
+extern "C" double ctcasr_birnn_stream_bytes(int T, int B, int H, int cell, int compute, int backward)
+{
+    const int slices = (B + 31) / 32;
+    if (compute == CTCASR_COMPUTE_FP32) return 0.0;
+    if (lstm_tc_eligible(T, B, H, cell)) return slices * lstm_tc_stream_bytes(T, H, cell, compute == CTCASR_COMPUTE_BF16 ? 1 : 2, backward);
+    if (rec_tc_eligible(T, B, H, cell)) return slices * rec_tc_stream_bytes(T, H);
+    return 0.0;
+}
+
 extern "C" int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const float *wx, const float *wh,
                                 const float *bias, float *y, void *reserve,
                                 int T, int B, int in, int H, int cell, int use_len, float forget_bias,

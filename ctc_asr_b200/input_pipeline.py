@@ -5,8 +5,8 @@ Reference: `input_fn_generator` / `__input_generator` (asr/input_functions.py:22
 `path;label;length` (asr/params.py:151-155; `path` relative to `corpus_dir`, `length` in seconds) and 16 kHz
 mono 16-bit WAV files.  The reference decodes + featurises every file on the host inside a tf.data Python
 generator and lets `bucket_by_sequence_length` form the batches; here the host only reads the PCM and decides
-the batches (the frame count follows from the sample count), and each batch is featurised in one call on the
-GPU (`features.featurize`), so what crosses PCIe is int16 samples.
+the batches (the frame count follows from the sample count in the WAV header, `frames_of_wav`), and each batch is
+featurised in one call on the GPU (`features.featurize`), so what crosses PCIe is int16 samples.
 
 Behaviour kept from the reference:
   * rows = `list(reader)[1:-1]`: the header and the LAST data row are dropped (asr/input_functions.py:134);
@@ -29,7 +29,7 @@ import random
 import numpy as np
 
 from . import labels as _labels
-from .params import WIN_STEP
+from .params import WIN_LENGTH, WIN_STEP
 
 CSV_HEADER_PATH, CSV_HEADER_LABEL, CSV_HEADER_LENGTH = "path", "label", "length"        # asr/params.py:151-153
 CSV_FIELDNAMES = [CSV_HEADER_PATH, CSV_HEADER_LABEL, CSV_HEADER_LENGTH]
@@ -63,6 +63,26 @@ def bucket_of(length, boundaries):
     return bisect.bisect_right(boundaries, length)
 
 
+def num_frames(num_samples, drop_every_second_frame=False, sampling_rate=16000):
+    """Frames python_speech_features makes of `num_samples` samples (25 ms windows, 10 ms steps, asr/params.py:146-147,
+    asr/input_functions.py:273-276): 1 + ceil((n - 400) / 160); halved (rounding up) when every second frame is dropped
+    (asr/input_functions.py:239-241).  Same numbers as ctcasr_feature_frames (tests/test_input_pipeline.py)."""
+    win, step = int(round(WIN_LENGTH * sampling_rate)), int(round(WIN_STEP * sampling_rate))
+    n = 1 if num_samples <= win else 1 + -(-(num_samples - win) // step)
+    return (n + 1) // 2 if drop_every_second_frame else n
+
+
+def frames_of_wav(corpus_dir, drop_every_second_frame=False):
+    """row -> spectrogram_length of the row's clip, from the WAV header alone (no decoding): what the reference's
+    bucket_by_sequence_length keys on (element_length_func = spectrogram_length, asr/input_functions.py:91-93)."""
+    import wave
+
+    def frames_of(row):
+        with wave.open(os.path.join(corpus_dir, row[CSV_HEADER_PATH]), "rb") as w:
+            return num_frames(w.getnframes(), drop_every_second_frame, w.getframerate())
+    return frames_of
+
+
 def pad_labels(rows):
     lmax = max(1, max(len(r) for r in rows))
     out = np.zeros((len(rows), lmax), np.int32)
@@ -73,8 +93,9 @@ def pad_labels(rows):
 
 def plan_batches(csv_path, batch_size, use_buckets, num_buckets=96, seed=None, frames_of=None):
     """The batches of one epoch as lists of CSV rows — everything the reference decides before any arithmetic.
-    frames_of(row) -> spectrogram length of the row's clip (default: from the CSV's `length` column, which is how
-    the boundaries themselves are computed)."""
+    frames_of(row) -> spectrogram length of the row's clip: `frames_of_wav(corpus_dir)` gives the real frame count the
+    reference buckets on; the default derives it from the CSV's `length` column (how the boundaries themselves are
+    computed, 1-2 frames longer than the real count), for planning without the audio files."""
     rows = _read_rows(csv_path)[1:-1]                      # header and final row (asr/input_functions.py:134)
     if frames_of is None:
         frames_of = lambda r: int(float(r[CSV_HEADER_LENGTH]) / WIN_STEP)
@@ -113,8 +134,10 @@ def input_fn_generator(target, flags, featurizer=None, read_wav=None, seed=None)
             getattr(flags, "features_drop_every_second_frame", False)))
         read_wav = read_wav or _features.read_wav
 
+    frames_of = frames_of_wav(flags.corpus_dir, getattr(flags, "features_drop_every_second_frame", False))
+
     def input_fn():
-        for rows in plan_batches(csv_path, flags.batch_size, use_buckets, getattr(flags, "num_buckets", 96), seed):
+        for rows in plan_batches(csv_path, flags.batch_size, use_buckets, getattr(flags, "num_buckets", 96), seed, frames_of):
             clips = []
             for r in rows:
                 rate, pcm = read_wav(os.path.join(flags.corpus_dir, r[CSV_HEADER_PATH]))

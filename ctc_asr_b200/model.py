@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib, labels as _labels, ops
-from .params import CELL_ID, FLAGS, ModelConfig, conv_plan, param_offsets, param_specs, storage_shape
+from .params import CELL_ID, FLAGS, ModelConfig, conv_plan, gradient_buckets, param_offsets, param_specs, storage_shape
 
 
 class CTCModel:
@@ -70,6 +70,11 @@ class CTCModel:
 
     def grads_numpy(self):
         return {k: v.detach().cpu().numpy().copy() for k, v in self.g.items()}
+
+    def gradient_buckets(self):
+        """`params.gradient_buckets(config)`: [lo, hi) ranges of the flat gradient buffer in the order `backward()`
+        finishes them."""
+        return gradient_buckets(self.cfg)
 
     @property
     def num_params(self):
@@ -232,8 +237,10 @@ class CTCModel:
         return decoded, plaintext, summary
 
     # ---- what AdamOptimizer.minimize differentiates (asr/model.py:79-83) ----------------------
-    def backward(self):
-        """d(mean loss)/d(parameters) into self.grad_flat (overwritten)."""
+    def backward(self, on_bucket=None):
+        """d(mean loss)/d(parameters) into self.grad_flat (overwritten).  on_bucket(lo, hi) is called as soon as the
+        kernels that produce grad_flat[lo:hi] are enqueued (the ranges of `gradient_buckets()`, in that order)."""
+        buckets = self.gradient_buckets() if on_bucket is not None else None
         s = self._saved
         if s is None or "dlogits" not in s:
             raise RuntimeError("backward() needs inference_fn() followed by loss_fn() on its logits")
@@ -249,6 +256,8 @@ class CTCModel:
         ops.dense_bwd(h, self.p["dense4/dense/kernel"], y4, d4, self.g["dense4/dense/kernel"],
                       self.g["dense4/dense/bias"], dx=drnn, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate,
                       seed=seed + 100, compute=self.compute)
+        if on_bucket is not None:
+            on_bucket(*buckets[0])
         cell = CELL_ID[cfg.rnn_cell]
         use_len = not cfg.cudnn
         dy = drnn
@@ -260,6 +269,8 @@ class CTCModel:
                           y, reserve, dy, dx, self.g["rnn/l%d/wx" % l], self.g["rnn/l%d/wh" % l],
                           self.g["rnn/l%d/bias" % l], cell, use_len, self.compute)
             dy = dx
+            if on_bucket is not None:
+                on_bucket(*buckets[cfg.num_layers_rnn - l])
         if cfg.used_model == "ds2":
             names = self._conv_names()
             for li in reversed(range(len(names))):
@@ -269,6 +280,8 @@ class CTCModel:
                                self.gs[names[li] + "/bias"], d["T"], B, d["F"], d["C"], d["kt"], d["kf"], d["st"], d["sf"],
                                act=1, cutoff=cfg.relu_cutoff, compute=self.compute)
                 dy = dx
+            if on_bucket is not None:
+                on_bucket(*buckets[-1])
             return self.grad_flat
         names = self._dense_names()
         for li in reversed(range(len(names))):
@@ -278,6 +291,8 @@ class CTCModel:
                           self.g[names[li] + "/bias"], dx=dx, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate,
                           seed=seed + li, compute=self.compute)
             dy = dx
+        if on_bucket is not None:
+            on_bucket(*buckets[-1])
         return self.grad_flat
 
     def apply_gradients(self, grad_scale=1.0):
@@ -287,16 +302,28 @@ class CTCModel:
         ops.adam(self.flat, self.adam_m, self.adam_v, self.grad_flat, self.global_step, cfg.learning_rate,
                  cfg.adam_beta1, cfg.adam_beta2, cfg.adam_epsilon, grad_scale)
 
-    def train_step(self, sequences, seq_length, labels, global_batch=None, allreduce=None):
+    def train_step(self, sequences, seq_length, labels, global_batch=None, allreduce=None, overlap=True):
         """model_fn's TRAIN branch (asr/model.py:53-54, 74, 79-83) on one batch.  Returns the loss as a 0-d device
         tensor.  Nothing in the step waits for the GPU: the checks the reference makes on its values (CTCLoss's
         InvalidArgumentError, NanTensorHook(loss) at asr/model.py:368) are made on the previous step's results when the
-        next step starts, or by `check_step()`."""
+        next step starts, or by `check_step()`.
+        allreduce(tensor, async_op=False): sums a slice of the flat gradient over the data-parallel ranks in place and,
+        with async_op=True, returns a handle with .wait() (torch.distributed semantics)."""
         self.check_step()
         logits, seq_length = self.inference_fn(sequences, seq_length, training=True)
         loss = self.loss_fn(logits, seq_length, labels, global_batch=global_batch, defer_check=True)
-        self.backward()
-        if allreduce is not None:
+        if allreduce is None:
+            self.backward()
+        elif overlap:
+            # data parallel: every bucket of the gradient is summed over the ranks (asynchronously, on the collective
+            # library's stream) while the backward pass of the layers below it is still running
+            works = []
+            self.backward(on_bucket=lambda lo, hi: works.append(allreduce(self.grad_flat[lo:hi], async_op=True)))
+            for w in works:
+                if w is not None:
+                    w.wait()
+        else:
+            self.backward()
             allreduce(self.grad_flat)
         self.apply_gradients()
         # loss + "any utterance rejected" travel to a pinned host slot behind the step's kernels

@@ -1,5 +1,7 @@
 """Data parallelism for the hot path: one process per GPU, equal shards, ONE all-reduce (sum) of the
-flat gradient buffer per step.  The reference is single-device
+flat gradient buffer per step, issued as one asynchronous all-reduce per bucket of
+`CTCModel.gradient_buckets()` (dense4 + logits, each RNN layer, the front-end) as soon as the backward pass has produced
+the bucket, so that the transfer runs under the backward pass of the layers below.  The reference is single-device
 (`train_distribute=None`, asr/train.py:41); this is the only collective the path needs, so the
 plumbing is `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) and nothing else.
 
@@ -22,9 +24,9 @@ def shard_bounds(global_batch, rank, world):
 
 def shard_indices(global_batch, rank, world, interleave=False):
     """Utterance indices of this rank's shard.  interleave=False: a contiguous block.  interleave=True:
-    rank, rank + world, rank + 2 world, ... — for the reference's length-bucketed batches, whose utterances are
-    sorted by duration inside a bucket (asr/util/csv_helper.py:29-38), this gives every GPU the same count AND
-    the same mix of lengths, so the ranks' step times stay balanced."""
+    rank, rank + world, rank + 2 world, ... — when the caller has sorted the batch by duration (the synthetic cfg4
+    batches are; the reference's bucketed batches hold similar lengths in arrival order) this gives every GPU the same
+    count AND the same mix of lengths, so the ranks' step times stay balanced."""
     lo, hi = shard_bounds(global_batch, rank, world)
     if not interleave:
         return slice(lo, hi)
@@ -36,11 +38,13 @@ def shard_batch(sequences, seq_length, labels, label_length, rank, world, interl
     return sequences[idx], seq_length[idx], labels[idx], label_length[idx]
 
 
-def allreduce_gradients(flat_grad, group=None):
-    """Sum the flat gradient over all ranks, in place."""
+def allreduce_gradients(flat_grad, group=None, async_op=False):
+    """Sum the flat gradient (or one bucket of it) over all ranks, in place.  async_op=True returns the
+    torch.distributed work handle (None when there is nothing to reduce)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
-    return flat_grad
+        work = dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return work if async_op else flat_grad
+    return None if async_op else flat_grad
 
 
 def allreduce_mean_loss(local_loss_sum_over_global_batch, group=None):
@@ -51,11 +55,18 @@ def allreduce_mean_loss(local_loss_sum_over_global_batch, group=None):
     return t[0]
 
 
-def train_step(model, sequences, seq_length, labels, label_length, group=None, interleave=False):
+def train_step(model, sequences, seq_length, labels, label_length, group=None, interleave=False, overlap=True):
     """One data-parallel step of `CTCModel` on this rank's shard of the global batch."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    gb = sequences.shape[0]
+    # the partly filled batches a bucketed epoch ends with (asr/input_functions.py:90-98) need not divide by the
+    # world size: the remainder utterances are dropped (every rank drops the same ones), a batch smaller than
+    # the world size is skipped
+    gb = sequences.shape[0] - sequences.shape[0] % world
+    if gb == 0:
+        return None
+    sequences, seq_length, labels, label_length = sequences[:gb], seq_length[:gb], labels[:gb], label_length[:gb]
     x, sl, lab, ll = shard_batch(sequences, seq_length, labels, label_length, rank, world, interleave)
-    loss = model.train_step(x, sl, (lab, ll), global_batch=gb, allreduce=lambda g: allreduce_gradients(g, group))
+    loss = model.train_step(x, sl, (lab, ll), global_batch=gb, overlap=overlap,
+                            allreduce=lambda g, async_op=False: allreduce_gradients(g, group, async_op))
     return allreduce_mean_loss(loss, group)

@@ -228,3 +228,22 @@ def flops_per_frame_fwd(cfg: ModelConfig):
         nin = 2 * H
     f += 2 * nin * D + 2 * D * V
     return f
+
+
+def gradient_buckets(cfg: ModelConfig):
+    """[lo, hi) ranges of the flat gradient buffer in the order the backward pass finishes them: dense4 + logits, the
+    RNN layers from the last to the first, the front-end.  Each range is contiguous (param_specs order) and 256-B
+    aligned, and together they cover the buffer, so a data-parallel caller can all-reduce a bucket while the layers
+    below it are still in backward."""
+    offsets, num_flat = param_offsets(cfg)
+    names = [n for n, _, _ in param_specs(cfg)]
+    starts = [offsets[n][0] for n in names] + [num_flat]
+
+    def span(pred):
+        sel = [i for i, n in enumerate(names) if pred(n)]
+        return (min(starts[i] for i in sel), max(starts[i + 1] for i in sel))
+    buckets = [span(lambda n: n.startswith("dense4/") or n.startswith("logits/"))]
+    for l in reversed(range(cfg.num_layers_rnn)):
+        buckets.append(span(lambda n, l=l: n.startswith("rnn/l%d/" % l)))
+    buckets.append(span(lambda n: n.startswith("dense/") or n.startswith("conv/")))
+    return buckets

@@ -129,6 +129,9 @@ int ctcasr_dense_bwd(const float *x, const float *w, const float *y, float *dy,
  * -------------------------------------------------------------------------------------------- */
 size_t ctcasr_birnn_reserve_bytes(int T, int B, int in, int H, int cell);
 size_t ctcasr_birnn_workspace_bytes(int T, int B, int in, int H, int cell);
+/* bytes one recurrence launch of this shape pulls through TMA from L2 / HBM (weight tiles not resident on chip +
+ * the state tiles of every step, all CTAs): the numerator of bench.py's L2-streaming bound.  0 for the stepwise path. */
+double ctcasr_birnn_stream_bytes(int T, int B, int H, int cell, int compute, int backward);
 int ctcasr_birnn_fwd(const float *x, const int32_t *seq_len, const float *wx, const float *wh,
                      const float *bias, float *y, void *reserve,
                      int T, int B, int in, int H, int cell, int use_len, float forget_bias,

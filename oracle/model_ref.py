@@ -26,8 +26,15 @@ def _dense_names(cfg):
     return ["dense/dense" if i == 0 else "dense/dense_%d" % i for i in range(cfg.num_layers_dense)]
 
 
-def forward(cfg, params, sequences, seq_length, training=False, seed=0, dtype=np.float64):
-    """sequences [B,T,F] batch-major (asr/model.py:129) -> logits [T,B,V] time-major + cache."""
+def forward(cfg, params, sequences, seq_length, training=False, seed=0, dtype=np.float64, round_operands=False):
+    """sequences [B,T,F] batch-major (asr/model.py:129) -> logits [T,B,V] time-major + cache.
+    round_operands: bf16 operand rounding in every matrix product but the 29-class logits layer (which the product
+    path's compute='bf16' mode runs in exact fp32, its width being no tensor-core tile)."""
+    with ref.operand_rounding(round_operands):
+        return _forward(cfg, params, sequences, seq_length, training, seed, dtype)
+
+
+def _forward(cfg, params, sequences, seq_length, training, seed, dtype):
     x = np.ascontiguousarray(np.transpose(np.asarray(sequences, dtype), (1, 0, 2)))   # [T,B,F]
     T, B, _ = x.shape
     seq_length = np.asarray(seq_length, np.int32)
@@ -64,7 +71,8 @@ def forward(cfg, params, sequences, seq_length, training=False, seed=0, dtype=np
     y4 = ref.dense_fwd(h, w, b, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + 100)
     cache["d4"] = (h, y4)
     w, b = params["logits/dense/kernel"].astype(dtype), params["logits/dense/bias"].astype(dtype)
-    logits = ref.dense_fwd(y4, w, b, act=0)
+    with ref.operand_rounding(False):
+        logits = ref.dense_fwd(y4, w, b, act=0)
     cache["lg"] = (y4,)
     cache["meta"] = (T, B, rate, seed)
     cache["seq_length"] = seq_length
@@ -72,10 +80,15 @@ def forward(cfg, params, sequences, seq_length, training=False, seed=0, dtype=np
 
 
 def loss_and_grads(cfg, params, sequences, seq_length, labels, label_len, training=False, seed=0,
-                   dtype=np.float64):
+                   dtype=np.float64, round_operands=False):
     """Mean CTC loss (asr/model.py:267) and d loss / d params (what AdamOptimizer.minimize
     differentiates, asr/model.py:83).  Returns (loss, grads dict, logits, dlogits)."""
-    logits, cache = forward(cfg, params, sequences, seq_length, training, seed, dtype)
+    with ref.operand_rounding(round_operands):
+        return _loss_and_grads(cfg, params, sequences, seq_length, labels, label_len, training, seed, dtype)
+
+
+def _loss_and_grads(cfg, params, sequences, seq_length, labels, label_len, training, seed, dtype):
+    logits, cache = _forward(cfg, params, sequences, seq_length, training, seed, dtype)
     T, B, rate, seed = cache["meta"]
     seq_length = cache["seq_length"]             # ds2: the conv length for every utterance
     loss_b, g, status = ref.ctc_loss(logits, labels, label_len, seq_length, blank=cfg.num_classes - 1)
@@ -86,8 +99,9 @@ def loss_and_grads(cfg, params, sequences, seq_length, labels, label_len, traini
     dy = dlogits.reshape(T * B, -1)
     (y4,) = cache["lg"]
     w = params["logits/dense/kernel"].astype(dtype)
-    dy, grads["logits/dense/kernel"], grads["logits/dense/bias"] = ref.dense_bwd(
-        y4, w, y4[:, :1], dy, act=0)
+    with ref.operand_rounding(False):
+        dy, grads["logits/dense/kernel"], grads["logits/dense/bias"] = ref.dense_bwd(
+            y4, w, y4[:, :1], dy, act=0)
     h, y4 = cache["d4"]
     w = params["dense4/dense/kernel"].astype(dtype)
     dy, grads["dense4/dense/kernel"], grads["dense4/dense/bias"] = ref.dense_bwd(

@@ -13,12 +13,16 @@
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
 
+int oracle_operand_rounding = 0;
+void oracle_set_operand_rounding(int mode) { oracle_operand_rounding = mode; }
+
 #define REAL float
 #define SUF(name) CAT(name, _f32)
 #include "oracle_impl.h"
 #undef REAL
 #undef SUF
 #undef NEG_INF
+#undef RB
 
 #define oracle_hash32 oracle_hash32_d
 #define oracle_drop_keep oracle_drop_keep_d

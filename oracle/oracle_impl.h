@@ -26,6 +26,25 @@
 
 #define NEG_INF (-(REAL)INFINITY)
 
+/* Operand rounding (oracle_set_operand_rounding(1)): every matrix product below rounds BOTH operands to bfloat16
+ * (round-to-nearest-even) before multiplying and accumulates in REAL — the arithmetic of the product path's
+ * compute = 'bf16' mode (BASELINE cfg3: bf16 tensor-core operands, fp32 accumulation, fp32 everything else), so
+ * that mode can be compared at the same 1e-3 bar as the exact modes.  Off (0) by default: exact products. */
+extern int oracle_operand_rounding;
+static inline REAL SUF(rb)(REAL v)
+{
+    if (!oracle_operand_rounding) return v;
+    float f = (float)v;
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return v;            /* inf / nan */
+    u += 0x7fffu + ((u >> 16) & 1u);
+    u &= 0xffff0000u;
+    memcpy(&f, &u, 4);
+    return (REAL)f;
+}
+#define RB(v) SUF(rb)(v)
+
 static inline REAL SUF(lse2)(REAL a, REAL b)
 {
     /* ctc_loss_util.h LogSumExp: log-zero is -inf */
@@ -184,7 +203,7 @@ int SUF(oracle_dense_fwd)(const REAL *x, const REAL *w, const REAL *bias, REAL *
     for (int m = 0; m < M; ++m) {
         for (int n = 0; n < N; ++n) {
             REAL acc = bias ? bias[n] : 0;
-            for (int k = 0; k < K; ++k) acc += x[(size_t)m * K + k] * w[(size_t)k * N + n];
+            for (int k = 0; k < K; ++k) acc += RB(x[(size_t)m * K + k]) * RB(w[(size_t)k * N + n]);
             if (act == 1) { acc = acc > 0 ? acc : 0; acc = acc < cutoff ? acc : cutoff; }
             if (drop_rate > 0) acc = oracle_drop_keep(seed, (uint64_t)m * N + n, drop_rate) ? acc * inv_keep : 0;
             y[(size_t)m * N + n] = acc;
@@ -222,7 +241,7 @@ int SUF(oracle_dense_bwd)(const REAL *x, const REAL *w, const REAL *y, const REA
         for (int k = 0; k < K; ++k)
             for (int n = 0; n < N; ++n) {
                 REAL s = 0;
-                for (int m = 0; m < M; ++m) s += x[(size_t)m * K + k] * dz[(size_t)m * N + n];
+                for (int m = 0; m < M; ++m) s += RB(x[(size_t)m * K + k]) * RB(dz[(size_t)m * N + n]);
                 dw[(size_t)k * N + n] = s;
             }
     }
@@ -231,7 +250,7 @@ int SUF(oracle_dense_bwd)(const REAL *x, const REAL *w, const REAL *y, const REA
         for (int m = 0; m < M; ++m)
             for (int k = 0; k < K; ++k) {
                 REAL s = 0;
-                for (int n = 0; n < N; ++n) s += dz[(size_t)m * N + n] * w[(size_t)k * N + n];
+                for (int n = 0; n < N; ++n) s += RB(dz[(size_t)m * N + n]) * RB(w[(size_t)k * N + n]);
                 dx[(size_t)m * K + k] = s;
             }
     }
@@ -284,9 +303,9 @@ int SUF(oracle_birnn_fwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                 const REAL *xt = x + ((size_t)t * B + b) * in;
                 for (int g = 0; g < GH; ++g) z[g] = bias[d * GH + g];
                 for (int k = 0; k < in; ++k) {
-                    const REAL xv = xt[k];
+                    const REAL xv = RB(xt[k]);
                     const REAL *wr = wx + (size_t)k * 2 * GH + d * GH;
-                    for (int g = 0; g < GH; ++g) z[g] += xv * wr[g];
+                    for (int g = 0; g < GH; ++g) z[g] += xv * RB(wr[g]);
                 }
                 REAL *gt = gates + (((size_t)d * T + t) * B + b) * GH;
                 REAL *yt = y + ((size_t)t * B + b) * 2 * H + d * H;
@@ -294,9 +313,9 @@ int SUF(oracle_birnn_fwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                     /* recurrent part kept apart: the candidate gate multiplies it by r */
                     REAL *rh = (REAL *)calloc(GH, sizeof(REAL));
                     for (int k = 0; k < H; ++k) {
-                        const REAL hv = h[k];
+                        const REAL hv = RB(h[k]);
                         const REAL *wr = whd + (size_t)k * GH;
-                        for (int g = 0; g < GH; ++g) rh[g] += hv * wr[g];
+                        for (int g = 0; g < GH; ++g) rh[g] += hv * RB(wr[g]);
                     }
                     REAL *qt = cstate + (((size_t)d * T + t) * B + b) * H;
                     for (int u = 0; u < H; ++u) {
@@ -311,9 +330,9 @@ int SUF(oracle_birnn_fwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                     continue;
                 }
                 for (int k = 0; k < H; ++k) {
-                    const REAL hv = h[k];
+                    const REAL hv = RB(h[k]);
                     const REAL *wr = whd + (size_t)k * GH;
-                    for (int g = 0; g < GH; ++g) z[g] += hv * wr[g];
+                    for (int g = 0; g < GH; ++g) z[g] += hv * RB(wr[g]);
                 }
                 if (cell == 2) {
                     REAL *ct = cstate + (((size_t)d * T + t) * B + b) * H;
@@ -380,7 +399,7 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                     for (int k = 0; k < H; ++k) {
                         const REAL *wr = whd + (size_t)k * GH;
                         REAL s = 0;
-                        for (int g = 0; g < GH; ++g) s += dzrt[g] * wr[g];
+                        for (int g = 0; g < GH; ++g) s += RB(dzrt[g]) * RB(wr[g]);
                         dh[k] = s + dhd[k];
                     }
                     continue;
@@ -409,7 +428,7 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                 for (int k = 0; k < H; ++k) {
                     const REAL *wr = whd + (size_t)k * GH;
                     REAL s = 0;
-                    for (int g = 0; g < GH; ++g) s += dzt[g] * wr[g];
+                    for (int g = 0; g < GH; ++g) s += RB(dzt[g]) * RB(wr[g]);
                     dh[k] = s;
                 }
             }
@@ -435,10 +454,10 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
 #pragma omp parallel for
         for (int k = 0; k < in; ++k) {
             for (int t = 0; t < T; ++t) for (int b = 0; b < B; ++b) {
-                const REAL xv = x[((size_t)t * B + b) * in + k];
+                const REAL xv = RB(x[((size_t)t * B + b) * in + k]);
                 const REAL *dzt = dz + (((size_t)d * T + t) * B + b) * GH;
                 REAL *o = dwx + (size_t)k * 2 * GH + d * GH;
-                for (int g = 0; g < GH; ++g) o[g] += xv * dzt[g];
+                for (int g = 0; g < GH; ++g) o[g] += xv * RB(dzt[g]);
             }
         }
 #pragma omp parallel for
@@ -448,10 +467,10 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                 for (int step = 1; step < len; ++step) {
                     const int t = d == 0 ? step : len - 1 - step;
                     const int tp = d == 0 ? t - 1 : t + 1;
-                    const REAL hv = y[((size_t)tp * B + b) * 2 * H + d * H + k];
+                    const REAL hv = RB(y[((size_t)tp * B + b) * 2 * H + d * H + k]);
                     const REAL *dzt = dzr + (((size_t)d * T + t) * B + b) * GH;
                     REAL *o = dwh + ((size_t)d * H + k) * GH;
-                    for (int g = 0; g < GH; ++g) o[g] += hv * dzt[g];
+                    for (int g = 0; g < GH; ++g) o[g] += hv * RB(dzt[g]);
                 }
             }
         }
@@ -462,7 +481,7 @@ int SUF(oracle_birnn_bwd)(const REAL *x, const int *seq_len, const REAL *wx, con
                 for (int k = 0; k < in; ++k) {
                     const REAL *wr = wx + (size_t)k * 2 * GH + d * GH;
                     REAL s = 0;
-                    for (int g = 0; g < GH; ++g) s += dzt[g] * wr[g];
+                    for (int g = 0; g < GH; ++g) s += RB(dzt[g]) * RB(wr[g]);
                     dx[(size_t)tb * in + k] += s;
                 }
             }
@@ -534,7 +553,7 @@ int SUF(oracle_conv2d_fwd)(const REAL *x, const REAL *w, const REAL *bias, REAL 
                         const REAL *wr = w + ((size_t)it * kf + jf) * C * N;
                         for (int c = 0; c < C; ++c) {
                             const REAL xv = xr[c];
-                            for (int n = 0; n < N; ++n) yr[n] += xv * wr[(size_t)c * N + n];
+                            for (int n = 0; n < N; ++n) yr[n] += RB(xv) * RB(wr[(size_t)c * N + n]);
                         }
                     }
                 }
@@ -586,7 +605,7 @@ int SUF(oracle_conv2d_bwd)(const REAL *x, const REAL *w, const REAL *y, const RE
                         const REAL *xr = x + (((size_t)t * B + b) * F + f) * C;
                         const REAL *gz = dz + (((size_t)to * B + b) * Fo + fo) * N;
                         for (int c = 0; c < C; ++c)
-                            for (int n = 0; n < N; ++n) dwr[(size_t)c * N + n] += xr[c] * gz[n];
+                            for (int n = 0; n < N; ++n) dwr[(size_t)c * N + n] += RB(xr[c]) * RB(gz[n]);
                     }
             }
         }
@@ -612,7 +631,7 @@ int SUF(oracle_conv2d_bwd)(const REAL *x, const REAL *w, const REAL *y, const RE
                             const REAL *wr = w + ((size_t)it * kf + jf) * C * N;
                             for (int c = 0; c < C; ++c) {
                                 REAL s = 0;
-                                for (int n = 0; n < N; ++n) s += gz[n] * wr[(size_t)c * N + n];
+                                for (int n = 0; n < N; ++n) s += RB(gz[n]) * RB(wr[(size_t)c * N + n]);
                                 dxr[c] += s;
                             }
                         }

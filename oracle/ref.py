@@ -51,6 +51,23 @@ def _c(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+class operand_rounding:
+    """with ref.operand_rounding(True): every matrix product of the oracle rounds both operands to bfloat16 (the
+    arithmetic of the product path's compute='bf16' mode, BASELINE cfg3); exact products otherwise."""
+
+    def __init__(self, on=True):
+        self.on = int(bool(on))
+
+    def __enter__(self):
+        self.prev = ctypes.c_int.in_dll(lib(), "oracle_operand_rounding").value
+        lib().oracle_set_operand_rounding(self.on)
+        return self
+
+    def __exit__(self, *exc):
+        lib().oracle_set_operand_rounding(self.prev)
+        return False
+
+
 NUM_GATES = {0: 1, 1: 1, 2: 4, 3: 3}
 CELL_IDS = {"rnn_tanh": 0, "rnn_relu": 1, "lstm": 2, "gru": 3}
 

@@ -91,3 +91,28 @@ def test_input_fn_yields_padded_batches_in_the_reference_layout(tmp_path):
         assert int(n.max()) - int(n.min()) <= 60
         seen += B
     assert seen == 40
+
+
+def test_frame_counts_and_real_length_bucketing(tmp_path):
+    """Buckets key on the real spectrogram length (WAV header), halved when every second frame is dropped; the
+    pure-Python frame formula equals the C-ABI's ctcasr_feature_frames."""
+    assert [ip.num_frames(n) for n in (401, 560, 561, 16000, 160000, 272000)] == [2, 2, 3, 99, 999, 1699]
+    assert ip.num_frames(16000, True) == 50 and ip.num_frames(160000, True) == 500
+    try:
+        from ctc_asr_b200 import _lib
+        lib = _lib.load()
+        for n in (401, 999, 16000, 123457, 272000):
+            assert lib.ctcasr_feature_frames(n, 16000) == ip.num_frames(n)
+    except _lib.CtcAsrError:
+        pass
+    csv_path, durations = _corpus(tmp_path)
+    frames_of = ip.frames_of_wav(str(tmp_path / "corpus"))
+    rows = ip._read_rows(csv_path)[1:-1]
+    for r, d in zip(rows, durations):
+        assert frames_of(r) == ip.num_frames(int(d * 16000))
+        assert 0 <= int(float(r["length"]) / 0.010) - frames_of(r) <= 2          # the CSV length over-counts by 1-2 frames
+    bounds = ip.get_bucket_boundaries(csv_path, 8)
+    for b in ip.plan_batches(csv_path, 4, True, 8, seed=3, frames_of=frames_of):
+        assert len({ip.bucket_of(frames_of(r), bounds) for r in b}) == 1
+    half = ip.frames_of_wav(str(tmp_path / "corpus"), drop_every_second_frame=True)
+    assert all(half(r) == (frames_of(r) + 1) // 2 for r in rows)

@@ -227,3 +227,30 @@ def test_ds2_whole_path_vs_torch_autograd():
     np.testing.assert_allclose(loss, float(tloss), rtol=1e-10)
     for k in params:
         np.testing.assert_allclose(grads[k], tgrads[k].numpy(), atol=1e-9, err_msg=k)
+
+
+def test_operand_rounding_mode_is_bf16_round_to_nearest_even():
+    """oracle operand_rounding (the arithmetic compute='bf16' is compared against): both operands of every product
+    rounded exactly like torch's float32 -> bfloat16 conversion, fp64 accumulation; off again afterwards."""
+    import torch
+    rng = np.random.default_rng(3)
+    x, w, b = rng.standard_normal((9, 31)), rng.standard_normal((31, 7)), rng.standard_normal(7)
+    bf = lambda a: torch.tensor(a, dtype=torch.float32).bfloat16().double().numpy()
+    exact = ref.dense_fwd(x, w, b, act=0)
+    with ref.operand_rounding(True):
+        y = ref.dense_fwd(x, w, b, act=0)
+        dx, dw, db = ref.dense_bwd(x, w, y, exact, act=0)
+    assert np.abs(y - (bf(x) @ bf(w) + b)).max() < 1e-12
+    assert np.abs(dw - bf(x).T @ bf(exact)).max() < 1e-12 and np.abs(dx - bf(exact) @ bf(w).T).max() < 1e-12
+    assert np.abs(ref.dense_fwd(x, w, b, act=0) - exact).max() == 0
+    assert 1e-4 < np.abs(y - exact).max() < 1e-1
+    # a recurrent layer: h_{t-1} is rounded where it enters the product, not where it is stored
+    T, B, nin, H = 5, 2, 6, 4
+    xs = rng.standard_normal((T, B, nin)); sl = np.array([5, 3], np.int32)
+    wx, wh, bias = rng.standard_normal((nin, 2 * H)) * 0.3, rng.standard_normal((2, H, H)) * 0.3, rng.standard_normal(2 * H) * 0.1
+    with ref.operand_rounding(True):
+        y, _, _ = ref.birnn_fwd(xs, sl, wx, wh, bias, 0, use_len=True)
+    h = np.zeros(H)
+    for t in range(5):                       # forward direction of utterance 0 by hand
+        h = np.tanh(bf(xs[t, 0]) @ bf(wx[:, :H]) + bf(h) @ bf(wh[0]) + bias[:H])
+        assert np.abs(y[t, 0, :H] - h).max() < 1e-12

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from ctc_asr_b200 import parallel, synthetic
-from ctc_asr_b200.params import ModelConfig, param_offsets
+from ctc_asr_b200.params import ModelConfig, gradient_buckets, param_offsets
 from oracle import model_ref
 
 CFG = ModelConfig(used_model="ds1", num_layers_dense=2, num_units_dense=16, num_layers_rnn=1, num_units_rnn=8, rnn_cell="lstm",
@@ -88,3 +88,41 @@ def test_shard_bounds_reject_ragged_split():
     except ValueError:
         return
     raise AssertionError("uneven shards must be rejected")
+
+
+def _bucket_worker(rank, world, port, n, buckets, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(n, dtype=torch.float64) * (rank + 1)
+    whole = g.clone()
+    parallel.allreduce_gradients(whole)
+    works = [parallel.allreduce_gradients(g[lo:hi], async_op=True) for lo, hi in buckets]       # views: reduced in place
+    for w in works:
+        w.wait()
+    if rank == 0:
+        out["same"] = bool(torch.equal(g, whole))
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_cover_the_buffer_and_reduce_like_one_allreduce():
+    """The overlapped data-parallel step all-reduces `gradient_buckets()` one by one (asynchronously, in backward
+    order): the buckets partition the flat buffer, for both front-ends, and the result is the single all-reduce."""
+    for cfg in (CFG, CFG.replace(num_layers_rnn=3), ModelConfig(used_model="ds2", conv_filters=(8, 8, 64), num_units_dense=16,
+                                                                num_layers_rnn=2, num_units_rnn=8, num_features=20)):
+        _, n = param_offsets(cfg)
+        buckets = gradient_buckets(cfg)
+        assert len(buckets) == cfg.num_layers_rnn + 2
+        assert sorted(buckets)[0][0] == 0 and sorted(buckets)[-1][1] == n
+        srt = sorted(buckets)
+        assert all(srt[i][1] == srt[i + 1][0] for i in range(len(srt) - 1))          # no gap, no overlap
+        assert buckets[0][1] == n                                                     # dense4 + logits come first, at the end
+        assert all(lo % 64 == 0 for lo, _ in buckets)                                 # 256-B aligned float offsets
+    _, n = param_offsets(CFG)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bucket_worker, args=(2, port, n, gradient_buckets(CFG), out), nprocs=2, join=True)
+    assert out["same"]
+    assert parallel.allreduce_gradients(torch.zeros(3), async_op=True) is None        # single process: nothing to wait for
