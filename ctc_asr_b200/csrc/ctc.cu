@@ -25,6 +25,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace ctcasr {
 namespace ctc {
@@ -39,6 +40,7 @@ struct Params {
     float *loss; float *grad; float grad_scale; int *status;
     float2 *ckpt;                   // [B][NCH][RS] alpha checkpoint rows (hi, lo)
     int CH, RS, GT, NCH, Lmax, VP;
+    float2 *rows;                   // warp kernel: [B][T][32 * SPL] spilled alpha / beta rows
 };
 
 struct SmemLayout {
@@ -466,12 +468,329 @@ __global__ void edit_distance_kernel(const int *hyp, int hstride, const int *hyp
     }
 }
 
-struct Plan { int CH, RS, GT, NCH, VP, SPT; size_t smem, ws_total; };
+// ------------------------------------------------------------------------------------------------
+// Warp-shuffle CTC (the common case: 2L+1 <= 384 lattice states, V <= 32 classes).
+//
+// One CTA of two warps per utterance, no block barrier inside the time loop:
+//   warp 0 walks t = 0 .. T_b-1 with the alpha recursion, warp 1 walks t = T_b-1 .. 0 with the beta recursion, AT THE
+//   SAME TIME.  Lane l holds the SPL consecutive lattice states s = l*SPL .. l*SPL+SPL-1 in registers as
+//   extended-range (m, e) numbers; a step needs the two neighbouring states of the next lane (4 shuffles), the
+//   frame's softmax (computed by the warp itself: lane k owns class k, max / sum by shuffles, prefetched one frame
+//   ahead) and y[l'_s] (one shuffle pair per label state).  Nothing of the recursion touches shared memory.
+//   During the FIRST half of its walk a warp spills its rows to HBM ([T][32 lanes][SPL] float2, coalesced 16-B
+//   stores); the warps meet in the middle (one 64-thread barrier), p(labels | x) = sum_s alpha_{h-1}(s) beta~_h(s)
+//   is formed there, and during the SECOND half each warp reads the other warp's spilled row of the same frame,
+//   forms the posteriors alpha beta / (y p) and writes the gradient row.  Two concurrent sweeps of T steps
+//   replace the three (alpha, alpha re-computation, beta) of the block-per-utterance kernel above, which stays
+//   for longer label sequences and wider alphabets.
+//   The recursion runs on UN-normalised y'_k = exp(x_k): a per-frame factor common to all states cancels in the
+//   posteriors, and log2 Z_t is taken out of the loss, so no reduction sits on the recursion's dependency chain.
+//   Per-class sums of the posteriors and the frame's Z_t are integer (fixed-point) warp reductions and shared-memory
+//   atomics: integer addition commutes, so the result is the same bits in any order.
+//   Logits and the other warp's rows arrive through a cp.async ring kPF frames ahead.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 xf_add(const float2 a, const float2 b)
+{
+    const int ea = xf_e(a), eb = xf_e(b), em = max(ea, eb);
+    const float s = fmaf(a.x, pow2_le0(ea - em), b.x * pow2_le0(eb - em));
+    if (s == 0.f) return xf_make(0.f, kZE);
+    const int bits = __float_as_int(s);
+    return xf_make(__int_as_float((bits & 0x007fffff) | 0x3f800000), em + (bits >> 23) - 127);
+}
+__device__ __forceinline__ float2 xf_mul(const float2 a, const float2 b)
+{
+    const float s = a.x * b.x;
+    if (s == 0.f) return xf_make(0.f, kZE);
+    const int bits = __float_as_int(s);
+    return xf_make(__int_as_float((bits & 0x007fffff) | 0x3f800000), xf_e(a) + xf_e(b) + (bits >> 23) - 127);
+}
+__device__ __forceinline__ float2 shfl2(const float2 v, int src)
+{
+    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+constexpr int kPF = 8;             // frames the warp kernel prefetches ahead (cp.async ring)
+
+struct WarpSmem {
+    size_t lab, csr_start, csr_pos, hand, post, ring, total;
+    __host__ __device__ WarpSmem(int Lmax, int V, int RS)
+    {
+        size_t o = 0;
+        lab = o;       o += (size_t)((Lmax + 3) / 4 * 4 + 4) * 4;
+        csr_start = o; o += (size_t)((V + 1 + 3) / 4 * 4) * 4;
+        csr_pos = o;   o += (size_t)((Lmax + 3) / 4 * 4 + 4) * 4;
+        o = (o + 15) / 16 * 16;
+        hand = o;      o += (size_t)2 * (RS + 4) * 8 + 32;         // alpha_{h-1} and beta_h rows at the hand-over, 2 doubles
+        post = o;      o += (size_t)2 * 2 * RS * 4;                // [warp][2 buffers][RS] posteriors of the current frame
+        ring = o;      o += (size_t)2 * kPF * (128 + (size_t)RS * 8);   // [warp][kPF slots]{32 logits, the other warp's row}
+        total = o + 32;
+    }
+};
+
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int warp_max_int(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(64)
+ctc_warp_kernel(const Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = p.V, blank = p.blank;
+    constexpr int RS = 32 * SPL;
+    constexpr size_t SLOT = 128 + (size_t)RS * 8;
+    const float2 kZero = xf_make(0.f, kZE), kOne = xf_make(1.f, 0);
+    const WarpSmem L(p.Lmax, V, RS);
+    int *lab = reinterpret_cast<int *>(smem_raw + L.lab);
+    float2 *hand = reinterpret_cast<float2 *>(smem_raw + L.hand);             // [2][RS + 4]
+    double *hand_lz = reinterpret_cast<double *>(smem_raw + L.hand + (size_t)2 * (RS + 4) * 8);
+    float *postbuf = reinterpret_cast<float *>(smem_raw + L.post) + (size_t)warp * 2 * RS;
+    unsigned char *ring = smem_raw + L.ring + (size_t)warp * kPF * SLOT;
+    int *flags = reinterpret_cast<int *>(smem_raw + L.total - 32);
+
+    const int Tb = p.seq_len[b], Ln = p.label_len[b], S = 2 * Ln + 1;
+    float *grad_b = p.grad ? p.grad + (size_t)b * V : nullptr;                 // row t at + t*B*V
+    const size_t gstride = (size_t)p.B * V;
+
+    // ---- setup: labels, validation (as in the block kernel) ------------------------------------
+    if (tid < 2) flags[tid] = 0;
+    __syncthreads();
+    int status = CTCASR_CTC_OK;
+    if (Tb > p.T || Tb < 0 || Ln < 0 || Ln > p.Lmax) status = CTCASR_CTC_BAD_LENGTH;
+    if (status == CTCASR_CTC_OK) {
+        int bad = 0, rep = 0;
+        for (int i = tid; i < Ln; i += 64) {
+            const int v = p.labels[(size_t)b * p.lstride + i];
+            lab[i] = v;
+            if (v < 0 || v >= V || v == blank) bad = 1;
+            if (i > 0 && v == p.labels[(size_t)b * p.lstride + i - 1]) ++rep;
+        }
+        if (bad) atomicOr(&flags[0], 1);
+        if (rep) atomicAdd(&flags[1], rep);
+    }
+    __syncthreads();
+    if (status == CTCASR_CTC_OK) {
+        if (flags[0]) status = CTCASR_CTC_BAD_LABEL;
+        else if (Tb < Ln + flags[1]) status = CTCASR_CTC_INFEASIBLE;
+    }
+    if (grad_b) {       // gradient rows the recursion never touches are zero (t >= T_b, or the whole utterance)
+        const int t0 = (status == CTCASR_CTC_OK) ? Tb : 0;
+        for (int i = tid; i < (p.T - t0) * V; i += 64)
+            grad_b[(size_t)(t0 + i / V) * gstride + i % V] = 0.f;
+    }
+    if (status != CTCASR_CTC_OK || Tb == 0) {
+        if (tid == 0) { p.status[b] = status; p.loss[b] = status == CTCASR_CTC_OK ? 0.f : INFINITY; }
+        return;
+    }
+    for (int i = tid; i < 2 * (RS + 4); i += 64) hand[i] = kZero;
+    __syncthreads();
+    reinterpret_cast<unsigned *>(postbuf)[lane] = 0;            // class accumulators [2 buffers][32] of my warp
+    reinterpret_cast<unsigned *>(postbuf)[32 + lane] = 0;
+    __syncwarp();
+
+    // ---- per-lane lattice constants: SPL is even, so state j of a lane is a blank for even j, a label for odd j ----
+    int cls[SPL];
+    unsigned skipA = 0, skipB = 0, validm = 0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = lane * SPL + j;
+        cls[j] = blank;
+        if (s < S) validm |= 1u << j;
+        if (s < S && (j & 1)) {
+            const int li = s >> 1;
+            cls[j] = lab[li];
+            if (li > 0 && lab[li] != lab[li - 1]) skipA |= 1u << j;
+            if (li + 1 < Ln && lab[li + 1] != lab[li]) skipB |= 1u << j;
+        }
+    }
+    const bool fwd = warp == 0;
+    const int h = p.grad ? Tb / 2 : Tb;                 // alpha owns frames [0, h) first, then [h, T_b); beta the reverse
+    float2 *rows_b = p.rows + (size_t)b * p.T * RS + (size_t)lane * SPL;        // row t at + t*RS
+    const float *logit_b = p.logits + (size_t)b * V + (lane < V ? lane : 0);
+    const float kLog2e = 1.4426950408889634f;
+
+    float2 a[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {     // virtual rows: alpha_{-1} = 1 at s = 0; beta_{T_b} = 1 at s = S-1
+        const int s = lane * SPL + j;
+        a[j] = (fwd ? s == 0 : s == S - 1) ? kOne : kZero;
+    }
+    float2 lp2 = kOne;
+    float inv_pm = 1.f;
+    int pe = 0;
+    double lz = 0.0;                                    // sum over my first-half frames of log2 Z_t
+    const int nsteps = (!fwd && !p.grad) ? 0 : Tb;
+    const int own_first = fwd ? h : Tb - h;             // steps of my walk before the hand-over
+    auto frame_of = [&](int n) { return fwd ? n : Tb - 1 - n; };
+    // prefetch of step i into ring slot i % kPF: the frame's logits (lane k: class k) and, in the second half, the
+    // other warp's row of that frame (each lane its own SPL states); one cp.async group per step
+    auto issue = [&](int i, bool with_row) {
+        if (i < nsteps) {
+            unsigned char *slot = ring + (size_t)(i % kPF) * SLOT;
+            const int t = frame_of(i);
+            if (lane < V) cp_async4(slot + lane * 4, logit_b + (size_t)t * gstride);
+            if (with_row) {
+                const float4 *src = reinterpret_cast<const float4 *>(rows_b + (size_t)t * RS);
+                float4 *dst = reinterpret_cast<float4 *>(slot + 128 + (size_t)lane * SPL * 8);
+#pragma unroll
+                for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q, src + q);
+            }
+        }
+        cp_async_commit();
+    };
+    for (int i = 0; i < kPF; ++i) issue(i, false);
+    for (int n = 0; n <= nsteps; ++n) {
+        if (n == own_first) {
+            // ---- hand-over: both warps have finished their first half -----------------------------
+            if (p.grad || fwd) {
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) hand[(size_t)warp * (RS + 4) + lane * SPL + j] = a[j];
+                if (lane == 0) hand_lz[warp] = lz;
+            } else if (lane == 0) {
+                hand_lz[warp] = 0.0;
+            }
+            __syncthreads();
+            // p' = sum_s alpha'_{h-1}(s) (beta'_h(s) + beta'_h(s+1) + [skip] beta'_h(s+2)); without a gradient h = T_b and beta_h is the virtual row
+            const float2 *ha = hand, *hb = hand + (RS + 4);
+            float2 acc = kZero;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                const int s = lane * SPL + j;
+                float2 b0 = hb[s], b1 = hb[s + 1], b2 = (skipB >> j) & 1 ? hb[s + 2] : kZero;
+                if (!p.grad) { b0 = s == S - 1 ? kOne : kZero; b1 = s + 1 == S - 1 ? kOne : kZero; b2 = kZero; }
+                acc = xf_add(acc, xf_mul(ha[s], xf_sum3_mul(b0, b1, b2, kOne)));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = xf_add(acc, shfl2(acc, lane ^ o));
+            lp2 = acc;
+            inv_pm = 1.f / lp2.x;
+            pe = xf_e(lp2);
+            if (tid == 0) {     // the rows are un-normalised (y' = exp(x)): p = p' / prod_t Z_t
+                p.loss[b] = (float)(-(xf_log2(lp2) - (hand_lz[0] + hand_lz[1])) * 0.6931471805599453);
+                p.status[b] = CTCASR_CTC_OK;
+            }
+            if (!p.grad) return;
+            // the other warp's rows of my next kPF frames (their logits are already in flight)
+            for (int i = n; i < n + kPF && i < nsteps; ++i) {
+                const float4 *src = reinterpret_cast<const float4 *>(rows_b + (size_t)frame_of(i) * RS);
+                float4 *dst = reinterpret_cast<float4 *>(ring + (size_t)(i % kPF) * SLOT + 128 + (size_t)lane * SPL * 8);
+#pragma unroll
+                for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q, src + q);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+        if (n == nsteps) break;
+        const int t = frame_of(n);
+        const bool second = n >= own_first;
+        // ---- frame t out of the ring ---------------------------------------------------------------
+        cp_async_wait<kPF - 1>();
+        const unsigned char *slot = ring + (size_t)(n % kPF) * SLOT;
+        const float x = lane < V ? *reinterpret_cast<const float *>(slot + lane * 4) : 0.f;
+        float4 o[SPL / 2];
+        if (second) {
+#pragma unroll
+            for (int q = 0; q < SPL / 2; ++q) o[q] = *reinterpret_cast<const float4 *>(slot + 128 + (size_t)lane * SPL * 8 + q * 16);
+        }
+        issue(n + kPF, second);             // rows only once the other warp has written them (after the hand-over)
+        // ---- y'_k = exp(x_k) as (m, e): no normalisation on the recursion's path (a per-frame factor of all states
+        // cancels in the posteriors and is taken out of the loss through log2 Z_t) -----------------------
+        const float l2 = x * kLog2e;
+        const float fl = floorf(l2);
+        const float2 y = lane < V ? xf_make(ex2f(l2 - fl), (int)fl) : kZero;
+        const float2 yblank = shfl2(y, blank);
+        // ---- the two states beyond my own range: from the previous (alpha) / next (beta) lane ----
+        float2 n1, n2;
+        if (fwd) {
+            n1 = make_float2(__shfl_up_sync(0xffffffffu, a[SPL - 1].x, 1), __shfl_up_sync(0xffffffffu, a[SPL - 1].y, 1));
+            n2 = make_float2(__shfl_up_sync(0xffffffffu, a[SPL - 2].x, 1), __shfl_up_sync(0xffffffffu, a[SPL - 2].y, 1));
+            if (lane == 0) { n1 = kZero; n2 = kZero; }
+        } else {
+            n1 = make_float2(__shfl_down_sync(0xffffffffu, a[0].x, 1), __shfl_down_sync(0xffffffffu, a[0].y, 1));
+            n2 = make_float2(__shfl_down_sync(0xffffffffu, a[1].x, 1), __shfl_down_sync(0xffffffffu, a[1].y, 1));
+            if (lane == 31) { n1 = kZero; n2 = kZero; }
+        }
+        float2 nw[SPL], ys[SPL];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const float2 yl = (j & 1) ? shfl2(y, cls[j]) : yblank;
+            ys[j] = (validm >> j) & 1 ? yl : kZero;
+            float2 s1, s2;
+            if (fwd) {
+                s1 = j >= 1 ? a[j - 1] : n1;
+                s2 = j >= 2 ? a[j - 2] : (j == 1 ? n1 : n2);
+                s2 = (skipA >> j) & 1 ? s2 : kZero;
+            } else {
+                s1 = j + 1 < SPL ? a[j + 1] : n1;
+                s2 = j + 2 < SPL ? a[j + 2] : (j + 1 < SPL ? n1 : n2);
+                s2 = (skipB >> j) & 1 ? s2 : kZero;
+            }
+            nw[j] = xf_sum3_mul(a[j], s1, s2, ys[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) a[j] = nw[j];
+        // ---- Z_t = sum_k y'_k, off the recursion's path: for the loss (first half) and the softmax of the gradient ----
+        // (integer warp reductions — one redux.sync each — instead of shuffle trees: every dependent shuffle is ~25 cycles of
+        // an in-order warp that has no other warp to hide behind; fixed point keeps the sums order-independent)
+        const int emax = __reduce_max_sync(0xffffffffu, lane < V ? xf_e(y) : kZE);
+        const float yrel = lane < V ? y.x * pow2_le0(xf_e(y) - emax) : 0.f;                                  // [0, 2)
+        const float zs = (float)__reduce_add_sync(0xffffffffu, __float2uint_rn(yrel * 4194304.f)) * (1.f / 4194304.f);   // 2^22: 32 x 2 x 2^22 < 2^32
+        if (!second) {
+            lz += (double)emax + (double)lg2f(zs);
+            // ---- first half: spill my row ---------------------------------------------------------
+            float4 *dst = reinterpret_cast<float4 *>(rows_b + (size_t)t * RS);
+#pragma unroll
+            for (int q = 0; q < SPL / 2; ++q) __stcg(dst + q, make_float4(a[2 * q].x, a[2 * q].y, a[2 * q + 1].x, a[2 * q + 1].y));
+        } else {
+            // ---- second half: posteriors from my row and the other warp's row of frame t, gradient row ----
+            // per-class sums of the posteriors in fixed point (2^-24): integer adds commute, so shared-memory atomics give
+            // the same bits in any order; lane k then owns class k
+            unsigned *cacc = reinterpret_cast<unsigned *>(postbuf) + (size_t)(n & 1) * 32;
+            unsigned pblank = 0;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                const float2 ot = (j & 1) ? make_float2(o[j / 2].z, o[j / 2].w) : make_float2(o[j / 2].x, o[j / 2].y);
+                float post = 0.f;                       // alpha * beta / (y * p): both rows include y_t
+                if (a[j].x != 0.f && ot.x != 0.f)
+                    post = __fdividef(a[j].x * ot.x, ys[j].x) * inv_pm * pow2_clamp(xf_e(a[j]) + xf_e(ot) - xf_e(ys[j]) - pe);
+                const unsigned q = __float2uint_rn(fminf(post, 1.f) * 16777216.f);
+                if (j & 1) { if (q) atomicAdd(cacc + cls[j], q); }
+                else pblank += q;
+            }
+            pblank = __reduce_add_sync(0xffffffffu, pblank);        // <= 2^24 in total (the posteriors of a frame sum to 1)
+            __syncwarp();
+            if (lane < V) {
+                const unsigned q = lane == blank ? pblank : cacc[lane];
+                cacc[lane] = 0;                                     // this buffer is used again two frames later
+                grad_b[(size_t)t * gstride + lane] = (__fdividef(yrel, zs) - (float)q * (1.f / 16777216.f)) * p.grad_scale;
+            }
+        }
+    }
+}
+
+struct Plan { int CH, RS, GT, NCH, VP, SPT, SPL; size_t smem, ws_total; };
 
 static int make_plan(int T, int B, int V, int Lmax, Plan *pl)
 {
     const int S = 2 * Lmax + 1;
     if (V < 1 || V > 128) return fail(CTCASR_ERR_UNSUPPORTED, "ctc: num_classes %d > 128", V);
+    // the warp-shuffle kernel: SPL lattice states per lane (0 = not eligible: the block kernel below)
+    static const int force_block = getenv("CTCASR_CTC_BLOCK") != nullptr;
+    pl->SPL = (V <= 32 && S <= 384 && !force_block) ? (S <= 64 ? 2 : (S <= 192 ? 6 : 12)) : 0;
     // Many utterances (more CTAs than SMs): the kernel is bound by instruction issue, so two lattice states
     // per thread — half the warps, the per-step addressing / barrier / loop overhead shared by two states,
     // and 64 registers per thread at 4 CTAs per SM instead of 32 with spills.  Few utterances: one state per
@@ -491,6 +810,10 @@ static int make_plan(int T, int B, int V, int Lmax, Plan *pl)
     pl->NCH = T > 0 ? (T + pl->CH - 1) / pl->CH : 1;
     pl->smem = SmemLayout(Lmax, V, pl->RS, pl->CH, pl->VP).total;
     pl->ws_total = align_up((size_t)B * pl->NCH * pl->RS * sizeof(float2), 256);
+    if (pl->SPL) {
+        const size_t rows = align_up((size_t)B * (T > 0 ? T : 1) * 32 * pl->SPL * sizeof(float2), 256);
+        if (rows > pl->ws_total) pl->ws_total = rows;
+    }
     return CTCASR_OK;
 }
 
@@ -523,6 +846,7 @@ extern "C" int ctcasr_ctc_loss(const float *logits, int T, int B, int V, int bla
     p.labels = labels; p.lstride = label_stride; p.label_len = label_len; p.seq_len = seq_len;
     p.loss = loss; p.grad = grad; p.grad_scale = grad_scale; p.status = status;
     p.ckpt = reinterpret_cast<float2 *>(ws);
+    p.rows = reinterpret_cast<float2 *>(ws);
     p.CH = pl.CH; p.RS = pl.RS; p.GT = pl.GT; p.NCH = pl.NCH; p.Lmax = max_label_len; p.VP = pl.VP;
     // three instantiations: one state per thread at high occupancy (the common case, S <= 224),
     // one state per thread up to S = 448, and the generic strided variant for longer labels
@@ -539,6 +863,23 @@ extern "C" int ctcasr_ctc_loss(const float *logits, int T, int B, int V, int bla
         return CTCASR_OK;
     };
     static size_t set0 = 0, set1 = 0, set2 = 0, set3 = 0;
+    if (pl.SPL) {       // two warps per utterance, alpha and beta walking towards each other
+        const size_t wsmem = ctc::WarpSmem(max_label_len, V, 32 * pl.SPL).total;
+        static size_t wset[3] = {0, 0, 0};
+        auto wlaunch = [&](auto kernel, size_t &smem_set) -> int {
+            if (wsmem > 48 * 1024 && wsmem > smem_set) {
+                CTCASR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                smem_set = wsmem;
+            }
+            ProfScope prof(PROF_CTC, (cudaStream_t)stream);
+            kernel<<<B, 64, wsmem, (cudaStream_t)stream>>>(p);
+            CTCASR_LAUNCH_CHECK();
+            return CTCASR_OK;
+        };
+        if (pl.SPL == 2) return wlaunch(ctc::ctc_warp_kernel<2>, wset[0]);
+        if (pl.SPL == 6) return wlaunch(ctc::ctc_warp_kernel<6>, wset[1]);
+        return wlaunch(ctc::ctc_warp_kernel<12>, wset[2]);
+    }
     if (pl.SPT == 2 && S <= 2 * pl.GT && NT <= 288) return launch(ctc::ctc_loss_kernel<2, 288, 4>, set3);
     if (S <= pl.GT && NT <= 480) return launch(ctc::ctc_loss_kernel<1, 480, 4>, set0);
     if (S <= pl.GT) return launch(ctc::ctc_loss_kernel<1, 2 * ctc::kMaxGT + ctc::kHelper, 1>, set1);

@@ -100,7 +100,7 @@ def test_csv_wav_corpus_to_train_step(tmp_path, target):
     csv_path = _write_corpus(str(tmp_path))
     flags = types.SimpleNamespace(train_csv=csv_path, dev_csv=csv_path, test_csv=csv_path, corpus_dir=str(tmp_path / "corpus"),
                                   batch_size=4, num_buckets=4, feature_type="mfcc", feature_normalization="local")
-    cfg = CFG.replace(learning_rate=2e-3, cudnn=True, rnn_cell="rnn_relu", compute="bf16x3", num_units_rnn=256)
+    cfg = CFG.replace(learning_rate=3e-4, compute="bf16x3", num_units_rnn=128)
     model = CTCModel(cfg, seed=1)
     input_fn = ip.input_fn_generator(target, flags, seed=1)
     epoch_loss = []
