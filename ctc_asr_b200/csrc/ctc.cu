@@ -544,6 +544,226 @@ __device__ __forceinline__ int warp_max_int(int v)
     return v;
 }
 
+// ---- arithmetic of the warp kernel: "probability zero" is the ordinary number 1.0 x 2^kZE (kZE = -2^29): it drops out
+// of every sum through the exponent clamp below and stays ~kZE through thousands of products, so neither the recursion
+// nor the posteriors need a zero test or a select on the mantissa.
+// x * 2^d for x in [1, 2), d <= 0: one integer multiply-add on the exponent field, 2^-127 (flushed) at the clamp
+__device__ __forceinline__ float scale_le0(float x, int d) { return __int_as_float(__float_as_int(x) + (max(d, -127) << 23)); }
+// (a0 + a1 + a2) * y with a2 optional; every mantissa is in [1, 2)
+template <bool THREE>
+__device__ __forceinline__ float2 xf_step(const float2 a0, const float2 a1, const float a2m, const int e2, const float2 y)
+{
+    const int e0 = xf_e(a0), e1 = xf_e(a1);
+    const int em = THREE ? max(e0, max(e1, e2)) : max(e0, e1);
+    float s = scale_le0(a0.x, e0 - em) + scale_le0(a1.x, e1 - em);
+    if (THREE) s += scale_le0(a2m, e2 - em);
+    s *= y.x;                                       // [1, 12)
+    const int bits = __float_as_int(s);
+    // (the clamp keeps a zero times a zero at kZE: exponents must not walk towards the integer range's end)
+    return xf_make(__int_as_float((bits & 0x007fffff) | 0x3f800000), max(em + xf_e(y) + (bits >> 23) - 127, kZE));
+}
+
+// one direction of the warp kernel: FWD = alpha (frames ascending), !FWD = beta (frames descending)
+template <int SPL, bool FWD>
+__device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_raw, const WarpSmem &L, int b, int lane, int Tb, int Ln)
+{
+    constexpr int RS = 32 * SPL;
+    constexpr size_t SLOT = 128 + (size_t)RS * 8;
+    constexpr int warp = FWD ? 0 : 1;
+    const int V = p.V, blank = p.blank, S = 2 * Ln + 1;
+    const float2 kZero = xf_make(1.f, kZE), kOne = xf_make(1.f, 0);     // zero = 1.0 x 2^kZE, see xf_step
+    const int *lab = reinterpret_cast<const int *>(smem_raw + L.lab);
+    float2 *hand = reinterpret_cast<float2 *>(smem_raw + L.hand);             // [2][RS + 4]
+    double *hand_lz = reinterpret_cast<double *>(smem_raw + L.hand + (size_t)2 * (RS + 4) * 8);
+    unsigned *postrow = reinterpret_cast<unsigned *>(smem_raw + L.post) + (size_t)warp * 2 * RS;      // [2 buffers][RS] fixed-point posteriors
+    const int *csr_start = reinterpret_cast<const int *>(smem_raw + L.csr_start), *csr_pos = reinterpret_cast<const int *>(smem_raw + L.csr_pos);
+    unsigned char *ring = smem_raw + L.ring + (size_t)warp * kPF * SLOT;
+    float *grad_b = p.grad ? p.grad + (size_t)b * V : nullptr;                 // row t at + t*B*V
+    const size_t gstride = (size_t)p.B * V;
+
+    // ---- per-lane lattice constants: SPL is even, so state j of a lane is a blank for even j, a label for odd j ----
+    int cls[SPL];
+    unsigned skip = 0, validm = 0;      // skip: the s-2 (alpha) / s+2 (beta) transition exists
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = lane * SPL + j;
+        cls[j] = blank;
+        if (s < S) validm |= 1u << j;
+        if (s < S && (j & 1)) {
+            const int li = s >> 1;
+            cls[j] = lab[li];
+            if (FWD ? (li > 0 && lab[li] != lab[li - 1]) : (li + 1 < Ln && lab[li + 1] != lab[li])) skip |= 1u << j;
+        }
+    }
+    unsigned skipB = 0;                 // the beta-side skips are also needed at the hand-over
+#pragma unroll
+    for (int j = 1; j < SPL; j += 2) {
+        const int s = lane * SPL + j, li = s >> 1;
+        if (s < S && li + 1 < Ln && lab[li + 1] != lab[li]) skipB |= 1u << j;
+    }
+
+    const int h = p.grad ? Tb / 2 : Tb;                 // alpha owns frames [0, h) first, then [h, T_b); beta the reverse
+    float2 *rows_b = p.rows + (size_t)b * p.T * RS + (size_t)lane * SPL;        // row t at + t*RS
+    const float *logit_b = p.logits + (size_t)b * V + (lane < V ? lane : 0);
+    const float kLog2e = 1.4426950408889634f;
+
+    float2 a[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {     // virtual rows: alpha_{-1} = 1 at s = 0; beta_{T_b} = 1 at s = S-1
+        const int s = lane * SPL + j;
+        a[j] = (FWD ? s == 0 : s == S - 1) ? kOne : kZero;
+    }
+    double lz = 0.0;                                    // sum over my first-half frames of log2 Z_t
+    const int nsteps = (!FWD && !p.grad) ? 0 : Tb;
+    const int own_first = FWD ? h : Tb - h;             // steps of my walk before the hand-over
+    auto frame_of = [&](int n) { return FWD ? n : Tb - 1 - n; };
+    // prefetch of step i into ring slot i % kPF: the frame's logits (lane k: class k) and, in the second half, the
+    // other warp's row of that frame (each lane its own SPL states); one cp.async group per step
+    auto issue = [&](int i, bool with_row) {
+        if (i < nsteps) {
+            unsigned char *slot = ring + (size_t)(i % kPF) * SLOT;
+            const int t = frame_of(i);
+            if (lane < V) cp_async4(slot + lane * 4, logit_b + (size_t)t * gstride);
+            if (with_row) {
+                const float4 *src = reinterpret_cast<const float4 *>(rows_b + (size_t)t * RS);
+                float4 *dst = reinterpret_cast<float4 *>(slot + 128 + (size_t)lane * SPL * 8);
+#pragma unroll
+                for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q, src + q);
+            }
+        }
+        cp_async_commit();
+    };
+    // one recursion step on frame n of my walk; returns y' of my lane's class, the per-state y' and this frame's Z pieces
+    float2 ys[SPL];
+    float yrel, zs;
+    int emax;
+    float4 o[SPL / 2];
+    auto step = [&](int n, bool second) {
+        cp_async_wait<kPF - 1>();
+        const unsigned char *slot = ring + (size_t)(n % kPF) * SLOT;
+        const float x = lane < V ? *reinterpret_cast<const float *>(slot + lane * 4) : 0.f;
+        if (second) {
+#pragma unroll
+            for (int q = 0; q < SPL / 2; ++q) o[q] = *reinterpret_cast<const float4 *>(slot + 128 + (size_t)lane * SPL * 8 + q * 16);
+        }
+        issue(n + kPF, second);         // rows only once the other warp has written them (after the hand-over)
+        // y'_k = exp(x_k) as (m, e): no normalisation on the recursion's path (a per-frame factor of all states cancels in
+        // the posteriors and is taken out of the loss through log2 Z_t)
+        const float l2 = x * kLog2e;
+        const float fl = floorf(l2);
+        const float2 y = (lane < V && l2 > -1e9f) ? xf_make(ex2f(l2 - fl), (int)fl) : kZero;      // logit -inf: probability zero
+        const float2 yblank = shfl2(y, blank);
+        // the two states beyond my own range: from the previous (alpha) / next (beta) lane
+        float2 n1, n2;
+        if (FWD) {
+            n1 = make_float2(__shfl_up_sync(0xffffffffu, a[SPL - 1].x, 1), __shfl_up_sync(0xffffffffu, a[SPL - 1].y, 1));
+            n2 = make_float2(__shfl_up_sync(0xffffffffu, a[SPL - 2].x, 1), __shfl_up_sync(0xffffffffu, a[SPL - 2].y, 1));
+            if (lane == 0) { n1.y = kZero.y; n2.y = kZero.y; }
+        } else {
+            n1 = make_float2(__shfl_down_sync(0xffffffffu, a[0].x, 1), __shfl_down_sync(0xffffffffu, a[0].y, 1));
+            n2 = make_float2(__shfl_down_sync(0xffffffffu, a[1].x, 1), __shfl_down_sync(0xffffffffu, a[1].y, 1));
+            if (lane == 31) { n1.y = kZero.y; n2.y = kZero.y; }
+        }
+        float2 nw[SPL];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const float2 yl = (j & 1) ? shfl2(y, cls[j]) : yblank;
+            ys[j] = make_float2(yl.x, (validm >> j) & 1 ? yl.y : kZero.y);          // states beyond 2L+1: exponent -> kZE
+            const float2 s1 = FWD ? (j >= 1 ? a[j - 1] : n1) : (j + 1 < SPL ? a[j + 1] : n1);
+            if (j & 1) {        // label state: the skip transition exists when the neighbouring labels differ
+                const float2 s2 = FWD ? (j >= 2 ? a[j - 2] : n1) : (j + 2 < SPL ? a[j + 2] : n2);      // j is odd: s-2 of j = 1 is the previous lane's last state
+                nw[j] = xf_step<true>(a[j], s1, s2.x, (skip >> j) & 1 ? xf_e(s2) : kZE, ys[j]);
+            } else {            // blank state: never skipped into
+                nw[j] = xf_step<false>(a[j], s1, 1.f, kZE, ys[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) a[j] = nw[j];
+        // Z_t = sum_k y'_k, off the recursion's path: for the loss (first half) and the softmax of the gradient.
+        // (integer warp reductions — one redux.sync each — instead of shuffle trees: every dependent shuffle is ~25 cycles of
+        // an in-order warp that has no other warp to hide behind; fixed point keeps the sums order-independent)
+        emax = __reduce_max_sync(0xffffffffu, lane < V ? xf_e(y) : kZE);
+        yrel = lane < V ? scale_le0(y.x, xf_e(y) - emax) : 0.f;     // (2^-127 at the clamp: nothing at 2^-22 resolution)                                           // [0, 2)
+        zs = (float)__reduce_add_sync(0xffffffffu, __float2uint_rn(yrel * 4194304.f)) * (1.f / 4194304.f);      // 2^22: 32 x 2 x 2^22 < 2^32
+    };
+
+    for (int i = 0; i < kPF; ++i) issue(i, false);
+    // ---- first half: recursion, spill my rows -----------------------------------------------------------
+    for (int n = 0; n < own_first; ++n) {
+        step(n, false);
+        lz += (double)emax + (double)lg2f(zs);
+        float4 *dst = reinterpret_cast<float4 *>(rows_b + (size_t)frame_of(n) * RS);
+#pragma unroll
+        for (int q = 0; q < SPL / 2; ++q) __stcg(dst + q, make_float4(a[2 * q].x, a[2 * q].y, a[2 * q + 1].x, a[2 * q + 1].y));
+    }
+    // ---- hand-over: both warps have finished their first half ------------------------------------------------
+    if (p.grad || FWD) {
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) hand[(size_t)warp * (RS + 4) + lane * SPL + j] = a[j];
+    }
+    if (lane == 0) hand_lz[warp] = lz;
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    // p' = sum_s alpha'_{h-1}(s) (beta'_h(s) + beta'_h(s+1) + [skip] beta'_h(s+2)); without a gradient h = T_b and beta_h is the virtual row
+    float2 lp2;
+    {
+        const float2 *ha = hand, *hb = hand + (RS + 4);
+        float2 acc = kZero;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int s = lane * SPL + j;
+            float2 b0 = hb[s], b1 = hb[s + 1], b2 = (skipB >> j) & 1 ? hb[s + 2] : kZero;
+            if (!p.grad) { b0 = s == S - 1 ? kOne : kZero; b1 = s + 1 == S - 1 ? kOne : kZero; b2 = kZero; }
+            acc = xf_add(acc, xf_mul(ha[s], xf_sum3_mul(b0, b1, b2, kOne)));
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) acc = xf_add(acc, shfl2(acc, lane ^ o2));
+        lp2 = acc;
+    }
+    const float inv_pm = 1.f / lp2.x;
+    const int pe = xf_e(lp2);
+    if (FWD && lane == 0) {     // the rows are un-normalised (y' = exp(x)): p = p' / prod_t Z_t
+        p.loss[b] = (float)(-(xf_log2(lp2) - (hand_lz[0] + hand_lz[1])) * 0.6931471805599453);
+        p.status[b] = CTCASR_CTC_OK;
+    }
+    if (!p.grad) return;
+    // the other warp's rows of my next kPF frames (their logits are already in flight)
+    for (int i = own_first; i < own_first + kPF && i < nsteps; ++i) {
+        const float4 *src = reinterpret_cast<const float4 *>(rows_b + (size_t)frame_of(i) * RS);
+        float4 *dst = reinterpret_cast<float4 *>(ring + (size_t)(i % kPF) * SLOT + 128 + (size_t)lane * SPL * 8);
+#pragma unroll
+        for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q, src + q);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    // ---- second half: posteriors from my row and the other warp's row of the frame, gradient row ----------------
+    for (int n = own_first; n < nsteps; ++n) {
+        step(n, true);
+        // per-class sums of the posteriors in fixed point (2^-24, integer adds commute: any order gives the same bits):
+        // the label states' values go through a shared-memory row, lane k gathers the positions of class k
+        unsigned *prow = postrow + (size_t)(n & 1) * RS;
+        unsigned pblank = 0;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const float2 ot = (j & 1) ? make_float2(o[j / 2].z, o[j / 2].w) : make_float2(o[j / 2].x, o[j / 2].y);
+            // alpha * beta / (y * p): both rows include y_t; a zero operand has exponent ~kZE and clamps the factor to 0
+            const float post = __fdividef(a[j].x * ot.x, ys[j].x) * inv_pm * pow2_clamp(xf_e(a[j]) + xf_e(ot) - xf_e(ys[j]) - pe);
+            const unsigned q = __float2uint_rn(fminf(post, 1.f) * 16777216.f);
+            if (j & 1) prow[lane * SPL + j] = q;
+            else pblank += q;
+        }
+        pblank = __reduce_add_sync(0xffffffffu, pblank);        // <= 2^24 in total (the posteriors of a frame sum to 1)
+        __syncwarp();
+        if (lane < V) {
+            unsigned q = pblank;
+            if (lane != blank) {
+                q = 0;
+                for (int i = csr_start[lane]; i < csr_start[lane + 1]; ++i) q += prow[csr_pos[i]];
+            }
+            grad_b[(size_t)frame_of(n) * gstride + lane] = (__fdividef(yrel, zs) - (float)q * (1.f / 16777216.f)) * p.grad_scale;
+        }
+    }
+}
+
 template <int SPL>
 __global__ void __launch_bounds__(64)
 ctc_warp_kernel(const Params p)
@@ -552,17 +772,12 @@ ctc_warp_kernel(const Params p)
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = p.V, blank = p.blank;
     constexpr int RS = 32 * SPL;
-    constexpr size_t SLOT = 128 + (size_t)RS * 8;
-    const float2 kZero = xf_make(0.f, kZE), kOne = xf_make(1.f, 0);
     const WarpSmem L(p.Lmax, V, RS);
     int *lab = reinterpret_cast<int *>(smem_raw + L.lab);
     float2 *hand = reinterpret_cast<float2 *>(smem_raw + L.hand);             // [2][RS + 4]
-    double *hand_lz = reinterpret_cast<double *>(smem_raw + L.hand + (size_t)2 * (RS + 4) * 8);
-    float *postbuf = reinterpret_cast<float *>(smem_raw + L.post) + (size_t)warp * 2 * RS;
-    unsigned char *ring = smem_raw + L.ring + (size_t)warp * kPF * SLOT;
     int *flags = reinterpret_cast<int *>(smem_raw + L.total - 32);
 
-    const int Tb = p.seq_len[b], Ln = p.label_len[b], S = 2 * Ln + 1;
+    const int Tb = p.seq_len[b], Ln = p.label_len[b];
     float *grad_b = p.grad ? p.grad + (size_t)b * V : nullptr;                 // row t at + t*B*V
     const size_t gstride = (size_t)p.B * V;
 
@@ -596,190 +811,19 @@ ctc_warp_kernel(const Params p)
         if (tid == 0) { p.status[b] = status; p.loss[b] = status == CTCASR_CTC_OK ? 0.f : INFINITY; }
         return;
     }
-    for (int i = tid; i < 2 * (RS + 4); i += 64) hand[i] = kZero;
+    for (int i = tid; i < 2 * (RS + 4); i += 64) hand[i] = xf_make(1.f, kZE);        // zero of the warp kernel's arithmetic
+    if (tid == 32) {    // per-class position lists of the label states (odd s), in label order
+        int *csr_start = reinterpret_cast<int *>(smem_raw + L.csr_start), *csr_pos = reinterpret_cast<int *>(smem_raw + L.csr_pos);
+        for (int k = 0; k <= V; ++k) csr_start[k] = 0;
+        for (int i = 0; i < Ln; ++i) csr_start[lab[i] + 1]++;
+        for (int k = 0; k < V; ++k) csr_start[k + 1] += csr_start[k];
+        int cursor[32];
+        for (int k = 0; k < V; ++k) cursor[k] = csr_start[k];
+        for (int i = 0; i < Ln; ++i) csr_pos[cursor[lab[i]]++] = 2 * i + 1;
+    }
     __syncthreads();
-    reinterpret_cast<unsigned *>(postbuf)[lane] = 0;            // class accumulators [2 buffers][32] of my warp
-    reinterpret_cast<unsigned *>(postbuf)[32 + lane] = 0;
-    __syncwarp();
-
-    // ---- per-lane lattice constants: SPL is even, so state j of a lane is a blank for even j, a label for odd j ----
-    int cls[SPL];
-    unsigned skipA = 0, skipB = 0, validm = 0;
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-        const int s = lane * SPL + j;
-        cls[j] = blank;
-        if (s < S) validm |= 1u << j;
-        if (s < S && (j & 1)) {
-            const int li = s >> 1;
-            cls[j] = lab[li];
-            if (li > 0 && lab[li] != lab[li - 1]) skipA |= 1u << j;
-            if (li + 1 < Ln && lab[li + 1] != lab[li]) skipB |= 1u << j;
-        }
-    }
-    const bool fwd = warp == 0;
-    const int h = p.grad ? Tb / 2 : Tb;                 // alpha owns frames [0, h) first, then [h, T_b); beta the reverse
-    float2 *rows_b = p.rows + (size_t)b * p.T * RS + (size_t)lane * SPL;        // row t at + t*RS
-    const float *logit_b = p.logits + (size_t)b * V + (lane < V ? lane : 0);
-    const float kLog2e = 1.4426950408889634f;
-
-    float2 a[SPL];
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) {     // virtual rows: alpha_{-1} = 1 at s = 0; beta_{T_b} = 1 at s = S-1
-        const int s = lane * SPL + j;
-        a[j] = (fwd ? s == 0 : s == S - 1) ? kOne : kZero;
-    }
-    float2 lp2 = kOne;
-    float inv_pm = 1.f;
-    int pe = 0;
-    double lz = 0.0;                                    // sum over my first-half frames of log2 Z_t
-    const int nsteps = (!fwd && !p.grad) ? 0 : Tb;
-    const int own_first = fwd ? h : Tb - h;             // steps of my walk before the hand-over
-    auto frame_of = [&](int n) { return fwd ? n : Tb - 1 - n; };
-    // prefetch of step i into ring slot i % kPF: the frame's logits (lane k: class k) and, in the second half, the
-    // other warp's row of that frame (each lane its own SPL states); one cp.async group per step
-    auto issue = [&](int i, bool with_row) {
-        if (i < nsteps) {
-            unsigned char *slot = ring + (size_t)(i % kPF) * SLOT;
-            const int t = frame_of(i);
-            if (lane < V) cp_async4(slot + lane * 4, logit_b + (size_t)t * gstride);
-            if (with_row) {
-                const float4 *src = reinterpret_cast<const float4 *>(rows_b + (size_t)t * RS);
-                float4 *dst = reinterpret_cast<float4 *>(slot + 128 + (size_t)lane * SPL * 8);
-#pragma unroll
-                for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q, src + q);
-            }
-        }
-        cp_async_commit();
-    };
-    for (int i = 0; i < kPF; ++i) issue(i, false);
-    for (int n = 0; n <= nsteps; ++n) {
-        if (n == own_first) {
-            // ---- hand-over: both warps have finished their first half -----------------------------
-            if (p.grad || fwd) {
-#pragma unroll
-                for (int j = 0; j < SPL; ++j) hand[(size_t)warp * (RS + 4) + lane * SPL + j] = a[j];
-                if (lane == 0) hand_lz[warp] = lz;
-            } else if (lane == 0) {
-                hand_lz[warp] = 0.0;
-            }
-            __syncthreads();
-            // p' = sum_s alpha'_{h-1}(s) (beta'_h(s) + beta'_h(s+1) + [skip] beta'_h(s+2)); without a gradient h = T_b and beta_h is the virtual row
-            const float2 *ha = hand, *hb = hand + (RS + 4);
-            float2 acc = kZero;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                const int s = lane * SPL + j;
-                float2 b0 = hb[s], b1 = hb[s + 1], b2 = (skipB >> j) & 1 ? hb[s + 2] : kZero;
-                if (!p.grad) { b0 = s == S - 1 ? kOne : kZero; b1 = s + 1 == S - 1 ? kOne : kZero; b2 = kZero; }
-                acc = xf_add(acc, xf_mul(ha[s], xf_sum3_mul(b0, b1, b2, kOne)));
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc = xf_add(acc, shfl2(acc, lane ^ o));
-            lp2 = acc;
-            inv_pm = 1.f / lp2.x;
-            pe = xf_e(lp2);
-            if (tid == 0) {     // the rows are un-normalised (y' = exp(x)): p = p' / prod_t Z_t
-                p.loss[b] = (float)(-(xf_log2(lp2) - (hand_lz[0] + hand_lz[1])) * 0.6931471805599453);
-                p.status[b] = CTCASR_CTC_OK;
-            }
-            if (!p.grad) return;
-            // the other warp's rows of my next kPF frames (their logits are already in flight)
-            for (int i = n; i < n + kPF && i < nsteps; ++i) {
-                const float4 *src = reinterpret_cast<const float4 *>(rows_b + (size_t)frame_of(i) * RS);
-                float4 *dst = reinterpret_cast<float4 *>(ring + (size_t)(i % kPF) * SLOT + 128 + (size_t)lane * SPL * 8);
-#pragma unroll
-                for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q, src + q);
-            }
-            cp_async_commit();
-            cp_async_wait<0>();
-        }
-        if (n == nsteps) break;
-        const int t = frame_of(n);
-        const bool second = n >= own_first;
-        // ---- frame t out of the ring ---------------------------------------------------------------
-        cp_async_wait<kPF - 1>();
-        const unsigned char *slot = ring + (size_t)(n % kPF) * SLOT;
-        const float x = lane < V ? *reinterpret_cast<const float *>(slot + lane * 4) : 0.f;
-        float4 o[SPL / 2];
-        if (second) {
-#pragma unroll
-            for (int q = 0; q < SPL / 2; ++q) o[q] = *reinterpret_cast<const float4 *>(slot + 128 + (size_t)lane * SPL * 8 + q * 16);
-        }
-        issue(n + kPF, second);             // rows only once the other warp has written them (after the hand-over)
-        // ---- y'_k = exp(x_k) as (m, e): no normalisation on the recursion's path (a per-frame factor of all states
-        // cancels in the posteriors and is taken out of the loss through log2 Z_t) -----------------------
-        const float l2 = x * kLog2e;
-        const float fl = floorf(l2);
-        const float2 y = lane < V ? xf_make(ex2f(l2 - fl), (int)fl) : kZero;
-        const float2 yblank = shfl2(y, blank);
-        // ---- the two states beyond my own range: from the previous (alpha) / next (beta) lane ----
-        float2 n1, n2;
-        if (fwd) {
-            n1 = make_float2(__shfl_up_sync(0xffffffffu, a[SPL - 1].x, 1), __shfl_up_sync(0xffffffffu, a[SPL - 1].y, 1));
-            n2 = make_float2(__shfl_up_sync(0xffffffffu, a[SPL - 2].x, 1), __shfl_up_sync(0xffffffffu, a[SPL - 2].y, 1));
-            if (lane == 0) { n1 = kZero; n2 = kZero; }
-        } else {
-            n1 = make_float2(__shfl_down_sync(0xffffffffu, a[0].x, 1), __shfl_down_sync(0xffffffffu, a[0].y, 1));
-            n2 = make_float2(__shfl_down_sync(0xffffffffu, a[1].x, 1), __shfl_down_sync(0xffffffffu, a[1].y, 1));
-            if (lane == 31) { n1 = kZero; n2 = kZero; }
-        }
-        float2 nw[SPL], ys[SPL];
-#pragma unroll
-        for (int j = 0; j < SPL; ++j) {
-            const float2 yl = (j & 1) ? shfl2(y, cls[j]) : yblank;
-            ys[j] = (validm >> j) & 1 ? yl : kZero;
-            float2 s1, s2;
-            if (fwd) {
-                s1 = j >= 1 ? a[j - 1] : n1;
-                s2 = j >= 2 ? a[j - 2] : (j == 1 ? n1 : n2);
-                s2 = (skipA >> j) & 1 ? s2 : kZero;
-            } else {
-                s1 = j + 1 < SPL ? a[j + 1] : n1;
-                s2 = j + 2 < SPL ? a[j + 2] : (j + 1 < SPL ? n1 : n2);
-                s2 = (skipB >> j) & 1 ? s2 : kZero;
-            }
-            nw[j] = xf_sum3_mul(a[j], s1, s2, ys[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < SPL; ++j) a[j] = nw[j];
-        // ---- Z_t = sum_k y'_k, off the recursion's path: for the loss (first half) and the softmax of the gradient ----
-        // (integer warp reductions — one redux.sync each — instead of shuffle trees: every dependent shuffle is ~25 cycles of
-        // an in-order warp that has no other warp to hide behind; fixed point keeps the sums order-independent)
-        const int emax = __reduce_max_sync(0xffffffffu, lane < V ? xf_e(y) : kZE);
-        const float yrel = lane < V ? y.x * pow2_le0(xf_e(y) - emax) : 0.f;                                  // [0, 2)
-        const float zs = (float)__reduce_add_sync(0xffffffffu, __float2uint_rn(yrel * 4194304.f)) * (1.f / 4194304.f);   // 2^22: 32 x 2 x 2^22 < 2^32
-        if (!second) {
-            lz += (double)emax + (double)lg2f(zs);
-            // ---- first half: spill my row ---------------------------------------------------------
-            float4 *dst = reinterpret_cast<float4 *>(rows_b + (size_t)t * RS);
-#pragma unroll
-            for (int q = 0; q < SPL / 2; ++q) __stcg(dst + q, make_float4(a[2 * q].x, a[2 * q].y, a[2 * q + 1].x, a[2 * q + 1].y));
-        } else {
-            // ---- second half: posteriors from my row and the other warp's row of frame t, gradient row ----
-            // per-class sums of the posteriors in fixed point (2^-24): integer adds commute, so shared-memory atomics give
-            // the same bits in any order; lane k then owns class k
-            unsigned *cacc = reinterpret_cast<unsigned *>(postbuf) + (size_t)(n & 1) * 32;
-            unsigned pblank = 0;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                const float2 ot = (j & 1) ? make_float2(o[j / 2].z, o[j / 2].w) : make_float2(o[j / 2].x, o[j / 2].y);
-                float post = 0.f;                       // alpha * beta / (y * p): both rows include y_t
-                if (a[j].x != 0.f && ot.x != 0.f)
-                    post = __fdividef(a[j].x * ot.x, ys[j].x) * inv_pm * pow2_clamp(xf_e(a[j]) + xf_e(ot) - xf_e(ys[j]) - pe);
-                const unsigned q = __float2uint_rn(fminf(post, 1.f) * 16777216.f);
-                if (j & 1) { if (q) atomicAdd(cacc + cls[j], q); }
-                else pblank += q;
-            }
-            pblank = __reduce_add_sync(0xffffffffu, pblank);        // <= 2^24 in total (the posteriors of a frame sum to 1)
-            __syncwarp();
-            if (lane < V) {
-                const unsigned q = lane == blank ? pblank : cacc[lane];
-                cacc[lane] = 0;                                     // this buffer is used again two frames later
-                grad_b[(size_t)t * gstride + lane] = (__fdividef(yrel, zs) - (float)q * (1.f / 16777216.f)) * p.grad_scale;
-            }
-        }
-    }
+    if (warp == 0) ctc_sweep<SPL, true>(p, smem_raw, L, b, lane, Tb, Ln);
+    else ctc_sweep<SPL, false>(p, smem_raw, L, b, lane, Tb, Ln);
 }
 
 struct Plan { int CH, RS, GT, NCH, VP, SPT, SPL; size_t smem, ws_total; };

@@ -302,13 +302,17 @@ class CTCModel:
         ops.adam(self.flat, self.adam_m, self.adam_v, self.grad_flat, self.global_step, cfg.learning_rate,
                  cfg.adam_beta1, cfg.adam_beta2, cfg.adam_epsilon, grad_scale)
 
-    def train_step(self, sequences, seq_length, labels, global_batch=None, allreduce=None, overlap=True):
+    def train_step(self, sequences, seq_length, labels, global_batch=None, allreduce=None, overlap=False):
         """model_fn's TRAIN branch (asr/model.py:53-54, 74, 79-83) on one batch.  Returns the loss as a 0-d device
         tensor.  Nothing in the step waits for the GPU: the checks the reference makes on its values (CTCLoss's
         InvalidArgumentError, NanTensorHook(loss) at asr/model.py:368) are made on the previous step's results when the
         next step starts, or by `check_step()`.
         allreduce(tensor, async_op=False): sums a slice of the flat gradient over the data-parallel ranks in place and,
-        with async_op=True, returns a handle with .wait() (torch.distributed semantics)."""
+        with async_op=True, returns a handle with .wait() (torch.distributed semantics).  overlap=True issues one
+        asynchronous all-reduce per `gradient_buckets()` range as soon as backward has produced it; the default is one
+        all-reduce after backward: measured on 2 x B200 at cfg2 the overlapped form is no faster (151.4 vs 151.0 ms/step) —
+        the collective's CTAs take SMs the persistent recurrence kernels of the next layer need all at once, which
+        start late by about the collective's duration (profiles/r2_multi_gpu.md)."""
         self.check_step()
         logits, seq_length = self.inference_fn(sequences, seq_length, training=True)
         loss = self.loss_fn(logits, seq_length, labels, global_batch=global_batch, defer_check=True)

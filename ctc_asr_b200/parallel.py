@@ -1,7 +1,8 @@
 """Data parallelism for the hot path: one process per GPU, equal shards, ONE all-reduce (sum) of the
-flat gradient buffer per step, issued as one asynchronous all-reduce per bucket of
+flat gradient buffer per step.  `overlap=True` issues it as one asynchronous all-reduce per bucket of
 `CTCModel.gradient_buckets()` (dense4 + logits, each RNN layer, the front-end) as soon as the backward pass has produced
-the bucket, so that the transfer runs under the backward pass of the layers below.  The reference is single-device
+the bucket; measured on B200 this is no faster than the single all-reduce after backward (the default), see
+CTCModel.train_step.  The reference is single-device
 (`train_distribute=None`, asr/train.py:41); this is the only collective the path needs, so the
 plumbing is `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) and nothing else.
 
@@ -55,7 +56,7 @@ def allreduce_mean_loss(local_loss_sum_over_global_batch, group=None):
     return t[0]
 
 
-def train_step(model, sequences, seq_length, labels, label_length, group=None, interleave=False, overlap=True):
+def train_step(model, sequences, seq_length, labels, label_length, group=None, interleave=False, overlap=False):
     """One data-parallel step of `CTCModel` on this rank's shard of the global batch."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
