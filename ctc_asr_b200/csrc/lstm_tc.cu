@@ -56,13 +56,15 @@ template <int PIECES> struct Ring {
     static constexpr int BARS = 1024;
     static constexpr int SMEM = NSTAGE * STAGE + XCH + 1024 + BARS;
 };
-// PIECES = 1 runs two rings: NSA stages of streamed weight tiles (16 KB each; the k-blocks resident in tensor memory
-// never enter it, so the producer prefetches a whole ring of the next step's tiles during the serial tail of this
-// one) and NSB stages of state tiles (4 KB).  A step visits the streamed k-blocks first, then the resident ones.
+// PIECES = 1 runs two rings whose stages hold GK = 2 consecutive k-blocks: NSA stages of streamed weight tiles (2 x 16
+// KB; the k-blocks resident in tensor memory never enter it, so the producer prefetches a whole ring of the next
+// step's tiles during the serial tail of this one) and NSB stages of state tiles (2 x 4 KB).  A step visits the
+// streamed k-blocks first, then the resident ones.  Two k-blocks per barrier because a (satisfied) mbarrier wait and
+// a commit cost the issuing thread as much as three of its 45-cycle MMAs (tools/ubench/mma_loop.cu).
 // (One shared ring, or all state tiles in one burst with a 5-stage weight ring, kept too few bytes in flight: the step
 // was bound by TMA latency per ring turn, 7.2 of 12.6 us at H = 2048.)
-constexpr int NSA = 10, NSB = 12;
-constexpr int SPLIT_SMEM = NSA * F_A_PIECE + NSB * F_B_PIECE + Ring<1>::XCH + 1024 + Ring<1>::BARS;
+constexpr int GK = 2, NSA = 5, NSB = 6;
+constexpr int SPLIT_SMEM = NSA * GK * F_A_PIECE + NSB * GK * F_B_PIECE + Ring<1>::XCH + 1024 + Ring<1>::BARS;
 // The two MMA issuers take alternate k-blocks.  Each owns a private sub-ring of stages (issuer 0 the first
 // ceil(n/2) stages, issuer 1 the rest) so that every full/empty barrier has its phases consumed by ONE thread in
 // order.  With a shared ring of odd depth the successive fills of a stage alternate between the issuers,
@@ -145,8 +147,8 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
     constexpr int NSTAGE = FULLB ? NSA : R::NSTAGE;
-    const uint32_t bbuf = smem_base + (uint32_t)NSA * F_A_PIECE;                    // FULLB: ring of state tiles
-    const uint32_t xch_base = FULLB ? bbuf + (uint32_t)NSB * F_B_PIECE : smem_base + NSTAGE * STAGE;
+    const uint32_t bbuf = smem_base + (uint32_t)NSA * GK * F_A_PIECE;               // FULLB: ring of state tiles
+    const uint32_t xch_base = FULLB ? bbuf + (uint32_t)NSB * GK * F_B_PIECE : smem_base + NSTAGE * STAGE;
     float *zs = reinterpret_cast<float *>(smem_gen + (xch_base - smem_base));        // [4][32 b][32 u]
     const uint32_t bar_base = xch_base + R::XCH;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
@@ -156,12 +158,13 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     const uint32_t tfull = bar_base + 8u * 44, tempty = tfull + 8;
     const uint32_t tmem_slot = tempty + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
-    auto a_addr = [&](int s, int pc) { return FULLB ? smem_base + s * F_A_PIECE : smem_base + s * STAGE + pc * F_A_PIECE; };
+    auto a_addr = [&](int s, int pc) { return FULLB ? smem_base + s * GK * F_A_PIECE + pc * F_A_PIECE : smem_base + s * STAGE + pc * F_A_PIECE; };   // FULLB: pc = k-block of the group
     auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * F_B_PIECE; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = blockIdx.x / p.CPD, c = blockIdx.x % p.CPD;
     const int T = p.T, B = p.B, H = p.H, KB = H / BK;
+    const bool TWO_ACC = (PIECES == 1 ? (KB + GK - 1) / GK : KB) > 1;      // the second issuer had work: add its accumulator
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), FULLB ? 1 : 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
@@ -204,9 +207,24 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             const int row0 = (d * p.CPD + c) * 128;
             const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int i = 0; i < T; ++i)
+                if (FULLB) {
+                    const int ns = KB - p.kres;                     // streamed k-blocks come first in the visiting order
+                    for (int g = 0; GK * g < ns; ++g) {
+                        SubRing &r = ring[g & 1];
+                        const int stage = r.slot(), cnt = min(GK, ns - GK * g);
+                        ptx::mbar_wait(empty(stage), r.phase ^ 1);
+                        ptx::mbar_expect_tx(fullA(stage), (uint32_t)cnt * F_A_PIECE);
+                        for (int q2 = 0; q2 < cnt; ++q2) {
+                            const int kb = p.kres + GK * g + q2;
+                            const uint64_t pol = kb - p.kres < p.kb_keep ? keep : stream;
+                            ptx::tma_load_3d_hint(a_addr(stage, q2), &mapW, kb * BK, row0, 0, fullA(stage), pol);
+                        }
+                        r.advance();
+                    }
+                    stamp(p, i, 6);
+                } else
                 for (int m = 0; m < KB; ++m) {
-                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;      // FULLB: streamed k-blocks first
-                    if (FULLB && kb < p.kres) continue;             // resident in tensor memory: no ring traffic at all
+                    const int kb = m;
                     SubRing &r = ring[m & 1];
                     const int stage = r.slot();
                     ptx::mbar_wait(empty(stage), r.phase ^ 1);
@@ -218,7 +236,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         ptx::tma_load_3d_hint(a_addr(stage, 0), &mapW, kb * BK, row0, 0, fullA(stage), pol);   // all pieces in one box
                     }
                     r.advance();
-                    if (m == KB - 1 || (FULLB && m == KB - p.kres - 1)) stamp(p, i, 6);
+                    if (m == KB - 1) stamp(p, i, 6);
                 }
         }
     } else if (warp == 5) {
@@ -232,14 +250,17 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 ptx::fence_proxy_async();
                 stamp(p, i, 0);
                 const int row0 = (d * 2 + (i & 1)) * NB;
-                if (FULLB) {        // own ring of 4-KB tiles, in the step's visiting order
-                    for (int m = 0; m < KB; ++m) {
-                        const int kb = m < KB - p.kres ? p.kres + m : m - (KB - p.kres);
-                        SubRing &r = ringB[m & 1];
-                        const int stage = r.slot();
+                if (FULLB) {        // own ring, GK tiles of 4 KB per stage, in the step's visiting order
+                    for (int g = 0; GK * g < KB; ++g) {
+                        SubRing &r = ringB[g & 1];
+                        const int stage = r.slot(), cnt = min(GK, KB - GK * g);
                         ptx::mbar_wait(emptyB(stage), r.phase ^ 1);
-                        ptx::mbar_expect_tx(fullB(stage), F_B_PIECE);
-                        ptx::tma_load_3d(bbuf + (uint32_t)stage * F_B_PIECE, &mapH, kb * BK, row0, 0, fullB(stage));
+                        ptx::mbar_expect_tx(fullB(stage), (uint32_t)cnt * F_B_PIECE);
+                        for (int q2 = 0; q2 < cnt; ++q2) {
+                            const int m = GK * g + q2;
+                            const int kb = m < KB - p.kres ? p.kres + m : m - (KB - p.kres);
+                            ptx::tma_load_3d(bbuf + (uint32_t)(stage * GK + q2) * F_B_PIECE, &mapH, kb * BK, row0, 0, fullB(stage));
+                        }
                         r.advance();
                     }
                 } else {
@@ -268,15 +289,20 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             for (int i = 0; i < T; ++i) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
-                for (int m = me; m < KB; m += 2) {
-                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;
+                // a unit of issue = one k-block, or (FULLB) a group of GK k-blocks behind one pair of barriers
+                const int NU = FULLB ? (KB + GK - 1) / GK : KB;
+                for (int u = me; u < NU; u += 2) {
                     const int stage = ring.slot(), stageB = ringB.slot();
-                    const int first = m == me;
-                    const bool ringed = !FULLB || kb >= p.kres;             // this k-block's weights go through the ring
+                    const int cnt = FULLB ? min(GK, KB - GK * u) : 1;
+                    const bool ringed = !FULLB || GK * u < KB - p.kres;     // this unit's weights go through the ring (streamed k-blocks come first)
                     if (FULLB) ptx::mbar_wait(fullB(stageB), ringB.phase);
                     if (ringed) ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
-                    const uint64_t bd = ptx::make_smem_desc(FULLB ? bbuf + (uint32_t)stageB * F_B_PIECE : b_addr(stage, 0), 16, 1024, 2);
+                  for (int q2 = 0; q2 < cnt; ++q2) {
+                    const int m = FULLB ? GK * u + q2 : u;
+                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;
+                    const int first = u == me && q2 == 0;
+                    const uint64_t bd = ptx::make_smem_desc(FULLB ? bbuf + (uint32_t)(stageB * GK + q2) * F_B_PIECE : b_addr(stage, 0), 16, 1024, 2);
                     if (PIECES == 2) {
                         // bf16x3 with 2 MMAs per k-step: the two pieces of h are consecutive rows of one K-major tile,
                         // so  A_hi x [B_hi; B_lo]  is ONE N = 64 MMA (columns 0-31: hi*hi, 32-63: hi*lo) and
@@ -304,12 +330,13 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                             for (int j = 0; j < BK / 16; ++j)
                                 ptx::mma_bf16_ts(acc, ta + 8 * j, bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
                         } else {
-                            const uint64_t ad = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+                            const uint64_t ad = ptx::make_smem_desc(a_addr(stage, FULLB ? q2 : 0), 16, 1024, 2);
 #pragma unroll
                             for (int j = 0; j < BK / 16; ++j)
                                 ptx::mma_bf16(acc, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
                         }
                     }
+                  }
                     if (ringed) { ptx::mma_commit(empty(stage)); ring.advance(); }
                     if (FULLB) { ptx::mma_commit(emptyB(stageB)); ringB.advance(); }
                 }
@@ -367,13 +394,13 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                     ptx::tmem_ld32(lane_base + PIECES * NB, r3);                        // issuer 1 (odd k-blocks)
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) pz[b] += __uint_as_float(r[b]) + (KB > 1 ? __uint_as_float(r3[b]) : 0.f);
+                    for (int b = 0; b < NB; ++b) pz[b] += __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
                     if (PIECES == 2) {
                         ptx::tmem_ld32(lane_base + 32, r);                              // hi*lo of both issuers
                         ptx::tmem_ld32(lane_base + 96, r3);
                         ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) pz[b] += __uint_as_float(r[b]) + (KB > 1 ? __uint_as_float(r3[b]) : 0.f);
+                        for (int b = 0; b < NB; ++b) pz[b] += __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
                     }
                 }
                 ptx::tc_fence_before();
@@ -659,8 +686,8 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
     constexpr int NSTAGE = FULLB ? NSA : R::NSTAGE;
-    const uint32_t bbuf = smem_base + (uint32_t)NSA * F_A_PIECE;                    // FULLB: ring of state tiles
-    const uint32_t xch_base = FULLB ? bbuf + (uint32_t)NSB * F_B_PIECE : smem_base + NSTAGE * STAGE;
+    const uint32_t bbuf = smem_base + (uint32_t)NSA * GK * F_A_PIECE;               // FULLB: ring of state tiles
+    const uint32_t xch_base = FULLB ? bbuf + (uint32_t)NSB * GK * F_B_PIECE : smem_base + NSTAGE * STAGE;
     const float *slots = reinterpret_cast<const float *>(smem_gen + (xch_base - smem_base));   // [4][32 b][32 u]
     const uint32_t bar_base = xch_base + R::XCH;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
@@ -670,7 +697,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     const uint32_t tfull = bar_base + 8u * 44, tempty = tfull + 8, xfull = tempty + 8;
     const uint32_t tmem_slot = xfull + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
-    auto a_addr = [&](int s, int pc) { return FULLB ? smem_base + s * F_A_PIECE : smem_base + s * STAGE + pc * F_A_PIECE; };
+    auto a_addr = [&](int s, int pc) { return FULLB ? smem_base + s * GK * F_A_PIECE + pc * F_A_PIECE : smem_base + s * STAGE + pc * F_A_PIECE; };   // FULLB: pc = k-block of the group
     auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * F_B_PIECE; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -679,6 +706,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     const int UBD = p.H / 128;                                  // unit blocks per direction
     const int d = cid / UBD, ub = cid % UBD;
     const int T = p.T, B = p.B, H = p.H, GH = G * H, KQ = GH / 4, KB = KQ / BK;
+    const bool TWO_ACC = (PIECES == 1 ? (KB + GK - 1) / GK : KB) > 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), FULLB ? 1 : 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
@@ -720,9 +748,24 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
             const int row0 = d * H + ub * 128;
             const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int n = 0; n < T; ++n)
+                if (FULLB) {
+                    const int ns = KB - p.kres;                     // streamed k-blocks come first in the visiting order
+                    for (int g = 0; GK * g < ns; ++g) {
+                        SubRing &r = ring[g & 1];
+                        const int stage = r.slot(), cnt = min(GK, ns - GK * g);
+                        ptx::mbar_wait(empty(stage), r.phase ^ 1);
+                        ptx::mbar_expect_tx(fullA(stage), (uint32_t)cnt * F_A_PIECE);
+                        for (int q2 = 0; q2 < cnt; ++q2) {
+                            const int kb = p.kres + GK * g + q2;
+                            const uint64_t pol = kb - p.kres < p.kb_keep ? keep : stream;
+                            ptx::tma_load_3d_hint(a_addr(stage, q2), &mapW, q * KQ + kb * BK, row0, 0, fullA(stage), pol);
+                        }
+                        r.advance();
+                    }
+                    
+                } else
                 for (int m = 0; m < KB; ++m) {
-                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;      // FULLB: streamed k-blocks first
-                    if (FULLB && kb < p.kres) continue;             // resident in tensor memory: no ring traffic at all
+                    const int kb = m;
                     SubRing &r = ring[m & 1];
                     const int stage = r.slot();
                     ptx::mbar_wait(empty(stage), r.phase ^ 1);
@@ -745,14 +788,17 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                 wait_counter(p.counters + d, (unsigned)(p.CPD * n), p.counters + 2);
                 ptx::fence_proxy_async();
                 const int row0 = (d * 2 + (n & 1)) * NB;
-                if (FULLB) {        // own ring of 4-KB tiles, in the step's visiting order
-                    for (int m = 0; m < KB; ++m) {
-                        const int kb = m < KB - p.kres ? p.kres + m : m - (KB - p.kres);
-                        SubRing &r = ringB[m & 1];
-                        const int stage = r.slot();
+                if (FULLB) {        // own ring, GK tiles of 4 KB per stage, in the step's visiting order
+                    for (int g = 0; GK * g < KB; ++g) {
+                        SubRing &r = ringB[g & 1];
+                        const int stage = r.slot(), cnt = min(GK, KB - GK * g);
                         ptx::mbar_wait(emptyB(stage), r.phase ^ 1);
-                        ptx::mbar_expect_tx(fullB(stage), F_B_PIECE);
-                        ptx::tma_load_3d(bbuf + (uint32_t)stage * F_B_PIECE, &mapZ, q * KQ + kb * BK, row0, 0, fullB(stage));
+                        ptx::mbar_expect_tx(fullB(stage), (uint32_t)cnt * F_B_PIECE);
+                        for (int q2 = 0; q2 < cnt; ++q2) {
+                            const int m = GK * g + q2;
+                            const int kb = m < KB - p.kres ? p.kres + m : m - (KB - p.kres);
+                            ptx::tma_load_3d(bbuf + (uint32_t)(stage * GK + q2) * F_B_PIECE, &mapZ, q * KQ + kb * BK, row0, 0, fullB(stage));
+                        }
                         r.advance();
                     }
                 } else {
@@ -777,15 +823,20 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
             for (int n = 0; n < T; ++n) {
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
-                for (int m = me; m < KB; m += 2) {
-                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;
+                // a unit of issue = one k-block, or (FULLB) a group of GK k-blocks behind one pair of barriers
+                const int NU = FULLB ? (KB + GK - 1) / GK : KB;
+                for (int u = me; u < NU; u += 2) {
                     const int stage = ring.slot(), stageB = ringB.slot();
-                    const int first = m == me;
-                    const bool ringed = !FULLB || kb >= p.kres;             // this k-block's weights go through the ring
+                    const int cnt = FULLB ? min(GK, KB - GK * u) : 1;
+                    const bool ringed = !FULLB || GK * u < KB - p.kres;     // this unit's weights go through the ring (streamed k-blocks come first)
                     if (FULLB) ptx::mbar_wait(fullB(stageB), ringB.phase);
                     if (ringed) ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
-                    const uint64_t bd = ptx::make_smem_desc(FULLB ? bbuf + (uint32_t)stageB * F_B_PIECE : b_addr(stage, 0), 16, 1024, 2);
+                  for (int q2 = 0; q2 < cnt; ++q2) {
+                    const int m = FULLB ? GK * u + q2 : u;
+                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;
+                    const int first = u == me && q2 == 0;
+                    const uint64_t bd = ptx::make_smem_desc(FULLB ? bbuf + (uint32_t)(stageB * GK + q2) * F_B_PIECE : b_addr(stage, 0), 16, 1024, 2);
                     if (PIECES == 2) {
                         if (kb < p.kres) {
                             const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
@@ -810,12 +861,13 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                             for (int j = 0; j < BK / 16; ++j)
                                 ptx::mma_bf16_ts(acc, ta + 8 * j, bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
                         } else {
-                            const uint64_t ad = ptx::make_smem_desc(a_addr(stage, 0), 16, 1024, 2);
+                            const uint64_t ad = ptx::make_smem_desc(a_addr(stage, FULLB ? q2 : 0), 16, 1024, 2);
 #pragma unroll
                             for (int j = 0; j < BK / 16; ++j)
                                 ptx::mma_bf16(acc, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, !(first && j == 0));
                         }
                     }
+                  }
                     if (ringed) { ptx::mma_commit(empty(stage)); ring.advance(); }
                     if (FULLB) { ptx::mma_commit(emptyB(stageB)); ringB.advance(); }
                 }
@@ -870,13 +922,13 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                     ptx::tmem_ld32(lane_base + PIECES * NB, r3);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) part[b] = __uint_as_float(r[b]) + (KB > 1 ? __uint_as_float(r3[b]) : 0.f);
+                    for (int b = 0; b < NB; ++b) part[b] = __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
                     if (PIECES == 2) {
                         ptx::tmem_ld32(lane_base + 32, r);
                         ptx::tmem_ld32(lane_base + 96, r3);
                         ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) part[b] += __uint_as_float(r[b]) + (KB > 1 ? __uint_as_float(r3[b]) : 0.f);
+                        for (int b = 0; b < NB; ++b) part[b] += __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
                     }
                 }
                 ptx::tc_fence_before();
