@@ -426,9 +426,9 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                     const float zi = zs[(0 * NB + b) * UPC + cu], zj = zs[(1 * NB + b) * UPC + cu];
                     const float zf = zs[(2 * NB + b) * UPC + cu], zo = zs[(3 * NB + b) * UPC + cu];
                     if (live) {
-                        const float gi = sigmoidf_(zi), gj = tanhf(zj), gf = sigmoidf_(zf + p.forget_bias), go = sigmoidf_(zo);
+                        const float gi = sigmoidf_(zi), gj = rec::tanhf_(zj), gf = sigmoidf_(zf + p.forget_bias), go = sigmoidf_(zo);
                         sreg[j] = gf * sreg[j] + gi * gj;
-                        h = go * tanhf(sreg[j]);
+                        h = go * rec::tanhf_(sreg[j]);
                         o_g[j][0] = gi; o_g[j][1] = gj; o_g[j][2] = gf; o_g[j][3] = go;
                     }
                     o_s[j] = sreg[j];
@@ -438,7 +438,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                     if (live) {
                         const float q = un + brn;
                         const float gr = sigmoidf_(pin[j * 3 + 0] + ur), gz = sigmoidf_(pin[j * 3 + 1] + uz);
-                        const float gn = tanhf(pin[j * 3 + 2] + gr * q);
+                        const float gn = rec::tanhf_(pin[j * 3 + 2] + gr * q);
                         h = (1.f - gz) * gn + gz * sreg[j];
                         sreg[j] = h;
                         o_g[j][0] = gr; o_g[j][1] = gz; o_g[j][2] = gn;
@@ -460,7 +460,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             // every writing thread orders its own h pieces for the other CTAs' TMA (async proxy) reads: a single
             // fence by the signalling thread after the barrier (the grid.sync idiom) is NOT enough here —
             // measured: nondeterministic results and rare hangs at H = 2048
-            __threadfence();
+            rec::fence_release_gpu();
             ptx::fence_proxy_async();
             cell_bar();
             if (tid == 0) { signal_counter(p.counters + d); stamp(p, i, 5); }
@@ -631,7 +631,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                 float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
                 if (live) {
                     const float dh = dyv[j] + dhs[b * (UPC + 1) + cu];
-                    const float tc = tanhf(cc[j]);
+                    const float tc = rec::tanhf_(cc[j]);
                     const float dc = dh * go[j] * (1.f - tc * tc) + dcreg[j];
                     dzi = dc * gj[j] * gi[j] * (1.f - gi[j]);
                     dzj = dc * gi[j] * (1.f - gj[j] * gj[j]);
@@ -654,7 +654,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
                     zb[piece + (size_t)b * 4 * H + (size_t)q * H] = lo;
                 }
             }
-            __threadfence();
+            rec::fence_release_gpu();
             ptx::fence_proxy_async();
             epi_bar();
             if (tid == 0) signal_counter(p.counters + d);
@@ -954,7 +954,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                     const float dh = dyv[j] + ((slots[o] + slots[NB * UPC + o]) + (slots[2 * NB * UPC + o] + slots[3 * NB * UPC + o]));
                     if (CELL == CELL_L) {
                         const float gi = ga[j][0], gj = ga[j][1], gf = ga[j][2], go = ga[j][3];
-                        const float tc = tanhf(sc[j]);
+                        const float tc = rec::tanhf_(sc[j]);
                         const float dc = dh * go * (1.f - tc * tc) + carry[j];
                         o_dz[j][0] = dc * gj * gi * (1.f - gi);
                         o_dz[j][1] = dc * gi * (1.f - gj * gj);
@@ -989,7 +989,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                 }
                 if (CELL == CELL_G) dbacc[3] += o_zr[j];
             }
-            __threadfence();                // per-thread fences: see the forward kernel
+            rec::fence_release_gpu();                // per-thread fences: see the forward kernel
             ptx::fence_proxy_async();
             cell_bar();
             if (tid == 0) signal_counter(p.counters + d);

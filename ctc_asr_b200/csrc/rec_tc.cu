@@ -243,7 +243,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                 if (live) {
                     if (FWD) {
                         const float z = a[j] + s;
-                        v = tanh_cell ? tanhf(z) : fmaxf(z, 0.f);
+                        v = tanh_cell ? rec::tanhf_(z) : fmaxf(z, 0.f);
                     } else {
                         const float dh = g[j] + s;
                         v = tanh_cell ? dh * (1.f - a[j] * a[j]) : (a[j] > 0.f ? dh : 0.f);
@@ -258,7 +258,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             }
             // every writing thread orders its own pieces for the other CTAs' TMA (async proxy) reads (see lstm_tc.cu)
             if (tid == 0) stamp(p, n, 5);
-            __threadfence();
+            rec::fence_release_gpu();
             ptx::fence_proxy_async();
             cell_bar();
             if (tid == 0) { rec::signal_counter(p.counters + d); stamp(p, n, 6); }
