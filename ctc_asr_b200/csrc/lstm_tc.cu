@@ -47,12 +47,15 @@ constexpr int CELL_L = CTCASR_CELL_LSTM, CELL_G = CTCASR_CELL_GRU;
 // PIECES = 2: bf16x3 arithmetic (operands split hi + lo, three products); PIECES = 1: plain bf16 operands, one
 // product (compute = 'bf16', BASELINE cfg3) — half the weight bytes, so most of a CTA's slice stays in tensor memory.
 constexpr int F_A_PIECE = 128 * BK * 2, F_B_PIECE = NB * BK * 2;
-template <int PIECES> struct Ring {
-    static constexpr int STAGE = PIECES * (F_A_PIECE + F_B_PIECE);           // 40 KB / 20 KB
-    static constexpr int NSTAGE = PIECES == 2 ? 5 : 9;
-    static constexpr int ACC_COLS = 2 * PIECES * NB;                         // two issuers x (PIECES x 32) accumulator columns
-    static constexpr int KRES_MAX = (512 - ACC_COLS) / (PIECES * 32);        // weight k-blocks resident in tensor memory: 6 / 14
-    static constexpr int XCH = 4 * NB * UPC * 4;                             // gate exchange [4][32 b][32 u] fp32
+// NBT = batch rows per launch = MMA N (x2 with the hi / lo pieces of the state stacked): 32, or 64 so that a batch of 64
+// (BASELINE cfg4) shares ONE weight stream per time step instead of running as two 32-row launches.
+template <int PIECES, int NBT = NB> struct Ring {
+    static constexpr int BP = NBT * BK * 2;                                  // one piece of a state tile: 4 KB / 8 KB
+    static constexpr int STAGE = PIECES * (F_A_PIECE + BP);                  // 40 KB / 20 KB (48 KB at NBT = 64)
+    static constexpr int NSTAGE = PIECES == 2 ? (NBT == 64 ? 4 : 5) : 9;
+    static constexpr int ACC_COLS = 2 * PIECES * NBT;                        // two issuers x (PIECES x NBT) accumulator columns
+    static constexpr int KRES_MAX = (512 - ACC_COLS) / (PIECES * 32);        // weight k-blocks resident in tensor memory: 6 / 14 (4 at NBT = 64)
+    static constexpr int XCH = 4 * NBT * UPC * 4;                            // gate exchange [4][NBT b][32 u] fp32
     static constexpr int BARS = 1024;
     static constexpr int SMEM = NSTAGE * STAGE + XCH + 1024 + BARS;
 };
@@ -135,11 +138,12 @@ __device__ __forceinline__ void cell_bar() { asm volatile("bar.sync 1, 256;" :::
 // CELL = LSTM: rows of a CTA tile = 4 gates (i, j, f, o) x 32 units.  CELL = GRU (cuDNN formulation, gate order
 // r, z, n): 3 gates x 32 units, the fourth 32-row group of the tile is zero weights; the recurrent product of the
 // candidate gate is kept apart from its input projection (n = tanh(P_n + r (h Rn + b_rn))).
-template <int CELL, int PIECES>
+template <int CELL, int PIECES, int NBT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH, const Params p)
 {
-    using R = Ring<PIECES>;
+    using R = Ring<PIECES, NBT>;
+    static_assert(NBT == 32 || (NBT == 64 && PIECES == 2), "64-row batch tiles: two-piece kernels only");
     constexpr int G = CELL == CELL_G ? 3 : 4;
     constexpr bool FULLB = PIECES == 1;
     constexpr int STAGE = R::STAGE;
@@ -149,7 +153,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     constexpr int NSTAGE = FULLB ? NSA : R::NSTAGE;
     const uint32_t bbuf = smem_base + (uint32_t)NSA * GK * F_A_PIECE;               // FULLB: ring of state tiles
     const uint32_t xch_base = FULLB ? bbuf + (uint32_t)NSB * GK * F_B_PIECE : smem_base + NSTAGE * STAGE;
-    float *zs = reinterpret_cast<float *>(smem_gen + (xch_base - smem_base));        // [4][32 b][32 u]
+    float *zs = reinterpret_cast<float *>(smem_gen + (xch_base - smem_base));        // [4][NBT b][32 u]
     const uint32_t bar_base = xch_base + R::XCH;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
     auto empty = [&](int s) { return bar_base + 8u * (10 + s); };
@@ -159,7 +163,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     const uint32_t tmem_slot = tempty + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
     auto a_addr = [&](int s, int pc) { return FULLB ? smem_base + s * GK * F_A_PIECE + pc * F_A_PIECE : smem_base + s * STAGE + pc * F_A_PIECE; };   // FULLB: pc = k-block of the group
-    auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * F_B_PIECE; };
+    auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * R::BP; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = blockIdx.x / p.CPD, c = blockIdx.x % p.CPD;
@@ -249,7 +253,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 wait_counter(p.counters + d, (unsigned)(p.CPD * i), p.counters + 2);
                 ptx::fence_proxy_async();
                 stamp(p, i, 0);
-                const int row0 = (d * 2 + (i & 1)) * NB;
+                const int row0 = (d * 2 + (i & 1)) * NBT;
                 if (FULLB) {        // own ring, GK tiles of 4 KB per stage, in the step's visiting order
                     for (int g = 0; GK * g < KB; ++g) {
                         SubRing &r = ringB[g & 1];
@@ -268,7 +272,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         SubRing &r = ring[kb & 1];
                         const int stage = r.slot();
                         ptx::mbar_wait(empty(stage), r.phase ^ 1);
-                        ptx::mbar_expect_tx(fullA(stage), PIECES * F_B_PIECE);
+                        ptx::mbar_expect_tx(fullA(stage), PIECES * R::BP);
                         ptx::tma_load_3d(b_addr(stage, 0), &mapH, kb * BK, row0, 0, fullA(stage));   // all pieces in one box
                         r.advance();
                     }
@@ -282,8 +286,8 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         // the streaming phase, so it is split over two threads; the epilogue adds the accumulators.
         if (lane == 0) {
             const int me = warp - 6;
-            const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
-            const uint32_t acc = tmem_d + (uint32_t)(me * PIECES * NB);
+            const uint32_t idesc32 = ptx::make_idesc_bf16(128, NBT, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NBT, 0, 0);     // N = NBT, 2 NBT
+            const uint32_t acc = tmem_d + (uint32_t)(me * PIECES * NBT);
             uint32_t tphase = 0;
             SubRing ring(me, NSTAGE), ringB(me, NSB);
             for (int i = 0; i < T; ++i) {
@@ -347,27 +351,28 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         }
     } else if (warp < 4 || warp >= 8) {
         // ---- cell math.  Warps 0-3 (warp = gate) also read the accumulators (LSTM: and add the input projection);
-        // then all 8 cell warps own (unit, 4 batch rows) cells with the state kept in registers across steps.
+        // then all 8 cell warps own (unit, CPT batch rows) cells with the state kept in registers across steps.
+        constexpr int NH = NBT / 32, CPT = NBT / 8;                          // 32-row halves of the batch tile; cells per thread
         const bool reader = warp < 4;
         const int g = warp, ul = lane;
         const int tid = threadIdx.x;
         const int e = reader ? tid : tid - 128;                              // 0..255
-        const int cu = e & 31, bg = e >> 5;                                  // cell ownership: rows bg*4 .. bg*4+3
+        const int cu = e & 31, bg = e >> 5;                                  // cell ownership: rows bg*CPT .. bg*CPT+CPT-1
         const int ucol = c * UPC;                                            // first unit of this CTA
-        float sreg[4];                                                       // LSTM: c;  GRU: h
-        int len4[4];
+        float sreg[CPT];                                                     // LSTM: c;  GRU: h
+        int lenv[CPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int b = bg * 4 + j; sreg[j] = 0.f; len4[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
+        for (int j = 0; j < CPT; ++j) { const int b = bg * CPT + j; sreg[j] = 0.f; lenv[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
         const float brn = CELL == CELL_G ? p.bias_rn[d * H + ucol + cu] : 0.f;
         uint32_t tphase = 0;
         const size_t GW = (size_t)2 * G * H;                                 // gates row pitch
         for (int i = 0; i < T; ++i) {
             const int tt = d == 0 ? i : T - 1 - i;
-            float pin[CELL == CELL_G ? 12 : 1];                              // GRU: input projections of my cells
+            float pin[CELL == CELL_G ? 3 * CPT : 1];                         // GRU: input projections of my cells
             if (CELL == CELL_G) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int b = bg * 4 + j;
+                for (int j = 0; j < CPT; ++j) {
+                    const int b = bg * CPT + j;
                     const float *prow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * G * H + ucol + cu;
 #pragma unroll
                     for (int q = 0; q < 3; ++q) pin[j * 3 + q] = b < B ? __ldg(prow + (size_t)q * H) : 0.f;
@@ -375,32 +380,34 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             }
             if (reader) {
                 // LSTM: pre-activations of my gate row for all batch rows (independent of the recurrence)
-                float pz[NB];
-                if (CELL == CELL_L) {
+                float pz[NH][NB];
+#pragma unroll
+                for (int hf = 0; hf < NH; ++hf) {
                     const float *prow = p.gates + (size_t)tt * p.BS * GW + (size_t)d * G * H + (size_t)g * H + ucol + ul;
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) pz[b] = b < B ? __ldg(prow + (size_t)b * GW) : 0.f;
-                } else {
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) pz[b] = 0.f;
+                    for (int b = 0; b < NB; ++b) pz[hf][b] = (CELL == CELL_L && hf * NB + b < B) ? __ldg(prow + (size_t)(hf * NB + b) * GW) : 0.f;
                 }
                 ptx::mbar_wait(tfull, tphase);
                 if (tid == 0) stamp(p, i, 3);
                 ptx::tc_fence_after();
                 if (g < G) {
-                    uint32_t r[32], r3[32];
+                    // accumulator columns of issuer m: [m PIECES NBT, +NBT) = hi*hi + lo*hi (or the single product), then NBT of hi*lo
                     const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
-                    ptx::tmem_ld32(lane_base, r);                                       // issuer 0: hi*hi + lo*hi  (or the single product)
-                    ptx::tmem_ld32(lane_base + PIECES * NB, r3);                        // issuer 1 (odd k-blocks)
-                    ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) pz[b] += __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
-                    if (PIECES == 2) {
-                        ptx::tmem_ld32(lane_base + 32, r);                              // hi*lo of both issuers
-                        ptx::tmem_ld32(lane_base + 96, r3);
+                    for (int hf = 0; hf < NH; ++hf) {
+                        uint32_t r[32], r3[32];
+                        ptx::tmem_ld32(lane_base + hf * NB, r);                                 // issuer 0
+                        ptx::tmem_ld32(lane_base + PIECES * NBT + hf * NB, r3);                 // issuer 1 (odd k-blocks)
                         ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) pz[b] += __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
+                        for (int b = 0; b < NB; ++b) pz[hf][b] += __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
+                        if (PIECES == 2) {
+                            ptx::tmem_ld32(lane_base + NBT + hf * NB, r);                       // hi*lo of both issuers
+                            ptx::tmem_ld32(lane_base + PIECES * NBT + NBT + hf * NB, r3);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) pz[hf][b] += __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
+                        }
                     }
                 }
                 ptx::tc_fence_before();
@@ -409,22 +416,24 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 tphase ^= 1;
                 if (g < G) {
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) zs[(g * NB + b) * UPC + ul] = pz[b];
+                    for (int hf = 0; hf < NH; ++hf)
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) zs[(g * NBT + hf * NB + b) * UPC + ul] = pz[hf][b];
                 }
             }
             cell_bar();
-            __nv_bfloat16 *hb = p.xbuf + ((size_t)(d * 2 + ((i + 1) & 1)) * NB) * H + ucol + cu;
-            const size_t piece = (size_t)2 * 2 * NB * H;
-            float o_g[4][4], o_s[4], o_h[4];
+            __nv_bfloat16 *hb = p.xbuf + ((size_t)(d * 2 + ((i + 1) & 1)) * NBT) * H + ucol + cu;
+            const size_t piece = (size_t)2 * 2 * NBT * H;
+            float o_g[CPT][4], o_s[CPT], o_h[CPT];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = bg * 4 + j;
-                const bool live = tt < len4[j];
+            for (int j = 0; j < CPT; ++j) {
+                const int b = bg * CPT + j;
+                const bool live = tt < lenv[j];
                 float h = 0.f;
                 o_g[j][0] = o_g[j][1] = o_g[j][2] = o_g[j][3] = 0.f;
                 if (CELL == CELL_L) {
-                    const float zi = zs[(0 * NB + b) * UPC + cu], zj = zs[(1 * NB + b) * UPC + cu];
-                    const float zf = zs[(2 * NB + b) * UPC + cu], zo = zs[(3 * NB + b) * UPC + cu];
+                    const float zi = zs[(0 * NBT + b) * UPC + cu], zj = zs[(1 * NBT + b) * UPC + cu];
+                    const float zf = zs[(2 * NBT + b) * UPC + cu], zo = zs[(3 * NBT + b) * UPC + cu];
                     if (live) {
                         const float gi = sigmoidf_(zi), gj = rec::tanhf_(zj), gf = sigmoidf_(zf + p.forget_bias), go = sigmoidf_(zo);
                         sreg[j] = gf * sreg[j] + gi * gj;
@@ -433,7 +442,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                     }
                     o_s[j] = sreg[j];
                 } else {
-                    const float ur = zs[(0 * NB + b) * UPC + cu], uz = zs[(1 * NB + b) * UPC + cu], un = zs[(2 * NB + b) * UPC + cu];
+                    const float ur = zs[(0 * NBT + b) * UPC + cu], uz = zs[(1 * NBT + b) * UPC + cu], un = zs[(2 * NBT + b) * UPC + cu];
                     o_s[j] = 0.f;
                     if (live) {
                         const float q = un + brn;
@@ -466,8 +475,8 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             if (tid == 0) { signal_counter(p.counters + d); stamp(p, i, 5); }
             // bulk stores (activations for the backward pass, layer output) after the signal
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = bg * 4 + j;
+            for (int j = 0; j < CPT; ++j) {
+                const int b = bg * CPT + j;
                 if (b < B) {
                     float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * G * H + ucol + cu;
 #pragma unroll
@@ -674,11 +683,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant_
 // to CTA w of the cluster through distributed shared memory, and CTA w adds the four partials and
 // runs the cell backward for those 32 units.  Per step and CTA (LSTM, H = 2048): 1 MB of weights (streamed), 256 KB
 // of dz (L2), 384 MMAs.  GRU: dz_t here is the gradient wrt h R (the n columns scaled by r).
-template <int CELL, int PIECES>
+template <int CELL, int PIECES, int NBT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ, const Params p)
 {
-    using R = Ring<PIECES>;
+    using R = Ring<PIECES, NBT>;
+    static_assert(NBT == 32 || (NBT == 64 && PIECES == 2), "64-row batch tiles: two-piece kernels only");
     constexpr int G = CELL == CELL_G ? 3 : 4;
     constexpr bool FULLB = PIECES == 1;
     constexpr int STAGE = R::STAGE;
@@ -688,7 +698,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     constexpr int NSTAGE = FULLB ? NSA : R::NSTAGE;
     const uint32_t bbuf = smem_base + (uint32_t)NSA * GK * F_A_PIECE;               // FULLB: ring of state tiles
     const uint32_t xch_base = FULLB ? bbuf + (uint32_t)NSB * GK * F_B_PIECE : smem_base + NSTAGE * STAGE;
-    const float *slots = reinterpret_cast<const float *>(smem_gen + (xch_base - smem_base));   // [4][32 b][32 u]
+    const float *slots = reinterpret_cast<const float *>(smem_gen + (xch_base - smem_base));   // [4][NBT b][32 u]
     const uint32_t bar_base = xch_base + R::XCH;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
     auto empty = [&](int s) { return bar_base + 8u * (10 + s); };
@@ -698,7 +708,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     const uint32_t tmem_slot = xfull + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
     auto a_addr = [&](int s, int pc) { return FULLB ? smem_base + s * GK * F_A_PIECE + pc * F_A_PIECE : smem_base + s * STAGE + pc * F_A_PIECE; };   // FULLB: pc = k-block of the group
-    auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * F_B_PIECE; };
+    auto b_addr = [&](int s, int pc) { return smem_base + s * STAGE + PIECES * F_A_PIECE + pc * R::BP; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = (int)ptx::cluster_ctarank();                  // K-quarter of this CTA
@@ -787,7 +797,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
             for (int n = 0; n < T; ++n) {
                 wait_counter(p.counters + d, (unsigned)(p.CPD * n), p.counters + 2);
                 ptx::fence_proxy_async();
-                const int row0 = (d * 2 + (n & 1)) * NB;
+                const int row0 = (d * 2 + (n & 1)) * NBT;
                 if (FULLB) {        // own ring, GK tiles of 4 KB per stage, in the step's visiting order
                     for (int g = 0; GK * g < KB; ++g) {
                         SubRing &r = ringB[g & 1];
@@ -806,7 +816,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                         SubRing &r = ring[kb & 1];
                         const int stage = r.slot();
                         ptx::mbar_wait(empty(stage), r.phase ^ 1);
-                        ptx::mbar_expect_tx(fullA(stage), PIECES * F_B_PIECE);
+                        ptx::mbar_expect_tx(fullA(stage), PIECES * R::BP);
                         ptx::tma_load_3d(b_addr(stage, 0), &mapZ, q * KQ + kb * BK, row0, 0, fullA(stage));   // all pieces
                         r.advance();
                     }
@@ -816,8 +826,8 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     } else if (warp == 6 || warp == 7) {
         if (lane == 0) {        // two MMA issuers (even / odd k-blocks, separate accumulators), see the forward kernel
             const int me = warp - 6;
-            const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
-            const uint32_t acc = tmem_d + (uint32_t)(me * PIECES * NB);
+            const uint32_t idesc32 = ptx::make_idesc_bf16(128, NBT, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NBT, 0, 0);     // N = NBT, 2 NBT
+            const uint32_t acc = tmem_d + (uint32_t)(me * PIECES * NBT);
             uint32_t tphase = 0;
             SubRing ring(me, NSTAGE), ringB(me, NSB);
             for (int n = 0; n < T; ++n) {
@@ -876,136 +886,150 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
             }
         }
     } else if (warp < 4 || warp >= 8) {
+        constexpr int NH = NBT / 32, CPT = NBT / 8, NP = CPT / 4;          // 32-row halves; cells per thread, in passes of 4
         const bool reader = warp < 4;                                       // warps 0-3 also ship the accumulator rows
         const int tid = threadIdx.x;
         const int e = reader ? tid : tid - 128;                             // 0..255
-        const int cu = e & 31, bg = e >> 5;                                 // cell ownership: rows bg*4 .. bg*4+3
+        const int cu = e & 31, bg = e >> 5;                                 // cell ownership: rows bg*CPT .. bg*CPT+CPT-1
         const int ucol = ub * 128 + q * UPC;                                // the 32 units whose cells this CTA owns
-        float carry[4];                                                     // LSTM: dc carried to the previous frame; GRU: z * dh
+        float carry[CPT];                                                   // LSTM: dc carried to the previous frame; GRU: z * dh
         float dbacc[4] = {0.f, 0.f, 0.f, 0.f};                              // bias gradient: sum of dz over time and my rows (GRU [3]: b_rn)
-        int len4[4];
+        int lenv[CPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int b = bg * 4 + j; carry[j] = 0.f; len4[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
+        for (int j = 0; j < CPT; ++j) { const int b = bg * CPT + j; carry[j] = 0.f; lenv[j] = b < B ? (p.use_len ? min(p.seq_len[b], T) : T) : 0; }
         uint32_t tphase = 0;
         const size_t GW = (size_t)2 * GH;
         // destination of my TMEM rows: CTA `warp` of the cluster, slot q, [b][lane]
-        const uint32_t remote_slot = ptx::mapa(xch_base + (uint32_t)(q * NB * UPC) * 4u, (uint32_t)(warp & 3));
+        const uint32_t remote_slot = ptx::mapa(xch_base + (uint32_t)(q * NBT * UPC) * 4u, (uint32_t)(warp & 3));
         const uint32_t remote_bar = ptx::mapa(xfull, (uint32_t)(warp & 3));
         for (int n = 0; n < T; ++n) {
             const int i = T - 1 - n;
             const int tt = d == 0 ? i : T - 1 - i;
             const int tp = d == 0 ? tt - 1 : tt + 1;
-            // everything the cell needs that does not depend on the recurrence
+            // everything the cell needs that does not depend on the recurrence, for one pass of 4 cells
             float ga[4][4], sc[4], sp[4], dyv[4];            // gate activations; LSTM: c_t, c_{t-1};  GRU: q_t, h_{t-1}
+            auto load_pass = [&](int ps) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = bg * 4 + j;
-                ga[j][0] = ga[j][1] = ga[j][2] = ga[j][3] = sc[j] = sp[j] = dyv[j] = 0.f;
-                if (b < B) {
-                    const float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
+                for (int j = 0; j < 4; ++j) {
+                    const int b = bg * CPT + ps * 4 + j;
+                    ga[j][0] = ga[j][1] = ga[j][2] = ga[j][3] = sc[j] = sp[j] = dyv[j] = 0.f;
+                    if (b < B) {
+                        const float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
 #pragma unroll
-                    for (int k = 0; k < G; ++k) ga[j][k] = grow[(size_t)k * H];
-                    const size_t so = (size_t)d * H + ucol + cu;
-                    sc[j] = p.cstate[((size_t)tt * p.BS + b) * 2 * H + so];
-                    if (i > 0) sp[j] = CELL == CELL_L ? p.cstate[((size_t)tp * p.BS + b) * 2 * H + so] : p.y[((size_t)tp * p.BS + b) * 2 * H + so];
-                    dyv[j] = p.dy[((size_t)tt * p.BS + b) * 2 * H + so];
+                        for (int kk = 0; kk < G; ++kk) ga[j][kk] = grow[(size_t)kk * H];
+                        const size_t so = (size_t)d * H + ucol + cu;
+                        sc[j] = p.cstate[((size_t)tt * p.BS + b) * 2 * H + so];
+                        if (i > 0) sp[j] = CELL == CELL_L ? p.cstate[((size_t)tp * p.BS + b) * 2 * H + so] : p.y[((size_t)tp * p.BS + b) * 2 * H + so];
+                        dyv[j] = p.dy[((size_t)tt * p.BS + b) * 2 * H + so];
+                    }
                 }
-            }
+            };
+            load_pass(0);
             if (reader) {
                 ptx::mbar_wait(tfull, tphase);
                 ptx::tc_fence_after();
-                float part[NB];
-                {
+                // accumulator columns of issuer m: [m PIECES NBT, +NBT) = hi*hi + lo*hi (or the single product), then NBT of hi*lo
+                const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);      // rows = units 32*warp + lane of the block
+#pragma unroll
+                for (int hf = 0; hf < NH; ++hf) {
+                    float part[NB];
                     uint32_t r[32], r3[32];
-                    const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);      // rows = units 32*warp + lane of the block
-                    ptx::tmem_ld32(lane_base, r);
-                    ptx::tmem_ld32(lane_base + PIECES * NB, r3);
+                    ptx::tmem_ld32(lane_base + hf * NB, r);
+                    ptx::tmem_ld32(lane_base + PIECES * NBT + hf * NB, r3);
                     ptx::tmem_ld_wait();
 #pragma unroll
                     for (int b = 0; b < NB; ++b) part[b] = __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
                     if (PIECES == 2) {
-                        ptx::tmem_ld32(lane_base + 32, r);
-                        ptx::tmem_ld32(lane_base + 96, r3);
+                        ptx::tmem_ld32(lane_base + NBT + hf * NB, r);
+                        ptx::tmem_ld32(lane_base + PIECES * NBT + NBT + hf * NB, r3);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int b = 0; b < NB; ++b) part[b] += __uint_as_float(r[b]) + (TWO_ACC ? __uint_as_float(r3[b]) : 0.f);
                     }
+#pragma unroll
+                    for (int b = 0; b < NB; ++b)
+                        ptx::st_cluster_f32(remote_slot + (uint32_t)((hf * NB + b) * UPC + lane) * 4u, part[b]);
                 }
                 ptx::tc_fence_before();
-#pragma unroll
-                for (int b = 0; b < NB; ++b)
-                    ptx::st_cluster_f32(remote_slot + (uint32_t)(b * UPC + lane) * 4u, part[b]);
                 __syncwarp();
                 if (lane == 0) { ptx::mbar_arrive(tempty); ptx::mbar_arrive_remote(remote_bar); }
             }
             ptx::mbar_wait_cluster(xfull, tphase);                          // the four partials of my units have landed
             tphase ^= 1;
-            __nv_bfloat16 *zb = p.xbuf + ((size_t)(d * 2 + ((n + 1) & 1)) * NB) * GH + ucol + cu;
-            const size_t piece = (size_t)2 * 2 * NB * GH;
+            __nv_bfloat16 *zb = p.xbuf + ((size_t)(d * 2 + ((n + 1) & 1)) * NBT) * GH + ucol + cu;
+            const size_t piece = (size_t)2 * 2 * NBT * GH;
             float o_dz[4][4], o_zr[4];                                      // o_zr (GRU): dn_pre * r, the n column of dzr
+            auto store_pass = [&](int ps) {             // fp32 dz for the weight-gradient GEMMs
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = bg * 4 + j;
-                const bool live = tt < len4[j];
-                o_dz[j][0] = o_dz[j][1] = o_dz[j][2] = o_dz[j][3] = 0.f;
-                o_zr[j] = 0.f;
-                if (live) {
-                    const int o = b * UPC + cu;
-                    const float dh = dyv[j] + ((slots[o] + slots[NB * UPC + o]) + (slots[2 * NB * UPC + o] + slots[3 * NB * UPC + o]));
-                    if (CELL == CELL_L) {
-                        const float gi = ga[j][0], gj = ga[j][1], gf = ga[j][2], go = ga[j][3];
-                        const float tc = rec::tanhf_(sc[j]);
-                        const float dc = dh * go * (1.f - tc * tc) + carry[j];
-                        o_dz[j][0] = dc * gj * gi * (1.f - gi);
-                        o_dz[j][1] = dc * gi * (1.f - gj * gj);
-                        o_dz[j][2] = dc * sp[j] * gf * (1.f - gf);
-                        o_dz[j][3] = dh * tc * go * (1.f - go);
-                        carry[j] = dc * gf;
-                    } else {
-                        const float gr = ga[j][0], gz = ga[j][1], gn = ga[j][2];
-                        const float dht = dh + carry[j];
-                        const float dn_pre = dht * (1.f - gz) * (1.f - gn * gn);
-                        o_dz[j][0] = dn_pre * sc[j] * gr * (1.f - gr);
-                        o_dz[j][1] = dht * (sp[j] - gn) * gz * (1.f - gz);
-                        o_dz[j][2] = dn_pre;
-                        o_zr[j] = dn_pre * gr;
-                        carry[j] = dht * gz;
-                    }
-                } else {
-                    carry[j] = 0.f;
-                }
+                for (int j = 0; j < 4; ++j) {
+                    const int b = bg * CPT + ps * 4 + j;
+                    if (b < B) {
+                        float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
 #pragma unroll
-                for (int g4 = 0; g4 < G; ++g4) {        // the bf16 pieces are what the other CTAs wait for
-                    const float v = (CELL == CELL_G && g4 == 2) ? o_zr[j] : o_dz[j][g4];
-                    dbacc[g4] += o_dz[j][g4];
-                    if (PIECES == 2) {
-                        __nv_bfloat16 hi, lo;
-                        split2(v, hi, lo);
-                        zb[(size_t)b * GH + (size_t)g4 * H] = hi;
-                        zb[piece + (size_t)b * GH + (size_t)g4 * H] = lo;
-                    } else {
-                        zb[(size_t)b * GH + (size_t)g4 * H] = __float2bfloat16_rn(v);
+                        for (int kk = 0; kk < G; ++kk) grow[(size_t)kk * H] = o_dz[j][kk];
+                        if (CELL == CELL_G) {
+                            float *zrow = p.dzr + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
+                            zrow[0] = o_dz[j][0]; zrow[H] = o_dz[j][1]; zrow[2 * (size_t)H] = o_zr[j];
+                        }
                     }
                 }
-                if (CELL == CELL_G) dbacc[3] += o_zr[j];
+            };
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) {
+                if (ps > 0) load_pass(ps);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int jj = ps * 4 + j, b = bg * CPT + jj;
+                    const bool live = tt < lenv[jj];
+                    o_dz[j][0] = o_dz[j][1] = o_dz[j][2] = o_dz[j][3] = 0.f;
+                    o_zr[j] = 0.f;
+                    if (live) {
+                        const int o = b * UPC + cu;
+                        const float dh = dyv[j] + ((slots[o] + slots[NBT * UPC + o]) + (slots[2 * NBT * UPC + o] + slots[3 * NBT * UPC + o]));
+                        if (CELL == CELL_L) {
+                            const float gi = ga[j][0], gj = ga[j][1], gf = ga[j][2], go = ga[j][3];
+                            const float tc = rec::tanhf_(sc[j]);
+                            const float dc = dh * go * (1.f - tc * tc) + carry[jj];
+                            o_dz[j][0] = dc * gj * gi * (1.f - gi);
+                            o_dz[j][1] = dc * gi * (1.f - gj * gj);
+                            o_dz[j][2] = dc * sp[j] * gf * (1.f - gf);
+                            o_dz[j][3] = dh * tc * go * (1.f - go);
+                            carry[jj] = dc * gf;
+                        } else {
+                            const float gr = ga[j][0], gz = ga[j][1], gn = ga[j][2];
+                            const float dht = dh + carry[jj];
+                            const float dn_pre = dht * (1.f - gz) * (1.f - gn * gn);
+                            o_dz[j][0] = dn_pre * sc[j] * gr * (1.f - gr);
+                            o_dz[j][1] = dht * (sp[j] - gn) * gz * (1.f - gz);
+                            o_dz[j][2] = dn_pre;
+                            o_zr[j] = dn_pre * gr;
+                            carry[jj] = dht * gz;
+                        }
+                    } else {
+                        carry[jj] = 0.f;
+                    }
+#pragma unroll
+                    for (int g4 = 0; g4 < G; ++g4) {        // the bf16 pieces are what the other CTAs wait for
+                        const float v = (CELL == CELL_G && g4 == 2) ? o_zr[j] : o_dz[j][g4];
+                        dbacc[g4] += o_dz[j][g4];
+                        if (PIECES == 2) {
+                            __nv_bfloat16 hi, lo;
+                            split2(v, hi, lo);
+                            zb[(size_t)b * GH + (size_t)g4 * H] = hi;
+                            zb[piece + (size_t)b * GH + (size_t)g4 * H] = lo;
+                        } else {
+                            zb[(size_t)b * GH + (size_t)g4 * H] = __float2bfloat16_rn(v);
+                        }
+                    }
+                    if (CELL == CELL_G) dbacc[3] += o_zr[j];
+                }
+                if (NP > 1) store_pass(ps);             // 8 cells per thread: no room to hold the stores back behind the signal
             }
-            rec::fence_release_gpu();                // per-thread fences: see the forward kernel
+            rec::fence_release_gpu();       // per-thread fences: see the forward kernel
             ptx::fence_proxy_async();
             cell_bar();
             if (tid == 0) signal_counter(p.counters + d);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {               // fp32 dz for the weight-gradient GEMMs, after the signal
-                const int b = bg * 4 + j;
-                if (b < B) {
-                    float *grow = p.gates + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
-#pragma unroll
-                    for (int k = 0; k < G; ++k) grow[(size_t)k * H] = o_dz[j][k];
-                    if (CELL == CELL_G) {
-                        float *zrow = p.dzr + ((size_t)tt * p.BS + b) * GW + (size_t)d * GH + ucol + cu;
-                        zrow[0] = o_dz[j][0]; zrow[H] = o_dz[j][1]; zrow[2 * (size_t)H] = o_zr[j];
-                    }
-                }
-            }
+            if (NP == 1) store_pass(0);                 // after the signal
         }
         if (p.dbias) {
             // column sums of dz for my 32 units x 4 sums: the 8 row groups meet in the (now idle) exchange slots
@@ -1083,7 +1107,7 @@ static WsLayout ws_layout(int H)
     w.wpack = 0;
     const size_t wbytes = align_up((size_t)2 * 2 * 4 * H * H * 2, 1024);                // 2 pieces x [2*4H][H] bf16
     w.xbuf = wbytes;
-    const size_t xbytes = align_up((size_t)2 * 2 * 2 * NB * 4 * H * 2, 1024);           // dzbuf is the larger user
+    const size_t xbytes = align_up((size_t)2 * 2 * 2 * 64 * 4 * H * 2, 1024);           // dzbuf (64-row tiles) is the larger user
     w.counters = w.xbuf + xbytes;
     w.total = w.counters + 1024;
     return w;
@@ -1110,10 +1134,10 @@ static int keep_kblocks(int H, int G, int pieces, int KB)
 
 // Tensor-memory-resident weight share: the columns next to the accumulators hold the first k-blocks of every
 // CTA's weight slice for the whole sequence (6 with two pieces, 14 with one), read by the MMA as a TMEM A operand.
-static int resident_kblocks(int KB, int pieces)
+static int resident_kblocks(int KB, int pieces, int nbt = NB)
 {
     static const int env = env_int("CTCASR_LSTM_KRES", -1);
-    const int kmax = pieces == 2 ? Ring<2>::KRES_MAX : Ring<1>::KRES_MAX;
+    const int kmax = pieces == 2 ? (nbt == 64 ? Ring<2, 64>::KRES_MAX : Ring<2>::KRES_MAX) : Ring<1>::KRES_MAX;
     int kres = env >= 0 ? env : kmax;
     if (kres > kmax) kres = kmax;
     return kres > KB ? KB : kres;
@@ -1133,15 +1157,17 @@ static int check_coop(const void *kernel, int smem, int grid)
 }
 
 typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
-static KernelFn fwd_kernel(int cell, int pieces)
+static KernelFn fwd_kernel(int cell, int pieces, int nbt)
 {
-    if (cell == CELL_G) return pieces == 2 ? gated_fwd_kernel<CELL_G, 2> : gated_fwd_kernel<CELL_G, 1>;
-    return pieces == 2 ? gated_fwd_kernel<CELL_L, 2> : gated_fwd_kernel<CELL_L, 1>;
+    if (nbt == 64) return cell == CELL_G ? gated_fwd_kernel<CELL_G, 2, 64> : gated_fwd_kernel<CELL_L, 2, 64>;
+    if (cell == CELL_G) return pieces == 2 ? gated_fwd_kernel<CELL_G, 2, 32> : gated_fwd_kernel<CELL_G, 1, 32>;
+    return pieces == 2 ? gated_fwd_kernel<CELL_L, 2, 32> : gated_fwd_kernel<CELL_L, 1, 32>;
 }
-static KernelFn bwd_kernel(int cell, int pieces)
+static KernelFn bwd_kernel(int cell, int pieces, int nbt)
 {
-    if (cell == CELL_G) return pieces == 2 ? gated_bwd_cluster_kernel<CELL_G, 2> : gated_bwd_cluster_kernel<CELL_G, 1>;
-    return pieces == 2 ? gated_bwd_cluster_kernel<CELL_L, 2> : gated_bwd_cluster_kernel<CELL_L, 1>;
+    if (nbt == 64) return cell == CELL_G ? gated_bwd_cluster_kernel<CELL_G, 2, 64> : gated_bwd_cluster_kernel<CELL_L, 2, 64>;
+    if (cell == CELL_G) return pieces == 2 ? gated_bwd_cluster_kernel<CELL_G, 2, 32> : gated_bwd_cluster_kernel<CELL_G, 1, 32>;
+    return pieces == 2 ? gated_bwd_cluster_kernel<CELL_L, 2, 32> : gated_bwd_cluster_kernel<CELL_L, 1, 32>;
 }
 
 }  // namespace lstm
@@ -1186,10 +1212,13 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
     unsigned int *ctr = reinterpret_cast<unsigned int *>(base + L.counters);
     const int G = cell == CELL_G ? 3 : 4;
     const int CPD = H / UPC, grid = 2 * CPD, KB = H / BK;
-    const int smem = pieces == 2 ? Ring<2>::SMEM : SPLIT_SMEM;
-    KernelFn kernel = fwd_kernel(cell, pieces);
-    static int checked_grid[2][2] = {{0, 0}, {0, 0}};
-    int &chk = checked_grid[cell == CELL_G][pieces - 1];
+    // a batch above 32 rows takes the 64-row tile (two-piece arithmetic): one weight stream per step for all of them
+    static const int wide_ok = env_int("CTCASR_LSTM_NO_WIDE", 0) == 0;
+    const int NBT = (B > NB && pieces == 2 && wide_ok) ? 64 : NB;
+    const int smem = pieces == 2 ? (NBT == 64 ? Ring<2, 64>::SMEM : Ring<2>::SMEM) : SPLIT_SMEM;
+    KernelFn kernel = fwd_kernel(cell, pieces, NBT);
+    static int checked_grid[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    int &chk = checked_grid[cell == CELL_G][NBT == 64 ? 2 : pieces - 1];
     if (chk != grid) { int rc = check_coop((const void *)kernel, smem, grid); if (rc) return rc; chk = grid; }
 
     if (G == 3) CTCASR_CUDA_CHECK(cudaMemsetAsync(wp, 0, (size_t)pieces * 2 * 4 * H * H * 2, stream));     // the unused fourth gate group
@@ -1198,19 +1227,19 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
     CUtensorMap mapW, mapH;
     int rc = make_map(&mapW, wp, H, (uint64_t)2 * 4 * H, 128, pieces, pieces);
     if (rc) return rc;
-    rc = make_map(&mapH, hbuf, H, (uint64_t)2 * 2 * NB, NB, pieces, pieces);
+    rc = make_map(&mapH, hbuf, H, (uint64_t)2 * 2 * NBT, NBT, pieces, pieces);
     if (rc) return rc;
     static const int stagger = env_int("CTCASR_LSTM_STAGGER_NS", 11000);
-    // batches above 32 rows run as consecutive launches over 32-row slices of the same buffers
-    for (int b0 = 0; b0 < B; b0 += NB) {
-        CTCASR_CUDA_CHECK(cudaMemsetAsync(hbuf, 0, (size_t)pieces * 2 * 2 * NB * H * 2, stream));  // h_{-1} = 0, padded batch rows = 0
+    // larger batches run as consecutive launches over NBT-row slices of the same buffers
+    for (int b0 = 0; b0 < B; b0 += NBT) {
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(hbuf, 0, (size_t)pieces * 2 * 2 * NBT * H * 2, stream));  // h_{-1} = 0, padded batch rows = 0
         CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
         Params p = {};
-        p.T = T; p.B = B - b0 < NB ? B - b0 : NB; p.BS = B; p.H = H; p.CPD = CPD; p.use_len = use_len;
+        p.T = T; p.B = B - b0 < NBT ? B - b0 : NBT; p.BS = B; p.H = H; p.CPD = CPD; p.use_len = use_len;
         p.forget_bias = forget_bias; p.seq_len = seq_len ? seq_len + b0 : nullptr;
         p.gates = gates + (size_t)b0 * 2 * G * H; p.cstate = cstate + (size_t)b0 * 2 * H; p.y = y + (size_t)b0 * 2 * H;
         p.bias_rn = bias_rn; p.xbuf = hbuf; p.counters = ctr;
-        p.kres = resident_kblocks(KB, pieces);
+        p.kres = resident_kblocks(KB, pieces, NBT);
         p.kb_keep = keep_kblocks(H, 4, pieces, KB);
         p.wpack = wp; p.wrows = 2 * 4 * H; p.wk = H;
         p.trace = g_trace;
@@ -1244,19 +1273,21 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     int rc = CTCASR_OK;
 
     // preferred: 4-CTA cluster split-K kernel (needs H % 128 == 0 and all clusters co-resident)
-    static int cluster_ok_grid[2][2] = {{0, 0}, {0, 0}}, cluster_bad_grid = 0, checked_grid = 0;
+    static int cluster_ok_grid[2][3] = {{0, 0, 0}, {0, 0, 0}}, cluster_bad_grid = 0, checked_grid = 0;
+    static const int wide_ok = env_int("CTCASR_LSTM_NO_WIDE", 0) == 0;
+    int NBT = (B > NB && pieces == 2 && H % 128 == 0 && wide_ok) ? 64 : NB;     // 64-row batch tile: see lstm_tc_fwd
     static const bool no_cluster = getenv("CTCASR_LSTM_NO_CLUSTER") != nullptr;
     bool use_cluster = false;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    KernelFn ckernel = bwd_kernel(cell, pieces);
-    const int csmem = pieces == 2 ? Ring<2>::SMEM : SPLIT_SMEM;
+    KernelFn ckernel = bwd_kernel(cell, pieces, NBT);
+    const int csmem = pieces == 2 ? (NBT == 64 ? Ring<2, 64>::SMEM : Ring<2>::SMEM) : SPLIT_SMEM;
     if (H % 128 == 0 && cluster_bad_grid != grid && (!no_cluster || cell == CELL_G)) {
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = csmem; cfg.stream = stream;
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        int &okg = cluster_ok_grid[cell == CELL_G][pieces - 1];
+        int &okg = cluster_ok_grid[cell == CELL_G][NBT == 64 ? 2 : pieces - 1];
         if (okg != grid) {
             CTCASR_CUDA_CHECK(cudaFuncSetAttribute(ckernel, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem));
             int nclusters = 0;
@@ -1268,11 +1299,12 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     }
     if (!use_cluster) {
         if (cell != CELL_L) return fail(CTCASR_ERR_UNSUPPORTED, "lstm_tc: the GRU backward pass needs the cluster kernel");
-        pieces = 2;                                       // the single-CTA kernel is two-piece only
+        pieces = 2;                                       // the single-CTA kernel is two-piece, 32 rows only
+        NBT = NB;
     }
     split_kernel<<<148 * 8, 256, 0, stream>>>(wh, wq, nw, pieces);
     CTCASR_LAUNCH_CHECK();
-    rc = make_map(&mapZ, zbuf, (uint64_t)GH, (uint64_t)2 * 2 * NB, NB, use_cluster ? pieces : 1, pieces);
+    rc = make_map(&mapZ, zbuf, (uint64_t)GH, (uint64_t)2 * 2 * NBT, NBT, use_cluster ? pieces : 1, pieces);
     if (rc) return rc;
     if (use_cluster) {
         rc = make_map(&mapW, wq, (uint64_t)GH, (uint64_t)2 * H, 128, pieces, pieces);
@@ -1283,16 +1315,16 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
     if (rc) return rc;
     static const int stagger = env_int("CTCASR_LSTM_STAGGER_NS", 11000);
     const int KB = GH / 4 / BK;
-    for (int b0 = 0; b0 < B; b0 += NB) {
-        CTCASR_CUDA_CHECK(cudaMemsetAsync(zbuf, 0, (size_t)pieces * 2 * 2 * NB * GH * 2, stream));  // no recurrent gradient into the last step
+    for (int b0 = 0; b0 < B; b0 += NBT) {
+        CTCASR_CUDA_CHECK(cudaMemsetAsync(zbuf, 0, (size_t)pieces * 2 * 2 * NBT * GH * 2, stream));  // no recurrent gradient into the last step
         CTCASR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 64, stream));
         Params p = {};
-        p.T = T; p.B = B - b0 < NB ? B - b0 : NB; p.BS = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = 0.f;
+        p.T = T; p.B = B - b0 < NBT ? B - b0 : NBT; p.BS = B; p.H = H; p.CPD = CPD; p.use_len = use_len; p.forget_bias = 0.f;
         p.seq_len = seq_len ? seq_len + b0 : nullptr;
         p.gates = gates + (size_t)b0 * 2 * GH; p.cstate = const_cast<float *>(cstate) + (size_t)b0 * 2 * H;
         p.y = const_cast<float *>(y) + (size_t)b0 * 2 * H;
         p.dy = dy + (size_t)b0 * 2 * H; p.dzr = dzr ? dzr + (size_t)b0 * 2 * GH : nullptr; p.xbuf = zbuf; p.counters = ctr;
-        p.kres = use_cluster ? resident_kblocks(KB, pieces) : 0; p.wpack = wq; p.wrows = 2 * H; p.wk = GH;
+        p.kres = use_cluster ? resident_kblocks(KB, pieces, NBT) : 0; p.wpack = wq; p.wrows = 2 * H; p.wk = GH;
         p.kb_keep = keep_kblocks(H, G, pieces, KB);
         p.dbias = use_cluster ? dbias : nullptr; p.db_accum = b0 > 0;
         p.trace = nullptr;

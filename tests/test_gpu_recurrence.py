@@ -68,11 +68,12 @@ def test_one_gate_persistent_layer_vs_oracle(cell, use_len, T, B, nin, H):
     assert fl < 12 + 2 * ((B + 31) // 32) and bl < 40, (fl, bl)
 
 
-@pytest.mark.parametrize("cell", ["rnn_tanh", "rnn_relu", "lstm", "gru"])
-def test_full_width_layer_vs_oracle(cell):
+@pytest.mark.parametrize("cell,B", [("rnn_tanh", 32), ("rnn_relu", 32), ("lstm", 32), ("gru", 32), ("lstm", 64), ("gru", 64), ("lstm", 70)])
+def test_full_width_layer_vs_oracle(cell, B):
     """One H = 2048 layer per cell (the benchmarked width: 128 CTAs, every k-block path, L2 policies)
-    against the fp64 oracle."""
-    _layer(cell, T=6, B=32, nin=64, H=2048, use_len=True, seed=5)
+    against the fp64 oracle.  B = 64 / 70: the 64-row batch tile of the gated kernels (BASELINE cfg4's batch size; one
+    weight stream per time step for all 64 rows), 70 = a full tile plus a 6-row one."""
+    _layer(cell, T=6, B=B, nin=64, H=2048, use_len=True, seed=5)
 
 
 @pytest.mark.parametrize("use_len", [True, False])
