@@ -35,9 +35,13 @@ def test_header_symbols_are_exported(lib):
 
 def test_abi_version_and_workspace_queries(lib):
     assert lib.ctcasr_abi_version() == 1
-    # cfg5: B=512, T=1700, L=84, V=29 -> checkpoints only, never the [T,S] alpha table
+    # cfg5: B=512, T=1700, L=84, V=29 -> the warp kernel's spilled rows: [B][T][32 lanes x 6 states] (m, e) pairs, one table
+    # shared by the alpha half and the beta half of every utterance
     ws = lib.ctcasr_ctc_workspace_bytes(1700, 512, 29, 84)
-    assert 0 < ws < 512 * 1700 * 169 * 8 / 4        # (hi, lo) checkpoint rows every 8 frames, not the table
+    assert ws == 512 * 1700 * 192 * 8
+    # long labels (2L+1 > 384) take the block kernel: checkpoint rows every 8 frames, never the [T,S] table
+    ws = lib.ctcasr_ctc_workspace_bytes(1700, 64, 29, 422)
+    assert 0 < ws < 64 * 1700 * 845 * 8 / 4
     assert lib.ctcasr_ctc_workspace_bytes(10, 1, 500, 4) == 0          # V > 128 is unsupported
     rb = lib.ctcasr_birnn_reserve_bytes(1000, 32, 2048, 2048, _lib.CELL_LSTM)
     assert rb >= 1000 * 32 * (2 * 4 * 2048 + 2 * 2048) * 4
