@@ -62,7 +62,8 @@ template <int PIECES, int NBT = NB> struct Ring {
 // PIECES = 1 runs two rings whose stages hold GK = 2 consecutive k-blocks: NSA stages of streamed weight tiles (2 x 16
 // KB; the k-blocks resident in tensor memory never enter it, so the producer prefetches a whole ring of the next
 // step's tiles during the serial tail of this one) and NSB stages of state tiles (2 x 4 KB).  A step visits the
-// streamed k-blocks first, then the resident ones.  Two k-blocks per barrier because a (satisfied) mbarrier wait and
+// groups in the order of Params::order: pairs of streamed groups alternate with pairs of resident ones, so that the
+// weight ring refills while the issuers work on resident groups.  Two k-blocks per barrier because a (satisfied) mbarrier wait and
 // a commit cost the issuing thread as much as three of its 45-cycle MMAs (tools/ubench/mma_loop.cu).
 // (One shared ring, or all state tiles in one burst with a 5-stage weight ring, kept too few bytes in flight: the step
 // was bound by TMA latency per ring turn, 7.2 of 12.6 us at H = 2048.)
@@ -109,6 +110,8 @@ struct Params {
     int wrows, wk;           // rows and K (row pitch) of wpack
     int stagger_ns;          // start delay of direction 1
     int kb_keep;             // weight k-blocks [0, kb_keep) are loaded with L2 evict_last, the rest evict_first
+    int nunits, nsg;         // PIECES = 1: groups per step; the first nsg group ids are streamed groups, the rest resident
+    unsigned char order[24]; //   group id visited at position u (issuer u & 1)
     float *dbias;            // bwd (cluster kernel): [2GH (+2H GRU)] column sums of dz, or null
     int db_accum;            // add to dbias instead of storing (batch slices after the first)
 };
@@ -168,7 +171,7 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = blockIdx.x / p.CPD, c = blockIdx.x % p.CPD;
     const int T = p.T, B = p.B, H = p.H, KB = H / BK;
-    const bool TWO_ACC = (PIECES == 1 ? (KB + GK - 1) / GK : KB) > 1;      // the second issuer had work: add its accumulator
+    const bool TWO_ACC = (PIECES == 1 ? p.nunits : KB) > 1;      // the second issuer had work: add its accumulator
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), FULLB ? 1 : 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
@@ -212,14 +215,15 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int i = 0; i < T; ++i)
                 if (FULLB) {
-                    const int ns = KB - p.kres;                     // streamed k-blocks come first in the visiting order
-                    for (int g = 0; GK * g < ns; ++g) {
-                        SubRing &r = ring[g & 1];
-                        const int stage = r.slot(), cnt = min(GK, ns - GK * g);
+                    for (int u = 0; u < p.nunits; ++u) {
+                        const int gid = p.order[u];
+                        if (gid >= p.nsg) continue;                 // resident group: no ring traffic at all
+                        SubRing &r = ring[u & 1];
+                        const int stage = r.slot(), cnt = min(GK, KB - p.kres - GK * gid);
                         ptx::mbar_wait(empty(stage), r.phase ^ 1);
                         ptx::mbar_expect_tx(fullA(stage), (uint32_t)cnt * F_A_PIECE);
                         for (int q2 = 0; q2 < cnt; ++q2) {
-                            const int kb = p.kres + GK * g + q2;
+                            const int kb = p.kres + GK * gid + q2;
                             const uint64_t pol = kb - p.kres < p.kb_keep ? keep : stream;
                             ptx::tma_load_3d_hint(a_addr(stage, q2), &mapW, kb * BK, row0, 0, fullA(stage), pol);
                         }
@@ -255,16 +259,16 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 stamp(p, i, 0);
                 const int row0 = (d * 2 + (i & 1)) * NBT;
                 if (FULLB) {        // own ring, GK tiles of 4 KB per stage, in the step's visiting order
-                    for (int g = 0; GK * g < KB; ++g) {
-                        SubRing &r = ringB[g & 1];
-                        const int stage = r.slot(), cnt = min(GK, KB - GK * g);
+                    for (int u = 0; u < p.nunits; ++u) {
+                        const int gid = p.order[u];
+                        const int kb0 = gid < p.nsg ? p.kres + GK * gid : GK * (gid - p.nsg);
+                        const int cnt = min(GK, (gid < p.nsg ? KB : p.kres) - kb0);
+                        SubRing &r = ringB[u & 1];
+                        const int stage = r.slot();
                         ptx::mbar_wait(emptyB(stage), r.phase ^ 1);
                         ptx::mbar_expect_tx(fullB(stage), (uint32_t)cnt * F_B_PIECE);
-                        for (int q2 = 0; q2 < cnt; ++q2) {
-                            const int m = GK * g + q2;
-                            const int kb = m < KB - p.kres ? p.kres + m : m - (KB - p.kres);
-                            ptx::tma_load_3d(bbuf + (uint32_t)(stage * GK + q2) * F_B_PIECE, &mapH, kb * BK, row0, 0, fullB(stage));
-                        }
+                        for (int q2 = 0; q2 < cnt; ++q2)
+                            ptx::tma_load_3d(bbuf + (uint32_t)(stage * GK + q2) * F_B_PIECE, &mapH, (kb0 + q2) * BK, row0, 0, fullB(stage));
                         r.advance();
                     }
                 } else {
@@ -294,17 +298,18 @@ gated_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
                 // a unit of issue = one k-block, or (FULLB) a group of GK k-blocks behind one pair of barriers
-                const int NU = FULLB ? (KB + GK - 1) / GK : KB;
+                const int NU = FULLB ? p.nunits : KB;
                 for (int u = me; u < NU; u += 2) {
                     const int stage = ring.slot(), stageB = ringB.slot();
-                    const int cnt = FULLB ? min(GK, KB - GK * u) : 1;
-                    const bool ringed = !FULLB || GK * u < KB - p.kres;     // this unit's weights go through the ring (streamed k-blocks come first)
+                    const int gid = FULLB ? p.order[u] : 0;
+                    const bool ringed = !FULLB || gid < p.nsg;              // this unit's weights go through the ring
+                    const int kb0 = FULLB ? (ringed ? p.kres + GK * gid : GK * (gid - p.nsg)) : u;
+                    const int cnt = FULLB ? min(GK, (ringed ? KB : p.kres) - kb0) : 1;
                     if (FULLB) ptx::mbar_wait(fullB(stageB), ringB.phase);
                     if (ringed) ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
                   for (int q2 = 0; q2 < cnt; ++q2) {
-                    const int m = FULLB ? GK * u + q2 : u;
-                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;
+                    const int kb = kb0 + q2;
                     const int first = u == me && q2 == 0;
                     const uint64_t bd = ptx::make_smem_desc(FULLB ? bbuf + (uint32_t)(stageB * GK + q2) * F_B_PIECE : b_addr(stage, 0), 16, 1024, 2);
                     if (PIECES == 2) {
@@ -716,7 +721,7 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
     const int UBD = p.H / 128;                                  // unit blocks per direction
     const int d = cid / UBD, ub = cid % UBD;
     const int T = p.T, B = p.B, H = p.H, GH = G * H, KQ = GH / 4, KB = KQ / BK;
-    const bool TWO_ACC = (PIECES == 1 ? (KB + GK - 1) / GK : KB) > 1;
+    const bool TWO_ACC = (PIECES == 1 ? p.nunits : KB) > 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(fullA(s), FULLB ? 1 : 2); ptx::mbar_init(empty(s), 1); }   // full: weight + state producer
@@ -759,14 +764,15 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
             const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
             for (int n = 0; n < T; ++n)
                 if (FULLB) {
-                    const int ns = KB - p.kres;                     // streamed k-blocks come first in the visiting order
-                    for (int g = 0; GK * g < ns; ++g) {
-                        SubRing &r = ring[g & 1];
-                        const int stage = r.slot(), cnt = min(GK, ns - GK * g);
+                    for (int u = 0; u < p.nunits; ++u) {
+                        const int gid = p.order[u];
+                        if (gid >= p.nsg) continue;                 // resident group: no ring traffic at all
+                        SubRing &r = ring[u & 1];
+                        const int stage = r.slot(), cnt = min(GK, KB - p.kres - GK * gid);
                         ptx::mbar_wait(empty(stage), r.phase ^ 1);
                         ptx::mbar_expect_tx(fullA(stage), (uint32_t)cnt * F_A_PIECE);
                         for (int q2 = 0; q2 < cnt; ++q2) {
-                            const int kb = p.kres + GK * g + q2;
+                            const int kb = p.kres + GK * gid + q2;
                             const uint64_t pol = kb - p.kres < p.kb_keep ? keep : stream;
                             ptx::tma_load_3d_hint(a_addr(stage, q2), &mapW, q * KQ + kb * BK, row0, 0, fullA(stage), pol);
                         }
@@ -799,16 +805,16 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                 ptx::fence_proxy_async();
                 const int row0 = (d * 2 + (n & 1)) * NBT;
                 if (FULLB) {        // own ring, GK tiles of 4 KB per stage, in the step's visiting order
-                    for (int g = 0; GK * g < KB; ++g) {
-                        SubRing &r = ringB[g & 1];
-                        const int stage = r.slot(), cnt = min(GK, KB - GK * g);
+                    for (int u = 0; u < p.nunits; ++u) {
+                        const int gid = p.order[u];
+                        const int kb0 = gid < p.nsg ? p.kres + GK * gid : GK * (gid - p.nsg);
+                        const int cnt = min(GK, (gid < p.nsg ? KB : p.kres) - kb0);
+                        SubRing &r = ringB[u & 1];
+                        const int stage = r.slot();
                         ptx::mbar_wait(emptyB(stage), r.phase ^ 1);
                         ptx::mbar_expect_tx(fullB(stage), (uint32_t)cnt * F_B_PIECE);
-                        for (int q2 = 0; q2 < cnt; ++q2) {
-                            const int m = GK * g + q2;
-                            const int kb = m < KB - p.kres ? p.kres + m : m - (KB - p.kres);
-                            ptx::tma_load_3d(bbuf + (uint32_t)(stage * GK + q2) * F_B_PIECE, &mapZ, q * KQ + kb * BK, row0, 0, fullB(stage));
-                        }
+                        for (int q2 = 0; q2 < cnt; ++q2)
+                            ptx::tma_load_3d(bbuf + (uint32_t)(stage * GK + q2) * F_B_PIECE, &mapZ, q * KQ + (kb0 + q2) * BK, row0, 0, fullB(stage));
                         r.advance();
                     }
                 } else {
@@ -834,17 +840,18 @@ gated_bwd_cluster_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_
                 ptx::mbar_wait(tempty, tphase ^ 1);
                 ptx::tc_fence_after();
                 // a unit of issue = one k-block, or (FULLB) a group of GK k-blocks behind one pair of barriers
-                const int NU = FULLB ? (KB + GK - 1) / GK : KB;
+                const int NU = FULLB ? p.nunits : KB;
                 for (int u = me; u < NU; u += 2) {
                     const int stage = ring.slot(), stageB = ringB.slot();
-                    const int cnt = FULLB ? min(GK, KB - GK * u) : 1;
-                    const bool ringed = !FULLB || GK * u < KB - p.kres;     // this unit's weights go through the ring (streamed k-blocks come first)
+                    const int gid = FULLB ? p.order[u] : 0;
+                    const bool ringed = !FULLB || gid < p.nsg;              // this unit's weights go through the ring
+                    const int kb0 = FULLB ? (ringed ? p.kres + GK * gid : GK * (gid - p.nsg)) : u;
+                    const int cnt = FULLB ? min(GK, (ringed ? KB : p.kres) - kb0) : 1;
                     if (FULLB) ptx::mbar_wait(fullB(stageB), ringB.phase);
                     if (ringed) ptx::mbar_wait(fullA(stage), ring.phase);
                     ptx::tc_fence_after();
                   for (int q2 = 0; q2 < cnt; ++q2) {
-                    const int m = FULLB ? GK * u + q2 : u;
-                    const int kb = FULLB ? (m < KB - p.kres ? p.kres + m : m - (KB - p.kres)) : m;
+                    const int kb = kb0 + q2;
                     const int first = u == me && q2 == 0;
                     const uint64_t bd = ptx::make_smem_desc(FULLB ? bbuf + (uint32_t)(stageB * GK + q2) * F_B_PIECE : b_addr(stage, 0), 16, 1024, 2);
                     if (PIECES == 2) {
@@ -1143,6 +1150,20 @@ static int resident_kblocks(int KB, int pieces, int nbt = NB)
     return kres > KB ? KB : kres;
 }
 
+// visiting order of the single-piece kernels: group ids 0 .. nsg-1 are the streamed groups (GK k-blocks from kres on),
+// nsg .. the resident ones; pairs of streamed groups alternate with pairs of resident groups (each issuer gets one of
+// every pair), the longer kind fills the end
+static void fill_order(Params &p, int KB)
+{
+    const int ns = KB - p.kres, nsg = (ns + GK - 1) / GK, nrg = (p.kres + GK - 1) / GK;
+    p.nsg = nsg; p.nunits = 0;
+    int is = 0, ir = 0;
+    while (is < nsg || ir < nrg) {
+        for (int k = 0; k < 2 && is < nsg; ++k) p.order[p.nunits++] = (unsigned char)(is++);
+        for (int k = 0; k < 2 && ir < nrg; ++k) p.order[p.nunits++] = (unsigned char)(nsg + ir++);
+    }
+}
+
 static int check_coop(const void *kernel, int smem, int grid)
 {
     int dev = 0, sms = 0, per_sm = 0, coop = 0;
@@ -1242,6 +1263,7 @@ int lstm_tc_fwd(const int *seq_len, const float *wh, float *gates, float *cstate
         p.kres = resident_kblocks(KB, pieces, NBT);
         p.kb_keep = keep_kblocks(H, 4, pieces, KB);
         p.wpack = wp; p.wrows = 2 * 4 * H; p.wk = H;
+        fill_order(p, KB);
         p.trace = g_trace;
         p.stagger_ns = stagger;
         cudaLaunchConfig_t cfg = {};
@@ -1326,6 +1348,7 @@ int lstm_tc_bwd(const int *seq_len, const float *wh, float *gates, const float *
         p.dy = dy + (size_t)b0 * 2 * H; p.dzr = dzr ? dzr + (size_t)b0 * 2 * GH : nullptr; p.xbuf = zbuf; p.counters = ctr;
         p.kres = use_cluster ? resident_kblocks(KB, pieces, NBT) : 0; p.wpack = wq; p.wrows = 2 * H; p.wk = GH;
         p.kb_keep = keep_kblocks(H, G, pieces, KB);
+        fill_order(p, KB);
         p.dbias = use_cluster ? dbias : nullptr; p.db_accum = b0 > 0;
         p.trace = nullptr;
         p.stagger_ns = stagger;
