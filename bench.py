@@ -199,12 +199,20 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = make_cfg(args)
     ccfg = cfg.replace(dense_dropout_rate=0.0)
-    sample_T = args.cpu_sample_frames or CPU_SAMPLE_FRAMES
     t0 = time.perf_counter()
+    # bounded sample: B utterances x sample_T frames per step.  BASELINE.md section 5 asks for T = 250; the whole
+    # --steps K --warmup W run has to end within a few minutes, so sample_T is what a 5-minute budget allows at the speed
+    # a 16-frame calibration step shows, between 64 and 250 frames (250 whenever K + W <= ~11 steps on 16 cores)
+    sample_T = args.cpu_sample_frames
+    if not sample_T:
+        _, dt16, _ = cpu_reference_frames_per_s(ccfg, args.batch, 16, CFG2_L, steps=1, warmup=0)
+        per_frame = dt16 / 16.0
+        sample_T = int(max(64, min(CPU_SAMPLE_FRAMES, 300.0 / ((args.steps + args.warmup) * per_frame))))
     fps, dt, cores = cpu_reference_frames_per_s(ccfg, args.batch, sample_T, CFG2_L, steps=args.steps, warmup=args.warmup)
-    sample = ("each step = B=%d utterances x %d frames (of the workload's %d; per-frame cost is independent of T), %d warm-up + %d timed "
-              "steps, torch-CPU restatement of the reference's TF graph (oracle/torch_ref.py; TF 1.12 is not installable offline), "
-              "all %d host threads" % (args.batch, sample_T, args.frames, args.warmup, args.steps, cores))
+    sample = ("each step = B=%d utterances x %d frames (of the workload's %d; per-frame cost is independent of T, the per-step fixed costs "
+              "- Adam over all parameters, Python dispatch - are included), %d warm-up + %d timed steps, torch-CPU restatement of the "
+              "reference's TF graph (oracle/torch_ref.py; TF 1.12 is not installable offline), all %d host threads, no dropout" % (
+                  args.batch, sample_T, args.frames, args.warmup, args.steps, cores))
     line = {
         "impl": "reference", "metric": "audio-frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
