@@ -17,9 +17,15 @@
 //      (parent id, label): a prefix that leaves the beam and later comes back is the same node, so
 //      its still-active descendants find it again (TF keeps the tree object for the same reason).
 // After the last frame the best prefix is read off the parent chain.
-// This is TF's algorithm with the beam defined order-independently (see oracle/beam_search.h,
-// `reoffer_wipe`); scores use the same fixed sequence of IEEE operations as the oracle
-// (softplus_neg below), so transcripts can be compared bit for bit.
+// Steps 3-4 define the beam order-independently: the beam_width best of {re-scored prefixes} U {absent children}.  TF
+// r1.12's Step() visits the prefixes in descending order of their previous score and grows the beam sequentially; the
+// result is the same set EXCEPT for one order-dependent side effect (oracle/beam_search.h, `reoffer_wipe`): a prefix X
+// that is pushed out of the beam in the middle of the grow loop and then re-offered (and rejected) as a child of its
+// parent P, when P's turn comes before X's own, no longer offers its own children.  Step 4b detects the frames in which
+// that can change the beam (X does not survive, P ranks before X, X has a child that would survive) and replays TF's
+// sequential loop for them, heap and all, in one thread; every other frame takes the parallel path.  Scores use the same
+// fixed sequence of IEEE operations as the oracle (softplus_neg below), so transcripts can be compared bit for bit with
+// the TF-faithful oracle mode.
 #include "common.cuh"
 
 #include <math.h>
@@ -138,6 +144,12 @@ __global__ void __launch_bounds__(NT, 1) beam_search_kernel(const Params p)
     float *nbl = reinterpret_cast<float *>(ip); ip += MAXW;       // re-scored blank
     float *nlb = reinterpret_cast<float *>(ip); ip += MAXW;       // re-scored label
     uint32_t *present = reinterpret_cast<uint32_t *>(ip); ip += MAXW;
+    int *psl = ip; ip += MAXW;                                    // slot of the parent prefix in the beam, or -1
+    int *chead = ip; ip += MAXW;                                  // step 4b: list of the children of a prefix that are in the beam
+    int *cnext = ip; ip += MAXW;
+    unsigned char *gone = reinterpret_cast<unsigned char *>(ip); ip += MAXW / 4;      // step 4b: pushed out of the beam
+    unsigned char *wiped = reinterpret_cast<unsigned char *>(ip); ip += MAXW / 4;     //          lost its right to grow
+    uint32_t *keep = reinterpret_cast<uint32_t *>(ip); ip += (MAXW * MAXV) / 32;      //          members of the final heap, one bit per candidate
     int *hkey = ip; ip += SLOTS;
     int *hval = ip; ip += SLOTS;
     int *hist = ip; ip += 256;
@@ -189,12 +201,14 @@ __global__ void __launch_bounds__(NT, 1) beam_search_kernel(const Params p)
         if (tid < n) {
             const int lab = B0.lab[tid], par = B0.par[tid];
             float prev = -INFINITY;
+            int pslot = -1;
             if (par >= 0) {
                 uint32_t h = ((uint32_t)par * 2654435761u) >> 21;
                 for (;;) {
                     const int k = hkey[h];
                     if (k == par) {
                         const int ps = hval[h];
+                        pslot = ps;
                         prev = lab == B0.lab[ps] ? B0.pb[ps] : B0.pt[ps];
                         atomicOr(&present[ps], 1u << lab);
                         break;
@@ -207,6 +221,7 @@ __global__ void __launch_bounds__(NT, 1) beam_search_kernel(const Params p)
             const float nb = __fadd_rn(B0.pt[tid], y[blank]);
             my_tot = lse(nb, nl);
             nbl[tid] = nb; nlb[tid] = nl;
+            psl[tid] = pslot;
         }
         if (tid < W) cand[tid] = my_tot;
         __syncthreads();
@@ -275,6 +290,125 @@ __global__ void __launch_bounds__(NT, 1) beam_search_kernel(const Params p)
                 __syncthreads();
             }
             thr = prefix; k_eq = k;
+        }
+        // ---- 4b. TF's order-dependent side effect (header comment): detect, and replay sequentially if it can matter ----
+        {
+            bool susp = false;
+            if (tid < n && M > W) {
+                const int ps = psl[tid];
+                if (ps >= 0 && B0.pt[ps] >= B0.pt[tid] && okey(cand[tid]) <= thr) {
+                    const float *row = cand + W + tid * VC;
+                    float mx = -INFINITY;
+                    for (int c = 0; c < VC; ++c) mx = fmaxf(mx, row[c]);
+                    susp = mx > -INFINITY && okey(mx) >= thr;
+                }
+            }
+            if (__syncthreads_or(susp)) {
+                // the hash table is free now: heap of at most W entries {score, push order, candidate index} + rank -> slot
+                float *hk = reinterpret_cast<float *>(hkey);
+                int *hs = hkey + MAXW, *hr = hval, *byrank = hval + MAXW;
+                if (tid < n) {      // TF's visiting order: descending previous score, earlier entry first on ties
+                    const float me = B0.pt[tid];
+                    int r = 0;
+                    for (int j = 0; j < n; ++j) { const float o = B0.pt[j]; r += (o > me) || (o == me && j < tid); }
+                    byrank[r] = tid;
+                    chead[tid] = -1; gone[tid] = 0; wiped[tid] = 0;
+                }
+                for (int i = tid; i < (NC + 31) / 32; i += NT) keep[i] = 0u;
+                __syncthreads();
+                if (tid < n && psl[tid] >= 0) cnext[tid] = atomicExch(&chead[psl[tid]], tid);
+                __syncthreads();
+                if (tid < 32) {
+                    // Warp 0 replays TF's grow loop.  The beam members live in an unsorted array (lane l owns entries
+                    // l, l+32, ...); "bottom" = the minimum by (score, later push first), kept as a per-lane minimum +
+                    // a shuffle reduction.  A child that fails against the current bottom fails against every later
+                    // one (the bottom only rises), so the 28 children of a prefix are screened with one ballot and only
+                    // the survivors are taken one by one, in class order.
+                    int hn = n, seq = n;
+                    for (int k = lane; k < n; k += 32) { const int sl = byrank[k]; hk[k] = cand[sl]; hs[k] = k; hr[k] = sl; }
+                    __syncwarp();
+                    float lmk; int lms, lmi;                        // my lowest entry
+                    auto lower = [](float ka, int sa, float kb, int sb) { return ka < kb || (ka == kb && sa > sb); };
+                    auto local_min = [&]() {
+                        lmk = INFINITY; lms = -1; lmi = -1;
+                        for (int k = lane; k < hn; k += 32)
+                            if (lmi < 0 || lower(hk[k], hs[k], lmk, lms)) { lmk = hk[k]; lms = hs[k]; lmi = k; }
+                    };
+                    float bk; int bs, bi;                           // the bottom of the beam
+                    auto bottom = [&]() {
+                        bk = lmk; bs = lms; bi = lmi;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ok2 = __shfl_xor_sync(0xffffffffu, bk, o);
+                            const int os = __shfl_xor_sync(0xffffffffu, bs, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (oi >= 0 && (bi < 0 || lower(ok2, os, bk, bs))) { bk = ok2; bs = os; bi = oi; }
+                        }
+                    };
+                    local_min();
+                    bottom();
+                    for (int r = 0; r < n; ++r) {
+                        const int i = byrank[r];
+                        __syncwarp();
+                        if (wiped[i]) continue;
+                        const float pti = B0.pt[i];
+                        if (!(pti > -INFINITY && (hn < W || pti > bk))) continue;
+                        const int lab = B0.lab[i];
+                        const uint32_t pres = present[i];
+                        float sc = -INFINITY;
+                        int sx = -1;
+                        const int c = lane;
+                        if (c < VC) {
+                            if ((pres >> c) & 1u) {     // this child is a prefix of the beam: only of interest once it has been pushed out
+                                sx = chead[i];
+                                while (sx >= 0 && B0.lab[sx] != c) sx = cnext[sx];
+                                if (sx >= 0 && gone[sx]) sc = __fadd_rn(y[c], c == lab ? B0.pb[i] : pti);
+                                else sx = -1;
+                            } else {
+                                sc = cand[W + i * VC + c];
+                            }
+                        }
+                        const bool pass = sc > -INFINITY && (hn < W || sc > bk);
+                        if (sx >= 0 && !pass) wiped[sx] = 1;            // re-offered and rejected
+                        uint32_t todo = __ballot_sync(0xffffffffu, pass);
+                        while (todo) {
+                            const int cc = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const float s2 = __shfl_sync(0xffffffffu, sc, cc);
+                            const int sx2 = __shfl_sync(0xffffffffu, sx, cc);
+                            const int idx = W + i * VC + cc;
+                            if (hn < W || s2 > bk) {
+                                int at = hn;
+                                if (hn == W) {
+                                    at = bi;
+                                    const int e = hr[bi];
+                                    if (lane == 0 && e < W) {
+                                        gone[e] = 1;
+                                        // a child of THIS prefix that is still ahead in class order is re-offered right away: rejected
+                                        // (its fresh score cannot exceed the re-scored one that has just been the bottom)
+                                        if (psl[e] == i && B0.lab[e] > cc) wiped[e] = 1;
+                                    }
+                                } else {
+                                    ++hn;
+                                }
+                                if (lane == (at & 31)) { hk[at] = s2; hs[at] = seq; hr[at] = idx; if (sx2 >= 0) cand[idx] = s2; }
+                                ++seq;
+                                __syncwarp();
+                                if (lane == (at & 31)) local_min();
+                                bottom();
+                            } else if (sx2 >= 0 && lane == 0) {
+                                wiped[sx2] = 1;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    for (int k = lane; k < hn; k += 32) atomicOr(&keep[hr[k] >> 5], 1u << (hr[k] & 31));
+                }
+                __syncthreads();
+                for (int i = tid; i < NC; i += NT)
+                    if (!((keep[i >> 5] >> (i & 31)) & 1u)) cand[i] = -INFINITY;
+                thr = KEY_NEG_INF + 1u; k_eq = 0x7fffffff;                  // the survivors are exactly the finite candidates
+                __syncthreads();
+            }
         }
         // ---- stable compaction: a contiguous run of candidates per thread ----
         const int per = (NC + NT - 1) / NT;
@@ -365,7 +499,8 @@ static size_t nodes_per_utt(int T, int W) { return (size_t)T * W + 1; }
 static size_t table_per_utt(int T, int W) { return 2 * ((size_t)T * W + 1) + 1; }
 static size_t smem_bytes(int W, int V)
 {
-    return sizeof(int) * ((size_t)12 * MAXW + 3 * MAXW + 2 * SLOTS + 256 + 40 + MAXV + 8) + sizeof(float) * (size_t)W * V;
+    return sizeof(int) * ((size_t)12 * MAXW + 3 * MAXW + 3 * MAXW + MAXW / 2 + MAXW * MAXV / 32 + 2 * SLOTS + 256 + 40 + MAXV + 8) +
+           sizeof(float) * (size_t)W * V;
 }
 
 }  // namespace beam

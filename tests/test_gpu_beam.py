@@ -1,6 +1,7 @@
 """GPU parity of the CTC prefix beam search (decode_fn's decoder, asr/model.py:292-296) against the
-oracle's restatement of TF's CTCBeamSearchDecoder.  Integer work: transcripts and lengths bit-exact
-(the kernel and the oracle evaluate log-sum-exp with the same IEEE operation sequence); the best
+oracle's restatement of TF's CTCBeamSearchDecoder in its TF-faithful mode (reoffer_wipe=True: including the
+order-dependent side effect of TF's Step(), oracle/beam_search.h).  Integer work: transcripts and lengths
+bit-exact (the kernel and the oracle evaluate log-sum-exp with the same IEEE operation sequence); the best
 path's log-score to 1e-5."""
 import numpy as np
 import pytest
@@ -18,7 +19,7 @@ pytestmark = pytest.mark.gpu
 def _check(x, sl, W, merge=False):
     ids, n, lp = ops.beam_search(dev(x), dev(sl, torch.int32), beam_width=W, merge_repeated=merge)
     torch.cuda.synchronize()
-    oi, on, olp = ref.ctc_beam_search(x, sl, beam_width=W, merge_repeated=merge)
+    oi, on, olp = ref.ctc_beam_search(x, sl, beam_width=W, merge_repeated=merge, reoffer_wipe=True)
     ids, n, lp = ids.cpu().numpy(), n.cpu().numpy(), lp.cpu().numpy()
     assert np.array_equal(n, on), (n, on)
     assert np.array_equal(ids, oi)
@@ -82,33 +83,20 @@ def test_decode_fn_uses_the_reference_decoder_at_full_size():
     assert all(torch.equal(a, c) for a, c in zip(decoded, d2))
 
 
-def test_divergence_from_the_tf_step_artifact_is_quantified():
-    """The kernel implements the order-independent beam (top beam_width of {re-scored leaves} U {absent children});
-    TF r1.12's Step(), as recalled, additionally wipes a leaf that is evicted and re-offered inside the grow loop
-    (oracle reoffer_wipe=True, oracle/beam_search.h).  Measured here against that TF-faithful oracle mode: on
-    model-like (peaked) frames the transcripts are always identical; on flat random logits, where thousands of
-    prefixes score within a few nats, a small share of utterances differs by a few labels."""
-    from ctc_asr_b200 import metrics
+def test_tf_step_order_artifact_is_reproduced():
+    """TF r1.12's Step() wipes a prefix that is pushed out of the beam and re-offered inside the grow loop (oracle
+    reoffer_wipe=True).  On flat random logits, where thousands of prefixes score within a few nats, that changes a few
+    transcripts relative to the order-independent beam (reoffer_wipe=False); the kernel detects those frames, replays
+    TF's sequential loop for them and must equal the TF-faithful mode everywhere — and this test only means something
+    if the two oracle modes do differ on its inputs."""
     rng = np.random.default_rng(11)
     T, B, V = 50, 32, 29
-    same, total, dist = 0, 0, []
-    for W, scale in ((16, 1.0), (256, 1.0), (256, 3.0)):
+    differ = 0
+    for W, scale in ((16, 1.0), (256, 1.0), (256, 3.0), (64, 0.5)):
         x = (rng.standard_normal((T, B, V)) * scale).astype(np.float32)
         sl = np.full(B, T, np.int32)
-        ids, n, _ = ops.beam_search(dev(x), dev(sl, torch.int32), beam_width=W)
-        ids, n = ids.cpu().numpy(), n.cpu().numpy()
-        ti, tn, _ = ref.ctc_beam_search(x, sl, beam_width=W, reoffer_wipe=True)
-        for b in range(B):
-            eq = n[b] == tn[b] and np.array_equal(ids[b, :n[b]], ti[b, :tn[b]])
-            same += int(eq); total += 1
-            dist.append(metrics.levenshtein(list(ids[b, :n[b]]), list(ti[b, :tn[b]])) / max(tn[b], 1))
-    print("flat random logits: %d of %d transcripts identical to the TF-faithful oracle mode, mean normalised edit distance %.4f"
-          % (same, total, float(np.mean(dist))))
-    assert same >= 0.85 * total and np.mean(dist) < 0.02
-    # peaked frames (what a trained acoustic model emits): identical
-    cls = rng.integers(0, V, (T, B)); cls[rng.random((T, B)) < 0.5] = V - 1
-    x = rng.standard_normal((T, B, V)).astype(np.float32)
-    np.put_along_axis(x, cls[..., None], 8.0, axis=2)
-    ids, n, _ = ops.beam_search(dev(x), dev(sl, torch.int32), beam_width=1024)
-    ti, tn, _ = ref.ctc_beam_search(x, sl, beam_width=1024, reoffer_wipe=True)
-    assert np.array_equal(n.cpu().numpy(), tn) and np.array_equal(ids.cpu().numpy(), ti)
+        ids, n = _check(x, sl, W)                                   # == reoffer_wipe=True, bit for bit
+        pi, pn, _ = ref.ctc_beam_search(x, sl, beam_width=W, reoffer_wipe=False)
+        differ += sum(int(n[b] != pn[b] or not np.array_equal(ids[b, :n[b]], pi[b, :pn[b]])) for b in range(B))
+    print("utterances on which TF's artifact changes the transcript: %d of %d" % (differ, 4 * B))
+    assert differ > 0
