@@ -43,7 +43,7 @@
 namespace ctcasr {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32;
+constexpr int BM = 128, BN = 256;
 constexpr int NACC = 2;
 constexpr int GROUP_M = 16;
 constexpr int NTHREADS = 192;
@@ -57,13 +57,18 @@ struct Cfg {
     static constexpr bool kBf16 = MODE != MODE_TF32;
     static constexpr int NP = (kBf16 && MODE != MODE_BF16X1) ? MODE : 1;     // pieces per operand
     static constexpr int ESZ = kBf16 ? 2 : 4;
+    // k-block of a pipeline stage.  One product per operand pair (BF16X1) takes 64 k (128-B rows, SWIZZLE_128B): with
+    // 32 k a stage is two 128-cycle MMAs, and the issuing thread's barrier wait + commit and the producer's TMA
+    // instructions (up to 6 boxes of 4 KB per stage) cost as much as those MMAs run — measured 830-1100 TFLOP/s
+    // depending only on the number of boxes per stage.  The multi-product modes do 3-6x the MMAs per stage.
+    static constexpr int BK = MODE == MODE_BF16X1 ? 64 : 32;
     static constexpr int A_PIECE = BM * BK * ESZ, B_PIECE = BN * BK * ESZ;
     static constexpr int STAGE_BYTES = NP * (A_PIECE + B_PIECE);
-    static constexpr int NSTAGE = MODE == MODE_BF16X6 ? 2 : (MODE == MODE_BF16X1 ? 6 : 4);
+    static constexpr int NSTAGE = MODE == MODE_BF16X6 ? 2 : 4;      // 192 KB (BF16X6: 144 KB)
     static constexpr int UMMA_K = kBf16 ? 16 : 8;
     static constexpr int KSTEPS = BK / UMMA_K;
     static constexpr int MN_BOX = 128 / ESZ;                    // m|n elements per 128-B row
-    static constexpr int MN_BOX_BYTES = BK * 128;               // one MN-major box: 32 k-rows x 128 B
+    static constexpr int MN_BOX_BYTES = BK * 128;               // one MN-major box: BK k-rows x 128 B
     static constexpr int NPROD = (MODE == MODE_TF32 || MODE == MODE_BF16X1) ? 1 : (MODE == MODE_BF16X3 ? 3 : 6);
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
     // per k-step advance of the descriptor start address (bytes)
@@ -102,6 +107,7 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t addr, bool mn_major)
     if (MODE == MODE_TF32)
         return mn_major ? ptx::make_smem_desc(addr, Cfg<MODE>::MN_BOX_BYTES, 512, 1)     // SWIZZLE_128B_BASE32B
                         : ptx::make_smem_desc(addr, 16, 1024, 2);                        // SWIZZLE_128B
+    if (!mn_major && Cfg<MODE>::BK == 64) return ptx::make_smem_desc(addr, 16, 1024, 2);   // bf16, 128-B rows: SWIZZLE_128B
     return mn_major ? ptx::make_smem_desc(addr, Cfg<MODE>::MN_BOX_BYTES, 1024, 2)        // SWIZZLE_128B
                     : ptx::make_smem_desc(addr, 16, 512, 4);                             // SWIZZLE_64B
 }
@@ -194,20 +200,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                     for (int pc = 0; pc < NP; ++pc) {
                         if (!p.ta) {
-                            ptx::tma_load_3d(a_addr(stage, pc), ma, kb * BK, mb * BM, pc, full_bar(stage));
+                            ptx::tma_load_3d(a_addr(stage, pc), ma, kb * C_::BK, mb * BM, pc, full_bar(stage));
                         } else {
 #pragma unroll
                             for (int j = 0; j < BM / C_::MN_BOX; ++j)
                                 ptx::tma_load_3d(a_addr(stage, pc) + j * C_::MN_BOX_BYTES, ma, mb * BM + j * C_::MN_BOX,
-                                                 kb * BK, pc, full_bar(stage));
+                                                 kb * C_::BK, pc, full_bar(stage));
                         }
                         if (p.tb) {
-                            ptx::tma_load_3d(b_addr(stage, pc), mbp, kb * BK, nb * BN, pc, full_bar(stage));
+                            ptx::tma_load_3d(b_addr(stage, pc), mbp, kb * C_::BK, nb * BN, pc, full_bar(stage));
                         } else {
 #pragma unroll
                             for (int j = 0; j < BN / C_::MN_BOX; ++j)
                                 ptx::tma_load_3d(b_addr(stage, pc) + j * C_::MN_BOX_BYTES, mbp, nb * BN + j * C_::MN_BOX,
-                                                 kb * BK, pc, full_bar(stage));
+                                                 kb * C_::BK, pc, full_bar(stage));
                         }
                     }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -309,6 +315,186 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 5) ptx::tmem_dealloc(tmem_base, NACC * BN);
+}
+
+// ================================== CTA-pair variant (cta_group::2) ================================
+// The bf16 modes on a 2-CTA cluster (the two SMs of a TPC): one 256 x 256 output tile per pair, tcgen05.mma
+// cta_group::2 with M = 256 issued by the leader CTA.  CTA r loads ITS 128 rows of A and ITS 128 columns of B; the
+// MMA reads both halves of B across the pair, so a CTA pulls 16 KB (A) + 16 KB (half of B) per 64 k of a 128 x 256
+// output instead of 16 + 32 KB: with one product per operand pair (MODE_BF16X1) the single-CTA kernel needs 94 B
+// per clock and SM from L2, more than the ~61 B the L2 -> SM path delivers (tools/ubench/l2_peak.cu), and ran at
+// 0.64 of the tensor peak; the pair needs 62.5.
+// Barriers: full[s] lives in the leader (its producer announces the bytes of BOTH CTAs, both producers' TMA boxes
+// complete on it); empty[s] and tfull[a] exist in both CTAs and are signalled by multicast commits; tempty[a] of the
+// leader collects the four epilogue warps of both CTAs.
+template <int MODE>
+struct Cfg2 {
+    using C1 = Cfg<MODE>;
+    static_assert(C1::kBf16, "CTA-pair kernel: bf16 modes");
+    static constexpr int NP = C1::NP;
+    static constexpr int BNH = BN / 2;                              // B columns held by one CTA
+    static constexpr int BK = C1::BK;
+    static constexpr int A_PIECE = BM * BK * 2, B_PIECE = BNH * BK * 2;
+    static constexpr int STAGE_BYTES = NP * (A_PIECE + B_PIECE);    // per CTA
+    static constexpr int NSTAGE = 6;                                // 192 KB
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256 + STG_BYTES;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
+                    const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+                    const Params p)
+{
+    using C_ = Cfg<MODE>;
+    using C2 = Cfg2<MODE>;
+    constexpr int NSTAGE = C2::NSTAGE, STAGE_BYTES = C2::STAGE_BYTES, NP = C2::NP;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + NSTAGE * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + NACC + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 2 * NACC);
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+    float *stg = reinterpret_cast<float *>(smem_raw + (bar_base + 256 - ptx::smem_u32(smem_raw))) + (threadIdx.x >> 5 & 3) * 32 * STG_LD;
+    auto a_addr = [&](int stage, int piece) { return smem_base + stage * STAGE_BYTES + piece * C2::A_PIECE; };
+    auto b_addr = [&](int stage, int piece) { return smem_base + stage * STAGE_BYTES + NP * C2::A_PIECE + piece * C2::B_PIECE; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < NACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 8); }
+        ptx::mbar_fence_init();
+    }
+    if (warp == 4 && lane == 0) {
+        ptx::tma_prefetch_desc(&mapA0); ptx::tma_prefetch_desc(&mapB0);
+        if (p.nz > 1) { ptx::tma_prefetch_desc(&mapA1); ptx::tma_prefetch_desc(&mapB1); }
+    }
+    if (warp == 5) ptx::tmem_alloc_pair(tmem_slot, NACC * BN);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();                 // the peer's barriers exist before anything is signalled across the pair
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        // ============ TMA producer (both CTAs): my rows of A, my columns of B, bytes on the leader's barrier ============
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = pair; u < p.num_tiles; u += npairs) {
+                int z, mb, nb;
+                decode_tile(p, u, z, mb, nb);
+                const CUtensorMap *ma = z ? &mapA1 : &mapA0;
+                const CUtensorMap *mbp = z ? &mapB1 : &mapB0;
+                const int m0 = mb * 2 * BM + (int)rank * BM, n0 = nb * BN + (int)rank * C2::BNH;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (leader) ptx::mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+#pragma unroll
+                    for (int pc = 0; pc < NP; ++pc) {
+                        if (!p.ta) {
+                            ptx::tma_load_3d_pair(a_addr(stage, pc), ma, kb * C_::BK, m0, pc, full_bar(stage));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BM / C_::MN_BOX; ++j)
+                                ptx::tma_load_3d_pair(a_addr(stage, pc) + j * C_::MN_BOX_BYTES, ma, m0 + j * C_::MN_BOX,
+                                                      kb * C_::BK, pc, full_bar(stage));
+                        }
+                        if (p.tb) {
+                            ptx::tma_load_3d_pair(b_addr(stage, pc), mbp, kb * C_::BK, n0, pc, full_bar(stage));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < C2::BNH / C_::MN_BOX; ++j)
+                                ptx::tma_load_3d_pair(b_addr(stage, pc) + j * C_::MN_BOX_BYTES, mbp, n0 + j * C_::MN_BOX,
+                                                      kb * C_::BK, pc, full_bar(stage));
+                        }
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================================ MMA issuer (leader CTA only) ================================
+        if (lane == 0 && leader) {
+            const uint32_t a_step = (p.ta ? C_::MNMAJ_STEP : C_::KMAJ_STEP) >> 4;
+            const uint32_t b_step = (p.tb ? C_::KMAJ_STEP : C_::MNMAJ_STEP) >> 4;
+            constexpr int PA[6] = {0, 0, 1, 0, 1, 2};
+            constexpr int PB[6] = {0, 1, 0, 2, 1, 0};
+            const uint32_t idesc = ptx::make_idesc_bf16(2 * BM, BN, p.ta ? 1 : 0, p.tb ? 0 : 1);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int u = pair; u < p.num_tiles; u += npairs) {
+                ptx::mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);     // epilogue warps of both CTAs
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int q = 0; q < C_::NPROD; ++q) {
+                        const uint64_t adesc = operand_desc<MODE>(a_addr(stage, PA[q]), p.ta != 0);
+                        const uint64_t bdesc = operand_desc<MODE>(b_addr(stage, PB[q]), p.tb == 0);
+#pragma unroll
+                        for (int j = 0; j < C_::KSTEPS; ++j)
+                            ptx::mma_bf16_pair(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc,
+                                               (kb | q | j) != 0);
+                    }
+                    ptx::mma_commit_pair(empty_bar(stage));         // frees the stage in both CTAs
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit_pair(tfull_bar(acc));
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================== epilogue (both CTAs): my 128 rows of the pair's accumulator ==================
+        int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t tempty_leader = ptx::mapa(tempty_bar(0), 0);
+        for (int u = pair; u < p.num_tiles; u += npairs) {
+            int z, mb, nb;
+            decode_tile(p, u, z, mb, nb);
+            float *C = p.C[z];
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const int m0 = mb * 2 * BM + (int)rank * BM + warp * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
+            const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld32(taddr + c * 32, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
+                        make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                __syncwarp();
+                const int n = nb * BN + c * 32 + sub_n;
+                if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                else if (p.epi.mode == EPI_MASK) store_rows<EK_MASK>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                else if (p.epi.accumulate) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                else store_rows<EK_RAW>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                __syncwarp();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(tempty_leader + 8u * acc);      // (the leader's own window for rank 0)
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();                 // nobody leaves while the pair's MMAs / remote arrivals can still touch it
+    if (warp == 5) ptx::tmem_dealloc_pair(tmem_base, NACC * BN);
 }
 
 // ---- operand split pre-pass: fp32 [rows][ld] -> NP bf16 matrices [NP][rows][ldo] ---------------------
@@ -452,6 +638,33 @@ static int acquire_split(const float *x, int rows, int cols, int ld, cudaStream_
 }
 
 template <int MODE>
+static int launch_pair(const CUtensorMap *maps, Params p, int num_sms, cudaStream_t stream)
+{
+    if (MODE != MODE_BF16X1 && MODE != MODE_BF16X3) return fail(CTCASR_ERR_INVALID, "gemm_tc: CTA-pair kernel: bf16 modes only");
+    constexpr int MP = (MODE == MODE_BF16X1 || MODE == MODE_BF16X3) ? MODE : MODE_BF16X1;     // (never instantiated for the others)
+    using C2 = Cfg2<MP>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
+        attr_set = true;
+    }
+    p.tiles_m = ceil_div(p.M, 2 * BM);                          // tiles of the pair: 256 rows
+    p.num_tiles = p.tiles_m * p.tiles_n * p.nz;
+    p.splits = 1; p.kb_per_split = p.kblocks; p.part = nullptr;
+    const int pairs = p.num_tiles < num_sms / 2 ? p.num_tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C2::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ProfScope prof_gemm(PROF_GEMM_TC, stream);
+    CTCASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<MP>, maps[0], maps[1], maps[2], maps[3], p));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return CTCASR_OK;
+}
+
+template <int MODE>
 static int launch(const GemmArgs &g, cudaStream_t stream)
 {
     using C_ = Cfg<MODE>;
@@ -486,31 +699,39 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
         }
         if (g.nz == 1) { Abase[1] = Abase[0]; Bbase[1] = Bbase[0]; }
     }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        CTCASR_CUDA_CHECK(cudaGetDevice(&dev));
+        CTCASR_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // CTA-pair kernel (gemm_tc_pair_kernel): whole 256-column tiles, at least one 256 x 256 tile per pair, no split-K
+    const int pair_tiles = ceil_div(g.M, 2 * BM) * (g.N / BN) * g.nz;
+    static const bool pair_enabled = !(getenv("CTCASR_GEMM_PAIR") && atoi(getenv("CTCASR_GEMM_PAIR")) == 0);
+    // (three products per operand pair are tensor-bound on one CTA already; measured: the pair gains 6 % with both operands
+    // as stored by the forward pass and loses 4 % in the dgrad / wgrad orientations)
+    const bool use_pair = pair_enabled && (MODE == MODE_BF16X1 || (MODE == MODE_BF16X3 && !g.ta && !g.tb)) && g.N % BN == 0 &&
+                          pair_tiles >= num_sms / 2;
     CUtensorMap maps[4];
-    const CUtensorMapSwizzle sw_k = C_::kBf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle sw_k = (C_::kBf16 && C_::BK == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;   // 64-B / 128-B rows
     const CUtensorMapSwizzle sw_mn = C_::kBf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     for (int z = 0; z < 2; ++z) {
         int rc;
-        if (!g.ta) rc = encode_map(&maps[2 * z], Abase[z], C_::kBf16, g.K, g.M, lda, NP, a_piece, BK, BM, sw_k);             // A[m][k]
-        else       rc = encode_map(&maps[2 * z], Abase[z], C_::kBf16, g.M, g.K, lda, NP, a_piece, C_::MN_BOX, BK, sw_mn);    // A[k][m]
+        if (!g.ta) rc = encode_map(&maps[2 * z], Abase[z], C_::kBf16, g.K, g.M, lda, NP, a_piece, C_::BK, BM, sw_k);             // A[m][k]
+        else       rc = encode_map(&maps[2 * z], Abase[z], C_::kBf16, g.M, g.K, lda, NP, a_piece, C_::MN_BOX, C_::BK, sw_mn);    // A[k][m]
         if (rc != CTCASR_OK) return rc;
-        if (g.tb)  rc = encode_map(&maps[2 * z + 1], Bbase[z], C_::kBf16, g.K, g.N, ldb, NP, b_piece, BK, BN, sw_k);         // B[n][k]
-        else       rc = encode_map(&maps[2 * z + 1], Bbase[z], C_::kBf16, g.N, g.K, ldb, NP, b_piece, C_::MN_BOX, BK, sw_mn); // B[k][n]
+        if (g.tb)  rc = encode_map(&maps[2 * z + 1], Bbase[z], C_::kBf16, g.K, g.N, ldb, NP, b_piece, C_::BK, use_pair ? BN / 2 : BN, sw_k);   // B[n][k]
+        else       rc = encode_map(&maps[2 * z + 1], Bbase[z], C_::kBf16, g.N, g.K, ldb, NP, b_piece, C_::MN_BOX, C_::BK, sw_mn); // B[k][n]
         if (rc != CTCASR_OK) return rc;
     }
     Params p;
     p.M = g.M; p.N = g.N; p.K = g.K; p.nz = g.nz; p.ta = g.ta; p.tb = g.tb; p.ldc = g.ldc;
     p.C[0] = g.C[0]; p.C[1] = g.nz > 1 ? g.C[1] : g.C[0];
     p.epi = g.epi;
-    p.tiles_m = ceil_div(g.M, BM); p.tiles_n = ceil_div(g.N, BN); p.kblocks = ceil_div(g.K, BK);
+    p.tiles_m = ceil_div(g.M, BM); p.tiles_n = ceil_div(g.N, BN); p.kblocks = ceil_div(g.K, C_::BK);
     p.num_tiles = p.tiles_m * p.tiles_n * g.nz;
-    static int num_sms = 0;
+    if (use_pair) return launch_pair<MODE>(maps, p, num_sms, stream);
     static bool attr_set = false;
-    if (!num_sms) {
-        int dev = 0;
-        CTCASR_CUDA_CHECK(cudaGetDevice(&dev));
-        CTCASR_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
     if (!attr_set) {
         CTCASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
         attr_set = true;
@@ -518,9 +739,10 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
     // split-K: under half a wave of output tiles on a long contraction (conv weight gradients: [Kp, 64]
     // outputs contracting 10^5..10^6 patch rows) -> ~2 waves of (slice, tile) units, >= 32 k-blocks per slice
     p.splits = 1; p.kb_per_split = p.kblocks; p.part = nullptr;
-    if (p.num_tiles <= num_sms / 2 && p.kblocks >= 128) {
+    constexpr int KB32 = C_::BK / 32;                           // thresholds in 32-wide k-blocks whatever the stage depth
+    if (p.num_tiles <= num_sms / 2 && p.kblocks * KB32 >= 128) {
         int S = (2 * num_sms) / p.num_tiles;
-        if (S > p.kblocks / 32) S = p.kblocks / 32;
+        if (S > p.kblocks * KB32 / 32) S = p.kblocks * KB32 / 32;
         if (S > 1) {
             const int per = ceil_div(p.kblocks, S);
             S = ceil_div(p.kblocks, per);
