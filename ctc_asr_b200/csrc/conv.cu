@@ -16,6 +16,8 @@
 // channels of y are exact zeros (zero kernel columns and bias) and are skipped by the next im2col.
 #include "gemm.cuh"
 
+#include <cuda_bf16.h>
+
 namespace ctcasr {
 namespace conv {
 
@@ -61,9 +63,12 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) { return f
 // One warp per output position (grid-stride), lanes along the patch in units of four columns: one 16-B
 // store per lane and iteration.  VEC (C and the input pitch multiples of 4): the four columns are four
 // channels of one tap -> one 16-B load; otherwise four scalar gathers.
-template <bool VEC>
-__global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ x, float *__restrict__ col, const Geom g, size_t rows,
-                                                     const FastDiv dC, const FastDiv dkf)
+// NP = 0: fp32 patch matrix `col`.  NP = 1..3: the patch matrix straight as the NP bf16 pieces the tcgen05 GEMM reads
+// (piece 1 = bf16(v), piece 2 = bf16(v - piece 1), ...; `pieces` [NP][rows][Kp]) — the fp32 matrix (9.5 GB for the
+// second layer at B = 32 x 10 s) is then never written, re-read and split.
+template <bool VEC, int NP>
+__global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ x, float *__restrict__ col, __nv_bfloat16 *__restrict__ pieces,
+                                                     const Geom g, size_t rows, const FastDiv dC, const FastDiv dkf)
 {
     const int lane = threadIdx.x & 31;
     const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -100,7 +105,20 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float *__restrict__ x
                     }
                 }
             }
-            crow[j] = make_float4(v[0], v[1], v[2], v[3]);
+            if (NP == 0) {
+                crow[j] = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int pc = 0; pc < (NP ? NP : 1); ++pc) {
+                    __nv_bfloat16 h[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { h[e] = __float2bfloat16_rn(v[e]); v[e] -= __bfloat162float(h[e]); }
+                    uint2 pk;
+                    pk.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+                    pk.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+                    *reinterpret_cast<uint2 *>(pieces + ((size_t)pc * rows + r) * g.Kp + 4 * j) = pk;
+                }
+            }
         }
     }
 }
@@ -145,18 +163,42 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float *__restrict__ d
     }
 }
 
-static int launch_im2col(const float *x, float *col, const Geom &g, size_t rows, cudaStream_t stream)
+template <int NP>
+static int launch_im2col_np(const float *x, float *col, __nv_bfloat16 *pieces, const Geom &g, size_t rows, cudaStream_t stream)
 {
-    CTCASR_REQUIRE(g.Kp < 65536, "conv2d: patch of %d elements", g.K);
     const size_t blocks = (rows + 7) / 8;
     const int grid = (int)(blocks < (size_t)148 * 16 ? blocks : (size_t)148 * 16);
     const FastDiv dC = make_fastdiv(g.C), dkf = make_fastdiv(g.kf);
     if (g.C % 4 == 0 && g.xpitch % 4 == 0 && ((uintptr_t)x & 15) == 0)
-        im2col_kernel<true><<<grid, 256, 0, stream>>>(x, col, g, rows, dC, dkf);
+        im2col_kernel<true, NP><<<grid, 256, 0, stream>>>(x, col, pieces, g, rows, dC, dkf);
     else
-        im2col_kernel<false><<<grid, 256, 0, stream>>>(x, col, g, rows, dC, dkf);
+        im2col_kernel<false, NP><<<grid, 256, 0, stream>>>(x, col, pieces, g, rows, dC, dkf);
     CTCASR_LAUNCH_CHECK();
     return CTCASR_OK;
+}
+
+// The patch matrix as the GEMM operand `col` [rows, Kp].  In the bf16 compute modes (inside an open split scope) the
+// pieces are produced directly and registered under the address of `col`, which is then only a key: the GEMM finds
+// the split in the cache.  np = pieces the GEMM that follows will ask for (3: six-product forward through the ReLU
+// kink, 2: three-product, 1: compute = 'bf16'); 0 = the fp32 matrix.
+static int launch_im2col(const float *x, float *col, const Geom &g, size_t rows, int np, cudaStream_t stream)
+{
+    CTCASR_REQUIRE(g.Kp < 65536, "conv2d: patch of %d elements", g.K);
+    if (np == 0) return launch_im2col_np<0>(x, col, nullptr, g, rows, stream);
+    __nv_bfloat16 *pieces = nullptr;
+    if (int rc = split_reserve(col, (int)rows, g.Kp, g.Kp, np, &pieces)) return rc;
+    ProfScope prof_split(PROF_SPLIT, stream);
+    if (np == 1) return launch_im2col_np<1>(x, col, pieces, g, rows, stream);
+    if (np == 2) return launch_im2col_np<2>(x, col, pieces, g, rows, stream);
+    return launch_im2col_np<3>(x, col, pieces, g, rows, stream);
+}
+// pieces per operand of the tcgen05 GEMM this product will run as (0: the fp32 / tf32 / SIMT paths read the fp32 matrix)
+static int gemm_pieces(const GemmArgs &a, int compute)
+{
+    if (!gemm_tc_eligible(a)) return 0;
+    if (compute == CTCASR_COMPUTE_BF16) return 1;
+    if (compute == CTCASR_COMPUTE_BF16X3) return a.precise ? 3 : 2;
+    return 0;
 }
 
 static int launch_col2im(const float *dcol, float *dx, const Geom &g, cudaStream_t stream)
@@ -206,11 +248,18 @@ extern "C" int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, co
     if (!ws || ws_bytes < need) return fail(CTCASR_ERR_WORKSPACE, "conv2d_fwd: workspace %zu < %zu", ws_bytes, need);
     if (int rcs = gemm_scratch_check(compute, 1, (int)rows, N, g.Kp)) return rcs;
     float *col = reinterpret_cast<float *>(ws);
-    if (int rc = conv::launch_im2col(x, col, g, rows, stream)) return rc;
     GemmArgs a;
     a.A[0] = col; a.B[0] = w; a.C[0] = y; a.M = (int)rows; a.N = N; a.K = g.Kp; a.lda = g.Kp; a.ldb = N; a.ldc = N;
     a.epi.mode = EPI_BIAS_ACT; a.epi.bias = bias; a.epi.act = act; a.epi.cutoff = cutoff;
     a.precise = act != 0;
+    const int np = conv::gemm_pieces(a, compute);
+    SplitScope scope;
+    if (np) {
+        const size_t elems[2] = {rows * (size_t)g.Kp, (size_t)g.Kp * N};
+        if (int rc = split_scope_begin(compute, elems, 2)) return rc;
+        scope.open = true;
+    }
+    if (int rc = conv::launch_im2col(x, col, g, rows, np, stream)) return rc;
     return gemm(a, compute, stream);
 }
 
@@ -235,10 +284,17 @@ extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, co
     if (rc != CTCASR_OK) return rc;
     rc = colsum(dy, (int)rows, N, N, db, stream);
     if (rc != CTCASR_OK) return rc;
-    if ((rc = conv::launch_im2col(x, col, g, rows, stream)) != CTCASR_OK) return rc;
     {   // dW[Kp,N] = col^T dz   (rows K..Kp of col^T are zero -> the pad rows of dW are zero)
         GemmArgs a;
         a.A[0] = col; a.B[0] = dy; a.C[0] = dw; a.ta = 1; a.M = g.Kp; a.N = N; a.K = (int)rows; a.lda = g.Kp; a.ldb = N; a.ldc = N;
+        const int np = conv::gemm_pieces(a, compute);
+        SplitScope scope;
+        if (np) {
+            const size_t elems[2] = {rows * (size_t)g.Kp, rows * (size_t)N};
+            if ((rc = split_scope_begin(compute, elems, 2)) != CTCASR_OK) return rc;
+            scope.open = true;
+        }
+        if ((rc = conv::launch_im2col(x, col, g, rows, np, stream)) != CTCASR_OK) return rc;
         rc = gemm(a, compute, stream);
         if (rc != CTCASR_OK) return rc;
     }

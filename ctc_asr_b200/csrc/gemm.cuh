@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace ctcasr {
 
 struct GemmArgs {
@@ -43,6 +45,10 @@ int gemm_scratch_check(int compute, int nz, int M, int N, int K);
 // their pieces do not fit in the scratch arena together.
 int split_scope_begin(int compute, const size_t *elems, int n);
 void split_scope_end();
+// Inside an open scope: arena space for the np bf16 pieces [np][rows][cols] (cols a multiple of 8) of an operand the
+// CALLER produces in that form, registered under `key` (the address a GEMM will name as its fp32 operand with pitch
+// ld; the fp32 matrix itself need not exist).  The caller fills *pieces before the GEMM runs (stream order).
+int split_reserve(const float *key, int rows, int cols, int ld, int np, __nv_bfloat16 **pieces);
 struct SplitScope {
     bool open = false;
     ~SplitScope() { if (open) split_scope_end(); }

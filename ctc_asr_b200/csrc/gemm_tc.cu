@@ -807,6 +807,24 @@ int split_scope_begin(int compute, const size_t *elems, int n)
 }
 void split_scope_end() { tc::g_scope = false; tc::g_nsplit = 0; tc::g_cursor = 0; }
 
+int split_reserve(const float *key, int rows, int cols, int ld, int np, __nv_bfloat16 **pieces)
+{
+    using namespace tc;
+    if (!g_scope || g_nsplit >= 16 || (cols & 7) || np < 1 || np > 3)
+        return fail(CTCASR_ERR_INVALID, "split_reserve: needs an open split scope and 16-B piece rows");
+    const size_t pc = (size_t)rows * cols;
+    const size_t bytes = align_up(pc * np * 2, 1024);
+    if (g_cursor + bytes > g_scratch_bytes) {
+        g_scratch_needed = g_cursor + bytes;
+        return fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", g_scratch_bytes, g_scratch_needed);
+    }
+    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(g_scratch + g_cursor);
+    g_cursor += bytes;
+    g_split[g_nsplit++] = SplitEntry{key, rows, cols, ld, np, dst, cols, pc};
+    *pieces = dst;
+    return CTCASR_OK;
+}
+
 void *scratch_free(size_t bytes)
 {
     const size_t used = tc::g_scope ? tc::g_cursor : 0;
