@@ -512,16 +512,15 @@ __device__ __forceinline__ float2 shfl2(const float2 v, int src)
 constexpr int kPF = 8;             // frames the warp kernel prefetches ahead (cp.async ring)
 
 struct WarpSmem {
-    size_t lab, csr_start, csr_pos, hand, post, ring, total;
+    size_t lab, hand, post, ring, total;
     __host__ __device__ WarpSmem(int Lmax, int V, int RS)
     {
+        (void)V;
         size_t o = 0;
         lab = o;       o += (size_t)((Lmax + 3) / 4 * 4 + 4) * 4;
-        csr_start = o; o += (size_t)((V + 1 + 3) / 4 * 4) * 4;
-        csr_pos = o;   o += (size_t)((Lmax + 3) / 4 * 4 + 4) * 4;
         o = (o + 15) / 16 * 16;
         hand = o;      o += (size_t)2 * (RS + 4) * 8 + 32;         // alpha_{h-1} and beta_h rows at the hand-over, 2 doubles
-        post = o;      o += (size_t)2 * 2 * RS * 4;                // [warp][2 buffers][RS] posteriors of the current frame
+        post = o;      o += (size_t)2 * 2 * 32 * 4;                // [warp][2 buffers][32] fixed-point class sums of a frame
         ring = o;      o += (size_t)2 * kPF * (128 + (size_t)RS * 8);   // [warp][kPF slots]{32 logits, the other warp's row}
         total = o + 32;
     }
@@ -575,8 +574,7 @@ __device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_r
     const int *lab = reinterpret_cast<const int *>(smem_raw + L.lab);
     float2 *hand = reinterpret_cast<float2 *>(smem_raw + L.hand);             // [2][RS + 4]
     double *hand_lz = reinterpret_cast<double *>(smem_raw + L.hand + (size_t)2 * (RS + 4) * 8);
-    unsigned *postrow = reinterpret_cast<unsigned *>(smem_raw + L.post) + (size_t)warp * 2 * RS;      // [2 buffers][RS] fixed-point posteriors
-    const int *csr_start = reinterpret_cast<const int *>(smem_raw + L.csr_start), *csr_pos = reinterpret_cast<const int *>(smem_raw + L.csr_pos);
+    unsigned *postrow = reinterpret_cast<unsigned *>(smem_raw + L.post) + (size_t)warp * 2 * 32;      // [2 buffers][32] fixed-point class sums
     unsigned char *ring = smem_raw + L.ring + (size_t)warp * kPF * SLOT;
     float *grad_b = p.grad ? p.grad + (size_t)b * V : nullptr;                 // row t at + t*B*V
     const size_t gstride = (size_t)p.B * V;
@@ -736,11 +734,28 @@ __device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_r
     cp_async_commit();
     cp_async_wait<0>();
     // ---- second half: posteriors from my row and the other warp's row of the frame, gradient row ----------------
+    // Per-class sums of the posteriors in fixed point (2^-24; integer adds commute: any order gives the same bits): every
+    // label state adds its value to its class's word with a shared-memory reduction (fire and forget, no dependent loads),
+    // the blank states go through one warp reduction.  The gradient row of a frame is written ONE ITERATION LATER, when its
+    // reductions have long landed: nothing of the class sums sits on the recursion's path.  (A per-class gather over
+    // position lists cost a serial chain of dependent shared-memory loads as long as the most frequent label: 37 % of this
+    // loop's stall samples.)
+    unsigned *csum = postrow;                               // [2 buffers][32 classes]
+    csum[lane] = 0u; csum[32 + lane] = 0u;
+    __syncwarp();
+    float pyrel = 0.f, pzs = 1.f;
+    unsigned ppb = 0u;
+    auto finish = [&](int n) {                              // gradient row of step n from its class sums
+        unsigned *pc = csum + (n & 1) * 32;
+        if (lane < V) {
+            const unsigned q = lane == blank ? ppb : pc[lane];
+            grad_b[(size_t)frame_of(n) * gstride + lane] = (__fdividef(pyrel, pzs) - (float)q * (1.f / 16777216.f)) * p.grad_scale;
+        }
+        pc[lane] = 0u;
+    };
     for (int n = own_first; n < nsteps; ++n) {
         step(n, true);
-        // per-class sums of the posteriors in fixed point (2^-24, integer adds commute: any order gives the same bits):
-        // the label states' values go through a shared-memory row, lane k gathers the positions of class k
-        unsigned *prow = postrow + (size_t)(n & 1) * RS;
+        unsigned *cs = csum + (n & 1) * 32;
         unsigned pblank = 0;
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
@@ -748,20 +763,15 @@ __device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_r
             // alpha * beta / (y * p): both rows include y_t; a zero operand has exponent ~kZE and clamps the factor to 0
             const float post = __fdividef(a[j].x * ot.x, ys[j].x) * inv_pm * pow2_clamp(xf_e(a[j]) + xf_e(ot) - xf_e(ys[j]) - pe);
             const unsigned q = __float2uint_rn(fminf(post, 1.f) * 16777216.f);
-            if (j & 1) prow[lane * SPL + j] = q;
+            if (j & 1) { if ((validm >> j) & 1) atomicAdd(cs + cls[j], q); }
             else pblank += q;
         }
         pblank = __reduce_add_sync(0xffffffffu, pblank);        // <= 2^24 in total (the posteriors of a frame sum to 1)
-        __syncwarp();
-        if (lane < V) {
-            unsigned q = pblank;
-            if (lane != blank) {
-                q = 0;
-                for (int i = csr_start[lane]; i < csr_start[lane + 1]; ++i) q += prow[csr_pos[i]];
-            }
-            grad_b[(size_t)frame_of(n) * gstride + lane] = (__fdividef(yrel, zs) - (float)q * (1.f / 16777216.f)) * p.grad_scale;
-        }
+        if (n > own_first) finish(n - 1);
+        __syncwarp();                                           // my reductions before the next iteration's reads, its zeroing before my next adds
+        pyrel = yrel; pzs = zs; ppb = pblank;
     }
+    if (nsteps > own_first) { __syncwarp(); finish(nsteps - 1); }
 }
 
 template <int SPL>
@@ -812,15 +822,6 @@ ctc_warp_kernel(const Params p)
         return;
     }
     for (int i = tid; i < 2 * (RS + 4); i += 64) hand[i] = xf_make(1.f, kZE);        // zero of the warp kernel's arithmetic
-    if (tid == 32) {    // per-class position lists of the label states (odd s), in label order
-        int *csr_start = reinterpret_cast<int *>(smem_raw + L.csr_start), *csr_pos = reinterpret_cast<int *>(smem_raw + L.csr_pos);
-        for (int k = 0; k <= V; ++k) csr_start[k] = 0;
-        for (int i = 0; i < Ln; ++i) csr_start[lab[i] + 1]++;
-        for (int k = 0; k < V; ++k) csr_start[k + 1] += csr_start[k];
-        int cursor[32];
-        for (int k = 0; k < V; ++k) cursor[k] = csr_start[k];
-        for (int i = 0; i < Ln; ++i) csr_pos[cursor[lab[i]]++] = 2 * i + 1;
-    }
     __syncthreads();
     if (warp == 0) ctc_sweep<SPL, true>(p, smem_raw, L, b, lane, Tb, Ln);
     else ctc_sweep<SPL, false>(p, smem_raw, L, b, lane, Tb, Ln);
