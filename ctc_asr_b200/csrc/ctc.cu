@@ -526,13 +526,21 @@ struct WarpSmem {
     }
 };
 
-__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+// (destinations as shared-space addresses computed once: a generic pointer costs a window conversion per copy)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -600,6 +608,14 @@ __device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_r
         if (s < S && li + 1 < Ln && lab[li + 1] != lab[li]) skipB |= 1u << j;
     }
 
+    constexpr int kOff = -(1 << 28);                    // added to an exponent: "this term does not exist"
+    int voff[SPL], skoff[SPL / 2];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) voff[j] = (validm >> j) & 1 ? 0 : kOff;
+#pragma unroll
+    for (int j = 1; j < SPL; j += 2) skoff[j / 2] = (skip >> j) & 1 ? 0 : kOff;
+    const int edge_off = (FWD ? lane == 0 : lane == 31) ? kOff : 0;
+
     const int h = p.grad ? Tb / 2 : Tb;                 // alpha owns frames [0, h) first, then [h, T_b); beta the reverse
     float2 *rows_b = p.rows + (size_t)b * p.T * RS + (size_t)lane * SPL;        // row t at + t*RS
     const float *logit_b = p.logits + (size_t)b * V + (lane < V ? lane : 0);
@@ -615,62 +631,72 @@ __device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_r
     const int nsteps = (!FWD && !p.grad) ? 0 : Tb;
     const int own_first = FWD ? h : Tb - h;             // steps of my walk before the hand-over
     auto frame_of = [&](int n) { return FWD ? n : Tb - 1 - n; };
-    // prefetch of step i into ring slot i % kPF: the frame's logits (lane k: class k) and, in the second half, the
-    // other warp's row of that frame (each lane its own SPL states); one cp.async group per step
-    auto issue = [&](int i, bool with_row) {
-        if (i < nsteps) {
-            unsigned char *slot = ring + (size_t)(i % kPF) * SLOT;
-            const int t = frame_of(i);
-            if (lane < V) cp_async4(slot + lane * 4, logit_b + (size_t)t * gstride);
+    // prefetch of the next step (they are issued strictly in order) into ring slot (step % kPF): the frame's logits (lane
+    // k: class k) and, in the second half, the other warp's row of that frame (each lane its own SPL states); one
+    // cp.async group per step.  Addresses are running pointers: one add per step instead of a 64-bit multiply each.
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t my_logit_s = ring_s + lane * 4, my_row_s = ring_s + 128 + lane * SPL * 8;
+    const ptrdiff_t lstep = FWD ? (ptrdiff_t)gstride : -(ptrdiff_t)gstride, rstep = FWD ? (ptrdiff_t)RS : -(ptrdiff_t)RS;
+    int iss = 0;
+    uint32_t iss_off = 0;                                                   // (iss % kPF) * SLOT
+    const float *iss_logit = logit_b + (size_t)frame_of(0) * gstride;
+    const float2 *iss_row = rows_b + (size_t)frame_of(0) * RS;
+    auto issue = [&](bool with_row) {
+        if (iss < nsteps) {
+            if (lane < V) cp_async4(my_logit_s + iss_off, iss_logit);
             if (with_row) {
-                const float4 *src = reinterpret_cast<const float4 *>(rows_b + (size_t)t * RS);
-                float4 *dst = reinterpret_cast<float4 *>(slot + 128 + (size_t)lane * SPL * 8);
 #pragma unroll
-                for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q, src + q);
+                for (int q = 0; q < SPL / 2; ++q) cp_async16(my_row_s + iss_off + q * 16, reinterpret_cast<const float4 *>(iss_row) + q);
             }
         }
         cp_async_commit();
+        ++iss; iss_off = iss_off + SLOT == kPF * SLOT ? 0u : iss_off + (uint32_t)SLOT;
+        iss_logit += lstep; iss_row += rstep;
     };
     // one recursion step on frame n of my walk; returns y' of my lane's class, the per-state y' and this frame's Z pieces
     float2 ys[SPL];
     float yrel, zs;
     int emax;
     float4 o[SPL / 2];
-    auto step = [&](int n, bool second) {
+    uint32_t cur_off = 0;                                                   // (n % kPF) * SLOT of the step being computed
+    auto step = [&](bool second) {
         cp_async_wait<kPF - 1>();
-        const unsigned char *slot = ring + (size_t)(n % kPF) * SLOT;
-        const float x = lane < V ? *reinterpret_cast<const float *>(slot + lane * 4) : 0.f;
+        const float x = lane < V ? lds_f32(my_logit_s + cur_off) : 0.f;
         if (second) {
 #pragma unroll
-            for (int q = 0; q < SPL / 2; ++q) o[q] = *reinterpret_cast<const float4 *>(slot + 128 + (size_t)lane * SPL * 8 + q * 16);
+            for (int q = 0; q < SPL / 2; ++q) o[q] = lds_f32x4(my_row_s + cur_off + q * 16);
         }
-        issue(n + kPF, second);         // rows only once the other warp has written them (after the hand-over)
+        cur_off = cur_off + SLOT == kPF * SLOT ? 0u : cur_off + (uint32_t)SLOT;
+        issue(second);                  // rows only once the other warp has written them (after the hand-over)
         // y'_k = exp(x_k) as (m, e): no normalisation on the recursion's path (a per-frame factor of all states cancels in
         // the posteriors and is taken out of the loss through log2 Z_t)
         const float l2 = x * kLog2e;
         const float fl = floorf(l2);
         const float2 y = (lane < V && l2 > -1e9f) ? xf_make(ex2f(l2 - fl), (int)fl) : kZero;      // logit -inf: probability zero
         const float2 yblank = shfl2(y, blank);
-        // the two states beyond my own range: from the previous (alpha) / next (beta) lane
+        // the two states beyond my own range: from the previous (alpha) / next (beta) lane; the edge lane's get the
+        // exponent of zero through edge_off
         float2 n1, n2;
         if (FWD) {
             n1 = make_float2(__shfl_up_sync(0xffffffffu, a[SPL - 1].x, 1), __shfl_up_sync(0xffffffffu, a[SPL - 1].y, 1));
             n2 = make_float2(__shfl_up_sync(0xffffffffu, a[SPL - 2].x, 1), __shfl_up_sync(0xffffffffu, a[SPL - 2].y, 1));
-            if (lane == 0) { n1.y = kZero.y; n2.y = kZero.y; }
         } else {
             n1 = make_float2(__shfl_down_sync(0xffffffffu, a[0].x, 1), __shfl_down_sync(0xffffffffu, a[0].y, 1));
             n2 = make_float2(__shfl_down_sync(0xffffffffu, a[1].x, 1), __shfl_down_sync(0xffffffffu, a[1].y, 1));
-            if (lane == 31) { n1.y = kZero.y; n2.y = kZero.y; }
         }
+        n1.y = __int_as_float(max(xf_e(n1) + edge_off, kZE));
+        n2.y = __int_as_float(max(xf_e(n2) + edge_off, kZE));
         float2 nw[SPL];
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
             const float2 yl = (j & 1) ? shfl2(y, cls[j]) : yblank;
-            ys[j] = make_float2(yl.x, (validm >> j) & 1 ? yl.y : kZero.y);          // states beyond 2L+1: exponent -> kZE
+            // states beyond 2L+1 and absent skip transitions: exponent pushed to "zero" by a per-state constant (one add that
+            // the clamp in xf_step absorbs) instead of a select on a predicate the loop would have to rebuild every step
+            ys[j] = make_float2(yl.x, __int_as_float(max(xf_e(yl) + voff[j], kZE)));
             const float2 s1 = FWD ? (j >= 1 ? a[j - 1] : n1) : (j + 1 < SPL ? a[j + 1] : n1);
             if (j & 1) {        // label state: the skip transition exists when the neighbouring labels differ
                 const float2 s2 = FWD ? (j >= 2 ? a[j - 2] : n1) : (j + 2 < SPL ? a[j + 2] : n2);      // j is odd: s-2 of j = 1 is the previous lane's last state
-                nw[j] = xf_step<true>(a[j], s1, s2.x, (skip >> j) & 1 ? xf_e(s2) : kZE, ys[j]);
+                nw[j] = xf_step<true>(a[j], s1, s2.x, max(xf_e(s2) + skoff[j / 2], kZE), ys[j]);
             } else {            // blank state: never skipped into
                 nw[j] = xf_step<false>(a[j], s1, 1.f, kZE, ys[j]);
             }
@@ -685,14 +711,16 @@ __device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_r
         zs = (float)__reduce_add_sync(0xffffffffu, __float2uint_rn(yrel * 4194304.f)) * (1.f / 4194304.f);      // 2^22: 32 x 2 x 2^22 < 2^32
     };
 
-    for (int i = 0; i < kPF; ++i) issue(i, false);
+    for (int i = 0; i < kPF; ++i) issue(false);
     // ---- first half: recursion, spill my rows -----------------------------------------------------------
+    float2 *spill = rows_b + (size_t)frame_of(0) * RS;
     for (int n = 0; n < own_first; ++n) {
-        step(n, false);
+        step(false);
         lz += (double)emax + (double)lg2f(zs);
-        float4 *dst = reinterpret_cast<float4 *>(rows_b + (size_t)frame_of(n) * RS);
+        float4 *dst = reinterpret_cast<float4 *>(spill);
 #pragma unroll
         for (int q = 0; q < SPL / 2; ++q) __stcg(dst + q, make_float4(a[2 * q].x, a[2 * q].y, a[2 * q + 1].x, a[2 * q + 1].y));
+        spill += rstep;
     }
     // ---- hand-over: both warps have finished their first half ------------------------------------------------
     if (p.grad || FWD) {
@@ -727,9 +755,9 @@ __device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_r
     // the other warp's rows of my next kPF frames (their logits are already in flight)
     for (int i = own_first; i < own_first + kPF && i < nsteps; ++i) {
         const float4 *src = reinterpret_cast<const float4 *>(rows_b + (size_t)frame_of(i) * RS);
-        float4 *dst = reinterpret_cast<float4 *>(ring + (size_t)(i % kPF) * SLOT + 128 + (size_t)lane * SPL * 8);
+        const uint32_t dst = my_row_s + (uint32_t)(i % kPF) * (uint32_t)SLOT;
 #pragma unroll
-        for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q, src + q);
+        for (int q = 0; q < SPL / 2; ++q) cp_async16(dst + q * 16, src + q);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -745,16 +773,18 @@ __device__ __forceinline__ void ctc_sweep(const Params &p, unsigned char *smem_r
     __syncwarp();
     float pyrel = 0.f, pzs = 1.f;
     unsigned ppb = 0u;
-    auto finish = [&](int n) {                              // gradient row of step n from its class sums
+    float *gptr = grad_b + (size_t)frame_of(own_first) * gstride + (lane < V ? lane : 0);
+    auto finish = [&](int n) {                              // gradient row of step n (called in step order) from its class sums
         unsigned *pc = csum + (n & 1) * 32;
         if (lane < V) {
             const unsigned q = lane == blank ? ppb : pc[lane];
-            grad_b[(size_t)frame_of(n) * gstride + lane] = (__fdividef(pyrel, pzs) - (float)q * (1.f / 16777216.f)) * p.grad_scale;
+            *gptr = (__fdividef(pyrel, pzs) - (float)q * (1.f / 16777216.f)) * p.grad_scale;
         }
+        gptr += lstep;
         pc[lane] = 0u;
     };
     for (int n = own_first; n < nsteps; ++n) {
-        step(n, true);
+        step(true);
         unsigned *cs = csum + (n & 1) * 32;
         unsigned pblank = 0;
 #pragma unroll
