@@ -537,7 +537,7 @@ def run_ctc(ctx):
                 "d2h_bytes_per_step": int(T * B * V * 4)},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": main["algorithmic_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": main["frac_of_hbm"], "traffic": traffic, "kernel": "ctc_loss_kernel",
+                     "frac": main["frac_of_hbm"], "traffic": traffic, "kernel": "ctc_warp_kernel<6>",
                      "note": "algorithmic bytes = logits in + gradient out + labels (SURVEY 8d); peak of %s" % peaks["source"]},
     }
     if args.sweep:

@@ -1,6 +1,6 @@
 """Small single-purpose GPU workloads for `ncu --set full` captures (one GPU, a few launches).
   python tools/profile_target.py lstm [T]     one BiLSTM-2048 layer, B=32: recurrence fwd + bwd kernels
-  python tools/profile_target.py gemm         the cfg2 GEMM shapes in the default arithmetic
+  python tools/profile_target.py gemm [mode]  the cfg2 GEMM shapes in the default arithmetic (or bf16 / tf32)
   python tools/profile_target.py ctc          cfg5 CTC forward-backward
   python tools/profile_target.py convgemm     the conv layers' GEMM shapes
   python tools/profile_target.py conv         second conv layer forward + backward (im2col / col2im kernels)
@@ -66,6 +66,8 @@ elif what == "beam":
         ops.beam_search(logits, sl, beam_width=1024)
     torch.cuda.synchronize()
 elif what == "gemm":
+    if len(sys.argv) > 2:
+        C = _lib.COMPUTE_ID[sys.argv[2]]            # e.g. bf16: the CTA-pair kernel with 64-wide k-blocks
     for (M, N, K, ta, tb) in [(32000, 16384, 4096, 0, 0), (4096, 16384, 32000, 1, 0), (32000, 4096, 16384, 0, 1)]:
         a = torch.randn((K, M) if ta else (M, K), device="cuda")
         b = torch.randn((N, K) if tb else (K, N), device="cuda")
