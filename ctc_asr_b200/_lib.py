@@ -41,8 +41,9 @@ SIGNATURES = {
     "ctcasr_featurize": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "ctcasr_conv2d_out_dims": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ctcasr_conv2d_workspace_bytes": (_sz, [_i] * 8),
-    "ctcasr_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 10 + [_f, _i, _vp, _sz, _vp]),
-    "ctcasr_conv2d_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_f, _i, _vp, _sz, _vp]),
+    "ctcasr_conv2d_fwd": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 10 + [_f, _f, _u32, _i, _vp, _sz, _vp]),
+    "ctcasr_conv2d_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_f, _f, _u32, _i, _vp, _sz, _vp]),
+    "ctcasr_dropout": (_i, [_vp, _vp, _sz, _f, _u32, _vp]),
     "ctcasr_profile_enable": (_i, [_i]),
     "ctcasr_profile_collect": (_i, [_vp, _vp, _i]),
     "ctcasr_set_scratch": (_i, [_vp, _sz]),

@@ -236,10 +236,12 @@ extern "C" size_t ctcasr_conv2d_workspace_bytes(int T, int B, int F, int C, int 
 
 extern "C" int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, const float *bias, float *y,
                                  int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
-                                 int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream_)
+                                 int act, float cutoff, float drop_rate, uint32_t seed, int compute,
+                                 void *ws, size_t ws_bytes, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     CTCASR_REQUIRE(x && w && y && N >= 1, "conv2d_fwd: bad args");
+    CTCASR_REQUIRE(drop_rate >= 0.f && drop_rate < 1.f, "conv2d_fwd: drop_rate %g", drop_rate);
     conv::Geom g{};
     if (int rc = conv::make_geom(T, B, F, C, x_pitch, kt, kf, st, sf, &g)) return rc;
     const size_t rows = (size_t)g.To * B * g.Fo;
@@ -251,6 +253,7 @@ extern "C" int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, co
     GemmArgs a;
     a.A[0] = col; a.B[0] = w; a.C[0] = y; a.M = (int)rows; a.N = N; a.K = g.Kp; a.lda = g.Kp; a.ldb = N; a.ldc = N;
     a.epi.mode = EPI_BIAS_ACT; a.epi.bias = bias; a.epi.act = act; a.epi.cutoff = cutoff;
+    a.epi.drop_rate = drop_rate; a.epi.seed = seed;
     a.precise = act != 0;
     const int np = conv::gemm_pieces(a, compute);
     SplitScope scope;
@@ -266,10 +269,12 @@ extern "C" int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, co
 extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, const float *y, float *dy,
                                  float *dx, float *dw, float *db,
                                  int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
-                                 int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream_)
+                                 int act, float cutoff, float drop_rate, uint32_t seed, int compute,
+                                 void *ws, size_t ws_bytes, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     CTCASR_REQUIRE(x && w && dy && dw && db && N >= 1, "conv2d_bwd: bad args");
+    CTCASR_REQUIRE(drop_rate >= 0.f && drop_rate < 1.f, "conv2d_bwd: drop_rate %g", drop_rate);
     CTCASR_REQUIRE(act == 0 || y, "conv2d_bwd: activation mask needs the forward output y");
     conv::Geom g{};
     if (int rc = conv::make_geom(T, B, F, C, x_pitch, kt, kf, st, sf, &g)) return rc;
@@ -280,7 +285,7 @@ extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, co
     if (int rcs = gemm_scratch_check(compute, 1, g.Kp, N, (int)rows)) return rcs;
     if (dx) if (int rcs = gemm_scratch_check(compute, 1, (int)rows, g.Kp, N)) return rcs;
     float *col = reinterpret_cast<float *>(ws);
-    int rc = mask_inplace(dy, y, rows, N, act, cutoff, 0.f, 0u, stream);       // dy -> dz
+    int rc = mask_inplace(dy, y, rows, N, act, cutoff, drop_rate, seed, stream);       // dy -> dz
     if (rc != CTCASR_OK) return rc;
     rc = colsum(dy, (int)rows, N, N, db, stream);
     if (rc != CTCASR_OK) return rc;

@@ -95,6 +95,14 @@ int mask_inplace(float *dy, const float *y, size_t M, int N, int act, float cuto
     return CTCASR_OK;
 }
 
+// ---- y = dropout(x): the keep-mask of the dense epilogue over the flat index (RNN input / output / inter-layer dropout) ----
+__global__ void dropout_kernel(const float *__restrict__ x, float *__restrict__ y, size_t total, float drop_rate, uint32_t seed)
+{
+    const float inv_keep = 1.f / (1.f - drop_rate);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = drop_keep(seed, i, drop_rate) ? x[i] * inv_keep : 0.f;
+}
+
 // ---- recurrent cell math, stepwise path --------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
@@ -271,6 +279,23 @@ extern "C" int ctcasr_adam(float *p, float *m, float *v, const float *g, size_t 
     const size_t want = (n / 4 + 255) / 256;
     const int blocks = (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, lr_t, beta1, beta2, eps, grad_scale);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+extern "C" int ctcasr_dropout(const float *x, float *y, size_t n, float drop_rate, uint32_t seed, void *stream_)
+{
+    using namespace ctcasr;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CTCASR_REQUIRE(x && y, "dropout: null pointer");
+    CTCASR_REQUIRE(drop_rate >= 0.f && drop_rate < 1.f, "dropout: drop_rate %g", drop_rate);
+    if (n == 0) return CTCASR_OK;
+    if (drop_rate == 0.f) {
+        if (x != y) CTCASR_CUDA_CHECK(cudaMemcpyAsync(y, x, n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        return CTCASR_OK;
+    }
+    const size_t blocks = (n + 255) / 256;
+    dropout_kernel<<<(int)(blocks < (size_t)148 * 16 ? blocks : (size_t)148 * 16), 256, 0, stream>>>(x, y, n, drop_rate, seed);
     CTCASR_LAUNCH_CHECK();
     return CTCASR_OK;
 }

@@ -121,9 +121,11 @@ class CTCModel:
             for li, d in enumerate(conv_plan(cfg, T)):
                 name = self._conv_names()[li]
                 y = self._buf("conv%d" % li, (d["To"] * B * d["Fo"], d["N"]))
+                # conv dropout is on in every mode: the reference calls conv_layers() without its `training` argument
+                # (asr/model.py:161), whose default is True (asr/util/tf_contrib.py:70,135)
                 ops.conv2d_fwd(xin, pitch, self.ps[name + "/kernel"], self.ps[name + "/bias"], y, d["T"], B, d["F"],
                                d["C"], d["kt"], d["kf"], d["st"], d["sf"], act=1, cutoff=cfg.relu_cutoff,
-                               compute=self.compute)
+                               drop_rate=cfg.conv_dropout_rate, seed=seed + 200 + li, compute=self.compute)
                 saved["conv"].append((xin, pitch, y, d))
                 xin, pitch = y, d["N"]
             T = d["To"]                                   # every utterance is stretched to the conv length of
@@ -140,8 +142,17 @@ class CTCModel:
         cell = CELL_ID[cfg.rnn_cell]
         use_len = not cfg.cudnn
         H = cfg.num_units_rnn
-        for l in range(cfg.num_layers_rnn):
+        # Dropout on the non-recurrent connections (asr/model.py:167): the TF path wraps every cell in
+        # DropoutWrapper(input_keep_prob, output_keep_prob) (asr/util/tf_contrib.py:190-194) — the layer's input and its
+        # output are dropped, the state that is fed back is not; the cuDNN RNNs drop between layers only
+        # (asr/model.py:201-206).  The layer itself always sees / keeps un-dropped outputs: backward needs them.
+        rnn_rate = cfg.rnn_dropout_rate if training else 0.0
+        saved["rnn_rate"] = rnn_rate
+        L = cfg.num_layers_rnn
+        for l in range(L):
             nin = h.shape[1]
+            if rnn_rate > 0.0 and not cfg.cudnn:
+                h = ops.dropout(h, rnn_rate, seed + 300 + l, out=self._buf("rnn_xd%d" % l, (T * B, nin)))
             rb, _ = ops.birnn_sizes(T, B, nin, H, cell)
             reserve = self._buf("rnn_reserve%d" % l, (rb,), torch.uint8)
             y = self._buf("rnn_y%d" % l, (T, B, 2 * H))
@@ -149,6 +160,8 @@ class CTCModel:
                           self.p["rnn/l%d/bias" % l], y, reserve, cell, use_len, cfg.forget_bias, self.compute)
             saved["rnn"].append((h, y, reserve))
             h = y.view(T * B, 2 * H)
+            if rnn_rate > 0.0 and (not cfg.cudnn or l < L - 1):
+                h = ops.dropout(h, rnn_rate, seed + 400 + l, out=self._buf("rnn_yd%d" % l, (T * B, 2 * H)))
         y4 = ops.dense_fwd(h, self.p["dense4/dense/kernel"], self.p["dense4/dense/bias"], act=1,
                            cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + 100, compute=self.compute,
                            out=self._buf("dense4", (T * B, cfg.num_units_dense)))
@@ -261,13 +274,18 @@ class CTCModel:
         cell = CELL_ID[cfg.rnn_cell]
         use_len = not cfg.cudnn
         dy = drnn
-        for l in reversed(range(cfg.num_layers_rnn)):
+        rnn_rate, L = s.get("rnn_rate", 0.0), cfg.num_layers_rnn
+        for l in reversed(range(L)):
             x, y, reserve = s["rnn"][l]
             nin = x.shape[1]
+            if rnn_rate > 0.0 and (not cfg.cudnn or l < L - 1):
+                ops.dropout(dy, rnn_rate, seed + 400 + l, out=dy)          # the layer's output dropout, on the gradient
             dx = self._buf("g_rnn_in%d" % (l % 2), (T * B, nin))
             ops.birnn_bwd(x.view(T, B, nin), s["seq_length"], self.p["rnn/l%d/wx" % l], self.p["rnn/l%d/wh" % l],
                           y, reserve, dy, dx, self.g["rnn/l%d/wx" % l], self.g["rnn/l%d/wh" % l],
                           self.g["rnn/l%d/bias" % l], cell, use_len, self.compute)
+            if rnn_rate > 0.0 and not cfg.cudnn:
+                ops.dropout(dx, rnn_rate, seed + 300 + l, out=dx)          # its input dropout
             dy = dx
             if on_bucket is not None:
                 on_bucket(*buckets[cfg.num_layers_rnn - l])
@@ -278,7 +296,8 @@ class CTCModel:
                 dx = self._buf("g_conv%d" % (li % 2), (d["T"] * B * d["F"], pitch)) if li > 0 else None
                 ops.conv2d_bwd(xin, pitch, self.ps[names[li] + "/kernel"], y, dy, dx, self.gs[names[li] + "/kernel"],
                                self.gs[names[li] + "/bias"], d["T"], B, d["F"], d["C"], d["kt"], d["kf"], d["st"], d["sf"],
-                               act=1, cutoff=cfg.relu_cutoff, compute=self.compute)
+                               act=1, cutoff=cfg.relu_cutoff, drop_rate=cfg.conv_dropout_rate, seed=seed + 200 + li,
+                               compute=self.compute)
                 dy = dx
             if on_bucket is not None:
                 on_bucket(*buckets[-1])

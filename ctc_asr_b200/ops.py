@@ -157,20 +157,32 @@ def dense_bwd(x, w, y, dy, dw, db, dx=None, act=1, cutoff=20.0, drop_rate=0.0, s
           cutoff, drop_rate, seed, compute, _stream())
 
 
-def conv2d_fwd(x, x_pitch, w, b, y, T, B, F, C, kt, kf, st, sf, act=1, cutoff=20.0, compute=_lib.COMPUTE_FP32):
+def conv2d_fwd(x, x_pitch, w, b, y, T, B, F, C, kt, kf, st, sf, act=1, cutoff=20.0, drop_rate=0.0, seed=0,
+               compute=_lib.COMPUTE_FP32):
     """x [T,B,F,x_pitch] (C real channels), w [Kp,N] padded HWIO kernel, b [N] -> y [To,B,Fo,N] (pre-allocated).
-    One conv layer of asr/util/tf_contrib.py:123-134."""
+    One conv layer of asr/util/tf_contrib.py:123-135 (conv2d + relu + minimum + dropout)."""
     lib = _lib.load()
     _f32(x, "x"); _f32(w, "w"); _f32(y, "y")
     N = w.shape[1]
     wsb = lib.ctcasr_conv2d_workspace_bytes(T, B, F, C, kt, kf, st, sf)
     ws = workspace(wsb, x.device, "conv")
     _call(lib.ctcasr_conv2d_fwd, "conv2d_fwd", ptr(x), x_pitch, ptr(w), ptr(b), ptr(y), T, B, F, C, kt, kf, st, sf, N,
-          act, cutoff, compute, ptr(ws), ws.numel(), _stream())
+          act, cutoff, drop_rate, seed & 0xffffffff, compute, ptr(ws), ws.numel(), _stream())
     return y
 
 
-def conv2d_bwd(x, x_pitch, w, y, dy, dx, dw, db, T, B, F, C, kt, kf, st, sf, act=1, cutoff=20.0,
+def dropout(x, rate, seed, out=None):
+    """out = dropout(x) with the library's counter-hash keep-mask over the flat index (out may be x).  The same call on
+    a gradient is the backward pass.  RNN input / output / inter-layer dropout (asr/util/tf_contrib.py:190-194,
+    asr/model.py:201-206)."""
+    lib = _lib.load()
+    _f32(x, "x")
+    out = torch.empty_like(x) if out is None else out
+    _call(lib.ctcasr_dropout, "dropout", ptr(x), ptr(out), x.numel(), rate, seed & 0xffffffff, _stream())
+    return out
+
+
+def conv2d_bwd(x, x_pitch, w, y, dy, dx, dw, db, T, B, F, C, kt, kf, st, sf, act=1, cutoff=20.0, drop_rate=0.0, seed=0,
                compute=_lib.COMPUTE_FP32):
     """dy [To,B,Fo,N] is clobbered (becomes dz); dx [T,B,F,x_pitch] may be None; dw [Kp,N], db [N] overwritten."""
     lib = _lib.load()
@@ -178,7 +190,7 @@ def conv2d_bwd(x, x_pitch, w, y, dy, dx, dw, db, T, B, F, C, kt, kf, st, sf, act
     wsb = lib.ctcasr_conv2d_workspace_bytes(T, B, F, C, kt, kf, st, sf)
     ws = workspace(wsb, x.device, "conv")
     _call(lib.ctcasr_conv2d_bwd, "conv2d_bwd", ptr(x), x_pitch, ptr(w), ptr(y), ptr(dy), ptr(dx), ptr(dw), ptr(db),
-          T, B, F, C, kt, kf, st, sf, N, act, cutoff, compute, ptr(ws), ws.numel(), _stream())
+          T, B, F, C, kt, kf, st, sf, N, act, cutoff, drop_rate, seed & 0xffffffff, compute, ptr(ws), ws.numel(), _stream())
 
 
 def birnn_sizes(T, B, nin, H, cell):

@@ -43,8 +43,8 @@ class ModelConfig:
     adam_beta2: float = 0.999           # :79
     adam_epsilon: float = 1e-8          # :81
     beam_width: int = 1024              # :85
-    conv_dropout_rate: float = 0.0      # :89  (only 0.0 is implemented, see __post_init__)
-    rnn_dropout_rate: float = 0.0       # :91  (only 0.0 is implemented)
+    conv_dropout_rate: float = 0.0      # :89  after every conv layer (asr/util/tf_contrib.py:135)
+    rnn_dropout_rate: float = 0.0       # :91  DropoutWrapper in/out (TF path) or between layers (cuDNN path)
     dense_dropout_rate: float = 0.1     # :93
     num_buckets: int = 96               # :97
     num_classes: int = _labels.num_classes()    # :100  (29, blank = 28)
@@ -80,11 +80,9 @@ class ModelConfig:
                 raise ValueError("conv_filters[-1] must be a multiple of 8 and >= 64")
         if self.rnn_cell not in RNN_CELLS:
             raise ValueError("rnn_cell must be one of {}".format(RNN_CELLS))
-        # asr/util/tf_contrib.py:135,190-194 / asr/params.py:89-91: the reference's defaults are 0.0 and only that is
-        # implemented; a silent no-op would train a different model from the reference
-        if self.rnn_dropout_rate != 0.0 or self.conv_dropout_rate != 0.0:
-            raise NotImplementedError("rnn_dropout_rate / conv_dropout_rate other than 0.0 (the reference's defaults) "
-                                      "are not implemented")
+        for name in ("conv_dropout_rate", "rnn_dropout_rate", "dense_dropout_rate"):      # asr/params.py:89-93
+            if not 0.0 <= getattr(self, name) < 1.0:
+                raise ValueError("%s must be in [0, 1)" % name)
         if self.compute not in ("fp32", "tf32", "bf16x3", "bf16"):
             raise ValueError("compute must be 'fp32', 'bf16x3', 'tf32' or 'bf16'")
 

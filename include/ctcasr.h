@@ -162,7 +162,9 @@ int ctcasr_beam_search(const float *logits, int T, int B, int V, int blank, cons
  * 2-D convolution layer of the 'ds2' front-end.  Replaces one iteration of the loop at
  * asr/util/tf_contrib.py:123-134: tf.layers.conv2d(padding='SAME', activation=relu) followed by
  * tf.minimum(., relu_cutoff); the image height is TIME and its width the feature axis
- * (asr/model.py:157-158).  Conv dropout (rate 0.0, asr/params.py:89) is not implemented.
+ * (asr/model.py:157-158), and tf.layers.dropout(rate=conv_dropout_rate) (asr/util/tf_contrib.py:135):
+ *   y = dropout( act( conv(x, w) + bias ) ), keep-mask = counter hash of (seed, position*N + n) as in
+ *   ctcasr_dense_fwd; drop_rate 0 (the reference's default, asr/params.py:89) disables it.
  *   x  [T, B, F, x_pitch]   time-major, the C real channels first in every x_pitch-float pixel
  *   w  [Kp, N]              TF's HWIO kernel [kt, kf, C, filters] flattened to rows
  *                           (it*kf + jf)*C + c and zero-padded to Kp = roundup(kt*kf*C, 8) rows and
@@ -177,11 +179,23 @@ int ctcasr_conv2d_out_dims(int T, int F, int kt, int kf, int st, int sf, int *To
 size_t ctcasr_conv2d_workspace_bytes(int T, int B, int F, int C, int kt, int kf, int st, int sf);
 int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, const float *bias, float *y,
                       int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
-                      int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream);
+                      int act, float cutoff, float drop_rate, uint32_t seed, int compute,
+                      void *ws, size_t ws_bytes, void *stream);
 int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, const float *y, float *dy,
                       float *dx, float *dw, float *db,
                       int T, int B, int F, int C, int kt, int kf, int st, int sf, int N,
-                      int act, float cutoff, int compute, void *ws, size_t ws_bytes, void *stream);
+                      int act, float cutoff, float drop_rate, uint32_t seed, int compute,
+                      void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Element-wise dropout of a contiguous buffer: y[i] = keep(seed, i) ? x[i] / (1 - rate) : 0, the keep-mask
+ * being the counter hash of ctcasr_dense_fwd over the flat index i.  y may be x (in place).  Applied to a
+ * gradient with the same (rate, seed) it is the layer's backward pass.  Replaces the dropout on the
+ * non-recurrent connections of the RNN stack: tf.nn.rnn_cell.DropoutWrapper(input_keep_prob, output_keep_prob)
+ * (asr/util/tf_contrib.py:190-194) and the `dropout` argument of the cuDNN RNNs, applied between layers
+ * (asr/model.py:201-206); rate = rnn_dropout_rate (asr/params.py:91).
+ * -------------------------------------------------------------------------------------------- */
+int ctcasr_dropout(const float *x, float *y, size_t n, float drop_rate, uint32_t seed, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature extraction.  Replaces the arithmetic of load_sample (asr/input_functions.py:156-262) from

@@ -44,11 +44,13 @@ def _forward(cfg, params, sequences, seq_length, training, seed, dtype):
     if getattr(cfg, "used_model", "ds1") == "ds2":
         # asr/model.py:154-161: expand_dims(sequences, 3) -> conv_layers; asr/util/tf_contrib.py:123-144
         x4 = x.reshape(T, B, -1, 1)
-        for name, strides in zip(_conv_names(cfg), CONV_STRIDES):
+        crate = getattr(cfg, "conv_dropout_rate", 0.0)      # on in every mode: conv_layers() is called without `training`
+        for li, (name, strides) in enumerate(zip(_conv_names(cfg), CONV_STRIDES)):
             w, b = params[name + "/kernel"].astype(dtype), params[name + "/bias"].astype(dtype)
             y = ref.conv2d_fwd(x4, w, b, strides, act=1, cutoff=cfg.relu_cutoff)
             cache["conv"].append((x4, y))
-            x4 = y
+            # tf.layers.dropout after the clipped ReLU (asr/util/tf_contrib.py:135); the index runs over the padded pitch
+            x4 = ref.dropout(y, crate, seed + 200 + li, pitch=max(64, (y.shape[-1] + 7) // 8 * 8))
         T = x4.shape[0]
         seq_length = np.full(B, T, np.int32)     # tf.tile([shape(output)[1]], [batch]) (tf_contrib.py:144)
         h = x4.reshape(T * B, -1)                # [T', B, Fo * filters] (tf_contrib.py:138)
@@ -60,13 +62,21 @@ def _forward(cfg, params, sequences, seq_length, training, seed, dtype):
             h = y
     cell = _CELL[cfg.rnn_cell]
     use_len = not cfg.cudnn
-    for l in range(cfg.num_layers_rnn):
+    # DropoutWrapper(input_keep_prob, output_keep_prob) on the TF path (asr/util/tf_contrib.py:190-194), inter-layer
+    # dropout on the cuDNN path (asr/model.py:201-206); rnn_dropout_rate if training else 0.0 (asr/model.py:167)
+    rrate = getattr(cfg, "rnn_dropout_rate", 0.0) if training else 0.0
+    L = cfg.num_layers_rnn
+    for l in range(L):
         wx, wh, bias = (params["rnn/l%d/%s" % (l, k)].astype(dtype) for k in ("wx", "wh", "bias"))
+        if not cfg.cudnn:
+            h = ref.dropout(h, rrate, seed + 300 + l)
         xin = h.reshape(T, B, -1)
         y, gates, cst = ref.birnn_fwd(xin, seq_length, wx, wh, bias, cell, use_len=use_len,
                                       forget_bias=cfg.forget_bias)
         cache["rnn"].append((xin, y, gates, cst))
         h = y.reshape(T * B, -1)
+        if not cfg.cudnn or l < L - 1:
+            h = ref.dropout(h, rrate, seed + 400 + l)
     w, b = params["dense4/dense/kernel"].astype(dtype), params["dense4/dense/bias"].astype(dtype)
     y4 = ref.dense_fwd(h, w, b, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + 100)
     cache["d4"] = (h, y4)
@@ -75,6 +85,7 @@ def _forward(cfg, params, sequences, seq_length, training, seed, dtype):
         logits = ref.dense_fwd(y4, w, b, act=0)
     cache["lg"] = (y4,)
     cache["meta"] = (T, B, rate, seed)
+    cache["rrate"] = rrate
     cache["seq_length"] = seq_length
     return logits.reshape(T, B, -1), cache
 
@@ -108,18 +119,25 @@ def _loss_and_grads(cfg, params, sequences, seq_length, labels, label_len, train
         h, w, y4, dy, act=1, cutoff=cfg.relu_cutoff, drop_rate=rate, seed=seed + 100)
     cell = _CELL[cfg.rnn_cell]
     use_len = not cfg.cudnn
-    for l in reversed(range(cfg.num_layers_rnn)):
+    rrate, L = cache["rrate"], cfg.num_layers_rnn
+    for l in reversed(range(L)):
         xin, y, gates, cst = cache["rnn"][l]
         wx, wh = (params["rnn/l%d/%s" % (l, k)].astype(dtype) for k in ("wx", "wh"))
+        if not cfg.cudnn or l < L - 1:
+            dy = ref.dropout(dy, rrate, seed + 400 + l)
         dx, dwx, dwh, db = ref.birnn_bwd(xin, seq_length, wx, wh, y, gates, cst,
                                          dy.reshape(T, B, -1), cell, use_len=use_len)
         grads["rnn/l%d/wx" % l], grads["rnn/l%d/wh" % l], grads["rnn/l%d/bias" % l] = dwx, dwh, db
         dy = dx.reshape(T * B, -1)
+        if not cfg.cudnn:
+            dy = ref.dropout(dy, rrate, seed + 300 + l)
     if getattr(cfg, "used_model", "ds1") == "ds2":
         names = _conv_names(cfg)
+        crate = getattr(cfg, "conv_dropout_rate", 0.0)
         for li in reversed(range(len(names))):
-            x4, y = cache["conv"][li]
+            x4, y = cache["conv"][li]            # y: the layer's output before its dropout
             w = params[names[li] + "/kernel"].astype(dtype)
+            dy = ref.dropout(dy.reshape(y.shape), crate, seed + 200 + li, pitch=max(64, (y.shape[-1] + 7) // 8 * 8))
             dy, grads[names[li] + "/kernel"], grads[names[li] + "/bias"] = ref.conv2d_bwd(
                 x4, w, y, dy.reshape(y.shape), CONV_STRIDES[li], act=1, cutoff=cfg.relu_cutoff, want_dx=li > 0)
         return loss, grads, logits, dlogits

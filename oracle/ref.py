@@ -176,6 +176,37 @@ def conv_out_size(n, k, s):
     return out, max((out - 1) * s + k - n, 0) // 2
 
 
+def _hash32(x):
+    """oracle_hash32 (oracle_impl.h) on a uint32 array."""
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16); x *= np.uint32(0x7feb352d); x ^= x >> np.uint32(15); x *= np.uint32(0x846ca68b); x ^= x >> np.uint32(16)
+    return x
+
+
+def drop_keep(seed, idx, rate):
+    """oracle_drop_keep (oracle_impl.h) for an array of flat indices: the keep-mask shared bit for bit with the CUDA path."""
+    idx = np.asarray(idx, np.uint64)
+    with np.errstate(over="ignore"):
+        hi = (idx >> np.uint64(32)).astype(np.uint32) * np.uint32(0x9e3779b9)
+        h = _hash32((idx & np.uint64(0xffffffff)).astype(np.uint32) ^ _hash32(np.uint32(seed & 0xffffffff) ^ hi))
+    return ((h >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)) >= np.float32(rate)
+
+
+def dropout(x, rate, seed, pitch=None):
+    """y = keep ? x / (1 - rate) : 0 over the flat index of x viewed as [rows, cols]; `pitch` >= cols: the row pitch the
+    product path stores the tensor with (conv outputs are padded to the GEMM width), which enters the index.
+    tf.layers.dropout / DropoutWrapper / the cuDNN RNNs' inter-layer dropout; applied to a gradient it is the backward."""
+    if rate <= 0:
+        return x
+    x = np.asarray(x)
+    cols = x.shape[-1]
+    flat = x.reshape(-1, cols)
+    pitch = cols if pitch is None else pitch
+    idx = np.arange(flat.shape[0], dtype=np.uint64)[:, None] * np.uint64(pitch) + np.arange(cols, dtype=np.uint64)[None, :]
+    inv_keep = x.dtype.type(1.0 / (1.0 - float(np.float32(rate))))
+    return (np.where(drop_keep(seed, idx, rate), flat * inv_keep, x.dtype.type(0))).reshape(x.shape)
+
+
 def conv2d_fwd(x, w, b, strides, act=1, cutoff=20.0):
     """x [T,B,F,C], w [kt,kf,C,N] (TF HWIO, height = time), 'SAME' -> y [To,B,Fo,N]."""
     dtype = x.dtype

@@ -95,7 +95,10 @@ def test_argument_validation_of_the_new_entry_points_needs_no_gpu(lib):
     assert rc == -1 and b"isn't supported" in lib.ctcasr_last_error()               # :196
     rc = lib.ctcasr_featurize(one, 1, 16000, n, 1, 1, 0, 16000, 80, one, 50, one, one, 1 << 20, None)
     assert rc == -1 and b"99" in lib.ctcasr_last_error()                            # output too short for 99 frames
-    rc = lib.ctcasr_conv2d_fwd(one, 1, one, one, one, 10, 1, 8, 2, 3, 3, 1, 1, 64, 1, 20.0, 0, None, 0, None)
+    rc = lib.ctcasr_conv2d_fwd(one, 1, one, one, one, 10, 1, 8, 2, 3, 3, 1, 1, 64, 1, 20.0, 0.0, 0, 0, None, 0, None)
     assert rc == -1                                                                 # pitch 1 < 2 channels
-    rc = lib.ctcasr_conv2d_fwd(one, 2, one, one, one, 10, 1, 8, 2, 3, 3, 1, 1, 64, 1, 20.0, 0, None, 0, None)
+    rc = lib.ctcasr_conv2d_fwd(one, 2, one, one, one, 10, 1, 8, 2, 3, 3, 1, 1, 64, 1, 20.0, 0.0, 0, 0, None, 0, None)
     assert rc == -3 and b"workspace" in lib.ctcasr_last_error()
+    rc = lib.ctcasr_conv2d_fwd(one, 2, one, one, one, 10, 1, 8, 2, 3, 3, 1, 1, 64, 1, 20.0, 1.0, 0, 0, None, 0, None)
+    assert rc == -1 and b"drop_rate" in lib.ctcasr_last_error()                     # keep probability 0
+    assert lib.ctcasr_dropout(one, one, 4, 1.5, 0, None) == -1

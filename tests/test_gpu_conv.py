@@ -90,6 +90,15 @@ def test_ds2_whole_path_small(compute):
     assert model._saved["T"] == 31
 
 
+def test_ds2_whole_path_with_conv_and_rnn_dropout():
+    """Every dropout of the ds2 path on: tf.layers.dropout after each conv layer (asr/util/tf_contrib.py:135; the keep-mask
+    index runs over the padded channel pitch), the DropoutWrapper masks of the RNN stack, dense4's dropout."""
+    cfg = ModelConfig(used_model="ds2", conv_filters=(8, 8, 64), num_units_dense=64, num_layers_rnn=2, num_units_rnn=32,
+                      rnn_cell="rnn_tanh", num_features=20, cudnn=False, dense_dropout_rate=0.1, conv_dropout_rate=0.15,
+                      rnn_dropout_rate=0.2, compute="fp32", random_seed=77)
+    _whole_path(cfg, B=4, T=61, L=6, ragged=True, training=True)
+
+
 def test_ds2_model_shapes_follow_the_reference():
     cfg = ModelConfig(used_model="ds2", num_layers_rnn=1, num_units_rnn=64, num_units_dense=64, compute="fp32")
     plan = conv_plan(cfg, 999)

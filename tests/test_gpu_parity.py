@@ -280,7 +280,7 @@ def test_adam_vs_oracle():
 
 
 # --------------------------------------------------------------------------------- whole hot path
-def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL, ltol=RTOL):
+def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL, ltol=RTOL, training=False):
     from ctc_asr_b200.model import CTCModel
     params = synthetic.init_params(cfg, seed=1)
     rng = np.random.default_rng(seed)
@@ -293,11 +293,13 @@ def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL, ltol=RTOL):
         for b in range(B):
             x[b, sl[b]:] = 0
     model = CTCModel(cfg, params=params)
-    logits, sl_out = model.inference_fn(torch.from_numpy(x), torch.from_numpy(sl), training=False)
+    logits, sl_out = model.inference_fn(torch.from_numpy(x), torch.from_numpy(sl), training=training)
     loss = model.loss_fn(logits, sl_out, (torch.from_numpy(lab), torch.from_numpy(ll)))
     model.backward()
     torch.cuda.synchronize()
-    oloss, ograds, ologits, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll)
+    # training: the dropout keep-masks are the counter hash both sides share, seeded by FLAGS.random_seed at step 0
+    oloss, ograds, ologits, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll, training=training,
+                                                         seed=int(cfg.random_seed))
     sl = sl_out.cpu().numpy()                          # ds2: the conv length for every utterance
     assert rel_err(logits.cpu().numpy(), ologits) < ltol
     assert abs(float(loss) - oloss) / abs(oloss) < ltol
@@ -310,6 +312,46 @@ def _whole_path(cfg, B, T, L, ragged, seed=0, gtol=RTOL, ltol=RTOL):
     oi, on = ref.greedy_decode(logits.cpu().numpy(), sl)
     assert (n.cpu().numpy() == on).all() and (ids.cpu().numpy() == oi).all()
     return model
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.25])
+def test_dropout_op_vs_oracle(rate):
+    """ctcasr_dropout: the keep-mask is integer work (bit-exact against the oracle's hash), kept values are x / (1 - rate)."""
+    rng = np.random.default_rng(12)
+    x = (rng.standard_normal((333, 40)) + 3.0).astype(np.float32)
+    y = ops.dropout(dev(x), rate, 987654321)
+    want = ref.dropout(x.astype(np.float64), rate, 987654321)
+    got = y.cpu().numpy()
+    assert np.array_equal(got == 0, want == 0)
+    assert rel_err(got, want) < 1e-6
+    if rate:
+        assert 0.2 < (got == 0).mean() < 0.3
+    z = dev(x)
+    ops.dropout(z, rate, 987654321, out=z)                                # in place: the backward pass on a gradient
+    assert torch.equal(z, y)
+
+
+@pytest.mark.parametrize("cudnn,cell,layers", [(False, "rnn_tanh", 2), (True, "rnn_relu", 3), (True, "lstm", 2)])
+def test_whole_path_with_rnn_and_dense_dropout(cudnn, cell, layers):
+    """Training mode with every dropout of the ds1 path on: dense (asr/util/tf_contrib.py:58), the RNN stack's
+    DropoutWrapper in / out masks (TF path, :190-194) or inter-layer dropout (cuDNN path, asr/model.py:201-206)."""
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=2, num_units_dense=64, num_layers_rnn=layers, num_units_rnn=32,
+                      rnn_cell=cell, cudnn=cudnn, dense_dropout_rate=0.1, rnn_dropout_rate=0.2, compute="fp32",
+                      random_seed=4321)
+    _whole_path(cfg, B=4, T=50, L=6, ragged=True, training=True)
+
+
+def test_rnn_dropout_is_off_in_eval_and_changes_training():
+    cfg = ModelConfig(used_model="ds1", num_layers_dense=1, num_units_dense=64, num_layers_rnn=2, num_units_rnn=32,
+                      rnn_cell="rnn_relu", cudnn=True, dense_dropout_rate=0.0, rnn_dropout_rate=0.5, compute="fp32")
+    from ctc_asr_b200.model import CTCModel
+    x, sl, lab, ll = synthetic.fixed_batch(3, 40, 5, F=cfg.num_features, seed=3)
+    m = CTCModel(cfg, params=synthetic.init_params(cfg, seed=1))
+    ev = m.inference_fn(torch.from_numpy(x), torch.from_numpy(sl), training=False)[0].clone()
+    m0 = CTCModel(cfg.replace(rnn_dropout_rate=0.0), params=synthetic.init_params(cfg, seed=1))
+    assert torch.equal(ev, m0.inference_fn(torch.from_numpy(x), torch.from_numpy(sl), training=True)[0])
+    tr = m.inference_fn(torch.from_numpy(x), torch.from_numpy(sl), training=True)[0]
+    assert not torch.allclose(ev, tr)
 
 
 def test_cfg1_ds1_tanh_single_utterance():

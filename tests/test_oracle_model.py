@@ -254,3 +254,42 @@ def test_operand_rounding_mode_is_bf16_round_to_nearest_even():
     for t in range(5):                       # forward direction of utterance 0 by hand
         h = np.tanh(bf(xs[t, 0]) @ bf(wx[:, :H]) + bf(h) @ bf(wh[0]) + bias[:H])
         assert np.abs(y[t, 0, :H] - h).max() < 1e-12
+
+
+def test_numpy_keep_mask_is_the_c_oracles():
+    """ref.dropout (numpy) uses the same counter hash as oracle_dense_fwd (and the CUDA epilogues): identical keep-mask and
+    scaling through an identity layer; about `rate` of the entries dropped; applying it twice to a gradient is what the
+    backward pass of the RNN / conv dropout does."""
+    rng = np.random.default_rng(0)
+    M, N = 37, 24
+    x = rng.standard_normal((M, N)) + 3.0
+    y = ref.dense_fwd(x, np.eye(N), np.zeros(N), act=0, drop_rate=0.3, seed=12345)
+    assert np.array_equal(y, ref.dropout(x, 0.3, 12345))
+    assert 0.2 < (y == 0).mean() < 0.4
+    assert ref.dropout(x, 0.0, 1) is x
+    # the padded pitch enters the index: a [M, 8] tensor stored with pitch 64 is columns 0..7 of the [M, 64] mask
+    wide = ref.dropout(np.ones((M, 64)), 0.5, 9)
+    assert np.array_equal(ref.dropout(np.ones((M, 8)), 0.5, 9, pitch=64), wide[:, :8])
+
+
+def test_whole_path_oracle_dropout_gradients_by_finite_differences():
+    """Oracle with every RNN dropout on (fixed masks): directional finite difference of the loss against its gradients."""
+    from types import SimpleNamespace
+    cfg = SimpleNamespace(used_model="ds1", num_layers_dense=1, num_units_dense=8, num_layers_rnn=2, num_units_rnn=6,
+                          rnn_cell="rnn_tanh", cudnn=False, dense_dropout_rate=0.2, rnn_dropout_rate=0.3, relu_cutoff=20.0,
+                          forget_bias=1.0, num_classes=5, num_features=4, conv_filters=())
+    rng = np.random.default_rng(3)
+    shapes = {"dense/dense/kernel": (4, 8), "dense/dense/bias": (8,), "rnn/l0/wx": (8, 12), "rnn/l0/wh": (2, 6, 6),
+              "rnn/l0/bias": (12,), "rnn/l1/wx": (12, 12), "rnn/l1/wh": (2, 6, 6), "rnn/l1/bias": (12,),
+              "dense4/dense/kernel": (12, 8), "dense4/dense/bias": (8,), "logits/dense/kernel": (8, 5), "logits/dense/bias": (5,)}
+    params = {k: rng.standard_normal(v) * 0.4 for k, v in shapes.items()}
+    x = rng.standard_normal((2, 9, 4))
+    sl, lab, ll = np.array([9, 7], np.int32), np.array([[1, 2], [3, 0]], np.int32), np.array([2, 1], np.int32)
+    loss, grads, _, _ = model_ref.loss_and_grads(cfg, params, x, sl, lab, ll, training=True, seed=5)
+    d = {k: rng.standard_normal(v.shape) for k, v in params.items()}
+    eps = 1e-6
+    lp = model_ref.loss_and_grads(cfg, {k: v + eps * d[k] for k, v in params.items()}, x, sl, lab, ll, training=True, seed=5)[0]
+    lm = model_ref.loss_and_grads(cfg, {k: v - eps * d[k] for k, v in params.items()}, x, sl, lab, ll, training=True, seed=5)[0]
+    fd = (lp - lm) / (2 * eps)
+    an = sum(float((grads[k] * d[k]).sum()) for k in params)
+    assert abs(fd - an) < 1e-6 * max(1.0, abs(an)), (fd, an)
