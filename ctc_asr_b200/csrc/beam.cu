@@ -380,13 +380,16 @@ __global__ void __launch_bounds__(NT, 1) beam_search_kernel(const Params p)
                                 int at = hn;
                                 if (hn == W) {
                                     at = bi;
-                                    const int e = hr[bi];
-                                    if (lane == 0 && e < W) {
-                                        gone[e] = 1;
-                                        // a child of THIS prefix that is still ahead in class order is re-offered right away: rejected
-                                        // (its fresh score cannot exceed the re-scored one that has just been the bottom)
-                                        if (psl[e] == i && B0.lab[e] > cc) wiped[e] = 1;
+                                    if (lane == 0) {
+                                        const int e = hr[bi];
+                                        if (e < W) {
+                                            gone[e] = 1;
+                                            // a child of THIS prefix that is still ahead in class order is re-offered right away: rejected
+                                            // (its fresh score cannot exceed the re-scored one that has just been the bottom)
+                                            if (psl[e] == i && B0.lab[e] > cc) wiped[e] = 1;
+                                        }
                                     }
+                                    __syncwarp();           // the read of the evicted entry before its slot is overwritten
                                 } else {
                                     ++hn;
                                 }
