@@ -48,6 +48,10 @@ SIGNATURES = {
     "ctcasr_profile_collect": (_i, [_vp, _vp, _i]),
     "ctcasr_set_scratch": (_i, [_vp, _sz]),
     "ctcasr_scratch_needed": (_sz, []),
+    "ctcasr_scratch_bytes": (_sz, []),
+    "ctcasr_create": (_i, [_vp]),
+    "ctcasr_use": (_i, [_vp]),
+    "ctcasr_destroy": (_i, [_vp]),
     "ctcasr_transpose01": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ctcasr_adam": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _f, _f, _f, _f, _f, _vp]),
     "ctcasr_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -569,19 +569,31 @@ static int encode_map(CUtensorMap *map, const void *base, bool bf16, uint64_t in
     return CTCASR_OK;
 }
 
-// ---- scratch arena for the split operands (set by the caller: the library allocates nothing) -------
-static char *g_scratch = nullptr;
-static size_t g_scratch_bytes = 0, g_scratch_needed = 0;
-
-// ---- split cache (see split_scope_begin in gemm.cuh) -----------------------------------------------------
+// ---- context: the caller's scratch arena for the split operands (the library allocates nothing) and the split cache
+// (see split_scope_begin in gemm.cuh).  One per ctcasr_handle_t; a thread works on the context it bound with
+// ctcasr_use() (the process-default one otherwise), so two host threads driving two streams do not share an arena.
 struct SplitEntry {
     const float *base; int rows, cols, ld, np;      // the fp32 matrix that was split
     __nv_bfloat16 *out; int ldo; size_t piece;      // its pieces in the arena
 };
-static SplitEntry g_split[16];
-static int g_nsplit = 0;
-static bool g_scope = false;
-static size_t g_cursor = 0;                          // arena bytes in use (reset per GEMM outside a scope)
+struct Context {
+    char *scratch = nullptr;
+    size_t scratch_bytes = 0, scratch_needed = 0;
+    SplitEntry split[16];
+    int nsplit = 0;
+    bool scope = false;
+    size_t cursor = 0;                              // arena bytes in use (reset per GEMM outside a scope)
+};
+static Context g_default_ctx;
+static thread_local Context *g_ctx = nullptr;
+static inline Context &ctx() { return g_ctx ? *g_ctx : g_default_ctx; }
+#define g_scratch (ctx().scratch)
+#define g_scratch_bytes (ctx().scratch_bytes)
+#define g_scratch_needed (ctx().scratch_needed)
+#define g_split (ctx().split)
+#define g_nsplit (ctx().nsplit)
+#define g_scope (ctx().scope)
+#define g_cursor (ctx().cursor)
 
 // bf16 pieces of the fp32 matrix x [rows][cols] (pitch ld): from the cache when x lies inside a matrix that
 // was split in this scope, otherwise split now.  Returns the pointer to piece 0, its pitch and the piece stride.
@@ -687,9 +699,9 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
                         g_scratch_bytes, need);
         }
         for (int z = 0; z < g.nz; ++z) {
-            const __nv_bfloat16 *sa, *sb;
-            int la, lb;
-            size_t pa, pb;
+            const __nv_bfloat16 *sa = nullptr, *sb = nullptr;
+            int la = 0, lb = 0;
+            size_t pa = 0, pb = 0;
             if (int rc = acquire_split<NP>(g.A[z], a_rows, a_cols, g.lda, stream, &sa, &la, &pa)) return rc;
             if (int rc = acquire_split<NP>(g.B[z], b_rows, b_cols, g.ldb, stream, &sb, &lb, &pb)) return rc;
             // the two problems of a batched GEMM share one tensor-map geometry
@@ -786,9 +798,9 @@ int gemm_scratch_check(int compute, int nz, int M, int N, int K)
     if (compute != CTCASR_COMPUTE_BF16X3 && compute != CTCASR_COMPUTE_BF16) return CTCASR_OK;
     auto pad = [](int v) { return (size_t)((v + 7) / 8 * 8); };
     const size_t need = (size_t)nz * (align_up(6 * pad(M) * pad(K), 1024) + align_up(6 * pad(K) * pad(N), 1024));
-    if (need > tc::g_scratch_bytes) {
-        if (need > tc::g_scratch_needed) tc::g_scratch_needed = need;
-        return fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", tc::g_scratch_bytes, need);
+    if (need > tc::ctx().scratch_bytes) {
+        if (need > tc::ctx().scratch_needed) tc::ctx().scratch_needed = need;
+        return fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", tc::ctx().scratch_bytes, need);
     }
     return CTCASR_OK;
 }
@@ -798,14 +810,14 @@ int split_scope_begin(int compute, const size_t *elems, int n)
     if (compute != CTCASR_COMPUTE_BF16X3 && compute != CTCASR_COMPUTE_BF16) return CTCASR_OK;
     size_t need = 0;
     for (int i = 0; i < n; ++i) need += align_up(6 * elems[i], 1024);
-    if (need > tc::g_scratch_bytes) {
-        if (need > tc::g_scratch_needed) tc::g_scratch_needed = need;
-        return fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", tc::g_scratch_bytes, need);
+    if (need > tc::ctx().scratch_bytes) {
+        if (need > tc::ctx().scratch_needed) tc::ctx().scratch_needed = need;
+        return fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", tc::ctx().scratch_bytes, need);
     }
-    tc::g_scope = true; tc::g_nsplit = 0; tc::g_cursor = 0;
+    tc::ctx().scope = true; tc::ctx().nsplit = 0; tc::ctx().cursor = 0;
     return CTCASR_OK;
 }
-void split_scope_end() { tc::g_scope = false; tc::g_nsplit = 0; tc::g_cursor = 0; }
+void split_scope_end() { tc::ctx().scope = false; tc::ctx().nsplit = 0; tc::ctx().cursor = 0; }
 
 int split_reserve(const float *key, int rows, int cols, int ld, int np, __nv_bfloat16 **pieces)
 {
@@ -827,9 +839,9 @@ int split_reserve(const float *key, int rows, int cols, int ld, int np, __nv_bfl
 
 void *scratch_free(size_t bytes)
 {
-    const size_t used = tc::g_scope ? tc::g_cursor : 0;
-    if (!tc::g_scratch || used + bytes > tc::g_scratch_bytes) return nullptr;
-    return tc::g_scratch + used;
+    const size_t used = tc::ctx().scope ? tc::ctx().cursor : 0;
+    if (!tc::ctx().scratch || used + bytes > tc::ctx().scratch_bytes) return nullptr;
+    return tc::ctx().scratch + used;
 }
 
 int gemm_tc(const GemmArgs &g, int compute, cudaStream_t stream)
@@ -847,8 +859,30 @@ int gemm_tc(const GemmArgs &g, int compute, cudaStream_t stream)
 extern "C" int ctcasr_set_scratch(void *ptr, size_t bytes)
 {
     if (bytes && (!ptr || ((uintptr_t)ptr & 1023))) return ctcasr::fail(CTCASR_ERR_INVALID, "set_scratch: need a 1024-B aligned device pointer");
-    ctcasr::tc::g_scratch = reinterpret_cast<char *>(ptr);
-    ctcasr::tc::g_scratch_bytes = bytes;
+    ctcasr::tc::ctx().scratch = reinterpret_cast<char *>(ptr);
+    ctcasr::tc::ctx().scratch_bytes = bytes;
     return CTCASR_OK;
 }
-extern "C" size_t ctcasr_scratch_needed(void) { return ctcasr::tc::g_scratch_needed; }
+extern "C" size_t ctcasr_scratch_needed(void) { return ctcasr::tc::ctx().scratch_needed; }
+extern "C" size_t ctcasr_scratch_bytes(void) { return ctcasr::tc::ctx().scratch_bytes; }
+
+extern "C" int ctcasr_create(ctcasr_handle_t *out)
+{
+    if (!out) return ctcasr::fail(CTCASR_ERR_INVALID, "create: null pointer");
+    *out = reinterpret_cast<ctcasr_handle_t>(new ctcasr::tc::Context());
+    return CTCASR_OK;
+}
+extern "C" int ctcasr_use(ctcasr_handle_t h)
+{
+    ctcasr::tc::g_ctx = reinterpret_cast<ctcasr::tc::Context *>(h);      // NULL: the process-default context
+    return CTCASR_OK;
+}
+extern "C" int ctcasr_destroy(ctcasr_handle_t h)
+{
+    if (!h) return CTCASR_OK;
+    ctcasr::tc::Context *c = reinterpret_cast<ctcasr::tc::Context *>(h);
+    if (c->scope) return ctcasr::fail(CTCASR_ERR_INVALID, "destroy: a split scope is open on this context");
+    if (ctcasr::tc::g_ctx == c) ctcasr::tc::g_ctx = nullptr;
+    delete c;
+    return CTCASR_OK;
+}

@@ -231,6 +231,17 @@ int ctcasr_profile_collect(double *ms, int *count, int ntags);
  * ctcasr_scratch_needed() tells how much. */
 int ctcasr_set_scratch(void *ptr, size_t bytes);
 size_t ctcasr_scratch_needed(void);
+size_t ctcasr_scratch_bytes(void);
+/* Contexts (no global mutable state except an opaque handle).  The scratch arena and the cache of
+ * split operands that lives in it belong to a context.  Every host thread works on the context it last bound with
+ * ctcasr_use() — the process-default context until then, or after ctcasr_use(NULL) — so two host threads that drive two
+ * CUDA streams (TensorFlow's inter-op pool running two towers) give each its own handle and its own arena and never
+ * share split operands.  Entry points that take a workspace argument use nothing else.  The reference has no
+ * counterpart: TF owns this state in its per-stream scratch allocators. */
+typedef struct ctcasr_context *ctcasr_handle_t;
+int ctcasr_create(ctcasr_handle_t *out);
+int ctcasr_use(ctcasr_handle_t handle);
+int ctcasr_destroy(ctcasr_handle_t handle);
 /* [A,B,C] -> [B,A,C]: batch-major sequences (asr/model.py:129) <-> the time-major layout used
  * internally and by the logits (asr/model.py:233) */
 int ctcasr_transpose01(const float *in, float *out, int A, int B, int C, void *stream);

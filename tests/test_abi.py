@@ -102,3 +102,24 @@ def test_argument_validation_of_the_new_entry_points_needs_no_gpu(lib):
     rc = lib.ctcasr_conv2d_fwd(one, 2, one, one, one, 10, 1, 8, 2, 3, 3, 1, 1, 64, 1, 20.0, 1.0, 0, 0, None, 0, None)
     assert rc == -1 and b"drop_rate" in lib.ctcasr_last_error()                     # keep probability 0
     assert lib.ctcasr_dropout(one, one, 4, 1.5, 0, None) == -1
+
+
+def test_contexts_keep_their_own_scratch_arena(lib):
+    """ctcasr_handle_t: the scratch arena belongs to a context; a thread sees the context it bound with
+    ctcasr_use(), other threads the process-default one."""
+    import threading
+    h1, h2 = ctypes.c_void_p(), ctypes.c_void_p()
+    assert lib.ctcasr_create(ctypes.byref(h1)) == 0 and lib.ctcasr_create(ctypes.byref(h2)) == 0
+    fake = ctypes.c_void_p(1 << 20)                         # 1024-B aligned "device" address; never dereferenced here
+    assert lib.ctcasr_set_scratch(None, 0) == 0             # default context: no arena
+    assert lib.ctcasr_use(h1) == 0 and lib.ctcasr_set_scratch(fake, 4096) == 0
+    assert lib.ctcasr_use(h2) == 0 and lib.ctcasr_set_scratch(fake, 8192) == 0
+    assert lib.ctcasr_scratch_bytes() == 8192
+    assert lib.ctcasr_use(h1) == 0 and lib.ctcasr_scratch_bytes() == 4096
+    seen = []
+    t = threading.Thread(target=lambda: seen.append(lib.ctcasr_scratch_bytes()))    # another thread: default context
+    t.start(); t.join()
+    assert seen == [0]
+    assert lib.ctcasr_use(None) == 0 and lib.ctcasr_scratch_bytes() == 0
+    assert lib.ctcasr_set_scratch(ctypes.c_void_p(12), 64) == -1                    # misaligned
+    assert lib.ctcasr_destroy(h1) == 0 and lib.ctcasr_destroy(h2) == 0 and lib.ctcasr_destroy(None) == 0

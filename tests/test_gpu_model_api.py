@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from ctc_asr_b200 import input_pipeline as ip, synthetic
+from ctc_asr_b200 import _lib, input_pipeline as ip, ops, synthetic
 from ctc_asr_b200.model import CTCModel
 from ctc_asr_b200.params import ModelConfig
 from oracle import ref
@@ -117,3 +117,48 @@ def test_csv_wav_corpus_to_train_step(tmp_path, target):
     logits, sl = model.inference_fn(features["spectrogram"], features["spectrogram_length"], training=False)
     decoded, plaintext, _ = model.decode_fn(logits, sl, features["label_plaintext"], decoder="greedy")
     assert len(plaintext) == len(features["label_plaintext"])
+
+
+def test_two_host_threads_with_their_own_contexts_and_streams():
+    """ctcasr_handle_t: two host threads, each bound to its own context (own split-operand arena) and its own stream,
+    run the tcgen05 dense layer at the same time; both get the bits the main thread gets alone."""
+    import ctypes
+    import threading
+    lib = _lib.load()
+    rng = np.random.default_rng(31)
+    M, K, N = 4096, 512, 1024
+    x = torch.from_numpy(rng.standard_normal((M, K)).astype(np.float32)).cuda()
+    ws = [torch.from_numpy((rng.standard_normal((K, N)) * 0.05).astype(np.float32)).cuda() for _ in range(2)]
+    b = torch.zeros(N, device="cuda")
+    C = _lib.COMPUTE_ID["bf16x3"]
+    want = [ops.dense_fwd(x, w, b, act=0, compute=C).clone() for w in ws]
+    torch.cuda.synchronize()
+    got, errs = [None, None], []
+
+    def worker(i):
+        try:
+            h = ctypes.c_void_p()
+            assert lib.ctcasr_create(ctypes.byref(h)) == 0 and lib.ctcasr_use(h) == 0
+            arena = torch.empty((64 << 20) + 1024, dtype=torch.uint8, device="cuda")
+            base = (arena.data_ptr() + 1023) // 1024 * 1024
+            assert lib.ctcasr_set_scratch(ctypes.c_void_p(base), 64 << 20) == 0
+            stream = torch.cuda.Stream()
+            y = torch.empty(M, N, device="cuda")
+            with torch.cuda.stream(stream):
+                for _ in range(20):
+                    rc = lib.ctcasr_dense_fwd(_lib.ptr(x), _lib.ptr(ws[i]), _lib.ptr(b), _lib.ptr(y), M, K, N, 0, 20.0, 0.0, 0, C,
+                                              ctypes.c_void_p(stream.cuda_stream))
+                    assert rc == 0, lib.ctcasr_last_error()
+            stream.synchronize()
+            got[i] = y
+            assert lib.ctcasr_use(None) == 0 and lib.ctcasr_destroy(h) == 0
+        except Exception as e:  # noqa
+            errs.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
