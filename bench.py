@@ -386,7 +386,7 @@ def run_train(ctx):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "roofline_gemm": {"kernel": "gemm_tc_kernel (%d launches)" % prof_n[2], "bound": "tensor", "achieved": gemm_tflops,
+        "roofline_gemm": {"kernel": "gemm_tc_kernel + gemm_tc_pair_kernel (%d launches)" % prof_n[2], "bound": "tensor", "achieved": gemm_tflops,
                           "peak": gemm_peak, "unit": "TFLOP/s", "frac": gemm_tflops / gemm_peak if gemm_peak else None,
                           "share_of_step": prof_ms[2] / ms,
                           "frac_of_bf16_sustained": gemm_tflops / peaks["bf16_tflops_sustained"],
