@@ -248,6 +248,16 @@ extern "C" int ctcasr_conv2d_fwd(const float *x, int x_pitch, const float *w, co
     CTCASR_REQUIRE(rows <= 0x7fffffff, "conv2d_fwd: %zu output positions", rows);
     const size_t need = align_up(rows * g.Kp * sizeof(float), 256);
     if (!ws || ws_bytes < need) return fail(CTCASR_ERR_WORKSPACE, "conv2d_fwd: workspace %zu < %zu", ws_bytes, need);
+    if (conv_tc_eligible(compute, T, B, F, C, kt, kf, st, sf, N) && ((uintptr_t)x & 15) == 0 && x_pitch % 4 == 0 && N % 8 == 0) {
+        // implicit GEMM (conv_tc.cu): the TMA unit gathers the taps from the layer input, no patch matrix
+        const int np = compute == CTCASR_COMPUTE_BF16 ? 1 : (act != 0 ? 3 : 2);
+        const size_t elems[2] = {(size_t)T * B * F * C, (size_t)g.Kp * N};
+        SplitScope scope;
+        if (int rc = split_scope_begin(compute, elems, 2)) return rc;
+        scope.open = true;
+        return conv_tc_fwd(x, x_pitch, w, N, bias, y, N, T, B, F, C, kt, kf, st, sf, g.To, g.Fo, g.pt, g.pf, N, np, act, cutoff,
+                           drop_rate, seed, stream);
+    }
     if (int rcs = gemm_scratch_check(compute, 1, (int)rows, N, g.Kp)) return rcs;
     float *col = reinterpret_cast<float *>(ws);
     GemmArgs a;

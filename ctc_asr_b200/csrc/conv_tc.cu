@@ -1,0 +1,314 @@
+// conv_tc.cu — implicit-GEMM forward pass of a 'ds2' conv layer on tcgen05 (sm_100a): tf.layers.conv2d(SAME) + relu +
+// tf.minimum + tf.layers.dropout (asr/util/tf_contrib.py:123-135) WITHOUT a patch matrix.
+//
+// conv.cu writes every output position's kt x kf x C patch to HBM (14.2 GB of bf16 pieces for the second layer at
+// B = 32 x 10 s) and multiplies that matrix by the kernel.  Here the A operand of the same GEMM is gathered by the TMA
+// unit straight from the layer input: the input's bf16 pieces are viewed as a 5-D tensor [piece][T][B][F][C] and one
+// k-block of the contraction is ONE TAP (it, jf) x 32 channels, i.e. the box
+//     { 32 channels, FOB output frequencies (traversal stride sf), BB utterances, TB output frames (stride st), 1 piece }
+// at coordinate (c0, fo0*sf + jf - pf, b0, to0*st + it - pt, piece) — FOB*BB*TB = 128 rows of 64 B, exactly the K-major
+// SWIZZLE_64B tile the MMA reads.  'SAME' padding is the TMA's out-of-range zero fill (coordinates may be negative), so
+// neither the input nor the patches are ever copied; the input pieces (181 MB for that layer) stay in L2.  The B operand
+// is the kernel [Kp, N] in its HWIO row order (row = (it*kf + jf)*C + c = k-block * 32 + c), split as in gemm_tc.cu.
+// Arithmetic, pipeline and epilogue are those of gemm_tc_kernel: NP = 3 pieces / 6 products (bf16x3 through the ReLU
+// kink) or NP = 1 (compute = 'bf16'), fp32 accumulation in tensor memory, TMA producer warp / one MMA-issuing thread /
+// four epilogue warps, two accumulators; the epilogue maps a tile row back to its output position (to, b, fo).
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+namespace ctcasr {
+namespace convtc {
+
+constexpr int BM = 128, BK = 32, NACC = 2, ACC_COLS = 128, NTHREADS = 192;
+constexpr int A_PIECE = BM * BK * 2;            // 8 KB: 128 rows x 32 bf16
+constexpr int B_BOX = BK * 128;                 // 4 KB: 32 k-rows x 64 filters (MN-major, SWIZZLE_128B)
+constexpr int STG_LD = 36, STG_BYTES = 4 * 32 * STG_LD * 4;
+
+template <int NP> struct Cfg {
+    static constexpr int NPROD = NP == 3 ? 6 : (NP == 2 ? 3 : 1);
+    static constexpr int STAGE = NP * (A_PIECE + 2 * B_BOX);                    // up to 128 filters: two boxes
+    static constexpr int NSTAGE = NP == 3 ? 4 : (NP == 2 ? 6 : 8);              // 192 / 192 / 128 KB
+    static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + STG_BYTES;
+};
+
+struct Params {
+    int To, B, Fo, N, ldc;              // output [To, B, Fo, ldc], N real GEMM columns (multiple of 16, <= 128)
+    int fob, bb, tb;                    // rows of a tile: tb x bb x fob = 128 (fo fastest)
+    int fo_groups, b_groups, to_groups, num_tiles;
+    int kt, kf, cchunks;                // taps and 32-channel chunks per tap: kt * kf * cchunks k-blocks
+    int st, sf, pt, pf;
+    int nbx;                            // 64-filter boxes of B per k-block (1 or 2)
+    float *y;
+    Epilogue epi;
+};
+
+__device__ __forceinline__ void decode_tile(const Params &p, int u, int &to0, int &b0, int &fo0)
+{
+    const int fg = u % p.fo_groups;
+    const int r = u / p.fo_groups;
+    const int bg = r % p.b_groups, tg = r / p.b_groups;
+    to0 = tg * p.tb; b0 = bg * p.bb; fo0 = fg * p.fob;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const Params p)
+{
+    using C_ = Cfg<NP>;
+    constexpr int NSTAGE = C_::NSTAGE, STAGE = C_::STAGE;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + NSTAGE * STAGE;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + NACC + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 2 * NACC);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+    float *stg = reinterpret_cast<float *>(smem_raw + (bar_base + 256 - ptx::smem_u32(smem_raw))) + (threadIdx.x >> 5 & 3) * 32 * STG_LD;
+    auto a_addr = [&](int stage, int pc) { return smem_base + stage * STAGE + pc * A_PIECE; };
+    auto b_addr = [&](int stage, int pc) { return smem_base + stage * STAGE + NP * A_PIECE + pc * 2 * B_BOX; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = p.kt * p.kf * p.cchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < NACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 4); }
+        ptx::mbar_fence_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapX); ptx::tma_prefetch_desc(&mapW); }
+    if (warp == 5) ptx::tmem_alloc(tmem_slot, NACC * ACC_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        // ===== TMA producer: one tap x 32 channels of the 128 output positions + the kernel rows of that tap =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t bytes = (uint32_t)NP * (A_PIECE + p.nbx * B_BOX);
+            for (int u = blockIdx.x; u < p.num_tiles; u += gridDim.x) {
+                int to0, b0, fo0;
+                decode_tile(p, u, to0, b0, fo0);
+                const int t0 = to0 * p.st - p.pt, f0 = fo0 * p.sf - p.pf;
+                int kb = 0;
+                for (int it = 0; it < p.kt; ++it)
+                    for (int jf = 0; jf < p.kf; ++jf)
+                        for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
+                            ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                            ptx::mbar_expect_tx(full_bar(stage), bytes);
+#pragma unroll
+                            for (int pc = 0; pc < NP; ++pc) {
+                                ptx::tma_load_5d(a_addr(stage, pc), &mapX, cc * BK, f0 + jf, b0, t0 + it, pc, full_bar(stage));
+                                for (int j = 0; j < p.nbx; ++j)
+                                    ptx::tma_load_3d(b_addr(stage, pc) + j * B_BOX, &mapW, j * 64, kb * BK, pc, full_bar(stage));
+                            }
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr int PA[6] = {0, 0, 1, 0, 1, 2};
+            constexpr int PB[6] = {0, 1, 0, 2, 1, 0};
+            const uint32_t idesc = ptx::make_idesc_bf16(BM, p.N, 0, 1);        // A K-major, B MN-major
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < p.num_tiles; u += gridDim.x) {
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int q = 0; q < C_::NPROD; ++q) {
+                        const uint64_t adesc = ptx::make_smem_desc(a_addr(stage, PA[q]), 16, 512, 4);          // K-major, SWIZZLE_64B
+                        const uint64_t bdesc = ptx::make_smem_desc(b_addr(stage, PB[q]), B_BOX, 1024, 2);      // MN-major, SWIZZLE_128B
+#pragma unroll
+                        for (int j = 0; j < BK / 16; ++j)
+                            ptx::mma_bf16(tmem_d, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(128 * j), idesc, (kb | q | j) != 0);
+                    }
+                    ptx::mma_commit(empty_bar(stage));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit(tfull_bar(acc));
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: tile row r = (tl * bb + bl) * fob + fol  ->  output row ((to0 + tl) * B + b0 + bl) * Fo + fo0 + fol =====
+        int acc = 0; uint32_t acc_phase = 0;
+        const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
+        for (int u = blockIdx.x; u < p.num_tiles; u += gridDim.x) {
+            int to0, b0, fo0;
+            decode_tile(p, u, to0, b0, fo0);
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * ACC_COLS;
+            // the output rows of the eight tile rows this lane stores (-1: beyond the tensor)
+            long long orow[8];
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+                const int r = warp * 32 + itr * 4 + sub_r;
+                const int fol = r % p.fob, q = r / p.fob;
+                const int bl = q % p.bb, tl = q / p.bb;
+                const int to = to0 + tl, b = b0 + bl, fo = fo0 + fol;
+                orow[itr] = (to < p.To && b < p.B && fo < p.Fo) ? ((long long)to * p.B + b) * p.Fo + fo : -1;
+            }
+            const int nchunks = (p.N + 31) / 32;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld32(taddr + c * 32, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
+                        make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                __syncwarp();
+                const int n = c * 32 + sub_n;
+                if (n < p.N) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        if (orow[itr] < 0) continue;
+                        const int rr = itr * 4 + sub_r;
+                        const float4 v = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
+                        const int m = (int)orow[itr];
+                        float4 o;
+                        o.x = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.x, m, n + 0, p.ldc, 0.f);
+                        o.y = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.y, m, n + 1, p.ldc, 0.f);
+                        o.z = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.z, m, n + 2, p.ldc, 0.f);
+                        o.w = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.w, m, n + 3, p.ldc, 0.f);
+                        *reinterpret_cast<float4 *>(p.y + (size_t)orow[itr] * p.ldc + n) = o;
+                    }
+                }
+                __syncwarp();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, NACC * ACC_COLS);
+}
+
+// pad columns N .. ldc of the output (GEMM width > filter count: the first two layers): exact zeros, as conv.cu's GEMM
+// writes them (zero kernel columns and bias)
+__global__ void zero_pad_columns_kernel(float *y, size_t rows, int n0, int ldc)
+{
+    const int w = ldc - n0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * (size_t)w; i += (size_t)gridDim.x * blockDim.x)
+        y[(i / w) * ldc + n0 + i % w] = 0.f;
+}
+
+template <int NP>
+static int launch(const CUtensorMap &mx, const CUtensorMap &mw, const Params &p, cudaStream_t stream)
+{
+    using C_ = Cfg<NP>;
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
+        int dev = 0;
+        CTCASR_CUDA_CHECK(cudaGetDevice(&dev));
+        CTCASR_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+        attr_set = true;
+    }
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    ProfScope prof(PROF_GEMM_TC, stream);
+    conv_fwd_kernel<NP><<<grid, NTHREADS, C_::SMEM, stream>>>(mx, mw, p);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+}  // namespace convtc
+
+// Which layers take the implicit kernel: a bf16 compute mode, whole 32-channel chunks, a GEMM width the accumulator and
+// the two B boxes hold, an activation layout whose rows are 16-B aligned for the TMA unit.  CTCASR_CONV_IMPLICIT=0 keeps
+// the patch-matrix path (conv.cu) for comparisons.
+bool conv_tc_eligible(int compute, int T, int B, int F, int C, int kt, int kf, int st, int sf, int N)
+{
+    static const bool enabled = !(getenv("CTCASR_CONV_IMPLICIT") && atoi(getenv("CTCASR_CONV_IMPLICIT")) == 0);
+    if (!enabled) return false;
+    if (compute != CTCASR_COMPUTE_BF16X3 && compute != CTCASR_COMPUTE_BF16) return false;
+    if (C < 32 || C % 32) return false;
+    if (N < 16 || N > 128 || N % 16) return false;
+    if (st < 1 || st > 8 || sf < 1 || sf > 8) return false;                     // TMA traversal strides
+    if (kt > 64 || kf > 64) return false;
+    return (double)T * B * F * kt * kf * C * N / (st * sf) >= 4.0e6;
+}
+
+// y [To, B, Fo, ldc] = dropout(act(conv(x, w) + bias)); x [T, B, F, x_pitch] fp32 (C real channels), w [Kp, ldw] fp32 with
+// N_real = the GEMM columns actually computed.  Must be called inside an open split scope (gemm.cuh).
+int conv_tc_fwd(const float *x, int x_pitch, const float *w, int ldw, const float *bias, float *y, int ldc,
+                int T, int B, int F, int C, int kt, int kf, int st, int sf, int To, int Fo, int pt, int pf, int N_real,
+                int np, int act, float cutoff, float drop_rate, uint32_t seed, cudaStream_t stream)
+{
+    using namespace convtc;
+    const int K = kt * kf * C, Kp = (K + 7) / 8 * 8;
+    // operand pieces: the input with its pad channels dropped ([T*B*F rows][C]), the kernel as the dense layers split theirs
+    const __nv_bfloat16 *xs = nullptr, *ws = nullptr;
+    int ldx = 0, ldws = 0;
+    size_t xpiece = 0, wpiece = 0;
+    if (int rc = gemm_tc_pieces(x, T * B * F, C, x_pitch, np, stream, &xs, &ldx, &xpiece)) return rc;
+    if (int rc = gemm_tc_pieces(w, Kp, ldw, ldw, np, stream, &ws, &ldws, &wpiece)) return rc;
+
+    Params p{};
+    p.To = To; p.B = B; p.Fo = Fo; p.N = (N_real + 15) / 16 * 16; p.ldc = ldc;
+    // 128 tile rows = tb x bb x fob (powers of two): the split that wastes the fewest rows on partial boxes
+    double best = 1e30;
+    for (int fob = 1; fob <= 128; fob *= 2)
+        for (int bb = 1; fob * bb <= 128; bb *= 2) {
+            const int tb = 128 / (fob * bb);
+            if (fob * sf > 256 || tb * st > 256) continue;                      // TMA box extents
+            const double waste = (double)((Fo + fob - 1) / fob * fob) / Fo * ((B + bb - 1) / bb * bb) / B * ((To + tb - 1) / tb * tb) / To;
+            if (waste < best - 1e-9) { best = waste; p.fob = fob; p.bb = bb; p.tb = tb; }
+        }
+    p.fo_groups = (Fo + p.fob - 1) / p.fob; p.b_groups = (B + p.bb - 1) / p.bb; p.to_groups = (To + p.tb - 1) / p.tb;
+    p.num_tiles = p.fo_groups * p.b_groups * p.to_groups;
+    p.kt = kt; p.kf = kf; p.cchunks = C / 32; p.st = st; p.sf = sf; p.pt = pt; p.pf = pf;
+    p.nbx = (p.N + 63) / 64;
+    p.y = y;
+    p.epi.mode = EPI_BIAS_ACT; p.epi.bias = bias; p.epi.act = act; p.epi.cutoff = cutoff; p.epi.drop_rate = drop_rate; p.epi.seed = seed;
+
+    CUtensorMap mx, mw;
+    {   // input pieces [np][T][B][F][ldx]: box {32 c, fob (stride sf), bb, tb (stride st), 1}
+        const unsigned long long dims[5] = {(unsigned long long)C, (unsigned long long)F, (unsigned long long)B, (unsigned long long)T, (unsigned long long)np};
+        const unsigned long long strides[4] = {(unsigned long long)ldx * 2, (unsigned long long)F * ldx * 2, (unsigned long long)B * F * ldx * 2, (unsigned long long)xpiece * 2};
+        const unsigned box[5] = {32u, (unsigned)(p.fob * sf), (unsigned)p.bb, (unsigned)(p.tb * st), 1u};
+        const unsigned estr[5] = {1u, (unsigned)sf, 1u, (unsigned)st, 1u};
+        if (int rc = tma_encode_bf16(&mx, xs, 5, dims, strides, box, estr, 64)) return rc;
+    }
+    {   // kernel pieces [np][Kp][ldws]: MN-major boxes {64 filters, 32 k-rows, 1}
+        const unsigned long long dims[3] = {(unsigned long long)ldw, (unsigned long long)Kp, (unsigned long long)np};
+        const unsigned long long strides[2] = {(unsigned long long)ldws * 2, (unsigned long long)wpiece * 2};
+        const unsigned box[3] = {64u, 32u, 1u};
+        const unsigned estr[3] = {1u, 1u, 1u};
+        if (int rc = tma_encode_bf16(&mw, ws, 3, dims, strides, box, estr, 128)) return rc;
+    }
+    int rc;
+    if (np == 3) rc = launch<3>(mx, mw, p, stream);
+    else if (np == 2) rc = launch<2>(mx, mw, p, stream);
+    else rc = launch<1>(mx, mw, p, stream);
+    if (rc != CTCASR_OK) return rc;
+    if (p.N < ldc) {
+        const size_t rows = (size_t)To * B * Fo;
+        zero_pad_columns_kernel<<<148 * 4, 256, 0, stream>>>(y, rows, p.N, ldc);
+        CTCASR_LAUNCH_CHECK();
+    }
+    return CTCASR_OK;
+}
+
+}  // namespace ctcasr

@@ -49,6 +49,14 @@ void split_scope_end();
 // CALLER produces in that form, registered under `key` (the address a GEMM will name as its fp32 operand with pitch
 // ld; the fp32 matrix itself need not exist).  The caller fills *pieces before the GEMM runs (stream order).
 int split_reserve(const float *key, int rows, int cols, int ld, int np, __nv_bfloat16 **pieces);
+// bf16 pieces [np][rows][*ldo] of the fp32 matrix x [rows][cols] (pitch ld) in the scratch arena: from the split cache of
+// the open scope, or split now (and cached).  For kernels outside gemm_tc.cu that read split operands (conv_tc.cu).
+int gemm_tc_pieces(const float *x, int rows, int cols, int ld, int np, cudaStream_t stream,
+                   const __nv_bfloat16 **out, int *ldo, size_t *piece);
+// cuTensorMapEncodeTiled for a bf16 tensor of `rank` <= 5 dimensions (dims / box / element strides innermost first,
+// strides in bytes for dimensions 1 .. rank-1); swizzle_bytes 64 or 128; out-of-range elements read as zero.
+int tma_encode_bf16(void *map, const void *base, int rank, const unsigned long long *dims, const unsigned long long *strides,
+                    const unsigned *box, const unsigned *estr, int swizzle_bytes);
 struct SplitScope {
     bool open = false;
     ~SplitScope() { if (open) split_scope_end(); }
@@ -58,6 +66,12 @@ struct SplitScope {
 void *scratch_free(size_t bytes);
 // dispatch on `compute`: TF32 -> tcgen05 when eligible, otherwise the SIMT kernel
 int gemm(const GemmArgs &g, int compute, cudaStream_t stream);
+
+// conv_tc.cu: implicit-GEMM forward pass of a conv layer (no patch matrix); inside an open split scope
+bool conv_tc_eligible(int compute, int T, int B, int F, int C, int kt, int kf, int st, int sf, int N);
+int conv_tc_fwd(const float *x, int x_pitch, const float *w, int ldw, const float *bias, float *y, int ldc,
+                int T, int B, int F, int C, int kt, int kf, int st, int sf, int To, int Fo, int pt, int pf, int N_real,
+                int np, int act, float cutoff, float drop_rate, uint32_t seed, cudaStream_t stream);
 
 // pointwise.cu
 int colsum(const float *x, int M, int N, int ld, float *out, cudaStream_t stream);

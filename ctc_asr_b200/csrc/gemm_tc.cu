@@ -819,6 +819,32 @@ int split_scope_begin(int compute, const size_t *elems, int n)
 }
 void split_scope_end() { tc::ctx().scope = false; tc::ctx().nsplit = 0; tc::ctx().cursor = 0; }
 
+int gemm_tc_pieces(const float *x, int rows, int cols, int ld, int np, cudaStream_t stream,
+                   const __nv_bfloat16 **out, int *ldo, size_t *piece)
+{
+    if (!tc::ctx().scope) return fail(CTCASR_ERR_INVALID, "gemm_tc_pieces: needs an open split scope");
+    if (np == 1) return tc::acquire_split<1>(x, rows, cols, ld, stream, out, ldo, piece);
+    if (np == 2) return tc::acquire_split<2>(x, rows, cols, ld, stream, out, ldo, piece);
+    if (np == 3) return tc::acquire_split<3>(x, rows, cols, ld, stream, out, ldo, piece);
+    return fail(CTCASR_ERR_INVALID, "gemm_tc_pieces: %d pieces", np);
+}
+
+int tma_encode_bf16(void *map, const void *base, int rank, const unsigned long long *dims, const unsigned long long *strides,
+                    const unsigned *box, const unsigned *estr, int swizzle_bytes)
+{
+    tc::EncodeTiledFn fn = tc::get_encode_fn();
+    if (!fn) return fail(CTCASR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i];
+    CUresult r = fn(reinterpret_cast<CUtensorMap *>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), d, st, b, e,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CTCASR_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r);
+    return CTCASR_OK;
+}
+
 int split_reserve(const float *key, int rows, int cols, int ld, int np, __nv_bfloat16 **pieces)
 {
     using namespace tc;

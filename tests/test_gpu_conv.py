@@ -31,6 +31,8 @@ def _pad_kernel(w, N):
     (21, 3, 40, 32, 64, 32, 11, 21, 1, 2),      # second layer: 32 real channels in a 64-float pitch
     (20, 2, 20, 32, 64, 96, 11, 21, 1, 2),      # third layer: 96 filters = its own pitch
     (13, 2, 9, 3, 5, 4, 3, 5, 2, 3),            # odd everything: K = 45 -> Kp = 48, partial tiles
+    (19, 5, 13, 32, 32, 64, 5, 7, 2, 3),        # implicit-GEMM path (C = 32) with strides in time and frequency, partial boxes
+    (16, 3, 11, 64, 64, 128, 3, 5, 1, 1),       # two 32-channel chunks per tap, 128 filters (two B boxes)
 ])
 def test_conv2d_layer_vs_oracle(dims, compute):
     T, B, F, C, xp, filt, kt, kf, st, sf = dims
@@ -88,6 +90,31 @@ def test_ds2_whole_path_small(compute):
                       cudnn=False, dense_dropout_rate=0.0, compute=compute)
     model = _whole_path(cfg, B=4, T=61, L=6, ragged=True)
     assert model._saved["T"] == 31
+
+
+def test_implicit_conv_bf16_mode_and_dropout():
+    """compute='bf16' (one product per operand pair) through the implicit-GEMM kernel against the oracle on operands
+    rounded to bfloat16, with the conv dropout mask in its epilogue (index over the padded pitch)."""
+    T, B, F, C, xp, filt, kt, kf, st, sf = 24, 4, 16, 32, 64, 32, 11, 21, 1, 2
+    N = 64
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((T, B, F, C)).astype(np.float32)
+    w = (rng.standard_normal((kt, kf, C, filt)) * (1.5 / np.sqrt(kt * kf * C))).astype(np.float32)
+    b = (rng.standard_normal(filt) * 0.1).astype(np.float32)
+    xpad = np.zeros((T, B, F, xp), np.float32); xpad[..., :C] = x
+    bp = np.zeros(N, np.float32); bp[:filt] = b
+    To, Fo = same_out(T, kt, st)[0], same_out(F, kf, sf)[0]
+    y_d = torch.full((To * B * Fo, N), float("nan"), device="cuda")
+    ops.conv2d_fwd(dev(xpad), xp, dev(_pad_kernel(w, N)), dev(bp), y_d, T, B, F, C, kt, kf, st, sf, act=1, cutoff=1.0,
+                   drop_rate=0.2, seed=99, compute=_lib.COMPUTE_ID["bf16"])
+    r = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float64).numpy()
+    want = ref.conv2d_fwd(r(x), r(w), b.astype(np.float64), (st, sf), cutoff=1.0)
+    want = ref.dropout(want, 0.2, 99, pitch=N)
+    y = y_d.cpu().numpy().reshape(To, B, Fo, N)
+    away = np.abs(np.abs(ref.conv2d_fwd(r(x), r(w), b.astype(np.float64), (st, sf), cutoff=1e9)) - 0.5) < 0.4999   # off both kinks
+    assert np.abs(y[..., :filt] - want)[away].max() < 1e-4
+    assert np.array_equal((y[..., :filt] == 0)[away], (want == 0)[away])
+    assert (y[..., filt:] == 0).all()
 
 
 def test_ds2_whole_path_with_conv_and_rnn_dropout():

@@ -1,0 +1,3 @@
+#!/bin/bash
+out=gpurun_out
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/r2c26_ncu_launches_ds2_step.csv python bench.py --model ds2 --steps 1 --warmup 3 --no-cpu-baseline > $out/r2c26_ncu_bench.log 2>&1; tail -1 $out/r2c26_ncu_launches_ds2_step.csv | cut -c1-100
