@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace ctcasr {
 namespace conv {
@@ -292,14 +293,26 @@ extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, co
     CTCASR_REQUIRE(rows <= 0x7fffffff, "conv2d_bwd: %zu output positions", rows);
     const size_t need = align_up(rows * g.Kp * sizeof(float), 256);
     if (!ws || ws_bytes < need) return fail(CTCASR_ERR_WORKSPACE, "conv2d_bwd: workspace %zu < %zu", ws_bytes, need);
-    if (int rcs = gemm_scratch_check(compute, 1, g.Kp, N, (int)rows)) return rcs;
+    static const bool implicit_wgrad = !(getenv("CTCASR_CONV_IMPLICIT_WGRAD") && atoi(getenv("CTCASR_CONV_IMPLICIT_WGRAD")) == 0);
+    const bool use_implicit = implicit_wgrad && conv_tc_eligible(compute, T, B, F, C, kt, kf, st, sf, N) && ((uintptr_t)x & 15) == 0 &&
+                              x_pitch % 4 == 0 && g.K == g.Kp;
+    if (!use_implicit) if (int rcs = gemm_scratch_check(compute, 1, g.Kp, N, (int)rows)) return rcs;
     if (dx) if (int rcs = gemm_scratch_check(compute, 1, (int)rows, g.Kp, N)) return rcs;
     float *col = reinterpret_cast<float *>(ws);
     int rc = mask_inplace(dy, y, rows, N, act, cutoff, drop_rate, seed, stream);       // dy -> dz
     if (rc != CTCASR_OK) return rc;
     rc = colsum(dy, (int)rows, N, N, db, stream);
     if (rc != CTCASR_OK) return rc;
-    {   // dW[Kp,N] = col^T dz   (rows K..Kp of col^T are zero -> the pad rows of dW are zero)
+    if (use_implicit) {
+        // implicit GEMM (conv_tc.cu): dW = col^T dz with the patches gathered by the TMA unit
+        const size_t elems[2] = {(size_t)T * B * F * C, rows * (size_t)N};
+        SplitScope scope;
+        if ((rc = split_scope_begin(compute, elems, 2)) != CTCASR_OK) return rc;
+        scope.open = true;
+        rc = conv_tc_wgrad(x, x_pitch, dy, N, dw, N, T, B, F, C, kt, kf, st, sf, g.To, g.Fo, g.pt, g.pf,
+                           compute == CTCASR_COMPUTE_BF16 ? 1 : 2, stream);
+        if (rc != CTCASR_OK) return rc;
+    } else {   // dW[Kp,N] = col^T dz   (rows K..Kp of col^T are zero -> the pad rows of dW are zero)
         GemmArgs a;
         a.A[0] = col; a.B[0] = dy; a.C[0] = dw; a.ta = 1; a.M = g.Kp; a.N = N; a.K = (int)rows; a.lda = g.Kp; a.ldb = N; a.ldc = N;
         const int np = conv::gemm_pieces(a, compute);

@@ -233,6 +233,215 @@ static int launch(const CUtensorMap &mx, const CUtensorMap &mw, const Params &p,
     return CTCASR_OK;
 }
 
+
+// ================================ weight gradient: dW[K, N] = col^T dz without col ================================
+// GEMM rows = patch elements k = (tap * C + c), columns = filters, contraction over the output positions.  An M tile is
+// four consecutive 32-row (tap, channel-chunk) units; a k-block is 32 output positions (fob x bb x tb, fo fastest):
+//   A  four boxes {32 channels, the 32 positions} of the input pieces, one per unit, each at its tap's offset — MN-major
+//      A operand (a row of shared memory = one position, 64 B = 32 consecutive k), SWIZZLE_64B;
+//   B  dz pieces viewed as [piece][To][B][Fo][N]: boxes {64 filters, fob, bb, tb} = the same 32 positions in the same
+//      order, MN-major, SWIZZLE_128B.
+// Few output tiles (58 for an 11 x 21 x 32 kernel) against 10^4 k-blocks: the positions are split into slices whose raw
+// partial tiles splitk_reduce adds in slice order (deterministic).
+constexpr int WG_BKP = 32;                          // positions per k-block
+constexpr int WG_A_BOX = WG_BKP * 64;               // 2 KB: 32 positions x 32 channels
+template <int NP> struct WCfg {
+    static constexpr int NPROD = NP == 3 ? 6 : (NP == 2 ? 3 : 1);
+    static constexpr int STAGE = NP * (4 * WG_A_BOX + 2 * B_BOX);               // 16 KB per piece
+    static constexpr int NSTAGE = NP == 3 ? 4 : (NP == 2 ? 6 : 10);
+    static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + STG_BYTES;
+};
+struct WParams {
+    int N, K;                           // GEMM columns (multiple of 16, <= 128), rows (= kt*kf*C)
+    int fob, bb, tb, fo_groups, b_groups, to_groups, ngroups;
+    int kf, cchunks, nunits;            // nunits = kt*kf*cchunks 32-row units
+    int st, sf, pt, pf;
+    int nbx, mtiles, splits, groups_per_split;
+    float *out;                         // dW [K, ldo] (splits == 1) or the partial tiles [splits][K][ldo]
+    int ldo;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ, const WParams p)
+{
+    using C_ = WCfg<NP>;
+    constexpr int NSTAGE = C_::NSTAGE, STAGE = C_::STAGE;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + NSTAGE * STAGE;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + NACC + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 2 * NACC);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+    float *stg = reinterpret_cast<float *>(smem_raw + (bar_base + 256 - ptx::smem_u32(smem_raw))) + (threadIdx.x >> 5 & 3) * 32 * STG_LD;
+    auto a_addr = [&](int stage, int pc) { return smem_base + stage * STAGE + pc * 4 * WG_A_BOX; };
+    auto b_addr = [&](int stage, int pc) { return smem_base + stage * STAGE + NP * 4 * WG_A_BOX + pc * 2 * B_BOX; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwork = p.mtiles * p.splits;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < NACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 4); }
+        ptx::mbar_fence_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapX); ptx::tma_prefetch_desc(&mapZ); }
+    if (warp == 5) ptx::tmem_alloc(tmem_slot, NACC * ACC_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t bytes = (uint32_t)NP * (4 * WG_A_BOX + p.nbx * B_BOX);
+            for (int u = blockIdx.x; u < nwork; u += gridDim.x) {
+                const int slice = u / p.mtiles, mt = u - slice * p.mtiles;
+                // the four units of this tile: channel offset and tap offsets (a unit beyond the kernel reads far out of range: zeros)
+                int c0[4], dt[4], df[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int un = mt * 4 + j;
+                    const int tap = un / p.cchunks;
+                    c0[j] = (un - tap * p.cchunks) * 32;
+                    const int it = tap / p.kf;
+                    dt[j] = un < p.nunits ? it - p.pt : (1 << 24);
+                    df[j] = (tap - it * p.kf) - p.pf;
+                }
+                const int g0 = slice * p.groups_per_split, g1 = min(p.ngroups, g0 + p.groups_per_split);
+                for (int g = g0; g < g1; ++g) {
+                    const int fg = g % p.fo_groups, r = g / p.fo_groups;
+                    const int bg = r % p.b_groups, tg = r / p.b_groups;
+                    const int to0 = tg * p.tb, b0 = bg * p.bb, fo0 = fg * p.fob;
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                    ptx::mbar_expect_tx(full_bar(stage), bytes);
+#pragma unroll
+                    for (int pc = 0; pc < NP; ++pc) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            ptx::tma_load_5d(a_addr(stage, pc) + j * WG_A_BOX, &mapX, c0[j], fo0 * p.sf + df[j], b0, to0 * p.st + dt[j], pc, full_bar(stage));
+                        for (int j = 0; j < p.nbx; ++j)
+                            ptx::tma_load_5d(b_addr(stage, pc) + j * B_BOX, &mapZ, j * 64, fo0, b0, to0, pc, full_bar(stage));
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr int PA[6] = {0, 0, 1, 0, 1, 2};
+            constexpr int PB[6] = {0, 1, 0, 2, 1, 0};
+            const uint32_t idesc = ptx::make_idesc_bf16(BM, p.N, 1, 1);        // both operands MN-major
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < nwork; u += gridDim.x) {
+                const int slice = u / p.mtiles;
+                const int g0 = slice * p.groups_per_split, g1 = min(p.ngroups, g0 + p.groups_per_split);
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+                for (int g = g0; g < g1; ++g) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int q = 0; q < C_::NPROD; ++q) {
+                        // A: MN-major, SWIZZLE_64B: 32-element atoms WG_A_BOX apart along M, 8-position groups 512 B apart
+                        const uint64_t adesc = ptx::make_smem_desc(a_addr(stage, PA[q]), WG_A_BOX, 512, 4);
+                        const uint64_t bdesc = ptx::make_smem_desc(b_addr(stage, PB[q]), B_BOX, 1024, 2);
+#pragma unroll
+                        for (int j = 0; j < WG_BKP / 16; ++j)       // 16 positions per MMA: 16 rows of 64 B (A) / 128 B (B)
+                            ptx::mma_bf16(tmem_d, adesc + (uint64_t)(64 * j), bdesc + (uint64_t)(128 * j), idesc, ((g - g0) | q | j) != 0);
+                    }
+                    ptx::mma_commit(empty_bar(stage));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit(tfull_bar(acc));
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        int acc = 0; uint32_t acc_phase = 0;
+        const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
+        for (int u = blockIdx.x; u < nwork; u += gridDim.x) {
+            const int slice = u / p.mtiles, mt = u - slice * p.mtiles;
+            float *out = p.out + (size_t)slice * p.K * p.ldo;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * ACC_COLS;
+            const int m0 = mt * BM + warp * 32;
+            const int nchunks = (p.N + 31) / 32;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld32(taddr + c * 32, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
+                        make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                __syncwarp();
+                const int n = c * 32 + sub_n;
+                if (n < p.N) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int rr = itr * 4 + sub_r, m = m0 + rr;
+                        if (m < p.K)
+                            *reinterpret_cast<float4 *>(out + (size_t)m * p.ldo + n) = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
+                    }
+                }
+                __syncwarp();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, NACC * ACC_COLS);
+}
+
+template <int NP>
+static int launch_wgrad(const CUtensorMap &mx, const CUtensorMap &mz, const WParams &p, cudaStream_t stream)
+{
+    using C_ = WCfg<NP>;
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
+        int dev = 0;
+        CTCASR_CUDA_CHECK(cudaGetDevice(&dev));
+        CTCASR_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+        attr_set = true;
+    }
+    const int nwork = p.mtiles * p.splits;
+    const int grid = nwork < num_sms ? nwork : num_sms;
+    ProfScope prof(PROF_GEMM_TC, stream);
+    conv_wgrad_kernel<NP><<<grid, NTHREADS, C_::SMEM, stream>>>(mx, mz, p);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+// the 128 = tb x bb x fob (fwd) / 32 (wgrad) rows of a box: powers of two wasting the fewest rows on partial boxes
+static void pick_boxes(int rows, int To, int B, int Fo, int st, int sf, int *fob_, int *bb_, int *tb_)
+{
+    double best = 1e30;
+    for (int fob = 1; fob <= rows; fob *= 2)
+        for (int bb = 1; fob * bb <= rows; bb *= 2) {
+            const int tb = rows / (fob * bb);
+            if (fob * sf > 256 || tb * st > 256) continue;                      // TMA box extents
+            const double waste = (double)((Fo + fob - 1) / fob * fob) / Fo * ((B + bb - 1) / bb * bb) / B * ((To + tb - 1) / tb * tb) / To;
+            if (waste < best - 1e-9) { best = waste; *fob_ = fob; *bb_ = bb; *tb_ = tb; }
+        }
+}
+
 }  // namespace convtc
 
 // Which layers take the implicit kernel: a bf16 compute mode, whole 32-channel chunks, a GEMM width the accumulator and
@@ -267,15 +476,7 @@ int conv_tc_fwd(const float *x, int x_pitch, const float *w, int ldw, const floa
 
     Params p{};
     p.To = To; p.B = B; p.Fo = Fo; p.N = (N_real + 15) / 16 * 16; p.ldc = ldc;
-    // 128 tile rows = tb x bb x fob (powers of two): the split that wastes the fewest rows on partial boxes
-    double best = 1e30;
-    for (int fob = 1; fob <= 128; fob *= 2)
-        for (int bb = 1; fob * bb <= 128; bb *= 2) {
-            const int tb = 128 / (fob * bb);
-            if (fob * sf > 256 || tb * st > 256) continue;                      // TMA box extents
-            const double waste = (double)((Fo + fob - 1) / fob * fob) / Fo * ((B + bb - 1) / bb * bb) / B * ((To + tb - 1) / tb * tb) / To;
-            if (waste < best - 1e-9) { best = waste; p.fob = fob; p.bb = bb; p.tb = tb; }
-        }
+    pick_boxes(128, To, B, Fo, st, sf, &p.fob, &p.bb, &p.tb);       // tile rows = tb x bb x fob
     p.fo_groups = (Fo + p.fob - 1) / p.fob; p.b_groups = (B + p.bb - 1) / p.bb; p.to_groups = (To + p.tb - 1) / p.tb;
     p.num_tiles = p.fo_groups * p.b_groups * p.to_groups;
     p.kt = kt; p.kf = kf; p.cchunks = C / 32; p.st = st; p.sf = sf; p.pt = pt; p.pf = pf;
@@ -307,6 +508,70 @@ int conv_tc_fwd(const float *x, int x_pitch, const float *w, int ldw, const floa
         const size_t rows = (size_t)To * B * Fo;
         zero_pad_columns_kernel<<<148 * 4, 256, 0, stream>>>(y, rows, p.N, ldc);
         CTCASR_LAUNCH_CHECK();
+    }
+    return CTCASR_OK;
+}
+
+// dW [K = kt*kf*C, ldw] = col^T dz for dz [To*B*Fo, ldz] fp32 (the layer's masked output gradient); inside an open split scope
+int conv_tc_wgrad(const float *x, int x_pitch, const float *dz, int ldz, float *dw, int ldw,
+                  int T, int B, int F, int C, int kt, int kf, int st, int sf, int To, int Fo, int pt, int pf,
+                  int np, cudaStream_t stream)
+{
+    using namespace convtc;
+    const int K = kt * kf * C;
+    const size_t rows = (size_t)To * B * Fo;
+    const __nv_bfloat16 *xs = nullptr, *zs = nullptr;
+    int ldx = 0, ldzs = 0;
+    size_t xpiece = 0, zpiece = 0;
+    if (int rc = gemm_tc_pieces(x, T * B * F, C, x_pitch, np, stream, &xs, &ldx, &xpiece)) return rc;
+    if (int rc = gemm_tc_pieces(dz, (int)rows, ldz, ldz, np, stream, &zs, &ldzs, &zpiece)) return rc;
+
+    WParams p{};
+    p.N = (ldz + 15) / 16 * 16; p.K = K; p.ldo = ldw;
+    pick_boxes(WG_BKP, To, B, Fo, st, sf, &p.fob, &p.bb, &p.tb);
+    p.fo_groups = (Fo + p.fob - 1) / p.fob; p.b_groups = (B + p.bb - 1) / p.bb; p.to_groups = (To + p.tb - 1) / p.tb;
+    p.ngroups = p.fo_groups * p.b_groups * p.to_groups;
+    p.kf = kf; p.cchunks = C / 32; p.nunits = kt * kf * p.cchunks;
+    p.st = st; p.sf = sf; p.pt = pt; p.pf = pf;
+    p.nbx = (p.N + 63) / 64;
+    p.mtiles = (p.nunits + 3) / 4;
+    // ~2 waves of (slice, tile) units, at least 64 position groups per slice; the partial tiles go behind the cached splits
+    int S = (2 * 148) / p.mtiles;
+    if (S > p.ngroups / 64) S = p.ngroups / 64;
+    float *part = nullptr;
+    if (S > 1) {
+        const int per = (p.ngroups + S - 1) / S;
+        S = (p.ngroups + per - 1) / per;
+        part = S > 1 ? reinterpret_cast<float *>(scratch_free((size_t)S * K * ldw * sizeof(float))) : nullptr;
+        if (part) { p.splits = S; p.groups_per_split = per; }
+    }
+    if (!part) { p.splits = 1; p.groups_per_split = p.ngroups; }
+    p.out = part ? part : dw;
+
+    CUtensorMap mx, mz;
+    {
+        const unsigned long long dims[5] = {(unsigned long long)C, (unsigned long long)F, (unsigned long long)B, (unsigned long long)T, (unsigned long long)np};
+        const unsigned long long strides[4] = {(unsigned long long)ldx * 2, (unsigned long long)F * ldx * 2, (unsigned long long)B * F * ldx * 2, (unsigned long long)xpiece * 2};
+        const unsigned box[5] = {32u, (unsigned)(p.fob * sf), (unsigned)p.bb, (unsigned)(p.tb * st), 1u};
+        const unsigned estr[5] = {1u, (unsigned)sf, 1u, (unsigned)st, 1u};
+        if (int rc = tma_encode_bf16(&mx, xs, 5, dims, strides, box, estr, 64)) return rc;
+    }
+    {   // dz pieces [np][To][B][Fo][ldzs]: boxes {64 filters, fob, bb, tb, 1}
+        const unsigned long long dims[5] = {(unsigned long long)ldz, (unsigned long long)Fo, (unsigned long long)B, (unsigned long long)To, (unsigned long long)np};
+        const unsigned long long strides[4] = {(unsigned long long)ldzs * 2, (unsigned long long)Fo * ldzs * 2, (unsigned long long)B * Fo * ldzs * 2, (unsigned long long)zpiece * 2};
+        const unsigned box[5] = {64u, (unsigned)p.fob, (unsigned)p.bb, (unsigned)p.tb, 1u};
+        const unsigned estr[5] = {1u, 1u, 1u, 1u, 1u};
+        if (int rc = tma_encode_bf16(&mz, zs, 5, dims, strides, box, estr, 128)) return rc;
+    }
+    int rc;
+    if (np == 3) rc = launch_wgrad<3>(mx, mz, p, stream);
+    else if (np == 2) rc = launch_wgrad<2>(mx, mz, p, stream);
+    else rc = launch_wgrad<1>(mx, mz, p, stream);
+    if (rc != CTCASR_OK) return rc;
+    if (p.splits > 1) {
+        GemmArgs g;
+        g.M = K; g.N = ldw; g.C[0] = dw; g.ldc = ldw;
+        return splitk_reduce(g, p.splits, part, stream);
     }
     return CTCASR_OK;
 }

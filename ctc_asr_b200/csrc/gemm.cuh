@@ -72,6 +72,9 @@ bool conv_tc_eligible(int compute, int T, int B, int F, int C, int kt, int kf, i
 int conv_tc_fwd(const float *x, int x_pitch, const float *w, int ldw, const float *bias, float *y, int ldc,
                 int T, int B, int F, int C, int kt, int kf, int st, int sf, int To, int Fo, int pt, int pf, int N_real,
                 int np, int act, float cutoff, float drop_rate, uint32_t seed, cudaStream_t stream);
+int conv_tc_wgrad(const float *x, int x_pitch, const float *dz, int ldz, float *dw, int ldw,
+                  int T, int B, int F, int C, int kt, int kf, int st, int sf, int To, int Fo, int pt, int pf,
+                  int np, cudaStream_t stream);
 
 // pointwise.cu
 int colsum(const float *x, int M, int N, int ld, float *out, cudaStream_t stream);
