@@ -304,14 +304,18 @@ extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, co
     rc = colsum(dy, (int)rows, N, N, db, stream);
     if (rc != CTCASR_OK) return rc;
     if (use_implicit) {
-        // implicit GEMM (conv_tc.cu): dW = col^T dz with the patches gathered by the TMA unit
-        const size_t elems[2] = {(size_t)T * B * F * C, rows * (size_t)N};
+        // implicit GEMMs (conv_tc.cu): dW = col^T dz with the patches gathered by the TMA unit, and dx = conv_transpose(dz, W)
+        // without dcol; dz is split once for both
+        const int np = compute == CTCASR_COMPUTE_BF16 ? 1 : 2;
+        const bool dgrad_implicit = dx && conv_tc_dgrad_eligible(C, kf, st, sf, x_pitch);
+        const size_t elems[3] = {(size_t)T * B * F * C, rows * (size_t)N, (size_t)g.Kp * N};
         SplitScope scope;
-        if ((rc = split_scope_begin(compute, elems, 2)) != CTCASR_OK) return rc;
+        if ((rc = split_scope_begin(compute, elems, 3)) != CTCASR_OK) return rc;
         scope.open = true;
-        rc = conv_tc_wgrad(x, x_pitch, dy, N, dw, N, T, B, F, C, kt, kf, st, sf, g.To, g.Fo, g.pt, g.pf,
-                           compute == CTCASR_COMPUTE_BF16 ? 1 : 2, stream);
+        rc = conv_tc_wgrad(x, x_pitch, dy, N, dw, N, T, B, F, C, kt, kf, st, sf, g.To, g.Fo, g.pt, g.pf, np, stream);
         if (rc != CTCASR_OK) return rc;
+        if (dgrad_implicit)
+            return conv_tc_dgrad(dy, N, w, N, dx, x_pitch, T, B, F, C, kt, kf, st, sf, g.To, g.Fo, g.pt, g.pf, np, stream);
     } else {   // dW[Kp,N] = col^T dz   (rows K..Kp of col^T are zero -> the pad rows of dW are zero)
         GemmArgs a;
         a.A[0] = col; a.B[0] = dy; a.C[0] = dw; a.ta = 1; a.M = g.Kp; a.N = N; a.K = (int)rows; a.lda = g.Kp; a.ldb = N; a.ldc = N;

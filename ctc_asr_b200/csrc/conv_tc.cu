@@ -429,6 +429,203 @@ static int launch_wgrad(const CUtensorMap &mx, const CUtensorMap &mz, const WPar
     return CTCASR_OK;
 }
 
+// ================================ input gradient: dx = conv_transpose(dz, W) without dcol ================================
+// dx[t, b, f, c] = sum over taps (it, jf) and filters n of dz[t + pt - it, b, (f + pf - jf) / sf, n] W[(it*kf + jf)*C + c, n]
+// (time stride 1), the frequency term only when sf divides f + pf - jf.  Input positions are processed per residue class
+// rho = f mod sf: f = rho + sf*i sees the taps jf = j0 + sf*j' (j0 = (rho + pf) mod sf) at fo = i + q0 - j', consecutive in i.
+// GEMM rows = 128 input positions of one class (ib x bb x tb, i fastest), columns = the C input channels, one k-block =
+// one tap x 32 filters:
+//   A  dz pieces [piece][To][B][Fo][N]: box {32 filters, ib, bb, tb} at (n0, i0 + q0 - j', b0, t0 + pt - it): K-major, SWIZZLE_64B;
+//      positions whose (to, fo) fall outside the layer's output read zeros (TMA out-of-range fill)
+//   B  kernel pieces [piece][Kp][N]: box {32 filters, the tap's C rows}: K-major, SWIZZLE_64B.
+struct DParams {
+    int T, B, F, C, ldx;                // dx [T, B, F, ldx], C real channels (multiple of 32, <= 128)
+    int ib, bb, tb, i_groups, b_groups, t_groups, num_tiles;   // tiles: class x t x b x i
+    int kt, kf, sf, pt, pf, nchunks;    // nchunks = 32-filter chunks of the GEMM's contraction per tap
+    float *dx;
+};
+template <int NP> struct DCfg {
+    static constexpr int NPROD = NP == 3 ? 6 : (NP == 2 ? 3 : 1);
+    static constexpr int STAGE = NP * (A_PIECE + A_PIECE);                      // A 8 KB + B up to 128 rows x 64 B
+    static constexpr int NSTAGE = NP == 3 ? 4 : (NP == 2 ? 6 : 10);
+    static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + STG_BYTES;
+};
+__device__ __forceinline__ void dgrad_tile(const DParams &p, int u, int &rho, int &t0, int &b0, int &i0, int &j0, int &q0, int &nj)
+{
+    const int ig = u % p.i_groups; int r = u / p.i_groups;
+    const int bg = r % p.b_groups; r /= p.b_groups;
+    const int tg = r % p.t_groups; rho = r / p.t_groups;
+    t0 = tg * p.tb; b0 = bg * p.bb; i0 = ig * p.ib;
+    j0 = (rho + p.pf) % p.sf;
+    q0 = (rho + p.pf - j0) / p.sf;
+    nj = j0 < p.kf ? (p.kf - 1 - j0) / p.sf + 1 : 0;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_dgrad_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapW, const DParams p)
+{
+    using C_ = DCfg<NP>;
+    constexpr int NSTAGE = C_::NSTAGE, STAGE = C_::STAGE;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + NSTAGE * STAGE;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + NACC + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 2 * NACC);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+    float *stg = reinterpret_cast<float *>(smem_raw + (bar_base + 256 - ptx::smem_u32(smem_raw))) + (threadIdx.x >> 5 & 3) * 32 * STG_LD;
+    auto a_addr = [&](int stage, int pc) { return smem_base + stage * STAGE + pc * A_PIECE; };
+    auto b_addr = [&](int stage, int pc) { return smem_base + stage * STAGE + NP * A_PIECE + pc * A_PIECE; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < NACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 4); }
+        ptx::mbar_fence_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapZ); ptx::tma_prefetch_desc(&mapW); }
+    if (warp == 5) ptx::tmem_alloc(tmem_slot, NACC * ACC_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t bytes = (uint32_t)NP * (A_PIECE + p.C * 64);
+            for (int u = blockIdx.x; u < p.num_tiles; u += gridDim.x) {
+                int rho, t0, b0, i0, j0, q0, nj;
+                dgrad_tile(p, u, rho, t0, b0, i0, j0, q0, nj);
+                for (int it = 0; it < p.kt; ++it)
+                    for (int jj = 0; jj < nj; ++jj) {
+                        const int jf = j0 + p.sf * jj;
+                        for (int nc = 0; nc < p.nchunks; ++nc) {
+                            ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                            ptx::mbar_expect_tx(full_bar(stage), bytes);
+#pragma unroll
+                            for (int pc = 0; pc < NP; ++pc) {
+                                ptx::tma_load_5d(a_addr(stage, pc), &mapZ, nc * 32, i0 + q0 - jj, b0, t0 + p.pt - it, pc, full_bar(stage));
+                                ptx::tma_load_3d(b_addr(stage, pc), &mapW, nc * 32, (it * p.kf + jf) * p.C, pc, full_bar(stage));
+                            }
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+                    }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr int PA[6] = {0, 0, 1, 0, 1, 2};
+            constexpr int PB[6] = {0, 1, 0, 2, 1, 0};
+            const uint32_t idesc = ptx::make_idesc_bf16(BM, p.C, 0, 0);        // both operands K-major
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < p.num_tiles; u += gridDim.x) {
+                int rho, t0, b0, i0, j0, q0, nj;
+                dgrad_tile(p, u, rho, t0, b0, i0, j0, q0, nj);
+                const int nk = p.kt * nj * p.nchunks;
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+                for (int kb = 0; kb < nk; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int q = 0; q < C_::NPROD; ++q) {
+                        const uint64_t adesc = ptx::make_smem_desc(a_addr(stage, PA[q]), 16, 512, 4);
+                        const uint64_t bdesc = ptx::make_smem_desc(b_addr(stage, PB[q]), 16, 512, 4);
+#pragma unroll
+                        for (int j = 0; j < BK / 16; ++j)
+                            ptx::mma_bf16(tmem_d, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | q | j) != 0);
+                    }
+                    ptx::mma_commit(empty_bar(stage));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit(tfull_bar(acc));
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        int acc = 0; uint32_t acc_phase = 0;
+        const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
+        for (int u = blockIdx.x; u < p.num_tiles; u += gridDim.x) {
+            int rho, t0, b0, i0, j0, q0, nj;
+            dgrad_tile(p, u, rho, t0, b0, i0, j0, q0, nj);
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * ACC_COLS;
+            long long orow[8];
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+                const int r = warp * 32 + itr * 4 + sub_r;
+                const int il = r % p.ib, q = r / p.ib;
+                const int bl = q % p.bb, tl = q / p.bb;
+                const int t = t0 + tl, b = b0 + bl, f = rho + p.sf * (i0 + il);
+                orow[itr] = (t < p.T && b < p.B && f < p.F) ? ((long long)t * p.B + b) * p.F + f : -1;
+            }
+            const int nchunks = (p.ldx + 31) / 32;              // the pad channels get their zeros here
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                const bool real = c * 32 < p.C;
+                if (real) {
+                    uint32_t r[32];
+                    ptx::tmem_ld32(taddr + c * 32, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
+                            make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                }
+                __syncwarp();
+                const int n = c * 32 + sub_n;
+                if (n < p.ldx) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        if (orow[itr] < 0) continue;
+                        const int rr = itr * 4 + sub_r;
+                        const float4 v = (real && nj > 0) ? *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(p.dx + (size_t)orow[itr] * p.ldx + n) = v;
+                    }
+                }
+                __syncwarp();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, NACC * ACC_COLS);
+}
+
+template <int NP>
+static int launch_dgrad(const CUtensorMap &mz, const CUtensorMap &mw, const DParams &p, cudaStream_t stream)
+{
+    using C_ = DCfg<NP>;
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
+        int dev = 0;
+        CTCASR_CUDA_CHECK(cudaGetDevice(&dev));
+        CTCASR_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        CTCASR_CUDA_CHECK(cudaFuncSetAttribute(conv_dgrad_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+        attr_set = true;
+    }
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    ProfScope prof(PROF_GEMM_TC, stream);
+    conv_dgrad_kernel<NP><<<grid, NTHREADS, C_::SMEM, stream>>>(mz, mw, p);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
 // the 128 = tb x bb x fob (fwd) / 32 (wgrad) rows of a box: powers of two wasting the fewest rows on partial boxes
 static void pick_boxes(int rows, int To, int B, int Fo, int st, int sf, int *fob_, int *bb_, int *tb_)
 {
@@ -574,6 +771,54 @@ int conv_tc_wgrad(const float *x, int x_pitch, const float *dz, int ldz, float *
         return splitk_reduce(g, p.splits, part, stream);
     }
     return CTCASR_OK;
+}
+
+// dx [T, B, F, x_pitch] = conv_transpose(dz [To, B, Fo, ldz], w [Kp, ldw]) for time stride 1; inside an open split scope
+bool conv_tc_dgrad_eligible(int C, int kf, int st, int sf, int x_pitch)
+{
+    static const bool enabled = !(getenv("CTCASR_CONV_IMPLICIT_DGRAD") && atoi(getenv("CTCASR_CONV_IMPLICIT_DGRAD")) == 0);
+    return enabled && st == 1 && kf >= sf && C <= 128 && x_pitch % 4 == 0;
+}
+int conv_tc_dgrad(const float *dz, int ldz, const float *w, int ldw, float *dx, int x_pitch,
+                  int T, int B, int F, int C, int kt, int kf, int st, int sf, int To, int Fo, int pt, int pf,
+                  int np, cudaStream_t stream)
+{
+    using namespace convtc;
+    (void)st;
+    const int K = kt * kf * C, Kp = (K + 7) / 8 * 8;
+    const size_t rows = (size_t)To * B * Fo;
+    const __nv_bfloat16 *zs = nullptr, *ws = nullptr;
+    int ldzs = 0, ldws = 0;
+    size_t zpiece = 0, wpiece = 0;
+    if (int rc = gemm_tc_pieces(dz, (int)rows, ldz, ldz, np, stream, &zs, &ldzs, &zpiece)) return rc;
+    if (int rc = gemm_tc_pieces(w, Kp, ldw, ldw, np, stream, &ws, &ldws, &wpiece)) return rc;
+
+    DParams p{};
+    p.T = T; p.B = B; p.F = F; p.C = C; p.ldx = x_pitch; p.dx = dx;
+    const int imax = (F + sf - 1) / sf;                         // positions of a residue class (the longest one)
+    pick_boxes(128, T, B, imax, 1, 1, &p.ib, &p.bb, &p.tb);
+    p.i_groups = (imax + p.ib - 1) / p.ib; p.b_groups = (B + p.bb - 1) / p.bb; p.t_groups = (T + p.tb - 1) / p.tb;
+    p.num_tiles = p.i_groups * p.b_groups * p.t_groups * sf;
+    p.kt = kt; p.kf = kf; p.sf = sf; p.pt = pt; p.pf = pf; p.nchunks = (ldz + 31) / 32;
+
+    CUtensorMap mz, mw;
+    {   // dz pieces [np][To][B][Fo][ldzs]: boxes {32 filters, ib, bb, tb, 1}
+        const unsigned long long dims[5] = {(unsigned long long)ldz, (unsigned long long)Fo, (unsigned long long)B, (unsigned long long)To, (unsigned long long)np};
+        const unsigned long long strides[4] = {(unsigned long long)ldzs * 2, (unsigned long long)Fo * ldzs * 2, (unsigned long long)B * Fo * ldzs * 2, (unsigned long long)zpiece * 2};
+        const unsigned box[5] = {32u, (unsigned)p.ib, (unsigned)p.bb, (unsigned)p.tb, 1u};
+        const unsigned estr[5] = {1u, 1u, 1u, 1u, 1u};
+        if (int rc = tma_encode_bf16(&mz, zs, 5, dims, strides, box, estr, 64)) return rc;
+    }
+    {   // kernel pieces [np][Kp][ldws]: K-major boxes {32 filters, C rows of one tap, 1}
+        const unsigned long long dims[3] = {(unsigned long long)ldw, (unsigned long long)Kp, (unsigned long long)np};
+        const unsigned long long strides[2] = {(unsigned long long)ldws * 2, (unsigned long long)wpiece * 2};
+        const unsigned box[3] = {32u, (unsigned)C, 1u};
+        const unsigned estr[3] = {1u, 1u, 1u};
+        if (int rc = tma_encode_bf16(&mw, ws, 3, dims, strides, box, estr, 64)) return rc;
+    }
+    if (np == 3) return launch_dgrad<3>(mz, mw, p, stream);
+    if (np == 2) return launch_dgrad<2>(mz, mw, p, stream);
+    return launch_dgrad<1>(mz, mw, p, stream);
 }
 
 }  // namespace ctcasr

@@ -75,6 +75,10 @@ int conv_tc_fwd(const float *x, int x_pitch, const float *w, int ldw, const floa
 int conv_tc_wgrad(const float *x, int x_pitch, const float *dz, int ldz, float *dw, int ldw,
                   int T, int B, int F, int C, int kt, int kf, int st, int sf, int To, int Fo, int pt, int pf,
                   int np, cudaStream_t stream);
+bool conv_tc_dgrad_eligible(int C, int kf, int st, int sf, int x_pitch);
+int conv_tc_dgrad(const float *dz, int ldz, const float *w, int ldw, float *dx, int x_pitch,
+                  int T, int B, int F, int C, int kt, int kf, int st, int sf, int To, int Fo, int pt, int pf,
+                  int np, cudaStream_t stream);
 
 // pointwise.cu
 int colsum(const float *x, int M, int N, int ld, float *out, cudaStream_t stream);
