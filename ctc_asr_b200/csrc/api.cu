@@ -114,20 +114,33 @@ extern "C" int ctcasr_dense_bwd(const float *x, const float *w, const float *y, 
     CTCASR_REQUIRE(act == 0 || y, "dense_bwd: activation mask needs the forward output y");
     if (int rcs = gemm_scratch_check(compute, 1, K, N, M)) return rcs;
     if (int rcs = gemm_scratch_check(compute, 1, M, K, N)) return rcs;
-    int rc = mask_inplace(dy, y, (size_t)M, N, act, cutoff, drop_rate, seed, stream);   // dy -> dz
-    if (rc != CTCASR_OK) return rc;
-    rc = colsum(dy, M, N, N, db, stream);
-    if (rc != CTCASR_OK) return rc;
-    {   // dW[K,N] = X^T dz
-        GemmArgs g;
-        g.A[0] = x; g.B[0] = dy; g.C[0] = dw; g.ta = 1; g.M = K; g.N = N; g.K = M; g.lda = K; g.ldb = N; g.ldc = N;
-        rc = gemm(g, compute, stream);
+    GemmArgs gw, gx;    // dW[K,N] = X^T dz;  dX[M,K] = dz W^T
+    gw.A[0] = x; gw.B[0] = dy; gw.C[0] = dw; gw.ta = 1; gw.M = K; gw.N = N; gw.K = M; gw.lda = K; gw.ldb = N; gw.ldc = N;
+    gx.A[0] = dy; gx.B[0] = w; gx.C[0] = dx; gx.tb = 1; gx.M = M; gx.N = K; gx.K = N; gx.lda = N; gx.ldb = N; gx.ldc = K;
+    // Both products on the tcgen05 GEMM in a bf16 mode: one pass makes dz's mask, column sums and bf16 pieces (the fp32 dz
+    // is then not needed); the two GEMMs share those pieces through the split scope.
+    const int np = compute == CTCASR_COMPUTE_BF16 ? 1 : (compute == CTCASR_COMPUTE_BF16X3 ? 2 : 0);
+    const bool fused = np && N <= 16384 && gemm_tc_eligible(gw);       // (independent of dx: so is the bias gradient's summation order)
+    const bool fp32_dz = fused && dx && !gemm_tc_eligible(gx);         // the input-gradient product reads dz itself
+    SplitScope scope;
+    int rc;
+    if (fused) {
+        const size_t elems[3] = {(size_t)M * K, (size_t)M * N, (size_t)K * N};
+        if ((rc = split_scope_begin(compute, elems, 3)) != CTCASR_OK) return rc;
+        scope.open = true;
+        rc = mask_colsum_split(dy, y, M, N, act, cutoff, drop_rate, seed, np, db, stream);
+        if (rc != CTCASR_OK) return rc;
+        if (fp32_dz && (rc = mask_inplace(dy, y, (size_t)M, N, act, cutoff, drop_rate, seed, stream)) != CTCASR_OK) return rc;
+    } else {
+        rc = mask_inplace(dy, y, (size_t)M, N, act, cutoff, drop_rate, seed, stream);   // dy -> dz
+        if (rc != CTCASR_OK) return rc;
+        rc = colsum(dy, M, N, N, db, stream);
         if (rc != CTCASR_OK) return rc;
     }
-    if (dx) {   // dX[M,K] = dz W^T
-        GemmArgs g;
-        g.A[0] = dy; g.B[0] = w; g.C[0] = dx; g.tb = 1; g.M = M; g.N = K; g.K = N; g.lda = N; g.ldb = N; g.ldc = K;
-        rc = gemm(g, compute, stream);
+    rc = gemm(gw, compute, stream);
+    if (rc != CTCASR_OK) return rc;
+    if (dx) {
+        rc = gemm(gx, compute, stream);
         if (rc != CTCASR_OK) return rc;
     }
     return CTCASR_OK;

@@ -299,23 +299,42 @@ extern "C" int ctcasr_conv2d_bwd(const float *x, int x_pitch, const float *w, co
     if (!use_implicit) if (int rcs = gemm_scratch_check(compute, 1, g.Kp, N, (int)rows)) return rcs;
     if (dx) if (int rcs = gemm_scratch_check(compute, 1, (int)rows, g.Kp, N)) return rcs;
     float *col = reinterpret_cast<float *>(ws);
-    int rc = mask_inplace(dy, y, rows, N, act, cutoff, drop_rate, seed, stream);       // dy -> dz
-    if (rc != CTCASR_OK) return rc;
-    rc = colsum(dy, (int)rows, N, N, db, stream);
-    if (rc != CTCASR_OK) return rc;
+    int rc;
+    const bool dgrad_implicit = use_implicit && dx && conv_tc_dgrad_eligible(C, kf, st, sf, x_pitch);
+    // all consumers of dz read its bf16 pieces: mask, bias gradient and pieces in one pass, no fp32 dz (pointwise.cu)
+    GemmArgs dcol_args;         // dcol[rows,Kp] = dz W^T of the patch-matrix input gradient
+    dcol_args.A[0] = dy; dcol_args.B[0] = w; dcol_args.C[0] = col; dcol_args.tb = 1; dcol_args.M = (int)rows; dcol_args.N = g.Kp; dcol_args.K = N;
+    dcol_args.lda = N; dcol_args.ldb = N; dcol_args.ldc = g.Kp;
+    const bool fused_dz = use_implicit && N <= 16384;          // (independent of dx: the bias gradient's summation order must not depend on it)
+    const bool fp32_dz = !fused_dz || (dx && !dgrad_implicit && !gemm_tc_eligible(dcol_args));    // someone reads dz itself
+    if (!fused_dz) {
+        rc = mask_inplace(dy, y, rows, N, act, cutoff, drop_rate, seed, stream);       // dy -> dz
+        if (rc != CTCASR_OK) return rc;
+        rc = colsum(dy, (int)rows, N, N, db, stream);
+        if (rc != CTCASR_OK) return rc;
+    }
     if (use_implicit) {
         // implicit GEMMs (conv_tc.cu): dW = col^T dz with the patches gathered by the TMA unit, and dx = conv_transpose(dz, W)
         // without dcol; dz is split once for both
         const int np = compute == CTCASR_COMPUTE_BF16 ? 1 : 2;
-        const bool dgrad_implicit = dx && conv_tc_dgrad_eligible(C, kf, st, sf, x_pitch);
         const size_t elems[3] = {(size_t)T * B * F * C, rows * (size_t)N, (size_t)g.Kp * N};
         SplitScope scope;
         if ((rc = split_scope_begin(compute, elems, 3)) != CTCASR_OK) return rc;
         scope.open = true;
+        if (fused_dz) {
+            rc = mask_colsum_split(dy, y, (int)rows, N, act, cutoff, drop_rate, seed, np, db, stream);
+            if (rc != CTCASR_OK) return rc;
+            if (fp32_dz && (rc = mask_inplace(dy, y, rows, N, act, cutoff, drop_rate, seed, stream)) != CTCASR_OK) return rc;
+        }
         rc = conv_tc_wgrad(x, x_pitch, dy, N, dw, N, T, B, F, C, kt, kf, st, sf, g.To, g.Fo, g.pt, g.pf, np, stream);
         if (rc != CTCASR_OK) return rc;
         if (dgrad_implicit)
             return conv_tc_dgrad(dy, N, w, N, dx, x_pitch, T, B, F, C, kt, kf, st, sf, g.To, g.Fo, g.pt, g.pf, np, stream);
+        if (dx) {   // patch-matrix input gradient (time stride > 1), still inside the scope: its GEMM reads dz's pieces
+            if ((rc = gemm(dcol_args, compute, stream)) != CTCASR_OK) return rc;
+            return conv::launch_col2im(col, dx, g, stream);
+        }
+        return CTCASR_OK;
     } else {   // dW[Kp,N] = col^T dz   (rows K..Kp of col^T are zero -> the pad rows of dW are zero)
         GemmArgs a;
         a.A[0] = col; a.B[0] = dy; a.C[0] = dw; a.ta = 1; a.M = g.Kp; a.N = N; a.K = (int)rows; a.lda = g.Kp; a.ldb = N; a.ldc = N;

@@ -84,5 +84,8 @@ int conv_tc_dgrad(const float *dz, int ldz, const float *w, int ldw, float *dx, 
 int colsum(const float *x, int M, int N, int ld, float *out, cudaStream_t stream);
 int mask_inplace(float *dy, const float *y, size_t M, int N, int act, float cutoff, float drop_rate,
                  uint32_t seed, cudaStream_t stream);
+// mask + column sums + bf16 pieces of dz in one pass (inside an open split scope; dy itself is left untouched)
+int mask_colsum_split(const float *dy, const float *y, int M, int N, int act, float cutoff, float drop_rate, uint32_t seed,
+                      int np, float *db, cudaStream_t stream);
 
 }  // namespace ctcasr

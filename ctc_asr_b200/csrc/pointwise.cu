@@ -3,6 +3,8 @@
 #include "gemm.cuh"
 #include "rnn.cuh"
 
+#include <cuda_bf16.h>
+
 namespace ctcasr {
 
 // ---- [A,B,C] -> [B,A,C] ---------------------------------------------------------------------
@@ -92,6 +94,85 @@ int mask_inplace(float *dy, const float *y, size_t M, int N, int act, float cuto
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     mask_inplace_kernel<<<blocks, 256, 0, stream>>>(dy, y, total, N, act, cutoff, drop_rate, seed);
     CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
+// ---- dense / conv backward prologue in one pass: dz = dy * act'(y) * dropout mask, its column sums (the bias gradient)
+// and its bf16 pieces for the tcgen05 GEMMs that read dz (dW = x^T dz, dx = dz W^T).  Replaces mask_inplace + colsum + two
+// split_bf16 passes (24 B per element of HBM traffic) by one pass of 8 B in + 2 NP B out; the fp32 dz is not written (only
+// the GEMMs read it, through the pieces).  Column sums: rows cut into slabs (grid.y), every CTA sums its slab for 64
+// columns (8 row phases added in order), the slabs are added in slab order: deterministic.
+template <int NP>
+__global__ void __launch_bounds__(256) mask_colsum_split_kernel(const float *__restrict__ dy, const float *__restrict__ y, int M, int N,
+                                                                int act, float cutoff, float drop_rate, uint32_t seed,
+                                                                __nv_bfloat16 *__restrict__ pieces, float *__restrict__ out,
+                                                                int rows_per_part, int to_partial)
+{
+    __shared__ float red[8][66];
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int n = blockIdx.x * 64 + 2 * lane;
+    const int m0 = blockIdx.y * rows_per_part, m1 = min(M, m0 + rows_per_part);
+    const float inv_keep = drop_rate > 0.f ? 1.f / (1.f - drop_rate) : 1.f;
+    const size_t piece = (size_t)M * N;
+    float a0 = 0.f, a1 = 0.f;
+    if (n < N)
+        for (int m = m0 + r; m < m1; m += 8) {
+            const size_t i = (size_t)m * N + n;
+            const float2 g = *reinterpret_cast<const float2 *>(dy + i);
+            bool p0 = drop_rate > 0.f ? drop_keep(seed, i, drop_rate) : true;
+            bool p1 = drop_rate > 0.f ? drop_keep(seed, i + 1, drop_rate) : true;
+            if (act == 1) {
+                const float2 v = *reinterpret_cast<const float2 *>(y + i);
+                p0 = p0 && v.x > 0.f && v.x < cutoff * inv_keep;
+                p1 = p1 && v.y > 0.f && v.y < cutoff * inv_keep;
+            }
+            float d0 = p0 ? g.x * inv_keep : 0.f, d1 = p1 ? g.y * inv_keep : 0.f;
+            a0 += d0; a1 += d1;
+#pragma unroll
+            for (int pc = 0; pc < NP; ++pc) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
+                d0 -= __bfloat162float(h0); d1 -= __bfloat162float(h1);
+                *reinterpret_cast<uint32_t *>(pieces + pc * piece + i) =
+                    (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            }
+        }
+    red[r][2 * lane] = a0; red[r][2 * lane + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int nn = blockIdx.x * 64 + threadIdx.x;
+        if (nn < N) {
+            float s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s2 += red[i][threadIdx.x];
+            if (to_partial) g_colsum_partial[(size_t)blockIdx.y * N + nn] = s2;
+            else out[nn] = s2;
+        }
+    }
+}
+
+// dz pieces registered in the open split scope under the address of dy (gemm.cuh, split_reserve); db = column sums of dz
+int mask_colsum_split(const float *dy, const float *y, int M, int N, int act, float cutoff, float drop_rate, uint32_t seed,
+                      int np, float *db, cudaStream_t stream)
+{
+    if (N % 8 || N > kColsumMaxN || np < 1 || np > 3) return fail(CTCASR_ERR_UNSUPPORTED, "mask_colsum_split: N = %d, %d pieces", N, np);
+    __nv_bfloat16 *pieces = nullptr;
+    if (int rc = split_reserve(dy, M, N, N, np, &pieces)) return rc;
+    const int nb = ceil_div(N, 64);
+    int parts = ceil_div(4 * 148, nb);
+    if (parts > kColsumMaxParts) parts = kColsumMaxParts;
+    if (parts > M / 64) parts = M / 64;
+    if (parts < 1) parts = 1;
+    const int rpp = ceil_div(M, parts);
+    const int to_partial = parts > 1;
+    ProfScope prof(PROF_SPLIT, stream);
+    if (np == 1) mask_colsum_split_kernel<1><<<dim3(nb, parts), 256, 0, stream>>>(dy, y, M, N, act, cutoff, drop_rate, seed, pieces, db, rpp, to_partial);
+    else if (np == 2) mask_colsum_split_kernel<2><<<dim3(nb, parts), 256, 0, stream>>>(dy, y, M, N, act, cutoff, drop_rate, seed, pieces, db, rpp, to_partial);
+    else mask_colsum_split_kernel<3><<<dim3(nb, parts), 256, 0, stream>>>(dy, y, M, N, act, cutoff, drop_rate, seed, pieces, db, rpp, to_partial);
+    CTCASR_LAUNCH_CHECK();
+    if (to_partial) {
+        colsum_finish_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(db, N, parts);
+        CTCASR_LAUNCH_CHECK();
+    }
     return CTCASR_OK;
 }
 

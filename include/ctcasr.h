@@ -102,7 +102,7 @@ int ctcasr_edit_distance(const int32_t *hyp, int hyp_stride, const int32_t *hyp_
  *   y[M,N] = dropout( act( x[M,K] w[K,N] + bias[N] ) ),  act: 0 linear, 1 min(relu(.), cutoff)
  *   dropout keep-mask = counter hash of (seed, m*N+n); rate 0 disables it.
  * Backward: dy[M,N] -> dx[M,K] (nullable), dw[K,N], db[N] (overwritten).  `y` is the forward
- * output (the activation/dropout mask is recovered from it).  dy is clobbered (becomes dz).
+ * output (the activation/dropout mask is recovered from it).  dy is clobbered (it may become dz).
  * -------------------------------------------------------------------------------------------- */
 int ctcasr_dense_fwd(const float *x, const float *w, const float *bias, float *y,
                      int M, int K, int N, int act, float cutoff, float drop_rate, uint32_t seed,
@@ -171,7 +171,7 @@ int ctcasr_beam_search(const float *logits, int T, int B, int V, int blank, cons
  *                           N >= filters columns (N = the pitch of y; pad entries must be zero)
  *   y  [To, B, Fo, N]       To = ceil(T/st), Fo = ceil(F/sf) (ctcasr_conv2d_out_dims)
  *   act: 0 linear, 1 min(relu, cutoff).
- * Backward: dy [To,B,Fo,N] (clobbered: becomes dz) -> dx [T,B,F,x_pitch] (nullable; pad channels
+ * Backward: dy [To,B,Fo,N] (clobbered: may become dz) -> dx [T,B,F,x_pitch] (nullable; pad channels
  * are written as zeros), dw [Kp,N], db [N] (overwritten).
  * ws: >= ctcasr_conv2d_workspace_bytes() (the patch matrix; rebuilt in the backward pass).
  * -------------------------------------------------------------------------------------------- */
