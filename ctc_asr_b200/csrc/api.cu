@@ -3,6 +3,8 @@
 // library-level bookkeeping (version, last error, launch counter).
 #include "gemm.cuh"
 
+#include <stdlib.h>
+
 #include <utility>
 #include <vector>
 
@@ -90,6 +92,16 @@ extern "C" int ctcasr_gemm(const float *A, const float *B, float *C, int M, int 
     return gemm(g, compute, (cudaStream_t)stream);
 }
 
+// A linear layer narrower than a tcgen05 tile (the 29-class logits layer, asr/model.py:229-232) over many rows: its
+// weight / output-gradient operands are widened to 64 columns in the scratch arena and the products run on the tensor
+// cores in the fp32-level bf16x3 arithmetic (in both bf16 compute modes), instead of three SIMT GEMMs (0.9 ms per step).
+static bool narrow_on_tc(int compute, int M, int K, int N, int act, float drop_rate)
+{
+    static const bool enabled = !(getenv("CTCASR_NARROW_TC") && atoi(getenv("CTCASR_NARROW_TC")) == 0);
+    return enabled && (compute == CTCASR_COMPUTE_BF16X3 || compute == CTCASR_COMPUTE_BF16) && N < 64 && M >= 2048 && M % 8 == 0 &&
+           K >= 64 && K % 8 == 0 && act == 0 && drop_rate == 0.f;
+}
+
 extern "C" int ctcasr_dense_fwd(const float *x, const float *w, const float *bias, float *y,
                                 int M, int K, int N, int act, float cutoff, float drop_rate, uint32_t seed,
                                 int compute, void *stream)
@@ -101,6 +113,22 @@ extern "C" int ctcasr_dense_fwd(const float *x, const float *w, const float *bia
     g.epi.mode = EPI_BIAS_ACT; g.epi.bias = bias; g.epi.act = act; g.epi.cutoff = cutoff;
     g.epi.drop_rate = drop_rate; g.epi.seed = seed;
     g.precise = act != 0;       // pre-activations near the ReLU / clip kinks decide the backward mask
+    if (narrow_on_tc(compute, M, K, N, act, drop_rate)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const size_t elems[3] = {(size_t)M * K, (size_t)K * 64, (size_t)(M + K) * 64};
+        SplitScope scope;
+        if (int rc = split_scope_begin(CTCASR_COMPUTE_BF16X3, elems, 3)) return rc;
+        scope.open = true;
+        float *wp = reinterpret_cast<float *>(scratch_alloc((size_t)K * 64 * 4)), *yp = reinterpret_cast<float *>(scratch_alloc((size_t)M * 64 * 4));
+        if (!wp || !yp) return CTCASR_ERR_WORKSPACE;
+        if (int rc = pad_cols64(w, K, N, wp, st)) return rc;
+        GemmArgs p;
+        p.A[0] = x; p.B[0] = wp; p.C[0] = yp; p.M = M; p.N = 64; p.K = K; p.lda = K; p.ldb = 64; p.ldc = 64;
+        if (gemm_tc_eligible(p)) {
+            if (int rc = gemm_tc(p, CTCASR_COMPUTE_BF16X3, st)) return rc;
+            return compact_cols64(yp, M, N, bias, y, st);
+        }
+    }
     return gemm(g, compute, (cudaStream_t)stream);
 }
 
@@ -114,6 +142,30 @@ extern "C" int ctcasr_dense_bwd(const float *x, const float *w, const float *y, 
     CTCASR_REQUIRE(act == 0 || y, "dense_bwd: activation mask needs the forward output y");
     if (int rcs = gemm_scratch_check(compute, 1, K, N, M)) return rcs;
     if (int rcs = gemm_scratch_check(compute, 1, M, K, N)) return rcs;
+    if (narrow_on_tc(compute, M, K, N, act, drop_rate)) {      // see ctcasr_dense_fwd
+        const size_t elems[4] = {(size_t)M * K, (size_t)M * 64, (size_t)K * 64, (size_t)(M + 2 * K) * 64};
+        SplitScope scope;
+        if (int rcs = split_scope_begin(CTCASR_COMPUTE_BF16X3, elems, 4)) return rcs;
+        scope.open = true;
+        float *zp = reinterpret_cast<float *>(scratch_alloc((size_t)M * 64 * 4)), *wp = reinterpret_cast<float *>(scratch_alloc((size_t)K * 64 * 4));
+        float *dwp = reinterpret_cast<float *>(scratch_alloc((size_t)K * 64 * 4));
+        if (!zp || !wp || !dwp) return CTCASR_ERR_WORKSPACE;
+        GemmArgs pw, px;
+        pw.A[0] = x; pw.B[0] = zp; pw.C[0] = dwp; pw.ta = 1; pw.M = K; pw.N = 64; pw.K = M; pw.lda = K; pw.ldb = 64; pw.ldc = 64;
+        px.A[0] = zp; px.B[0] = wp; px.C[0] = dx; px.tb = 1; px.M = M; px.N = K; px.K = 64; px.lda = 64; px.ldb = 64; px.ldc = K;
+        if (gemm_tc_eligible(pw) && (!dx || gemm_tc_eligible(px))) {
+            int rc = colsum(dy, M, N, N, db, stream);
+            if (rc != CTCASR_OK) return rc;
+            if ((rc = pad_cols64(dy, M, N, zp, stream)) != CTCASR_OK) return rc;
+            if ((rc = gemm_tc(pw, CTCASR_COMPUTE_BF16X3, stream)) != CTCASR_OK) return rc;
+            if ((rc = compact_cols64(dwp, K, N, nullptr, dw, stream)) != CTCASR_OK) return rc;
+            if (dx) {
+                if ((rc = pad_cols64(w, K, N, wp, stream)) != CTCASR_OK) return rc;
+                if ((rc = gemm_tc(px, CTCASR_COMPUTE_BF16X3, stream)) != CTCASR_OK) return rc;
+            }
+            return CTCASR_OK;
+        }
+    }
     GemmArgs gw, gx;    // dW[K,N] = X^T dz;  dX[M,K] = dz W^T
     gw.A[0] = x; gw.B[0] = dy; gw.C[0] = dw; gw.ta = 1; gw.M = K; gw.N = N; gw.K = M; gw.lda = K; gw.ldb = N; gw.ldc = N;
     gx.A[0] = dy; gx.B[0] = w; gx.C[0] = dx; gx.tb = 1; gx.M = M; gx.N = K; gx.K = N; gx.lda = N; gx.ldb = N; gx.ldc = K;

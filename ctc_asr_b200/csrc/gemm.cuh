@@ -61,6 +61,9 @@ struct SplitScope {
     bool open = false;
     ~SplitScope() { if (open) split_scope_end(); }
 };
+// Inside an open scope: `bytes` of the arena for the caller's own temporaries (released with the scope); nullptr and
+// CTCASR_ERR_WORKSPACE in ctcasr_last_error() when they do not fit.
+void *scratch_alloc(size_t bytes);
 // Free space of the caller's scratch arena behind the cached splits (not reserved: valid until the next
 // GEMM call on the stream), or nullptr when `bytes` do not fit.
 void *scratch_free(size_t bytes);
@@ -84,6 +87,9 @@ int conv_tc_dgrad(const float *dz, int ldz, const float *w, int ldw, float *dx, 
 int colsum(const float *x, int M, int N, int ld, float *out, cudaStream_t stream);
 int mask_inplace(float *dy, const float *y, size_t M, int N, int act, float cutoff, float drop_rate,
                  uint32_t seed, cudaStream_t stream);
+// dst [rows, 64] = src [rows, n] with zero columns n .. 63;  dst [rows, n] = src [rows, 64] (+ bias[n])
+int pad_cols64(const float *src, int rows, int n, float *dst, cudaStream_t stream);
+int compact_cols64(const float *src, int rows, int n, const float *bias, float *dst, cudaStream_t stream);
 // mask + column sums + bf16 pieces of dz in one pass (inside an open split scope; dy itself is left untouched)
 int mask_colsum_split(const float *dy, const float *y, int M, int N, int act, float cutoff, float drop_rate, uint32_t seed,
                       int np, float *db, cudaStream_t stream);

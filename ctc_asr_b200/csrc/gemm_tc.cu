@@ -863,6 +863,21 @@ int split_reserve(const float *key, int rows, int cols, int ld, int np, __nv_bfl
     return CTCASR_OK;
 }
 
+void *scratch_alloc(size_t bytes)
+{
+    tc::Context &c = tc::ctx();
+    bytes = align_up(bytes, 1024);
+    if (!c.scope) { fail(CTCASR_ERR_INVALID, "scratch_alloc: needs an open split scope"); return nullptr; }
+    if (!c.scratch || c.cursor + bytes > c.scratch_bytes) {
+        c.scratch_needed = c.cursor + bytes;
+        fail(CTCASR_ERR_WORKSPACE, "split-operand scratch %zu B < %zu B needed (ctcasr_set_scratch)", c.scratch_bytes, c.scratch_needed);
+        return nullptr;
+    }
+    void *p = c.scratch + c.cursor;
+    c.cursor += bytes;
+    return p;
+}
+
 void *scratch_free(size_t bytes)
 {
     const size_t used = tc::ctx().scope ? tc::ctx().cursor : 0;

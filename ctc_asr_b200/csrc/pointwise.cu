@@ -176,6 +176,37 @@ int mask_colsum_split(const float *dy, const float *y, int M, int N, int act, fl
     return CTCASR_OK;
 }
 
+// ---- the 29-class layer on the tensor cores: its operands widened to 64 columns (zeros), its results narrowed back ----
+__global__ void pad_cols64_kernel(const float *__restrict__ src, size_t rows, int n, float *__restrict__ dst)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * 64; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 63);
+        dst[i] = c < n ? src[(i >> 6) * n + c] : 0.f;
+    }
+}
+__global__ void compact_cols64_kernel(const float *__restrict__ src, size_t rows, int n, const float *__restrict__ bias, float *__restrict__ dst)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / n;
+        const int c = (int)(i - r * n);
+        dst[i] = src[r * 64 + c] + (bias ? bias[c] : 0.f);
+    }
+}
+int pad_cols64(const float *src, int rows, int n, float *dst, cudaStream_t stream)
+{
+    const size_t blocks = ((size_t)rows * 64 + 255) / 256;
+    pad_cols64_kernel<<<(int)(blocks < (size_t)148 * 8 ? blocks : (size_t)148 * 8), 256, 0, stream>>>(src, (size_t)rows, n, dst);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+int compact_cols64(const float *src, int rows, int n, const float *bias, float *dst, cudaStream_t stream)
+{
+    const size_t blocks = ((size_t)rows * n + 255) / 256;
+    compact_cols64_kernel<<<(int)(blocks < (size_t)148 * 8 ? blocks : (size_t)148 * 8), 256, 0, stream>>>(src, (size_t)rows, n, bias, dst);
+    CTCASR_LAUNCH_CHECK();
+    return CTCASR_OK;
+}
+
 // ---- y = dropout(x): the keep-mask of the dense epilogue over the flat index (RNN input / output / inter-layer dropout) ----
 __global__ void dropout_kernel(const float *__restrict__ x, float *__restrict__ y, size_t total, float drop_rate, uint32_t seed)
 {

@@ -73,3 +73,26 @@ def test_pair_and_single_cta_kernels_agree_on_shared_columns():
         torch.cuda.synchronize()
         print("compute %d: pair vs single-CTA kernel bit-identical: %s" % (cid, torch.equal(wide[:, :256], narrow)))
         assert rel_err(wide[:, :256].cpu().numpy(), narrow.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("compute", ["bf16x3", "bf16"])
+def test_narrow_linear_layer_on_the_tensor_cores(compute):
+    """The 29-class logits layer over many rows (asr/model.py:229-232): operands widened to 64 columns, three tcgen05
+    products in the fp32-level bf16x3 arithmetic in BOTH bf16 compute modes (the oracle of compute='bf16' keeps this layer
+    exact), results narrowed back: forward, weight, bias and input gradients against fp64 numpy."""
+    rng = np.random.default_rng(41)
+    M, K, N = 4096, 256, 29
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((K, N)) * 0.1).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    dy = rng.standard_normal((M, N)).astype(np.float32)
+    cid = _lib.COMPUTE_ID[compute]
+    y = ops.dense_fwd(dev(x), dev(w), dev(b), act=0, compute=cid)
+    dw, db, dx = torch.full((K, N), float("nan")).cuda(), torch.empty(N).cuda(), torch.full((M, K), float("nan")).cuda()
+    ops.dense_bwd(dev(x), dev(w), y, dev(dy), dw, db, dx=dx, act=0, compute=cid)
+    torch.cuda.synchronize()
+    x64, w64, dy64 = x.astype(np.float64), w.astype(np.float64), dy.astype(np.float64)
+    assert rel_err(y.cpu().numpy(), x64 @ w64 + b) < 3e-5
+    assert rel_err(dw.cpu().numpy(), x64.T @ dy64) < 3e-5
+    assert rel_err(dx.cpu().numpy(), dy64 @ w64.T) < 3e-5
+    assert rel_err(db.cpu().numpy(), dy64.sum(0)) < 1e-5
