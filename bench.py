@@ -366,7 +366,7 @@ def run_train(ctx):
                               "every step, all CTAs) against the L2 read peak measured with tools/ubench/l2_peak.cu"},
         "dram": {"achieved_gbs": traffic / (ms_launch * 1e-3) / 1e9 if (traffic and ms_launch) else None, "peak_gbs": peaks["hbm_gbs"],
                  "frac": traffic / (ms_launch * 1e-3) / 1e9 / peaks["hbm_gbs"] if (traffic and ms_launch) else None,
-                 "note": "ncu dram__bytes_read + write per launch captured at this commit (profiles/r2_rec_dram_traffic.json)"},
+                 "note": "ncu dram__bytes_read + write per launch from the round-2 capture of these kernels, unchanged since (profiles/r2_rec_dram_traffic.json)"},
         "note": "achieved = algorithmic recurrent FLOPs (2 directions x 2 B H GH per time step) / CUDA-event time; peak = %s bf16 sustained. "
                 "At B = 32 the recurrence is a T-step chain of skinny products: the tensor fraction is low by construction, the step "
                 "period (us_per_time_step) against its latency chain is what DESIGN.md section 4 analyses" % peaks["source"]}
