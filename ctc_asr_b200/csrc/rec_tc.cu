@@ -10,7 +10,7 @@
 // Both passes are the same contraction  D[128 units, 32 batch] = W'[units, K = H] . x^T  with W' = Wh^T (forward)
 // or Wh (backward), x = h_{t-1} or dz_t.  A cluster of 4 CTAs owns 128 units of one direction; CTA q contracts
 // the K-quarter [q H/4, (q+1) H/4): its weight slice [128 x H/4] in two bf16 pieces is 256 KB at H = 2048 and
-// stays ON CHIP for the whole sequence — the first 7 k-blocks in tensor memory (read by the MMA as a TMEM A
+// stays ON CHIP for the whole sequence — the first 6 k-blocks in tensor memory (read by the MMA as a TMEM A
 // operand), the rest in shared memory — so a time step moves only the K-quarter of h / dz (64 KB per CTA)
 // through TMA.  The four partial [128 x 32] accumulators are exchanged through distributed shared memory (warp w
 // ships its 32 unit rows to CTA w), CTA w adds them and runs the cell math for its 32 units x 32 batch rows,
@@ -25,11 +25,11 @@ namespace rnn1 {
 using rec::BK;
 constexpr int NB = 32;                  // batch rows per launch (MMA N; hi and lo pieces stacked: N = 64)
 constexpr int UPC = 32;                 // units whose cells one CTA owns
-constexpr int NTHREADS = 384;           // warps 0-3 TMEM readers + cells, 4 TMA producer, 6 MMA issuer, 8-11 cells
+constexpr int NTHREADS = 384;           // warps 0-3 TMEM readers + cells, 4 TMA producer, 6-7 MMA issuers, 8-11 cells
 constexpr int A_PIECE = 128 * BK * 2;   // 16 KB: one bf16 piece of a [128 x 64] weight k-block
 constexpr int B_TILE = 2 * NB * BK * 2; // 8 KB: both pieces of a [32 x 64] state k-block
-constexpr int TMEM_KB = 7;              // weight k-blocks resident in tensor memory (7 x 64 columns + 64 accumulator columns)
-constexpr int MAX_KB = 10;              // k-blocks per CTA (H/4/64): the rest (<= 3) stays in shared memory
+constexpr int TMEM_KB = 6;              // weight k-blocks resident in tensor memory (6 x 64 columns + 2 x 64 accumulator columns)
+constexpr int MAX_KB = 10;              // k-blocks per CTA (H/4/64): the rest (<= 4) stays in shared memory
 constexpr int XCH = 4 * NB * UPC * 4;   // exchange slots [4 sources][32 b][32 u] fp32
 
 struct Params {
@@ -90,8 +90,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int g = 0; g < (NKB + 3) / 4; ++g) ptx::mbar_init(fullB(g), 1);
-        ptx::mbar_init(wres, 1); ptx::mbar_init(bfree, 1);
-        ptx::mbar_init(tfull, 1); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
+        ptx::mbar_init(wres, 1); ptx::mbar_init(bfree, 2);           // bfree / tfull: one commit per MMA issuer
+        ptx::mbar_init(tfull, 2); ptx::mbar_init(tempty, 4); ptx::mbar_init(xfull, 4);
         ptx::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) { ptx::tma_prefetch_desc(&mapW); ptx::tma_prefetch_desc(&mapX); }
@@ -101,7 +101,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     ptx::cluster_sync_all();            // every CTA's barriers exist before anyone arrives remotely
     ptx::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot_ptr;
-    const uint32_t tmem_w = tmem_d + 64;        // resident weights: k-block kb, piece pc at column 64 + (kb*2+pc)*32
+    const uint32_t tmem_w = tmem_d + 128;       // resident weights: k-block kb, piece pc at column 128 + (kb*2+pc)*32
     if (warp < 4) {
         // my unit row's weights for the first k-blocks of the K-quarter: 32 columns (= 64 bf16) per k-block and piece
         const int row = d * H + ub * 128 + warp * 32 + lane;
@@ -145,18 +145,25 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                 stamp(p, n, 1);
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 6 || warp == 7) {
+        // two MMA issuers (even / odd k-blocks, own accumulators): every MMA of this kernel is a small one whose cost is its
+        // ~45-cycle issue, not its math (tools/ubench/mma_loop.cu), and two threads issue in parallel
         if (lane == 0) {
+            const int me = warp - 6;
+            const uint32_t acc = tmem_d + (uint32_t)(me * 64);
             const uint32_t idesc32 = ptx::make_idesc_bf16(128, NB, 0, 0), idesc64 = ptx::make_idesc_bf16(128, 2 * NB, 0, 0);
             if (NSW > 0) ptx::mbar_wait(wres, 0);
             for (int n = 0; n < T; ++n) {
                 ptx::mbar_wait(tempty, (uint32_t)((n & 1) ^ 1));
                 ptx::tc_fence_after();
-                for (int kb = 0; kb < NKB; ++kb) {
-                    if ((kb & 3) == 0) {
-                        ptx::mbar_wait(fullB(kb >> 2), (uint32_t)(n & 1));
+                int group = -1;
+                for (int kb = me; kb < NKB; kb += 2) {
+                    if ((kb >> 2) != group) {
+                        group = kb >> 2;
+                        ptx::mbar_wait(fullB(group), (uint32_t)(n & 1));
                         ptx::tc_fence_after();
                     }
+                    const bool first = kb == me;
                     // bf16x3 with 2 MMAs per k-step: the two pieces of x are consecutive rows of one K-major tile, so
                     // A_hi x [x_hi; x_lo] is ONE N = 64 MMA (columns 0-31: hi*hi, 32-63: hi*lo) and A_lo x x_hi
                     // accumulates into columns 0-31; the epilogue adds the column groups.
@@ -165,22 +172,22 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                         const uint32_t ta_hi = tmem_w + (uint32_t)((kb * 2 + 0) * 32), ta_lo = ta_hi + 32;
 #pragma unroll
                         for (int j = 0; j < BK / 16; ++j) {
-                            ptx::mma_bf16_ts(tmem_d, ta_hi + 8 * j, bd + (uint64_t)(2 * j), idesc64, !(kb == 0 && j == 0));
-                            ptx::mma_bf16_ts(tmem_d, ta_lo + 8 * j, bd + (uint64_t)(2 * j), idesc32, 1);
+                            ptx::mma_bf16_ts(acc, ta_hi + 8 * j, bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                            ptx::mma_bf16_ts(acc, ta_lo + 8 * j, bd + (uint64_t)(2 * j), idesc32, 1);
                         }
                     } else {
                         const uint32_t wa = w_base + (uint32_t)(kb - TMEM_KB) * 2 * A_PIECE;
                         const uint64_t ad_hi = ptx::make_smem_desc(wa, 16, 1024, 2), ad_lo = ptx::make_smem_desc(wa + A_PIECE, 16, 1024, 2);
 #pragma unroll
                         for (int j = 0; j < BK / 16; ++j) {
-                            ptx::mma_bf16(tmem_d, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, 1);
-                            ptx::mma_bf16(tmem_d, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
+                            ptx::mma_bf16(acc, ad_hi + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc64, !(first && j == 0));
+                            ptx::mma_bf16(acc, ad_lo + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc32, 1);
                         }
                     }
                 }
                 ptx::mma_commit(bfree);
                 ptx::mma_commit(tfull);
-                stamp(p, n, 2);
+                if (me == 0) stamp(p, n, 2);
             }
         }
     } else if (warp < 4 || warp >= 8) {
@@ -219,13 +226,23 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                 if (tid == 0) stamp(p, n, 3);
                 ptx::tc_fence_after();
                 uint32_t r[32], r2[32];
+                float acc[NB];
                 ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), r);      // rows = units 32*warp + lane of the block
                 ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, r2);
                 ptx::tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < NB; ++b) acc[b] = __uint_as_float(r[b]) + __uint_as_float(r2[b]);
+                if (NKB > 1) {                                                  // the odd k-blocks: the second issuer's accumulator
+                    ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 64, r);
+                    ptx::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 96, r2);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) acc[b] += __uint_as_float(r[b]) + __uint_as_float(r2[b]);
+                }
                 ptx::tc_fence_before();
 #pragma unroll
                 for (int b = 0; b < NB; ++b)
-                    ptx::st_cluster_f32(remote_slot + (uint32_t)(b * UPC + lane) * 4u, __uint_as_float(r[b]) + __uint_as_float(r2[b]));
+                    ptx::st_cluster_f32(remote_slot + (uint32_t)(b * UPC + lane) * 4u, acc[b]);
                 __syncwarp();
                 if (lane == 0) { ptx::mbar_arrive(tempty); ptx::mbar_arrive_remote(remote_bar); }
             }
