@@ -1,5 +1,6 @@
-// conv_tc.cu — implicit-GEMM forward pass of a 'ds2' conv layer on tcgen05 (sm_100a): tf.layers.conv2d(SAME) + relu +
-// tf.minimum + tf.layers.dropout (asr/util/tf_contrib.py:123-135) WITHOUT a patch matrix.
+// conv_tc.cu — the 'ds2' conv layers as implicit GEMMs on tcgen05 (sm_100a): tf.layers.conv2d(SAME) + relu + tf.minimum +
+// tf.layers.dropout (asr/util/tf_contrib.py:123-135), forward pass, weight gradient and input gradient, WITHOUT a patch
+// matrix (three kernels: conv_fwd_kernel here at the top, conv_wgrad_kernel and conv_dgrad_kernel further down).
 //
 // conv.cu writes every output position's kt x kf x C patch to HBM (14.2 GB of bf16 pieces for the second layer at
 // B = 32 x 10 s) and multiplies that matrix by the kernel.  Here the A operand of the same GEMM is gathered by the TMA
@@ -11,8 +12,9 @@
 // neither the input nor the patches are ever copied; the input pieces (181 MB for that layer) stay in L2.  The B operand
 // is the kernel [Kp, N] in its HWIO row order (row = (it*kf + jf)*C + c = k-block * 32 + c), split as in gemm_tc.cu.
 // Arithmetic, pipeline and epilogue are those of gemm_tc_kernel: NP = 3 pieces / 6 products (bf16x3 through the ReLU
-// kink) or NP = 1 (compute = 'bf16'), fp32 accumulation in tensor memory, TMA producer warp / one MMA-issuing thread /
-// four epilogue warps, two accumulators; the epilogue maps a tile row back to its output position (to, b, fo).
+// kink), NP = 2 / 3 products (the gradients) or NP = 1 (compute = 'bf16'), fp32 accumulation in tensor memory, TMA
+// producer warp / one MMA-issuing thread / four epilogue warps, two accumulators; the epilogue maps a tile row back to
+// its output position (to, b, fo).
 #include "gemm.cuh"
 #include "ptx.cuh"
 

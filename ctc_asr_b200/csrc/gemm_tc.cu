@@ -1,4 +1,5 @@
-// gemm_tc.cu — tcgen05 / TMA / TMEM GEMM for sm_100a (CTCASR_COMPUTE_TF32, CTCASR_COMPUTE_BF16X3).
+// gemm_tc.cu — tcgen05 / TMA / TMEM GEMM for sm_100a (CTCASR_COMPUTE_TF32, CTCASR_COMPUTE_BF16X3, CTCASR_COMPUTE_BF16):
+// the single-CTA kernel gemm_tc_kernel and its CTA-pair (cta_group::2) variant gemm_tc_pair_kernel.
 //
 // C[M,N] = op(A) op(B), fp32 in HBM, fp32 accumulation in tensor memory.  Used for every GEMM-shaped
 // piece of the path: the dense layers (asr/util/tf_contrib.py:52-58, asr/model.py:220-232), the
