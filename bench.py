@@ -150,7 +150,7 @@ def workload_config(args, cfg, world):
             "global_batch": B * world,
             "params": int(sum(int(np.prod(s)) for _, s, _ in param_specs(cfg))),
             "arithmetic": {"bf16x3": "fp32 storage; GEMMs and recurrence as 3 (6 for ReLU-kinked layers) bf16 tcgen05 products "
-                                     "of split operands, fp32 TMEM accumulation (fp32-level accuracy)",
+                                     "of split operands, fp32 TMEM accumulation in chains of <= 8192 (1e-5 .. 3e-5 of fp64)",
                            "tf32": "fp32 storage; tcgen05 kind::tf32 GEMMs, bf16x3 recurrence", "fp32": "SIMT FFMA",
                            "bf16": "BASELINE cfg3 arithmetic: GEMM and recurrence operands rounded to bf16, one tcgen05 product, fp32 "
                                    "accumulation, fp32 master weights, state and CTC"}[args.compute],

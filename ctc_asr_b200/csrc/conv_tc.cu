@@ -259,6 +259,7 @@ struct WParams {
     int kf, cchunks, nunits;            // nunits = kt*kf*cchunks 32-row units
     int st, sf, pt, pf;
     int nbx, mtiles, splits, groups_per_split;
+    int groups_per_chunk;               // chained accumulation (gemm_tc.cu): position groups per accumulator
     float *out;                         // dW [K, ldo] (splits == 1) or the partial tiles [splits][K][ldo]
     int ldo;
 };
@@ -343,26 +344,29 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             for (int u = blockIdx.x; u < nwork; u += gridDim.x) {
                 const int slice = u / p.mtiles;
                 const int g0 = slice * p.groups_per_split, g1 = min(p.ngroups, g0 + p.groups_per_split);
-                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-                for (int g = g0; g < g1; ++g) {
-                    ptx::mbar_wait(full_bar(stage), phase);
+                for (int c0 = g0; c0 < g1; c0 += p.groups_per_chunk) {     // one accumulator per chunk of the chain
+                    const int c1 = min(g1, c0 + p.groups_per_chunk);
+                    ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                     ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+                    for (int g = c0; g < c1; ++g) {
+                        ptx::mbar_wait(full_bar(stage), phase);
+                        ptx::tc_fence_after();
 #pragma unroll
-                    for (int q = 0; q < C_::NPROD; ++q) {
-                        // A: MN-major, SWIZZLE_64B: 32-element atoms WG_A_BOX apart along M, 8-position groups 512 B apart
-                        const uint64_t adesc = ptx::make_smem_desc(a_addr(stage, PA[q]), WG_A_BOX, 512, 4);
-                        const uint64_t bdesc = ptx::make_smem_desc(b_addr(stage, PB[q]), B_BOX, 1024, 2);
+                        for (int q = 0; q < C_::NPROD; ++q) {
+                            // A: MN-major, SWIZZLE_64B: 32-element atoms WG_A_BOX apart along M, 8-position groups 512 B apart
+                            const uint64_t adesc = ptx::make_smem_desc(a_addr(stage, PA[q]), WG_A_BOX, 512, 4);
+                            const uint64_t bdesc = ptx::make_smem_desc(b_addr(stage, PB[q]), B_BOX, 1024, 2);
 #pragma unroll
-                        for (int j = 0; j < WG_BKP / 16; ++j)       // 16 positions per MMA: 16 rows of 64 B (A) / 128 B (B)
-                            ptx::mma_bf16(tmem_d, adesc + (uint64_t)(64 * j), bdesc + (uint64_t)(128 * j), idesc, ((g - g0) | q | j) != 0);
+                            for (int j = 0; j < WG_BKP / 16; ++j)       // 16 positions per MMA: 16 rows of 64 B (A) / 128 B (B)
+                                ptx::mma_bf16(tmem_d, adesc + (uint64_t)(64 * j), bdesc + (uint64_t)(128 * j), idesc, ((g - c0) | q | j) != 0);
+                        }
+                        ptx::mma_commit(empty_bar(stage));
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
-                    ptx::mma_commit(empty_bar(stage));
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    ptx::mma_commit(tfull_bar(acc));
+                    if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                 }
-                ptx::mma_commit(tfull_bar(acc));
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -371,6 +375,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         for (int u = blockIdx.x; u < nwork; u += gridDim.x) {
             const int slice = u / p.mtiles, mt = u - slice * p.mtiles;
             float *out = p.out + (size_t)slice * p.K * p.ldo;
+            const int g0 = slice * p.groups_per_split, g1 = min(p.ngroups, g0 + p.groups_per_split);
+            // chunks of the chain: the first stores, the others add to what this thread stored (fp32, round to nearest)
+            for (int c0 = g0; c0 < g1; c0 += p.groups_per_chunk) {
+            const bool first = c0 == g0;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * ACC_COLS;
@@ -389,11 +397,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 __syncwarp();
                 const int n = c * 32 + sub_n;
                 if (n < p.N) {
+                    float4 old[8];                  // (all loads in flight before the first store, as in gemm_tc.cu)
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int m = m0 + itr * 4 + sub_r;
+                        old[itr] = (!first && m < p.K) ? *reinterpret_cast<const float4 *>(out + (size_t)m * p.ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
 #pragma unroll
                     for (int itr = 0; itr < 8; ++itr) {
                         const int rr = itr * 4 + sub_r, m = m0 + rr;
-                        if (m < p.K)
-                            *reinterpret_cast<float4 *>(out + (size_t)m * p.ldo + n) = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
+                        if (m < p.K) {
+                            const float4 v = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
+                            *reinterpret_cast<float4 *>(out + (size_t)m * p.ldo + n) =
+                                make_float4(v.x + old[itr].x, v.y + old[itr].y, v.z + old[itr].z, v.w + old[itr].w);
+                        }
                     }
                 }
                 __syncwarp();
@@ -402,6 +419,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
             if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
         }
     }
     __syncwarp();
@@ -745,6 +763,7 @@ int conv_tc_wgrad(const float *x, int x_pitch, const float *dz, int ldz, float *
         if (part) { p.splits = S; p.groups_per_split = per; }
     }
     if (!part) { p.splits = 1; p.groups_per_split = p.ngroups; }
+    p.groups_per_chunk = np >= 2 ? chain_chunk_kblocks(p.groups_per_split, WG_BKP) : p.groups_per_split;   // (bf16x3 arithmetic only)
     p.out = part ? part : dw;
 
     CUtensorMap mx, mz;

@@ -67,6 +67,9 @@ void *scratch_alloc(size_t bytes);
 // Free space of the caller's scratch arena behind the cached splits (not reserved: valid until the next
 // GEMM call on the stream), or nullptr when `bytes` do not fit.
 void *scratch_free(size_t bytes);
+// Chained accumulation (gemm_tc.cu): k-blocks (of bk contraction elements) per chunk for a chain of `kblocks` — the whole
+// chain up to 12288 elements, equal chunks of <= 8192 beyond (CTCASR_GEMM_CHAIN = elements per chunk, 0 = never chunk)
+int chain_chunk_kblocks(int kblocks, int bk);
 // dispatch on `compute`: TF32 -> tcgen05 when eligible, otherwise the SIMT kernel
 int gemm(const GemmArgs &g, int compute, cudaStream_t stream);
 

@@ -86,6 +86,11 @@ struct Params {
     // k-blocks [s * kb_per_split, ...) and stores its raw partial tile to part[s][z][M][N]
     int splits, kb_per_split;
     float *part;
+    // chained accumulation: the k-blocks of a unit are summed in chunks of kb_per_chunk, one tensor-memory accumulator per
+    // chunk, and the epilogue adds the chunks in fp32 (round to nearest) into the output it wrote for the first one.  The
+    // tensor core truncates every accumulation (measured bias -2.4e-8 of the accumulator per MMA, profiles/
+    // r2_accum_error.json): the error of ONE chain grows linearly with its length (1.2e-4 at K = 32,000), the chunks bound it
+    int kb_per_chunk;
 };
 
 __device__ __forceinline__ void decode_tile(const Params &p, int t, int &z, int &mb, int &nb)
@@ -119,17 +124,32 @@ enum { EK_RAW = 0, EK_ACC = 1, EK_BIAS_ACT = 2, EK_MASK = 3 };
 template <int EK>
 __device__ __forceinline__ void store_rows(const Params &p, const float *stg, float *base, int ld, int m0, int n, int sub_r, int sub_n)
 {
+    if (EK == EK_ACC) {
+        // all eight loads of the old values in flight before the first store: with the load inside the store loop they
+        // serialise behind each other (the compiler cannot reorder them across stores that may alias), eight L2 / HBM round
+        // trips per 32-column block — longer than the MMAs of a chunk of a chained accumulation
+        float4 old[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < 8; ++it) {
+            const int m = m0 + it * 4 + sub_r;
+            old[it] = m < p.M ? *reinterpret_cast<const float4 *>(base + (size_t)m * ld + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub_r, m = m0 + rr;
+            if (m >= p.M) break;
+            const float4 v = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
+            *reinterpret_cast<float4 *>(base + (size_t)m * ld + n) = make_float4(v.x + old[it].x, v.y + old[it].y, v.z + old[it].z, v.w + old[it].w);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < (EK == EK_ACC ? 0 : 8); ++it) {
         const int rr = it * 4 + sub_r, m = m0 + rr;
         if (m >= p.M) break;
         const float4 v = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
         float *cp = base + (size_t)m * ld + n;
         float4 o = v;
-        if (EK == EK_ACC) {
-            const float4 old = *reinterpret_cast<const float4 *>(cp);
-            o = make_float4(v.x + old.x, v.y + old.y, v.z + old.z, v.w + old.w);
-        } else if (EK == EK_BIAS_ACT) {
+        if (EK == EK_BIAS_ACT) {
             o.x = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.x, m, n + 0, p.N, 0.f);
             o.y = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.y, m, n + 1, p.N, 0.f);
             o.z = epilogue_apply_m<EPI_BIAS_ACT>(p.epi, v.z, m, n + 2, p.N, 0.f);
@@ -241,28 +261,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t idesc = C_::kBf16 ? ptx::make_idesc_bf16(BM, n_eff, p.ta ? 1 : 0, p.tb ? 0 : 1)
                                                  : ptx::make_idesc_tf32(BM, n_eff, p.ta ? 1 : 0, p.tb ? 0 : 1);
                 const int kb0 = slice * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(full_bar(stage), phase);
+                for (int c0 = kb0; c0 < kb1; c0 += p.kb_per_chunk) {        // one accumulator per chunk of the chain
+                    const int c1 = min(kb1, c0 + p.kb_per_chunk);
+                    ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                     ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * BN;
+                    for (int kb = c0; kb < c1; ++kb) {
+                        ptx::mbar_wait(full_bar(stage), phase);
+                        ptx::tc_fence_after();
 #pragma unroll
-                    for (int q = 0; q < C_::NPROD; ++q) {
-                        const uint64_t adesc = operand_desc<MODE>(a_addr(stage, PA[q]), p.ta != 0);
-                        const uint64_t bdesc = operand_desc<MODE>(b_addr(stage, PB[q]), p.tb == 0);
+                        for (int q = 0; q < C_::NPROD; ++q) {
+                            const uint64_t adesc = operand_desc<MODE>(a_addr(stage, PA[q]), p.ta != 0);
+                            const uint64_t bdesc = operand_desc<MODE>(b_addr(stage, PB[q]), p.tb == 0);
 #pragma unroll
-                        for (int j = 0; j < C_::KSTEPS; ++j) {
-                            const uint32_t accum = ((kb - kb0) | q | j) != 0;
-                            if (C_::kBf16) ptx::mma_bf16(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc, accum);
-                            else           ptx::mma_tf32(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc, accum);
+                            for (int j = 0; j < C_::KSTEPS; ++j) {
+                                const uint32_t accum = ((kb - c0) | q | j) != 0;
+                                if (C_::kBf16) ptx::mma_bf16(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc, accum);
+                                else           ptx::mma_tf32(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc, accum);
+                            }
                         }
+                        ptx::mma_commit(empty_bar(stage));          // stage reusable once these MMAs retire
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
-                    ptx::mma_commit(empty_bar(stage));          // stage reusable once these MMAs retire
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    ptx::mma_commit(tfull_bar(acc));                // accumulator complete
+                    if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                 }
-                ptx::mma_commit(tfull_bar(acc));                // accumulator complete
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -273,6 +296,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int slice = u / p.num_tiles;
             decode_tile(p, u - slice * p.num_tiles, z, mb, nb);
             float *C = p.C[z];
+            const int kb0 = slice * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+            // chunks of a chained accumulation: the first one stores, the others add to what THIS thread stored (same
+            // rows and columns every time: program order is all the ordering the read-modify-write needs)
+            for (int c0 = kb0; c0 < kb1; c0 += p.kb_per_chunk) {
+            const bool first = c0 == kb0;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const int m0 = mb * BM + warp * 32;
@@ -297,11 +325,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (n < p.N) {                // N % 8 == 0 (eligibility), so a float4 is all-in or all-out
                     // one straight-line variant per epilogue kind (a single epilogue warp per scheduler has
                     // nobody to hide its latency behind: instruction count is what the K = 64 GEMMs pay for)
-                    if (p.splits > 1)   // raw partial sums; splitk_reduce adds the slices and applies the epilogue
-                        store_rows<EK_RAW>(p, stg, p.part + ((size_t)slice * p.nz + z) * p.M * p.N, p.N, m0, n, sub_r, sub_n);
-                    else if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    if (p.splits > 1) { // raw partial sums; splitk_reduce adds the slices and applies the epilogue
+                        float *part = p.part + ((size_t)slice * p.nz + z) * p.M * p.N;
+                        if (first) store_rows<EK_RAW>(p, stg, part, p.N, m0, n, sub_r, sub_n);
+                        else store_rows<EK_ACC>(p, stg, part, p.N, m0, n, sub_r, sub_n);
+                    }
+                    else if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);   // (never chunked)
                     else if (p.epi.mode == EPI_MASK) store_rows<EK_MASK>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
-                    else if (p.epi.accumulate) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    else if (p.epi.accumulate || !first) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
                     else store_rows<EK_RAW>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
                 }
                 __syncwarp();
@@ -310,6 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));   // 4 arrivals free the accumulator
             if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
         }
     }
     __syncwarp();
@@ -432,26 +464,29 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int u = pair; u < p.num_tiles; u += npairs) {
-                ptx::mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);     // epilogue warps of both CTAs
-                ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    ptx::mbar_wait(full_bar(stage), phase);
+                for (int c0 = 0; c0 < p.kblocks; c0 += p.kb_per_chunk) {   // one accumulator per chunk of the chain
+                    const int c1 = min(p.kblocks, c0 + p.kb_per_chunk);
+                    ptx::mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);     // epilogue warps of both CTAs
                     ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * BN;
+                    for (int kb = c0; kb < c1; ++kb) {
+                        ptx::mbar_wait(full_bar(stage), phase);
+                        ptx::tc_fence_after();
 #pragma unroll
-                    for (int q = 0; q < C_::NPROD; ++q) {
-                        const uint64_t adesc = operand_desc<MODE>(a_addr(stage, PA[q]), p.ta != 0);
-                        const uint64_t bdesc = operand_desc<MODE>(b_addr(stage, PB[q]), p.tb == 0);
+                        for (int q = 0; q < C_::NPROD; ++q) {
+                            const uint64_t adesc = operand_desc<MODE>(a_addr(stage, PA[q]), p.ta != 0);
+                            const uint64_t bdesc = operand_desc<MODE>(b_addr(stage, PB[q]), p.tb == 0);
 #pragma unroll
-                        for (int j = 0; j < C_::KSTEPS; ++j)
-                            ptx::mma_bf16_pair(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc,
-                                               (kb | q | j) != 0);
+                            for (int j = 0; j < C_::KSTEPS; ++j)
+                                ptx::mma_bf16_pair(tmem_d, adesc + (uint64_t)(a_step * j), bdesc + (uint64_t)(b_step * j), idesc,
+                                                   ((kb - c0) | q | j) != 0);
+                        }
+                        ptx::mma_commit_pair(empty_bar(stage));         // frees the stage in both CTAs
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
-                    ptx::mma_commit_pair(empty_bar(stage));         // frees the stage in both CTAs
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    ptx::mma_commit_pair(tfull_bar(acc));
+                    if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                 }
-                ptx::mma_commit_pair(tfull_bar(acc));
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -462,6 +497,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             int z, mb, nb;
             decode_tile(p, u, z, mb, nb);
             float *C = p.C[z];
+            for (int c0 = 0; c0 < p.kblocks; c0 += p.kb_per_chunk) {       // chunks of a chained accumulation, as in gemm_tc_kernel
+            const bool first = c0 == 0;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const int m0 = mb * 2 * BM + (int)rank * BM + warp * 32;
@@ -481,7 +518,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 const int n = nb * BN + c * 32 + sub_n;
                 if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
                 else if (p.epi.mode == EPI_MASK) store_rows<EK_MASK>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
-                else if (p.epi.accumulate) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                else if (p.epi.accumulate || !first) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
                 else store_rows<EK_RAW>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
                 __syncwarp();
             }
@@ -489,6 +526,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_remote(tempty_leader + 8u * acc);      // (the leader's own window for rank 0)
             if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
         }
     }
     __syncwarp();
@@ -650,6 +688,21 @@ static int acquire_split(const float *x, int rows, int cols, int ld, cudaStream_
     return CTCASR_OK;
 }
 
+// k-blocks per chunk of a chained accumulation (Params::kb_per_chunk) for a unit of `kblocks` k-blocks of `bk` elements:
+// chains up to 12288 elements stay whole (every forward product of the path: K <= 4096), longer ones (the weight gradients:
+// K = frames of the batch; input gradients through 8H = 16384 gate columns) are cut into equal chunks of <= 8192: error
+// <= 3e-5 whatever K, +0.3 % on a K = 32,000 weight-gradient GEMM (chunks of 4096: 1.6e-5, +2.7 %).  Not for the
+// bias + activation and mask epilogues of an unsplit GEMM, which are applied once to the complete sum (split-K slices
+// store raw partial sums whatever the epilogue).
+template <int MODE>
+static int chunk_kblocks(const Epilogue &epi, int splits, int kblocks, int bk)
+{
+    // one product per operand pair (bf16, tf32): the operand rounding (2e-3 / 3e-4) is far above the accumulator's error
+    if (MODE != MODE_BF16X3 && MODE != MODE_BF16X6) return kblocks;
+    if (splits == 1 && epi.mode != EPI_STORE) return kblocks;
+    return chain_chunk_kblocks(kblocks, bk);
+}
+
 template <int MODE>
 static int launch_pair(const CUtensorMap *maps, Params p, int num_sms, cudaStream_t stream)
 {
@@ -664,6 +717,7 @@ static int launch_pair(const CUtensorMap *maps, Params p, int num_sms, cudaStrea
     p.tiles_m = ceil_div(p.M, 2 * BM);                          // tiles of the pair: 256 rows
     p.num_tiles = p.tiles_m * p.tiles_n * p.nz;
     p.splits = 1; p.kb_per_split = p.kblocks; p.part = nullptr;
+    p.kb_per_chunk = chunk_kblocks<MODE>(p.epi, 1, p.kblocks, C2::BK);
     const int pairs = p.num_tiles < num_sms / 2 ? p.num_tiles : num_sms / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C2::SMEM_BYTES; cfg.stream = stream;
@@ -766,6 +820,7 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
             }
         }
     }
+    p.kb_per_chunk = chunk_kblocks<MODE>(p.epi, p.splits, p.kb_per_split, C_::BK);
     const int units = p.num_tiles * p.splits;
     const int grid = units < num_sms ? units : num_sms;
     {
@@ -778,6 +833,16 @@ static int launch(const GemmArgs &g, cudaStream_t stream)
 }
 
 }  // namespace tc
+
+int chain_chunk_kblocks(int kblocks, int bk)
+{
+    static const int chain = getenv("CTCASR_GEMM_CHAIN") ? atoi(getenv("CTCASR_GEMM_CHAIN")) : 8192;
+    if (chain <= 0) return kblocks;
+    const int target = chain / bk > 0 ? chain / bk : 1;
+    if (kblocks <= target + target / 2) return kblocks;
+    const int n = ceil_div(kblocks, target);
+    return ceil_div(kblocks, n);
+}
 
 bool gemm_tc_eligible(const GemmArgs &g)
 {

@@ -44,9 +44,9 @@ enum {
     CTCASR_COMPUTE_FP32 = 0,      /* SIMT FFMA, fp32 everywhere (parity mode, any shape) */
     CTCASR_COMPUTE_TF32 = 1,      /* tcgen05 kind::tf32, fp32 storage + fp32 accumulate in TMEM */
     CTCASR_COMPUTE_BF16X3 = 2,    /* tcgen05 kind::f16 on bf16-split operands (a = a1 + a2 [+ a3]),
-                                     3 or 6 products accumulated in fp32 TMEM: fp32-level accuracy */
-    CTCASR_COMPUTE_BF16 = 3       /* GEMMs: operands rounded to bf16, one tcgen05 kind::f16 product, fp32 accumulate
-                                     (fp32 master weights, fp32 CTC; the LSTM recurrence keeps the bf16x3 kernel) */
+                                     3 or 6 products accumulated in fp32 TMEM (chains of <= 8192, gemm_tc.cu): 1e-5 .. 3e-5 of fp64 */
+    CTCASR_COMPUTE_BF16 = 3       /* GEMMs and recurrence: operands rounded to bf16, one tcgen05 kind::f16 product, fp32
+                                     accumulate (fp32 master weights, state and CTC; the 29-class logits layer stays bf16x3) */
 };
 
 /* per-utterance CTC status words (TF raises InvalidArgumentError for 1..3) */

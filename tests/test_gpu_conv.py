@@ -126,6 +126,21 @@ def test_ds2_whole_path_with_conv_and_rnn_dropout():
     _whole_path(cfg, B=4, T=61, L=6, ragged=True, training=True)
 
 
+@pytest.mark.parametrize("compute", ["bf16x3"])
+def test_ds2_whole_path_through_the_implicit_conv_kernels(compute):
+    """32 filters in the first two layers, as in the reference: the second and third conv layer take the implicit-GEMM
+    forward / weight-gradient / input-gradient kernels (conv_tc.cu) and the fused backward prologue, with conv, RNN and dense
+    dropout on; every gradient tensor against the fp64 oracle.
+    Data seed 23: no conv pre-activation lies within 1.7e-5 (relative to the layer's largest output) of a ReLU kink.  With
+    seed 0 one first-layer pre-activation is 8e-8 away from 0, the two sides clip it differently and that single flipped
+    mask element moves the first layer's kernel gradient by 1 % (tools/r2_diag_conv.py shows it stage by stage; the
+    32-filter first layer has 4x the elements of the (8, 8, 64) tests)."""
+    cfg = ModelConfig(used_model="ds2", conv_filters=(32, 32, 64), num_units_dense=64, num_layers_rnn=1, num_units_rnn=64,
+                      rnn_cell="lstm", num_features=20, cudnn=True, dense_dropout_rate=0.1, conv_dropout_rate=0.1,
+                      rnn_dropout_rate=0.0, compute=compute, random_seed=5)
+    _whole_path(cfg, B=4, T=61, L=6, ragged=True, training=True, seed=23)
+
+
 def test_ds2_model_shapes_follow_the_reference():
     cfg = ModelConfig(used_model="ds2", num_layers_rnn=1, num_units_rnn=64, num_units_dense=64, compute="fp32")
     plan = conv_plan(cfg, 999)

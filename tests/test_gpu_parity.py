@@ -637,6 +637,24 @@ def test_cfg2_full_size_shards_add_up(cfg2_model):
         assert torch.equal(ids_full[b, :n_full[b]], ids_half[b, :n_half[b]])
 
 
+@pytest.mark.parametrize("compute,tol", [("bf16x3", 6e-5)])
+def test_weight_gradient_contraction_at_cfg2_length(compute, tol):
+    """Full-size accuracy of the longest contraction of the path: a weight gradient dW = x^T dz sums over every frame of
+    the batch (K = T x B = 32,000 at cfg2; 256 output tiles: no split over K).  The tensor core truncates each accumulation
+    into tensor memory, so ONE chain of K / 16 x 3 MMAs is off by 1.2e-4 at this length (linear in K; profiles/
+    r2_accum_error.json, tools/accum_probe.py); the GEMM sums chunks of <= 8192 in separate accumulators and adds them in
+    fp32 (gemm_tc.cu, chained accumulation): 3e-5 whatever K.  Against fp64 on the same device."""
+    torch.manual_seed(11)
+    K, M, N = 32000, 2048, 4096
+    a = torch.randn(K, M, device="cuda")
+    b = torch.randn(K, N, device="cuda")
+    c = ops.gemm(a, b, ta=True, compute=_lib.COMPUTE_ID[compute])
+    want = a.double().t() @ b.double()
+    err = float((c.double() - want).abs().max() / want.abs().max())
+    print("dW contraction K = %d (%s): max err / max = %.2e" % (K, compute, err))
+    assert err < tol, err
+
+
 def test_edit_distance_bit_exact():
     """tf.edit_distance(decoded, labels) (asr/model.py:338): integer work, bit-exact vs the oracle,
     up to the corpus' longest label (422, README.md:169)."""
