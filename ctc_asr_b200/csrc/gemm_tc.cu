@@ -691,7 +691,8 @@ static int acquire_split(const float *x, int rows, int cols, int ld, cudaStream_
 // k-blocks per chunk of a chained accumulation (Params::kb_per_chunk) for a unit of `kblocks` k-blocks of `bk` elements:
 // chains up to 12288 elements stay whole (every forward product of the path: K <= 4096), longer ones (the weight gradients:
 // K = frames of the batch; input gradients through 8H = 16384 gate columns) are cut into equal chunks of <= 8192: error
-// <= 3e-5 whatever K, +0.3 % on a K = 32,000 weight-gradient GEMM (chunks of 4096: 1.6e-5, +2.7 %).  Not for the
+// <= 3e-5 whatever K, +0.3 % on a lone K = 32,000 weight-gradient GEMM and ~1 % of the cfg2 step (profiles/r2_chain_ab.json;
+// chunks of 4096: 1.6e-5, +2.7 % on that GEMM).  Not for the
 // bias + activation and mask epilogues of an unsplit GEMM, which are applied once to the complete sum (split-K slices
 // store raw partial sums whatever the epilogue).
 template <int MODE>
