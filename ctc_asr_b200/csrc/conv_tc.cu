@@ -378,47 +378,47 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             const int g0 = slice * p.groups_per_split, g1 = min(p.ngroups, g0 + p.groups_per_split);
             // chunks of the chain: the first stores, the others add to what this thread stored (fp32, round to nearest)
             for (int c0 = g0; c0 < g1; c0 += p.groups_per_chunk) {
-            const bool first = c0 == g0;
-            ptx::mbar_wait(tfull_bar(acc), acc_phase);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * ACC_COLS;
-            const int m0 = mt * BM + warp * 32;
-            const int nchunks = (p.N + 31) / 32;
+                const bool first = c0 == g0;
+                ptx::mbar_wait(tfull_bar(acc), acc_phase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * ACC_COLS;
+                const int m0 = mt * BM + warp * 32;
+                const int nchunks = (p.N + 31) / 32;
 #pragma unroll 1
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld32(taddr + c * 32, r);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
-                        make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
-                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                __syncwarp();
-                const int n = c * 32 + sub_n;
-                if (n < p.N) {
-                    float4 old[8];                  // (all loads in flight before the first store, as in gemm_tc.cu)
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
+                            make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    __syncwarp();
+                    const int n = c * 32 + sub_n;
+                    if (n < p.N) {
+                        float4 old[8];                  // (all loads in flight before the first store, as in gemm_tc.cu)
 #pragma unroll
-                    for (int itr = 0; itr < 8; ++itr) {
-                        const int m = m0 + itr * 4 + sub_r;
-                        old[itr] = (!first && m < p.K) ? *reinterpret_cast<const float4 *>(out + (size_t)m * p.ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const int m = m0 + itr * 4 + sub_r;
+                            old[itr] = (!first && m < p.K) ? *reinterpret_cast<const float4 *>(out + (size_t)m * p.ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
 #pragma unroll
-                    for (int itr = 0; itr < 8; ++itr) {
-                        const int rr = itr * 4 + sub_r, m = m0 + rr;
-                        if (m < p.K) {
-                            const float4 v = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
-                            *reinterpret_cast<float4 *>(out + (size_t)m * p.ldo + n) =
-                                make_float4(v.x + old[itr].x, v.y + old[itr].y, v.z + old[itr].z, v.w + old[itr].w);
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const int rr = itr * 4 + sub_r, m = m0 + rr;
+                            if (m < p.K) {
+                                const float4 v = *reinterpret_cast<const float4 *>(stg + rr * STG_LD + sub_n);
+                                *reinterpret_cast<float4 *>(out + (size_t)m * p.ldo + n) =
+                                    make_float4(v.x + old[itr].x, v.y + old[itr].y, v.z + old[itr].z, v.w + old[itr].w);
+                            }
                         }
                     }
+                    __syncwarp();
                 }
+                ptx::tc_fence_before();
                 __syncwarp();
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
-            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     }

@@ -300,47 +300,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // chunks of a chained accumulation: the first one stores, the others add to what THIS thread stored (same
             // rows and columns every time: program order is all the ordering the read-modify-write needs)
             for (int c0 = kb0; c0 < kb1; c0 += p.kb_per_chunk) {
-            const bool first = c0 == kb0;
-            ptx::mbar_wait(tfull_bar(acc), acc_phase);
-            ptx::tc_fence_after();
-            const int m0 = mb * BM + warp * 32;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
-            const int nchunks = min(BN / 32, (p.N - nb * BN + 31) / 32);      // the columns the MMAs wrote
-            // tcgen05.ld hands lane l the 32 columns of ROW l; storing that straight out would touch 32
-            // different rows per instruction.  The 32 x 32 block is turned through a padded shared-memory
-            // tile so that every store (and mask / accumulate load) instruction covers four whole 128-B rows.
-            const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
+                const bool first = c0 == kb0;
+                ptx::mbar_wait(tfull_bar(acc), acc_phase);
+                ptx::tc_fence_after();
+                const int m0 = mb * BM + warp * 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
+                const int nchunks = min(BN / 32, (p.N - nb * BN + 31) / 32);      // the columns the MMAs wrote
+                // tcgen05.ld hands lane l the 32 columns of ROW l; storing that straight out would touch 32
+                // different rows per instruction.  The 32 x 32 block is turned through a padded shared-memory
+                // tile so that every store (and mask / accumulate load) instruction covers four whole 128-B rows.
+                const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
 #pragma unroll 1
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld32(taddr + c * 32, r);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
-                        make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
-                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                __syncwarp();
-                const int n = nb * BN + c * 32 + sub_n;
-                if (n < p.N) {                // N % 8 == 0 (eligibility), so a float4 is all-in or all-out
-                    // one straight-line variant per epilogue kind (a single epilogue warp per scheduler has
-                    // nobody to hide its latency behind: instruction count is what the K = 64 GEMMs pay for)
-                    if (p.splits > 1) { // raw partial sums; splitk_reduce adds the slices and applies the epilogue
-                        float *part = p.part + ((size_t)slice * p.nz + z) * p.M * p.N;
-                        if (first) store_rows<EK_RAW>(p, stg, part, p.N, m0, n, sub_r, sub_n);
-                        else store_rows<EK_ACC>(p, stg, part, p.N, m0, n, sub_r, sub_n);
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
+                            make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    __syncwarp();
+                    const int n = nb * BN + c * 32 + sub_n;
+                    if (n < p.N) {                // N % 8 == 0 (eligibility), so a float4 is all-in or all-out
+                        // one straight-line variant per epilogue kind (a single epilogue warp per scheduler has
+                        // nobody to hide its latency behind: instruction count is what the K = 64 GEMMs pay for)
+                        if (p.splits > 1) { // raw partial sums; splitk_reduce adds the slices and applies the epilogue
+                            float *part = p.part + ((size_t)slice * p.nz + z) * p.M * p.N;
+                            if (first) store_rows<EK_RAW>(p, stg, part, p.N, m0, n, sub_r, sub_n);
+                            else store_rows<EK_ACC>(p, stg, part, p.N, m0, n, sub_r, sub_n);
+                        }
+                        else if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);   // (never chunked)
+                        else if (p.epi.mode == EPI_MASK) store_rows<EK_MASK>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                        else if (p.epi.accumulate || !first) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                        else store_rows<EK_RAW>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
                     }
-                    else if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);   // (never chunked)
-                    else if (p.epi.mode == EPI_MASK) store_rows<EK_MASK>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
-                    else if (p.epi.accumulate || !first) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
-                    else store_rows<EK_RAW>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    __syncwarp();
                 }
+                ptx::tc_fence_before();
                 __syncwarp();
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));   // 4 arrivals free the accumulator
-            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));   // 4 arrivals free the accumulator
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     }
@@ -498,34 +498,34 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             decode_tile(p, u, z, mb, nb);
             float *C = p.C[z];
             for (int c0 = 0; c0 < p.kblocks; c0 += p.kb_per_chunk) {       // chunks of a chained accumulation, as in gemm_tc_kernel
-            const bool first = c0 == 0;
-            ptx::mbar_wait(tfull_bar(acc), acc_phase);
-            ptx::tc_fence_after();
-            const int m0 = mb * 2 * BM + (int)rank * BM + warp * 32;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
-            const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
+                const bool first = c0 == 0;
+                ptx::mbar_wait(tfull_bar(acc), acc_phase);
+                ptx::tc_fence_after();
+                const int m0 = mb * 2 * BM + (int)rank * BM + warp * 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
+                const int sub_n = 4 * (lane & 7), sub_r = lane >> 3;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld32(taddr + c * 32, r);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
-                        make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
-                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * q) =
+                            make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    __syncwarp();
+                    const int n = nb * BN + c * 32 + sub_n;
+                    if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    else if (p.epi.mode == EPI_MASK) store_rows<EK_MASK>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    else if (p.epi.accumulate || !first) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    else store_rows<EK_RAW>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
+                    __syncwarp();
+                }
+                ptx::tc_fence_before();
                 __syncwarp();
-                const int n = nb * BN + c * 32 + sub_n;
-                if (p.epi.mode == EPI_BIAS_ACT) store_rows<EK_BIAS_ACT>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
-                else if (p.epi.mode == EPI_MASK) store_rows<EK_MASK>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
-                else if (p.epi.accumulate || !first) store_rows<EK_ACC>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
-                else store_rows<EK_RAW>(p, stg, C, p.ldc, m0, n, sub_r, sub_n);
-                __syncwarp();
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_remote(tempty_leader + 8u * acc);      // (the leader's own window for rank 0)
-            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                if (lane == 0) ptx::mbar_arrive_remote(tempty_leader + 8u * acc);      // (the leader's own window for rank 0)
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     }
